@@ -1,0 +1,114 @@
+"""ctypes binding of libbrk_b200.so (the C ABI declared in include/brk_b200.h).
+
+PyTorch is only the plumbing here: it owns device memory and streams; every compute call goes
+through the C ABI with raw device pointers.  There is no CPU fallback: if the library is missing,
+or no sm_100 device is present, the calls raise.
+"""
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbrk_b200.so")
+
+
+class BrkError(RuntimeError):
+    pass
+
+
+class brk_table(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+                ("touched", C.c_void_p), ("rows", C.c_int64), ("d", C.c_int32), ("_pad", C.c_int32)]
+
+
+class brk_adam_hyper(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
+
+
+_P, _I32, _I64, _U32, _F32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float
+
+# name -> (restype, argtypes); mirrors include/brk_b200.h one to one.
+SIGNATURES = {
+    "brk_abi_version": (C.c_int, []),
+    "brk_last_error": (C.c_char_p, []),
+    "brk_create": (C.c_int, [C.POINTER(_P), C.c_int]),
+    "brk_destroy": (C.c_int, [_P]),
+    "brk_sm_count": (C.c_int, [_P]),
+    "brk_gather_rows": (C.c_int, [_P, _P, _I64, _I32, _P, _I64, _P, _P]),
+    "brk_scatter_add_rows": (C.c_int, [_P, _P, _I64, _I32, _P, _I64, _P, _P, _I32, _P]),
+    "brk_philox_bpr_negatives": (C.c_int, [_P, _P, _I64, _I64, _U32, _U32, _I32, _P, _P, _P, _P]),
+    "brk_philox_neumf_negatives": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _U32, _U32, _P, _P, _P]),
+    "brk_philox4x32_10": (C.c_int, [_P, _P, _I64, _U32, _U32, _P, _P]),
+    "brk_bpr_fwd_bwd": (C.c_int, [_P, C.POINTER(brk_table), C.POINTER(brk_table), _P, _P, _P, _I64, _P, _P]),
+    "brk_bpr_scores": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _I64, _P, _P]),
+    "brk_adam_dense_keras": (C.c_int, [_P, C.POINTER(brk_table), _I32, brk_adam_hyper, _P, _I32, _P]),
+    "brk_adam_rows": (C.c_int, [_P, C.POINTER(brk_table), _I32, brk_adam_hyper, _P, _I32, _P]),
+    "brk_adagrad_rows": (C.c_int, [_P, C.POINTER(brk_table), _I32, _F32, _F32, _P]),
+    "brk_adagrad_dense": (C.c_int, [_P, C.POINTER(brk_table), _I32, _F32, _F32, _P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_ctx = {}
+
+
+def lib():
+    """Loads the shared library (no GPU needed for this step)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise BrkError(
+                        f"{LIB_PATH} is missing: build it with binary-recommendation_b200/csrc/build.sh "
+                        "(or __graft_entry__.build()); there is no CPU fallback")
+                l = C.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(l, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().brk_last_error().decode(errors="replace")
+        raise BrkError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ctx(device=None):
+    """Per-device library context (created on first use)."""
+    if not torch.cuda.is_available():
+        raise BrkError("no CUDA device: the brk_b200 hot path is sm_100a CUDA only (no CPU fallback)")
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if dev is None:
+        dev = torch.cuda.current_device()
+    h = _ctx.get(dev)
+    if h is None:
+        with _lock:
+            h = _ctx.get(dev)
+            if h is None:
+                torch.cuda.init()
+                out = _P()
+                check(lib().brk_create(C.byref(out), dev), "brk_create")
+                h = out
+                _ctx[dev] = h
+    return h
+
+
+def stream_ptr():
+    return _P(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (or None)."""
+    if t is None:
+        return _P(0)
+    if not t.is_cuda:
+        raise BrkError("expected a CUDA tensor")
+    if not t.is_contiguous():
+        raise BrkError("expected a contiguous tensor")
+    return _P(t.data_ptr())

@@ -1,0 +1,205 @@
+// Fused BPR triplet forward + backward (K1+K4+K5 in one pass; no activations ever reach HBM).
+// Reference graph: /root/reference/src/models/BPRModel.py:49-74, loss :124-144 (1 - sigmoid).
+// Per triplet: 3 rows gathered (3*4d B) and 3 row gradients reduced into the dense accumulators
+// (3*4d B of RED traffic) => 1536 B of algorithmic traffic at d = 64.
+// Mapping: a group of LPR lanes owns a triplet, each lane holds NCH float4 chunks of u, p and n in
+// registers; the dot product is a group shuffle-reduction; gradients leave as 16-byte vector REDs.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void mark_touched(uint32_t* touched, int64_t row) {
+  if (touched == nullptr) return;
+  const uint32_t bit = 1u << (row & 31);
+  uint32_t* wptr = touched + (row >> 5);
+  if (!(*reinterpret_cast<volatile uint32_t*>(wptr) & bit)) atomicOr(wptr, bit);
+}
+
+// Adds this block's partial loss; the last block to arrive publishes the mean and resets the slot.
+__device__ __forceinline__ void finish_loss(double part, double inv_batch, double* acc, unsigned int* ticket,
+                                            float* loss_out) {
+  __shared__ double red[32];
+  const double tot = block_sum_double(part, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(acc, tot);
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1) {
+      __threadfence();
+      const double sum = atomicAdd(acc, 0.0);
+      if (loss_out) loss_out[0] = float(sum * inv_batch);
+      *acc = 0.0;
+      *ticket = 0u;
+      __threadfence();
+    }
+  }
+}
+
+template <int LPR, int NCH, bool TRAIN>
+__global__ void __launch_bounds__(kThreads)
+bpr_vec(const float* __restrict__ Wu, const float* __restrict__ Wi, float* __restrict__ Gu,
+        float* __restrict__ Gi, uint32_t* __restrict__ Tu, uint32_t* __restrict__ Ti, int d4,
+        const int32_t* __restrict__ uid, const int32_t* __restrict__ pid, const int32_t* __restrict__ nid,
+        int64_t batch, float inv_batch, double* loss_acc, unsigned int* ticket, float* __restrict__ out) {
+  constexpr int GPW = 32 / LPR;  // groups (triplets) per warp
+  const int lane_in = threadIdx.x & (LPR - 1);
+  const int64_t group = (int64_t(blockIdx.x) * kThreads + threadIdx.x) / LPR;
+  const int64_t n_groups = int64_t(gridDim.x) * kThreads / LPR;
+  const int64_t warp_first = group - ((threadIdx.x & 31) / LPR);  // first triplet of this warp
+  const float4* __restrict__ Wu4 = reinterpret_cast<const float4*>(Wu);
+  const float4* __restrict__ Wi4 = reinterpret_cast<const float4*>(Wi);
+  float loss_local = 0.f;
+
+  for (int64_t wb = warp_first; wb < batch; wb += n_groups) {
+    const int64_t b = wb + (threadIdx.x & 31) / LPR;
+    const bool valid = b < batch;
+    int64_t ru = 0, rp = 0, rn = 0;
+    if (valid) { ru = __ldg(uid + b); rp = __ldg(pid + b); rn = __ldg(nid + b); }
+    float4 u[NCH], p[NCH], n[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = lane_in + k * LPR;
+      if (valid && c < d4) {
+        u[k] = __ldg(Wu4 + ru * d4 + c);
+        p[k] = __ldg(Wi4 + rp * d4 + c);
+        n[k] = __ldg(Wi4 + rn * d4 + c);
+      } else {
+        u[k] = p[k] = n[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      // difference first, then the product: mirrors x = <u,p> - <u,n> up to fp32 reassociation
+      dot = fmaf(u[k].x, p[k].x - n[k].x, dot);
+      dot = fmaf(u[k].y, p[k].y - n[k].y, dot);
+      dot = fmaf(u[k].z, p[k].z - n[k].z, dot);
+      dot = fmaf(u[k].w, p[k].w - n[k].w, dot);
+    }
+    const float x = group_sum<LPR>(dot);
+    if constexpr (!TRAIN) {
+      if (valid && lane_in == 0) out[b] = x;
+    } else {
+      const float s = sigmoidf_acc(x);
+      if (valid && lane_in == 0) loss_local += 1.0f - s;
+      const float g = -s * (1.0f - s) * inv_batch;
+      if (valid) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const int c = lane_in + k * LPR;
+          if (c < d4) {
+            const float4 du = make_float4(g * (p[k].x - n[k].x), g * (p[k].y - n[k].y),
+                                          g * (p[k].z - n[k].z), g * (p[k].w - n[k].w));
+            const float4 dp = make_float4(g * u[k].x, g * u[k].y, g * u[k].z, g * u[k].w);
+            const float4 dn = make_float4(-dp.x, -dp.y, -dp.z, -dp.w);
+            red_add_f4(Gu + (ru * d4 + c) * 4, du);
+            red_add_f4(Gi + (rp * d4 + c) * 4, dp);
+            red_add_f4(Gi + (rn * d4 + c) * 4, dn);
+          }
+        }
+        if (lane_in == 0) { mark_touched(Tu, ru); mark_touched(Ti, rp); mark_touched(Ti, rn); }
+      }
+    }
+  }
+  (void)GPW;
+  if constexpr (TRAIN) finish_loss(double(loss_local), double(inv_batch), loss_acc, ticket, out);
+}
+
+// Generic width (d % 4 != 0 or unaligned): one warp per triplet, rows re-read for the backward.
+template <bool TRAIN>
+__global__ void __launch_bounds__(kThreads)
+bpr_scalar(const float* __restrict__ Wu, const float* __restrict__ Wi, float* __restrict__ Gu,
+           float* __restrict__ Gi, uint32_t* __restrict__ Tu, uint32_t* __restrict__ Ti, int d,
+           const int32_t* __restrict__ uid, const int32_t* __restrict__ pid, const int32_t* __restrict__ nid,
+           int64_t batch, float inv_batch, double* loss_acc, unsigned int* ticket, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+  const int64_t n_warps = int64_t(gridDim.x) * kThreads >> 5;
+  float loss_local = 0.f;
+  for (int64_t b = warp; b < batch; b += n_warps) {
+    const int64_t ru = __ldg(uid + b), rp = __ldg(pid + b), rn = __ldg(nid + b);
+    float dot = 0.f;
+    for (int c = lane; c < d; c += 32)
+      dot = fmaf(__ldg(Wu + ru * d + c), __ldg(Wi + rp * d + c) - __ldg(Wi + rn * d + c), dot);
+    const float x = warp_sum(dot);
+    if constexpr (!TRAIN) {
+      if (lane == 0) out[b] = x;
+    } else {
+      const float s = sigmoidf_acc(x);
+      if (lane == 0) loss_local += 1.0f - s;
+      const float g = -s * (1.0f - s) * inv_batch;
+      for (int c = lane; c < d; c += 32) {
+        const float uu = __ldg(Wu + ru * d + c), pp = __ldg(Wi + rp * d + c), nn = __ldg(Wi + rn * d + c);
+        atomicAdd(Gu + ru * d + c, g * (pp - nn));
+        atomicAdd(Gi + rp * d + c, g * uu);
+        atomicAdd(Gi + rn * d + c, -g * uu);
+      }
+      if (lane == 0) { mark_touched(Tu, ru); mark_touched(Ti, rp); mark_touched(Ti, rn); }
+    }
+  }
+  if constexpr (TRAIN) finish_loss(double(loss_local), double(inv_batch), loss_acc, ticket, out);
+}
+
+template <bool TRAIN>
+int launch_bpr(brk_ctx* ctx, const float* Wu, const float* Wi, float* Gu, float* Gi, uint32_t* Tu, uint32_t* Ti,
+               int d, const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch, float* out,
+               cudaStream_t st) {
+  const float inv_batch = 1.0f / float(batch);
+  double* acc = ctx->loss_acc + 0;
+  unsigned int* ticket = ctx->tickets + 0;
+  const int64_t cap = int64_t(ctx->sm_count) * (2048 / kThreads);
+  const bool vec = (d & 3) == 0 && d <= 512 && brk_aligned16(Wu) && brk_aligned16(Wi) &&
+                   (!TRAIN || (brk_aligned16(Gu) && brk_aligned16(Gi)));
+  if (vec) {
+    const int d4 = d >> 2;
+    const int lpr = brk_lanes_per_row(d4);
+    const int nch = (d4 + lpr - 1) / lpr;
+    int64_t need = (batch * lpr + kThreads - 1) / kThreads;
+    const int grid = int(need < 1 ? 1 : (need < cap ? need : cap));
+#define BRK_BPR_CASE(L, N)                                                                          \
+  bpr_vec<L, N, TRAIN><<<grid, kThreads, 0, st>>>(Wu, Wi, Gu, Gi, Tu, Ti, d4, u, p, n, batch, inv_batch, \
+                                                  acc, ticket, out)
+    if (lpr == 1) BRK_BPR_CASE(1, 1);
+    else if (lpr == 2) BRK_BPR_CASE(2, 1);
+    else if (lpr == 4) BRK_BPR_CASE(4, 1);
+    else if (lpr == 8) BRK_BPR_CASE(8, 1);
+    else if (lpr == 16) BRK_BPR_CASE(16, 1);
+    else if (nch == 1) BRK_BPR_CASE(32, 1);
+    else if (nch == 2) BRK_BPR_CASE(32, 2);
+    else if (nch == 3) BRK_BPR_CASE(32, 3);
+    else BRK_BPR_CASE(32, 4);
+#undef BRK_BPR_CASE
+  } else {
+    int64_t need = (batch * 32 + kThreads - 1) / kThreads;
+    const int grid = int(need < 1 ? 1 : (need < cap ? need : cap));
+    bpr_scalar<TRAIN><<<grid, kThreads, 0, st>>>(Wu, Wi, Gu, Gi, Tu, Ti, d, u, p, n, batch, inv_batch, acc,
+                                                 ticket, out);
+  }
+  BRK_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int brk_bpr_fwd_bwd(brk_ctx* ctx, const brk_table* user, const brk_table* item,
+                               const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch,
+                               float* loss_out, void* stream) {
+  BRK_REQUIRE(ctx && user && item && u && p && n, BRK_E_ARG, "brk_bpr_fwd_bwd: null argument");
+  BRK_REQUIRE(user->w && user->g && item->w && item->g, BRK_E_ARG, "brk_bpr_fwd_bwd: table w/g missing");
+  BRK_REQUIRE(user->d == item->d && user->d > 0, BRK_E_ARG, "brk_bpr_fwd_bwd: user d=%d item d=%d", user->d,
+              item->d);
+  BRK_REQUIRE(batch > 0, BRK_E_ARG, "brk_bpr_fwd_bwd: batch=%lld", (long long)batch);
+  return launch_bpr<true>(ctx, user->w, item->w, user->g, item->g, user->touched, item->touched, user->d, u, p,
+                          n, batch, loss_out, (cudaStream_t)stream);
+}
+
+extern "C" int brk_bpr_scores(brk_ctx* ctx, const float* user_w, const float* item_w, int32_t d,
+                              const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch,
+                              float* x_out, void* stream) {
+  BRK_REQUIRE(ctx && user_w && item_w && u && p && n && x_out, BRK_E_ARG, "brk_bpr_scores: null argument");
+  BRK_REQUIRE(d > 0 && batch > 0, BRK_E_ARG, "brk_bpr_scores: d=%d batch=%lld", d, (long long)batch);
+  return launch_bpr<false>(ctx, user_w, item_w, nullptr, nullptr, nullptr, nullptr, d, u, p, n, batch, x_out,
+                           (cudaStream_t)stream);
+}

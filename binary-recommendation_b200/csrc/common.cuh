@@ -1,0 +1,127 @@
+// Shared device/host helpers for libbrk_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/brk_b200.h"
+
+struct brk_ctx {
+  int device;
+  int sm_count;
+  double*       loss_acc;     // [BRK_LOSS_SLOTS] double accumulators, zero between calls
+  unsigned int* tickets;      // [BRK_TICKETS] last-block tickets, zero between calls
+  void*         scratch;      // sort / misc scratch
+  size_t        scratch_bytes;
+};
+
+#define BRK_LOSS_SLOTS 16
+#define BRK_TICKETS 16
+
+void brk_set_error(const char* fmt, ...);
+
+#define BRK_REQUIRE(cond, code, ...)            \
+  do {                                          \
+    if (!(cond)) {                              \
+      brk_set_error(__VA_ARGS__);               \
+      return (code);                            \
+    }                                           \
+  } while (0)
+
+#define BRK_CUDA(expr)                                                            \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess) {                                                      \
+      brk_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),       \
+                    __FILE__, __LINE__);                                          \
+      return (int)_e;                                                             \
+    }                                                                             \
+  } while (0)
+
+#define BRK_LAUNCH_CHECK()                                                        \
+  do {                                                                            \
+    cudaError_t _e = cudaGetLastError();                                          \
+    if (_e != cudaSuccess) {                                                      \
+      brk_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),   \
+                    __FILE__, __LINE__);                                          \
+      return (int)_e;                                                             \
+    }                                                                             \
+  } while (0)
+
+#ifdef __CUDACC__
+#define BRK_HD __host__ __device__
+#else
+#define BRK_HD
+#endif
+BRK_HD static inline bool brk_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Lanes-per-row for a vectorised row of d4 float4 chunks: smallest power of two >= d4, capped at 32.
+static inline int brk_lanes_per_row(int d4) {
+  int l = 1;
+  while (l < d4 && l < 32) l <<= 1;
+  return l;
+}
+
+#ifdef __CUDACC__
+
+// 128-bit streaming loads/stores. Table rows are read through the read-only path; rows that are
+// written once and not re-read by the same kernel bypass L1 allocation.
+__device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_na_f4(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// Vector reduction to global memory: one 16-byte RED instead of four scalar ones (sm_90+).
+__device__ __forceinline__ void red_add_f4(float* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+template <int LANES>
+__device__ __forceinline__ float group_sum(float x) {   // sum over aligned groups of LANES lanes
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+// Block-wide sum of a per-thread double; result valid in thread 0. smem: >= 32 doubles.
+__device__ __forceinline__ double block_sum_double(double x, double* smem) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) smem[w] = x;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  x = (threadIdx.x < nw) ? smem[threadIdx.x] : 0.0;
+  if (w == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  }
+  return x;
+}
+
+// Philox4x32-10 (Random123).  Known answers in tests/test_philox.py.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+#endif  // __CUDACC__

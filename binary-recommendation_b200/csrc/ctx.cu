@@ -1,0 +1,55 @@
+// Context, error string and workspace of libbrk_b200.
+#include <stdarg.h>
+#include <string.h>
+#include <stdlib.h>
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void brk_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int brk_abi_version(void) { return BRK_ABI_VERSION; }
+extern "C" const char* brk_last_error(void) { return g_err; }
+
+extern "C" int brk_create(brk_ctx** out, int device) {
+  BRK_REQUIRE(out != nullptr, BRK_E_ARG, "brk_create: out is null");
+  *out = nullptr;
+  int ndev = 0;
+  BRK_CUDA(cudaGetDeviceCount(&ndev));
+  BRK_REQUIRE(device >= 0 && device < ndev, BRK_E_ARG, "brk_create: device %d of %d", device, ndev);
+  BRK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BRK_CUDA(cudaGetDeviceProperties(&prop, device));
+  BRK_REQUIRE(prop.major == 10, BRK_E_STATE,
+              "brk_create: device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  brk_ctx* c = (brk_ctx*)calloc(1, sizeof(brk_ctx));
+  BRK_REQUIRE(c != nullptr, BRK_E_STATE, "brk_create: out of host memory");
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  BRK_CUDA(cudaMalloc(&c->loss_acc, BRK_LOSS_SLOTS * sizeof(double)));
+  BRK_CUDA(cudaMemset(c->loss_acc, 0, BRK_LOSS_SLOTS * sizeof(double)));
+  BRK_CUDA(cudaMalloc(&c->tickets, BRK_TICKETS * sizeof(unsigned int)));
+  BRK_CUDA(cudaMemset(c->tickets, 0, BRK_TICKETS * sizeof(unsigned int)));
+  c->scratch = nullptr;
+  c->scratch_bytes = 0;
+  BRK_CUDA(cudaDeviceSynchronize());
+  *out = c;
+  return 0;
+}
+
+extern "C" int brk_destroy(brk_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  if (c->loss_acc) cudaFree(c->loss_acc);
+  if (c->tickets) cudaFree(c->tickets);
+  if (c->scratch) cudaFree(c->scratch);
+  free(c);
+  return 0;
+}
+
+extern "C" int brk_sm_count(const brk_ctx* c) { return c ? c->sm_count : BRK_E_ARG; }

@@ -1,0 +1,160 @@
+// K1 gather_rows and K5 scatter_add_rows (atomic mode).  HBM-bound byte movers:
+//   gather  : 4d B read + 4d B written per row (+4 B id)
+//   scatter : 4d B read (vals) + 2*4d B read-modify-write of the accumulator row per occurrence
+// Mapping: a group of LPR = pow2(d/4) <= 32 lanes owns one row and moves it as float4 chunks, so a
+// warp covers 32/LPR rows per request wave with fully coalesced 128-bit accesses; ROWS_PER_ITER
+// rows per group are kept in flight to cover HBM latency.  Grid = SM count x resident CTAs.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kRowsPerIter = 4;
+
+template <int LPR>
+__global__ void __launch_bounds__(kThreads)
+gather_rows_vec(const float* __restrict__ table, int d4, const int32_t* __restrict__ ids,
+                int64_t n, float* __restrict__ out) {
+  const int lane_in = threadIdx.x & (LPR - 1);
+  const int64_t group = (int64_t(blockIdx.x) * kThreads + threadIdx.x) / LPR;
+  const int64_t n_groups = int64_t(gridDim.x) * kThreads / LPR;
+  const float4* __restrict__ t4 = reinterpret_cast<const float4*>(table);
+  float4* __restrict__ o4 = reinterpret_cast<float4*>(out);
+  for (int64_t b0 = group * kRowsPerIter; b0 < n; b0 += n_groups * kRowsPerIter) {
+    int64_t row[kRowsPerIter];
+#pragma unroll
+    for (int r = 0; r < kRowsPerIter; ++r) row[r] = (b0 + r < n) ? int64_t(__ldg(ids + b0 + r)) : -1;
+    for (int c = lane_in; c < d4; c += LPR) {
+      float4 v[kRowsPerIter];
+#pragma unroll
+      for (int r = 0; r < kRowsPerIter; ++r)
+        if (row[r] >= 0) v[r] = ldg_nc_f4(t4 + row[r] * d4 + c);
+#pragma unroll
+      for (int r = 0; r < kRowsPerIter; ++r)
+        if (row[r] >= 0) stg_na_f4(o4 + (b0 + r) * d4 + c, v[r]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+gather_rows_scalar(const float* __restrict__ table, int d, const int32_t* __restrict__ ids, int64_t n,
+                   float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+  const int64_t n_warps = int64_t(gridDim.x) * kThreads >> 5;
+  for (int64_t b = warp; b < n; b += n_warps) {
+    const int64_t row = __ldg(ids + b);
+    for (int c = lane; c < d; c += 32) out[b * d + c] = __ldg(table + row * d + c);
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(kThreads)
+scatter_add_rows_vec(float* __restrict__ acc, int d4, const int32_t* __restrict__ ids, int64_t n,
+                     const float* __restrict__ vals, uint32_t* __restrict__ touched) {
+  const int lane_in = threadIdx.x & (LPR - 1);
+  const int64_t group = (int64_t(blockIdx.x) * kThreads + threadIdx.x) / LPR;
+  const int64_t n_groups = int64_t(gridDim.x) * kThreads / LPR;
+  const float4* __restrict__ v4 = reinterpret_cast<const float4*>(vals);
+  for (int64_t b0 = group * kRowsPerIter; b0 < n; b0 += n_groups * kRowsPerIter) {
+    int64_t row[kRowsPerIter];
+#pragma unroll
+    for (int r = 0; r < kRowsPerIter; ++r) row[r] = (b0 + r < n) ? int64_t(__ldg(ids + b0 + r)) : -1;
+    for (int c = lane_in; c < d4; c += LPR) {
+      float4 v[kRowsPerIter];
+#pragma unroll
+      for (int r = 0; r < kRowsPerIter; ++r)
+        if (row[r] >= 0) v[r] = ldg_nc_f4(v4 + (b0 + r) * d4 + c);
+#pragma unroll
+      for (int r = 0; r < kRowsPerIter; ++r)
+        if (row[r] >= 0) red_add_f4(acc + (row[r] * d4 + c) * 4, v[r]);
+    }
+    if (touched != nullptr && lane_in == 0) {
+#pragma unroll
+      for (int r = 0; r < kRowsPerIter; ++r)
+        if (row[r] >= 0) {
+          const uint32_t bit = 1u << (row[r] & 31);
+          uint32_t* wptr = touched + (row[r] >> 5);
+          if (!(*reinterpret_cast<volatile uint32_t*>(wptr) & bit)) atomicOr(wptr, bit);
+        }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+scatter_add_rows_scalar(float* __restrict__ acc, int d, const int32_t* __restrict__ ids, int64_t n,
+                        const float* __restrict__ vals, uint32_t* __restrict__ touched) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+  const int64_t n_warps = int64_t(gridDim.x) * kThreads >> 5;
+  for (int64_t b = warp; b < n; b += n_warps) {
+    const int64_t row = __ldg(ids + b);
+    for (int c = lane; c < d; c += 32) atomicAdd(acc + row * d + c, __ldg(vals + b * d + c));
+    if (touched != nullptr && lane == 0) atomicOr(touched + (row >> 5), 1u << (row & 31));
+  }
+}
+
+int grid_for(const brk_ctx* ctx, int64_t work_items, int items_per_block) {
+  int64_t need = (work_items + items_per_block - 1) / items_per_block;
+  int64_t cap = int64_t(ctx->sm_count) * (2048 / kThreads);
+  if (need < 1) need = 1;
+  return int(need < cap ? need : cap);
+}
+
+}  // namespace
+
+extern "C" int brk_gather_rows(brk_ctx* ctx, const float* table, int64_t rows, int32_t d,
+                               const int32_t* ids, int64_t n, float* out, void* stream) {
+  BRK_REQUIRE(ctx && table && out && (ids || n == 0), BRK_E_ARG, "brk_gather_rows: null argument");
+  BRK_REQUIRE(rows > 0 && d > 0 && n >= 0, BRK_E_ARG, "brk_gather_rows: rows=%lld d=%d n=%lld",
+              (long long)rows, d, (long long)n);
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((d & 3) == 0 && brk_aligned16(table) && brk_aligned16(out)) {
+    const int d4 = d >> 2;
+    const int lpr = brk_lanes_per_row(d4);
+    const int grid = grid_for(ctx, n, (kThreads / lpr) * kRowsPerIter);
+    switch (lpr) {
+      case 1:  gather_rows_vec<1><<<grid, kThreads, 0, st>>>(table, d4, ids, n, out); break;
+      case 2:  gather_rows_vec<2><<<grid, kThreads, 0, st>>>(table, d4, ids, n, out); break;
+      case 4:  gather_rows_vec<4><<<grid, kThreads, 0, st>>>(table, d4, ids, n, out); break;
+      case 8:  gather_rows_vec<8><<<grid, kThreads, 0, st>>>(table, d4, ids, n, out); break;
+      case 16: gather_rows_vec<16><<<grid, kThreads, 0, st>>>(table, d4, ids, n, out); break;
+      default: gather_rows_vec<32><<<grid, kThreads, 0, st>>>(table, d4, ids, n, out); break;
+    }
+  } else {
+    const int grid = grid_for(ctx, n, kThreads / 32);
+    gather_rows_scalar<<<grid, kThreads, 0, st>>>(table, d, ids, n, out);
+  }
+  BRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int brk_scatter_add_rows(brk_ctx* ctx, float* acc, int64_t rows, int32_t d,
+                                    const int32_t* ids, int64_t n, const float* vals,
+                                    uint32_t* touched, int32_t mode, void* stream) {
+  BRK_REQUIRE(ctx && acc && (n == 0 || (ids && vals)), BRK_E_ARG, "brk_scatter_add_rows: null argument");
+  BRK_REQUIRE(rows > 0 && d > 0 && n >= 0, BRK_E_ARG, "brk_scatter_add_rows: rows=%lld d=%d n=%lld",
+              (long long)rows, d, (long long)n);
+  BRK_REQUIRE(mode == 0, BRK_E_ARG, "brk_scatter_add_rows: mode %d not available (0 = vector atomics)", mode);
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((d & 3) == 0 && brk_aligned16(acc) && brk_aligned16(vals)) {
+    const int d4 = d >> 2;
+    const int lpr = brk_lanes_per_row(d4);
+    const int grid = grid_for(ctx, n, (kThreads / lpr) * kRowsPerIter);
+    switch (lpr) {
+      case 1:  scatter_add_rows_vec<1><<<grid, kThreads, 0, st>>>(acc, d4, ids, n, vals, touched); break;
+      case 2:  scatter_add_rows_vec<2><<<grid, kThreads, 0, st>>>(acc, d4, ids, n, vals, touched); break;
+      case 4:  scatter_add_rows_vec<4><<<grid, kThreads, 0, st>>>(acc, d4, ids, n, vals, touched); break;
+      case 8:  scatter_add_rows_vec<8><<<grid, kThreads, 0, st>>>(acc, d4, ids, n, vals, touched); break;
+      case 16: scatter_add_rows_vec<16><<<grid, kThreads, 0, st>>>(acc, d4, ids, n, vals, touched); break;
+      default: scatter_add_rows_vec<32><<<grid, kThreads, 0, st>>>(acc, d4, ids, n, vals, touched); break;
+    }
+  } else {
+    const int grid = grid_for(ctx, n, kThreads / 32);
+    scatter_add_rows_scalar<<<grid, kThreads, 0, st>>>(acc, d, ids, n, vals, touched);
+  }
+  BRK_LAUNCH_CHECK();
+  return 0;
+}

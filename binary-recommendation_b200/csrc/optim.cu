@@ -1,0 +1,244 @@
+// K6: fused optimizers consuming the dense gradient accumulators written by the fwd/bwd kernels.
+//   adam_dense_keras : exact Keras Adam; every element moves (dense-equivalent for sparse grads).
+//                      Traffic per element: w,m,v read+write + g read + g zeroed = 32 B.
+//   adam_rows        : lazy Adam over rows flagged in the touched bitmask.  Per touched row:
+//                      6*4d (w,m,v r+w) + 4d (g read) + 4d (g zeroed) B; the bitmask scan adds rows/8 B.
+//   adagrad_rows     : Keras sparse Adagrad over touched rows: 4*4d + 4d + 4d B per touched row.
+// Reference call sites: Adam(1e-3) /root/reference/src/models/NeuMFModel.py:89, BPRModel.py:70,
+// bpr.py:201; Adam(lr=0.005) trainers/NFC_plain.py:153; "Adagrad" 0.1 trainers/twoTower.py:278-279.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxTabs = 16;
+
+struct TabList {
+  brk_table t[kMaxTabs];
+  int n;
+};
+
+struct AdamOp {
+  float alpha, b1, b2, omb1, omb2, eps;
+  __device__ __forceinline__ void operator()(float& w, float& m, float& v, float g) const {
+    m = b1 * m + omb1 * g;
+    v = b2 * v + omb2 * g * g;
+    w -= alpha * m / (sqrtf(v) + eps);
+  }
+};
+struct AdagradOp {
+  float lr, eps;
+  __device__ __forceinline__ void operator()(float& w, float& acc, float& /*unused*/, float g) const {
+    acc += g * g;
+    w -= lr * g / (sqrtf(acc) + eps);
+  }
+};
+
+template <class Op, bool HAS_V>
+__device__ __forceinline__ void apply4(const Op& op, float* w, float* m, float* v, float* g, int64_t i4) {
+  float4 w4 = reinterpret_cast<float4*>(w)[i4];
+  float4 m4 = reinterpret_cast<float4*>(m)[i4];
+  float4 v4 = HAS_V ? reinterpret_cast<float4*>(v)[i4] : make_float4(0, 0, 0, 0);
+  const float4 g4 = reinterpret_cast<float4*>(g)[i4];
+  op(w4.x, m4.x, v4.x, g4.x);
+  op(w4.y, m4.y, v4.y, g4.y);
+  op(w4.z, m4.z, v4.z, g4.z);
+  op(w4.w, m4.w, v4.w, g4.w);
+  reinterpret_cast<float4*>(w)[i4] = w4;
+  reinterpret_cast<float4*>(m)[i4] = m4;
+  if (HAS_V) reinterpret_cast<float4*>(v)[i4] = v4;
+  reinterpret_cast<float4*>(g)[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <class Op, bool HAS_V>
+__device__ __forceinline__ void apply1(const Op& op, float* w, float* m, float* v, float* g, int64_t i) {
+  float ww = w[i], mm = m[i], vv = HAS_V ? v[i] : 0.f;
+  op(ww, mm, vv, g[i]);
+  w[i] = ww; m[i] = mm;
+  if (HAS_V) v[i] = vv;
+  g[i] = 0.f;
+}
+
+__device__ __forceinline__ float adam_alpha(const brk_adam_hyper& h, const int64_t* step_dev) {
+  __shared__ float s_alpha;
+  if (threadIdx.x == 0) {
+    const double t = double(*step_dev + 1);
+    s_alpha = float(double(h.lr) * sqrt(1.0 - pow(double(h.beta2), t)) / (1.0 - pow(double(h.beta1), t)));
+  }
+  __syncthreads();
+  return s_alpha;
+}
+
+__device__ __forceinline__ void advance_step_last_block(int64_t* step_dev, unsigned int* ticket, int advance) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    if (t == gridDim.x - 1) {
+      if (advance) *step_dev += 1;
+      *ticket = 0u;
+      __threadfence();
+    }
+  }
+}
+
+template <class Op, bool HAS_V>
+__device__ __forceinline__ void dense_pass(const TabList& tl, const Op& op) {
+  const int64_t tid = int64_t(blockIdx.x) * kThreads + threadIdx.x;
+  const int64_t nthr = int64_t(gridDim.x) * kThreads;
+  for (int k = 0; k < tl.n; ++k) {
+    const brk_table& t = tl.t[k];
+    const int64_t numel = t.rows * t.d;
+    const bool vec = brk_aligned16(t.w) && brk_aligned16(t.m) && brk_aligned16(t.g) && (!HAS_V || brk_aligned16(t.v));
+    const int64_t n4 = vec ? (numel >> 2) : 0;
+    for (int64_t i = tid; i < n4; i += nthr) apply4<Op, HAS_V>(op, t.w, t.m, t.v, t.g, i);
+    for (int64_t i = n4 * 4 + tid; i < numel; i += nthr) apply1<Op, HAS_V>(op, t.w, t.m, t.v, t.g, i);
+    if (t.touched != nullptr) {
+      const int64_t nwords = (t.rows + 31) >> 5;
+      for (int64_t i = tid; i < nwords; i += nthr) t.touched[i] = 0u;
+    }
+  }
+}
+
+// Row-sparse pass: warps scan the touched bitmask 32 words at a time, clear what they read and
+// update the flagged rows; a row is handled by `lpr` lanes as float4 chunks.
+template <class Op, bool HAS_V>
+__device__ __forceinline__ void rows_pass(const TabList& tl, const Op& op) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
+  const int64_t n_warps = (int64_t(gridDim.x) * kThreads) >> 5;
+  for (int k = 0; k < tl.n; ++k) {
+    const brk_table& t = tl.t[k];
+    const bool vec = (t.d & 3) == 0 && brk_aligned16(t.w) && brk_aligned16(t.m) && brk_aligned16(t.g) &&
+                     (!HAS_V || brk_aligned16(t.v));
+    const int chunks = vec ? (t.d >> 2) : t.d;   // per-row work items (float4 or float)
+    int lpr = 1;
+    while (lpr < chunks && lpr < 32) lpr <<= 1;
+    const int gpw = 32 / lpr;
+    const int grp = lane / lpr, lane_in = lane % lpr;
+    const int64_t nwords = (t.rows + 31) >> 5;
+    // words per warp: 32 for big tables (coalesced scan), fewer when the table is too small to
+    // give every warp something to do
+    int wpw = 32;
+    while (wpw > 1 && nwords < n_warps * wpw) wpw >>= 1;
+    for (int64_t base = warp * wpw; base < nwords; base += n_warps * wpw) {
+      uint32_t word = 0u;
+      if (lane < wpw && base + lane < nwords) {
+        word = t.touched[base + lane];
+        if (word) t.touched[base + lane] = 0u;
+      }
+      uint32_t active = __ballot_sync(0xffffffffu, word != 0u);
+      while (active) {
+        const int src = __ffs(active) - 1;
+        active &= active - 1;
+        const uint32_t w = __shfl_sync(0xffffffffu, word, src);
+        const int64_t row_base = (base + src) << 5;
+        const int cnt = __popc(w);
+        for (int j = 0; j < cnt; j += gpw) {
+          const int kth = j + grp;
+          if (kth < cnt) {
+            const int64_t row = row_base + __fns(w, 0, kth + 1);
+            for (int c = lane_in; c < chunks; c += lpr) {
+              if (vec) apply4<Op, HAS_V>(op, t.w, t.m, t.v, t.g, row * chunks + c);
+              else     apply1<Op, HAS_V>(op, t.w, t.m, t.v, t.g, row * chunks + c);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+adam_dense_kernel(TabList tl, brk_adam_hyper h, int64_t* step_dev, unsigned int* ticket, int advance) {
+  AdamOp op;
+  op.alpha = adam_alpha(h, step_dev);
+  op.b1 = h.beta1; op.b2 = h.beta2; op.omb1 = 1.0f - h.beta1; op.omb2 = 1.0f - h.beta2; op.eps = h.eps;
+  dense_pass<AdamOp, true>(tl, op);
+  advance_step_last_block(step_dev, ticket, advance);
+}
+
+__global__ void __launch_bounds__(kThreads)
+adam_rows_kernel(TabList tl, brk_adam_hyper h, int64_t* step_dev, unsigned int* ticket, int advance) {
+  AdamOp op;
+  op.alpha = adam_alpha(h, step_dev);
+  op.b1 = h.beta1; op.b2 = h.beta2; op.omb1 = 1.0f - h.beta1; op.omb2 = 1.0f - h.beta2; op.eps = h.eps;
+  rows_pass<AdamOp, true>(tl, op);
+  advance_step_last_block(step_dev, ticket, advance);
+}
+
+__global__ void __launch_bounds__(kThreads) adagrad_rows_kernel(TabList tl, float lr, float eps) {
+  AdagradOp op{lr, eps};
+  rows_pass<AdagradOp, false>(tl, op);
+}
+__global__ void __launch_bounds__(kThreads) adagrad_dense_kernel(TabList tl, float lr, float eps) {
+  AdagradOp op{lr, eps};
+  dense_pass<AdagradOp, false>(tl, op);
+}
+
+int pack(const char* who, const brk_table* tabs, int32_t n_tabs, bool need_v, bool need_touched, TabList* out,
+         int64_t* work_items) {
+  BRK_REQUIRE(tabs != nullptr && n_tabs > 0 && n_tabs <= kMaxTabs, BRK_E_ARG, "%s: n_tabs=%d (1..%d)", who,
+              n_tabs, kMaxTabs);
+  int64_t work = 0;
+  for (int k = 0; k < n_tabs; ++k) {
+    const brk_table& t = tabs[k];
+    BRK_REQUIRE(t.w && t.g && t.m && (!need_v || t.v), BRK_E_ARG, "%s: table %d lacks w/g/m/v", who, k);
+    BRK_REQUIRE(!need_touched || t.touched, BRK_E_ARG, "%s: table %d lacks the touched bitmask", who, k);
+    BRK_REQUIRE(t.rows > 0 && t.d > 0, BRK_E_ARG, "%s: table %d rows=%lld d=%d", who, k, (long long)t.rows, t.d);
+    out->t[k] = t;
+    work += need_touched ? (t.rows + 31) / 32 * 32 : (t.rows * t.d + 3) / 4;  // threads wanted
+  }
+  out->n = n_tabs;
+  *work_items = work;
+  return 0;
+}
+
+int grid_for(const brk_ctx* ctx, int64_t threads_wanted) {
+  int64_t need = (threads_wanted + kThreads - 1) / kThreads;
+  const int64_t cap = int64_t(ctx->sm_count) * (2048 / kThreads);
+  return int(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+}  // namespace
+
+extern "C" int brk_adam_dense_keras(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, brk_adam_hyper h,
+                                    int64_t* step_dev, int32_t advance_step, void* stream) {
+  BRK_REQUIRE(ctx && step_dev, BRK_E_ARG, "brk_adam_dense_keras: null argument");
+  TabList tl; int64_t work;
+  if (int rc = pack("brk_adam_dense_keras", tabs, n_tabs, true, false, &tl, &work)) return rc;
+  adam_dense_kernel<<<grid_for(ctx, work), kThreads, 0, (cudaStream_t)stream>>>(tl, h, step_dev, ctx->tickets + 1,
+                                                                               advance_step);
+  BRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int brk_adam_rows(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, brk_adam_hyper h,
+                             int64_t* step_dev, int32_t advance_step, void* stream) {
+  BRK_REQUIRE(ctx && step_dev, BRK_E_ARG, "brk_adam_rows: null argument");
+  TabList tl; int64_t work;
+  if (int rc = pack("brk_adam_rows", tabs, n_tabs, true, true, &tl, &work)) return rc;
+  adam_rows_kernel<<<grid_for(ctx, work), kThreads, 0, (cudaStream_t)stream>>>(tl, h, step_dev, ctx->tickets + 2,
+                                                                              advance_step);
+  BRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int brk_adagrad_rows(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, float lr, float eps,
+                                void* stream) {
+  BRK_REQUIRE(ctx, BRK_E_ARG, "brk_adagrad_rows: null context");
+  TabList tl; int64_t work;
+  if (int rc = pack("brk_adagrad_rows", tabs, n_tabs, false, true, &tl, &work)) return rc;
+  adagrad_rows_kernel<<<grid_for(ctx, work), kThreads, 0, (cudaStream_t)stream>>>(tl, lr, eps);
+  BRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int brk_adagrad_dense(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, float lr, float eps,
+                                 void* stream) {
+  BRK_REQUIRE(ctx, BRK_E_ARG, "brk_adagrad_dense: null context");
+  TabList tl; int64_t work;
+  if (int rc = pack("brk_adagrad_dense", tabs, n_tabs, false, false, &tl, &work)) return rc;
+  adagrad_dense_kernel<<<grid_for(ctx, work), kThreads, 0, (cudaStream_t)stream>>>(tl, lr, eps);
+  BRK_LAUNCH_CHECK();
+  return 0;
+}

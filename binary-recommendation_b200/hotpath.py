@@ -1,0 +1,203 @@
+"""Python face of the C ABI: device-resident embedding tables, the fused kernels and the Keras-named
+optimizers the reference's model code asks for.  Each function validates shapes/dtypes (raising, as
+Keras would) and forwards raw device pointers to libbrk_b200.so on the current torch stream.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+
+def _i32(t, name):
+    if t.dtype != torch.int32:
+        raise TypeError(f"{name} must be int32 (the reference feeds float32 ids, "
+                        f"src/models/BPRModel.py:101-103; this path is int32 end to end)")
+    return t.contiguous()
+
+
+def _f32(t, name):
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32")
+    return t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# K1 / K5
+# ----------------------------------------------------------------------------------------------
+def gather_rows(table, ids, out=None):
+    """out[b,:] = table[ids[b],:]  -- keras Embedding lookup (NeuMFModel.py:58-63 etc.)."""
+    table = _f32(table, "table"); ids = _i32(ids, "ids")
+    rows, d = table.shape
+    n = ids.numel()
+    if out is None:
+        out = torch.empty((n, d), dtype=torch.float32, device=table.device)
+    N.check(N.lib().brk_gather_rows(N.ctx(table.device), N.ptr(table), rows, d, N.ptr(ids), n, N.ptr(out),
+                                    N.stream_ptr()), "brk_gather_rows")
+    return out
+
+
+def scatter_add_rows(acc, ids, vals, touched=None, mode=0):
+    """acc[ids[b],:] += vals[b,:]  -- IndexedSlices gradient accumulation."""
+    acc = _f32(acc, "acc"); ids = _i32(ids, "ids"); vals = _f32(vals, "vals")
+    rows, d = acc.shape
+    N.check(N.lib().brk_scatter_add_rows(N.ctx(acc.device), N.ptr(acc), rows, d, N.ptr(ids), ids.numel(),
+                                         N.ptr(vals), N.ptr(touched), mode, N.stream_ptr()),
+            "brk_scatter_add_rows")
+    return acc
+
+
+# ----------------------------------------------------------------------------------------------
+# K10
+# ----------------------------------------------------------------------------------------------
+def philox4x32_10(ctr, key0, key1):
+    ctr = ctr.contiguous()
+    out = torch.empty_like(ctr)
+    N.check(N.lib().brk_philox4x32_10(N.ctx(ctr.device), N.ptr(ctr), ctr.shape[0], key0 & 0xFFFFFFFF,
+                                      key1 & 0xFFFFFFFF, N.ptr(out), N.stream_ptr()), "brk_philox4x32_10")
+    return out
+
+
+def philox_bpr_negatives(users, seed, epoch, num_items, csr_indptr, csr_items, first_index=0, out=None):
+    users = _i32(users, "users")
+    if csr_indptr.dtype != torch.int64 or csr_items.dtype != torch.int32:
+        raise TypeError("csr_indptr must be int64 and csr_items int32")
+    if out is None:
+        out = torch.empty_like(users)
+    N.check(N.lib().brk_philox_bpr_negatives(N.ctx(users.device), N.ptr(users), users.numel(), first_index,
+                                             seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, num_items,
+                                             N.ptr(csr_indptr), N.ptr(csr_items), N.ptr(out), N.stream_ptr()),
+            "brk_philox_bpr_negatives")
+    return out
+
+
+def philox_neumf_negatives(pos_users, pos_items, n_neg, seed, epoch, first_index=0):
+    pos_users = _i32(pos_users, "pos_users"); pos_items = _i32(pos_items, "pos_items")
+    nu = torch.empty(n_neg, dtype=torch.int32, device=pos_users.device)
+    ni = torch.empty(n_neg, dtype=torch.int32, device=pos_users.device)
+    N.check(N.lib().brk_philox_neumf_negatives(N.ctx(pos_users.device), N.ptr(pos_users), N.ptr(pos_items),
+                                               pos_users.numel(), n_neg, first_index, seed & 0xFFFFFFFF,
+                                               epoch & 0xFFFFFFFF, N.ptr(nu), N.ptr(ni), N.stream_ptr()),
+            "brk_philox_neumf_negatives")
+    return nu, ni
+
+
+# ----------------------------------------------------------------------------------------------
+# Tables and optimizers
+# ----------------------------------------------------------------------------------------------
+class Table:
+    """An embedding table (or a flat dense parameter) resident in HBM with its gradient
+    accumulator, optimizer slots and touched-row bitmask.  Layout: row-major fp32 [rows, d]."""
+
+    def __init__(self, w, slots=2, touched=True, slot_init=0.0):
+        self.w = _f32(w, "w")
+        if self.w.dim() == 1:
+            self.w = self.w.view(1, -1)
+        self.rows, self.d = self.w.shape
+        dev = self.w.device
+        self.g = torch.zeros_like(self.w)
+        self.m = torch.full_like(self.w, slot_init) if slots >= 1 else None
+        self.v = torch.zeros_like(self.w) if slots >= 2 else None
+        self.touched = torch.zeros((self.rows + 31) // 32, dtype=torch.int32, device=dev) if touched else None
+
+    def c_struct(self):
+        return N.brk_table(self.w.data_ptr(), self.g.data_ptr(),
+                           self.m.data_ptr() if self.m is not None else None,
+                           self.v.data_ptr() if self.v is not None else None,
+                           self.touched.data_ptr() if self.touched is not None else None,
+                           self.rows, self.d, 0)
+
+    @property
+    def bytes(self):
+        return self.w.numel() * 4
+
+
+def _pack(tables):
+    arr = (N.brk_table * len(tables))(*[t.c_struct() for t in tables])
+    return arr
+
+
+class Adam:
+    """tf.keras.optimizers.Adam with its defaults (lr 1e-3, beta 0.9/0.999, epsilon 1e-7), as the
+    reference constructs it (NeuMFModel.py:89, BPRModel.py:70, bpr.py:201, NFC_plain.py:153).
+    sparse='keras' reproduces Keras' dense-equivalent handling of embedding gradients exactly;
+    sparse='lazy' updates only the rows hit by the batch (for tables too large for a dense pass)."""
+
+    def __init__(self, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, sparse="keras", device=None):
+        if sparse not in ("keras", "lazy"):
+            raise ValueError("sparse must be 'keras' or 'lazy'")
+        self.h = N.brk_adam_hyper(learning_rate, beta_1, beta_2, epsilon)
+        self.sparse = sparse
+        self.step = torch.zeros(1, dtype=torch.int64, device=device or "cuda")
+
+    def apply(self, tables, dense=()):
+        """One optimizer step over embedding `tables` and `dense` parameters (always dense)."""
+        lib, ctx, st = N.lib(), N.ctx(self.step.device), N.stream_ptr()
+        tables, dense = list(tables), list(dense)
+        if self.sparse == "keras":
+            allp = tables + dense
+            N.check(lib.brk_adam_dense_keras(ctx, _pack(allp), len(allp), self.h, N.ptr(self.step), 1, st),
+                    "brk_adam_dense_keras")
+        else:
+            if dense:
+                N.check(lib.brk_adam_dense_keras(ctx, _pack(dense), len(dense), self.h, N.ptr(self.step), 0, st),
+                        "brk_adam_dense_keras")
+            N.check(lib.brk_adam_rows(ctx, _pack(tables), len(tables), self.h, N.ptr(self.step), 1, st),
+                    "brk_adam_rows")
+
+
+class Adagrad:
+    """tf.keras.optimizers.Adagrad defaults (initial accumulator 0.1, epsilon 1e-7); the reference
+    uses lr 0.1 (trainers/twoTower.py:278-279).  Untouched rows have g == 0 and do not move, so
+    the dense pass and the row-sparse pass give identical results; `rows_threshold_bytes` picks."""
+
+    INITIAL_ACCUMULATOR = 0.1
+
+    def __init__(self, learning_rate=0.001, epsilon=1e-7, rows_threshold_bytes=64 << 20):
+        self.lr, self.eps = learning_rate, epsilon
+        self.rows_threshold_bytes = rows_threshold_bytes
+
+    def apply(self, tables, dense=()):
+        lib, st = N.lib(), N.stream_ptr()
+        tables, dense = list(tables), list(dense)
+        big = [t for t in tables if t.bytes > self.rows_threshold_bytes and t.touched is not None]
+        small = [t for t in tables if t not in big] + dense
+        dev = (tables + dense)[0].w.device
+        if small:
+            N.check(lib.brk_adagrad_dense(N.ctx(dev), _pack(small), len(small), self.lr, self.eps, st),
+                    "brk_adagrad_dense")
+        if big:
+            N.check(lib.brk_adagrad_rows(N.ctx(dev), _pack(big), len(big), self.lr, self.eps, st),
+                    "brk_adagrad_rows")
+
+
+# ----------------------------------------------------------------------------------------------
+# Fused BPR
+# ----------------------------------------------------------------------------------------------
+def bpr_fwd_bwd(user, item, u, p, n, loss_out=None):
+    """Fused triplet forward/backward (BPRModel.py:49-74,124-144); returns the device loss scalar."""
+    u = _i32(u, "u"); p = _i32(p, "p"); n = _i32(n, "n")
+    if not (u.numel() == p.numel() == n.numel()):
+        raise ValueError("u, p, n must have the same length")
+    if loss_out is None:
+        loss_out = torch.empty(1, dtype=torch.float32, device=user.w.device)
+    us, it = user.c_struct(), item.c_struct()
+    N.check(N.lib().brk_bpr_fwd_bwd(N.ctx(user.w.device), C.byref(us), C.byref(it), N.ptr(u), N.ptr(p),
+                                    N.ptr(n), u.numel(), N.ptr(loss_out), N.stream_ptr()), "brk_bpr_fwd_bwd")
+    return loss_out
+
+
+def bpr_scores(user_w, item_w, u, p, n):
+    u = _i32(u, "u"); p = _i32(p, "p"); n = _i32(n, "n")
+    out = torch.empty(u.numel(), dtype=torch.float32, device=user_w.device)
+    N.check(N.lib().brk_bpr_scores(N.ctx(user_w.device), N.ptr(_f32(user_w, "user_w")),
+                                   N.ptr(_f32(item_w, "item_w")), user_w.shape[1], N.ptr(u), N.ptr(p),
+                                   N.ptr(n), u.numel(), N.ptr(out), N.stream_ptr()), "brk_bpr_scores")
+    return out
+
+
+def keras_embedding_init(rows, dim, rng):
+    """Keras Embedding default initializer U(-0.05, 0.05), generated on the host so that the
+    oracle and the device start from identical weights."""
+    return rng.uniform(-0.05, 0.05, size=(rows, dim)).astype(np.float32)

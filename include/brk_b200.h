@@ -1,0 +1,138 @@
+/*
+ * brk_b200.h -- C ABI of the B200-native recommender hot path (libbrk_b200.so).
+ *
+ * The reference (leotimus/binary-recommendation) is pure Python over TensorFlow/Keras/TFRS and
+ * has no FFI layer of its own; the interface this library replaces is the set of framework ops
+ * its model/trainer code calls.  Each entry point below cites the
+ * reference call site(s) whose framework op it stands in for (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all
+ *     buffers; the library allocates nothing except the opaque context's small workspace;
+ *   - ids are int32, tables are row-major contiguous fp32 [rows, d];
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), no hidden syncs,
+ *     safe to capture into a CUDA graph;
+ *   - return 0 on success, <0 for a bad argument (BRK_E_*), >0 for a cudaError_t; the message is
+ *     available from brk_last_error() (thread-local);
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef BRK_B200_H
+#define BRK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRK_ABI_VERSION 1
+
+#define BRK_E_ARG   (-1)   /* null pointer, negative size, unsupported dimension */
+#define BRK_E_ALIGN (-2)   /* pointer / row stride not aligned as required */
+#define BRK_E_STATE (-3)   /* context unusable */
+
+typedef struct brk_ctx brk_ctx;
+
+/* One embedding table (or one flat dense parameter when rows == 1) with its gradient
+ * accumulator and optimizer slots.  g is a dense fp32 accumulator of the same shape that the
+ * fused forward/backward kernels add row gradients into and the optimizer kernels consume and
+ * zero.  touched is a bitmask over rows ((rows+31)/32 words, zero between steps) recording which
+ * rows received a gradient this step; required by the row-sparse optimizers, may be NULL when
+ * only dense optimizers are used. m, v: Adam moments; for Adagrad m is the accumulator. */
+typedef struct brk_table {
+  float*    w;
+  float*    g;
+  float*    m;
+  float*    v;
+  uint32_t* touched;
+  int64_t   rows;
+  int32_t   d;
+  int32_t   _pad;
+} brk_table;
+
+typedef struct brk_adam_hyper {
+  float lr, beta1, beta2, eps;   /* Keras defaults: 1e-3, 0.9, 0.999, 1e-7 */
+} brk_adam_hyper;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int         brk_abi_version(void);
+const char* brk_last_error(void);
+int         brk_create(brk_ctx** out, int device);
+int         brk_destroy(brk_ctx* ctx);
+int         brk_sm_count(const brk_ctx* ctx);
+
+/* ---- K1: embedding row gather -------------------------------------------------------------
+ * Stands in for keras Embedding(...)(ids) -> tf ResourceGather:
+ *   src/models/NeuMFModel.py:58-63, src/models/BPRModel.py:55-61, src/models/bpr.py:178-184,
+ *   trainers/twoTower.py:34,36.   out[b,:] = table[ids[b],:], b < n.  ids must be in [0,rows). */
+int brk_gather_rows(brk_ctx* ctx, const float* table, int64_t rows, int32_t d,
+                    const int32_t* ids, int64_t n, float* out, void* stream);
+
+/* ---- K5: sparse embedding-gradient scatter-add -------------------------------------------
+ * Stands in for the IndexedSlices gradient of the gathers above and the optimizer's duplicate
+ * summation (tf UnsortedSegmentSum; inside model.fit src/models/RModel.py:130 and
+ * tape.gradient trainers/twoTower.py:97).  acc[ids[b],:] += vals[b,:].
+ * mode 0: vector atomics (red.global.add.v4.f32); mode 1: sort-and-segment-reduce (deterministic).
+ * touched (may be NULL) gets bit ids[b] set. */
+int brk_scatter_add_rows(brk_ctx* ctx, float* acc, int64_t rows, int32_t d,
+                         const int32_t* ids, int64_t n, const float* vals,
+                         uint32_t* touched, int32_t mode, void* stream);
+
+/* ---- K10: counter-based negative sampling (Philox4x32-10) ---------------------------------
+ * Replaces the host-RNG sampling of src/models/NeuMFModel.py:104-105 and the exhaustive
+ * enumeration of src/models/BPRModel.py:111-119 / src/models/bpr.py:96-107.  The stream is
+ * defined in oracle/philox.py ("brk sampler v1") and reproduced bit-for-bit.
+ * BPR: for sample first_index+b with user users[b], the first candidate item that is not in the
+ * user's sorted positive list (csr_indptr int64 [U+1], csr_items int32) is written to neg[b]. */
+int brk_philox_bpr_negatives(brk_ctx* ctx, const int32_t* users, int64_t n, int64_t first_index,
+                             uint32_t seed, uint32_t epoch, int32_t num_items,
+                             const int64_t* csr_indptr, const int32_t* csr_items,
+                             int32_t* neg, void* stream);
+/* NeuMF: neg_user[b] = pos_users[(w0*P)>>32], neg_item[b] = pos_items[(w1*P)>>32]. */
+int brk_philox_neumf_negatives(brk_ctx* ctx, const int32_t* pos_users, const int32_t* pos_items,
+                               int64_t num_pos, int64_t n, int64_t first_index,
+                               uint32_t seed, uint32_t epoch,
+                               int32_t* neg_users, int32_t* neg_items, void* stream);
+/* Raw generator (known-answer tests): out[i,0..3] = philox4x32_10(ctr[i,0..3], key). */
+int brk_philox4x32_10(brk_ctx* ctx, const uint32_t* ctr, int64_t n, uint32_t key0, uint32_t key1,
+                      uint32_t* out, void* stream);
+
+/* ---- K1+K4+K5 fused: BPR triplet forward + backward ----------------------------------------
+ * Stands in for the graph of src/models/BPRModel.py:49-74 with bprTripletLoss/identityLoss
+ * (:124-144; twin src/models/bpr.py:136-192) and its gradient inside model.fit (BPRModel.py:109):
+ *   x = <u,p> - <u,n>;  l = 1 - sigmoid(x);  loss = mean(l);
+ *   user.g[u] += g(p-n), item.g[p] += g u, item.g[n] -= g u,  g = -s(1-s)/B.
+ * loss_out[0] receives the batch mean.  Row gradients are accumulated into user->g / item->g
+ * (which must be zero on entry -- the optimizer calls below re-zero them). */
+int brk_bpr_fwd_bwd(brk_ctx* ctx, const brk_table* user, const brk_table* item,
+                    const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch,
+                    float* loss_out, void* stream);
+/* Forward only: x_out[b] = <u,p> - <u,n> (scores for evaluation, bpr.py:122-133). */
+int brk_bpr_scores(brk_ctx* ctx, const float* user_w, const float* item_w, int32_t d,
+                   const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch,
+                   float* x_out, void* stream);
+
+/* ---- K6: optimizers -----------------------------------------------------------------------
+ * step_dev: device int64 holding the number of completed optimizer steps t; the kernels use
+ * t+1 and, when advance_step != 0, the last block increments it (so a whole epoch can be
+ * captured in one CUDA graph).
+ * brk_adam_dense_keras: exact Keras Adam (src/models/NeuMFModel.py:89, BPRModel.py:70,
+ *   bpr.py:201, trainers/NFC_plain.py:153): every element of every listed table moves,
+ *   alpha_t = lr*sqrt(1-b2^t)/(1-b1^t), w -= alpha_t*m/(sqrt(v)+eps); g is zeroed, touched cleared.
+ * brk_adam_rows: lazy variant touching only rows whose touched bit is set (clears the bits).
+ * brk_adagrad_rows: Keras Adagrad sparse apply (trainers/twoTower.py:278-279; accumulator in
+ *   tab.m, initial value 0.1 set by the caller): acc += g^2, w -= lr*g/(sqrt(acc)+eps).
+ * brk_adagrad_dense: same on whole tables (dense kernels/biases). */
+int brk_adam_dense_keras(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, brk_adam_hyper h,
+                         int64_t* step_dev, int32_t advance_step, void* stream);
+int brk_adam_rows(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, brk_adam_hyper h,
+                  int64_t* step_dev, int32_t advance_step, void* stream);
+int brk_adagrad_rows(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, float lr, float eps,
+                     void* stream);
+int brk_adagrad_dense(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, float lr, float eps,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRK_B200_H */

@@ -1,0 +1,73 @@
+"""ORACLE (test infrastructure, never the product path): BPR matrix factorisation restated on
+the CPU.  PARITY UNPINNED at the Keras boundary (no golden vectors in the reference; SURVEY.md
+section 0.3); pinned by hand-computed fp64 cases in tests/test_oracle_models.py.
+
+Follows /root/reference/src/models/BPRModel.py:49-74 (graph: one user table, one item table
+shared by the positive and negative lookup), :124-144 (bprTripletLoss, identityLoss) and the
+script twin /root/reference/src/models/bpr.py:136-192.
+
+  x_b   = sum_d u_b*p_b - sum_d u_b*n_b              (BPRModel.py:139-142)
+  l_b   = 1 - sigmoid(x_b)                           (BPRModel.py:144; NOT -log sigmoid)
+  loss  = mean_b l_b                                 (identityLoss, BPRModel.py:126)
+  dl/dx = -s(1-s)/B;  du = g (p-n), dp = g u, dn = -g u
+"""
+import numpy as np
+
+from . import embedding as E
+
+
+def bpr_forward(user_tab, item_tab, u, p, n):
+    ue, pe, ne = user_tab[u], item_tab[p], item_tab[n]
+    x = (ue * pe).sum(-1) - (ue * ne).sum(-1)
+    s = 1.0 / (1.0 + np.exp(-x.astype(np.float64)))
+    return x, s.astype(user_tab.dtype)
+
+
+def bpr_loss_and_grads(user_tab, item_tab, u, p, n):
+    """Returns (loss, dense grad of user table, dense grad of item table)."""
+    dt = user_tab.dtype
+    u = np.asarray(u, dtype=np.int64); p = np.asarray(p, dtype=np.int64); n = np.asarray(n, dtype=np.int64)
+    B = len(u)
+    ue, pe, ne = user_tab[u], item_tab[p], item_tab[n]
+    x, s = bpr_forward(user_tab, item_tab, u, p, n)
+    loss = dt.type(np.mean(1.0 - s.astype(np.float64)))
+    g = (-(s * (1 - s)) / dt.type(B)).astype(dt)[:, None]
+    gu = E.scatter_add_rows(user_tab.shape[0], u, g * (pe - ne), dtype=dt)
+    gi = E.scatter_add_rows(item_tab.shape[0], p, g * ue, dtype=dt)
+    np.add.at(gi, n, -g * ue)
+    return loss, gu, gi
+
+
+class BPROracle:
+    """Training loop state: tables + Adam moments.  optimizer 'adam_keras' is what the reference
+    runs (dense-equivalent sparse Adam); 'adam_lazy' is the row-sparse variant."""
+
+    def __init__(self, num_users, num_items, dim, seed=42, dtype=np.float32, lr=1e-3,
+                 optimizer="adam_keras"):
+        rng = np.random.Generator(np.random.Philox(key=seed))
+        self.user = E.keras_embedding_init(rng, num_users, dim, dtype)
+        self.item = E.keras_embedding_init(rng, num_items, dim, dtype)
+        self.mu = np.zeros_like(self.user); self.vu = np.zeros_like(self.user)
+        self.mi = np.zeros_like(self.item); self.vi = np.zeros_like(self.item)
+        self.t = 0
+        self.lr = lr
+        self.optimizer = optimizer
+
+    def step(self, u, p, n):
+        loss, gu, gi = bpr_loss_and_grads(self.user, self.item, u, p, n)
+        self.t += 1
+        if self.optimizer == "adam_keras":
+            E.adam_dense_keras(self.user, self.mu, self.vu, gu, self.t, lr=self.lr)
+            E.adam_dense_keras(self.item, self.mi, self.vi, gi, self.t, lr=self.lr)
+        elif self.optimizer == "adam_lazy":
+            E.adam_rows_lazy(self.user, self.mu, self.vu, gu, np.unique(u), self.t, lr=self.lr)
+            E.adam_rows_lazy(self.item, self.mi, self.vi, gi,
+                             np.unique(np.concatenate([p, n])), self.t, lr=self.lr)
+        else:
+            raise ValueError(self.optimizer)
+        return loss
+
+
+def bpr_predict(user_tab, item_tab, user_id, item_ids):
+    """bpr.py:122-133: user vector times item matrix."""
+    return item_tab[np.asarray(item_ids, dtype=np.int64)] @ user_tab[user_id]

@@ -1,0 +1,78 @@
+"""Oracle pins for the BPR loss/gradients and the Keras optimizers: hand-computed fp64 cases
+(the reference holds no golden vectors for these; SURVEY.md section 8c, pins (2))."""
+import math
+
+import numpy as np
+
+from oracle import bpr as B
+from oracle import embedding as E
+
+
+def test_gather_scatter_roundtrip():
+    t = np.arange(12, dtype=np.float32).reshape(4, 3)
+    ids = np.array([3, 0, 3], dtype=np.int32)
+    out = E.gather_rows(t, ids)
+    assert np.array_equal(out, t[[3, 0, 3]])
+    acc = E.scatter_add_rows(4, ids, out)
+    assert np.array_equal(acc[3], 2 * t[3]) and np.array_equal(acc[0], t[0]) and not acc[1].any()
+
+
+def test_bpr_hand_case_fp64():
+    # U=3, I=4, F=2; one triplet (u=1, p=2, n=0)
+    user = np.array([[0.1, 0.2], [0.3, -0.4], [0.5, 0.6]], dtype=np.float64)
+    item = np.array([[0.2, 0.1], [0.0, 0.3], [-0.5, 0.7], [0.9, 0.9]], dtype=np.float64)
+    x = (0.3 * -0.5 + -0.4 * 0.7) - (0.3 * 0.2 + -0.4 * 0.1)   # = -0.43 - 0.02 = -0.45
+    s = 1 / (1 + math.exp(-x))
+    loss, gu, gi = B.bpr_loss_and_grads(user, item, [1], [2], [0])
+    assert abs(loss - (1 - s)) < 1e-15
+    g = -s * (1 - s)
+    np.testing.assert_allclose(gu[1], g * (item[2] - item[0]), rtol=1e-14)
+    np.testing.assert_allclose(gi[2], g * user[1], rtol=1e-14)
+    np.testing.assert_allclose(gi[0], -g * user[1], rtol=1e-14)
+    assert not gu[0].any() and not gu[2].any() and not gi[1].any() and not gi[3].any()
+
+
+def test_bpr_grads_match_finite_differences():
+    rng = np.random.default_rng(0)
+    user = rng.normal(size=(5, 3)); item = rng.normal(size=(6, 3))
+    u = np.array([0, 1, 1, 4]); p = np.array([2, 2, 3, 5]); n = np.array([1, 0, 2, 2])
+    loss, gu, gi = B.bpr_loss_and_grads(user, item, u, p, n)
+    eps = 1e-6
+    for (tab, g) in ((user, gu), (item, gi)):
+        for r in range(tab.shape[0]):
+            for c in range(tab.shape[1]):
+                tab[r, c] += eps; lp = B.bpr_loss_and_grads(user, item, u, p, n)[0]
+                tab[r, c] -= 2 * eps; lm = B.bpr_loss_and_grads(user, item, u, p, n)[0]
+                tab[r, c] += eps
+                assert abs((lp - lm) / (2 * eps) - g[r, c]) < 1e-8
+
+
+def test_keras_adam_first_steps_fp64():
+    # Keras: alpha_t = lr*sqrt(1-b2^t)/(1-b1^t); w -= alpha_t*m/(sqrt(v)+eps), eps=1e-7 outside sqrt
+    w = np.array([[1.0, -2.0]]); m = np.zeros_like(w); v = np.zeros_like(w)
+    g = np.array([[0.5, 0.0]])
+    E.adam_dense_keras(w, m, v, g, 1)
+    a1 = 1e-3 * math.sqrt(1 - 0.999) / (1 - 0.9)
+    assert abs(w[0, 0] - (1.0 - a1 * 0.05 / (math.sqrt(0.001 * 0.25) + 1e-7))) < 1e-15
+    assert w[0, 1] == -2.0          # zero grad, zero moments: does not move
+    # second step with zero gradient: Keras still moves the row on stale momentum (dense-equivalent)
+    w1 = w.copy()
+    E.adam_dense_keras(w, m, v, np.zeros_like(g), 2)
+    assert w[0, 0] < w1[0, 0]
+    # lazy Adam leaves an untouched row alone
+    w2 = w.copy()
+    E.adam_rows_lazy(w, m, v, np.zeros_like(g), np.array([], dtype=np.int64), 3)
+    assert np.array_equal(w, w2)
+
+
+def test_keras_adagrad_fp64():
+    w = np.array([[1.0], [2.0]]); acc = np.full_like(w, 0.1)
+    g = np.array([[0.3], [0.0]])
+    E.adagrad_rows(w, acc, g, [0], lr=0.1)
+    assert abs(acc[0, 0] - 0.19) < 1e-15
+    assert abs(w[0, 0] - (1.0 - 0.1 * 0.3 / (math.sqrt(0.19) + 1e-7))) < 1e-15
+    assert w[1, 0] == 2.0 and acc[1, 0] == 0.1
+    # dense pass is identical (zero gradient rows do not move)
+    w2 = np.array([[1.0], [2.0]]); acc2 = np.full_like(w2, 0.1)
+    E.adagrad_dense(w2, acc2, g, lr=0.1)
+    assert np.array_equal(w, w2) and np.array_equal(acc, acc2)
