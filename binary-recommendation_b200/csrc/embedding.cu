@@ -105,7 +105,7 @@ int grid_for(const brk_ctx* ctx, int64_t work_items, int items_per_block) {
 
 extern "C" int brk_gather_rows(brk_ctx* ctx, const float* table, int64_t rows, int32_t d,
                                const int32_t* ids, int64_t n, float* out, void* stream) {
-  BRK_REQUIRE(ctx && table && out && (ids || n == 0), BRK_E_ARG, "brk_gather_rows: null argument");
+  BRK_REQUIRE(ctx && table && (n == 0 || (ids && out)), BRK_E_ARG, "brk_gather_rows: null argument");
   BRK_REQUIRE(rows > 0 && d > 0 && n >= 0, BRK_E_ARG, "brk_gather_rows: rows=%lld d=%d n=%lld",
               (long long)rows, d, (long long)n);
   if (n == 0) return 0;
