@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native recommender hot path.
+
+Workload (BASELINE.json configs[1]): BPR matrix factorisation, d = 64, on synthetic binary implicit
+feedback of MovieLens-1M shape (6040 users x 3706 items, 1 000 209 positives), one Philox negative
+per positive, loss 1 - sigmoid (reference BPRModel.py:144), exact Keras Adam(1e-3), batch 16 384.
+A "step" is one batch: fused gather + loss + scatter-add kernel, then the fused Adam pass.
+Metric: training interactions (triplets) per second.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is produced.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "train interactions/sec (BPR, d=64, ML-1M shape)"
+UNIT = "interactions/s"
+BATCH = 16384
+DIM = 64
+BYTES_PER_TRIPLET = 3 * 4 * DIM * 2          # 3 rows gathered + 3 row gradients reduced: 1536 B
+L2_FLUSH_BYTES = 256 << 20
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+def make_workload():
+    from binrec_b200 import synth
+    users, items = synth.make_interactions()           # ML-1M shape, skewed
+    return users, items, synth.ML1M_USERS, synth.ML1M_ITEMS
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's torch-CPU BPR loop on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_loop(users, items, U, I, steps, warmup, time_budget_s=None):
+    """Returns (interactions/s, steps timed, threads)."""
+    from oracle import bpr as OB, bpr_torch as OT, philox as OP
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    orc = OB.BPROracle(U, I, DIM, seed=42)
+    model = OT.BPRTorchCPU(orc.user, orc.item)
+    n_batches = len(users) // BATCH
+    need = min(n_batches, steps + warmup)
+    indptr, sitems = OP.build_csr(users, items, U)
+    neg = OP.bpr_negatives(users[:need * BATCH], 7, 0, I, indptr, sitems)
+
+    def run(k):
+        b = k % need
+        sl = slice(b * BATCH, (b + 1) * BATCH)
+        return model.step(users[sl], items[sl], neg[sl])
+
+    for k in range(warmup):
+        run(k)
+    t0 = time.perf_counter()
+    done = 0
+    for k in range(steps):
+        run(warmup + k)
+        done += 1
+        if time_budget_s is not None and time.perf_counter() - t0 > time_budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done * BATCH / dt, done, threads, dt
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    users, items, U, I = make_workload()
+    val, done, threads, dt = cpu_loop(users, items, U, I, args.steps, args.warmup)
+    sample = f"{done} steps x {BATCH} triplets (full batches of the same workload), torch-CPU oracle port, fp32"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(done, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1]: BPR MF d=64, ML-1M shape, batch 16384, Keras Adam",
+                   "note": "oracle port of the reference loop (TensorFlow/Keras cannot be installed here); not TensorFlow"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# product arm
+# ------------------------------------------------------------------------------------------------
+def product_arm(args):
+    import torch.distributed as dist
+    from binrec_b200 import hotpath as H
+    from binrec_b200.BPRModel import BPRNet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    users, items, U, I = make_workload()
+    n_batches = len(users) // BATCH                        # 61 full batches per epoch
+    # weak scaling: every rank trains a replica-sized batch stream of its own (rank-rotated batch order)
+    net = BPRNet(U, I, DIM, seed=42, learning_rate=1e-3, sparse_adam="keras", device=dev)
+    net.set_training_pairs(users, items)
+    net.sample_negatives(7, 0)
+    pr = net._pairs
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+    K, W = args.steps, args.warmup
+
+    def one_step(k, ev=None):
+        b = (k + rank * 7) % n_batches
+        sl = slice(b * BATCH, (b + 1) * BATCH)
+        if ev is not None:
+            ev[0].record()
+        loss = H.bpr_fwd_bwd(net.user, net.item, pr["u"][sl], pr["p"][sl], pr["n"][sl])
+        if ev is not None:
+            ev[1].record()
+        net.optimizer.apply([net.user, net.item])
+        if ev is not None:
+            ev[2].record()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- (1) device-resident value: K steps, L2 flushed between steps, CUDA events per step ------
+    for k in range(W):
+        flush.zero_(); one_step(k)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    sampler = ClockSampler(physical_gpu_index(local)); sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(K):
+        flush.zero_()
+        one_step(W + k, evs[k])
+    barrier()
+    wall = time.perf_counter() - wall0
+    step_ms = np.array([e[0].elapsed_time(e[2]) for e in evs])
+    fb_ms = np.array([e[0].elapsed_time(e[1]) for e in evs])
+    total_ms = float(step_ms.sum())
+
+    # ---- (2) same steps back to back (tables stay in L2, as in the real training loop) -----------
+    order = [(k + rank * 7) % n_batches for k in range(K)]
+    net.train_steps(order[:max(W, 3)], BATCH)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); net.train_steps(order, BATCH); e1.record()
+    barrier()
+    hot_ms = e0.elapsed_time(e1)
+
+    # ---- (3) end to end through the public API with HOST buffers --------------------------------
+    hu = torch.from_numpy(users[:n_batches * BATCH].copy()).pin_memory()
+    hp = torch.from_numpy(items[:n_batches * BATCH].copy()).pin_memory()
+    du = torch.empty(BATCH, dtype=torch.int32, device=dev); dp = torch.empty_like(du); dn = torch.empty_like(du)
+    hloss = torch.empty(K + W, dtype=torch.float32).pin_memory()
+
+    def e2e_step(k):
+        b = (k + rank * 7) % n_batches
+        sl = slice(b * BATCH, (b + 1) * BATCH)
+        du.copy_(hu[sl], non_blocking=True); dp.copy_(hp[sl], non_blocking=True)
+        H.philox_bpr_negatives(du, 7, 1, I, pr["indptr"], pr["sitems"], b * BATCH, out=dn)
+        loss = net.train_on_batch(du, dp, dn)
+        hloss[k:k + 1].copy_(loss, non_blocking=True)
+
+    for k in range(W):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for k in range(K):
+        e2e_step(W + k)
+    e1.record()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * e2e_wall)
+    clocks = sampler.stop()
+    assert np.isfinite(hloss[W:W + K].numpy()).all()
+
+    # ---- max over ranks ---------------------------------------------------------------------------
+    t = torch.tensor([total_ms, hot_ms, e2e_ms, float(fb_ms.mean())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, hot_ms, e2e_ms, fb_mean_ms = (float(x) for x in t.tolist())
+
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        value = world * K * BATCH / (total_ms * 1e-3)
+        achieved = BYTES_PER_TRIPLET * BATCH / (fb_mean_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[1]: BPR MF d=64, ML-1M shape (6040x3706, 1000209 positives), "
+                                   "1 Philox negative/positive, loss 1-sigmoid, exact Keras Adam(1e-3)",
+                       "batch": BATCH, "l2": "flushed between timed steps (256 MiB memset); step time = CUDA events "
+                                             "around the step's two kernels, flush excluded",
+                       "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "wall_s_timed_region": wall},
+            "value_hot_l2": world * K * BATCH / (hot_ms * 1e-3),
+            "roofline": {"bound": "hbm", "kernel": "bpr_vec<16,1,true> (fused gather+loss+scatter-add)",
+                         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": BYTES_PER_TRIPLET * BATCH,
+                         "avg_launch_ms": fb_mean_ms,
+                         "note": "tables (2.5 MB) are cold in L2 at launch (flush) but every row is re-read ~4x "
+                                 "from L2 within the launch; REDs resolve in L2"},
+            "e2e": {"value": world * K * BATCH / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": 2 * BATCH * 4, "d2h_bytes_per_step": 4,
+                    "note": "pinned host ids -> H2D, Philox negatives on device, fused step, loss D2H (async, one sync per K steps)"},
+            "gpu_launches": 2 * K,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            val, done, threads, dt = cpu_loop(users, items, U, I, steps=100000, warmup=3, time_budget_s=12.0)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{done} full batches of {BATCH} triplets in {dt:.1f} s, torch-CPU "
+                                              f"oracle port of the reference loop (not TensorFlow)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=600)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="brk", choices=["brk", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        product_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,226 @@
+"""BPR matrix factorisation -- drop-in mirror of the reference's src/models/BPRModel.py (class,
+method names and call shapes) and of the functional script src/models/bpr.py.
+
+What runs underneath: tables in HBM, Philox negative sampling (csrc/sampler.cu), one fused
+gather + loss + scatter-add kernel per batch (csrc/bpr.cu) and a fused Keras-Adam pass
+(csrc/optim.cu), all through the C ABI.
+
+Differences from the reference, stated once:
+  * the reference enumerates every (positive, non-interacted) pair on the host
+    (BPRModel.py:111-119) -- O(P*I), infeasible beyond toy sizes; `train` samples one
+    non-interacted negative per positive per epoch with the counter-based sampler instead
+    (extractPositivesNegatives is kept for small inputs and for tests);
+  * BPRModel.train in the reference calls compileModel with 3 arguments against a 4-argument
+    signature and stores the returned tuple as the model (BPRModel.py:107 vs :49,74); here the
+    signature is the 4-argument one and `self.model` is the model;
+  * ids are int32 (the reference casts them to float32, BPRModel.py:101-103).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import hotpath as H
+from . import synth
+from .RModel import RModel
+
+
+class BPRNet:
+    """The 'Keras model' of BPRModel.compileModel: inputs customerId_input / pProduct_input /
+    nProduct_input, output the per-row triplet loss 1 - sigmoid(x_ui - x_uj)."""
+
+    def __init__(self, numUser, numItem, numFactor, seed=42, learning_rate=1e-3, sparse_adam="keras",
+                 device=None):
+        self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+        self.numUser, self.numItem, self.numFactor = int(numUser), int(numItem), int(numFactor)
+        rng = np.random.Generator(np.random.Philox(key=seed))
+        # Keras Embedding default init U(-0.05, 0.05); user table first, then item (same draw order as the oracle)
+        lazy = sparse_adam == "lazy"   # the touched-row bitmask is only needed by the row-sparse optimizer
+        self.user = H.Table(torch.from_numpy(H.keras_embedding_init(self.numUser, self.numFactor, rng)).to(self.device),
+                            touched=lazy)
+        self.item = H.Table(torch.from_numpy(H.keras_embedding_init(self.numItem, self.numFactor, rng)).to(self.device),
+                            touched=lazy)
+        self.optimizer = H.Adam(learning_rate, sparse=sparse_adam, device=self.device)
+        self._pairs = None
+        self.history = {"loss": []}
+
+    # ---- data residency ------------------------------------------------------------------------
+    def set_training_pairs(self, users, items):
+        """Uploads the positive pairs once; they stay resident for all epochs."""
+        users = np.ascontiguousarray(users, dtype=np.int32); items = np.ascontiguousarray(items, dtype=np.int32)
+        indptr, sitems = synth.build_csr(users, items, self.numUser)
+        dev = self.device
+        self._pairs = dict(u=torch.from_numpy(users).to(dev), p=torch.from_numpy(items).to(dev),
+                           n=torch.empty(len(users), dtype=torch.int32, device=dev),
+                           indptr=torch.from_numpy(indptr).to(dev), sitems=torch.from_numpy(sitems).to(dev),
+                           total=len(users))
+
+    def sample_negatives(self, seed, epoch):
+        pr = self._pairs
+        H.philox_bpr_negatives(pr["u"], seed, epoch, self.numItem, pr["indptr"], pr["sitems"], 0, out=pr["n"])
+        return pr["n"]
+
+    def set_negatives(self, negs):
+        self._pairs["n"].copy_(torch.as_tensor(np.ascontiguousarray(negs, dtype=np.int32)))
+
+    # ---- training -------------------------------------------------------------------------------
+    def train_steps(self, batch_indices, batch_size, losses=None):
+        """Enqueues len(batch_indices) training steps over the resident triplets; returns the device
+        tensor of per-step mean losses (no host sync)."""
+        pr = self._pairs
+        k = len(batch_indices)
+        if losses is None:
+            losses = torch.empty(k, dtype=torch.float32, device=self.device)
+        idx = (C.c_int64 * k)(*[int(b) for b in batch_indices])
+        us, it = self.user.c_struct(), self.item.c_struct()
+        N.check(N.lib().brk_bpr_train_steps(N.ctx(self.device), C.byref(us), C.byref(it), N.ptr(pr["u"]),
+                                            N.ptr(pr["p"]), N.ptr(pr["n"]), pr["total"], batch_size, idx, k,
+                                            self.optimizer.h, 1 if self.optimizer.sparse == "lazy" else 0,
+                                            N.ptr(self.optimizer.state), N.ptr(losses), N.stream_ptr()),
+                "brk_bpr_train_steps")
+        return losses
+
+    def train_on_batch(self, u, p, n):
+        """One step on device id tensors; returns the device loss scalar."""
+        loss = H.bpr_fwd_bwd(self.user, self.item, u, p, n)
+        self.optimizer.apply([self.user, self.item])
+        return loss
+
+    def fit(self, X, y=None, batch_size=64, epochs=1, shuffle=True, sampler_seed=7, verbose=0, initial_epoch=0):
+        """Keras-like fit (BPRModel.py:109).  X: dict with 'customerId_input', 'pProduct_input' and
+        optionally 'nProduct_input'; without the latter a fresh Philox negative is drawn per positive
+        per epoch.  y is ignored exactly as identityLoss ignores it (BPRModel.py:125-126).
+        Batches are contiguous slices of the given row order; with shuffle=True the batch ORDER is
+        permuted per epoch (seeded), which is what tf.data .batch().shuffle() does in the reference's
+        other pipeline (NeuMFModel.py:117-121)."""
+        users = np.asarray(X['customerId_input']); pos = np.asarray(X['pProduct_input'])
+        self.set_training_pairs(users, pos)
+        fixed_neg = X.get('nProduct_input')
+        if fixed_neg is not None:
+            self.set_negatives(fixed_neg)
+        total = self._pairs["total"]
+        n_batches = (total + batch_size - 1) // batch_size
+        rng = np.random.Generator(np.random.Philox(key=sampler_seed + 1000003))
+        for e in range(initial_epoch, initial_epoch + epochs):
+            if fixed_neg is None:
+                self.sample_negatives(sampler_seed, e)
+            order = rng.permutation(n_batches) if shuffle else np.arange(n_batches)
+            losses = self.train_steps(order, batch_size)
+            # Keras reports the running mean of the per-batch losses
+            mean = float(losses.double().mean().item())
+            self.history["loss"].append(mean)
+            if verbose:
+                print(f"epoch {e + 1}: loss {mean:.6f}")
+        return self
+
+    # ---- inference ------------------------------------------------------------------------------
+    def predict(self, X):
+        """Model output = per-row triplet loss (BPRModel.py:63,144)."""
+        dev = self.device
+        u, p, n = (torch.as_tensor(np.ascontiguousarray(X[k], dtype=np.int32)).to(dev)
+                   for k in ('customerId_input', 'pProduct_input', 'nProduct_input'))
+        x = H.bpr_scores(self.user.w, self.item.w, u, p, n)
+        return (1.0 - torch.sigmoid(x)).unsqueeze(1)
+
+    def get_layer_weights(self, name):
+        return {"user_embedding": self.user.w, "item_embedding": self.item.w}[name]
+
+    def state_dict(self):
+        return {"user": self.user.w.cpu(), "item": self.item.w.cpu(), "user_m": self.user.m.cpu(),
+                "user_v": self.user.v.cpu(), "item_m": self.item.m.cpu(), "item_v": self.item.v.cpu(),
+                "opt_state": self.optimizer.state.cpu()}
+
+    def load_state_dict(self, sd):
+        self.user.w.copy_(sd["user"]); self.item.w.copy_(sd["item"])
+        self.user.m.copy_(sd["user_m"]); self.user.v.copy_(sd["user_v"])
+        self.item.m.copy_(sd["item_m"]); self.item.v.copy_(sd["item_v"])
+        self.optimizer.state.copy_(sd["opt_state"])
+
+
+def bpr_predict(model, user_id, item_ids, user_layer='user_embedding', item_layer='item_embedding'):
+    """bpr.py:122-133: scores of one user against item_ids (user vector times item matrix)."""
+    dev = model.device
+    item_ids = torch.as_tensor(np.ascontiguousarray(item_ids, dtype=np.int32)).to(dev)
+    rows = H.gather_rows(model.get_layer_weights(item_layer), item_ids)
+    uvec = model.get_layer_weights(user_layer)[int(user_id)]
+    return (rows * uvec).sum(-1)
+
+
+class BPRModel(RModel):
+    def __init__(self, workDir=None):
+        super().__init__('BPRModel', workDir)
+        self._trainDf = None
+        self._productIds: list = []
+        self._results: list = []
+        self.sparseAdam = "keras"
+
+    @property
+    def results(self) -> list:
+        return self._results
+
+    @results.setter
+    def results(self, value: list):
+        self._results = value
+
+    @property
+    def productIds(self) -> list:
+        return self._productIds
+
+    @productIds.setter
+    def productIds(self, value: list):
+        self._productIds = value
+
+    @property
+    def trainDf(self):
+        return self._trainDf
+
+    @trainDf.setter
+    def trainDf(self, value):
+        self._trainDf = value
+
+    def compileModel(self, distributedConfig, numUser: int, numItem: int, numFactor: int):
+        """Returns (model, strategy) like BPRModel.py:49,74; Adam(1e-3) as :70."""
+        self.model = BPRNet(numUser, numItem, numFactor, seed=self.seed, learning_rate=1e-3,
+                            sparse_adam=self.sparseAdam)
+        return self.model, None
+
+    def train(self, path, rowLimit, metricDict: dict = None, distributedConfig=None):
+        self.batchSize = 64                                              # BPRModel.py:77
+        numItem, numUser, (users, items) = self.readData(path, rowLimit)
+        (trU, trI), _ = synth.train_test_split(users, items, self.testSize, seed=self.splitSeed)
+        self.trainDf = (trU, trI)
+        customerIds = np.unique(trU)
+        self.productIds = np.unique(trI).tolist()
+        print('Having %s customers and %s products' % (len(customerIds), len(self._productIds)))
+        self.compileModel(distributedConfig, int(customerIds.max()) + 1, int(max(self.productIds)) + 1,
+                          self.numFactor)
+        X = {'customerId_input': trU, 'pProduct_input': trI}
+        self.model.fit(X, None, batch_size=self.batchSize, epochs=self.epochs, sampler_seed=self.samplerSeed)
+        return {'result': 'completed', 'metrics': [self.model.history["loss"][-1]]}
+
+    def extractPositivesNegatives(self, customerId) -> list:
+        """Exhaustive (positive, non-interacted) pairs of one customer -- BPRModel.py:111-119."""
+        trU, trI = self._trainDf
+        existing = trI[trU == customerId].tolist()
+        have = set(existing)
+        entries = []
+        for existingProductId in existing:
+            for productId in self._productIds:
+                if productId not in have:
+                    entries.append({'CUSTOMER_ID': customerId, 'pPRODUCT_ID': existingProductId,
+                                    'nPRODUCT_ID': productId})
+        return entries
+
+    def outShape(self, shapes):
+        return shapes[0]
+
+    def identityLoss(self, _, y_pred):
+        return torch.mean(y_pred)                                          # BPRModel.py:125-126
+
+    def bprTripletLoss(self, X):
+        """1 - sigmoid(<u,p> - <u,n>) on three [B,F] latent tensors -- BPRModel.py:128-144."""
+        userLatent, positiveItemLatent, negativeItemLatent = X
+        pos = (userLatent * positiveItemLatent).sum(-1, keepdim=True)
+        neg = (userLatent * negativeItemLatent).sum(-1, keepdim=True)
+        return 1.0 - torch.sigmoid(pos - neg)

@@ -1,0 +1,174 @@
+"""Base class of the recommender models -- the drop-in mirror of the reference's
+src/models/RModel.py (same attribute names, property setters, train() orchestration and return
+value), with the Keras model underneath replaced by device-resident tables driven through the
+C ABI.
+
+Deliberate differences from the reference (SURVEY.md section 0.5 lists its broken entry points):
+  * `train` works without a distributedConfig (the reference raises NameError at RModel.py:139
+    because `strategy` is unbound);
+  * data may be given as a CSV path with the reference's columns (NeuMFModel.py:21-27), or
+    directly as a (users, items) pair of int arrays / a dict with CUSTOMER_ID and PRODUCT_ID;
+  * splits, shuffles and samplers are seeded (the reference's are not reproducible);
+  * plotting / model_to_dot / SMB access are out of scope (not compute).
+"""
+import os
+
+import numpy as np
+
+from . import synth
+
+
+class LocalDataStore:
+    """Local-file half of the reference's DataStore.openFile (src/datasource/DataStore.py:12-16);
+    the SMB half needs credentials and a network and is out of scope."""
+
+    def openFile(self, path, mode="r"):
+        return open(path, mode)
+
+
+class RModel:
+    CUSTOMER_ID = 'CUSTOMER_ID'
+    PRODUCT_ID = 'PRODUCT_ID'
+    METRICS = ['mse', 'mae', 'binary_accuracy']
+
+    def __init__(self, moduleName, workDir=None):
+        self.modelName = moduleName
+        base = workDir or os.getcwd()
+        self.checkpointPath = os.path.join(base, 'checkpoints/{}/cp'.format(self.modelName))
+        self.modelProducts = os.path.join(base, 'checkpoints/{}/modelData/products'.format(self.modelName))
+        self.modelUsers = os.path.join(base, 'checkpoints/{}/modelData/users'.format(self.modelName))
+
+        self.numFactor: int = 32          # RModel.py:35
+        self._epochs: int = 10            # RModel.py:36
+        self._batchSize: int = 1024       # RModel.py:37
+        self._validationSteps: int = 20   # RModel.py:38
+        self._testSize: float = 0.2       # RModel.py:39
+        self._model = None
+        self._dataStore = LocalDataStore()
+        self.seed = 42                    # weights (bpr.py:21 uses SEED = 42)
+        self.samplerSeed = 7
+        self.splitSeed = synth.DATA_SEED + 1
+        self.history = None
+
+    # -- properties, as RModel.py:45-91 ------------------------------------------------------
+    @property
+    def testSize(self) -> float:
+        return self._testSize
+
+    @testSize.setter
+    def testSize(self, value: float):
+        self._testSize = value
+
+    @property
+    def validationSteps(self) -> int:
+        return self._validationSteps
+
+    @validationSteps.setter
+    def validationSteps(self, value):
+        self._validationSteps = value
+
+    @property
+    def epochs(self) -> int:
+        return self._epochs
+
+    @epochs.setter
+    def epochs(self, value: int):
+        self._epochs = value
+
+    @property
+    def batchSize(self) -> int:
+        return self._batchSize
+
+    @batchSize.setter
+    def batchSize(self, value: int):
+        self._batchSize = value
+
+    @property
+    def dataStore(self):
+        return self._dataStore
+
+    @dataStore.setter
+    def dataStore(self, value):
+        pass                               # read-only, as in the reference (RModel.py:82-84)
+
+    @property
+    def model(self):
+        return self._model
+
+    @model.setter
+    def model(self, value):
+        self._model = value
+
+    # -- to be specialised ---------------------------------------------------------------------
+    def compileModel(self, distributedConfig, numUser: int, numItem: int, numFactor: int):
+        print('placeholder')
+        return None
+
+    def bootstrapDataset(self, df, negRatio=3., batchSize=128, shuffle=True):
+        return None
+
+    def prepareToTrain(self, distributedConfig, path, rowLimit):
+        return None
+
+    def predictForUser(self, customerId, numberOfItem=5):
+        return None
+
+    def getPredictableUsers(self) -> list:
+        return []
+
+    def readyToTrain(self):
+        return True
+
+    def getNumberOfWorkers(self, distributedConfig) -> int:
+        """Reference: len(TF_CONFIG['cluster']['worker']) (RModel.py:201-202).  Here a
+        distributedConfig may be that dict or None; with torch.distributed initialised the world
+        size wins."""
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                return dist.get_world_size()
+        except Exception:
+            pass
+        if distributedConfig is None:
+            return 1
+        return len(distributedConfig['cluster']['worker'])
+
+    # -- data --------------------------------------------------------------------------------
+    def readData(self, path, rowLimit):
+        """Returns (numItem, numUser, (users, items)) -- NeuMFModel.py:21-27: the table sizes are
+        max id + 1."""
+        users, items = self._loadPairs(path, rowLimit)
+        numUser = int(users.max()) + 1
+        numItem = int(items.max()) + 1
+        return numItem, numUser, (users, items)
+
+    def _loadPairs(self, path, rowLimit):
+        if isinstance(path, dict):
+            users, items = path[self.CUSTOMER_ID], path[self.PRODUCT_ID]
+        elif isinstance(path, (tuple, list)) and len(path) == 2:
+            users, items = path
+        else:
+            import pandas as pd
+            with self.dataStore.openFile(path=path, mode='r') as f:
+                df = pd.read_csv(f, nrows=rowLimit)
+            users, items = df[self.CUSTOMER_ID].values, df[self.PRODUCT_ID].values
+        users = np.ascontiguousarray(np.asarray(users)[:rowLimit], dtype=np.int32)
+        items = np.ascontiguousarray(np.asarray(items)[:rowLimit], dtype=np.int32)
+        if len(users) != len(items) or len(users) == 0:
+            raise ValueError("need equally long, non-empty CUSTOMER_ID / PRODUCT_ID columns")
+        if users.min() < 0 or items.min() < 0:
+            raise ValueError("ids must be non-negative")
+        return users, items
+
+    # -- checkpoint (RModel.py:139,172-196) ----------------------------------------------------
+    def isMaster(self, taskType, taskId) -> bool:
+        return taskType is None or taskType == 'chief' or (taskType == 'worker' and taskId == 0)
+
+    def saveCheckPoint(self):
+        import torch
+        os.makedirs(os.path.dirname(self.checkpointPath), exist_ok=True)
+        torch.save(self.model.state_dict(), self.checkpointPath)
+
+    def restoreFromLatestCheckPoint(self):
+        import torch
+        self.model.load_state_dict(torch.load(self.checkpointPath, map_location="cpu"))

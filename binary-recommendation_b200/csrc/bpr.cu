@@ -10,11 +10,14 @@ namespace {
 
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ void mark_touched(uint32_t* touched, int64_t row) {
-  if (touched == nullptr) return;
+// Touched-row bitmask: the word is read early (plain load, issued with the row loads; a stale
+// value only costs a redundant RED) and the bit is set with a fire-and-forget RED.OR.
+__device__ __forceinline__ uint32_t peek_touched(const uint32_t* touched, int64_t row) {
+  return touched ? __ldg(touched + (row >> 5)) : 0xffffffffu;
+}
+__device__ __forceinline__ void mark_touched(uint32_t* touched, int64_t row, uint32_t seen) {
   const uint32_t bit = 1u << (row & 31);
-  uint32_t* wptr = touched + (row >> 5);
-  if (!(*reinterpret_cast<volatile uint32_t*>(wptr) & bit)) atomicOr(wptr, bit);
+  if (!(seen & bit)) atomicOr(touched + (row >> 5), bit);
 }
 
 // Adds this block's partial loss; the last block to arrive publishes the mean and resets the slot.
@@ -57,6 +60,8 @@ bpr_vec(const float* __restrict__ Wu, const float* __restrict__ Wi, float* __res
     const bool valid = b < batch;
     int64_t ru = 0, rp = 0, rn = 0;
     if (valid) { ru = __ldg(uid + b); rp = __ldg(pid + b); rn = __ldg(nid + b); }
+    uint32_t su = 0xffffffffu, sp = 0xffffffffu, sn = 0xffffffffu;
+    if (TRAIN && valid && lane_in == 0) { su = peek_touched(Tu, ru); sp = peek_touched(Ti, rp); sn = peek_touched(Ti, rn); }
     float4 u[NCH], p[NCH], n[NCH];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) {
@@ -99,7 +104,7 @@ bpr_vec(const float* __restrict__ Wu, const float* __restrict__ Wi, float* __res
             red_add_f4(Gi + (rn * d4 + c) * 4, dn);
           }
         }
-        if (lane_in == 0) { mark_touched(Tu, ru); mark_touched(Ti, rp); mark_touched(Ti, rn); }
+        if (lane_in == 0) { mark_touched(Tu, ru, su); mark_touched(Ti, rp, sp); mark_touched(Ti, rn, sn); }
       }
     }
   }
@@ -120,6 +125,8 @@ bpr_scalar(const float* __restrict__ Wu, const float* __restrict__ Wi, float* __
   float loss_local = 0.f;
   for (int64_t b = warp; b < batch; b += n_warps) {
     const int64_t ru = __ldg(uid + b), rp = __ldg(pid + b), rn = __ldg(nid + b);
+    uint32_t su = 0xffffffffu, sp = 0xffffffffu, sn = 0xffffffffu;
+    if (TRAIN && lane == 0) { su = peek_touched(Tu, ru); sp = peek_touched(Ti, rp); sn = peek_touched(Ti, rn); }
     float dot = 0.f;
     for (int c = lane; c < d; c += 32)
       dot = fmaf(__ldg(Wu + ru * d + c), __ldg(Wi + rp * d + c) - __ldg(Wi + rn * d + c), dot);
@@ -136,7 +143,7 @@ bpr_scalar(const float* __restrict__ Wu, const float* __restrict__ Wi, float* __
         atomicAdd(Gi + rp * d + c, g * uu);
         atomicAdd(Gi + rn * d + c, -g * uu);
       }
-      if (lane == 0) { mark_touched(Tu, ru); mark_touched(Ti, rp); mark_touched(Ti, rn); }
+      if (lane == 0) { mark_touched(Tu, ru, su); mark_touched(Ti, rp, sp); mark_touched(Ti, rn, sn); }
     }
   }
   if constexpr (TRAIN) finish_loss(double(loss_local), double(inv_batch), loss_acc, ticket, out);
@@ -202,4 +209,34 @@ extern "C" int brk_bpr_scores(brk_ctx* ctx, const float* user_w, const float* it
   BRK_REQUIRE(d > 0 && batch > 0, BRK_E_ARG, "brk_bpr_scores: d=%d batch=%lld", d, (long long)batch);
   return launch_bpr<false>(ctx, user_w, item_w, nullptr, nullptr, nullptr, nullptr, d, u, p, n, batch, x_out,
                            (cudaStream_t)stream);
+}
+
+// Multi-step driver: one C call enqueues n_steps x (fused fwd/bwd + optimizer) so that the host
+// cost per step is two kernel launches and nothing else (model.fit's inner loop,
+// /root/reference/src/models/BPRModel.py:109).  batch_index_host[k] selects which batch of the
+// device-resident triplet arrays step k consumes (Keras shuffles batches per epoch).
+extern "C" int brk_bpr_train_steps(brk_ctx* ctx, const brk_table* user, const brk_table* item,
+                                   const int32_t* u, const int32_t* p, const int32_t* n, int64_t total,
+                                   int64_t batch, const int64_t* batch_index_host, int32_t n_steps,
+                                   brk_adam_hyper h, int32_t lazy_adam, int64_t* step_dev, float* losses,
+                                   void* stream) {
+  BRK_REQUIRE(ctx && user && item && u && p && n && batch_index_host && step_dev, BRK_E_ARG,
+              "brk_bpr_train_steps: null argument");
+  BRK_REQUIRE(total > 0 && batch > 0 && n_steps >= 0, BRK_E_ARG, "brk_bpr_train_steps: total=%lld batch=%lld",
+              (long long)total, (long long)batch);
+  const int64_t n_batches = (total + batch - 1) / batch;
+  brk_table tabs[2] = {*user, *item};
+  for (int k = 0; k < n_steps; ++k) {
+    const int64_t bi = batch_index_host[k];
+    BRK_REQUIRE(bi >= 0 && bi < n_batches, BRK_E_ARG, "brk_bpr_train_steps: batch index %lld of %lld",
+                (long long)bi, (long long)n_batches);
+    const int64_t off = bi * batch;
+    const int64_t cnt = (off + batch <= total) ? batch : total - off;
+    int rc = brk_bpr_fwd_bwd(ctx, user, item, u + off, p + off, n + off, cnt, losses ? losses + k : nullptr, stream);
+    if (rc) return rc;
+    rc = lazy_adam ? brk_adam_rows(ctx, tabs, 2, h, step_dev, 1, stream)
+                   : brk_adam_dense_keras(ctx, tabs, 2, h, step_dev, 1, stream);
+    if (rc) return rc;
+  }
+  return 0;
 }

@@ -60,6 +60,17 @@ scatter_add_rows_vec(float* __restrict__ acc, int d4, const int32_t* __restrict_
     int64_t row[kRowsPerIter];
 #pragma unroll
     for (int r = 0; r < kRowsPerIter; ++r) row[r] = (b0 + r < n) ? int64_t(__ldg(ids + b0 + r)) : -1;
+    if (touched != nullptr && lane_in == 0) {
+      // early plain read of the bitmask word; the bit is set with a fire-and-forget RED.OR
+      uint32_t seen[kRowsPerIter];
+#pragma unroll
+      for (int r = 0; r < kRowsPerIter; ++r) seen[r] = row[r] >= 0 ? __ldg(touched + (row[r] >> 5)) : 0xffffffffu;
+#pragma unroll
+      for (int r = 0; r < kRowsPerIter; ++r) {
+        const uint32_t bit = 1u << (row[r] & 31);
+        if (row[r] >= 0 && !(seen[r] & bit)) atomicOr(touched + (row[r] >> 5), bit);
+      }
+    }
     for (int c = lane_in; c < d4; c += LPR) {
       float4 v[kRowsPerIter];
 #pragma unroll
@@ -68,15 +79,6 @@ scatter_add_rows_vec(float* __restrict__ acc, int d4, const int32_t* __restrict_
 #pragma unroll
       for (int r = 0; r < kRowsPerIter; ++r)
         if (row[r] >= 0) red_add_f4(acc + (row[r] * d4 + c) * 4, v[r]);
-    }
-    if (touched != nullptr && lane_in == 0) {
-#pragma unroll
-      for (int r = 0; r < kRowsPerIter; ++r)
-        if (row[r] >= 0) {
-          const uint32_t bit = 1u << (row[r] & 31);
-          uint32_t* wptr = touched + (row[r] >> 5);
-          if (!(*reinterpret_cast<volatile uint32_t*>(wptr) & bit)) atomicOr(wptr, bit);
-        }
     }
   }
 }

@@ -58,23 +58,32 @@ __device__ __forceinline__ void apply1(const Op& op, float* w, float* m, float* 
   g[i] = 0.f;
 }
 
-__device__ __forceinline__ float adam_alpha(const brk_adam_hyper& h, const int64_t* step_dev) {
+// Optimizer state in device memory (see brk_b200.h): state[0] = t as int64, state[1] = beta1^t and
+// state[2] = beta2^t as doubles (running products; no pow() on the device).
+__device__ __forceinline__ float adam_alpha(const brk_adam_hyper& h, const int64_t* state) {
   __shared__ float s_alpha;
   if (threadIdx.x == 0) {
-    const double t = double(*step_dev + 1);
-    s_alpha = float(double(h.lr) * sqrt(1.0 - pow(double(h.beta2), t)) / (1.0 - pow(double(h.beta1), t)));
+    const double* pw = reinterpret_cast<const double*>(state);
+    const double p1 = pw[1] * double(h.beta1), p2 = pw[2] * double(h.beta2);
+    s_alpha = float(double(h.lr) * sqrt(1.0 - p2) / (1.0 - p1));
   }
   __syncthreads();
   return s_alpha;
 }
 
-__device__ __forceinline__ void advance_step_last_block(int64_t* step_dev, unsigned int* ticket, int advance) {
+__device__ __forceinline__ void advance_step_last_block(int64_t* state, const brk_adam_hyper& h,
+                                                        unsigned int* ticket, int advance) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned int t = atomicAdd(ticket, 1u);
     if (t == gridDim.x - 1) {
-      if (advance) *step_dev += 1;
+      if (advance) {
+        double* pw = reinterpret_cast<double*>(state);
+        state[0] += 1;
+        pw[1] *= double(h.beta1);
+        pw[2] *= double(h.beta2);
+      }
       *ticket = 0u;
       __threadfence();
     }
@@ -154,7 +163,7 @@ adam_dense_kernel(TabList tl, brk_adam_hyper h, int64_t* step_dev, unsigned int*
   op.alpha = adam_alpha(h, step_dev);
   op.b1 = h.beta1; op.b2 = h.beta2; op.omb1 = 1.0f - h.beta1; op.omb2 = 1.0f - h.beta2; op.eps = h.eps;
   dense_pass<AdamOp, true>(tl, op);
-  advance_step_last_block(step_dev, ticket, advance);
+  advance_step_last_block(step_dev, h, ticket, advance);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -163,7 +172,7 @@ adam_rows_kernel(TabList tl, brk_adam_hyper h, int64_t* step_dev, unsigned int* 
   op.alpha = adam_alpha(h, step_dev);
   op.b1 = h.beta1; op.b2 = h.beta2; op.omb1 = 1.0f - h.beta1; op.omb2 = 1.0f - h.beta2; op.eps = h.eps;
   rows_pass<AdamOp, true>(tl, op);
-  advance_step_last_block(step_dev, ticket, advance);
+  advance_step_last_block(step_dev, h, ticket, advance);
 }
 
 __global__ void __launch_bounds__(kThreads) adagrad_rows_kernel(TabList tl, float lr, float eps) {

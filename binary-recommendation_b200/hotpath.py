@@ -129,7 +129,14 @@ class Adam:
             raise ValueError("sparse must be 'keras' or 'lazy'")
         self.h = N.brk_adam_hyper(learning_rate, beta_1, beta_2, epsilon)
         self.sparse = sparse
-        self.step = torch.zeros(1, dtype=torch.int64, device=device or "cuda")
+        # device state: [t (int64), beta1^t (double), beta2^t (double)] -- see brk_b200.h
+        state = np.zeros(3, dtype=np.int64)
+        state[1:] = np.array([1.0, 1.0], dtype=np.float64).view(np.int64)
+        self.state = torch.from_numpy(state).to(device or "cuda")
+
+    @property
+    def step(self):
+        return self.state[0:1]
 
     def apply(self, tables, dense=()):
         """One optimizer step over embedding `tables` and `dense` parameters (always dense)."""
@@ -137,13 +144,13 @@ class Adam:
         tables, dense = list(tables), list(dense)
         if self.sparse == "keras":
             allp = tables + dense
-            N.check(lib.brk_adam_dense_keras(ctx, _pack(allp), len(allp), self.h, N.ptr(self.step), 1, st),
+            N.check(lib.brk_adam_dense_keras(ctx, _pack(allp), len(allp), self.h, N.ptr(self.state), 1, st),
                     "brk_adam_dense_keras")
         else:
             if dense:
-                N.check(lib.brk_adam_dense_keras(ctx, _pack(dense), len(dense), self.h, N.ptr(self.step), 0, st),
+                N.check(lib.brk_adam_dense_keras(ctx, _pack(dense), len(dense), self.h, N.ptr(self.state), 0, st),
                         "brk_adam_dense_keras")
-            N.check(lib.brk_adam_rows(ctx, _pack(tables), len(tables), self.h, N.ptr(self.step), 1, st),
+            N.check(lib.brk_adam_rows(ctx, _pack(tables), len(tables), self.h, N.ptr(self.state), 1, st),
                     "brk_adam_rows")
 
 

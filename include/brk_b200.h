@@ -107,15 +107,26 @@ int brk_philox4x32_10(brk_ctx* ctx, const uint32_t* ctr, int64_t n, uint32_t key
 int brk_bpr_fwd_bwd(brk_ctx* ctx, const brk_table* user, const brk_table* item,
                     const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch,
                     float* loss_out, void* stream);
+/* n_steps x (brk_bpr_fwd_bwd + Adam) enqueued by one call: the inner loop of model.fit
+ * (src/models/BPRModel.py:109, src/models/bpr.py:220-223).  u/p/n are device arrays of `total`
+ * triplets cut into batches of `batch`; batch_index_host[k] (HOST array) names the batch step k
+ * consumes; losses (device, [n_steps], may be NULL) receives each step's mean loss.
+ * lazy_adam 0: exact Keras Adam (dense pass); 1: row-sparse lazy Adam. */
+int brk_bpr_train_steps(brk_ctx* ctx, const brk_table* user, const brk_table* item,
+                        const int32_t* u, const int32_t* p, const int32_t* n, int64_t total,
+                        int64_t batch, const int64_t* batch_index_host, int32_t n_steps,
+                        brk_adam_hyper h, int32_t lazy_adam, int64_t* step_dev, float* losses,
+                        void* stream);
 /* Forward only: x_out[b] = <u,p> - <u,n> (scores for evaluation, bpr.py:122-133). */
 int brk_bpr_scores(brk_ctx* ctx, const float* user_w, const float* item_w, int32_t d,
                    const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch,
                    float* x_out, void* stream);
 
 /* ---- K6: optimizers -----------------------------------------------------------------------
- * step_dev: device int64 holding the number of completed optimizer steps t; the kernels use
- * t+1 and, when advance_step != 0, the last block increments it (so a whole epoch can be
- * captured in one CUDA graph).
+ * step_dev: device optimizer state of three 8-byte words: [0] int64 t = completed steps,
+ * [1] double beta1^t, [2] double beta2^t (initialise to 0, 1.0, 1.0).  The kernels use step t+1
+ * and, when advance_step != 0, the last block advances the state (so a whole epoch can be
+ * enqueued or captured in a CUDA graph without host involvement).
  * brk_adam_dense_keras: exact Keras Adam (src/models/NeuMFModel.py:89, BPRModel.py:70,
  *   bpr.py:201, trainers/NFC_plain.py:153): every element of every listed table moves,
  *   alpha_t = lr*sqrt(1-b2^t)/(1-b1^t), w -= alpha_t*m/(sqrt(v)+eps); g is zeroed, touched cleared.

@@ -1,0 +1,127 @@
+"""Kernel micro-benchmarks (CUDA events, L2 flushed between iterations) used to fill the roofline
+tables in DESIGN.md.  Run on the GPU box:  python profiles/microbench.py [section ...]
+Sections: gather scatter bpr adam."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+from binrec_b200 import hotpath as H
+
+dev = torch.device("cuda:0")
+torch.cuda.set_device(0)
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+flush = torch.empty(256 << 18, dtype=torch.float32, device=dev)
+
+
+def timeit(fn, iters=20, warm=3, do_flush=True):
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if do_flush:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)) * 1e-3
+
+
+def report(name, secs, nbytes):
+    gbs = nbytes / secs / 1e9
+    print(f"{name:64s} {secs*1e6:9.1f} us  {gbs:8.1f} GB/s  {gbs/PEAK:6.3f} of measured HBM peak", flush=True)
+
+
+def ids_of(kind, rows, n, g):
+    if kind == "uniform":
+        return torch.randint(0, rows, (n,), generator=g, device=dev, dtype=torch.int32)
+    r = torch.rand(n, generator=g, device=dev)
+    return (rows * r ** 3).to(torch.int32).clamp_(0, rows - 1)
+
+
+def sec_gather():
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    for rows, d, n in ((20_000_000, 64, 4_000_000), (2_000_000, 64, 4_000_000), (20_000_000, 32, 4_000_000),
+                       (6040, 64, 1_000_000)):
+        table = torch.empty(rows, d, device=dev).uniform_(-1, 1)
+        out = torch.empty(n, d, device=dev)
+        for kind in ("uniform", "skew"):
+            ids = ids_of(kind, rows, n, g)
+            s = timeit(lambda: H.gather_rows(table, ids, out))
+            report(f"gather_rows rows={rows} d={d} n={n} ids={kind}", s, n * (2 * 4 * d + 4))
+        del table, out
+
+
+def sec_scatter():
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    for rows, d, n in ((20_000_000, 64, 4_000_000), (2_000_000, 64, 4_000_000), (6040, 64, 1_000_000),
+                       (6040, 64, 16384)):
+        acc = torch.zeros(rows, d, device=dev)
+        vals = torch.empty(n, d, device=dev).uniform_(-1, 1)
+        for kind in ("uniform", "skew"):
+            ids = ids_of(kind, rows, n, g)
+            s = timeit(lambda: H.scatter_add_rows(acc, ids, vals))
+            report(f"scatter_add_rows rows={rows} d={d} n={n} ids={kind}", s, n * (3 * 4 * d + 4))
+        del acc, vals
+
+
+def sec_bpr():
+    g = torch.Generator(device=dev); g.manual_seed(2)
+    U, I, d = 6040, 3706, 64
+    for B in (16384, 65536, 1_000_000):
+        for touched in (True, False):
+            for kind in ("uniform", "skew"):
+                user = H.Table(torch.empty(U, d, device=dev).uniform_(-.05, .05), touched=touched)
+                item = H.Table(torch.empty(I, d, device=dev).uniform_(-.05, .05), touched=touched)
+                u, p, n = ids_of(kind, U, B, g), ids_of(kind, I, B, g), ids_of("uniform", I, B, g)
+                loss = torch.empty(1, device=dev)
+                s = timeit(lambda: H.bpr_fwd_bwd(user, item, u, p, n, loss))
+                report(f"bpr_fwd_bwd ML-1M tables B={B} touched={touched} ids={kind}", s, B * 1536)
+    U, I = 20_000_000, 2_000_000
+    user = H.Table(torch.empty(U, d, device=dev).uniform_(-.05, .05), slots=0)
+    item = H.Table(torch.empty(I, d, device=dev).uniform_(-.05, .05), slots=0)
+    for B in (65536, 1_000_000):
+        for kind in ("uniform", "skew"):
+            u, p, n = ids_of(kind, U, B, g), ids_of(kind, I, B, g), ids_of("uniform", I, B, g)
+            loss = torch.empty(1, device=dev)
+            s = timeit(lambda: H.bpr_fwd_bwd(user, item, u, p, n, loss))
+            report(f"bpr_fwd_bwd 20M x 2M tables B={B} ids={kind}", s, B * 1536)
+
+
+def sec_adam():
+    for rows, d in ((6040 + 3706, 64), (2_000_000, 64), (20_000_000, 64)):
+        t = H.Table(torch.empty(rows, d, device=dev).uniform_(-.05, .05))
+        opt = H.Adam(1e-3, device=dev)
+        s = timeit(lambda: opt.apply([t]))
+        report(f"adam_dense_keras rows={rows} d={d}", s, rows * d * 32)
+        g = torch.Generator(device=dev); g.manual_seed(3)
+        lazy = H.Adam(1e-3, sparse="lazy", device=dev)
+        for n in (65536, 1_000_000):
+            ids = torch.randint(0, rows, (n,), generator=g, device=dev, dtype=torch.int32)
+            vals = torch.ones(n, d, device=dev)
+            uniq = int(torch.unique(ids).numel())
+            def run():
+                H.scatter_add_rows(t.g, ids, vals, t.touched)
+                lazy.apply([t])
+            def only_scatter():
+                H.scatter_add_rows(t.g, ids, vals, t.touched)
+            s_both = timeit(run)
+            t.g.zero_(); t.touched.zero_()
+            s_sc = timeit(only_scatter)
+            t.g.zero_(); t.touched.zero_()
+            report(f"adam_rows rows={rows} d={d} touched={uniq} (scatter time subtracted)", max(s_both - s_sc, 1e-9),
+                   uniq * d * 32 + rows // 8)
+        del t
+
+
+if __name__ == "__main__":
+    secs = sys.argv[1:] or ["gather", "scatter", "bpr", "adam"]
+    print(torch.cuda.get_device_name(0), "HBM peak (measured)", PEAK, "GB/s")
+    for s in secs:
+        globals()["sec_" + s]()
