@@ -49,6 +49,11 @@ SIGNATURES = {
     "brk_adam_rows": (C.c_int, [_P, C.POINTER(brk_table), _I32, brk_adam_hyper, _P, _I32, _P]),
     "brk_adagrad_rows": (C.c_int, [_P, C.POINTER(brk_table), _I32, _F32, _F32, _P]),
     "brk_adagrad_dense": (C.c_int, [_P, C.POINTER(brk_table), _I32, _F32, _F32, _P]),
+    "brk_bf16_padded_dim": (C.c_int32, [_I32]),
+    "brk_rows_to_bf16": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _P]),
+    "brk_score_topk_workspace_bytes": (C.c_int64, [_P, _I64, _I64, _I32]),
+    "brk_score_topk_bf16": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _I64, _P]),
+    "brk_topk_merge": (C.c_int, [_P, _P, _P, _I32, _I64, _I32, _P, _P, _P]),
 }
 
 _lib = None

@@ -208,3 +208,70 @@ def keras_embedding_init(rows, dim, rng):
     """Keras Embedding default initializer U(-0.05, 0.05), generated on the host so that the
     oracle and the device start from identical weights."""
     return rng.uniform(-0.05, 0.05, size=(rows, dim)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
+# K7 / K8: full-catalog scoring + top-K (tcgen05 GEMM with a top-K epilogue)
+# ----------------------------------------------------------------------------------------------
+def rows_to_bf16(x):
+    """fp32 [rows, d] -> bf16 [rows, dpad] (zero padded to a multiple of 64 columns)."""
+    x = _f32(x, "x")
+    rows, d = x.shape
+    dpad = N.lib().brk_bf16_padded_dim(d)
+    out = torch.empty((rows, dpad), dtype=torch.bfloat16, device=x.device)
+    N.check(N.lib().brk_rows_to_bf16(N.ctx(x.device), N.ptr(x), rows, d, N.ptr(out), dpad, N.stream_ptr()),
+            "brk_rows_to_bf16")
+    return out
+
+
+class BruteForceIndex:
+    """tfrs.layers.factorized_top_k.BruteForce as the reference uses it (trainers/twoTower.py:64-69,
+    src/origin_models/svd/SVD.py:424-432): index(candidates, identifiers) once, then call(queries)
+    -> (scores [U,k], identifiers [U,k]) sorted by descending score, ties -> lower candidate index."""
+
+    def __init__(self, k=10):
+        self.k = int(k)
+        self._c = None
+        self._identifiers = None
+        self.id_offset = 0
+
+    def index(self, candidates, identifiers=None, id_offset=0):
+        self.num_candidates, self.dim = candidates.shape
+        self._c = rows_to_bf16(candidates)
+        self._identifiers = identifiers
+        self.id_offset = int(id_offset)
+        return self
+
+    def __call__(self, queries, k=None):
+        if self._c is None:
+            raise RuntimeError("BruteForceIndex: call index(candidates) first")
+        k = min(int(k or self.k), self.num_candidates)
+        if queries.shape[1] != self.dim:
+            raise ValueError(f"query dim {queries.shape[1]} != candidate dim {self.dim}")
+        U = queries.shape[0]
+        dev = queries.device
+        vals = torch.empty((U, k), dtype=torch.float32, device=dev)
+        ids = torch.empty((U, k), dtype=torch.int32, device=dev)
+        if U == 0:
+            return vals, ids
+        q = rows_to_bf16(queries)
+        lib, ctx = N.lib(), N.ctx(dev)
+        ws_bytes = lib.brk_score_topk_workspace_bytes(ctx, U, self.num_candidates, k)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        N.check(lib.brk_score_topk_bf16(ctx, N.ptr(q), U, N.ptr(self._c), self.num_candidates, q.shape[1], k,
+                                        self.id_offset, N.ptr(vals), N.ptr(ids), N.ptr(ws), ws_bytes,
+                                        N.stream_ptr()), "brk_score_topk_bf16")
+        if self._identifiers is not None:
+            return vals, self._identifiers[(ids - self.id_offset).long()]
+        return vals, ids
+
+
+def topk_merge(part_vals, part_ids):
+    """Merges [S, U, k] partial lists (global ids) into [U, k]: score desc, id asc."""
+    part_vals = _f32(part_vals, "part_vals"); part_ids = _i32(part_ids, "part_ids")
+    S, U, k = part_vals.shape
+    vals = torch.empty((U, k), dtype=torch.float32, device=part_vals.device)
+    ids = torch.empty((U, k), dtype=torch.int32, device=part_vals.device)
+    N.check(N.lib().brk_topk_merge(N.ctx(part_vals.device), N.ptr(part_vals), N.ptr(part_ids), S, U, k,
+                                   N.ptr(vals), N.ptr(ids), N.stream_ptr()), "brk_topk_merge")
+    return vals, ids

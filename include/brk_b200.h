@@ -143,6 +143,29 @@ int brk_adagrad_rows(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, float 
 int brk_adagrad_dense(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, float lr, float eps,
                       void* stream);
 
+/* ---- K7/K8: full-catalog scoring + top-K ------------------------------------------------------
+ * Stands in for tfrs.layers.factorized_top_k.BruteForce(k).index(candidates) + call(queries)
+ * (trainers/twoTower.py:64-69,60-62,229-230; src/origin_models/svd/SVD.py:424-432), for
+ * bpr_predict (src/models/bpr.py:122-133) and for the streaming __topk of
+ * trainers/topKmetrics.py:51-72.  scores = Q C^T (bf16 operands, fp32 accumulation on tcgen05);
+ * per query row the k best (score, item id) come back sorted by descending score, ties -> lower
+ * item id (tf.math.top_k's rule, and __topk's).  Scores are never written to HBM.
+ *   brk_bf16_padded_dim(d)      row width of the bf16 operand copies (d rounded up to 64)
+ *   brk_rows_to_bf16            fp32 [rows,d] -> bf16 [rows,dpad], zero padded (the "index" step)
+ *   brk_score_topk_bf16         out_vals/out_ids [U,k]; id_offset is added to every item id (item-
+ *                               range shards); workspace: brk_score_topk_workspace_bytes(...) bytes
+ *   brk_topk_merge              merges n_parts partial lists [n_parts,U,k] (score desc, id asc) --
+ *                               the result is identical to an unsharded scan. */
+int32_t brk_bf16_padded_dim(int32_t d);
+int brk_rows_to_bf16(brk_ctx* ctx, const float* src, int64_t rows, int32_t d, uint16_t* dst,
+                     int32_t dpad, void* stream);
+int64_t brk_score_topk_workspace_bytes(brk_ctx* ctx, int64_t U, int64_t I, int32_t k);
+int brk_score_topk_bf16(brk_ctx* ctx, const uint16_t* q_bf16, int64_t U, const uint16_t* c_bf16,
+                        int64_t I, int32_t dpad, int32_t k, int32_t id_offset, float* out_vals,
+                        int32_t* out_ids, void* workspace, int64_t workspace_bytes, void* stream);
+int brk_topk_merge(brk_ctx* ctx, const float* part_vals, const int32_t* part_ids, int32_t n_parts,
+                   int64_t U, int32_t k, float* out_vals, int32_t* out_ids, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
