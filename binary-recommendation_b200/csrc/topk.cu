@@ -10,21 +10,26 @@
 // only on a hit runs the exact sorted insertion.  Tie rule: strict '>' while items stream in
 // ascending id, i.e. equal scores keep the lower item id (tf.math.top_k / the reference's __topk).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected
-// lane), warps 2-5 = epilogue (warp w reads TMEM lanes 32*(w%4)...).  Two 256-column accumulators
-// double-buffer MMA against epilogue.  Algorithmic traffic: 2*dpad B per user + 2*dpad B per item
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected
+// lane), warps 2-9 = epilogue: warp w reads TMEM lanes 32*(w%4)..., and the two warps that share a
+// lane quadrant each take one 128-column half of every tile (two partial lists per row, merged by
+// topk_merge_kernel).  tcgen05.ld is double-buffered against the compare work.  Two 256-column
+// accumulators double-buffer MMA against epilogue.  Algorithmic traffic: 2*dpad B per user + 2*dpad B per item
 // per m-tile pass (L2-resident item index) + 8k B of results per user.
 #include "common.cuh"
 #include "tc.cuh"
 #include <cuda_bf16.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace {
 
 constexpr int kBM = 128;          // users per CTA (TMEM lanes)
 constexpr int kBN = 256;          // items per MMA tile (TMEM columns per accumulator)
 constexpr int kKBlock = 64;       // bf16 elements per 128-byte swizzle row
-constexpr int kThreadsTopk = 192;
+constexpr int kThreadsTopk = 320;
+constexpr int kEpiWarps = 8;
+constexpr int kHalves = 2;        // column halves per tile (epilogue warps per TMEM lane quadrant)
 constexpr int kMaxKB = 4;         // dpad <= 256
 constexpr uint32_t kABytesPerKB = kBM * 128;   // 16 KB
 constexpr uint32_t kBBytes = kBN * 128;        // 32 KB per stage (one k-block of one item tile)
@@ -37,7 +42,8 @@ struct TopkParams {
   int32_t tiles_per_split;
   int32_t stages;
   int32_t id_offset;     // added to local item ids (item-range shards)
-  float* out_vals;       // [n_splits, U, k]
+  int32_t probe;         // diagnostics: 1 = epilogue only drains TMEM (measures the TMEM-read ceiling)
+  float* out_vals;       // [n_splits * kHalves, U, k]
   int32_t* out_ids;
 };
 
@@ -84,7 +90,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     tc::prefetch_tensormap(&tmap_c);
     for (int s = 0; s < P.stages; ++s) { tc::mbar_init(full_bar(s), 1); tc::mbar_init(empty_bar(s), 1); }
     tc::mbar_init(a_full, 1);
-    for (int b = 0; b < 2; ++b) { tc::mbar_init(tmem_full(b), 1); tc::mbar_init(tmem_empty(b), 4); }
+    for (int b = 0; b < 2; ++b) { tc::mbar_init(tmem_full(b), 1); tc::mbar_init(tmem_empty(b), kEpiWarps); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc<512>(tc::smem_u32(tmem_slot));
@@ -137,58 +143,100 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   } else {
     // ===== epilogue: threshold filter + exact top-K per user row =====
     const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;                   // which 128-column half of each tile
     const int64_t row = int64_t(m_tile) * kBM + quad * 32 + lane;
     float vals[K_CAP]; int32_t ids[K_CAP];
 #pragma unroll
     for (int j = 0; j < K_CAP; ++j) { vals[j] = -CUDART_INF_F; ids[j] = -1; }
     float thr = -CUDART_INF_F;
+    constexpr int kChunks = kBN / kHalves / 32;         // 4 chunks of 32 columns per tile per warp
+
+    // Slow-path scratch: 32 floats per epilogue thread, column-major so that lane i of a warp hits
+    // bank i (conflict-free).  Keeps ONE compact copy of the insertion code (a dynamic loop) instead
+    // of 32 unrolled copies per call site -- the unrolled form overflowed the instruction cache.
+    float* scratch = reinterpret_cast<float*>(smem + P.KB * kABytesPerKB + P.stages * kBBytes + 256) +
+                     (threadIdx.x - 64);
+    constexpr int kScratchStride = kEpiWarps * 32;
+
+    auto process = [&](uint32_t (&r)[32], int64_t col0, bool ragged) {
+      if (P.probe) {                                    // keep the loads alive, do nothing else
+        uint32_t x = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x ^= r[j];
+        if (x == 0x7fc12345u) thr = 0.f;
+        return;
+      }
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (ragged) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (col0 + j >= P.I) v[j] = -CUDART_INF_F;
+      }
+      // 4 independent FMNMX3 chains, one per group of 8 columns
+      float gm[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float m = fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), v[8 * g + 2]);
+        m = fmaxf(fmaxf(m, v[8 * g + 3]), v[8 * g + 4]);
+        m = fmaxf(fmaxf(m, v[8 * g + 5]), v[8 * g + 6]);
+        gm[g] = fmaxf(m, v[8 * g + 7]);
+      }
+      const float cmax = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), gm[3]);
+      if (cmax > thr) {
+        // candidates = bitmask of columns beating the threshold; only groups whose max beats it are
+        // examined and spilled.  The loop below then runs once per candidate (usually once).
+        uint32_t mask = 0u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (gm[g] > thr) {
+#pragma unroll
+            for (int j = 8 * g; j < 8 * g + 8; ++j) {
+              scratch[j * kScratchStride] = v[j];
+              mask |= (v[j] > thr) ? (1u << j) : 0u;
+            }
+          }
+        }
+#pragma unroll 1
+        while (mask) {                                  // ascending column = ascending item id
+          const int j = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float x = scratch[j * kScratchStride];
+          if (x > thr) {
+            topk_insert<K_CAP>(vals, ids, x, int32_t(col0 + j) + P.id_offset);
+            thr = vals[K_CAP - 1];
+          }
+        }
+      }
+    };
+
     for (int t = 0; t < my_tiles; ++t) {
       const int buf = t & 1;
       tc::mbar_wait(tmem_full(buf), (t >> 1) & 1);
       tc::fence_after_sync();
-      const int64_t col_tile = int64_t(tile_begin + t) * kBN;
-      const bool ragged = col_tile + kBN > P.I;           // only the last item tile
+      const int64_t col_half = int64_t(tile_begin + t) * kBN + half * (kBN / kHalves);
+      const bool ragged = col_half + kBN / kHalves > P.I;   // only in the last item tile
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + buf * kBN + half * (kBN / kHalves);
+      uint32_t ra[32], rb[32];
+      tc::tmem_ld_32x32_issue(taddr, ra);
+      tc::tmem_ld_wait(ra);
 #pragma unroll 1
-      for (int c = 0; c < kBN / 32; ++c) {
-        float v[32];
-        tc::tmem_ld_32x32(tmem_base + (uint32_t(quad * 32) << 16) + buf * kBN + c * 32, v);
-        const int64_t col0 = col_tile + c * 32;
-        if (ragged) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (col0 + j >= P.I) v[j] = -CUDART_INF_F;
-        }
-        // 4 independent FMNMX3 chains, one per group of 8 columns
-        float gm[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float m = fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), v[8 * g + 2]);
-          m = fmaxf(fmaxf(m, v[8 * g + 3]), v[8 * g + 4]);
-          m = fmaxf(fmaxf(m, v[8 * g + 5]), v[8 * g + 6]);
-          gm[g] = fmaxf(m, v[8 * g + 7]);
-        }
-        const float cmax = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), gm[3]);
-        if (cmax > thr) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (gm[g] > thr) {
-#pragma unroll
-              for (int j = 8 * g; j < 8 * g + 8; ++j) {
-                if (v[j] > thr) {
-                  topk_insert<K_CAP>(vals, ids, v[j], int32_t(col0 + j) + P.id_offset);
-                  thr = vals[K_CAP - 1];
-                }
-              }
-            }
-          }
-        }
+      for (int c = 0; c < kChunks; c += 2) {
+        tc::tmem_ld_32x32_issue(taddr + (c + 1) * 32, rb);     // in flight while chunk c is processed
+        process(ra, col_half + c * 32, ragged);
+        tc::tmem_ld_wait(rb);
+        if (c + 2 < kChunks) tc::tmem_ld_32x32_issue(taddr + (c + 2) * 32, ra);
+        process(rb, col_half + (c + 1) * 32, ragged);
+        if (c + 2 < kChunks) tc::tmem_ld_wait(ra);
       }
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(tmem_empty(buf));
     }
     if (row < P.U) {
-      float* ov = P.out_vals + (int64_t(split) * P.U + row) * P.k;
-      int32_t* oi = P.out_ids + (int64_t(split) * P.U + row) * P.k;
+      const int64_t part = int64_t(split) * kHalves + half;
+      float* ov = P.out_vals + (part * P.U + row) * P.k;
+      int32_t* oi = P.out_ids + (part * P.U + row) * P.k;
 #pragma unroll
       for (int j = 0; j < K_CAP; ++j)
         if (j < P.k) { ov[j] = vals[j]; oi[j] = ids[j]; }
@@ -249,7 +297,7 @@ int plan_splits(const brk_ctx* ctx, int64_t U, int64_t I, int* n_splits, int* ti
   int S = 1;
   if (m_tiles < ctx->sm_count) S = int((ctx->sm_count + m_tiles - 1) / m_tiles);
   if (S > n_tiles) S = n_tiles;
-  if (S > 64) S = 64;
+  if (S > 32) S = 32;
   if (S < 1) S = 1;
   const int tps = (n_tiles + S - 1) / S;
   *tiles_per_split = tps;
@@ -280,7 +328,7 @@ extern "C" int64_t brk_score_topk_workspace_bytes(brk_ctx* ctx, int64_t U, int64
   if (!ctx || U <= 0 || I <= 0 || k <= 0) return 0;
   int S, tps;
   plan_splits(ctx, U, I, &S, &tps);
-  return S > 1 ? int64_t(S) * U * k * 8 : 0;
+  return int64_t(S) * kHalves * U * k * 8;
 }
 
 extern "C" int brk_score_topk_bf16(brk_ctx* ctx, const uint16_t* q_bf16, int64_t U, const uint16_t* c_bf16,
@@ -297,25 +345,25 @@ extern "C" int brk_score_topk_bf16(brk_ctx* ctx, const uint16_t* q_bf16, int64_t
 
   TopkParams P;
   P.U = U; P.I = I; P.KB = dpad / kKBlock; P.k = k; P.id_offset = id_offset;
+  P.probe = getenv("BRK_TOPK_PROBE") != nullptr;
   int S, tps;
   P.n_tiles = plan_splits(ctx, U, I, &S, &tps);
   P.tiles_per_split = tps;
   const size_t a_bytes = size_t(P.KB) * kABytesPerKB;
-  int stages = int((227 * 1024 - 1024 - 256 - a_bytes) / kBBytes);
+  constexpr size_t kScratchBytes = size_t(kEpiWarps) * 32 * 32 * sizeof(float);   // 32 KB
+  int stages = int((227 * 1024 - 1024 - 256 - kScratchBytes - a_bytes) / kBBytes);
   if (stages > 6) stages = 6;
   BRK_REQUIRE(stages >= 2, BRK_E_ARG, "brk_score_topk_bf16: no room for a 2-stage pipeline at dpad=%d", dpad);
   P.stages = stages;
-  const size_t smem = 1024 + a_bytes + size_t(stages) * kBBytes + 8 * (2 * stages + 5) + 16;
+  const size_t smem = 1024 + a_bytes + size_t(stages) * kBBytes + 256 + kScratchBytes;
 
-  float* pv = out_vals; int32_t* pi = out_ids;
-  if (S > 1) {
-    const int64_t need = int64_t(S) * U * k * 8;
-    BRK_REQUIRE(workspace && workspace_bytes >= need, BRK_E_ARG,
-                "brk_score_topk_bf16: workspace of %lld bytes needed, %lld given", (long long)need,
-                (long long)workspace_bytes);
-    pv = reinterpret_cast<float*>(workspace);
-    pi = reinterpret_cast<int32_t*>(pv + int64_t(S) * U * k);
-  }
+  const int parts = S * kHalves;                       // partial lists per user row
+  const int64_t need = int64_t(parts) * U * k * 8;
+  BRK_REQUIRE(workspace && workspace_bytes >= need, BRK_E_ARG,
+              "brk_score_topk_bf16: workspace of %lld bytes needed, %lld given", (long long)need,
+              (long long)workspace_bytes);
+  float* pv = reinterpret_cast<float*>(workspace);
+  int32_t* pi = reinterpret_cast<int32_t*>(pv + int64_t(parts) * U * k);
   P.out_vals = pv; P.out_ids = pi;
 
   CUtensorMap tq, tcm;
@@ -330,10 +378,8 @@ extern "C" int brk_score_topk_bf16(brk_ctx* ctx, const uint16_t* q_bf16, int64_t
   else if (k <= 16) rc = launch_topk<16>(tq, tcm, P, grid, smem, st);
   else rc = launch_topk<32>(tq, tcm, P, grid, smem, st);
   if (rc) return rc;
-  if (S > 1) {
-    topk_merge_kernel<<<unsigned((U + 255) / 256), 256, 0, st>>>(pv, pi, S, U, k, out_vals, out_ids);
-    BRK_LAUNCH_CHECK();
-  }
+  topk_merge_kernel<<<unsigned((U + 255) / 256), 256, 0, st>>>(pv, pi, parts, U, k, out_vals, out_ids);
+  BRK_LAUNCH_CHECK();
   return 0;
 }
 

@@ -1,6 +1,6 @@
 """Kernel micro-benchmarks (CUDA events, L2 flushed between iterations) used to fill the roofline
 tables in DESIGN.md.  Run on the GPU box:  python profiles/microbench.py [section ...]
-Sections: gather scatter bpr adam."""
+Sections: gather scatter bpr adam topk."""
 import json
 import os
 import sys
@@ -118,6 +118,31 @@ def sec_adam():
             report(f"adam_rows rows={rows} d={d} touched={uniq} (scatter time subtracted)", max(s_both - s_sc, 1e-9),
                    uniq * d * 32 + rows // 8)
         del t
+
+
+def sec_topk():
+    """users/s of the fused scoring+top-K kernel; tensor-pipe fraction = 2*U*I*dpad / t / bf16 peak."""
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0}
+    for U, I, d in ((6040, 3706, 128), (6040, 3706, 64), (131072, 250000, 64), (131072, 250000, 128),
+                    (32768, 2000000, 64)):
+        Q = torch.randn(U, d, device=dev); C = torch.randn(I, d, device=dev)
+        idx = H.BruteForceIndex(10).index(C)
+        q = H.rows_to_bf16(Q)
+        # time the kernel alone (bf16 query conversion excluded, as the index is built once)
+        from binrec_b200 import _native as N
+        lib, ctx = N.lib(), N.ctx(dev)
+        vals = torch.empty(U, 10, device=dev); ids = torch.empty(U, 10, dtype=torch.int32, device=dev)
+        wsb = lib.brk_score_topk_workspace_bytes(ctx, U, I, 10)
+        ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
+        def run():
+            N.check(lib.brk_score_topk_bf16(ctx, N.ptr(q), U, N.ptr(idx._c), I, q.shape[1], 10, 0, N.ptr(vals),
+                                            N.ptr(ids), N.ptr(ws), wsb, N.stream_ptr()), "topk")
+        s = timeit(run, iters=5, warm=2)
+        flops = 2.0 * U * I * q.shape[1]
+        print(f"score_topk U={U} I={I} d={d}: {s*1e3:9.3f} ms  {U/s/1e6:8.3f} M users/s  "
+              f"{flops/s/1e12:7.1f} TFLOP/s = {flops/s/1e12/peaks['bf16_tflops']:.3f} of measured bf16 peak", flush=True)
+        del Q, C, idx, q
 
 
 if __name__ == "__main__":
