@@ -166,6 +166,18 @@ int brk_score_topk_bf16(brk_ctx* ctx, const uint16_t* q_bf16, int64_t U, const u
 int brk_topk_merge(brk_ctx* ctx, const float* part_vals, const int32_t* part_ids, int32_t n_parts,
                    int64_t U, int32_t k, float* out_vals, int32_t* out_ids, void* stream);
 
+/* ---- K9: ranking metrics ----------------------------------------------------------------------
+ * Stands in for topKMetrics (trainers/topKmetrics.py:74-99): ids [U,k] are the recommended item ids
+ * of users user_ids[r] (NULL: user r); positives are a CSR over csr_users users with sorted item
+ * lists (distinct pairs).  counts_out[0] = tp, counts_out[1] = hits (users with >= 1 tp);
+ * fp = U*k - tp, fn = |positives| - tp, tn = U*I - tp - fp - fn, precision, recall and
+ * hitRate = hits / U follow on the host.  ndcg_sum_out = sum over users of DCG@k / IDCG@k (NDCG is
+ * not in the reference; binary relevance, IDCG over min(|pos_u|, k)).  Negative ids (short lists)
+ * count as misses. */
+int brk_topk_metrics(brk_ctx* ctx, const int32_t* ids, int64_t U, int32_t k, const int32_t* user_ids,
+                     const int64_t* pos_indptr, const int32_t* pos_items, int64_t csr_users,
+                     int64_t* counts_out, double* ndcg_sum_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
