@@ -1,0 +1,317 @@
+"""NeuMF (GMF + MLP) -- drop-in mirror of the reference's src/models/NeuMFModel.py (class, method
+names, call shapes, return values) and of the script variant trainers/NFC_plain.py.
+
+Underneath: four embedding tables and one flat dense-parameter block resident in HBM, the fused
+five-kernel forward/backward of csrc/neumf.cu, Philox negative sampling (csrc/sampler.cu) and one
+fused Keras-Adam launch over all parameters (csrc/optim.cu), all through the C ABI.
+
+Differences from the reference, stated once:
+  * negatives come from the counter-based sampler (same marginals as NeuMFModel.py:104-105: user and
+    item both follow the positives' empirical popularity, no collision check), so runs are reproducible;
+  * dropout masks come from Philox with keep probability 205/256 (oracle/neumf.py); TensorFlow's
+    dropout stream is not reproducible, so rate 0.2 is matched in distribution, not bit for bit;
+  * `train` works without a distributedConfig (the reference raises NameError, RModel.py:139);
+  * predictForUser sorts by the numeric score (the reference sorts the string form of the score,
+    NeuMFModel.py:146,150) and scores each product once (the reference scores 4x redundantly through
+    bootstrapDataset's negatives, NeuMFModel.py:135 -> RModel.py:168-170).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import hotpath as H
+from . import synth
+from .RModel import RModel
+
+BUILT_SPECS = {(32, 32, 16, 8), (64, 64, 32, 16), (16, 16, 8, 4), (8, 8, 4, 2), (10, 100, 50, 10)}
+
+
+class NeuMFNet:
+    """The 'Keras model' of NeuMFModel.compileModel: inputs {'user','item'}, sigmoid output."""
+
+    DENSE_ORDER = ("W1", "b1", "g1", "be1", "W2", "b2", "g2", "be2", "W3", "b3", "W4", "b4")
+
+    def __init__(self, numUser, numItem, numFactor, hidden=None, act="relu", loss="mse", learning_rate=1e-3,
+                 dropout=0.2, seed=42, dropout_seed=11, sparse_adam="keras", device=None, head_order="h3_mf"):
+        self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+        E = int(numFactor)
+        h1, h2, h3 = hidden or (E, E // 2, E // 4)
+        if (E, h1, h2, h3) not in BUILT_SPECS:
+            raise ValueError(f"no kernel instance for E={E}, hidden={(h1, h2, h3)}; built: {sorted(BUILT_SPECS)}")
+        self.E, self.hidden = E, (h1, h2, h3)
+        self.numUser, self.numItem = int(numUser), int(numItem)
+        self.act, self.loss, self.dropout = act, loss, float(dropout)
+        self.dropout_seed = dropout_seed
+        self.head_order = head_order
+        lazy = sparse_adam == "lazy"
+        dev = self.device
+        rng = np.random.Generator(np.random.Philox(key=seed))
+
+        def emb(rows):
+            return H.Table(torch.from_numpy(H.keras_embedding_init(rows, E, rng)).to(dev), touched=lazy)
+
+        # draw order = oracle/neumf.py: uMLP, iMLP, uMF, iMF, then the Dense kernels (glorot-uniform)
+        self.uMLP, self.iMLP, self.uMF, self.iMF = emb(self.numUser), emb(self.numItem), emb(self.numUser), emb(self.numItem)
+
+        def glorot(i, o):
+            lim = np.sqrt(6.0 / (i + o))
+            return rng.uniform(-lim, lim, size=(i, o)).astype(np.float32)
+
+        parts = {"W1": glorot(2 * E, h1), "b1": np.zeros(h1, np.float32), "g1": np.ones(h1, np.float32),
+                 "be1": np.zeros(h1, np.float32), "W2": glorot(h1, h2), "b2": np.zeros(h2, np.float32),
+                 "g2": np.ones(h2, np.float32), "be2": np.zeros(h2, np.float32), "W3": glorot(h2, h3),
+                 "b3": np.zeros(h3, np.float32), "W4": glorot(h3 + 1, 1), "b4": np.zeros(1, np.float32)}
+        n = int(N.lib().brk_neumf_dense_floats(E, h1, h2, h3))
+        flat = np.concatenate([parts[k].reshape(-1) for k in self.DENSE_ORDER])
+        assert flat.size == n
+        npad = (n + 3) // 4 * 4
+        self.dense = H.Table(torch.from_numpy(np.pad(flat, (0, npad - n))).to(dev).view(1, -1), touched=False)
+        self._offsets, off = {}, 0
+        for k in self.DENSE_ORDER:
+            self._offsets[k] = (off, parts[k].shape)
+            off += parts[k].size
+        bn = np.concatenate([np.zeros(h1), np.ones(h1), np.zeros(h2), np.ones(h2)]).astype(np.float32)
+        self.bn_moving = torch.from_numpy(bn).to(dev)
+        self.optimizer = H.Adam(learning_rate, sparse=sparse_adam, device=dev)
+        self._ws_batch = 0
+        self._ws = None
+        self.history = {"loss": []}
+
+    # ---- parameter views -------------------------------------------------------------------------
+    def param(self, name, grad=False):
+        off, shape = self._offsets[name]
+        src = self.dense.g if grad else self.dense.w
+        return src.view(-1)[off:off + int(np.prod(shape))].view(*shape)
+
+    def tables(self):
+        return [self.uMLP, self.iMLP, self.uMF, self.iMF]
+
+    def _c_model(self):
+        h1, h2, h3 = self.hidden
+        return N.brk_neumf_model(self.uMLP.c_struct(), self.iMLP.c_struct(), self.uMF.c_struct(), self.iMF.c_struct(),
+                                 self.dense.c_struct(), self.bn_moving.data_ptr(), self.E, h1, h2, h3,
+                                 0 if self.act == "relu" else 1, 0 if self.loss == "mse" else 1,
+                                 1 if self.dropout > 0 else 0, 0)
+
+    def _workspace(self, batch):
+        if batch > self._ws_batch:
+            h1, h2, _ = self.hidden
+            dev = self.device
+            acc_n = int(N.lib().brk_neumf_acc_doubles(h1, h2))
+            self._bufs = dict(h1=torch.empty(h1 * batch, device=dev), h2=torch.empty(h2 * batch, device=dev),
+                              dy1=torch.empty(h1 * batch, device=dev), dy2=torch.empty(h2 * batch, device=dev),
+                              acc=torch.zeros(acc_n, dtype=torch.float64, device=dev))
+            self._ws_batch = batch
+        b = self._bufs
+        return N.brk_neumf_workspace(b["h1"].data_ptr(), b["h2"].data_ptr(), b["dy1"].data_ptr(), b["dy2"].data_ptr(),
+                                     b["acc"].data_ptr())
+
+    # ---- steps ---------------------------------------------------------------------------------------
+    def forward_backward(self, u, i, y, first_index=0, epoch=0, out=None, loss_out=None):
+        """Fused forward + backward on device tensors; gradients land in the tables' accumulators."""
+        B = u.numel()
+        out = out if out is not None else torch.empty(B, dtype=torch.float32, device=self.device)
+        loss_out = loss_out if loss_out is not None else torch.empty(1, dtype=torch.float32, device=self.device)
+        m, ws = self._c_model(), self._workspace(B)
+        N.check(N.lib().brk_neumf_step(N.ctx(self.device), C.byref(m), N.ptr(H._i32(u, "u")), N.ptr(H._i32(i, "i")),
+                                       N.ptr(H._f32(y, "y")), B, first_index, 1, self.dropout_seed & 0xFFFFFFFF,
+                                       epoch & 0xFFFFFFFF, C.byref(ws), N.ptr(out), N.ptr(loss_out), N.stream_ptr()),
+                "brk_neumf_step")
+        return loss_out, out
+
+    def train_on_batch(self, u, i, y, first_index=0, epoch=0, out=None, loss_out=None):
+        loss, out = self.forward_backward(u, i, y, first_index, epoch, out, loss_out)
+        self.optimizer.apply(self.tables(), dense=[self.dense])
+        return loss, out
+
+    def predict_on_batch(self, u, i, y=None):
+        """Inference with the BN moving statistics; returns (predictions, loss or None)."""
+        B = u.numel()
+        out = torch.empty(B, dtype=torch.float32, device=self.device)
+        loss_out = torch.empty(1, dtype=torch.float32, device=self.device) if y is not None else None
+        m, ws = self._c_model(), self._workspace(B)
+        N.check(N.lib().brk_neumf_step(N.ctx(self.device), C.byref(m), N.ptr(H._i32(u, "u")), N.ptr(H._i32(i, "i")),
+                                       N.ptr(y) if y is not None else None, B, 0, 0, 0, 0, C.byref(ws), N.ptr(out),
+                                       N.ptr(loss_out) if loss_out is not None else None, N.stream_ptr()),
+                "brk_neumf_step")
+        return out, loss_out
+
+    # ---- Keras-like API -------------------------------------------------------------------------------
+    def fit(self, dataset, validation_data=None, epochs=1, steps_per_epoch=None, verbose=0):
+        """dataset: a NeuMFDataset (bootstrapDataset).  One pass per epoch; batch ORDER reshuffled per
+        epoch as tf.data's .batch().shuffle() does (NeuMFModel.py:117-121)."""
+        for e in range(epochs):
+            losses = dataset.run_epoch(self, e, steps_per_epoch)
+            mean = float(losses.double().mean().item())
+            self.history["loss"].append(mean)
+            if validation_data is not None:
+                self.history.setdefault("val_loss", []).append(self.evaluate(validation_data)[0])
+            if verbose:
+                print(f"epoch {e + 1}: loss {mean:.6f}")
+        return self
+
+    def evaluate(self, dataset, steps=None):
+        """[loss, mse, mae, binary_accuracy] -- the reference's METRICS list (RModel.py:20,144-147)."""
+        tot = 0; acc = np.zeros(4)
+        for k, (u, i, y) in enumerate(dataset.batches()):
+            if steps is not None and k >= steps:
+                break
+            out, loss = self.predict_on_batch(u, i, y)
+            n = u.numel()
+            err = out - y
+            acc += n * np.array([float(loss.item()), float((err * err).mean().item()), float(err.abs().mean().item()),
+                                 float(((out > 0.5).float() == y).float().mean().item())])
+            tot += n
+        return list(acc / max(tot, 1))
+
+    def predict(self, dataset):
+        return torch.cat([self.predict_on_batch(u, i)[0] for u, i, _ in dataset.batches()]).unsqueeze(1)
+
+    def score_all(self, usersId, itemsId, k):
+        """Top-k over the whole catalog for each user (topKRatings' "NFC" path, topKmetrics.py:29-33):
+        NeuMF has no factorised scorer, so every (user, item) pair goes through the fused forward."""
+        dev = self.device
+        items = torch.as_tensor(np.asarray(itemsId, dtype=np.int32)).to(dev)
+        I = items.numel()
+        k = min(k, I)
+        vals, idxs = [], []
+        chunk = max(1, (1 << 22) // I)
+        users = np.asarray(usersId, dtype=np.int32)
+        for s in range(0, len(users), chunk):
+            uu = torch.as_tensor(users[s:s + chunk]).to(dev)
+            out, _ = self.predict_on_batch(uu.repeat_interleave(I), items.repeat(uu.numel()))
+            v, ix = H.topk_rows(out.view(uu.numel(), I), k)
+            vals.append(v); idxs.append(ix)
+        return torch.cat(vals), torch.cat(idxs)
+
+    def state_dict(self):
+        sd = {"bn_moving": self.bn_moving.cpu(), "opt_state": self.optimizer.state.cpu()}
+        for name, t in zip(("uMLP", "iMLP", "uMF", "iMF", "dense"), self.tables() + [self.dense]):
+            sd[name] = t.w.cpu(); sd[name + "_m"] = t.m.cpu(); sd[name + "_v"] = t.v.cpu()
+        return sd
+
+    def load_state_dict(self, sd):
+        self.bn_moving.copy_(sd["bn_moving"]); self.optimizer.state.copy_(sd["opt_state"])
+        for name, t in zip(("uMLP", "iMLP", "uMF", "iMF", "dense"), self.tables() + [self.dense]):
+            t.w.copy_(sd[name]); t.m.copy_(sd[name + "_m"]); t.v.copy_(sd[name + "_v"])
+
+
+class NeuMFDataset:
+    """What bootstrapDataset returns: positives + Philox negatives, labels 1/0, one seeded row shuffle,
+    cut into batches; resident on the device.  Iterating yields ({"user": ids, "item": ids}, label)
+    like the reference's tf.data pipeline (NeuMFModel.py:111-123)."""
+
+    def __init__(self, users, items, negRatio, batchSize, shuffle, device, seed=7, epoch=0):
+        dev = device
+        pu = torch.from_numpy(np.ascontiguousarray(users, dtype=np.int32)).to(dev)
+        pi = torch.from_numpy(np.ascontiguousarray(items, dtype=np.int32)).to(dev)
+        P = pu.numel()
+        n_neg = int(round(P * negRatio))
+        if n_neg > 0:
+            nu, ni = H.philox_neumf_negatives(pu, pi, n_neg, seed, epoch)
+            u = torch.cat([pu, nu]); i = torch.cat([pi, ni])
+        else:
+            u, i = pu, pi
+        y = torch.cat([torch.ones(P, device=dev), torch.zeros(n_neg, device=dev)])
+        # mergeDf.sample(frac=1.): one row shuffle (seeded here; NeuMFModel.py:109)
+        perm = torch.from_numpy(np.random.Generator(np.random.Philox(key=seed + 77)).permutation(P + n_neg)).to(dev)
+        self.u, self.i, self.y = u[perm].contiguous(), i[perm].contiguous(), y[perm].contiguous()
+        self.batchSize, self.shuffle, self.seed = int(batchSize), shuffle, seed
+        self.n = P + n_neg
+        self.device = dev
+
+    def __len__(self):
+        return (self.n + self.batchSize - 1) // self.batchSize
+
+    def batches(self, order=None):
+        nb = len(self)
+        for b in (order if order is not None else range(nb)):
+            s = slice(b * self.batchSize, min(self.n, (b + 1) * self.batchSize))
+            yield self.u[s], self.i[s], self.y[s]
+
+    def __iter__(self):
+        for u, i, y in self.batches():
+            yield {"user": u, "item": i}, y
+
+    def run_epoch(self, net, epoch, steps=None):
+        nb = len(self)
+        order = (np.random.Generator(np.random.Philox(key=self.seed + 1009 * (epoch + 1))).permutation(nb)
+                 if self.shuffle else np.arange(nb))
+        if steps is not None:
+            order = order[:int(steps)]
+        losses = torch.empty(len(order), dtype=torch.float32, device=self.device)
+        outs = torch.empty(self.batchSize, dtype=torch.float32, device=self.device)
+        for k, b in enumerate(order):
+            s = slice(b * self.batchSize, min(self.n, (b + 1) * self.batchSize))
+            net.train_on_batch(self.u[s], self.i[s], self.y[s], first_index=int(b) * self.batchSize, epoch=epoch,
+                               out=outs[:s.stop - s.start], loss_out=losses[k:k + 1])
+        return losses
+
+
+class NeuMFModel(RModel):
+
+    def __init__(self, workDir=None):
+        super().__init__('NeuMFModel', workDir)
+        self.sparseAdam = "keras"
+        self.dropout = 0.2
+        self._testProducts, self._testUsers = [], []
+
+    def prepareToTrain(self, distributedConfig, path, rowLimit):
+        numItem, numUser, (users, items) = self.readData(path, rowLimit)
+        (trU, trI), (teU, teI) = synth.train_test_split(users, items, self.testSize, seed=self.splitSeed)
+        self._testProducts = np.unique(teI).tolist()          # pickled in the reference (NeuMFModel.py:34-38)
+        self._testUsers = np.unique(teU).tolist()
+        print(len(trU), 'train examples')
+        print(len(teU), 'testSplit examples')
+        if distributedConfig is None:
+            trainDataset = self.bootstrapDataset((trU, trI))
+            testDataset = self.bootstrapDataset((teU, teI), shuffle=False)
+        else:
+            trainDataset = self.bootstrapDataset((trU, trI), batchSize=self.batchSize)
+            testDataset = self.bootstrapDataset((teU, teI), batchSize=self.batchSize, shuffle=False)
+        self.model = self.compileModel(distributedConfig, numUser, numItem, self.numFactor)
+        return trainDataset, testDataset, (trU, trI)
+
+    def compileModel(self, distributedConfig, numUser: int, numItem: int, numFactor: int):
+        """Adam(1e-3), mean squared error, metrics mse/mae/binary_accuracy (NeuMFModel.py:87-91)."""
+        self.model = NeuMFNet(numUser, numItem, numFactor, act="relu", loss="mse", learning_rate=1e-3,
+                              dropout=self.dropout, seed=self.seed, sparse_adam=self.sparseAdam)
+        return self.model
+
+    def bootstrapDataset(self, df, negRatio=3., batchSize=128, shuffle=True):
+        users, items = self._loadPairs(df, None)
+        dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+        return NeuMFDataset(users, items, negRatio, batchSize, shuffle, dev, seed=self.samplerSeed)
+
+    def train(self, path, rowLimit, metricDict: dict = {}, distributedConfig=None):
+        trainDataset, testDataset, trainSplit = self.prepareToTrain(distributedConfig, path, rowLimit)
+        if distributedConfig is None:
+            self.model.fit(trainDataset, validation_data=testDataset, epochs=self.epochs)
+        else:
+            steps = int(len(trainDataset) / self.epochs / self.getNumberOfWorkers(distributedConfig))
+            self.model.fit(trainDataset, validation_data=testDataset, epochs=self.epochs, steps_per_epoch=max(steps, 1))
+        self.saveCheckPoint()
+        print("Evaluating trained model...")
+        _, val = synth.train_test_split(trainSplit[0], trainSplit[1], 0.2, seed=self.splitSeed + 1)
+        valDataset = self.bootstrapDataset(val, shuffle=False)
+        evaluatedMetric = self.model.evaluate(valDataset, steps=self.validationSteps)
+        return {'result': 'completed', 'metrics': evaluatedMetric}
+
+    def getPredictableUsers(self) -> list:
+        return list(self._testUsers)
+
+    def getPredictDataFrame(self, customerId):
+        return {self.PRODUCT_ID: list(self._testProducts), self.CUSTOMER_ID: [customerId] * len(self._testProducts)}
+
+    def predictForUser(self, customerId, numberOfItem=5):
+        """[(str(item), str(score)), ...] best first, as NeuMFModel.py:133-150 returns."""
+        dev = self.model.device
+        items = torch.as_tensor(np.asarray(self._testProducts, dtype=np.int32)).to(dev)
+        users = torch.full_like(items, int(customerId))
+        out, _ = self.model.predict_on_batch(users, items)
+        k = min(numberOfItem, items.numel())
+        v, ix = H.topk_rows(out.view(1, -1), k)
+        v, ix = v.cpu().numpy()[0], ix.cpu().numpy()[0]
+        return [(str(self._testProducts[j]), str(s)) for s, j in zip(v, ix)]

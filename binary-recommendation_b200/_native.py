@@ -27,6 +27,18 @@ class brk_adam_hyper(C.Structure):
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
 
 
+class brk_neumf_model(C.Structure):
+    _fields_ = [("uMLP", brk_table), ("iMLP", brk_table), ("uMF", brk_table), ("iMF", brk_table),
+                ("dense", brk_table), ("bn_moving", C.c_void_p), ("E", C.c_int32), ("H1", C.c_int32),
+                ("H2", C.c_int32), ("H3", C.c_int32), ("act", C.c_int32), ("loss", C.c_int32),
+                ("dropout", C.c_int32), ("_pad", C.c_int32)]
+
+
+class brk_neumf_workspace(C.Structure):
+    _fields_ = [("h1", C.c_void_p), ("h2", C.c_void_p), ("dy1", C.c_void_p), ("dy2", C.c_void_p),
+                ("acc", C.c_void_p)]
+
+
 _P, _I32, _I64, _U32, _F32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float
 
 # name -> (restype, argtypes); mirrors include/brk_b200.h one to one.
@@ -49,11 +61,16 @@ SIGNATURES = {
     "brk_adam_rows": (C.c_int, [_P, C.POINTER(brk_table), _I32, brk_adam_hyper, _P, _I32, _P]),
     "brk_adagrad_rows": (C.c_int, [_P, C.POINTER(brk_table), _I32, _F32, _F32, _P]),
     "brk_adagrad_dense": (C.c_int, [_P, C.POINTER(brk_table), _I32, _F32, _F32, _P]),
+    "brk_neumf_dense_floats": (C.c_int64, [_I32, _I32, _I32, _I32]),
+    "brk_neumf_acc_doubles": (C.c_int64, [_I32, _I32]),
+    "brk_neumf_step": (C.c_int, [_P, C.POINTER(brk_neumf_model), _P, _P, _P, _I64, _I64, _I32, _U32, _U32,
+                                 C.POINTER(brk_neumf_workspace), _P, _P, _P]),
     "brk_bf16_padded_dim": (C.c_int32, [_I32]),
     "brk_rows_to_bf16": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _P]),
     "brk_score_topk_workspace_bytes": (C.c_int64, [_P, _I64, _I64, _I32]),
     "brk_score_topk_bf16": (C.c_int, [_P, _P, _I64, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _I64, _P]),
     "brk_topk_metrics": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _I64, _P, _P, _P]),
+    "brk_topk_rows": (C.c_int, [_P, _P, _I64, _I64, _I32, _P, _P, _P]),
     "brk_topk_merge": (C.c_int, [_P, _P, _P, _I32, _I64, _I32, _P, _P, _P]),
 }
 

@@ -282,6 +282,42 @@ rows_to_bf16_kernel(const float* __restrict__ src, int64_t rows, int d, __nv_bfl
   }
 }
 
+// Warp-level top-K over rows of a materialised score matrix (models without a factorised scorer,
+// e.g. NeuMF: /root/reference/trainers/topKmetrics.py:29-33 + __topk :51-72).  One warp per row: each
+// lane keeps a sorted register list over its strided columns, then k rounds of a shuffle arg-max
+// (score desc, column asc) pop the winners.  4 B read per score.
+template <int K_CAP>
+__global__ void __launch_bounds__(256)
+topk_rows_kernel(const float* __restrict__ scores, int64_t R, int64_t I, int k, float* __restrict__ ov,
+                 int32_t* __restrict__ oi) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= R) return;
+  float vals[K_CAP]; int32_t ids[K_CAP];
+#pragma unroll
+  for (int j = 0; j < K_CAP; ++j) { vals[j] = -CUDART_INF_F; ids[j] = 0x7fffffff; }
+  const float* sr = scores + row * I;
+  for (int64_t c = lane; c < I; c += 32) {
+    const float v = __ldg(sr + c);
+    if (v > vals[K_CAP - 1]) topk_insert<K_CAP>(vals, ids, v, int32_t(c));
+  }
+  for (int j = 0; j < k; ++j) {
+    float bv = vals[0]; int32_t bi = ids[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov2 = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int32_t oi2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov2 > bv || (ov2 == bv && oi2 < bi)) { bv = ov2; bi = oi2; }
+    }
+    if (lane == 0) { ov[row * k + j] = bv; oi[row * k + j] = bi == 0x7fffffff ? -1 : bi; }
+    if (ids[0] == bi && vals[0] == bv) {                 // the winning lane pops its head
+#pragma unroll
+      for (int q = 0; q < K_CAP - 1; ++q) { vals[q] = vals[q + 1]; ids[q] = ids[q + 1]; }
+      vals[K_CAP - 1] = -CUDART_INF_F; ids[K_CAP - 1] = 0x7fffffff;
+    }
+  }
+}
+
 template <int K_CAP>
 int launch_topk(const CUtensorMap& tq, const CUtensorMap& tcm, const TopkParams& P, dim3 grid, size_t smem,
                 cudaStream_t st) {
@@ -390,6 +426,20 @@ extern "C" int brk_topk_merge(brk_ctx* ctx, const float* part_vals, const int32_
               n_parts, (long long)U, k);
   topk_merge_kernel<<<unsigned((U + 255) / 256), 256, 0, (cudaStream_t)stream>>>(part_vals, part_ids, n_parts, U, k,
                                                                                out_vals, out_ids);
+  BRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int brk_topk_rows(brk_ctx* ctx, const float* scores, int64_t R, int64_t I, int32_t k, float* out_vals,
+                             int32_t* out_ids, void* stream) {
+  BRK_REQUIRE(ctx && scores && out_vals && out_ids, BRK_E_ARG, "brk_topk_rows: null argument");
+  BRK_REQUIRE(R > 0 && I > 0 && I < (int64_t(1) << 31) && k >= 1 && k <= 32, BRK_E_ARG,
+              "brk_topk_rows: R=%lld I=%lld k=%d", (long long)R, (long long)I, k);
+  const unsigned grid = unsigned((R * 32 + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k <= 10) topk_rows_kernel<10><<<grid, 256, 0, st>>>(scores, R, I, k, out_vals, out_ids);
+  else if (k <= 16) topk_rows_kernel<16><<<grid, 256, 0, st>>>(scores, R, I, k, out_vals, out_ids);
+  else topk_rows_kernel<32><<<grid, 256, 0, st>>>(scores, R, I, k, out_vals, out_ids);
   BRK_LAUNCH_CHECK();
   return 0;
 }

@@ -275,3 +275,15 @@ def topk_merge(part_vals, part_ids):
     N.check(N.lib().brk_topk_merge(N.ctx(part_vals.device), N.ptr(part_vals), N.ptr(part_ids), S, U, k,
                                    N.ptr(vals), N.ptr(ids), N.stream_ptr()), "brk_topk_merge")
     return vals, ids
+
+
+def topk_rows(scores, k):
+    """Top-k per row of a score matrix [R, I] (score desc, ties -> lower column)."""
+    scores = _f32(scores, "scores")
+    R, I = scores.shape
+    k = min(int(k), I)
+    vals = torch.empty((R, k), dtype=torch.float32, device=scores.device)
+    ids = torch.empty((R, k), dtype=torch.int32, device=scores.device)
+    N.check(N.lib().brk_topk_rows(N.ctx(scores.device), N.ptr(scores), R, I, k, N.ptr(vals), N.ptr(ids),
+                                  N.stream_ptr()), "brk_topk_rows")
+    return vals, ids

@@ -143,6 +143,41 @@ int brk_adagrad_rows(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, float 
 int brk_adagrad_dense(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, float lr, float eps,
                       void* stream);
 
+/* ---- K1+K2+K3+K4+K5 fused: NeuMF forward + backward --------------------------------------------
+ * Stands in for the Keras graph of src/models/NeuMFModel.py:53-100 (class spec) and
+ * trainers/NFC_plain.py:109-155 (script spec) inside model.fit / predict / evaluate
+ * (src/models/RModel.py:130-147):
+ *   x0 = [uMLP[u], iMLP[i]] -> dropout -> act(W1) -> BN -> dropout -> act(W2) -> BN -> dropout -> act(W3) = h3
+ *   out = sigmoid([h3, <uMF[u], iMF[i]>] W4 + b4);   loss = mean squared error (0) | binary cross-entropy (1)
+ * dense is ONE flat parameter block (brk_table with rows = 1) laid out as
+ *   W1[2E,H1] b1[H1] gamma1[H1] beta1[H1] W2[H1,H2] b2[H2] gamma2[H2] beta2[H2] W3[H2,H3] b3[H3] W4[H3+1] b4[1]
+ * (Keras Dense kernels are [in, out] row-major; W4 rows are ordered [h3..., mf]); its length is
+ * brk_neumf_dense_floats().  bn_moving holds moving mean1[H1], var1[H1], mean2[H2], var2[H2]
+ * (Keras: momentum 0.99, eps 1e-3, biased batch variance).  act: 0 relu, 1 sigmoid.  dropout != 0
+ * applies the Philox-defined masks of oracle/neumf.py (keep 205/256) in training.
+ * Built instances (E; H1,H2,H3): (32;32,16,8) (64;64,32,16) (16;16,8,4) (8;8,4,2) (10;100,50,10).
+ * Workspace: h1,dy1 [H1*batch], h2,dy2 [H2*batch] floats, acc brk_neumf_acc_doubles() doubles that
+ * must be ZERO before the first call (every call leaves them zero again).
+ * training != 0: accumulates all gradients into the tables' g (to be consumed by the optimizer
+ * calls), updates bn_moving, writes out[batch] (predictions) and loss_out[0].
+ * training == 0: inference with the moving statistics; y may be NULL (then no loss). */
+typedef struct brk_neumf_model {
+  brk_table uMLP, iMLP, uMF, iMF, dense;
+  float*  bn_moving;
+  int32_t E, H1, H2, H3;
+  int32_t act, loss, dropout, _pad;
+} brk_neumf_model;
+typedef struct brk_neumf_workspace {
+  float *h1, *h2, *dy1, *dy2;
+  double* acc;
+} brk_neumf_workspace;
+int64_t brk_neumf_dense_floats(int32_t E, int32_t H1, int32_t H2, int32_t H3);
+int64_t brk_neumf_acc_doubles(int32_t H1, int32_t H2);
+int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, const int32_t* i,
+                   const float* y, int64_t batch, int64_t first_index, int32_t training,
+                   uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
+                   float* out, float* loss_out, void* stream);
+
 /* ---- K7/K8: full-catalog scoring + top-K ------------------------------------------------------
  * Stands in for tfrs.layers.factorized_top_k.BruteForce(k).index(candidates) + call(queries)
  * (trainers/twoTower.py:64-69,60-62,229-230; src/origin_models/svd/SVD.py:424-432), for
@@ -163,6 +198,11 @@ int64_t brk_score_topk_workspace_bytes(brk_ctx* ctx, int64_t U, int64_t I, int32
 int brk_score_topk_bf16(brk_ctx* ctx, const uint16_t* q_bf16, int64_t U, const uint16_t* c_bf16,
                         int64_t I, int32_t dpad, int32_t k, int32_t id_offset, float* out_vals,
                         int32_t* out_ids, void* workspace, int64_t workspace_bytes, void* stream);
+/* Top-k per row of a materialised score matrix [R, I] (models without a factorised scorer: NeuMF,
+ * trainers/topKmetrics.py:29-33 + __topk :51-72); same ordering rule; ids are column indices,
+ * -1 pads rows with fewer than k columns. */
+int brk_topk_rows(brk_ctx* ctx, const float* scores, int64_t R, int64_t I, int32_t k, float* out_vals,
+                  int32_t* out_ids, void* stream);
 int brk_topk_merge(brk_ctx* ctx, const float* part_vals, const int32_t* part_ids, int32_t n_parts,
                    int64_t U, int32_t k, float* out_vals, int32_t* out_ids, void* stream);
 

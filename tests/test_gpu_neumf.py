@@ -1,0 +1,134 @@
+"""GPU parity of the fused NeuMF forward/backward (through the C ABI) against the torch-autograd
+oracle (oracle/neumf.py) on identical inputs and initial weights.
+
+Stated fp32 tolerances: loss/predictions rtol 1e-5 / atol 1e-6; gradients rtol 1e-3 / atol 1e-6
+(reduction-order noise of the batch sums, the BN-backward cancellation and the atomic accumulation); weights after one Keras-Adam
+step rtol 1e-5 / atol 2e-6, after 5 steps atol 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import neumf as ON
+from oracle import topk as OT
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(dev, E, hidden, act, loss, dropout, U=300, I=200, seed=42):
+    from binrec_b200.NeuMFModel import NeuMFNet
+    orc = ON.NeuMFOracle(U, I, emb=E, hidden=hidden, seed=seed, act=act, loss=loss, dropout=dropout, dropout_seed=11)
+    net = NeuMFNet(U, I, E, hidden=hidden, act=act, loss=loss, dropout=dropout, seed=seed, dropout_seed=11, device=dev)
+    # identical initial weights (same draw order) -- verify instead of assuming
+    ref = orc.p.numpy()
+    for name, tab in zip(("uMLP", "iMLP", "uMF", "iMF"), net.tables()):
+        assert np.array_equal(tab.w.cpu().numpy(), ref[name])
+    for name in net.DENSE_ORDER:
+        assert np.array_equal(net.param(name).cpu().numpy().reshape(ref[name].shape), ref[name])
+    return orc, net
+
+
+def _batch(rng, U, I, B):
+    u = (U * rng.random(B) ** 2).astype(np.int32)
+    i = (I * rng.random(B) ** 2).astype(np.int32)
+    y = (rng.random(B) < 0.25).astype(np.float32)
+    return u, i, y
+
+
+SPECS = [(8, (8, 4, 2), "relu", "mse"), (32, (32, 16, 8), "relu", "mse"), (64, (64, 32, 16), "relu", "mse"),
+         (16, (16, 8, 4), "sigmoid", "bce"), (10, (100, 50, 10), "sigmoid", "bce")]
+
+
+@pytest.mark.parametrize("E,hidden,act,loss", SPECS)
+@pytest.mark.parametrize("dropout", [0.0, 0.2])
+@pytest.mark.parametrize("B", [1000, 128])
+def test_neumf_forward_backward_matches_autograd(dev, E, hidden, act, loss, dropout, B):
+    U, I = 300, 200
+    orc, net = _mk(dev, E, hidden, act, loss, dropout, U, I)
+    rng = np.random.default_rng(B + E)
+    u, i, y = _batch(rng, U, I, B)
+    first = 4096
+    lref, oref, aux = orc.loss_and_grads(u, i, y, first_index=first, epoch=3)
+    ud, idd, yd = (torch.from_numpy(x).to(dev) for x in (u, i, y))
+    lgot, ogot = net.forward_backward(ud, idd, yd, first_index=first, epoch=3)
+    np.testing.assert_allclose(ogot.cpu().numpy(), oref.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(lgot.item(), float(lref), rtol=1e-5, atol=1e-6)
+    for name, tab in zip(("uMLP", "iMLP", "uMF", "iMF"), net.tables()):
+        np.testing.assert_allclose(tab.g.cpu().numpy(), orc.p.t[name].grad.numpy(), rtol=1e-3, atol=1e-6, err_msg=name)
+    for name in net.DENSE_ORDER:
+        g = orc.p.t[name].grad.numpy()
+        np.testing.assert_allclose(net.param(name, grad=True).cpu().numpy().reshape(g.shape), g, rtol=1e-3, atol=1e-6,
+                                   err_msg=name)
+    # workspace accumulators are left zero for the next step
+    assert not net._bufs["acc"].any().item()
+
+
+@pytest.mark.parametrize("E,hidden,act,loss", [SPECS[1], SPECS[4]])
+def test_neumf_five_steps_match_oracle_keras_adam(dev, E, hidden, act, loss):
+    """Five Keras-Adam steps.  Adam divides by sqrt(v)+eps, which amplifies sub-1e-7 gradient noise
+    wherever |g| is of the order of eps (1e-7), so weights are judged against an fp64 run of the
+    oracle: the device must be as close to it as the fp32 oracle is (factor 5 + 2e-6 slack), and
+    within atol 5e-5 of the fp32 oracle outright."""
+    from binrec_b200.NeuMFModel import NeuMFNet
+    U, I, B = 300, 200, 512
+    orc, net = _mk(dev, E, hidden, act, loss, 0.2, U, I)
+    o64 = ON.NeuMFOracle(U, I, emb=E, hidden=hidden, act=act, loss=loss, dropout=0.2, dropout_seed=11,
+                         dtype=torch.float64)
+    rng = np.random.default_rng(5)
+    for step in range(5):
+        u, i, y = _batch(rng, U, I, B)
+        lref, _ = orc.step(u, i, y, first_index=step * B, epoch=0)
+        o64.step(u, i, y, first_index=step * B, epoch=0)
+        lgot, _ = net.train_on_batch(*(torch.from_numpy(x).to(dev) for x in (u, i, y)), first_index=step * B, epoch=0)
+        np.testing.assert_allclose(lgot.item(), lref, rtol=1e-4, atol=1e-6)
+    ref, ref64 = orc.p.numpy(), o64.p.numpy()
+    got = {name: tab.w.cpu().numpy() for name, tab in zip(("uMLP", "iMLP", "uMF", "iMF"), net.tables())}
+    got.update({name: net.param(name).cpu().numpy().reshape(ref[name].shape) for name in net.DENSE_ORDER})
+    for name, w in got.items():
+        err_dev = np.abs(w - ref64[name]).max()
+        err_o32 = np.abs(ref[name] - ref64[name]).max()
+        assert err_dev <= 5 * err_o32 + 2e-6, (name, err_dev, err_o32)
+        np.testing.assert_allclose(w, ref[name], rtol=1e-4, atol=5e-5, err_msg=name)
+    h1, h2, _ = hidden
+    bn = net.bn_moving.cpu().numpy()
+    for g, want in ((bn[:h1], orc.p.mm1), (bn[h1:2 * h1], orc.p.mv1), (bn[2 * h1:2 * h1 + h2], orc.p.mm2),
+                    (bn[2 * h1 + h2:], orc.p.mv2)):
+        np.testing.assert_allclose(g, want.numpy(), rtol=1e-5, atol=1e-7)
+    assert net.optimizer.step.item() == 5
+    # inference path uses the moving statistics
+    u, i, y = _batch(rng, U, I, 777)
+    out, l = net.predict_on_batch(*(torch.from_numpy(x).to(dev) for x in (u, i, y)))
+    np.testing.assert_allclose(out.cpu().numpy(), orc.predict(u, i), rtol=1e-4, atol=1e-5)
+    out2, none = net.predict_on_batch(torch.from_numpy(u).to(dev), torch.from_numpy(i).to(dev))
+    assert none is None and torch.equal(out, out2)
+
+
+def test_topk_rows_matches_oracle_with_ties(dev):
+    from binrec_b200 import hotpath as H
+    rng = np.random.default_rng(0)
+    for R, I, k in ((7, 5, 10), (33, 3706, 10), (4, 100000, 32), (100, 64, 5)):
+        S = (rng.integers(-20, 21, size=(R, I)) / 8.0).astype(np.float32)
+        v, ix = H.topk_rows(torch.from_numpy(S).to(dev), k)
+        rv, ri = OT.topk_from_scores(S, k)
+        assert np.array_equal(ix.cpu().numpy(), ri) and np.array_equal(v.cpu().numpy(), rv)
+
+
+def test_neumf_model_class_end_to_end(dev, tmp_path):
+    from binrec_b200.NeuMFModel import NeuMFModel
+    from binrec_b200 import synth
+    users, items = synth.make_interactions(num_users=400, num_items=300, num_pos=20000, seed=5)
+    m = NeuMFModel(workDir=str(tmp_path))
+    m.epochs = 2
+    res = m.train((users, items), None)
+    assert res["result"] == "completed" and len(res["metrics"]) == 4
+    assert m.model.history["loss"][1] < m.model.history["loss"][0]          # it learns
+    ds = m.bootstrapDataset((users[:1000], items[:1000]), shuffle=False)
+    feats, label = next(iter(ds))
+    assert set(feats) == {"user", "item"} and label.shape == feats["user"].shape
+    assert abs(float(ds.y.mean().item()) - 0.25) < 1e-6                     # negRatio 3 -> 1 positive in 4
+    recs = m.predictForUser(m.getPredictableUsers()[0], 5)
+    assert len(recs) == 5 and all(isinstance(a, str) and isinstance(b, str) for a, b in recs)
+    scores = [float(b) for _, b in recs]
+    assert scores == sorted(scores, reverse=True)
+    m2 = NeuMFModel(workDir=str(tmp_path)); m2.compileModel(None, m.model.numUser, m.model.numItem, m.numFactor)
+    m2.restoreFromLatestCheckPoint()
+    assert torch.equal(m2.model.uMLP.w, m.model.uMLP.w)
