@@ -1,6 +1,6 @@
 """Kernel micro-benchmarks (CUDA events, L2 flushed between iterations) used to fill the roofline
 tables in DESIGN.md.  Run on the GPU box:  python profiles/microbench.py [section ...]
-Sections: gather scatter bpr adam topk."""
+Sections: gather scatter bpr adam topk neumf."""
 import json
 import os
 import sys
@@ -143,6 +143,27 @@ def sec_topk():
         print(f"score_topk U={U} I={I} d={d}: {s*1e3:9.3f} ms  {U/s/1e6:8.3f} M users/s  "
               f"{flops/s/1e12:7.1f} TFLOP/s = {flops/s/1e12/peaks['bf16_tflops']:.3f} of measured bf16 peak", flush=True)
         del Q, C, idx, q
+
+
+def sec_neumf():
+    """interactions/s of one NeuMF training step (5 fwd/bwd kernels + fused Adam), ML-1M tables."""
+    from binrec_b200.NeuMFModel import NeuMFNet
+    g = torch.Generator(device=dev); g.manual_seed(4)
+    for E, B in ((32, 16384), (32, 65536), (64, 65536)):
+        U, I = (6040, 3706) if E == 32 else (2_000_000, 200_000)
+        net = NeuMFNet(U, I, E, dropout=0.2, device=dev)
+        u, i = ids_of("skew", U, B, g), ids_of("skew", I, B, g)
+        y = (torch.rand(B, generator=g, device=dev) < 0.2).float()
+        out = torch.empty(B, device=dev); loss = torch.empty(1, device=dev)
+        s = timeit(lambda: net.train_on_batch(u, i, y, out=out, loss_out=loss))
+        s_fb = timeit(lambda: net.forward_backward(u, i, y, out=out, loss_out=loss))
+        for t in net.tables() + [net.dense]:
+            t.g.zero_()
+        per = 4 * 4 * E * 2 + 16
+        print(f"neumf_step E={E} B={B} tables {U}x{I}: step {s*1e6:8.1f} us ({B/s/1e6:7.1f} M inter/s)  fwd+bwd only "
+              f"{s_fb*1e6:8.1f} us  -> {B*per/s_fb/1e9:7.1f} GB/s algorithmic = {B*per/s_fb/1e9/PEAK:.3f} of HBM peak; "
+              f"{B*16182*(E/32)**2/s_fb/1e12:6.2f} TFLOP/s fp32", flush=True)
+        del net
 
 
 if __name__ == "__main__":
