@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _native as N
+from . import distributed as D
 from . import hotpath as H
 from . import synth
 from .RModel import RModel
@@ -37,10 +38,13 @@ class BPRNet:
         rng = np.random.Generator(np.random.Philox(key=seed))
         # Keras Embedding default init U(-0.05, 0.05); user table first, then item (same draw order as the oracle)
         lazy = sparse_adam == "lazy"   # the touched-row bitmask is only needed by the row-sparse optimizer
+        # one flat gradient arena for both tables: data-parallel replicas sum it with ONE all-reduce
+        nu, ni = self.numUser * self.numFactor, self.numItem * self.numFactor
+        self.grad_arena = torch.zeros(nu + ni, dtype=torch.float32, device=self.device)
         self.user = H.Table(torch.from_numpy(H.keras_embedding_init(self.numUser, self.numFactor, rng)).to(self.device),
-                            touched=lazy)
+                            touched=lazy, g=self.grad_arena[:nu])
         self.item = H.Table(torch.from_numpy(H.keras_embedding_init(self.numItem, self.numFactor, rng)).to(self.device),
-                            touched=lazy)
+                            touched=lazy, g=self.grad_arena[nu:])
         self.optimizer = H.Adam(learning_rate, sparse=sparse_adam, device=self.device)
         self._pairs = None
         self.history = {"loss": []}
@@ -81,9 +85,17 @@ class BPRNet:
                 "brk_bpr_train_steps")
         return losses
 
-    def train_on_batch(self, u, p, n):
-        """One step on device id tensors; returns the device loss scalar."""
-        loss = H.bpr_fwd_bwd(self.user, self.item, u, p, n)
+    def train_on_batch(self, u, p, n, loss_out=None):
+        """One step on device id tensors; returns the device loss scalar (local-batch mean).
+        Under torch.distributed this is the mirrored synchronous step of RModel.py:119-121: each rank
+        trains its own slice, gradients are scaled by 1/(world * batch) and summed by one all-reduce,
+        every rank applies the same Adam step."""
+        w = D.world_size()
+        loss = H.bpr_fwd_bwd(self.user, self.item, u, p, n, loss_out=loss_out, global_batch=w * u.numel() if w > 1 else 0)
+        if w > 1:
+            if self.optimizer.sparse == "lazy":
+                raise NotImplementedError("mirrored data parallelism uses the dense (Keras) Adam pass")
+            D.all_reduce_sum_(self.grad_arena)
         self.optimizer.apply([self.user, self.item])
         return loss
 

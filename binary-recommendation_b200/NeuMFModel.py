@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _native as N
+from . import distributed as D
 from . import hotpath as H
 from . import synth
 from .RModel import RModel
@@ -48,9 +49,15 @@ class NeuMFNet:
         lazy = sparse_adam == "lazy"
         dev = self.device
         rng = np.random.Generator(np.random.Philox(key=seed))
+        n_dense = int(N.lib().brk_neumf_dense_floats(E, h1, h2, h3))
+        npad = (n_dense + 3) // 4 * 4
+        # one flat gradient arena (4 tables + dense block): data-parallel replicas all-reduce it once per step
+        sizes = [self.numUser * E, self.numItem * E, self.numUser * E, self.numItem * E, npad]
+        self.grad_arena = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        views = list(torch.split(self.grad_arena, sizes))
 
         def emb(rows):
-            return H.Table(torch.from_numpy(H.keras_embedding_init(rows, E, rng)).to(dev), touched=lazy)
+            return H.Table(torch.from_numpy(H.keras_embedding_init(rows, E, rng)).to(dev), touched=lazy, g=views.pop(0))
 
         # draw order = oracle/neumf.py: uMLP, iMLP, uMF, iMF, then the Dense kernels (glorot-uniform)
         self.uMLP, self.iMLP, self.uMF, self.iMF = emb(self.numUser), emb(self.numItem), emb(self.numUser), emb(self.numItem)
@@ -63,11 +70,10 @@ class NeuMFNet:
                  "be1": np.zeros(h1, np.float32), "W2": glorot(h1, h2), "b2": np.zeros(h2, np.float32),
                  "g2": np.ones(h2, np.float32), "be2": np.zeros(h2, np.float32), "W3": glorot(h2, h3),
                  "b3": np.zeros(h3, np.float32), "W4": glorot(h3 + 1, 1), "b4": np.zeros(1, np.float32)}
-        n = int(N.lib().brk_neumf_dense_floats(E, h1, h2, h3))
         flat = np.concatenate([parts[k].reshape(-1) for k in self.DENSE_ORDER])
-        assert flat.size == n
-        npad = (n + 3) // 4 * 4
-        self.dense = H.Table(torch.from_numpy(np.pad(flat, (0, npad - n))).to(dev).view(1, -1), touched=False)
+        assert flat.size == n_dense
+        self.dense = H.Table(torch.from_numpy(np.pad(flat, (0, npad - n_dense))).to(dev).view(1, -1), touched=False,
+                             g=views.pop(0))
         self._offsets, off = {}, 0
         for k in self.DENSE_ORDER:
             self._offsets[k] = (off, parts[k].shape)
@@ -109,20 +115,27 @@ class NeuMFNet:
                                      b["acc"].data_ptr())
 
     # ---- steps ---------------------------------------------------------------------------------------
-    def forward_backward(self, u, i, y, first_index=0, epoch=0, out=None, loss_out=None):
+    def forward_backward(self, u, i, y, first_index=0, epoch=0, out=None, loss_out=None, global_batch=0):
         """Fused forward + backward on device tensors; gradients land in the tables' accumulators."""
         B = u.numel()
         out = out if out is not None else torch.empty(B, dtype=torch.float32, device=self.device)
         loss_out = loss_out if loss_out is not None else torch.empty(1, dtype=torch.float32, device=self.device)
         m, ws = self._c_model(), self._workspace(B)
         N.check(N.lib().brk_neumf_step(N.ctx(self.device), C.byref(m), N.ptr(H._i32(u, "u")), N.ptr(H._i32(i, "i")),
-                                       N.ptr(H._f32(y, "y")), B, first_index, 1, self.dropout_seed & 0xFFFFFFFF,
+                                       N.ptr(H._f32(y, "y")), B, global_batch, first_index, 1, self.dropout_seed & 0xFFFFFFFF,
                                        epoch & 0xFFFFFFFF, C.byref(ws), N.ptr(out), N.ptr(loss_out), N.stream_ptr()),
                 "brk_neumf_step")
         return loss_out, out
 
     def train_on_batch(self, u, i, y, first_index=0, epoch=0, out=None, loss_out=None):
-        loss, out = self.forward_backward(u, i, y, first_index, epoch, out, loss_out)
+        """One training step.  Under torch.distributed: mirrored synchronous data parallelism
+        (RModel.py:119-121) -- gradients scaled by 1/(world * batch), ONE all-reduce of the flat arena,
+        identical Adam step on every rank; BatchNorm statistics stay per replica."""
+        w = D.world_size()
+        loss, out = self.forward_backward(u, i, y, first_index, epoch, out, loss_out,
+                                          global_batch=w * u.numel() if w > 1 else 0)
+        if w > 1:
+            D.all_reduce_sum_(self.grad_arena)
         self.optimizer.apply(self.tables(), dense=[self.dense])
         return loss, out
 
@@ -133,7 +146,7 @@ class NeuMFNet:
         loss_out = torch.empty(1, dtype=torch.float32, device=self.device) if y is not None else None
         m, ws = self._c_model(), self._workspace(B)
         N.check(N.lib().brk_neumf_step(N.ctx(self.device), C.byref(m), N.ptr(H._i32(u, "u")), N.ptr(H._i32(i, "i")),
-                                       N.ptr(y) if y is not None else None, B, 0, 0, 0, 0, C.byref(ws), N.ptr(out),
+                                       N.ptr(y) if y is not None else None, B, 0, 0, 0, 0, 0, C.byref(ws), N.ptr(out),
                                        N.ptr(loss_out) if loss_out is not None else None, N.stream_ptr()),
                 "brk_neumf_step")
         return out, loss_out

@@ -53,7 +53,7 @@ SIGNATURES = {
     "brk_philox_bpr_negatives": (C.c_int, [_P, _P, _I64, _I64, _U32, _U32, _I32, _P, _P, _P, _P]),
     "brk_philox_neumf_negatives": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _U32, _U32, _P, _P, _P]),
     "brk_philox4x32_10": (C.c_int, [_P, _P, _I64, _U32, _U32, _P, _P]),
-    "brk_bpr_fwd_bwd": (C.c_int, [_P, C.POINTER(brk_table), C.POINTER(brk_table), _P, _P, _P, _I64, _P, _P]),
+    "brk_bpr_fwd_bwd": (C.c_int, [_P, C.POINTER(brk_table), C.POINTER(brk_table), _P, _P, _P, _I64, _I64, _P, _P]),
     "brk_bpr_train_steps": (C.c_int, [_P, C.POINTER(brk_table), C.POINTER(brk_table), _P, _P, _P, _I64, _I64,
                                       C.POINTER(C.c_int64), _I32, brk_adam_hyper, _I32, _P, _P, _P]),
     "brk_bpr_scores": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _I64, _P, _P]),
@@ -63,7 +63,7 @@ SIGNATURES = {
     "brk_adagrad_dense": (C.c_int, [_P, C.POINTER(brk_table), _I32, _F32, _F32, _P]),
     "brk_neumf_dense_floats": (C.c_int64, [_I32, _I32, _I32, _I32]),
     "brk_neumf_acc_doubles": (C.c_int64, [_I32, _I32]),
-    "brk_neumf_step": (C.c_int, [_P, C.POINTER(brk_neumf_model), _P, _P, _P, _I64, _I64, _I32, _U32, _U32,
+    "brk_neumf_step": (C.c_int, [_P, C.POINTER(brk_neumf_model), _P, _P, _P, _I64, _I64, _I64, _I32, _U32, _U32,
                                  C.POINTER(brk_neumf_workspace), _P, _P, _P]),
     "brk_bf16_padded_dim": (C.c_int32, [_I32]),
     "brk_rows_to_bf16": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _P]),

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kThreads)
 bpr_vec(const float* __restrict__ Wu, const float* __restrict__ Wi, float* __restrict__ Gu,
         float* __restrict__ Gi, uint32_t* __restrict__ Tu, uint32_t* __restrict__ Ti, int d4,
         const int32_t* __restrict__ uid, const int32_t* __restrict__ pid, const int32_t* __restrict__ nid,
-        int64_t batch, float inv_batch, double* loss_acc, unsigned int* ticket, float* __restrict__ out) {
+        int64_t batch, float inv_batch, double inv_local, double* loss_acc, unsigned int* ticket, float* __restrict__ out) {
   constexpr int GPW = 32 / LPR;  // groups (triplets) per warp
   const int lane_in = threadIdx.x & (LPR - 1);
   const int64_t group = (int64_t(blockIdx.x) * kThreads + threadIdx.x) / LPR;
@@ -109,7 +109,7 @@ bpr_vec(const float* __restrict__ Wu, const float* __restrict__ Wi, float* __res
     }
   }
   (void)GPW;
-  if constexpr (TRAIN) finish_loss(double(loss_local), double(inv_batch), loss_acc, ticket, out);
+  if constexpr (TRAIN) finish_loss(double(loss_local), inv_local, loss_acc, ticket, out);
 }
 
 // Generic width (d % 4 != 0 or unaligned): one warp per triplet, rows re-read for the backward.
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kThreads)
 bpr_scalar(const float* __restrict__ Wu, const float* __restrict__ Wi, float* __restrict__ Gu,
            float* __restrict__ Gi, uint32_t* __restrict__ Tu, uint32_t* __restrict__ Ti, int d,
            const int32_t* __restrict__ uid, const int32_t* __restrict__ pid, const int32_t* __restrict__ nid,
-           int64_t batch, float inv_batch, double* loss_acc, unsigned int* ticket, float* __restrict__ out) {
+           int64_t batch, float inv_batch, double inv_local, double* loss_acc, unsigned int* ticket, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
   const int64_t n_warps = int64_t(gridDim.x) * kThreads >> 5;
@@ -146,14 +146,17 @@ bpr_scalar(const float* __restrict__ Wu, const float* __restrict__ Wi, float* __
       if (lane == 0) { mark_touched(Tu, ru, su); mark_touched(Ti, rp, sp); mark_touched(Ti, rn, sn); }
     }
   }
-  if constexpr (TRAIN) finish_loss(double(loss_local), double(inv_batch), loss_acc, ticket, out);
+  if constexpr (TRAIN) finish_loss(double(loss_local), inv_local, loss_acc, ticket, out);
 }
 
 template <bool TRAIN>
 int launch_bpr(brk_ctx* ctx, const float* Wu, const float* Wi, float* Gu, float* Gi, uint32_t* Tu, uint32_t* Ti,
-               int d, const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch, float* out,
-               cudaStream_t st) {
-  const float inv_batch = 1.0f / float(batch);
+               int d, const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch, int64_t global_batch,
+               float* out, cudaStream_t st) {
+  // gradients are scaled by 1/global_batch (data-parallel replicas sum their accumulators); the
+  // reported loss is the mean over the local batch
+  const float inv_batch = 1.0f / float(global_batch > 0 ? global_batch : batch);
+  const double inv_local = 1.0 / double(batch);
   double* acc = ctx->loss_acc + 0;
   unsigned int* ticket = ctx->tickets + 0;
   const int64_t cap = int64_t(ctx->sm_count) * (2048 / kThreads);
@@ -167,7 +170,7 @@ int launch_bpr(brk_ctx* ctx, const float* Wu, const float* Wi, float* Gu, float*
     const int grid = int(need < 1 ? 1 : (need < cap ? need : cap));
 #define BRK_BPR_CASE(L, N)                                                                          \
   bpr_vec<L, N, TRAIN><<<grid, kThreads, 0, st>>>(Wu, Wi, Gu, Gi, Tu, Ti, d4, u, p, n, batch, inv_batch, \
-                                                  acc, ticket, out)
+                                                  inv_local, acc, ticket, out)
     if (lpr == 1) BRK_BPR_CASE(1, 1);
     else if (lpr == 2) BRK_BPR_CASE(2, 1);
     else if (lpr == 4) BRK_BPR_CASE(4, 1);
@@ -181,8 +184,8 @@ int launch_bpr(brk_ctx* ctx, const float* Wu, const float* Wi, float* Gu, float*
   } else {
     int64_t need = (batch * 32 + kThreads - 1) / kThreads;
     const int grid = int(need < 1 ? 1 : (need < cap ? need : cap));
-    bpr_scalar<TRAIN><<<grid, kThreads, 0, st>>>(Wu, Wi, Gu, Gi, Tu, Ti, d, u, p, n, batch, inv_batch, acc,
-                                                 ticket, out);
+    bpr_scalar<TRAIN><<<grid, kThreads, 0, st>>>(Wu, Wi, Gu, Gi, Tu, Ti, d, u, p, n, batch, inv_batch, inv_local,
+                                                 acc, ticket, out);
   }
   BRK_LAUNCH_CHECK();
   return 0;
@@ -192,14 +195,14 @@ int launch_bpr(brk_ctx* ctx, const float* Wu, const float* Wi, float* Gu, float*
 
 extern "C" int brk_bpr_fwd_bwd(brk_ctx* ctx, const brk_table* user, const brk_table* item,
                                const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch,
-                               float* loss_out, void* stream) {
+                               int64_t global_batch, float* loss_out, void* stream) {
   BRK_REQUIRE(ctx && user && item && u && p && n, BRK_E_ARG, "brk_bpr_fwd_bwd: null argument");
   BRK_REQUIRE(user->w && user->g && item->w && item->g, BRK_E_ARG, "brk_bpr_fwd_bwd: table w/g missing");
   BRK_REQUIRE(user->d == item->d && user->d > 0, BRK_E_ARG, "brk_bpr_fwd_bwd: user d=%d item d=%d", user->d,
               item->d);
   BRK_REQUIRE(batch > 0, BRK_E_ARG, "brk_bpr_fwd_bwd: batch=%lld", (long long)batch);
   return launch_bpr<true>(ctx, user->w, item->w, user->g, item->g, user->touched, item->touched, user->d, u, p,
-                          n, batch, loss_out, (cudaStream_t)stream);
+                          n, batch, global_batch, loss_out, (cudaStream_t)stream);
 }
 
 extern "C" int brk_bpr_scores(brk_ctx* ctx, const float* user_w, const float* item_w, int32_t d,
@@ -207,7 +210,7 @@ extern "C" int brk_bpr_scores(brk_ctx* ctx, const float* user_w, const float* it
                               float* x_out, void* stream) {
   BRK_REQUIRE(ctx && user_w && item_w && u && p && n && x_out, BRK_E_ARG, "brk_bpr_scores: null argument");
   BRK_REQUIRE(d > 0 && batch > 0, BRK_E_ARG, "brk_bpr_scores: d=%d batch=%lld", d, (long long)batch);
-  return launch_bpr<false>(ctx, user_w, item_w, nullptr, nullptr, nullptr, nullptr, d, u, p, n, batch, x_out,
+  return launch_bpr<false>(ctx, user_w, item_w, nullptr, nullptr, nullptr, nullptr, d, u, p, n, batch, 0, x_out,
                            (cudaStream_t)stream);
 }
 
@@ -232,7 +235,7 @@ extern "C" int brk_bpr_train_steps(brk_ctx* ctx, const brk_table* user, const br
                 (long long)bi, (long long)n_batches);
     const int64_t off = bi * batch;
     const int64_t cnt = (off + batch <= total) ? batch : total - off;
-    int rc = brk_bpr_fwd_bwd(ctx, user, item, u + off, p + off, n + off, cnt, losses ? losses + k : nullptr, stream);
+    int rc = brk_bpr_fwd_bwd(ctx, user, item, u + off, p + off, n + off, cnt, 0, losses ? losses + k : nullptr, stream);
     if (rc) return rc;
     rc = lazy_adam ? brk_adam_rows(ctx, tabs, 2, h, step_dev, 1, stream)
                    : brk_adam_dense_keras(ctx, tabs, 2, h, step_dev, 1, stream);

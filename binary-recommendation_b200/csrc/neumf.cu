@@ -52,7 +52,7 @@ struct Acc {
 struct NeumfArgs {
   brk_table uMLP, iMLP, uMF, iMF, dense;
   const int32_t* u; const int32_t* i; const float* y;
-  int64_t B; int64_t first_index;
+  int64_t B; int64_t first_index; int64_t global_B;   // global_B scales the loss gradient (data parallel)
   float* h1; float* h2; float* dy1; float* dy2;   // feature-major [H, B]
   float* out;                                      // [B] predictions
   double* acc;                                     // Acc<H1,H2>::total doubles, zero on entry
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kTile) neumf_head(const NeumfArgs A) {
     const float o = 1.0f / (1.0f + expf(-logit));
     A.out[b0 + t] = o;
     const float yv = __ldg(A.y + b0 + t);
-    const float invB = 1.0f / float(A.B);
+    const float invB = 1.0f / float(A.global_B);
     if (A.loss_kind == 0) {
       const float e = o - yv;
       loss_local = e * e;
@@ -699,7 +699,7 @@ extern "C" int64_t brk_neumf_dense_floats(int32_t E, int32_t H1, int32_t H2, int
 extern "C" int64_t brk_neumf_acc_doubles(int32_t H1, int32_t H2) { return 4 * int64_t(H1) + 4 * int64_t(H2) + 1; }
 
 extern "C" int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, const int32_t* i,
-                              const float* y, int64_t batch, int64_t first_index, int32_t training,
+                              const float* y, int64_t batch, int64_t global_batch, int64_t first_index, int32_t training,
                               uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
                               float* out, float* loss_out, void* stream) {
   BRK_REQUIRE(ctx && m && u && i && ws && out, BRK_E_ARG, "brk_neumf_step: null argument");
@@ -712,7 +712,7 @@ extern "C" int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int3
   BRK_REQUIRE(ws->h1 && ws->h2 && ws->dy1 && ws->dy2 && ws->acc, BRK_E_ARG, "brk_neumf_step: workspace missing");
   NeumfArgs A;
   A.uMLP = m->uMLP; A.iMLP = m->iMLP; A.uMF = m->uMF; A.iMF = m->iMF; A.dense = m->dense;
-  A.u = u; A.i = i; A.y = y ? y : out; A.B = batch; A.first_index = first_index;
+  A.u = u; A.i = i; A.y = y ? y : out; A.B = batch; A.first_index = first_index; A.global_B = global_batch > 0 ? global_batch : batch;
   A.h1 = ws->h1; A.h2 = ws->h2; A.dy1 = ws->dy1; A.dy2 = ws->dy2; A.out = out; A.acc = ws->acc;
   A.bn_moving = m->bn_moving; A.loss_out = y ? loss_out : nullptr;
   A.drop_seed = dropout_seed; A.drop_epoch = dropout_epoch;

@@ -90,13 +90,14 @@ class Table:
     """An embedding table (or a flat dense parameter) resident in HBM with its gradient
     accumulator, optimizer slots and touched-row bitmask.  Layout: row-major fp32 [rows, d]."""
 
-    def __init__(self, w, slots=2, touched=True, slot_init=0.0):
+    def __init__(self, w, slots=2, touched=True, slot_init=0.0, g=None):
         self.w = _f32(w, "w")
         if self.w.dim() == 1:
             self.w = self.w.view(1, -1)
         self.rows, self.d = self.w.shape
         dev = self.w.device
-        self.g = torch.zeros_like(self.w)
+        # g may be a view into a flat gradient arena shared by several tables (one all-reduce per step)
+        self.g = torch.zeros_like(self.w) if g is None else g.view(self.rows, self.d)
         self.m = torch.full_like(self.w, slot_init) if slots >= 1 else None
         self.v = torch.zeros_like(self.w) if slots >= 2 else None
         self.touched = torch.zeros((self.rows + 31) // 32, dtype=torch.int32, device=dev) if touched else None
@@ -182,7 +183,7 @@ class Adagrad:
 # ----------------------------------------------------------------------------------------------
 # Fused BPR
 # ----------------------------------------------------------------------------------------------
-def bpr_fwd_bwd(user, item, u, p, n, loss_out=None):
+def bpr_fwd_bwd(user, item, u, p, n, loss_out=None, global_batch=0):
     """Fused triplet forward/backward (BPRModel.py:49-74,124-144); returns the device loss scalar."""
     u = _i32(u, "u"); p = _i32(p, "p"); n = _i32(n, "n")
     if not (u.numel() == p.numel() == n.numel()):
@@ -191,7 +192,7 @@ def bpr_fwd_bwd(user, item, u, p, n, loss_out=None):
         loss_out = torch.empty(1, dtype=torch.float32, device=user.w.device)
     us, it = user.c_struct(), item.c_struct()
     N.check(N.lib().brk_bpr_fwd_bwd(N.ctx(user.w.device), C.byref(us), C.byref(it), N.ptr(u), N.ptr(p),
-                                    N.ptr(n), u.numel(), N.ptr(loss_out), N.stream_ptr()), "brk_bpr_fwd_bwd")
+                                    N.ptr(n), u.numel(), global_batch, N.ptr(loss_out), N.stream_ptr()), "brk_bpr_fwd_bwd")
     return loss_out
 
 

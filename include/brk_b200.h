@@ -103,10 +103,13 @@ int brk_philox4x32_10(brk_ctx* ctx, const uint32_t* ctr, int64_t n, uint32_t key
  *   x = <u,p> - <u,n>;  l = 1 - sigmoid(x);  loss = mean(l);
  *   user.g[u] += g(p-n), item.g[p] += g u, item.g[n] -= g u,  g = -s(1-s)/B.
  * loss_out[0] receives the batch mean.  Row gradients are accumulated into user->g / item->g
- * (which must be zero on entry -- the optimizer calls below re-zero them). */
+ * (which must be zero on entry -- the optimizer calls below re-zero them).
+ * global_batch (0 = batch): data-parallel replicas pass the summed batch of all replicas so that
+ * the SUM of their accumulators (one all-reduce) is the gradient of the global mean loss -- the
+ * synchronous mirrored training of src/models/RModel.py:119-121. */
 int brk_bpr_fwd_bwd(brk_ctx* ctx, const brk_table* user, const brk_table* item,
                     const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch,
-                    float* loss_out, void* stream);
+                    int64_t global_batch, float* loss_out, void* stream);
 /* n_steps x (brk_bpr_fwd_bwd + Adam) enqueued by one call: the inner loop of model.fit
  * (src/models/BPRModel.py:109, src/models/bpr.py:220-223).  u/p/n are device arrays of `total`
  * triplets cut into batches of `batch`; batch_index_host[k] (HOST array) names the batch step k
@@ -160,7 +163,9 @@ int brk_adagrad_dense(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, float
  * must be ZERO before the first call (every call leaves them zero again).
  * training != 0: accumulates all gradients into the tables' g (to be consumed by the optimizer
  * calls), updates bn_moving, writes out[batch] (predictions) and loss_out[0].
- * training == 0: inference with the moving statistics; y may be NULL (then no loss). */
+ * training == 0: inference with the moving statistics; y may be NULL (then no loss).
+ * global_batch (0 = batch) scales the loss gradient for data-parallel replicas; BatchNorm statistics
+ * stay per replica (MirroredStrategy's default). */
 typedef struct brk_neumf_model {
   brk_table uMLP, iMLP, uMF, iMF, dense;
   float*  bn_moving;
@@ -174,7 +179,7 @@ typedef struct brk_neumf_workspace {
 int64_t brk_neumf_dense_floats(int32_t E, int32_t H1, int32_t H2, int32_t H3);
 int64_t brk_neumf_acc_doubles(int32_t H1, int32_t H2);
 int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, const int32_t* i,
-                   const float* y, int64_t batch, int64_t first_index, int32_t training,
+                   const float* y, int64_t batch, int64_t global_batch, int64_t first_index, int32_t training,
                    uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
                    float* out, float* loss_out, void* stream);
 
