@@ -39,6 +39,14 @@ class brk_neumf_workspace(C.Structure):
                 ("acc", C.c_void_p)]
 
 
+class brk_tower(C.Structure):
+    _fields_ = [("emb", brk_table), ("dense", brk_table), ("E", C.c_int32), ("S", C.c_int32)]
+
+
+class brk_twotower_workspace(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("eu", "ei", "q", "c", "dq", "dc", "scores", "ones", "acc")]
+
+
 _P, _I32, _I64, _U32, _F32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float
 
 # name -> (restype, argtypes); mirrors include/brk_b200.h one to one.
@@ -65,6 +73,10 @@ SIGNATURES = {
     "brk_neumf_acc_doubles": (C.c_int64, [_I32, _I32]),
     "brk_neumf_step": (C.c_int, [_P, C.POINTER(brk_neumf_model), _P, _P, _P, _I64, _I64, _I64, _I32, _U32, _U32,
                                  C.POINTER(brk_neumf_workspace), _P, _P, _P]),
+    "brk_sgemm": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F32, _I32, _P]),
+    "brk_tower_forward": (C.c_int, [_P, C.POINTER(brk_tower), _P, _I64, _P, _P, _P]),
+    "brk_twotower_step": (C.c_int, [_P, C.POINTER(brk_tower), C.POINTER(brk_tower), _P, _P, _P, _P, _I64, _I32, _I32,
+                                    C.POINTER(brk_twotower_workspace), _P, _P]),
     "brk_bf16_padded_dim": (C.c_int32, [_I32]),
     "brk_rows_to_bf16": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _P]),
     "brk_score_topk_workspace_bytes": (C.c_int64, [_P, _I64, _I64, _I32]),

@@ -1,0 +1,277 @@
+"""Two-tower retrieval model -- drop-in mirror of the reference's trainers/twoTower.py
+(TwoTowerModel with the same constructor arguments and method names, splitTrainTest,
+crossValidation).
+
+Underneath: two embedding tables + two linear Dense layers resident in HBM; towers, in-batch softmax
+(TFRS Retrieval semantics) or rdZero BCE, all gradients in csrc/twotower.cu; Keras Adagrad in
+csrc/optim.cu; full-catalog scoring + top-K on tcgen05 (csrc/topk.cu); metrics in csrc/metrics.cu.
+
+Differences from the reference, stated once:
+  * `trainers.model_utils.getOptimizer` does not exist in the reference tree (twoTower.py:5); here
+    compile() accepts hotpath.Adagrad / hotpath.Adam objects or the strings "Adagrad" / "Adam";
+  * crossValidation takes in-memory folds (lists of dicts with the userKey / itemKey [/ resKey]
+    columns) instead of prompting for SMB credentials (twoTower.py:130-134);
+  * StringLookup is a host dictionary: vocabulary entry j -> row j + 2 (0 mask, 1 OOV), as TF 2.3/2.4.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import distributed as D
+from . import hotpath as H
+from .topKmetrics import topKMetrics
+
+
+class StringLookup:
+    """tf.keras.layers.experimental.preprocessing.StringLookup(vocabulary=...) (twoTower.py:33,35)."""
+
+    def __init__(self, vocabulary):
+        self.vocabulary = list(vocabulary)
+        self._map = {v: j + 2 for j, v in enumerate(self.vocabulary)}
+
+    def __call__(self, values):
+        return np.fromiter((self._map.get(v, 1) for v in values), dtype=np.int32, count=len(values))
+
+
+class Tower:
+    def __init__(self, rows, E, S, rng, device):
+        self.E, self.S = E, S
+        self.emb = H.Table(torch.from_numpy(H.keras_embedding_init(rows, E, rng)).to(device), slots=1,
+                           slot_init=H.Adagrad.INITIAL_ACCUMULATOR)
+        self._W0 = None
+
+    def init_dense(self, rng, device):
+        lim = np.sqrt(6.0 / (self.E + self.S))
+        W = rng.uniform(-lim, lim, size=(self.E, self.S)).astype(np.float32)
+        flat = np.concatenate([W.reshape(-1), np.zeros(self.S, np.float32)])
+        pad = (-len(flat)) % 4
+        self.dense = H.Table(torch.from_numpy(np.pad(flat, (0, pad))).to(device).view(1, -1), slots=1, touched=False,
+                             slot_init=H.Adagrad.INITIAL_ACCUMULATOR)
+
+    def c_struct(self):
+        return N.brk_tower(self.emb.c_struct(), self.dense.c_struct(), self.E, self.S)
+
+    @property
+    def W(self):
+        return self.dense.w.view(-1)[:self.E * self.S].view(self.E, self.S)
+
+    @property
+    def b(self):
+        return self.dense.w.view(-1)[self.E * self.S:self.E * self.S + self.S]
+
+
+class TwoTowerModel:
+    def __init__(self, embedDim, nbrItem, nbrUser, userKey, itemKey, usersId, itemsId, eval_batch_size=8000,
+                 loss=None, rdZero=False, resKey=None, semb=100, seed=42, device=None):
+        self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+        self.embedDim, self.nbrItem, self.nbrUser = embedDim, nbrItem, nbrUser
+        self.userKey, self.itemKey, self.resKey = userKey, itemKey, resKey
+        self.eval_batch_size, self.rdZero, self.semb = eval_batch_size, rdZero, semb
+        self.userTowerIn = StringLookup(usersId)
+        self.itemTowerIn = StringLookup(itemsId)
+        rng = np.random.Generator(np.random.Philox(key=seed))
+        # draw order = oracle/twotower.py: Eu, Ei, Wu, Wi
+        self.userTower = Tower(nbrUser + 2, embedDim, semb, rng, self.device)
+        self.itemTower = Tower(nbrItem + 2, embedDim, semb, rng, self.device)
+        self.userTower.init_dense(rng, self.device)
+        self.itemTower.init_dense(rng, self.device)
+        self.bruteForceLayer = None
+        self._candidates = None
+        self.optimizer = None
+        self.computeLoss = self.computeLossRdZero if rdZero else self.computeLossTfrs
+        self._ws_batch = 0
+        self.history = {"loss": []}
+
+    # ---- Keras-like surface -----------------------------------------------------------------------
+    def compile(self, optimizer="Adagrad", loss=None, learningRate=0.1):
+        if isinstance(optimizer, str):
+            name = optimizer.lower()
+            if name == "adagrad":
+                optimizer = H.Adagrad(learningRate)
+            else:
+                raise ValueError(f"two-tower training is built for Adagrad (twoTower.py:278-279), got {optimizer}")
+        self.optimizer = optimizer
+        return self
+
+    def _workspace(self, B):
+        if B > self._ws_batch:
+            dev, S = self.device, self.semb
+            f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+            self._bufs = dict(eu=f(B, self.embedDim), ei=f(B, self.embedDim), q=f(B, S), c=f(B, S), dq=f(B, S),
+                              dc=f(B, S), scores=f(B, B) if not self.rdZero else None,
+                              ones=torch.ones(B, dtype=torch.float32, device=dev),
+                              acc=torch.zeros(1, dtype=torch.float64, device=dev))
+            self._ws_batch = B
+        b = self._bufs
+        return N.brk_twotower_workspace(*[b[k].data_ptr() if b[k] is not None else None
+                                          for k in ("eu", "ei", "q", "c", "dq", "dc", "scores", "ones", "acc")])
+
+    def _ids(self, info):
+        dev = self.device
+        u = torch.from_numpy(self.userTowerIn(info[self.userKey])).to(dev)
+        i = torch.from_numpy(self.itemTowerIn(info[self.itemKey])).to(dev)
+        return u, i
+
+    def _step(self, u, i, labels, training, loss_out=None):
+        B = u.numel()
+        loss_out = loss_out if loss_out is not None else torch.empty(1, dtype=torch.float32, device=self.device)
+        ws = self._workspace(B)
+        ut, it = self.userTower.c_struct(), self.itemTower.c_struct()
+        N.check(N.lib().brk_twotower_step(N.ctx(self.device), C.byref(ut), C.byref(it), N.ptr(u), N.ptr(i), N.ptr(i),
+                                          N.ptr(labels) if labels is not None else None, B, 1 if self.rdZero else 0,
+                                          1 if training else 0, C.byref(ws), N.ptr(loss_out), N.stream_ptr()),
+                "brk_twotower_step")
+        return loss_out
+
+    def computeEmb(self, info):
+        """(user embeddings [B,S], item embeddings [B,S]) -- twoTower.py:77-80."""
+        u, i = self._ids(info)
+        return self._tower_forward(self.userTower, u), self._tower_forward(self.itemTower, i)
+
+    def _tower_forward(self, tower, ids):
+        n = ids.numel()
+        emb = torch.empty(n, tower.E, dtype=torch.float32, device=self.device)
+        out = torch.empty(n, tower.S, dtype=torch.float32, device=self.device)
+        t = tower.c_struct()
+        N.check(N.lib().brk_tower_forward(N.ctx(self.device), C.byref(t), N.ptr(ids), n, N.ptr(emb), N.ptr(out),
+                                          N.stream_ptr()), "brk_tower_forward")
+        return out
+
+    def computeLossTfrs(self, usersCaracteristics, itemCaracteristics, info):
+        """In-batch softmax loss of already computed tower outputs (twoTower.py:82-83), forward only."""
+        scores = usersCaracteristics @ itemCaracteristics.T
+        ids = torch.from_numpy(self.itemTowerIn(info[self.itemKey])).to(self.device)
+        B = scores.shape[0]
+        dup = (ids[:, None] == ids[None, :]).float() - torch.eye(B, device=self.device)
+        scores = scores + dup * (float(np.finfo(np.float32).min) / 100.0)
+        return torch.nn.functional.cross_entropy(scores, torch.arange(B, device=self.device), reduction="sum")
+
+    def computeLossRdZero(self, usersCaracteristics, itemCaracteristics, info):
+        y = torch.as_tensor(np.asarray(info[self.resKey], dtype=np.float32)).to(self.device)
+        return torch.nn.functional.binary_cross_entropy_with_logits((usersCaracteristics * itemCaracteristics).sum(1), y)
+
+    def _labels(self, info):
+        if not self.rdZero:
+            return None
+        return torch.as_tensor(np.asarray(info[self.resKey], dtype=np.float32)).to(self.device)
+
+    def train_step(self, info):
+        """One fused forward/backward + Adagrad step; returns {"loss": device scalar} (twoTower.py:89-102).
+        Under torch.distributed the replicas' SUM-reduced gradients are summed by one all-reduce per
+        tower (MirroredStrategy sums per-replica gradients of a SUM-reduced loss)."""
+        if self.optimizer is None:
+            self.compile()
+        u, i = self._ids(info)
+        loss = self._step(u, i, self._labels(info), True)
+        if D.world_size() > 1:
+            for t in (self.userTower.emb, self.itemTower.emb, self.userTower.dense, self.itemTower.dense):
+                D.all_reduce_sum_(t.g)
+        self.optimizer.apply([self.userTower.emb, self.itemTower.emb], dense=[self.userTower.dense, self.itemTower.dense])
+        return {"loss": loss}
+
+    def test_step(self, info):
+        u, i = self._ids(info)
+        return {"loss": self._step(u, i, self._labels(info), False)}
+
+    def fit(self, dataset, epochs=1, verbose=0):
+        """dataset: iterable of info dicts (batches), replayed every epoch like a cached tf.data set."""
+        batches = list(dataset)
+        for e in range(epochs):
+            tot = 0.0
+            for info in batches:
+                tot += float(self.train_step(info)["loss"].item())
+            self.history["loss"].append(tot / max(len(batches), 1))
+            if verbose:
+                print(f"epoch {e + 1}: loss {self.history['loss'][-1]:.6f}")
+        return self
+
+    # ---- retrieval --------------------------------------------------------------------------------------
+    def setCandidates(self, items, k):
+        """BruteForce(k).index(itemTower(items), identifiers=items) -- twoTower.py:64-69."""
+        items = list(items)
+        vecs = []
+        for s in range(0, len(items), self.eval_batch_size):
+            ids = torch.from_numpy(self.itemTowerIn(items[s:s + self.eval_batch_size])).to(self.device)
+            vecs.append(self._tower_forward(self.itemTower, ids))
+        self._candidates = items
+        self.bruteForceLayer = H.BruteForceIndex(k).index(torch.cat(vecs))
+        return self
+
+    def call(self, info):
+        """userTower(info) -> BruteForce: (scores [U,k], identifiers [U,k] as list of lists) -- :60-62."""
+        ids = torch.from_numpy(self.userTowerIn(list(info))).to(self.device)
+        vals, idx = self.bruteForceLayer(self._tower_forward(self.userTower, ids))
+        return vals, idx
+
+    __call__ = call
+
+    def predict(self, usersId, batch_size=5000):
+        """(scores ndarray [U,k], identifiers list-of-lists [U][k]) like model.predict(usersId) at :230."""
+        usersId = list(usersId)
+        vs, ixs = [], []
+        for s in range(0, len(usersId), batch_size):
+            v, ix = self.call(usersId[s:s + batch_size])
+            vs.append(v); ixs.append(ix)
+        v = torch.cat(vs).cpu().numpy(); ix = torch.cat(ixs).cpu().numpy()
+        idents = [[self._candidates[j] for j in row] for row in ix]
+        return v, idents
+
+    def score_vectors(self, usersId, itemsId):
+        """(user vectors, item vectors) for topKmetrics.topKRatings."""
+        u = torch.from_numpy(self.userTowerIn(list(usersId))).to(self.device)
+        i = torch.from_numpy(self.itemTowerIn(list(itemsId))).to(self.device)
+        return self._tower_forward(self.userTower, u), self._tower_forward(self.itemTower, i)
+
+
+def batch_dataset(data, batchSize, keys):
+    """tf.data.Dataset.from_tensor_slices(dict(df)).batch(batchSize): list of info dicts."""
+    n = len(data[keys[0]])
+    return [{k: data[k][s:s + batchSize] for k in keys} for s in range(0, n, batchSize)]
+
+
+def splitTrainTest(data, ratio, seed=0):
+    """Shuffle once, then take/skip (twoTower.py:113-122); data is a dict of equally long columns."""
+    keys = list(data)
+    n = len(data[keys[0]])
+    perm = np.random.Generator(np.random.Philox(key=seed)).permutation(n)
+    cut = int(n * ratio)
+    take = lambda idx: {k: [data[k][j] for j in idx] for k in keys}
+    return take(perm[:cut]), take(perm[cut:])
+
+
+def crossValidation(dataSets, k, learningRate, optimiser, loss, epoch, embNum, batchSize, randomZero=False,
+                    rdZeroDataSets=None, testBatchSize=5000, semb=64, userKey="CUSTOMER_ID", itemKey="MATERIAL",
+                    resKey="RATING_TYPE", seed=42, verbose=0):
+    """k-fold cross-validation of twoTower.py:125-272 on in-memory folds: train on all folds but one,
+    index the whole catalog, top-k for every user, topKMetrics against the held-out fold and against
+    the training folds ("full_" keys), averaged over folds."""
+    folds = list(dataSets)
+    usersId = list(dict.fromkeys(u for f in folds for u in f[userKey]))
+    matId = list(dict.fromkeys(m for f in folds for m in f[itemKey]))
+    train_folds = list(rdZeroDataSets) if randomZero else folds
+    keys = [userKey, itemKey] + ([resKey] if randomZero else [])
+    res, fullRes = [], []
+    for it in range(len(folds)):
+        test = folds[it]
+        rest = [f for j, f in enumerate(train_folds) if j != it]
+        train = {kk: [x for f in rest for x in f[kk]] for kk in keys}
+        perm = np.random.Generator(np.random.Philox(key=seed + it)).permutation(len(train[userKey]))
+        train = {kk: [train[kk][j] for j in perm] for kk in keys}          # shuffle once (:196)
+        model = TwoTowerModel(embNum, len(matId), len(usersId), userKey, itemKey, usersId, matId,
+                              eval_batch_size=batchSize, loss=loss, rdZero=randomZero, resKey=resKey, semb=semb, seed=seed)
+        model.compile(optimiser, learningRate=learningRate)
+        model.fit(batch_dataset(train, batchSize, keys), epochs=epoch, verbose=verbose)
+        model.setCandidates(matId, k)
+        scores, idents = model.predict(usersId, batch_size=testBatchSize)
+        topk = [(u, [(scores[r][j], idents[r][j]) for j in range(len(idents[r]))]) for r, u in enumerate(usersId)]
+        res.append(topKMetrics(topk, list(zip(test[userKey], test[itemKey])), usersId, matId))
+        others = [f for j, f in enumerate(folds) if j != it]
+        fullRes.append(topKMetrics(topk, [(u, m) for f in others for u, m in zip(f[userKey], f[itemKey])], usersId, matId))
+    averageMetrics = {}
+    for m in res[0]:
+        averageMetrics[m] = sum(r[m] for r in res) / len(folds)
+    for m in fullRes[0]:
+        averageMetrics["full_" + m] = sum(r[m] for r in fullRes) / len(folds)
+    return averageMetrics

@@ -183,6 +183,38 @@ int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, con
                    uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
                    float* out, float* loss_out, void* stream);
 
+/* ---- two-tower: towers + in-batch softmax / rdZero loss + backward -------------------------------
+ * Stands in for TwoTowerModel.computeEmb / computeLossTfrs / computeLossRdZero / train_step
+ * (trainers/twoTower.py:77-102) and tfrs.tasks.Retrieval (:47,83).  A tower is an embedding table
+ * [rows, E] plus ONE flat dense block: the Keras Dense kernel W [E, S] row-major followed by the bias
+ * [S] (twoTower.py:40-41: linear, no activation).
+ *   brk_tower_forward : out[n,S] = table[ids] W + b (emb_out [n,E] receives the gathered rows)
+ *   brk_twotower_step : mode 0 -- scores = Q C^T [B,B]; off-diagonal entries whose candidate id
+ *     (cand_ids, may be NULL) equals the row's positive id get finfo(float32).min/100 added;
+ *     loss = sum_b -log softmax_b[b] (reduction SUM, as TFRS).  mode 1 (rdZero) --
+ *     sigmoid(<q_b, c_b>) against labels[b], mean binary cross-entropy.
+ *     training != 0 additionally accumulates every gradient (emb.g rows, dense.g) for the optimizer.
+ * Workspace (caller-owned, floats): eu [B,Eu], ei [B,Ei], q, c, dq, dc [B,S], scores [B,B] (mode 0),
+ * ones [B] filled with 1.0, acc 1 double zero-initialised.
+ *   brk_sgemm : C (+)= alpha opA(A) opB(B) (+ bias); trans_a: A stored [K,M]; trans_b: B stored [N,K]. */
+typedef struct brk_tower {
+  brk_table emb, dense;
+  int32_t E, S;
+} brk_tower;
+typedef struct brk_twotower_workspace {
+  float *eu, *ei, *q, *c, *dq, *dc, *scores, *ones;
+  double* acc;
+} brk_twotower_workspace;
+int brk_sgemm(brk_ctx* ctx, const float* A, const float* B, float* C, const float* bias, int32_t M,
+              int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t trans_a, int32_t trans_b,
+              float alpha, int32_t accumulate, void* stream);
+int brk_tower_forward(brk_ctx* ctx, const brk_tower* t, const int32_t* ids, int64_t n, float* emb_out,
+                      float* out, void* stream);
+int brk_twotower_step(brk_ctx* ctx, const brk_tower* user, const brk_tower* item, const int32_t* u,
+                      const int32_t* i, const int32_t* cand_ids, const float* labels, int64_t batch,
+                      int32_t mode, int32_t training, const brk_twotower_workspace* ws, float* loss_out,
+                      void* stream);
+
 /* ---- K7/K8: full-catalog scoring + top-K ------------------------------------------------------
  * Stands in for tfrs.layers.factorized_top_k.BruteForce(k).index(candidates) + call(queries)
  * (trainers/twoTower.py:64-69,60-62,229-230; src/origin_models/svd/SVD.py:424-432), for

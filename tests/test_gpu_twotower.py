@@ -1,0 +1,112 @@
+"""GPU parity of the two-tower step (towers, in-batch softmax with accidental-hit removal / rdZero BCE,
+all gradients, Keras Adagrad) against oracle/twotower.py, plus retrieval and cross-validation.
+fp32 tolerances: loss rtol 1e-5; gradients rtol 1e-3 / atol 1e-6; weights after 5 Adagrad steps
+rtol 1e-4 / atol 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import topk as OT
+from oracle.twotower import TwoTowerOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(dev, nu, ni, E, S, rdZero=False):
+    from binrec_b200.twoTower import TwoTowerModel
+    users = [f"u{j}" for j in range(nu)]; items = [f"m{j}" for j in range(ni)]
+    m = TwoTowerModel(E, ni, nu, "CUSTOMER_ID", "MATERIAL", users, items, rdZero=rdZero, resKey="RATING_TYPE", semb=S,
+                      device=dev)
+    m.compile("Adagrad", learningRate=0.1)
+    o = TwoTowerOracle(nu, ni, E, S, rdZero=rdZero)
+    assert np.array_equal(m.userTower.emb.w.cpu().numpy(), o.t["Eu"].detach().numpy())
+    assert np.array_equal(m.itemTower.W.cpu().numpy(), o.t["Wi"].detach().numpy())
+    return m, o, users, items
+
+
+def _batch(rng, users, items, B, rd=False):
+    u = rng.integers(0, len(users), B); i = (len(items) * rng.random(B) ** 2).astype(np.int64)   # repeated items
+    info = {"CUSTOMER_ID": [users[j] for j in u], "MATERIAL": [items[j] for j in i]}
+    if rd:
+        info["RATING_TYPE"] = (rng.random(B) < 0.5).astype(np.float32)
+    return info, u + 2, i + 2                      # StringLookup offset
+
+
+@pytest.mark.parametrize("E,S,B", [(128, 128, 1000), (75, 50, 1000), (16, 8, 77), (64, 64, 2048)])
+def test_twotower_softmax_step_matches_oracle(dev, E, S, B):
+    m, o, users, items = _mk(dev, 300, 200, E, S)
+    rng = np.random.default_rng(B)
+    info, ui, ii = _batch(rng, users, items, B)
+    assert len(set(ii.tolist())) < B                                     # accidental hits are exercised
+    lref = o.loss_and_grads(ui, ii, cand_ids=ii)
+    uid, iid = m._ids(info)
+    loss = m._step(uid, iid, None, True)
+    np.testing.assert_allclose(loss.item(), float(lref), rtol=1e-5)
+    for tab, name in ((m.userTower.emb, "Eu"), (m.itemTower.emb, "Ei")):
+        np.testing.assert_allclose(tab.g.cpu().numpy(), o.t[name].grad.numpy(), rtol=1e-3, atol=1e-6, err_msg=name)
+    for tw, wn, bn in ((m.userTower, "Wu", "bu"), (m.itemTower, "Wi", "bi")):
+        g = tw.dense.g.view(-1)
+        np.testing.assert_allclose(g[:E * S].view(E, S).cpu().numpy(), o.t[wn].grad.numpy(), rtol=1e-3, atol=2e-6, err_msg=wn)
+        # the item-bias gradient is mathematically zero (rows of softmax - I sum to 0): both sides hold
+        # rounding noise of a B-term sum, hence the absolute tolerance
+        np.testing.assert_allclose(g[E * S:E * S + S].cpu().numpy(), o.t[bn].grad.numpy(), rtol=1e-3, atol=2e-5, err_msg=bn)
+    # eval mode: same loss, no gradient side effects
+    for t in (m.userTower.emb, m.itemTower.emb, m.userTower.dense, m.itemTower.dense):
+        t.g.zero_()
+    l2 = m._step(uid, iid, None, False)
+    assert abs(l2.item() - loss.item()) <= 1e-6 * abs(loss.item()) and not m.userTower.emb.g.any().item()
+
+
+def test_twotower_five_adagrad_steps_and_rdzero(dev):
+    for rd in (False, True):
+        m, o, users, items = _mk(dev, 300, 200, 32, 16, rdZero=rd)
+        rng = np.random.default_rng(9)
+        for step in range(5):
+            info, ui, ii = _batch(rng, users, items, 256, rd)
+            lref = o.step(ui, ii, cand_ids=ii, labels=info.get("RATING_TYPE"))
+            lgot = m.train_step(info)["loss"]
+            np.testing.assert_allclose(lgot.item(), lref, rtol=1e-4)
+        np.testing.assert_allclose(m.userTower.emb.w.cpu().numpy(), o.t["Eu"].detach().numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(m.itemTower.emb.w.cpu().numpy(), o.t["Ei"].detach().numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(m.userTower.W.cpu().numpy(), o.t["Wu"].detach().numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(m.itemTower.b.cpu().numpy(), o.t["bi"].detach().numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(m.userTower.emb.m.cpu().numpy(), o.acc["Eu"].numpy(), rtol=1e-4, atol=1e-7)
+        q, c = m.computeEmb(info)
+        np.testing.assert_allclose(q.cpu().numpy(), o.user_vectors(ui), rtol=1e-4, atol=1e-6)
+        assert not m.userTower.emb.g.any().item() and not m.itemTower.dense.g.any().item()
+
+
+def test_twotower_retrieval_and_metrics(dev):
+    from binrec_b200.topKmetrics import topKMetrics
+    m, o, users, items = _mk(dev, 300, 200, 32, 16)
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        info, ui, ii = _batch(rng, users, items, 256)
+        m.train_step(info); o.step(ui, ii, cand_ids=ii)
+    m.setCandidates(items, 10)
+    scores, idents = m.predict(users, batch_size=128)
+    Q = o.user_vectors(np.arange(300) + 2); Cm = o.item_vectors(np.arange(200) + 2)
+    S = OT.scores(Q, Cm, "bf16")
+    rv, ri = OT.topk_from_scores(S, 10)
+    np.testing.assert_allclose(scores, rv, rtol=1e-3, atol=1e-4)
+    got = np.array([[int(x[1:]) for x in row] for row in idents])
+    # every returned item is a genuine top-10 member up to the bf16 / fp32 noise
+    assert (np.take_along_axis(S, got, 1) >= rv[:, 9:10] - 1e-4).all()
+    topk = [(u, [(scores[r][j], idents[r][j]) for j in range(10)]) for r, u in enumerate(users)]
+    res = topKMetrics(topk, [(users[a], items[b]) for a, b in zip(rng.integers(0, 300, 500), rng.integers(0, 200, 500))],
+                      users, items)
+    assert res["tp"] + res["fp"] == 3000 and 0 <= res["hitRate"] <= 1
+
+
+def test_crossvalidation_runs_and_learns(dev):
+    from binrec_b200.twoTower import crossValidation
+    rng = np.random.default_rng(2)
+    # users prefer items of their own cluster: a learnable structure
+    nu, ni = 120, 60
+    folds = []
+    for f in range(3):
+        u = rng.integers(0, nu, 1500); m = (u % 6) * 10 + rng.integers(0, 10, 1500)
+        folds.append({"CUSTOMER_ID": [f"c{j}" for j in u], "MATERIAL": [f"m{j}" for j in m]})
+    res = crossValidation(folds, 10, 0.1, "Adagrad", None, 3, 16, 500, semb=8)
+    assert set(res) >= {"tp", "precision", "recall", "hitRate", "full_hitRate"}
+    assert res["hitRate"] > 0.5          # random guessing of 10 of 60 items would reach far less per positive
