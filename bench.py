@@ -214,15 +214,25 @@ def product_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def flush_l2():
+        # write a buffer larger than L2, then read it back: evicts everything and leaves the lines clean,
+        # so the timed kernels' cold misses are not also charged the write-back of the flush's own data
+        flush.zero_()
+        flush_sink.copy_(flush[:flush_sink.numel()] + flush[-flush_sink.numel():])
+        torch.sum(flush, dim=0, out=flush_sum)
+
+    flush_sink = torch.empty(1024, dtype=torch.float32, device=dev)
+    flush_sum = torch.empty((), dtype=torch.float32, device=dev)
+
     # ---- (1) device-resident value: K steps, L2 flushed between steps, CUDA events per step ------
     for k in range(W):
-        flush.zero_(); one_step(k)
+        flush_l2(); one_step(k)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     sampler = ClockSampler(physical_gpu_index(local)); sampler.start()
     barrier()
     wall0 = time.perf_counter()
     for k in range(K):
-        flush.zero_()
+        flush_l2()
         one_step(W + k, evs[k])
     barrier()
     wall = time.perf_counter() - wall0
@@ -262,19 +272,32 @@ def product_arm(args):
         loss = net.train_on_batch(du, dp, dn)
         hloss[k:k + 1].copy_(loss, non_blocking=True)
 
-    for k in range(W):
-        e2e_step(k)
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for k in range(K):
-        e2e_step(W + k)
-    e1.record()
-    barrier()
+    if world == 1:
+        # one C call enqueues K x (H2D ids, sampler, fused step, Adam, loss D2H): BPRNet.train_steps_from_host
+        net.train_steps_from_host(hu, hp, order[:W], BATCH, 7, 1, hloss[:W])
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        net.train_steps_from_host(hu, hp, order, BATCH, 7, 1, hloss[W:W + K])
+        e1.record()
+        barrier()
+        e2e_launches = 3 * K
+    else:
+        for k in range(W):
+            e2e_step(k)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for k in range(K):
+            e2e_step(W + k)
+        e1.record()
+        barrier()
+        e2e_launches = 3 * K
     e2e_wall = time.perf_counter() - t0
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * e2e_wall)
     clocks = sampler.stop()
     assert np.isfinite(hloss[W:W + K].numpy()).all()
+    extras = secondary_measurements(dev) if (world == 1 and not args.no_extras) else None
 
     # ---- max over ranks ---------------------------------------------------------------------------
     t = torch.tensor([total_ms, hot_ms, e2e_ms, float(fb_ms.mean())], dtype=torch.float64, device=dev)
@@ -292,8 +315,8 @@ def product_arm(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE.json configs[1]: BPR MF d=64, ML-1M shape (6040x3706, 1000209 positives), "
                                    "1 Philox negative/positive, loss 1-sigmoid, exact Keras Adam(1e-3)",
-                       "batch": BATCH, "l2": "flushed between timed steps (256 MiB memset); step time = CUDA events "
-                                             "around the step's two kernels, flush excluded",
+                       "batch": BATCH, "l2": "flushed between timed steps (256 MiB written, then read back so the lines "
+                                             "are clean); step time = CUDA events around the step's kernels, flush excluded",
                        "parallelism": (f"mirrored data parallel x{world}: local batch {BATCH}, one NCCL all-reduce of the "
                                        f"2.5 MB gradient arena per step") if world > 1 else "single GPU",
                        "wall_s_timed_region": wall},
@@ -307,10 +330,14 @@ def product_arm(args):
                                  "from L2 within the launch; REDs resolve in L2"},
             "e2e": {"value": world * K * BATCH / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": 2 * BATCH * 4, "d2h_bytes_per_step": 4,
-                    "note": "pinned host ids -> H2D, Philox negatives on device, fused step, loss D2H (async, one sync per K steps)"},
+                    "gpu_launches": e2e_launches,
+                    "note": "BPRNet.train_steps_from_host: pinned host ids -> H2D, Philox negatives on device, fused step, "
+                            "Adam, loss D2H per step (all asynchronous on one stream, one sync per K steps)"},
             "gpu_launches": 2 * K,            # per rank: fused fwd/bwd + fused Adam (the NCCL all-reduce kernel is not ours)
             "clocks": clocks,
         }
+        if extras:
+            line["extras"] = extras
         if world == 1 and not args.no_cpu_baseline:
             val, done, threads, dt = cpu_loop(users, items, U, I, steps=100000, warmup=3, time_budget_s=12.0)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
@@ -321,6 +348,66 @@ def product_arm(args):
         dist.destroy_process_group()
 
 
+def secondary_measurements(dev):
+    """Other BASELINE.json configs on one GPU, short runs (CUDA events, back-to-back steps): NeuMF
+    (configs[0] shape), two-tower in-batch softmax + full-catalog top-K (configs[2])."""
+    from binrec_b200 import hotpath as H
+    from binrec_b200.NeuMFModel import NeuMFNet
+    from binrec_b200.twoTower import TwoTowerModel
+    out = {}
+
+    def timed(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / iters
+
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    U, I, B = 6040, 3706, BATCH
+    net = NeuMFNet(U, I, 32, dropout=0.2, device=dev)
+    u = torch.randint(0, U, (B,), generator=g, device=dev, dtype=torch.int32)
+    i = torch.randint(0, I, (B,), generator=g, device=dev, dtype=torch.int32)
+    y = (torch.rand(B, generator=g, device=dev) < 0.2).float()
+    o = torch.empty(B, device=dev); l = torch.empty(1, device=dev)
+    s = timed(lambda: net.train_on_batch(u, i, y, out=o, loss_out=l), 50)
+    out["neumf_train"] = {"value": B / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
+                          "config": "NeuMF F=32 (MLP 64-32-16-8, BN, dropout 0.2, MSE), ML-1M tables, batch 16384, Keras Adam"}
+    users = list(range(U)); items = list(range(I))
+    tt = TwoTowerModel(128, I, U, "u", "i", users, items, semb=128, device=dev)
+    tt.compile("Adagrad", learningRate=0.1)
+    Bt = 1000
+    uid = torch.randint(2, U + 2, (Bt,), generator=g, device=dev, dtype=torch.int32)
+    iid = torch.randint(2, I + 2, (Bt,), generator=g, device=dev, dtype=torch.int32)
+
+    def tt_step():
+        tt._step(uid, iid, None, True)
+        tt.optimizer.apply([tt.userTower.emb, tt.itemTower.emb], dense=[tt.userTower.dense, tt.itemTower.dense])
+
+    s = timed(tt_step, 50)
+    out["twotower_train"] = {"value": Bt / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
+                             "config": "two-tower E=S=128, in-batch softmax batch 1000 (twoTower.py:292), Adagrad 0.1, fp32"}
+    Q = torch.randn(U, 128, generator=g, device=dev); Cm = torch.randn(I, 128, generator=g, device=dev)
+    idx = H.BruteForceIndex(10).index(Cm)
+    s = timed(lambda: idx(Q), 50)
+    out["topk_ml1m"] = {"value": U / s, "unit": "users/s", "ms": s * 1e3,
+                        "config": "6040 users x 3706 items, d=128, k=10, bf16 tcgen05 scoring + fused top-K (incl. query bf16 conversion)"}
+    Ub, Ib = 65536, 250000
+    Q = torch.randn(Ub, 64, generator=g, device=dev); Cm = torch.randn(Ib, 64, generator=g, device=dev)
+    idx = H.BruteForceIndex(10).index(Cm)
+    s = timed(lambda: idx(Q), 5, warm=1)
+    peaks, _ = load_peaks()
+    out["topk_shard"] = {"value": Ub / s, "unit": "users/s", "ms": s * 1e3,
+                         "tensor_tflops": 2.0 * Ub * Ib * 64 / s / 1e12,
+                         "frac_of_measured_bf16_peak": 2.0 * Ub * Ib * 64 / s / 1e12 / peaks.get("bf16_tflops", 1590.0),
+                         "config": "65536 users x 250000 items (one 8-way item shard of BASELINE.json configs[4]), d=64, k=10"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -328,6 +415,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="brk", choices=["brk", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -85,6 +85,30 @@ class BPRNet:
                 "brk_bpr_train_steps")
         return losses
 
+    def train_steps_from_host(self, u_host, p_host, batch_indices, batch_size, sampler_seed, epoch, losses_host=None):
+        """End-to-end steps from page-locked HOST id arrays (torch CPU int32 tensors, pinned): H2D, device
+        negative sampling, fused step, Adam and loss D2H are all enqueued by ONE C call; returns the pinned
+        host loss tensor (valid after a stream synchronize).  Needs set_training_pairs() for the sampler's
+        positive lists."""
+        pr = self._pairs
+        k = len(batch_indices)
+        dev = self.device
+        if getattr(self, "_stage", None) is None or self._stage.numel() < 6 * batch_size:
+            self._stage = torch.empty(6 * batch_size, dtype=torch.int32, device=dev)
+        d_losses = torch.empty(k, dtype=torch.float32, device=dev)
+        if losses_host is None:
+            losses_host = torch.empty(k, dtype=torch.float32).pin_memory()
+        idx = (C.c_int64 * k)(*[int(b) for b in batch_indices])
+        us, it = self.user.c_struct(), self.item.c_struct()
+        N.check(N.lib().brk_bpr_train_steps_host(
+            N.ctx(dev), C.byref(us), C.byref(it), C.c_void_p(u_host.data_ptr()), C.c_void_p(p_host.data_ptr()),
+            u_host.numel(), batch_size, idx, k, sampler_seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, self.numItem,
+            N.ptr(pr["indptr"]), N.ptr(pr["sitems"]), self.optimizer.h, 1 if self.optimizer.sparse == "lazy" else 0,
+            N.ptr(self.optimizer.state), N.ptr(self._stage), N.ptr(d_losses), C.c_void_p(losses_host.data_ptr()),
+            N.stream_ptr()), "brk_bpr_train_steps_host")
+        self._d_losses = d_losses            # keep alive until the stream has consumed it
+        return losses_host
+
     def train_on_batch(self, u, p, n, loss_out=None):
         """One step on device id tensors; returns the device loss scalar (local-batch mean).
         Under torch.distributed this is the mirrored synchronous step of RModel.py:119-121: each rank

@@ -243,3 +243,43 @@ extern "C" int brk_bpr_train_steps(brk_ctx* ctx, const brk_table* user, const br
   }
   return 0;
 }
+
+// End-to-end steps from HOST buffers in one call (the public-API path bench.py's `e2e` times):
+// per step  H2D(user ids, positive ids)  ->  Philox negatives on device  ->  fused fwd/bwd  ->  Adam
+// ->  D2H(loss).  u_host/p_host/losses_host must be page-locked for the copies to be asynchronous.
+// d_stage: device int32 scratch of 6*batch (two slots of u,p,n); d_losses: device [n_steps].
+extern "C" int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, const brk_table* item,
+                                        const int32_t* u_host, const int32_t* p_host, int64_t total, int64_t batch,
+                                        const int64_t* batch_index_host, int32_t n_steps, uint32_t seed, uint32_t epoch,
+                                        int32_t num_items, const int64_t* csr_indptr, const int32_t* csr_items,
+                                        brk_adam_hyper h, int32_t lazy_adam, int64_t* step_dev, int32_t* d_stage,
+                                        float* d_losses, float* losses_host, void* stream) {
+  BRK_REQUIRE(ctx && user && item && u_host && p_host && batch_index_host && step_dev && d_stage && d_losses &&
+                  csr_indptr && csr_items, BRK_E_ARG, "brk_bpr_train_steps_host: null argument");
+  BRK_REQUIRE(total > 0 && batch > 0 && n_steps >= 0, BRK_E_ARG, "brk_bpr_train_steps_host: total=%lld batch=%lld",
+              (long long)total, (long long)batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_batches = (total + batch - 1) / batch;
+  brk_table tabs[2] = {*user, *item};
+  for (int k = 0; k < n_steps; ++k) {
+    const int64_t bi = batch_index_host[k];
+    BRK_REQUIRE(bi >= 0 && bi < n_batches, BRK_E_ARG, "brk_bpr_train_steps_host: batch index %lld of %lld",
+                (long long)bi, (long long)n_batches);
+    const int64_t off = bi * batch;
+    const int64_t cnt = (off + batch <= total) ? batch : total - off;
+    int32_t* du = d_stage + (k & 1) * 3 * batch;
+    int32_t* dp = du + batch;
+    int32_t* dn = dp + batch;
+    BRK_CUDA(cudaMemcpyAsync(du, u_host + off, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    BRK_CUDA(cudaMemcpyAsync(dp, p_host + off, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    int rc = brk_philox_bpr_negatives(ctx, du, cnt, off, seed, epoch, num_items, csr_indptr, csr_items, dn, stream);
+    if (rc) return rc;
+    rc = brk_bpr_fwd_bwd(ctx, user, item, du, dp, dn, cnt, 0, d_losses + k, stream);
+    if (rc) return rc;
+    rc = lazy_adam ? brk_adam_rows(ctx, tabs, 2, h, step_dev, 1, stream)
+                   : brk_adam_dense_keras(ctx, tabs, 2, h, step_dev, 1, stream);
+    if (rc) return rc;
+    if (losses_host) BRK_CUDA(cudaMemcpyAsync(losses_host + k, d_losses + k, sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  return 0;
+}

@@ -120,6 +120,16 @@ int brk_bpr_train_steps(brk_ctx* ctx, const brk_table* user, const brk_table* it
                         int64_t batch, const int64_t* batch_index_host, int32_t n_steps,
                         brk_adam_hyper h, int32_t lazy_adam, int64_t* step_dev, float* losses,
                         void* stream);
+/* The same loop fed from HOST memory (what a caller holding NumPy / pandas columns does): per step
+ * H2D of the batch's user and positive ids, Philox negatives on the device, fused step, Adam, D2H of
+ * the loss.  u_host / p_host / losses_host should be page-locked (then nothing here blocks);
+ * d_stage: device int32 scratch [6*batch]; d_losses: device [n_steps]. */
+int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, const brk_table* item,
+                             const int32_t* u_host, const int32_t* p_host, int64_t total, int64_t batch,
+                             const int64_t* batch_index_host, int32_t n_steps, uint32_t seed, uint32_t epoch,
+                             int32_t num_items, const int64_t* csr_indptr, const int32_t* csr_items,
+                             brk_adam_hyper h, int32_t lazy_adam, int64_t* step_dev, int32_t* d_stage,
+                             float* d_losses, float* losses_host, void* stream);
 /* Forward only: x_out[b] = <u,p> - <u,n> (scores for evaluation, bpr.py:122-133). */
 int brk_bpr_scores(brk_ctx* ctx, const float* user_w, const float* item_w, int32_t d,
                    const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch,
