@@ -201,9 +201,7 @@ def product_arm(args):
                              global_batch=world * BATCH if world > 1 else 0)
         if ev is not None:
             ev[1].record()
-        if world > 1:
-            D.all_reduce_sum_(net.grad_arena)
-        net.optimizer.apply([net.user, net.item])
+        net.apply_gradients()      # N=1: fused Adam; N>1: fused reduce-scatter + Adam + all-gather over NVLink peers
         if ev is not None:
             ev[2].record()
         return loss
@@ -317,7 +315,10 @@ def product_arm(args):
                                    "1 Philox negative/positive, loss 1-sigmoid, exact Keras Adam(1e-3)",
                        "batch": BATCH, "l2": "flushed between timed steps (256 MiB written, then read back so the lines "
                                              "are clean); step time = CUDA events around the step's kernels, flush excluded",
-                       "parallelism": (f"mirrored data parallel x{world}: local batch {BATCH}, one NCCL all-reduce of the "
+                       "parallelism": (f"mirrored data parallel x{world}: local batch {BATCH}; per step one fused "
+                                       f"reduce-scatter + Adam + all-gather kernel over NVLink peer memory "
+                                       f"(2.5 MB arenas, sharded Adam moments)" if net.peer is not None else
+                                       f"mirrored data parallel x{world}: local batch {BATCH}, one NCCL all-reduce of the "
                                        f"2.5 MB gradient arena per step") if world > 1 else "single GPU",
                        "wall_s_timed_region": wall},
             "value_hot_l2": world * K * BATCH / (hot_ms * 1e-3),

@@ -40,11 +40,22 @@ class BPRNet:
         lazy = sparse_adam == "lazy"   # the touched-row bitmask is only needed by the row-sparse optimizer
         # one flat gradient arena for both tables: data-parallel replicas sum it with ONE all-reduce
         nu, ni = self.numUser * self.numFactor, self.numItem * self.numFactor
-        self.grad_arena = torch.zeros(nu + ni, dtype=torch.float32, device=self.device)
-        self.user = H.Table(torch.from_numpy(H.keras_embedding_init(self.numUser, self.numFactor, rng)).to(self.device),
-                            touched=lazy, g=self.grad_arena[:nu])
-        self.item = H.Table(torch.from_numpy(H.keras_embedding_init(self.numItem, self.numFactor, rng)).to(self.device),
-                            touched=lazy, g=self.grad_arena[nu:])
+        wu = torch.from_numpy(H.keras_embedding_init(self.numUser, self.numFactor, rng)).to(self.device)
+        wi = torch.from_numpy(H.keras_embedding_init(self.numItem, self.numFactor, rng)).to(self.device)
+        # multi-rank: weights and gradients live in NVLink peer-mapped arenas and the optimizer step is the
+        # fused reduce-scatter + Adam + all-gather kernel (csrc/dp_peer.cu); Adam moments are sharded
+        self.peer = None if lazy else D.peer_arena_or_none(nu + ni, self.device)
+        if self.peer is not None:
+            self.grad_arena = self.peer.g
+            self.peer.w[:nu].copy_(wu.view(-1)); self.peer.w[nu:nu + ni].copy_(wi.view(-1))
+            self.user = H.Table(self.peer.w[:nu].view(self.numUser, self.numFactor), slots=0, touched=False,
+                                g=self.grad_arena[:nu])
+            self.item = H.Table(self.peer.w[nu:nu + ni].view(self.numItem, self.numFactor), slots=0, touched=False,
+                                g=self.grad_arena[nu:nu + ni])
+        else:
+            self.grad_arena = torch.zeros(nu + ni, dtype=torch.float32, device=self.device)
+            self.user = H.Table(wu, touched=lazy, g=self.grad_arena[:nu])
+            self.item = H.Table(wi, touched=lazy, g=self.grad_arena[nu:])
         self.optimizer = H.Adam(learning_rate, sparse=sparse_adam, device=self.device)
         self._pairs = None
         self.history = {"loss": []}
@@ -116,12 +127,19 @@ class BPRNet:
         every rank applies the same Adam step."""
         w = D.world_size()
         loss = H.bpr_fwd_bwd(self.user, self.item, u, p, n, loss_out=loss_out, global_batch=w * u.numel() if w > 1 else 0)
-        if w > 1:
+        self.apply_gradients()
+        return loss
+
+    def apply_gradients(self):
+        """Optimizer step on the accumulated gradients (data-parallel aware)."""
+        if self.peer is not None:
+            self.peer.adam_step(self.optimizer.h, self.optimizer.state)
+            return
+        if D.world_size() > 1:
             if self.optimizer.sparse == "lazy":
                 raise NotImplementedError("mirrored data parallelism uses the dense (Keras) Adam pass")
             D.all_reduce_sum_(self.grad_arena)
         self.optimizer.apply([self.user, self.item])
-        return loss
 
     def fit(self, X, y=None, batch_size=64, epochs=1, shuffle=True, sampler_seed=7, verbose=0, initial_epoch=0):
         """Keras-like fit (BPRModel.py:109).  X: dict with 'customerId_input', 'pProduct_input' and

@@ -60,6 +60,64 @@ def broadcast_(t, src=0):
     return t
 
 
+# ---- symmetric (peer-mapped) arenas for the fused data-parallel optimizer ---------------------------------
+class PeerArena:
+    """Weight and gradient arenas in NVLink peer-mapped memory plus the flag block of
+    brk_dp_adam_peer.  The allocation / pointer exchange is torch's symmetric-memory plumbing; the
+    reduce + Adam + broadcast + barriers are ours (csrc/dp_peer.cu)."""
+
+    def __init__(self, n_floats, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _native as N
+        self.n = (int(n_floats) + 3) // 4 * 4
+        self.device = device
+        G, r = world_size(), rank()
+        group = dist.group.WORLD.group_name
+        self.w = symm_mem.empty(self.n, dtype=torch.float32, device=device)
+        self.g = symm_mem.empty(self.n, dtype=torch.float32, device=device)
+        self.flags = symm_mem.empty(2 * 64, dtype=torch.int32, device=device)
+        hw = symm_mem.rendezvous(self.w, group)
+        hg = symm_mem.rendezvous(self.g, group)
+        hf = symm_mem.rendezvous(self.flags, group)
+        self.w.zero_(); self.g.zero_(); self.flags.zero_()
+        self._ptrs = [torch.tensor(list(h.buffer_ptrs), dtype=torch.int64, device=device) for h in (hw, hg, hf)]
+        n4 = self.n // 4
+        self.slice_lo, self.slice_hi = 4 * (n4 * r // G), 4 * (n4 * (r + 1) // G)
+        sl = max(self.slice_hi - self.slice_lo, 4)
+        self.m = torch.zeros(sl, dtype=torch.float32, device=device)
+        self.v = torch.zeros(sl, dtype=torch.float32, device=device)
+        self.local_sync = torch.zeros(8, dtype=torch.int32, device=device)
+        self._handles = (hw, hg, hf)
+        torch.cuda.synchronize(device)
+        dist.barrier()                       # nobody posts a flag before everyone has zeroed its block
+        self.desc = N.brk_dp_peer(self._ptrs[0].data_ptr(), self._ptrs[1].data_ptr(), self._ptrs[2].data_ptr(),
+                                  self.m.data_ptr(), self.v.data_ptr(), self.local_sync.data_ptr(), self.n, r, G)
+
+    def adam_step(self, hyper, state):
+        """One fused reduce-scatter + Adam + all-gather step (all ranks must call it)."""
+        import ctypes as C
+        from . import _native as N
+        N.check(N.lib().brk_dp_adam_peer(N.ctx(self.device), C.byref(self.desc), hyper, N.ptr(state), N.stream_ptr()),
+                "brk_dp_adam_peer")
+
+    def check(self):
+        if int(self.local_sync[4].item()) != 0:
+            raise RuntimeError("brk_dp_adam_peer: a cross-GPU barrier timed out (a rank did not reach the step)")
+
+
+def peer_arena_or_none(n_floats, device):
+    """PeerArena when running multi-rank on CUDA with peer access (and BRK_DP != 'nccl'), else None --
+    the caller then falls back to one NCCL all-reduce per step."""
+    if not is_dist() or world_size() == 1 or os.environ.get("BRK_DP", "peer") == "nccl":
+        return None
+    try:
+        return PeerArena(n_floats, device)
+    except Exception as e:                    # pragma: no cover - depends on the box
+        if rank() == 0:
+            print(f"[binrec_b200] symmetric memory unavailable ({e!r}); using NCCL all-reduce", flush=True)
+        return None
+
+
 # ---- batch slicing ------------------------------------------------------------------------------------
 def local_slice(n, r=None, w=None):
     """Contiguous slice [lo, hi) of n items owned by rank r of w (remainder to the low ranks)."""

@@ -193,6 +193,30 @@ int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, con
                    uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
                    float* out, float* loss_out, void* stream);
 
+/* ---- data-parallel optimizer over NVLink peer memory ----------------------------------------------
+ * Stands in for the per-step gradient all-reduce of MultiWorkerMirroredStrategy
+ * (src/models/RModel.py:119-121) + Adam (NeuMFModel.py:89, BPRModel.py:70) when one process drives
+ * each GPU: reduce-scatter of the gradient arena, Adam on the owned slice, all-gather of the new
+ * weights, fused in one cooperative kernel with its own cross-GPU barriers (no NCCL on this path).
+ * peer_w / peer_g / peer_flags are DEVICE arrays of `world` pointers into each rank's symmetric
+ * (peer-mapped) weight arena, gradient arena (n floats each, n % 4 == 0) and flag block
+ * (2*world uint32, zero-initialised before the first call on every rank).  m, v: local Adam moments of
+ * the OWNED slice only (float4 range [rank*n/4/world, (rank+1)*n/4/world)).  local_sync: 8 uint32,
+ * zero-initialised; local_sync[4] != 0 afterwards means a barrier timed out (a peer never arrived).
+ * All ranks must call it once per step; on return (stream order) every rank's w is updated and
+ * bit-identical, and this rank's g is zero. */
+typedef struct brk_dp_peer {
+  float* const* peer_w;
+  float* const* peer_g;
+  uint32_t* const* peer_flags;
+  float* m;
+  float* v;
+  uint32_t* local_sync;
+  int64_t n;
+  int32_t rank, world;
+} brk_dp_peer;
+int brk_dp_adam_peer(brk_ctx* ctx, const brk_dp_peer* d, brk_adam_hyper h, int64_t* state, void* stream);
+
 /* ---- two-tower: towers + in-batch softmax / rdZero loss + backward -------------------------------
  * Stands in for TwoTowerModel.computeEmb / computeLossTfrs / computeLossRdZero / train_step
  * (trainers/twoTower.py:77-102) and tfrs.tasks.Retrieval (:47,83).  A tower is an embedding table
