@@ -5,6 +5,8 @@
 // Mapping: a group of LPR lanes owns a triplet, each lane holds NCH float4 chunks of u, p and n in
 // registers; the dot product is a group shuffle-reduction; gradients leave as 16-byte vector REDs.
 #include "common.cuh"
+#include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -149,6 +151,128 @@ bpr_scalar(const float* __restrict__ Wu, const float* __restrict__ Wi, float* __
   if constexpr (TRAIN) finish_loss(double(loss_local), inv_local, loss_acc, ticket, out);
 }
 
+// ---- whole training steps in ONE cooperative kernel ------------------------------------------------
+// K steps x (fused fwd/bwd -> grid.sync -> exact Keras Adam over both tables -> grid.sync): no kernel
+// launch and no host involvement between steps; both phases are single-wave and latency-bound, so the
+// launch gaps and cold starts between separate kernels were ~40 % of the step.
+struct BprCoopParams {
+  brk_table user, item;
+  const int32_t* u; const int32_t* p; const int32_t* n;
+  const int64_t* batch_index;     // device [n_steps] (long calls) ...
+  int64_t inline_index[16];       // ... or by value (n_steps <= 16: no H2D copy at all)
+  int32_t use_inline;
+  int64_t total, batch;
+  int32_t n_steps;
+  brk_adam_hyper h;
+  int64_t* state;                 // [t, beta1^t, beta2^t]
+  float* losses;                  // device [n_steps] or null
+  double* loss_acc;               // 2 doubles (ping-pong), zero on entry
+};
+
+__device__ __forceinline__ void adam4(float4& w, float4& m, float4& v, const float4 g, float alpha, float b1, float b2,
+                                      float eps) {
+  const float omb1 = 1.f - b1, omb2 = 1.f - b2;
+  m.x = b1 * m.x + omb1 * g.x; v.x = b2 * v.x + omb2 * g.x * g.x; w.x -= alpha * m.x / (sqrtf(v.x) + eps);
+  m.y = b1 * m.y + omb1 * g.y; v.y = b2 * v.y + omb2 * g.y * g.y; w.y -= alpha * m.y / (sqrtf(v.y) + eps);
+  m.z = b1 * m.z + omb1 * g.z; v.z = b2 * v.z + omb2 * g.z * g.z; w.z -= alpha * m.z / (sqrtf(v.z) + eps);
+  m.w = b1 * m.w + omb1 * g.w; v.w = b2 * v.w + omb2 * g.w * g.w; w.w -= alpha * m.w / (sqrtf(v.w) + eps);
+}
+
+template <int LPR, int NCH>
+__global__ void __launch_bounds__(kThreads) bpr_steps_coop(const BprCoopParams P) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double red[32];
+  const int d4 = P.user.d >> 2;
+  const int lane_in = threadIdx.x & (LPR - 1);
+  const int sub = (threadIdx.x & 31) / LPR;
+  const int64_t group = (int64_t(blockIdx.x) * kThreads + threadIdx.x) / LPR;
+  const int64_t n_groups = int64_t(gridDim.x) * kThreads / LPR;
+  const int64_t warp_first = group - sub;
+  const int64_t tid = int64_t(blockIdx.x) * kThreads + threadIdx.x, nthr = int64_t(gridDim.x) * kThreads;
+  // no __restrict__/read-only path here: phase 2 of this same kernel rewrites the tables, so rows are
+  // read with ld.global.cg (L2 only) -- another SM's L1 could otherwise hold a stale line across steps
+  const float4* Wu4 = reinterpret_cast<const float4*>(P.user.w);
+  const float4* Wi4 = reinterpret_cast<const float4*>(P.item.w);
+  const double* pw = reinterpret_cast<const double*>(P.state);
+  double p1 = pw[1], p2 = pw[2];                       // running beta powers, advanced per step in registers
+  const brk_table tabs[2] = {P.user, P.item};
+
+  for (int s = 0; s < P.n_steps; ++s) {
+    const int64_t off = (P.use_inline ? P.inline_index[s] : P.batch_index[s]) * P.batch;
+    const int64_t batch = (off + P.batch <= P.total) ? P.batch : P.total - off;
+    const float inv_batch = 1.0f / float(batch);
+    const int32_t* uid = P.u + off; const int32_t* pid = P.p + off; const int32_t* nid = P.n + off;
+    // ---- phase 1: fused gather + loss + gradient REDs (same math as bpr_vec) ----
+    float loss_local = 0.f;
+    for (int64_t wb = warp_first; wb < batch; wb += n_groups) {
+      const int64_t b = wb + sub;
+      const bool valid = b < batch;
+      int64_t ru = 0, rp = 0, rn = 0;
+      if (valid) { ru = uid[b]; rp = pid[b]; rn = nid[b]; }
+      float4 u[NCH], p[NCH], n[NCH];
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int c = lane_in + k * LPR;
+        if (valid && c < d4) {           // plain loads: the tables are rewritten by phase 2 of the same kernel
+          u[k] = __ldcg(Wu4 + ru * d4 + c); p[k] = __ldcg(Wi4 + rp * d4 + c); n[k] = __ldcg(Wi4 + rn * d4 + c);
+        } else {
+          u[k] = p[k] = n[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        dot = fmaf(u[k].x, p[k].x - n[k].x, dot); dot = fmaf(u[k].y, p[k].y - n[k].y, dot);
+        dot = fmaf(u[k].z, p[k].z - n[k].z, dot); dot = fmaf(u[k].w, p[k].w - n[k].w, dot);
+      }
+      const float x = group_sum<LPR>(dot);
+      const float sg = sigmoidf_acc(x);
+      if (valid && lane_in == 0) loss_local += 1.0f - sg;
+      const float g = -sg * (1.0f - sg) * inv_batch;
+      if (valid) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const int c = lane_in + k * LPR;
+          if (c < d4) {
+            const float4 dp = make_float4(g * u[k].x, g * u[k].y, g * u[k].z, g * u[k].w);
+            red_add_f4(P.user.g + (ru * d4 + c) * 4, make_float4(g * (p[k].x - n[k].x), g * (p[k].y - n[k].y),
+                                                                 g * (p[k].z - n[k].z), g * (p[k].w - n[k].w)));
+            red_add_f4(P.item.g + (rp * d4 + c) * 4, dp);
+            red_add_f4(P.item.g + (rn * d4 + c) * 4, make_float4(-dp.x, -dp.y, -dp.z, -dp.w));
+          }
+        }
+      }
+    }
+    const double part = block_sum_double(double(loss_local), red);
+    if (threadIdx.x == 0) atomicAdd(P.loss_acc + (s & 1), part);
+    grid.sync();
+    // ---- phase 2: exact Keras Adam over every element of both tables; zero the accumulators ----
+    p1 *= double(P.h.beta1); p2 *= double(P.h.beta2);
+    const float alpha = float(double(P.h.lr) * sqrt(1.0 - p2) / (1.0 - p1));
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int64_t n4 = tabs[k].rows * tabs[k].d / 4;
+      float4* w4 = reinterpret_cast<float4*>(tabs[k].w); float4* g4 = reinterpret_cast<float4*>(tabs[k].g);
+      float4* m4 = reinterpret_cast<float4*>(tabs[k].m); float4* v4 = reinterpret_cast<float4*>(tabs[k].v);
+      for (int64_t i = tid; i < n4; i += nthr) {
+        float4 w = w4[i], m = m4[i], v = v4[i];
+        adam4(w, m, v, g4[i], alpha, P.h.beta1, P.h.beta2, P.h.eps);
+        w4[i] = w; m4[i] = m; v4[i] = v; g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if (tid == 0) {
+      if (P.losses) P.losses[s] = float(P.loss_acc[s & 1] / double(batch));
+      P.loss_acc[s & 1] = 0.0;
+    }
+    grid.sync();
+  }
+  if (tid == 0) {
+    double* pwo = reinterpret_cast<double*>(P.state);
+    P.state[0] += P.n_steps; pwo[1] = p1; pwo[2] = p2;
+  }
+}
+
 template <bool TRAIN>
 int launch_bpr(brk_ctx* ctx, const float* Wu, const float* Wi, float* Gu, float* Gi, uint32_t* Tu, uint32_t* Ti,
                int d, const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch, int64_t global_batch,
@@ -214,6 +338,57 @@ extern "C" int brk_bpr_scores(brk_ctx* ctx, const float* user_w, const float* it
                            (cudaStream_t)stream);
 }
 
+static bool coop_eligible(const brk_table* user, const brk_table* item, int lazy_adam) {
+  const int d = user->d;
+  return !lazy_adam && (d & 3) == 0 && d <= 128 && user->m && user->v && item->m && item->v &&
+         brk_aligned16(user->w) && brk_aligned16(item->w) && brk_aligned16(user->g) && brk_aligned16(item->g) &&
+         ((user->rows * d) & 3) == 0 && ((item->rows * d) & 3) == 0 && getenv("BRK_NO_COOP") == nullptr;
+}
+
+static int launch_coop_steps(brk_ctx* ctx, const brk_table* user, const brk_table* item, const int32_t* u,
+                             const int32_t* p, const int32_t* n, int64_t total, int64_t batch,
+                             const int64_t* batch_index_host, int32_t n_steps, brk_adam_hyper h, int64_t* step_dev,
+                             float* losses, cudaStream_t st) {
+  const int d = user->d;
+    BprCoopParams P;
+    P.use_inline = n_steps <= 16;
+    if (P.use_inline) {
+      for (int k = 0; k < n_steps; ++k) P.inline_index[k] = batch_index_host[k];
+    } else {
+      // batch indices to the device (the context keeps a small scratch buffer)
+      const size_t need = size_t(n_steps) * sizeof(int64_t) + 64;
+      if (ctx->scratch_bytes < need) {
+        if (ctx->scratch) BRK_CUDA(cudaFree(ctx->scratch));
+        BRK_CUDA(cudaMalloc(&ctx->scratch, need * 2));
+        ctx->scratch_bytes = need * 2;
+      }
+      BRK_CUDA(cudaMemcpyAsync(ctx->scratch, batch_index_host, size_t(n_steps) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    }
+    P.user = *user; P.item = *item; P.u = u; P.p = p; P.n = n;
+    P.batch_index = reinterpret_cast<const int64_t*>(ctx->scratch);
+    P.total = total; P.batch = batch; P.n_steps = n_steps; P.h = h; P.state = step_dev; P.losses = losses;
+    P.loss_acc = ctx->loss_acc + 2;
+    const int lpr = brk_lanes_per_row(d >> 2);
+    void* fn = nullptr;
+    switch (lpr) {
+      case 1: fn = (void*)bpr_steps_coop<1, 1>; break;
+      case 2: fn = (void*)bpr_steps_coop<2, 1>; break;
+      case 4: fn = (void*)bpr_steps_coop<4, 1>; break;
+      case 8: fn = (void*)bpr_steps_coop<8, 1>; break;
+      case 16: fn = (void*)bpr_steps_coop<16, 1>; break;
+      default: fn = (void*)bpr_steps_coop<32, 1>; break;
+    }
+    int per_sm = 0;
+    BRK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
+    BRK_REQUIRE(per_sm > 0, BRK_E_STATE, "brk_bpr_train_steps: cooperative kernel does not fit");
+    int64_t want = (batch * lpr + kThreads - 1) / kThreads;
+    const int64_t cap = int64_t(per_sm) * ctx->sm_count;
+    const int grid = int(want < cap ? (want < 1 ? 1 : want) : cap);
+    void* args[] = {(void*)&P};
+    BRK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, st));
+    return 0;
+}
+
 // Multi-step driver: one C call enqueues n_steps x (fused fwd/bwd + optimizer) so that the host
 // cost per step is two kernel launches and nothing else (model.fit's inner loop,
 // /root/reference/src/models/BPRModel.py:109).  batch_index_host[k] selects which batch of the
@@ -228,11 +403,16 @@ extern "C" int brk_bpr_train_steps(brk_ctx* ctx, const brk_table* user, const br
   BRK_REQUIRE(total > 0 && batch > 0 && n_steps >= 0, BRK_E_ARG, "brk_bpr_train_steps: total=%lld batch=%lld",
               (long long)total, (long long)batch);
   const int64_t n_batches = (total + batch - 1) / batch;
+  for (int k = 0; k < n_steps; ++k)
+    BRK_REQUIRE(batch_index_host[k] >= 0 && batch_index_host[k] < n_batches, BRK_E_ARG,
+                "brk_bpr_train_steps: batch index %lld of %lld", (long long)batch_index_host[k], (long long)n_batches);
+  if (n_steps == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool coop_ok = coop_eligible(user, item, lazy_adam);
+  if (coop_ok) return launch_coop_steps(ctx, user, item, u, p, n, total, batch, batch_index_host, n_steps, h, step_dev, losses, st);
   brk_table tabs[2] = {*user, *item};
   for (int k = 0; k < n_steps; ++k) {
     const int64_t bi = batch_index_host[k];
-    BRK_REQUIRE(bi >= 0 && bi < n_batches, BRK_E_ARG, "brk_bpr_train_steps: batch index %lld of %lld",
-                (long long)bi, (long long)n_batches);
     const int64_t off = bi * batch;
     const int64_t cnt = (off + batch <= total) ? batch : total - off;
     int rc = brk_bpr_fwd_bwd(ctx, user, item, u + off, p + off, n + off, cnt, 0, losses ? losses + k : nullptr, stream);
@@ -260,26 +440,64 @@ extern "C" int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, con
               (long long)total, (long long)batch);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n_batches = (total + batch - 1) / batch;
+  for (int k = 0; k < n_steps; ++k)
+    BRK_REQUIRE(batch_index_host[k] >= 0 && batch_index_host[k] < n_batches, BRK_E_ARG,
+                "brk_bpr_train_steps_host: batch index %lld of %lld", (long long)batch_index_host[k], (long long)n_batches);
+  if (n_steps == 0) return 0;
+  if (!ctx->copy_ready) {
+    BRK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int q = 0; q < 2; ++q) {
+      BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[q], cudaEventDisableTiming));
+      BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[q], cudaEventDisableTiming));
+    }
+    ctx->copy_ready = 1;
+  }
+  cudaStream_t cs = ctx->copy_stream;
+  const bool coop_ok = coop_eligible(user, item, lazy_adam);
   brk_table tabs[2] = {*user, *item};
+  const int64_t zero_index = 0;
+  // the copy stream must not run ahead of work already queued on `st` that still uses the staging slots
+  BRK_CUDA(cudaEventRecord(ctx->ev_done[0], st));
+  BRK_CUDA(cudaEventRecord(ctx->ev_done[1], st));
+  auto stage = [&](int k) -> int {                 // H2D of step k's ids into slot k&1, on the copy stream
+    const int64_t off = batch_index_host[k] * batch;
+    const int64_t cnt = (off + batch <= total) ? batch : total - off;
+    int32_t* du = d_stage + (k & 1) * 3 * batch;
+    BRK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_done[k & 1], 0));          // slot free (step k-2 finished)
+    BRK_CUDA(cudaMemcpyAsync(du, u_host + off, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    BRK_CUDA(cudaMemcpyAsync(du + batch, p_host + off, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    BRK_CUDA(cudaEventRecord(ctx->ev_ready[k & 1], cs));
+    return 0;
+  };
+  if (int rc = stage(0)) return rc;
   for (int k = 0; k < n_steps; ++k) {
-    const int64_t bi = batch_index_host[k];
-    BRK_REQUIRE(bi >= 0 && bi < n_batches, BRK_E_ARG, "brk_bpr_train_steps_host: batch index %lld of %lld",
-                (long long)bi, (long long)n_batches);
-    const int64_t off = bi * batch;
+    if (k + 1 < n_steps) { if (int rc = stage(k + 1)) return rc; }       // prefetch the next batch's ids
+    const int64_t off = batch_index_host[k] * batch;
     const int64_t cnt = (off + batch <= total) ? batch : total - off;
     int32_t* du = d_stage + (k & 1) * 3 * batch;
     int32_t* dp = du + batch;
     int32_t* dn = dp + batch;
-    BRK_CUDA(cudaMemcpyAsync(du, u_host + off, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    BRK_CUDA(cudaMemcpyAsync(dp, p_host + off, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    BRK_CUDA(cudaStreamWaitEvent(st, ctx->ev_ready[k & 1], 0));
     int rc = brk_philox_bpr_negatives(ctx, du, cnt, off, seed, epoch, num_items, csr_indptr, csr_items, dn, stream);
     if (rc) return rc;
-    rc = brk_bpr_fwd_bwd(ctx, user, item, du, dp, dn, cnt, 0, d_losses + k, stream);
-    if (rc) return rc;
-    rc = lazy_adam ? brk_adam_rows(ctx, tabs, 2, h, step_dev, 1, stream)
-                   : brk_adam_dense_keras(ctx, tabs, 2, h, step_dev, 1, stream);
-    if (rc) return rc;
-    if (losses_host) BRK_CUDA(cudaMemcpyAsync(losses_host + k, d_losses + k, sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (coop_ok) {
+      rc = launch_coop_steps(ctx, user, item, du, dp, dn, cnt, cnt, &zero_index, 1, h, step_dev, d_losses + k, st);
+      if (rc) return rc;
+    } else {
+      rc = brk_bpr_fwd_bwd(ctx, user, item, du, dp, dn, cnt, 0, d_losses + k, stream);
+      if (rc) return rc;
+      rc = lazy_adam ? brk_adam_rows(ctx, tabs, 2, h, step_dev, 1, stream)
+                     : brk_adam_dense_keras(ctx, tabs, 2, h, step_dev, 1, stream);
+      if (rc) return rc;
+    }
+    BRK_CUDA(cudaEventRecord(ctx->ev_done[k & 1], st));
+    if (losses_host) {                               // the step's result goes back on the copy stream
+      BRK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_done[k & 1], 0));
+      BRK_CUDA(cudaMemcpyAsync(losses_host + k, d_losses + k, sizeof(float), cudaMemcpyDeviceToHost, cs));
+    }
   }
+  // rejoin: everything the copy stream did is ordered before whatever follows on `st`
+  BRK_CUDA(cudaEventRecord(ctx->ev_ready[0], cs));
+  BRK_CUDA(cudaStreamWaitEvent(st, ctx->ev_ready[0], 0));
   return 0;
 }

@@ -12,6 +12,10 @@ struct brk_ctx {
   unsigned int* tickets;      // [BRK_TICKETS] last-block tickets, zero between calls
   void*         scratch;      // sort / misc scratch
   size_t        scratch_bytes;
+  // host-fed training: copy stream + events for H2D prefetch / loss D2H (created on first use)
+  cudaStream_t  copy_stream;
+  cudaEvent_t   ev_ready[2], ev_done[2];
+  int           copy_ready;
 };
 
 #define BRK_LOSS_SLOTS 16

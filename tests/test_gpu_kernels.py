@@ -184,3 +184,64 @@ def test_adagrad_rows_and_dense_agree_with_oracle(dev):
         np.testing.assert_allclose(t.w.cpu().numpy(), ref_w, rtol=RTOL, atol=ATOL)
         np.testing.assert_allclose(t.m.cpu().numpy(), ref_acc, rtol=RTOL, atol=ATOL)
         assert not t.g.any().item()
+
+
+def test_bpr_multi_step_cooperative_kernel_matches_oracle(dev):
+    """brk_bpr_train_steps: K steps inside one cooperative kernel (fwd/bwd -> grid.sync -> Adam) must
+    equal K oracle steps, including a ragged last batch and a permuted batch order."""
+    from binrec_b200.BPRModel import BPRNet
+    U, I, d, B = 400, 300, 64, 512
+    rng = np.random.default_rng(21)
+    total = 5 * B + 77                                  # ragged last batch
+    u = rng.integers(0, U, total).astype(np.int32); p = rng.integers(0, I, total).astype(np.int32)
+    n = rng.integers(0, I, total).astype(np.int32)
+    net = BPRNet(U, I, d, seed=42, device=dev)
+    orc = OB.BPROracle(U, I, d, seed=42)
+    net.set_training_pairs(u, p); net.set_negatives(n)
+    order = [3, 0, 5, 1, 4, 2, 5, 0]
+    losses = net.train_steps(order, B)
+    ref = []
+    for b in order:
+        sl = slice(b * B, min(total, (b + 1) * B))
+        ref.append(orc.step(u[sl], p[sl], n[sl]))
+    np.testing.assert_allclose(losses.cpu().numpy(), np.array(ref), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(net.user.w.cpu().numpy(), orc.user, rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(net.item.w.cpu().numpy(), orc.item, rtol=1e-4, atol=2e-6)
+    assert net.optimizer.step.item() == len(order) and not net.grad_arena.any().item()
+    # the separate-kernel path (BRK_NO_COOP) gives the same result
+    import os
+    net2 = BPRNet(U, I, d, seed=42, device=dev); net2.set_training_pairs(u, p); net2.set_negatives(n)
+    os.environ["BRK_NO_COOP"] = "1"
+    try:
+        l2 = net2.train_steps(order, B)
+    finally:
+        del os.environ["BRK_NO_COOP"]
+    np.testing.assert_allclose(l2.cpu().numpy(), losses.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(net2.user.w.cpu().numpy(), net.user.w.cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_bpr_host_fed_steps_match_oracle(dev):
+    """BPRNet.train_steps_from_host (pinned host ids -> H2D prefetch on a copy stream -> device Philox
+    negatives -> cooperative step kernel -> loss D2H) against the oracle with the oracle's sampler."""
+    from binrec_b200.BPRModel import BPRNet
+    U, I, d, B = 300, 200, 64, 256
+    rng = np.random.default_rng(31)
+    key = np.unique(rng.integers(0, U * I, 4000))
+    u, p = (key // I).astype(np.int32), (key % I).astype(np.int32)
+    perm = rng.permutation(len(u)); u, p = u[perm], p[perm]
+    net = BPRNet(U, I, d, seed=42, device=dev)
+    net.set_training_pairs(u, p)
+    orc = OB.BPROracle(U, I, d, seed=42)
+    indptr, sitems = OP.build_csr(u, p, U)
+    order = [2, 0, 7, 3, 3, 1, len(u) // B]             # includes the ragged tail batch
+    hu, hp = torch.from_numpy(u).pin_memory(), torch.from_numpy(p).pin_memory()
+    losses = net.train_steps_from_host(hu, hp, order, B, 7, 5)
+    torch.cuda.synchronize()
+    ref = []
+    for b in order:
+        sl = slice(b * B, min(len(u), (b + 1) * B))
+        neg = OP.bpr_negatives(u[sl], 7, 5, I, indptr, sitems, first_index=b * B)
+        ref.append(orc.step(u[sl], p[sl], neg))
+    np.testing.assert_allclose(losses.numpy(), np.array(ref), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(net.user.w.cpu().numpy(), orc.user, rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(net.item.w.cpu().numpy(), orc.item, rtol=1e-4, atol=2e-6)
