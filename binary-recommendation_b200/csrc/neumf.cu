@@ -23,6 +23,7 @@
 // 4 B prediction (528 B) + 4 row gradients (512 B) + 2x re-gather in the backward.
 #include "common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -38,8 +39,7 @@ template <int E, int H1, int H2, int H3>
 struct Layout {   // offsets (floats) inside the flat dense parameter block -- mirrored in hotpath.py
   static constexpr int W1 = 0, b1 = W1 + 2 * E * H1, g1 = b1 + H1, be1 = g1 + H1;
   static constexpr int W2 = be1 + H1, b2 = W2 + H1 * H2, g2 = b2 + H2, be2 = g2 + H2;
-  static constexpr int W3 = be2 + H2, b3 = W3 + H2 * H3, W4 = b3 + H3, b4 = W4 + H3 + 1;
-  static constexpr int total = b4 + 1;
+  static constexpr int W3 = be2 + H2, b3 = W3 + H2 * H3, W4 = b3 + H3;   // b4 = W4 + H3 + 1
 };
 // accumulator block (doubles): forward sums, backward sums, loss
 template <int H1, int H2>
@@ -693,6 +693,12 @@ int run_neumf(brk_ctx* ctx, const NeumfArgs& A, cudaStream_t st) {
 
 }  // namespace
 
+// second-generation kernels (neumf2.cu); returns 1 when the spec is not one of theirs
+int brk_neumf_step_v2(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, const int32_t* i, const float* y,
+                      int64_t batch, int64_t global_batch, int64_t first_index, int32_t training, uint32_t dropout_seed,
+                      uint32_t dropout_epoch, const brk_neumf_workspace* ws, float* out, float* loss_out,
+                      cudaStream_t st, int* rc_out);
+
 extern "C" int64_t brk_neumf_dense_floats(int32_t E, int32_t H1, int32_t H2, int32_t H3) {
   return int64_t(2) * E * H1 + 3 * H1 + int64_t(H1) * H2 + 3 * H2 + int64_t(H2) * H3 + H3 + (H3 + 1) + 1;
 }
@@ -710,6 +716,12 @@ extern "C" int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int3
   BRK_REQUIRE(!training || (m->uMLP.g && m->iMLP.g && m->uMF.g && m->iMF.g && m->dense.g), BRK_E_ARG,
               "brk_neumf_step: gradient accumulators missing");
   BRK_REQUIRE(ws->h1 && ws->h2 && ws->dy1 && ws->dy2 && ws->acc, BRK_E_ARG, "brk_neumf_step: workspace missing");
+  if (getenv("BRK_NEUMF_V1") == nullptr) {
+    int rc2 = 0;
+    if (brk_neumf_step_v2(ctx, m, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch, ws,
+                          out, loss_out, (cudaStream_t)stream, &rc2) == 0)
+      return rc2;
+  }
   NeumfArgs A;
   A.uMLP = m->uMLP; A.iMLP = m->iMLP; A.uMF = m->uMF; A.iMF = m->iMF; A.dense = m->dense;
   A.u = u; A.i = i; A.y = y ? y : out; A.B = batch; A.first_index = first_index; A.global_B = global_batch > 0 ? global_batch : batch;
