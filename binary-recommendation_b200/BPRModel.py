@@ -96,28 +96,70 @@ class BPRNet:
                 "brk_bpr_train_steps")
         return losses
 
+    @staticmethod
+    def pack_host_batches(users, items, batch_size):
+        """Batch-major pinned host layout [n_batches, 2, batch] (each batch's user ids, then its item ids; the
+        last block zero-padded): what a loader producing ({"user": ids, "item": ids}) batches writes
+        (NeuMFModel.py:111-117).  With it train_steps_from_host moves each step's inputs with ONE copy."""
+        users = np.ascontiguousarray(users, dtype=np.int32); items = np.ascontiguousarray(items, dtype=np.int32)
+        nb = (len(users) + batch_size - 1) // batch_size
+        packed = torch.zeros((nb, 2, batch_size), dtype=torch.int32).pin_memory()
+        flat = packed.numpy()
+        full = len(users) // batch_size
+        flat[:full, 0, :] = users[:full * batch_size].reshape(full, batch_size)
+        flat[:full, 1, :] = items[:full * batch_size].reshape(full, batch_size)
+        if full < nb:
+            r = len(users) - full * batch_size
+            flat[full, 0, :r] = users[full * batch_size:]; flat[full, 1, :r] = items[full * batch_size:]
+        packed.total = len(users)
+        return packed
+
     def train_steps_from_host(self, u_host, p_host, batch_indices, batch_size, sampler_seed, epoch, losses_host=None):
         """End-to-end steps from page-locked HOST id arrays (torch CPU int32 tensors, pinned): H2D, device
         negative sampling, fused step, Adam and loss D2H are all enqueued by ONE C call; returns the pinned
         host loss tensor (valid after a stream synchronize).  Needs set_training_pairs() for the sampler's
-        positive lists."""
+        positive lists.  u_host may be a pack_host_batches() tensor (then p_host is None)."""
         pr = self._pairs
         k = len(batch_indices)
         dev = self.device
-        if getattr(self, "_stage", None) is None or self._stage.numel() < 6 * batch_size:
-            self._stage = torch.empty(6 * batch_size, dtype=torch.int32, device=dev)
+        if p_host is None:                                  # batch-major [n_batches, 2, batch]
+            total, stride = int(u_host.total), 2 * batch_size
+            u_ptr, p_ptr = u_host.data_ptr(), u_host.data_ptr() + 4 * batch_size
+        else:
+            total, stride = u_host.numel(), batch_size
+            u_ptr, p_ptr = u_host.data_ptr(), p_host.data_ptr()
+        need = int(N.lib().brk_bpr_host_stage_ints(batch_size))
+        if getattr(self, "_stage", None) is None or self._stage.numel() < need:
+            self._stage = torch.empty(need, dtype=torch.int32, device=dev)
         d_losses = torch.empty(k, dtype=torch.float32, device=dev)
         if losses_host is None:
             losses_host = torch.empty(k, dtype=torch.float32).pin_memory()
         idx = (C.c_int64 * k)(*[int(b) for b in batch_indices])
         us, it = self.user.c_struct(), self.item.c_struct()
         N.check(N.lib().brk_bpr_train_steps_host(
-            N.ctx(dev), C.byref(us), C.byref(it), C.c_void_p(u_host.data_ptr()), C.c_void_p(p_host.data_ptr()),
-            u_host.numel(), batch_size, idx, k, sampler_seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, self.numItem,
+            N.ctx(dev), C.byref(us), C.byref(it), C.c_void_p(u_ptr), C.c_void_p(p_ptr),
+            total, batch_size, stride, idx, k, sampler_seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, self.numItem,
             N.ptr(pr["indptr"]), N.ptr(pr["sitems"]), self.optimizer.h, 1 if self.optimizer.sparse == "lazy" else 0,
             N.ptr(self.optimizer.state), N.ptr(self._stage), N.ptr(d_losses), C.c_void_p(losses_host.data_ptr()),
             N.stream_ptr()), "brk_bpr_train_steps_host")
         self._d_losses = d_losses            # keep alive until the stream has consumed it
+        return losses_host
+
+    def train_steps_mapped(self, u_host, p_host, batch_indices, batch_size, sampler_seed, epoch, losses_host=None):
+        """Zero-copy variant of train_steps_from_host: the pinned host id arrays stay where they are, ONE
+        cooperative launch runs every step and pulls each step's ids over PCIe itself; per-step losses are
+        stored straight into the pinned `losses_host` (valid after a stream synchronize)."""
+        pr = self._pairs
+        k = len(batch_indices)
+        if losses_host is None:
+            losses_host = torch.empty(k, dtype=torch.float32).pin_memory()
+        idx = (C.c_int64 * k)(*[int(b) for b in batch_indices])
+        us, it = self.user.c_struct(), self.item.c_struct()
+        N.check(N.lib().brk_bpr_train_steps_mapped(
+            N.ctx(self.device), C.byref(us), C.byref(it), C.c_void_p(u_host.data_ptr()), C.c_void_p(p_host.data_ptr()),
+            u_host.numel(), batch_size, idx, k, sampler_seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, self.numItem,
+            N.ptr(pr["indptr"]), N.ptr(pr["sitems"]), self.optimizer.h, N.ptr(self.optimizer.state),
+            C.c_void_p(losses_host.data_ptr()), N.stream_ptr()), "brk_bpr_train_steps_mapped")
         return losses_host
 
     def train_on_batch(self, u, p, n, loss_out=None):

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <stdlib.h>
+#include <vector>
 
 namespace {
 
@@ -155,18 +156,34 @@ bpr_scalar(const float* __restrict__ Wu, const float* __restrict__ Wi, float* __
 // K steps x (fused fwd/bwd -> grid.sync -> exact Keras Adam over both tables -> grid.sync): no kernel
 // launch and no host involvement between steps; both phases are single-wave and latency-bound, so the
 // launch gaps and cold starts between separate kernels were ~40 % of the step.
+// Sampling mode (P.n == nullptr): the kernel draws its own Philox negatives.  Two warps of every CTA
+// spend the Adam phase of step s staging step s+1 -- ids copied from P.u / P.p (which may be MAPPED HOST
+// memory: this is where the PCIe reads happen) into a device ring, negatives sampled next to them --
+// while the other six warps run Adam, so neither the binary search in the positive lists nor the PCIe
+// latency is on the step's critical path (only step 0 is staged up front).
+struct BprStep {                   // one training step of a cooperative launch
+  int64_t off;                     // first triplet of the step inside P.u / P.p / P.n
+  int64_t sample_index;            // Philox sample index of that triplet (sampling mode)
+  int32_t count;                   // triplets in the step (ragged tail batches are shorter)
+  int32_t _pad;
+};
+constexpr int kInlineSteps = 16;
 struct BprCoopParams {
   brk_table user, item;
   const int32_t* u; const int32_t* p; const int32_t* n;
-  const int64_t* batch_index;     // device [n_steps] (long calls) ...
-  int64_t inline_index[16];       // ... or by value (n_steps <= 16: no H2D copy at all)
+  const BprStep* steps;           // device [n_steps] (long calls) ...
+  BprStep inline_steps[kInlineSteps];   // ... or by value (n_steps <= 16: no H2D copy at all)
   int32_t use_inline;
-  int64_t total, batch;
   int32_t n_steps;
   brk_adam_hyper h;
   int64_t* state;                 // [t, beta1^t, beta2^t]
-  float* losses;                  // device [n_steps] or null
+  float* losses;                  // [n_steps] or null; device memory or mapped page-locked host memory
   double* loss_acc;               // 2 doubles (ping-pong), zero on entry
+  // sampling mode
+  int32_t* stage;                 // device [2][3][stage_pitch]: u, p, n of the step being staged / consumed
+  int64_t stage_pitch;
+  const int64_t* csr_indptr; const int32_t* csr_items;
+  uint32_t seed, epoch, num_items;
 };
 
 __device__ __forceinline__ void adam4(float4& w, float4& m, float4& v, const float4 g, float alpha, float b1, float b2,
@@ -178,11 +195,25 @@ __device__ __forceinline__ void adam4(float4& w, float4& m, float4& v, const flo
   m.w = b1 * m.w + omb1 * g.w; v.w = b2 * v.w + omb2 * g.w * g.w; w.w -= alpha * m.w / (sqrtf(v.w) + eps);
 }
 
+// Stage one step: ids into the device ring, one Philox negative per triplet (thread-per-triplet).
+__device__ __forceinline__ void bpr_stage_step(const BprCoopParams& P, const BprStep sd, int slot, int64_t tid, int64_t nthr) {
+  int32_t* su = P.stage + int64_t(slot) * 3 * P.stage_pitch;
+  int32_t* sp = su + P.stage_pitch; int32_t* sn = sp + P.stage_pitch;
+  for (int64_t b = tid; b < sd.count; b += nthr) {
+    const int32_t uu = P.u[sd.off + b];
+    su[b] = uu; sp[b] = P.p[sd.off + b];
+    sn[b] = brk_sample_bpr_negative(uint64_t(sd.sample_index + b), uu, P.seed, P.epoch, P.num_items, P.csr_indptr, P.csr_items);
+  }
+}
+
+constexpr int kStageThreads = 64;   // threads per CTA that stage the next step during the Adam phase
+
 template <int LPR, int NCH>
-__global__ void __launch_bounds__(kThreads) bpr_steps_coop(const BprCoopParams P) {
+__global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParams P) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
   __shared__ double red[32];
+  const bool sample = P.n == nullptr;
   const int d4 = P.user.d >> 2;
   const int lane_in = threadIdx.x & (LPR - 1);
   const int sub = (threadIdx.x & 31) / LPR;
@@ -198,23 +229,29 @@ __global__ void __launch_bounds__(kThreads) bpr_steps_coop(const BprCoopParams P
   double p1 = pw[1], p2 = pw[2];                       // running beta powers, advanced per step in registers
   const brk_table tabs[2] = {P.user, P.item};
 
+  if (sample) {                                         // step 0 is staged by everybody, up front
+    bpr_stage_step(P, P.use_inline ? P.inline_steps[0] : P.steps[0], 0, tid, nthr);
+    grid.sync();
+  }
   for (int s = 0; s < P.n_steps; ++s) {
-    const int64_t off = (P.use_inline ? P.inline_index[s] : P.batch_index[s]) * P.batch;
-    const int64_t batch = (off + P.batch <= P.total) ? P.batch : P.total - off;
+    const BprStep sd = P.use_inline ? P.inline_steps[s] : P.steps[s];
+    const int64_t batch = sd.count;
     const float inv_batch = 1.0f / float(batch);
-    const int32_t* uid = P.u + off; const int32_t* pid = P.p + off; const int32_t* nid = P.n + off;
+    const int32_t *uid, *pid, *nid;
+    if (sample) { uid = P.stage + int64_t(s & 1) * 3 * P.stage_pitch; pid = uid + P.stage_pitch; nid = pid + P.stage_pitch; }
+    else { uid = P.u + sd.off; pid = P.p + sd.off; nid = P.n + sd.off; }
     // ---- phase 1: fused gather + loss + gradient REDs (same math as bpr_vec) ----
     float loss_local = 0.f;
     for (int64_t wb = warp_first; wb < batch; wb += n_groups) {
       const int64_t b = wb + sub;
       const bool valid = b < batch;
       int64_t ru = 0, rp = 0, rn = 0;
-      if (valid) { ru = uid[b]; rp = pid[b]; rn = nid[b]; }
+      if (valid) { ru = __ldcg(uid + b); rp = __ldcg(pid + b); rn = __ldcg(nid + b); }
       float4 u[NCH], p[NCH], n[NCH];
 #pragma unroll
       for (int k = 0; k < NCH; ++k) {
         const int c = lane_in + k * LPR;
-        if (valid && c < d4) {           // plain loads: the tables are rewritten by phase 2 of the same kernel
+        if (valid && c < d4) {           // L2-only loads: the tables are rewritten by phase 2 of the same kernel
           u[k] = __ldcg(Wu4 + ru * d4 + c); p[k] = __ldcg(Wi4 + rp * d4 + c); n[k] = __ldcg(Wi4 + rn * d4 + c);
         } else {
           u[k] = p[k] = n[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -247,21 +284,30 @@ __global__ void __launch_bounds__(kThreads) bpr_steps_coop(const BprCoopParams P
     const double part = block_sum_double(double(loss_local), red);
     if (threadIdx.x == 0) atomicAdd(P.loss_acc + (s & 1), part);
     grid.sync();
-    // ---- phase 2: exact Keras Adam over every element of both tables; zero the accumulators ----
+    // ---- phase 2: exact Keras Adam over every element of both tables; zero the accumulators.  In sampling
+    //      mode the first two warps of each CTA stage step s+1 instead (ids + negatives) ----
     p1 *= double(P.h.beta1); p2 *= double(P.h.beta2);
     const float alpha = float(double(P.h.lr) * sqrt(1.0 - p2) / (1.0 - p1));
+    const bool staging = sample && s + 1 < P.n_steps;
+    if (staging && threadIdx.x < kStageThreads) {
+      bpr_stage_step(P, P.use_inline ? P.inline_steps[s + 1] : P.steps[s + 1], (s + 1) & 1,
+                     int64_t(blockIdx.x) * kStageThreads + threadIdx.x, int64_t(gridDim.x) * kStageThreads);
+    } else {
+      const int64_t atid = staging ? int64_t(blockIdx.x) * (kThreads - kStageThreads) + (threadIdx.x - kStageThreads) : tid;
+      const int64_t anthr = staging ? int64_t(gridDim.x) * (kThreads - kStageThreads) : nthr;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int64_t n4 = tabs[k].rows * tabs[k].d / 4;
-      float4* w4 = reinterpret_cast<float4*>(tabs[k].w); float4* g4 = reinterpret_cast<float4*>(tabs[k].g);
-      float4* m4 = reinterpret_cast<float4*>(tabs[k].m); float4* v4 = reinterpret_cast<float4*>(tabs[k].v);
-      for (int64_t i = tid; i < n4; i += nthr) {
-        float4 w = w4[i], m = m4[i], v = v4[i];
-        adam4(w, m, v, g4[i], alpha, P.h.beta1, P.h.beta2, P.h.eps);
-        w4[i] = w; m4[i] = m; v4[i] = v; g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < 2; ++k) {
+        const int64_t n4 = tabs[k].rows * tabs[k].d / 4;
+        float4* w4 = reinterpret_cast<float4*>(tabs[k].w); float4* g4 = reinterpret_cast<float4*>(tabs[k].g);
+        float4* m4 = reinterpret_cast<float4*>(tabs[k].m); float4* v4 = reinterpret_cast<float4*>(tabs[k].v);
+        for (int64_t i = atid; i < n4; i += anthr) {
+          float4 w = w4[i], m = m4[i], v = v4[i];
+          adam4(w, m, v, g4[i], alpha, P.h.beta1, P.h.beta2, P.h.eps);
+          w4[i] = w; m4[i] = m; v4[i] = v; g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     }
-    if (tid == 0) {
+    if (tid == nthr - 1) {
       if (P.losses) P.losses[s] = float(P.loss_acc[s & 1] / double(batch));
       P.loss_acc[s & 1] = 0.0;
     }
@@ -345,48 +391,86 @@ static bool coop_eligible(const brk_table* user, const brk_table* item, int lazy
          ((user->rows * d) & 3) == 0 && ((item->rows * d) & 3) == 0 && getenv("BRK_NO_COOP") == nullptr;
 }
 
+struct CoopSampler {                 // fused negative sampling for launch_coop_steps (n == nullptr)
+  const int64_t* csr_indptr; const int32_t* csr_items;
+  uint32_t seed, epoch, num_items;
+};
+
+static int ensure_scratch(brk_ctx* ctx, size_t need) {
+  if (ctx->scratch_bytes < need) {
+    if (ctx->scratch) BRK_CUDA(cudaFree(ctx->scratch));      // cudaFree waits for the device: no kernel still uses it
+    ctx->scratch = nullptr; ctx->scratch_bytes = 0;
+    BRK_CUDA(cudaMalloc(&ctx->scratch, need));
+    ctx->scratch_bytes = need;
+  }
+  return 0;
+}
+
+// steps_host[k]: off / count / sample_index of step k inside u, p (and n).  max_count: largest step.
 static int launch_coop_steps(brk_ctx* ctx, const brk_table* user, const brk_table* item, const int32_t* u,
-                             const int32_t* p, const int32_t* n, int64_t total, int64_t batch,
-                             const int64_t* batch_index_host, int32_t n_steps, brk_adam_hyper h, int64_t* step_dev,
-                             float* losses, cudaStream_t st) {
+                             const int32_t* p, const int32_t* n, const BprStep* steps_host, int32_t n_steps,
+                             int64_t max_count, brk_adam_hyper h, int64_t* step_dev, float* losses, cudaStream_t st,
+                             const CoopSampler* smp = nullptr) {
   const int d = user->d;
-    BprCoopParams P;
-    P.use_inline = n_steps <= 16;
-    if (P.use_inline) {
-      for (int k = 0; k < n_steps; ++k) P.inline_index[k] = batch_index_host[k];
-    } else {
-      // batch indices to the device (the context keeps a small scratch buffer)
-      const size_t need = size_t(n_steps) * sizeof(int64_t) + 64;
-      if (ctx->scratch_bytes < need) {
-        if (ctx->scratch) BRK_CUDA(cudaFree(ctx->scratch));
-        BRK_CUDA(cudaMalloc(&ctx->scratch, need * 2));
-        ctx->scratch_bytes = need * 2;
-      }
-      BRK_CUDA(cudaMemcpyAsync(ctx->scratch, batch_index_host, size_t(n_steps) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    }
-    P.user = *user; P.item = *item; P.u = u; P.p = p; P.n = n;
-    P.batch_index = reinterpret_cast<const int64_t*>(ctx->scratch);
-    P.total = total; P.batch = batch; P.n_steps = n_steps; P.h = h; P.state = step_dev; P.losses = losses;
-    P.loss_acc = ctx->loss_acc + 2;
-    const int lpr = brk_lanes_per_row(d >> 2);
-    void* fn = nullptr;
-    switch (lpr) {
-      case 1: fn = (void*)bpr_steps_coop<1, 1>; break;
-      case 2: fn = (void*)bpr_steps_coop<2, 1>; break;
-      case 4: fn = (void*)bpr_steps_coop<4, 1>; break;
-      case 8: fn = (void*)bpr_steps_coop<8, 1>; break;
-      case 16: fn = (void*)bpr_steps_coop<16, 1>; break;
-      default: fn = (void*)bpr_steps_coop<32, 1>; break;
-    }
-    int per_sm = 0;
+  BprCoopParams P;
+  P.use_inline = n_steps <= kInlineSteps;
+  const size_t steps_bytes = P.use_inline ? 0 : ((size_t(n_steps) * sizeof(BprStep) + 255) & ~size_t(255));
+  const int64_t pitch = (max_count + 3) & ~int64_t(3);
+  const size_t stage_bytes = smp ? size_t(2) * 3 * pitch * sizeof(int32_t) : 0;
+  if (steps_bytes + stage_bytes) { if (int rc = ensure_scratch(ctx, steps_bytes + stage_bytes)) return rc; }
+  if (P.use_inline) {
+    for (int k = 0; k < n_steps; ++k) P.inline_steps[k] = steps_host[k];
+  } else {
+    BRK_CUDA(cudaMemcpyAsync(ctx->scratch, steps_host, size_t(n_steps) * sizeof(BprStep), cudaMemcpyHostToDevice, st));
+  }
+  P.user = *user; P.item = *item; P.u = u; P.p = p; P.n = n;
+  P.steps = reinterpret_cast<const BprStep*>(ctx->scratch);
+  P.n_steps = n_steps; P.h = h; P.state = step_dev; P.losses = losses;
+  P.loss_acc = ctx->loss_acc + 2;
+  if (smp) {
+    P.stage = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ctx->scratch) + steps_bytes);
+    P.stage_pitch = pitch;
+    P.csr_indptr = smp->csr_indptr; P.csr_items = smp->csr_items;
+    P.seed = smp->seed; P.epoch = smp->epoch; P.num_items = smp->num_items;
+  } else {
+    BRK_REQUIRE(n != nullptr, BRK_E_ARG, "brk_bpr_train_steps: negatives missing");
+    P.stage = nullptr; P.stage_pitch = 0; P.csr_indptr = nullptr; P.csr_items = nullptr;
+    P.seed = P.epoch = P.num_items = 0;
+  }
+  const int lpr = brk_lanes_per_row(d >> 2);
+  void* fn = nullptr;
+  int slot = 0;
+  switch (lpr) {
+    case 1: fn = (void*)bpr_steps_coop<1, 1>; slot = 0; break;
+    case 2: fn = (void*)bpr_steps_coop<2, 1>; slot = 1; break;
+    case 4: fn = (void*)bpr_steps_coop<4, 1>; slot = 2; break;
+    case 8: fn = (void*)bpr_steps_coop<8, 1>; slot = 3; break;
+    case 16: fn = (void*)bpr_steps_coop<16, 1>; slot = 4; break;
+    default: fn = (void*)bpr_steps_coop<32, 1>; slot = 5; break;
+  }
+  static int per_sm_cache[6] = {0, 0, 0, 0, 0, 0};      // occupancy is a property of the kernel: query once
+  int per_sm = per_sm_cache[slot];
+  if (per_sm == 0) {
     BRK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0));
     BRK_REQUIRE(per_sm > 0, BRK_E_STATE, "brk_bpr_train_steps: cooperative kernel does not fit");
-    int64_t want = (batch * lpr + kThreads - 1) / kThreads;
-    const int64_t cap = int64_t(per_sm) * ctx->sm_count;
-    const int grid = int(want < cap ? (want < 1 ? 1 : want) : cap);
-    void* args[] = {(void*)&P};
-    BRK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, st));
-    return 0;
+    per_sm_cache[slot] = per_sm;
+  }
+  int64_t want = (max_count * lpr + kThreads - 1) / kThreads;
+  const int64_t cap = int64_t(per_sm) * ctx->sm_count;
+  const int grid = int(want < cap ? (want < 1 ? 1 : want) : cap);
+  void* args[] = {(void*)&P};
+  BRK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, 0, st));
+  return 0;
+}
+
+// step descriptors of batches `batch_index[k]` of arrays cut into batches of `batch`
+static void make_steps(BprStep* out, const int64_t* batch_index, int n_steps, int64_t total, int64_t batch) {
+  for (int k = 0; k < n_steps; ++k) {
+    const int64_t off = batch_index[k] * batch;
+    out[k].off = off; out[k].sample_index = off;
+    out[k].count = int32_t((off + batch <= total) ? batch : total - off);
+    out[k]._pad = 0;
+  }
 }
 
 // Multi-step driver: one C call enqueues n_steps x (fused fwd/bwd + optimizer) so that the host
@@ -409,7 +493,12 @@ extern "C" int brk_bpr_train_steps(brk_ctx* ctx, const brk_table* user, const br
   if (n_steps == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const bool coop_ok = coop_eligible(user, item, lazy_adam);
-  if (coop_ok) return launch_coop_steps(ctx, user, item, u, p, n, total, batch, batch_index_host, n_steps, h, step_dev, losses, st);
+  if (coop_ok) {
+    std::vector<BprStep> steps(n_steps);
+    make_steps(steps.data(), batch_index_host, n_steps, total, batch);
+    return launch_coop_steps(ctx, user, item, u, p, n, steps.data(), n_steps, batch < total ? batch : total, h, step_dev,
+                             losses, st);
+  }
   brk_table tabs[2] = {*user, *item};
   for (int k = 0; k < n_steps; ++k) {
     const int64_t bi = batch_index_host[k];
@@ -425,19 +514,36 @@ extern "C" int brk_bpr_train_steps(brk_ctx* ctx, const brk_table* user, const br
 }
 
 // End-to-end steps from HOST buffers in one call (the public-API path bench.py's `e2e` times):
-// per step  H2D(user ids, positive ids)  ->  Philox negatives on device  ->  fused fwd/bwd  ->  Adam
-// ->  D2H(loss).  u_host/p_host/losses_host must be page-locked for the copies to be asynchronous.
-// d_stage: device int32 scratch of 6*batch (two slots of u,p,n); d_losses: device [n_steps].
+// every step's user / positive ids go H2D with their own cudaMemcpyAsync from the caller's page-locked
+// arrays (ONE copy per step when the host layout is batch-major [n_batches][2][batch], i.e.
+// p_host == u_host + batch and host_batch_stride == 2*batch), the step runs, and the losses come back D2H
+// once per chunk.  Steps are launched in
+// chunks of kChunk: one cooperative kernel runs kChunk steps (sampling its own Philox negatives, see
+// bpr_steps_coop), so launch latency and the up-front staging of the first step are paid once per chunk.
+// Copies run on a second stream through a ring of 2*kChunk staging slots (two chunks in flight):
+//   copy stream,    chunk j : wait done[j-2] ; D2H losses of chunk j-2 (one copy) ; H2D ids of chunk j ; record ready[j]
+//   compute stream, chunk j : wait ready[j] ; cooperative kernel (kChunk steps) ; record done[j]
+// d_stage: device int32 scratch of BRK_BPR_STAGE_INTS(batch) = 4*kChunk*batch; d_losses: device [n_steps].
+constexpr int kChunk = 16;
+
+extern "C" int64_t brk_bpr_host_stage_ints(int64_t batch) { return int64_t(4) * kChunk * batch; }
+
 extern "C" int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, const brk_table* item,
                                         const int32_t* u_host, const int32_t* p_host, int64_t total, int64_t batch,
-                                        const int64_t* batch_index_host, int32_t n_steps, uint32_t seed, uint32_t epoch,
+                                        int64_t host_batch_stride, const int64_t* batch_index_host, int32_t n_steps, uint32_t seed, uint32_t epoch,
                                         int32_t num_items, const int64_t* csr_indptr, const int32_t* csr_items,
                                         brk_adam_hyper h, int32_t lazy_adam, int64_t* step_dev, int32_t* d_stage,
                                         float* d_losses, float* losses_host, void* stream) {
   BRK_REQUIRE(ctx && user && item && u_host && p_host && batch_index_host && step_dev && d_stage && d_losses &&
                   csr_indptr && csr_items, BRK_E_ARG, "brk_bpr_train_steps_host: null argument");
-  BRK_REQUIRE(total > 0 && batch > 0 && n_steps >= 0, BRK_E_ARG, "brk_bpr_train_steps_host: total=%lld batch=%lld",
-              (long long)total, (long long)batch);
+  BRK_REQUIRE(total > 0 && batch > 0 && n_steps >= 0 && num_items > 0, BRK_E_ARG,
+              "brk_bpr_train_steps_host: total=%lld batch=%lld", (long long)total, (long long)batch);
+  if (host_batch_stride <= 0) host_batch_stride = batch;
+  BRK_REQUIRE(host_batch_stride >= batch, BRK_E_ARG, "brk_bpr_train_steps_host: host_batch_stride=%lld < batch",
+              (long long)host_batch_stride);
+  // batch-major host layout [n_batches][2][batch] (a loader that writes each batch's user ids then its item
+  // ids): the step's inputs are ONE contiguous block -> one DMA per step instead of two
+  const bool packed = host_batch_stride == 2 * batch && p_host == u_host + batch;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n_batches = (total + batch - 1) / batch;
   for (int k = 0; k < n_steps; ++k)
@@ -446,7 +552,7 @@ extern "C" int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, con
   if (n_steps == 0) return 0;
   if (!ctx->copy_ready) {
     BRK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < BRK_STAGE_EVENTS; ++q) {
       BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[q], cudaEventDisableTiming));
       BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[q], cudaEventDisableTiming));
     }
@@ -455,49 +561,120 @@ extern "C" int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, con
   cudaStream_t cs = ctx->copy_stream;
   const bool coop_ok = coop_eligible(user, item, lazy_adam);
   brk_table tabs[2] = {*user, *item};
-  const int64_t zero_index = 0;
-  // the copy stream must not run ahead of work already queued on `st` that still uses the staging slots
-  BRK_CUDA(cudaEventRecord(ctx->ev_done[0], st));
-  BRK_CUDA(cudaEventRecord(ctx->ev_done[1], st));
-  auto stage = [&](int k) -> int {                 // H2D of step k's ids into slot k&1, on the copy stream
-    const int64_t off = batch_index_host[k] * batch;
-    const int64_t cnt = (off + batch <= total) ? batch : total - off;
-    int32_t* du = d_stage + (k & 1) * 3 * batch;
-    BRK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_done[k & 1], 0));          // slot free (step k-2 finished)
-    BRK_CUDA(cudaMemcpyAsync(du, u_host + off, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
-    BRK_CUDA(cudaMemcpyAsync(du + batch, p_host + off, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
-    BRK_CUDA(cudaEventRecord(ctx->ev_ready[k & 1], cs));
+  const int n_chunks = (n_steps + kChunk - 1) / kChunk;
+  auto count_of = [&](int k) { const int64_t off = batch_index_host[k] * batch; return (off + batch <= total) ? batch : total - off; };
+  // slot of step k: two chunk halves of kChunk slots, each slot = [u: batch][p: batch]
+  auto slot_of = [&](int k) { return d_stage + (int64_t((k / kChunk) & 1) * kChunk + (k % kChunk)) * 2 * batch; };
+  auto copy_chunk = [&](int j) -> int {            // on the copy stream: results of chunk j-2 back, ids of chunk j in
+    if (j >= 2) {
+      BRK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_done[j & 1], 0));
+      if (losses_host)                               // the kChunk step losses of chunk j-2, one DMA
+        BRK_CUDA(cudaMemcpyAsync(losses_host + (j - 2) * kChunk, d_losses + (j - 2) * kChunk, kChunk * sizeof(float),
+                                 cudaMemcpyDeviceToHost, cs));
+    }
+    for (int k = j * kChunk; k < (j + 1) * kChunk && k < n_steps; ++k) {
+      const int64_t hoff = batch_index_host[k] * host_batch_stride, cnt = count_of(k);
+      if (packed) {
+        BRK_CUDA(cudaMemcpyAsync(slot_of(k), u_host + hoff, 2 * batch * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+      } else {
+        BRK_CUDA(cudaMemcpyAsync(slot_of(k), u_host + hoff, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+        BRK_CUDA(cudaMemcpyAsync(slot_of(k) + batch, p_host + hoff, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+      }
+    }
+    BRK_CUDA(cudaEventRecord(ctx->ev_ready[j & 1], cs));
     return 0;
   };
-  if (int rc = stage(0)) return rc;
-  for (int k = 0; k < n_steps; ++k) {
-    if (k + 1 < n_steps) { if (int rc = stage(k + 1)) return rc; }       // prefetch the next batch's ids
-    const int64_t off = batch_index_host[k] * batch;
-    const int64_t cnt = (off + batch <= total) ? batch : total - off;
-    int32_t* du = d_stage + (k & 1) * 3 * batch;
-    int32_t* dp = du + batch;
-    int32_t* dn = dp + batch;
-    BRK_CUDA(cudaStreamWaitEvent(st, ctx->ev_ready[k & 1], 0));
-    int rc = brk_philox_bpr_negatives(ctx, du, cnt, off, seed, epoch, num_items, csr_indptr, csr_items, dn, stream);
-    if (rc) return rc;
+  // the copy stream must not run ahead of work already queued on `st` that may still use the staging slots
+  BRK_CUDA(cudaEventRecord(ctx->ev_done[2], st));
+  BRK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_done[2], 0));
+  if (int rc = copy_chunk(0)) return rc;
+  for (int j = 0; j < n_chunks; ++j) {
+    if (j + 1 < n_chunks) { if (int rc = copy_chunk(j + 1)) return rc; }
+    const int k0 = j * kChunk, k1 = (k0 + kChunk < n_steps) ? k0 + kChunk : n_steps;
+    BRK_CUDA(cudaStreamWaitEvent(st, ctx->ev_ready[j & 1], 0));
     if (coop_ok) {
-      rc = launch_coop_steps(ctx, user, item, du, dp, dn, cnt, cnt, &zero_index, 1, h, step_dev, d_losses + k, st);
+      BprStep steps[kChunk];
+      for (int k = k0; k < k1; ++k) {
+        steps[k - k0].off = slot_of(k) - d_stage;                     // u at off, p at off + batch (see P.p below)
+        steps[k - k0].sample_index = batch_index_host[k] * batch;
+        steps[k - k0].count = int32_t(count_of(k)); steps[k - k0]._pad = 0;
+      }
+      CoopSampler smp{csr_indptr, csr_items, seed, epoch, uint32_t(num_items)};
+      int rc = launch_coop_steps(ctx, user, item, d_stage, d_stage + batch, nullptr, steps, k1 - k0, batch, h, step_dev,
+                                 d_losses + k0, st, &smp);
       if (rc) return rc;
     } else {
-      rc = brk_bpr_fwd_bwd(ctx, user, item, du, dp, dn, cnt, 0, d_losses + k, stream);
-      if (rc) return rc;
-      rc = lazy_adam ? brk_adam_rows(ctx, tabs, 2, h, step_dev, 1, stream)
-                     : brk_adam_dense_keras(ctx, tabs, 2, h, step_dev, 1, stream);
-      if (rc) return rc;
+      // generic widths / lazy Adam: separate sampler, fused fwd/bwd and optimizer launches (negatives in the
+      // context scratch; steps are ordered on `st`, so one buffer serves all of them)
+      if (int rc = ensure_scratch(ctx, size_t(batch) * sizeof(int32_t))) return rc;
+      int32_t* dn = reinterpret_cast<int32_t*>(ctx->scratch);
+      for (int k = k0; k < k1; ++k) {
+        const int64_t off = batch_index_host[k] * batch, cnt = count_of(k);
+        int32_t* du = slot_of(k);
+        int rc = brk_philox_bpr_negatives(ctx, du, cnt, off, seed, epoch, num_items, csr_indptr, csr_items, dn, stream);
+        if (rc) return rc;
+        rc = brk_bpr_fwd_bwd(ctx, user, item, du, du + batch, dn, cnt, 0, d_losses + k, stream);
+        if (rc) return rc;
+        rc = lazy_adam ? brk_adam_rows(ctx, tabs, 2, h, step_dev, 1, stream)
+                       : brk_adam_dense_keras(ctx, tabs, 2, h, step_dev, 1, stream);
+        if (rc) return rc;
+      }
     }
-    BRK_CUDA(cudaEventRecord(ctx->ev_done[k & 1], st));
-    if (losses_host) {                               // the step's result goes back on the copy stream
-      BRK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_done[k & 1], 0));
-      BRK_CUDA(cudaMemcpyAsync(losses_host + k, d_losses + k, sizeof(float), cudaMemcpyDeviceToHost, cs));
-    }
+    BRK_CUDA(cudaEventRecord(ctx->ev_done[j & 1], st));
   }
-  // rejoin: everything the copy stream did is ordered before whatever follows on `st`
-  BRK_CUDA(cudaEventRecord(ctx->ev_ready[0], cs));
-  BRK_CUDA(cudaStreamWaitEvent(st, ctx->ev_ready[0], 0));
+  // results of the last two chunks, then rejoin: everything the copy stream did is ordered before
+  // whatever follows on `st`
+  if (losses_host) {
+    const int first = (n_chunks >= 2 ? n_chunks - 2 : 0) * kChunk;
+    BRK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_done[(n_chunks - 1) & 1], 0));
+    BRK_CUDA(cudaMemcpyAsync(losses_host + first, d_losses + first, (n_steps - first) * sizeof(float),
+                             cudaMemcpyDeviceToHost, cs));
+  }
+  BRK_CUDA(cudaEventRecord(ctx->ev_ready[2], cs));
+  BRK_CUDA(cudaStreamWaitEvent(st, ctx->ev_ready[2], 0));
   return 0;
+}
+
+// The same loop with the ids left in page-locked (mapped) HOST memory and no copy engine involved: ONE
+// cooperative launch runs all n_steps; each step's kernel phase pulls that step's ids over PCIe
+// (8*batch bytes), draws the negatives, trains, and stores the step's loss straight into
+// losses_host.  u_host / p_host / losses_host must be device-accessible page-locked memory
+// (cudaHostAlloc / torch pin_memory under unified addressing).
+extern "C" int brk_bpr_train_steps_mapped(brk_ctx* ctx, const brk_table* user, const brk_table* item,
+                                          const int32_t* u_host, const int32_t* p_host, int64_t total, int64_t batch,
+                                          const int64_t* batch_index_host, int32_t n_steps, uint32_t seed,
+                                          uint32_t epoch, int32_t num_items, const int64_t* csr_indptr,
+                                          const int32_t* csr_items, brk_adam_hyper h, int64_t* step_dev,
+                                          float* losses_host, void* stream) {
+  BRK_REQUIRE(ctx && user && item && u_host && p_host && batch_index_host && step_dev && csr_indptr && csr_items,
+              BRK_E_ARG, "brk_bpr_train_steps_mapped: null argument");
+  BRK_REQUIRE(total > 0 && batch > 0 && n_steps >= 0 && num_items > 0, BRK_E_ARG,
+              "brk_bpr_train_steps_mapped: total=%lld batch=%lld", (long long)total, (long long)batch);
+  const int64_t n_batches = (total + batch - 1) / batch;
+  for (int k = 0; k < n_steps; ++k)
+    BRK_REQUIRE(batch_index_host[k] >= 0 && batch_index_host[k] < n_batches, BRK_E_ARG,
+                "brk_bpr_train_steps_mapped: batch index %lld of %lld", (long long)batch_index_host[k], (long long)n_batches);
+  BRK_REQUIRE(coop_eligible(user, item, 0), BRK_E_ARG,
+              "brk_bpr_train_steps_mapped: needs the cooperative path (d %% 4 == 0, d <= 128, Adam slots, 16-byte aligned tables)");
+  if (n_steps == 0) return 0;
+  // device-visible aliases of the caller's buffers (mapped page-locked host memory, or plain device memory)
+  auto dev_alias = [](const void* hp, const void** out) -> int {
+    cudaPointerAttributes a;
+    BRK_CUDA(cudaPointerGetAttributes(&a, hp));
+    BRK_REQUIRE((a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) &&
+                    a.devicePointer, BRK_E_ARG,
+                "brk_bpr_train_steps_mapped: buffer %p is not device-accessible (page-lock it: cudaHostAlloc / pin_memory)", hp);
+    *out = a.devicePointer;
+    return 0;
+  };
+  const void *du = nullptr, *dp = nullptr, *dl = nullptr;
+  if (int rc = dev_alias(u_host, &du)) return rc;
+  if (int rc = dev_alias(p_host, &dp)) return rc;
+  if (losses_host) { if (int rc = dev_alias(losses_host, &dl)) return rc; }
+  CoopSampler smp{csr_indptr, csr_items, seed, epoch, uint32_t(num_items)};
+  std::vector<BprStep> steps(n_steps);
+  make_steps(steps.data(), batch_index_host, n_steps, total, batch);
+  return launch_coop_steps(ctx, user, item, reinterpret_cast<const int32_t*>(du), reinterpret_cast<const int32_t*>(dp),
+                           nullptr, steps.data(), n_steps, batch < total ? batch : total, h, step_dev,
+                           reinterpret_cast<float*>(const_cast<void*>(dl)), (cudaStream_t)stream, &smp);
 }

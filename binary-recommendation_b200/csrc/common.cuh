@@ -14,10 +14,11 @@ struct brk_ctx {
   size_t        scratch_bytes;
   // host-fed training: copy stream + events for H2D prefetch / loss D2H (created on first use)
   cudaStream_t  copy_stream;
-  cudaEvent_t   ev_ready[2], ev_done[2];
+  cudaEvent_t   ev_ready[4], ev_done[4];
   int           copy_ready;
 };
 
+#define BRK_STAGE_EVENTS 4
 #define BRK_LOSS_SLOTS 16
 #define BRK_TICKETS 16
 
@@ -124,6 +125,28 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
     k1 += 0xBB67AE85u;
   }
   return c;
+}
+
+// "brk sampler v2" BPR stream (oracle/philox.py): one Philox draw picks rank r among the I - n items the
+// user has NOT interacted with; the negative is the r-th such item: r + t with t the smallest index in
+// [0, n] such that t == n or a[t] - t > r (a = the user's sorted positive list).  One binary search, no
+// rejection loop, so the slowest sample of a batch costs the same as every other one.
+constexpr uint32_t kBrkTagBpr = 0xB9u;
+__device__ __forceinline__ int32_t brk_sample_bpr_negative(uint64_t idx, int64_t u, uint32_t seed, uint32_t epoch,
+                                                           uint32_t num_items, const int64_t* __restrict__ indptr,
+                                                           const int32_t* __restrict__ items) {
+  const int64_t base = __ldg(indptr + u);
+  const uint32_t n = uint32_t(__ldg(indptr + u + 1) - base);
+  const uint4 w = philox4x32_10(make_uint4(uint32_t(idx), uint32_t(idx >> 32), 0u, kBrkTagBpr), seed, epoch);
+  if (n >= num_items) return int32_t(__umulhi(w.x, num_items));
+  const uint32_t r = __umulhi(w.x, num_items - n);
+  const int32_t* __restrict__ a = items + base;
+  uint32_t lo = 0, hi = n;                       // smallest t in [0, n] with t == n or a[t] - t > r
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) - int32_t(mid) > int32_t(r)) hi = mid; else lo = mid + 1;
+  }
+  return int32_t(r + lo);
 }
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }

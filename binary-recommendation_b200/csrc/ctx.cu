@@ -50,7 +50,7 @@ extern "C" int brk_destroy(brk_ctx* c) {
   if (c->scratch) cudaFree(c->scratch);
   if (c->copy_ready) {
     cudaStreamDestroy(c->copy_stream);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_ready[i]); cudaEventDestroy(c->ev_done[i]); }
+    for (int i = 0; i < BRK_STAGE_EVENTS; ++i) { cudaEventDestroy(c->ev_ready[i]); cudaEventDestroy(c->ev_done[i]); }
   }
   free(c);
   return 0;

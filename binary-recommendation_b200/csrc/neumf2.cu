@@ -435,7 +435,10 @@ __global__ void __launch_bounds__(NT) head(const Args A) {
     Ys[j * PT + s] = dz;
     Zt[s * ZP + j] = dz;
   }
-  if (H3 < 4) for (int idx = t; idx < TS * (4 - H3); idx += NT) Zt[(idx / (4 - H3)) * ZP + H3 + idx % (4 - H3)] = 0.f;
+  if constexpr (H3 < 4) {
+    constexpr int PADC = 4 - H3;
+    for (int idx = t; idx < TS * PADC; idx += NT) Zt[(idx / PADC) * ZP + H3 + idx % PADC] = 0.f;
+  }
   __syncthreads();
   layer_wgrad<H2, H3>(Xs, Ys, A.dense.g + L::W3, A.dense.g + L::b3);
   // MF embedding gradients (thread-per-sample, rows re-read through L1)

@@ -1,4 +1,4 @@
-// K10: counter-based negative sampling, Philox4x32-10.  The stream ("brk sampler v1") is defined
+// K10: counter-based negative sampling, Philox4x32-10.  The stream ("brk sampler v2") is defined
 // in oracle/philox.py; the reference samples with the host's global RNG
 // (/root/reference/src/models/NeuMFModel.py:104-105) or enumerates exhaustively
 // (/root/reference/src/models/BPRModel.py:111-119).  One thread per sample; ~4 B id read +
@@ -8,19 +8,7 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr uint32_t kTagBpr = 0xB9u;
 constexpr uint32_t kTagNeumf = 0x4Eu;
-constexpr int kBprMaxAttempts = 16;
-
-__device__ __forceinline__ bool csr_has(const int32_t* __restrict__ items, int64_t lo, int64_t hi,
-                                        int32_t key) {
-  const int64_t end = hi;
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (__ldg(items + mid) < key) lo = mid + 1; else hi = mid;
-  }
-  return lo < end && __ldg(items + lo) == key;
-}
 
 __global__ void __launch_bounds__(kThreads)
 philox_bpr_negatives(const int32_t* __restrict__ users, int64_t n, int64_t first_index, uint32_t seed,
@@ -28,24 +16,7 @@ philox_bpr_negatives(const int32_t* __restrict__ users, int64_t n, int64_t first
                      const int32_t* __restrict__ items, int32_t* __restrict__ neg) {
   const int64_t stride = int64_t(gridDim.x) * kThreads;
   for (int64_t b = int64_t(blockIdx.x) * kThreads + threadIdx.x; b < n; b += stride) {
-    const uint64_t idx = uint64_t(first_index + b);
-    const int64_t u = __ldg(users + b);
-    const int64_t lo = __ldg(indptr + u), hi = __ldg(indptr + u + 1);
-    int32_t cand = 0;
-    bool done = false;
-    for (int a = 0; a < kBprMaxAttempts && !done; ++a) {
-      const uint4 w = philox4x32_10(make_uint4(uint32_t(idx), uint32_t(idx >> 32), uint32_t(a), kTagBpr),
-                                    seed, epoch);
-      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (!done) {
-          cand = int32_t(__umulhi(ww[k], num_items));
-          done = !csr_has(items, lo, hi, cand);
-        }
-      }
-    }
-    neg[b] = cand;
+    neg[b] = brk_sample_bpr_negative(uint64_t(first_index + b), __ldg(users + b), seed, epoch, num_items, indptr, items);
   }
 }
 

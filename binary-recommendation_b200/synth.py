@@ -57,11 +57,15 @@ def build_csr(users, items, num_users):
     This is the membership structure the device sampler probes (csrc/sampler.cu)."""
     users = np.asarray(users, dtype=np.int64)
     items = np.asarray(items, dtype=np.int64)
-    order = np.lexsort((items, users))
-    counts = np.bincount(users, minlength=num_users)
+    # distinct (user, item) pairs, sorted by user then item: repeated interactions count once (the sampler's
+    # rank-select needs strictly increasing lists)
+    width = int(items.max()) + 1 if len(items) else 1
+    keys = np.unique(users * width + items)
+    su, si = keys // width, keys % width
+    counts = np.bincount(su, minlength=num_users)
     indptr = np.zeros(num_users + 1, dtype=np.int64)
     np.cumsum(counts, out=indptr[1:])
-    return indptr, items[order].astype(np.int32)
+    return indptr, si.astype(np.int32)
 
 
 def train_test_split(users, items, test_size=0.2, seed=DATA_SEED + 1):

@@ -81,9 +81,10 @@ int brk_scatter_add_rows(brk_ctx* ctx, float* acc, int64_t rows, int32_t d,
 /* ---- K10: counter-based negative sampling (Philox4x32-10) ---------------------------------
  * Replaces the host-RNG sampling of src/models/NeuMFModel.py:104-105 and the exhaustive
  * enumeration of src/models/BPRModel.py:111-119 / src/models/bpr.py:96-107.  The stream is
- * defined in oracle/philox.py ("brk sampler v1") and reproduced bit-for-bit.
- * BPR: for sample first_index+b with user users[b], the first candidate item that is not in the
- * user's sorted positive list (csr_indptr int64 [U+1], csr_items int32) is written to neg[b]. */
+ * defined in oracle/philox.py ("brk sampler v2") and reproduced bit-for-bit.
+ * BPR: for sample first_index+b with user users[b], one draw picks a rank among the items that are
+ * not in the user's sorted positive list (csr_indptr int64 [U+1], csr_items int32); that item is
+ * written to neg[b] (uniform over the non-interacted items, one binary search, no rejection loop). */
 int brk_philox_bpr_negatives(brk_ctx* ctx, const int32_t* users, int64_t n, int64_t first_index,
                              uint32_t seed, uint32_t epoch, int32_t num_items,
                              const int64_t* csr_indptr, const int32_t* csr_items,
@@ -120,16 +121,31 @@ int brk_bpr_train_steps(brk_ctx* ctx, const brk_table* user, const brk_table* it
                         int64_t batch, const int64_t* batch_index_host, int32_t n_steps,
                         brk_adam_hyper h, int32_t lazy_adam, int64_t* step_dev, float* losses,
                         void* stream);
-/* The same loop fed from HOST memory (what a caller holding NumPy / pandas columns does): per step
- * H2D of the batch's user and positive ids, Philox negatives on the device, fused step, Adam, D2H of
- * the loss.  u_host / p_host / losses_host should be page-locked (then nothing here blocks);
- * d_stage: device int32 scratch [6*batch]; d_losses: device [n_steps]. */
+/* The same loop fed from HOST memory (what a caller holding NumPy / pandas columns does): every step's
+ * user and positive ids go H2D with their own cudaMemcpyAsync (copy stream, ring of staging slots), the
+ * steps run in cooperative launches of up to 16 steps each (the kernel draws its own Philox negatives
+ * while the previous step's Adam phase runs), every step's loss comes back D2H.
+ * u_host / p_host / losses_host should be page-locked (then nothing here blocks).
+ * host_batch_stride: int32 elements between consecutive batches in u_host / p_host (0 = batch, i.e. two flat
+ * arrays); with the batch-major layout [n_batches][2][batch] (p_host == u_host + batch, stride 2*batch;
+ * the last block padded to full size) each step's ids move with ONE copy.
+ * d_stage: device int32 scratch [brk_bpr_host_stage_ints(batch)]; d_losses: device [n_steps]. */
+int64_t brk_bpr_host_stage_ints(int64_t batch);
 int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, const brk_table* item,
                              const int32_t* u_host, const int32_t* p_host, int64_t total, int64_t batch,
-                             const int64_t* batch_index_host, int32_t n_steps, uint32_t seed, uint32_t epoch,
+                             int64_t host_batch_stride, const int64_t* batch_index_host, int32_t n_steps, uint32_t seed, uint32_t epoch,
                              int32_t num_items, const int64_t* csr_indptr, const int32_t* csr_items,
                              brk_adam_hyper h, int32_t lazy_adam, int64_t* step_dev, int32_t* d_stage,
                              float* d_losses, float* losses_host, void* stream);
+/* Zero-copy variant: u_host / p_host / losses_host are MAPPED page-locked host memory; ONE cooperative
+ * launch runs all n_steps, every step's kernel phase pulls that step's ids over PCIe (8*batch bytes),
+ * draws the negatives, trains, and stores the loss straight into losses_host[k].  Exact Keras Adam
+ * only (the cooperative path). */
+int brk_bpr_train_steps_mapped(brk_ctx* ctx, const brk_table* user, const brk_table* item,
+                               const int32_t* u_host, const int32_t* p_host, int64_t total, int64_t batch,
+                               const int64_t* batch_index_host, int32_t n_steps, uint32_t seed, uint32_t epoch,
+                               int32_t num_items, const int64_t* csr_indptr, const int32_t* csr_items,
+                               brk_adam_hyper h, int64_t* step_dev, float* losses_host, void* stream);
 /* Forward only: x_out[b] = <u,p> - <u,n> (scores for evaluation, bpr.py:122-133). */
 int brk_bpr_scores(brk_ctx* ctx, const float* user_w, const float* item_w, int32_t d,
                    const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch,

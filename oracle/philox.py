@@ -10,15 +10,20 @@ kernel (csrc/sampler.cu) must reproduce it exactly.
 Pinning: Philox4x32-10 is the Random123 generator (Salmon et al., SC'11); its published
 known-answer vectors are checked in tests/test_oracle_philox.py.
 
-Stream definition ("brk sampler v1"):
+Stream definition ("brk sampler v2"):
   key      = (seed & 0xffffffff, epoch & 0xffffffff)
   counter  = (idx & 0xffffffff, idx >> 32, attempt, stream_tag)
   a draw r in [0, 2^32) maps to an index in [0, n) by the multiply-shift  (r * n) >> 32.
 
-  BPR negatives (stream_tag 0xB9): for sample idx with user u, attempts a = 0..15 each give
-  four candidates (words 0..3 in order); the first candidate item j with (u, j) NOT in the
-  user's positive set wins.  If all 64 collide the last candidate is returned.  This keeps
-  the reference's guarantee that a BPR negative is a non-interacted item (BPRModel.py:116).
+  BPR negatives (stream_tag 0xB9): one Philox call per sample (attempt = 0, word 0).  For user
+  u with sorted positive list a[0..n) the draw picks rank r = (w0 * (I - n)) >> 32 among the
+  I - n NON-interacted items and the negative is the r-th such item in ascending id order:
+  j = r + t with t the smallest index in [0, n] such that t == n or a[t] - t > r.  Uniform over
+  the non-interacted items (what the reference's exhaustive enumeration samples from,
+  BPRModel.py:116), one binary search per sample and no rejection loop (v1 re-drew on a
+  collision: same distribution, but the slowest of a batch's samples needed ~10 searches and
+  a whole step waited for it).  A user who interacted with every item (n == I) gets
+  j = (w0 * I) >> 32, the only case in which the "negative" is a positive.
 
   NeuMF negatives (stream_tag 0x4E): one Philox call per negative, attempt = 0;
   user = pos_user[(w0 * P) >> 32], item = pos_item[(w1 * P) >> 32].  Like the reference
@@ -35,7 +40,6 @@ MASK = np.uint64(0xFFFFFFFF)
 
 TAG_BPR = 0xB9
 TAG_NEUMF = 0x4E
-BPR_MAX_ATTEMPTS = 16
 
 
 def philox4x32_10(ctr, key):
@@ -63,11 +67,11 @@ def _mulshift(r, n):
 
 
 def build_csr(users, items, num_users):
-    """Sorted per-user positive lists: (indptr int64 [U+1], sorted_items int32 [P])."""
+    """Sorted per-user lists of DISTINCT positives: (indptr int64 [U+1], sorted_items int32 [<= P])."""
     users = np.asarray(users, dtype=np.int64)
     items = np.asarray(items, dtype=np.int64)
-    order = np.lexsort((items, users))
-    su, si = users[order], items[order]
+    pairs = np.unique(np.stack([users, items], axis=1), axis=0) if len(users) else np.zeros((0, 2), dtype=np.int64)
+    su, si = pairs[:, 0], pairs[:, 1]
     indptr = np.zeros(num_users + 1, dtype=np.int64)
     np.add.at(indptr, su + 1, 1)
     indptr = np.cumsum(indptr)
@@ -84,33 +88,56 @@ def _is_positive(indptr, sorted_items, num_items, u, j):
     return (keys[pos] == q) if len(keys) else np.zeros(len(q), dtype=bool)
 
 
+def _bpr_draws(users, seed, epoch, first_index):
+    n = len(users)
+    idx = np.arange(first_index, first_index + n, dtype=np.uint64)
+    ctr = np.stack([(idx & MASK), (idx >> np.uint64(32)), np.zeros(n, dtype=np.uint64),
+                    np.full(n, TAG_BPR, dtype=np.uint64)], axis=1).astype(np.uint32)
+    return philox4x32_10(ctr, (seed, epoch))[:, 0]
+
+
+def bpr_negatives_scalar(users, seed, epoch, num_items, indptr, sorted_items, first_index=0):
+    """The definition, sample by sample (small inputs; bpr_negatives is the vectorised form)."""
+    users = np.asarray(users, dtype=np.int64)
+    w0 = _bpr_draws(users, seed, epoch, first_index)
+    indptr = np.asarray(indptr, dtype=np.int64)
+    sorted_items = np.asarray(sorted_items, dtype=np.int64)
+    out = np.empty(len(users), dtype=np.int64)
+    for s in range(len(users)):
+        lo, hi = int(indptr[users[s]]), int(indptr[users[s] + 1])
+        missing = [j for j in range(num_items) if j not in set(sorted_items[lo:hi].tolist())]
+        if not missing:
+            out[s] = (int(w0[s]) * num_items) >> 32
+        else:
+            out[s] = missing[(int(w0[s]) * len(missing)) >> 32]
+    return out.astype(np.int32)
+
+
 def bpr_negatives(users, seed, epoch, num_items, indptr, sorted_items, first_index=0):
     """Negatives for samples first_index .. first_index+len(users)-1 (int32 [N])."""
     users = np.asarray(users, dtype=np.int64)
     n = len(users)
-    idx = np.arange(first_index, first_index + n, dtype=np.uint64)
-    out = np.full(n, -1, dtype=np.int64)
-    last = np.zeros(n, dtype=np.int64)
-    pending = np.arange(n)
-    for attempt in range(BPR_MAX_ATTEMPTS):
-        if len(pending) == 0:
+    w0 = _bpr_draws(users, seed, epoch, first_index).astype(np.uint64)
+    indptr = np.asarray(indptr, dtype=np.int64)
+    items = np.asarray(sorted_items, dtype=np.int64)
+    base = indptr[users]
+    cnt = indptr[users + 1] - base
+    full = cnt >= num_items
+    r = ((w0 * (np.uint64(num_items) - np.minimum(cnt, num_items).astype(np.uint64))) >> np.uint64(32)).astype(np.int64)
+    # smallest t in [0, cnt] with t == cnt or a[t] - t > r  (a[t] - t is non-decreasing), all samples at once
+    lo = np.zeros(n, dtype=np.int64)
+    hi = cnt.copy()
+    while True:
+        act = lo < hi
+        if not act.any():
             break
-        ctr = np.stack([(idx[pending] & MASK), (idx[pending] >> np.uint64(32)),
-                        np.full(len(pending), attempt, dtype=np.uint64),
-                        np.full(len(pending), TAG_BPR, dtype=np.uint64)], axis=1).astype(np.uint32)
-        words = philox4x32_10(ctr, (seed, epoch))
-        for w in range(4):
-            if len(pending) == 0:
-                break
-            cand = _mulshift(words[:, w], num_items)
-            last[pending] = cand
-            hit = _is_positive(indptr, sorted_items, num_items, users[pending], cand)
-            acc = ~hit
-            out[pending[acc]] = cand[acc]
-            keep = hit
-            pending = pending[keep]
-            words = words[keep]
-    out[pending] = last[pending]
+        mid = (lo + hi) >> 1
+        probe = np.where(act, base + np.minimum(mid, np.maximum(cnt - 1, 0)), 0)
+        above = (items[probe] - mid > r) if len(items) else np.zeros(n, dtype=bool)
+        hi = np.where(act & above, mid, hi)
+        lo = np.where(act & ~above, mid + 1, lo)
+    out = r + lo
+    out[full] = ((w0[full] * np.uint64(num_items)) >> np.uint64(32)).astype(np.int64)
     return out.astype(np.int32)
 
 

@@ -220,9 +220,12 @@ def test_bpr_multi_step_cooperative_kernel_matches_oracle(dev):
     np.testing.assert_allclose(net2.user.w.cpu().numpy(), net.user.w.cpu().numpy(), rtol=1e-5, atol=1e-7)
 
 
-def test_bpr_host_fed_steps_match_oracle(dev):
-    """BPRNet.train_steps_from_host (pinned host ids -> H2D prefetch on a copy stream -> device Philox
-    negatives -> cooperative step kernel -> loss D2H) against the oracle with the oracle's sampler."""
+@pytest.mark.parametrize("path", ["copy", "copy_packed", "mapped"])
+def test_bpr_host_fed_steps_match_oracle(dev, path):
+    """BPRNet.train_steps_from_host (pinned host ids -> H2D on a copy stream through a ring of staging
+    slots -> cooperative step kernel drawing its own Philox negatives -> loss D2H) and the zero-copy
+    train_steps_mapped (one launch, ids pulled over PCIe by the kernel) against the oracle with the
+    oracle's sampler."""
     from binrec_b200.BPRModel import BPRNet
     U, I, d, B = 300, 200, 64, 256
     rng = np.random.default_rng(31)
@@ -233,9 +236,14 @@ def test_bpr_host_fed_steps_match_oracle(dev):
     net.set_training_pairs(u, p)
     orc = OB.BPROracle(U, I, d, seed=42)
     indptr, sitems = OP.build_csr(u, p, U)
-    order = [2, 0, 7, 3, 3, 1, len(u) // B]             # includes the ragged tail batch
+    order = [2, 0, 7, 3, 3, 1, len(u) // B, 5, 4, 6, 0, 1, 2, len(u) // B, 9, 8, 3, 7, 10]   # ragged tail batches; three chunks of the host-fed ring
     hu, hp = torch.from_numpy(u).pin_memory(), torch.from_numpy(p).pin_memory()
-    losses = net.train_steps_from_host(hu, hp, order, B, 7, 5)
+    if path == "copy":
+        losses = net.train_steps_from_host(hu, hp, order, B, 7, 5)
+    elif path == "copy_packed":
+        losses = net.train_steps_from_host(BPRNet.pack_host_batches(u, p, B), None, order, B, 7, 5)
+    else:
+        losses = net.train_steps_mapped(hu, hp, order, B, 7, 5)
     torch.cuda.synchronize()
     ref = []
     for b in order:

@@ -45,6 +45,29 @@ def test_bpr_negatives_never_positive_and_chunking_invariant():
     assert not np.array_equal(neg, P.bpr_negatives(pu, 7, 4, I, indptr, sitems))
 
 
+def test_bpr_negatives_vectorised_form_equals_the_definition():
+    U, I = 50, 40
+    pu, pi = _toy(U, I)
+    # user 3 interacts with everything, user 4 with nothing
+    keep = (pu != 3) & (pu != 4)
+    pu = np.concatenate([pu[keep], np.full(I, 3, dtype=np.int32)]); pi = np.concatenate([pi[keep], np.arange(I, dtype=np.int32)])
+    indptr, sitems = P.build_csr(pu, pi, U)
+    q = np.concatenate([pu, np.array([3, 4, 4, 3], dtype=np.int32)])
+    assert np.array_equal(P.bpr_negatives(q, 11, 2, I, indptr, sitems, first_index=5),
+                          P.bpr_negatives_scalar(q, 11, 2, I, indptr, sitems, first_index=5))
+
+
+def test_bpr_negatives_are_uniform_over_non_interacted_items():
+    # one user with positives {1, 2, 5} of 8 items: every non-interacted item must be reachable, roughly equally often
+    I = 8
+    pu = np.zeros(3, dtype=np.int32); pi = np.array([1, 2, 5], dtype=np.int32)
+    indptr, sitems = P.build_csr(pu, pi, 1)
+    neg = P.bpr_negatives(np.zeros(20000, dtype=np.int32), 3, 0, I, indptr, sitems)
+    vals, counts = np.unique(neg, return_counts=True)
+    assert vals.tolist() == [0, 3, 4, 6, 7]
+    assert counts.min() > 3600 and counts.max() < 4400
+
+
 def test_bpr_negatives_saturated_user_returns_last_candidate():
     U, I = 2, 3
     pu = np.array([0, 0, 0, 1], dtype=np.int32); pi = np.array([0, 1, 2, 0], dtype=np.int32)
