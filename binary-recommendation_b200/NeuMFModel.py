@@ -62,14 +62,10 @@ class NeuMFNet:
         # draw order = oracle/neumf.py: uMLP, iMLP, uMF, iMF, then the Dense kernels (glorot-uniform)
         self.uMLP, self.iMLP, self.uMF, self.iMF = emb(self.numUser), emb(self.numItem), emb(self.numUser), emb(self.numItem)
 
-        def glorot(i, o):
-            lim = np.sqrt(6.0 / (i + o))
-            return rng.uniform(-lim, lim, size=(i, o)).astype(np.float32)
-
-        parts = {"W1": glorot(2 * E, h1), "b1": np.zeros(h1, np.float32), "g1": np.ones(h1, np.float32),
-                 "be1": np.zeros(h1, np.float32), "W2": glorot(h1, h2), "b2": np.zeros(h2, np.float32),
-                 "g2": np.ones(h2, np.float32), "be2": np.zeros(h2, np.float32), "W3": glorot(h2, h3),
-                 "b3": np.zeros(h3, np.float32), "W4": glorot(h3 + 1, 1), "b4": np.zeros(1, np.float32)}
+        if lazy and (E, h1, h2, h3) == (10, 100, 50, 10):
+            raise ValueError("row-sparse Adam needs the touched-row marking of the tiled kernels (csrc/neumf2.cu); "
+                             "the (10;100,50,10) script spec runs on the first-generation kernels")
+        parts = self.initial_dense_parts(E, (h1, h2, h3), rng)
         flat = np.concatenate([parts[k].reshape(-1) for k in self.DENSE_ORDER])
         assert flat.size == n_dense
         self.dense = H.Table(torch.from_numpy(np.pad(flat, (0, npad - n_dense))).to(dev).view(1, -1), touched=False,
@@ -84,6 +80,25 @@ class NeuMFNet:
         self._ws_batch = 0
         self._ws = None
         self.history = {"loss": []}
+
+    @staticmethod
+    def initial_dense_parts(E, hidden, rng):
+        """Keras defaults: Dense glorot-uniform kernels / zero biases, BN gamma 1 / beta 0 (draw order W1..W4)."""
+        h1, h2, h3 = hidden
+
+        def glorot(i, o):
+            lim = np.sqrt(6.0 / (i + o))
+            return rng.uniform(-lim, lim, size=(i, o)).astype(np.float32)
+
+        return {"W1": glorot(2 * E, h1), "b1": np.zeros(h1, np.float32), "g1": np.ones(h1, np.float32),
+                "be1": np.zeros(h1, np.float32), "W2": glorot(h1, h2), "b2": np.zeros(h2, np.float32),
+                "g2": np.ones(h2, np.float32), "be2": np.zeros(h2, np.float32), "W3": glorot(h2, h3),
+                "b3": np.zeros(h3, np.float32), "W4": glorot(h3 + 1, 1), "b4": np.zeros(1, np.float32)}
+
+    @classmethod
+    def initial_dense(cls, E, hidden, rng):
+        parts = cls.initial_dense_parts(E, hidden, rng)
+        return np.concatenate([parts[k].reshape(-1) for k in cls.DENSE_ORDER])
 
     # ---- parameter views -------------------------------------------------------------------------
     def param(self, name, grad=False):

@@ -39,6 +39,18 @@ class brk_neumf_workspace(C.Structure):
                 ("acc", C.c_void_p)]
 
 
+BRK_MAX_PEERS = 8
+
+
+class brk_shards(C.Structure):
+    _fields_ = [("w", C.c_void_p * BRK_MAX_PEERS), ("g", C.c_void_p * BRK_MAX_PEERS),
+                ("touched", C.c_void_p * BRK_MAX_PEERS), ("world", C.c_int32), ("rank", C.c_int32)]
+
+
+class brk_neumf_shards(C.Structure):
+    _fields_ = [("uMLP", brk_shards), ("iMLP", brk_shards), ("uMF", brk_shards), ("iMF", brk_shards)]
+
+
 class brk_dp_peer(C.Structure):
     _fields_ = [("peer_w", C.c_void_p), ("peer_g", C.c_void_p), ("peer_flags", C.c_void_p), ("m", C.c_void_p),
                 ("v", C.c_void_p), ("local_sync", C.c_void_p), ("n", C.c_int64), ("rank", C.c_int32),
@@ -86,6 +98,9 @@ SIGNATURES = {
     "brk_neumf_acc_doubles": (C.c_int64, [_I32, _I32]),
     "brk_neumf_step": (C.c_int, [_P, C.POINTER(brk_neumf_model), _P, _P, _P, _I64, _I64, _I64, _I32, _U32, _U32,
                                  C.POINTER(brk_neumf_workspace), _P, _P, _P]),
+    "brk_neumf_step_sharded": (C.c_int, [_P, C.POINTER(brk_neumf_model), C.POINTER(brk_neumf_shards), _P, _P, _P, _I64,
+                                         _I64, _I64, _I32, _U32, _U32, C.POINTER(brk_neumf_workspace), _P, _P, _P]),
+    "brk_peer_barrier": (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
     "brk_dp_adam_peer": (C.c_int, [_P, C.POINTER(brk_dp_peer), brk_adam_hyper, _P, _P]),
     "brk_sgemm": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F32, _I32, _P]),
     "brk_tower_forward": (C.c_int, [_P, C.POINTER(brk_tower), _P, _I64, _P, _P, _P]),

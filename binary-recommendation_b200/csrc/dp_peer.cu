@@ -142,6 +142,21 @@ __global__ void __launch_bounds__(kThreads) dp_adam_peer_kernel(const DpParams P
     g_me[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// Stand-alone cross-GPU barrier (one CTA): rank r posts epoch e on every peer's flag block and waits
+// until every peer has posted e on its own.  Used between the sharded fused step (whose REDs land in the
+// peers' accumulators) and the owners' optimizer pass.
+__global__ void peer_barrier_kernel(uint32_t* const* peer_flags, uint32_t* local_sync, int rank, int world) {
+  const int t = threadIdx.x;
+  const uint32_t epoch = local_sync[0] + 1u;
+  __threadfence_system();
+  if (t < world) {
+    st_release_sys(peer_flags[t] + rank, epoch);
+    spin_until(peer_flags[rank] + t, epoch, true, local_sync + 1);
+  }
+  __syncthreads();
+  if (t == 0) local_sync[0] = epoch;
+}
+
 }  // namespace
 
 extern "C" int brk_dp_adam_peer(brk_ctx* ctx, const brk_dp_peer* d, brk_adam_hyper h, int64_t* state, void* stream) {
@@ -163,5 +178,15 @@ extern "C" int brk_dp_adam_peer(brk_ctx* ctx, const brk_dp_peer* d, brk_adam_hyp
   void* args[] = {(void*)&P};
   BRK_CUDA(cudaLaunchCooperativeKernel((void*)dp_adam_peer_kernel, dim3(grid), dim3(kThreads), args, 0,
                                        (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int brk_peer_barrier(brk_ctx* ctx, uint32_t* const* peer_flags, uint32_t* local_sync, int32_t rank,
+                                int32_t world, void* stream) {
+  BRK_REQUIRE(ctx && peer_flags && local_sync, BRK_E_ARG, "brk_peer_barrier: null argument");
+  BRK_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, BRK_E_ARG, "brk_peer_barrier: rank=%d world=%d",
+              rank, world);
+  peer_barrier_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(peer_flags, local_sync, rank, world);
+  BRK_LAUNCH_CHECK();
   return 0;
 }

@@ -694,10 +694,10 @@ int run_neumf(brk_ctx* ctx, const NeumfArgs& A, cudaStream_t st) {
 }  // namespace
 
 // second-generation kernels (neumf2.cu); returns 1 when the spec is not one of theirs
-int brk_neumf_step_v2(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, const int32_t* i, const float* y,
-                      int64_t batch, int64_t global_batch, int64_t first_index, int32_t training, uint32_t dropout_seed,
-                      uint32_t dropout_epoch, const brk_neumf_workspace* ws, float* out, float* loss_out,
-                      cudaStream_t st, int* rc_out);
+int brk_neumf_step_v2(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_shards* sh, const int32_t* u,
+                      const int32_t* i, const float* y, int64_t batch, int64_t global_batch, int64_t first_index,
+                      int32_t training, uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
+                      float* out, float* loss_out, cudaStream_t st, int* rc_out);
 
 extern "C" int64_t brk_neumf_dense_floats(int32_t E, int32_t H1, int32_t H2, int32_t H3) {
   return int64_t(2) * E * H1 + 3 * H1 + int64_t(H1) * H2 + 3 * H2 + int64_t(H2) * H3 + H3 + (H3 + 1) + 1;
@@ -718,8 +718,8 @@ extern "C" int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int3
   BRK_REQUIRE(ws->h1 && ws->h2 && ws->dy1 && ws->dy2 && ws->acc, BRK_E_ARG, "brk_neumf_step: workspace missing");
   if (getenv("BRK_NEUMF_V1") == nullptr) {
     int rc2 = 0;
-    if (brk_neumf_step_v2(ctx, m, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch, ws,
-                          out, loss_out, (cudaStream_t)stream, &rc2) == 0)
+    if (brk_neumf_step_v2(ctx, m, nullptr, u, i, y, batch, global_batch, first_index, training, dropout_seed,
+                          dropout_epoch, ws, out, loss_out, (cudaStream_t)stream, &rc2) == 0)
       return rc2;
   }
   NeumfArgs A;
@@ -743,5 +743,36 @@ extern "C" int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int3
 #undef BRK_NEUMF_CASE
   brk_set_error("brk_neumf_step: no kernel instance for E=%d H=(%d,%d,%d); built: (32;32,16,8) (64;64,32,16) "
                 "(16;16,8,4) (8;8,4,2) (10;100,50,10)", m->E, m->H1, m->H2, m->H3);
+  return BRK_E_ARG;
+}
+
+// Row-sharded tables over NVLink peer memory (BASELINE.json configs[3]): the four
+// tables' rows live on rank (row % world) at local row (row / world); `m` describes THIS rank's shards (for
+// the optimizer), `sh` every rank's shard pointers.  The gathers read peer rows directly and the gradient
+// scatter-adds are REDs into the owner's accumulator, so there is no separate exchange step.
+extern "C" int brk_neumf_step_sharded(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_shards* sh,
+                                      const int32_t* u, const int32_t* i, const float* y, int64_t batch,
+                                      int64_t global_batch, int64_t first_index, int32_t training, uint32_t dropout_seed,
+                                      uint32_t dropout_epoch, const brk_neumf_workspace* ws, float* out, float* loss_out,
+                                      void* stream) {
+  BRK_REQUIRE(ctx && m && sh && u && i && ws && out, BRK_E_ARG, "brk_neumf_step_sharded: null argument");
+  BRK_REQUIRE(y || !training, BRK_E_ARG, "brk_neumf_step_sharded: labels are required for training");
+  BRK_REQUIRE(batch > 0, BRK_E_ARG, "brk_neumf_step_sharded: batch=%lld", (long long)batch);
+  BRK_REQUIRE(m->dense.w && m->bn_moving && (!training || m->dense.g), BRK_E_ARG, "brk_neumf_step_sharded: dense block missing");
+  BRK_REQUIRE(ws->h1 && ws->h2 && ws->dy1 && ws->dy2 && ws->acc, BRK_E_ARG, "brk_neumf_step_sharded: workspace missing");
+  const brk_shards* all[4] = {&sh->uMLP, &sh->iMLP, &sh->uMF, &sh->iMF};
+  for (int k = 0; k < 4; ++k) {
+    BRK_REQUIRE(all[k]->world >= 1 && all[k]->world <= BRK_MAX_PEERS && all[k]->world == all[0]->world, BRK_E_ARG,
+                "brk_neumf_step_sharded: world=%d (max %d, equal for all tables)", all[k]->world, BRK_MAX_PEERS);
+    for (int p = 0; p < all[k]->world; ++p)
+      BRK_REQUIRE(all[k]->w[p] && (!training || all[k]->g[p]) && brk_aligned16(all[k]->w[p]) && brk_aligned16(all[k]->g[p]),
+                  BRK_E_ARG, "brk_neumf_step_sharded: shard %d of table %d missing or not 16-byte aligned", p, k);
+  }
+  int rc2 = 0;
+  if (brk_neumf_step_v2(ctx, m, sh, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch, ws,
+                        out, loss_out, (cudaStream_t)stream, &rc2) == 0)
+    return rc2;
+  brk_set_error("brk_neumf_step_sharded: no sharded kernel instance for E=%d H=(%d,%d,%d); built: (32;32,16,8) "
+                "(64;64,32,16) (16;16,8,4) (8;8,4,2)", m->E, m->H1, m->H2, m->H3);
   return BRK_E_ARG;
 }

@@ -37,8 +37,34 @@ struct Acc {
   static constexpr int loss = e1 + H1, total = loss + 1;
 };
 
+// A table as the kernels address it: one shard per rank, row r on rank r % world at local row r / world
+// (world == 1: the table itself).  Shard pointers of other ranks are NVLink peer mappings: rows are read
+// with ordinary loads and gradients leave as REDs straight into the owner's accumulator -- the row
+// "all-to-all" of a sharded lookup and of its gradient happen inside the gather / scatter instructions.
+struct TabRef {
+  const float* w[BRK_MAX_PEERS];
+  float* g[BRK_MAX_PEERS];
+  uint32_t* t[BRK_MAX_PEERS];
+  int32_t world;
+};
+struct RowRef { const float* w; float* g; uint32_t* t; int64_t lrow; };
+template <int E>
+__device__ __forceinline__ RowRef locate(const TabRef& T, int64_t row) {
+  int o = 0; int64_t l = row;
+  if (T.world > 1) { o = int(row % T.world); l = row / T.world; }
+  RowRef r; r.w = T.w[o] + l * E; r.g = T.g[o] ? T.g[o] + l * E : nullptr; r.t = T.t[o]; r.lrow = l;
+  return r;
+}
+__device__ __forceinline__ void mark_row(const RowRef& r) {
+  if (r.t) {
+    const uint32_t bit = 1u << (r.lrow & 31);
+    if (!(*(volatile const uint32_t*)(r.t + (r.lrow >> 5)) & bit)) atomicOr(r.t + (r.lrow >> 5), bit);
+  }
+}
+
 struct Args {
-  brk_table uMLP, iMLP, uMF, iMF, dense;
+  TabRef uMLP, iMLP, uMF, iMF;
+  brk_table dense;
   const int32_t* u; const int32_t* i; const float* y;
   int64_t B, first_index, global_B;
   float *h1, *h2, *dy1, *dy2, *out;
@@ -140,10 +166,10 @@ __device__ __forceinline__ void drop_col(float* T, int s, uint64_t idx, int laye
 // Thread-per-row gather of embedding rows into a feature-major tile: thread (s = t % TS) reads its row as
 // float4 and writes T[col0 + 4c + q][s]; lanes hold consecutive samples -> conflict-free stores.
 template <int E>
-__device__ __forceinline__ void gather_col(float* T, int col0, const float* __restrict__ table, int64_t row, int s, bool valid) {
+__device__ __forceinline__ void gather_col(float* T, int col0, const float* __restrict__ rowp, int s, bool valid) {
 #pragma unroll 4
   for (int c = 0; c < E / 4; ++c) {
-    const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(table + row * E) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(rowp) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     T[(col0 + 4 * c + 0) * PT + s] = v.x; T[(col0 + 4 * c + 1) * PT + s] = v.y;
     T[(col0 + 4 * c + 2) * PT + s] = v.z; T[(col0 + 4 * c + 3) * PT + s] = v.w;
   }
@@ -306,8 +332,8 @@ __global__ void __launch_bounds__(NT) fwd1(const Args A) {
   copy_to_smem<2 * E * H1>(Ws, A.dense.w + L::W1);
   copy_to_smem<H1>(bs, A.dense.w + L::b1);
   const bool ok = s < valid;
-  if (t < TS) gather_col<E>(Xs, 0, A.uMLP.w, ok ? int64_t(__ldg(A.u + b0 + s)) : 0, s, ok);
-  else        gather_col<E>(Xs, E, A.iMLP.w, ok ? int64_t(__ldg(A.i + b0 + s)) : 0, s, ok);
+  if (t < TS) gather_col<E>(Xs, 0, locate<E>(A.uMLP, ok ? int64_t(__ldg(A.u + b0 + s)) : 0).w, s, ok);
+  else        gather_col<E>(Xs, E, locate<E>(A.iMLP, ok ? int64_t(__ldg(A.i + b0 + s)) : 0).w, s, ok);
   __syncthreads();
   if (A.dropout && t < TS && ok) drop_col<2 * E>(Xs, s, uint64_t(A.first_index + b0 + s), 0, A.drop_seed, A.drop_epoch);
   if (A.dropout) __syncthreads();
@@ -374,14 +400,15 @@ __global__ void __launch_bounds__(NT) head(const Args A) {
   bn_prepare<H2>(mean, rstd, A.acc + AC::s2, A.acc + AC::q2, A.bn_moving + 2 * H1, A.bn_moving + 2 * H1 + H2, A.B, A.training);
   load_tile<H2>(Xs, A.h2, A.B, b0, valid);
   // MF dot product: thread-per-sample straight from the tables (threads TS..2TS-1; rows stay in L1 for the backward)
-  int64_t ru = 0, ri = 0;
+  RowRef ru, ri;
+  ru.w = ri.w = nullptr; ru.g = ri.g = nullptr; ru.t = ri.t = nullptr; ru.lrow = ri.lrow = 0;
   if (t >= TS && t - TS < valid) {
-    ru = __ldg(A.u + b0 + t - TS); ri = __ldg(A.i + b0 + t - TS);
+    ru = locate<E>(A.uMF, __ldg(A.u + b0 + t - TS)); ri = locate<E>(A.iMF, __ldg(A.i + b0 + t - TS));
     float mf = 0.f;
 #pragma unroll 4
     for (int c = 0; c < E / 4; ++c) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(A.uMF.w + ru * E) + c);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(A.iMF.w + ri * E) + c);
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ru.w) + c);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ri.w) + c);
       mf = fmaf(a.x, b.x, mf); mf = fmaf(a.y, b.y, mf); mf = fmaf(a.z, b.z, mf); mf = fmaf(a.w, b.w, mf);
     }
     mfs[t - TS] = mf;
@@ -444,14 +471,15 @@ __global__ void __launch_bounds__(NT) head(const Args A) {
   // MF embedding gradients (thread-per-sample, rows re-read through L1)
   if (t >= TS && t - TS < valid) {
     const float dmf = dl[t - TS] * w4[H3];
-    float* gu = A.uMF.g + ru * E; float* gi = A.iMF.g + ri * E;
+    float* gu = ru.g; float* gi = ri.g;
 #pragma unroll 4
     for (int c = 0; c < E / 4; ++c) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(A.uMF.w + ru * E) + c);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(A.iMF.w + ri * E) + c);
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ru.w) + c);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ri.w) + c);
       red_add_f4(gu + 4 * c, make_float4(dmf * b.x, dmf * b.y, dmf * b.z, dmf * b.w));
       red_add_f4(gi + 4 * c, make_float4(dmf * a.x, dmf * a.y, dmf * a.z, dmf * a.w));
     }
+    mark_row(ru); mark_row(ri);
   }
   __syncthreads();                                          // wgrad has consumed Xs
   layer_dgrad<H2, H3>(Zt, Ws, Xs);                          // Xs <- dd2 [H2][PT]
@@ -558,9 +586,8 @@ __global__ void __launch_bounds__(NT) bwd1(const Args A, unsigned int* ticket) {
     }
   }
   const bool ok = s < valid;
-  const int64_t row = ok ? int64_t(__ldg((t < TS ? A.u : A.i) + b0 + s)) : 0;
-  if (t < TS) gather_col<E>(Xs, 0, A.uMLP.w, row, s, ok);
-  else        gather_col<E>(Xs, E, A.iMLP.w, row, s, ok);
+  const RowRef rr = locate<E>(t < TS ? A.uMLP : A.iMLP, ok ? int64_t(__ldg((t < TS ? A.u : A.i) + b0 + s)) : 0);
+  gather_col<E>(Xs, t < TS ? 0 : E, rr.w, s, ok);
   __syncthreads();
   bn_backward_dz<H1, ACT>(Zf, Zt, A.h1, A.dy1, mean1, rstd1, gam1, sdy, sdyx, A.B, b0, valid);
   if (A.dropout && t < TS && ok) drop_col<2 * E>(Xs, s, uint64_t(A.first_index + b0 + s), 0, A.drop_seed, A.drop_epoch);
@@ -573,12 +600,13 @@ __global__ void __launch_bounds__(NT) bwd1(const Args A, unsigned int* ticket) {
   __syncthreads();
   // MLP embedding gradients: threads 0..63 scatter the user half, 64..127 the item half (16-byte REDs)
   if (ok) {
-    float* g = (t < TS ? A.uMLP.g : A.iMLP.g) + row * E;
+    float* g = rr.g;
     const int c0 = t < TS ? 0 : E;
 #pragma unroll 4
     for (int c = 0; c < E; c += 4)
       red_add_f4(g + c, make_float4(Xs[(c0 + c) * PT + s], Xs[(c0 + c + 1) * PT + s], Xs[(c0 + c + 2) * PT + s],
                                     Xs[(c0 + c + 3) * PT + s]));
+    mark_row(rr);
   }
   // last CTA: BN moving statistics, loss output, accumulator reset
   __syncthreads();
@@ -649,12 +677,24 @@ int run(brk_ctx* ctx, const Args& A, cudaStream_t st) {
 }  // namespace v2
 
 // Returns 0 when the spec was handled, 1 when it is not a v2 spec (caller falls through to neumf.cu).
-int brk_neumf_step_v2(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, const int32_t* i, const float* y,
-                      int64_t batch, int64_t global_batch, int64_t first_index, int32_t training, uint32_t dropout_seed,
-                      uint32_t dropout_epoch, const brk_neumf_workspace* ws, float* out, float* loss_out,
-                      cudaStream_t st, int* rc_out) {
+static void tab_ref(v2::TabRef& T, const brk_table& local, const brk_shards* sh) {
+  for (int p = 0; p < BRK_MAX_PEERS; ++p) { T.w[p] = nullptr; T.g[p] = nullptr; T.t[p] = nullptr; }
+  if (sh && sh->world > 1) {
+    T.world = sh->world;
+    for (int p = 0; p < sh->world; ++p) { T.w[p] = sh->w[p]; T.g[p] = sh->g[p]; T.t[p] = sh->touched[p]; }
+  } else {
+    T.world = 1; T.w[0] = local.w; T.g[0] = local.g; T.t[0] = local.touched;
+  }
+}
+
+int brk_neumf_step_v2(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_shards* sh, const int32_t* u,
+                      const int32_t* i, const float* y, int64_t batch, int64_t global_batch, int64_t first_index,
+                      int32_t training, uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
+                      float* out, float* loss_out, cudaStream_t st, int* rc_out) {
   v2::Args A;
-  A.uMLP = m->uMLP; A.iMLP = m->iMLP; A.uMF = m->uMF; A.iMF = m->iMF; A.dense = m->dense;
+  tab_ref(A.uMLP, m->uMLP, sh ? &sh->uMLP : nullptr); tab_ref(A.iMLP, m->iMLP, sh ? &sh->iMLP : nullptr);
+  tab_ref(A.uMF, m->uMF, sh ? &sh->uMF : nullptr); tab_ref(A.iMF, m->iMF, sh ? &sh->iMF : nullptr);
+  A.dense = m->dense;
   A.u = u; A.i = i; A.y = y ? y : out; A.B = batch; A.first_index = first_index;
   A.global_B = global_batch > 0 ? global_batch : batch;
   A.h1 = ws->h1; A.h2 = ws->h2; A.dy1 = ws->dy1; A.dy2 = ws->dy2; A.out = out; A.acc = ws->acc;

@@ -209,6 +209,37 @@ int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, con
                    uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
                    float* out, float* loss_out, void* stream);
 
+/* ---- row-sharded tables over NVLink peer memory ----------------------------------------------------
+ * Stands in for the embedding lookups and their IndexedSlices gradients (NeuMFModel.py:58-63) when the
+ * tables are too large to mirror on every worker as MultiWorkerMirroredStrategy does (RModel.py:119-121):
+ * row r of a table lives on rank r % world at local row r / world.  w / g / touched hold every rank's
+ * shard pointer (this rank's own and the NVLink peer mappings of the others).  The fused kernels read
+ * peer rows with ordinary loads and send row gradients as REDs into the owner's accumulator (touched
+ * bits likewise), i.e. the all-to-all of looked-up rows and of their gradients is carried by the gather
+ * and scatter instructions themselves.  brk_neumf_step_sharded: as brk_neumf_step; m's tables describe
+ * THIS rank's shards.  After it, every rank must pass brk_peer_barrier before an owner applies its
+ * optimizer to its shard, and again (or through brk_dp_adam_peer's own barriers) before the next step
+ * reads the updated rows. */
+#define BRK_MAX_PEERS 8
+typedef struct brk_shards {
+  float*    w[BRK_MAX_PEERS];
+  float*    g[BRK_MAX_PEERS];
+  uint32_t* touched[BRK_MAX_PEERS];
+  int32_t   world, rank;
+} brk_shards;
+typedef struct brk_neumf_shards { brk_shards uMLP, iMLP, uMF, iMF; } brk_neumf_shards;
+int brk_neumf_step_sharded(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_shards* sh,
+                           const int32_t* u, const int32_t* i, const float* y, int64_t batch,
+                           int64_t global_batch, int64_t first_index, int32_t training, uint32_t dropout_seed,
+                           uint32_t dropout_epoch, const brk_neumf_workspace* ws, float* out, float* loss_out,
+                           void* stream);
+/* Cross-GPU barrier on `stream`: returns (in stream order) once every rank's earlier work on its stream
+ * has completed.  peer_flags: DEVICE array of `world` pointers to each rank's flag block (world uint32,
+ * zero-initialised, peer-mapped); local_sync: 4 uint32 zero-initialised ([0] epoch, [1] error: a peer did
+ * not arrive within ~3 s). */
+int brk_peer_barrier(brk_ctx* ctx, uint32_t* const* peer_flags, uint32_t* local_sync, int32_t rank,
+                     int32_t world, void* stream);
+
 /* ---- data-parallel optimizer over NVLink peer memory ----------------------------------------------
  * Stands in for the per-step gradient all-reduce of MultiWorkerMirroredStrategy
  * (src/models/RModel.py:119-121) + Adam (NeuMFModel.py:89, BPRModel.py:70) when one process drives
