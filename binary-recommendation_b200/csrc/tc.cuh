@@ -75,6 +75,40 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
   d |= uint64_t(2) << 61;            // SWIZZLE_128B
   return d;
 }
+// General shared-memory matrix descriptor, SWIZZLE_128B atoms (8 rows x 128 B, 1024-byte aligned):
+//   K-major operand  (rows = M/N index, 128 B = the K extent of one K-block): LBO unused, SBO = 1024;
+//   MN-major operand (rows = K index, 128 B = 32 fp32 / 64 bf16 along M/N):   LBO = distance between
+//     128-byte column blocks along M/N, SBO = distance between 8-row groups along K.
+__device__ __forceinline__ uint64_t smem_desc_sw128_ex(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3FFFu);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= uint64_t((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= uint64_t(1) << 46;            // descriptor version (Blackwell)
+  d |= uint64_t(2) << 61;            // SWIZZLE_128B
+  return d;
+}
+// MN-major TF32 operands only exist in the "128B swizzle, 32-byte base" form (layout type 1): rows = K index,
+// 128 B = 32 fp32 along M/N, atoms of 4 rows (512 B), the 32-byte chunk index XORed with (row & 3).
+__device__ __forceinline__ uint64_t smem_desc_sw128_base32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3FFFu);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= uint64_t((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= uint64_t(1) << 46;            // descriptor version (Blackwell)
+  d |= uint64_t(1) << 61;            // SWIZZLE_128B_BASE32B
+  return d;
+}
+// kind::tf32 instruction descriptor: D = F32, A = B = TF32 (fp32 bits in shared memory, 10-bit mantissa used);
+// a_mn / b_mn = 1 selects the MN-major (transposed) view of that operand.
+__host__ __device__ constexpr uint32_t idesc_tf32_f32(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(a_mn) << 15) | (uint32_t(b_mn) << 16) |
+         (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+// Generic-proxy shared-memory writes (st.shared) must be made visible to the async proxy that
+// tcgen05.mma reads operands through.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M x N tile.
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
@@ -88,6 +122,15 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uin
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // Arrives on the mbarrier when all previously issued tcgen05.mma of this thread have completed

@@ -209,6 +209,13 @@ int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, con
                    uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
                    float* out, float* loss_out, void* stream);
 
+/* Test hook for the tcgen05 building blocks of the NeuMF tensor-core path (csrc/neumf_tc.cu): stages A
+ * [a_rows, a_cols] and B [b_rows, b_cols] (row-major fp32; cols multiples of 32, rows multiples of 8) as
+ * 128-byte-swizzled tiles and computes D = A B^T (mode bit0/bit1 = 0: K-major operand, rows = M / N) or
+ * with the operand read transposed (bit set: rows = K); out [128, N] receives TMEM lanes 0..127. */
+int brk_tc_selftest(brk_ctx* ctx, int32_t M, int32_t N, int32_t K, int32_t mode, const float* A, int32_t a_rows,
+                    int32_t a_cols, const float* B, int32_t b_rows, int32_t b_cols, float* out, void* stream);
+
 /* ---- row-sharded tables over NVLink peer memory ----------------------------------------------------
  * Stands in for the embedding lookups and their IndexedSlices gradients (NeuMFModel.py:58-63) when the
  * tables are too large to mirror on every worker as MultiWorkerMirroredStrategy does (RModel.py:119-121):
