@@ -26,6 +26,7 @@ from . import hotpath as H
 from . import synth
 from .RModel import RModel
 
+TC_SPECS = {(64, 64, 32, 16), (32, 32, 16, 8)}
 BUILT_SPECS = {(32, 32, 16, 8), (64, 64, 32, 16), (16, 16, 8, 4), (8, 8, 4, 2), (10, 100, 50, 10)}
 
 
@@ -35,13 +36,18 @@ class NeuMFNet:
     DENSE_ORDER = ("W1", "b1", "g1", "be1", "W2", "b2", "g2", "be2", "W3", "b3", "W4", "b4")
 
     def __init__(self, numUser, numItem, numFactor, hidden=None, act="relu", loss="mse", learning_rate=1e-3,
-                 dropout=0.2, seed=42, dropout_seed=11, sparse_adam="keras", device=None, head_order="h3_mf"):
+                 dropout=0.2, seed=42, dropout_seed=11, sparse_adam="keras", device=None, head_order="h3_mf",
+                 tensor_cores=False):
         self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
         E = int(numFactor)
         h1, h2, h3 = hidden or (E, E // 2, E // 4)
         if (E, h1, h2, h3) not in BUILT_SPECS:
             raise ValueError(f"no kernel instance for E={E}, hidden={(h1, h2, h3)}; built: {sorted(BUILT_SPECS)}")
         self.E, self.hidden = E, (h1, h2, h3)
+        # tensor_cores: the Dense products run on tcgen05 with TF32 operands (csrc/neumf_tc.cu); fp32 otherwise
+        if tensor_cores and (E, h1, h2, h3) not in TC_SPECS:
+            raise ValueError(f"no tensor-core instance for E={E}, hidden={(h1, h2, h3)}; built: {sorted(TC_SPECS)}")
+        self.tensor_cores = bool(tensor_cores)
         self.numUser, self.numItem = int(numUser), int(numItem)
         self.act, self.loss, self.dropout = act, loss, float(dropout)
         self.dropout_seed = dropout_seed
@@ -114,7 +120,7 @@ class NeuMFNet:
         return N.brk_neumf_model(self.uMLP.c_struct(), self.iMLP.c_struct(), self.uMF.c_struct(), self.iMF.c_struct(),
                                  self.dense.c_struct(), self.bn_moving.data_ptr(), self.E, h1, h2, h3,
                                  0 if self.act == "relu" else 1, 0 if self.loss == "mse" else 1,
-                                 1 if self.dropout > 0 else 0, 0)
+                                 1 if self.dropout > 0 else 0, 1 if self.tensor_cores else 0)
 
     def _workspace(self, batch):
         if batch > self._ws_batch:

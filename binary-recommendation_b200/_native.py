@@ -31,7 +31,7 @@ class brk_neumf_model(C.Structure):
     _fields_ = [("uMLP", brk_table), ("iMLP", brk_table), ("uMF", brk_table), ("iMF", brk_table),
                 ("dense", brk_table), ("bn_moving", C.c_void_p), ("E", C.c_int32), ("H1", C.c_int32),
                 ("H2", C.c_int32), ("H3", C.c_int32), ("act", C.c_int32), ("loss", C.c_int32),
-                ("dropout", C.c_int32), ("_pad", C.c_int32)]
+                ("dropout", C.c_int32), ("tensor_cores", C.c_int32)]
 
 
 class brk_neumf_workspace(C.Structure):

@@ -10,7 +10,7 @@ objs=""
 pids=""
 for f in *.cu; do
   o=build/${f%.cu}.o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ../../include/brk_b200.h -nt "$o" ] || { [ -f tc.cuh ] && [ tc.cuh -nt "$o" ]; }; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ../../include/brk_b200.h -nt "$o" ] || { [ -f tc.cuh ] && [ tc.cuh -nt "$o" ]; } || [ neumf_common.cuh -nt "$o" ]; then
     $NVCC $FLAGS ${BRK_PTXAS_V:+-Xptxas -v} -c "$f" -o "$o" &
     pids="$pids $!"
   fi

@@ -16,6 +16,9 @@ struct brk_ctx {
   cudaStream_t  copy_stream;
   cudaEvent_t   ev_ready[4], ev_done[4];
   int           copy_ready;
+  // NeuMF tensor-core path: swizzled weight images, rebuilt every step (csrc/neumf_tc.cu)
+  float*        neumf_img;
+  size_t        neumf_img_floats;
 };
 
 #define BRK_STAGE_EVENTS 4

@@ -48,6 +48,7 @@ extern "C" int brk_destroy(brk_ctx* c) {
   if (c->loss_acc) cudaFree(c->loss_acc);
   if (c->tickets) cudaFree(c->tickets);
   if (c->scratch) cudaFree(c->scratch);
+  if (c->neumf_img) cudaFree(c->neumf_img);
   if (c->copy_ready) {
     cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < BRK_STAGE_EVENTS; ++i) { cudaEventDestroy(c->ev_ready[i]); cudaEventDestroy(c->ev_done[i]); }

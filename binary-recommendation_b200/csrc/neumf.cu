@@ -699,6 +699,11 @@ int brk_neumf_step_v2(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_sh
                       int32_t training, uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
                       float* out, float* loss_out, cudaStream_t st, int* rc_out);
 
+int brk_neumf_step_tc(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_shards* sh, const int32_t* u,
+                      const int32_t* i, const float* y, int64_t batch, int64_t global_batch, int64_t first_index,
+                      int32_t training, uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
+                      float* out, float* loss_out, cudaStream_t st, int* rc_out);
+
 extern "C" int64_t brk_neumf_dense_floats(int32_t E, int32_t H1, int32_t H2, int32_t H3) {
   return int64_t(2) * E * H1 + 3 * H1 + int64_t(H1) * H2 + 3 * H2 + int64_t(H2) * H3 + H3 + (H3 + 1) + 1;
 }
@@ -716,6 +721,15 @@ extern "C" int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int3
   BRK_REQUIRE(!training || (m->uMLP.g && m->iMLP.g && m->uMF.g && m->iMF.g && m->dense.g), BRK_E_ARG,
               "brk_neumf_step: gradient accumulators missing");
   BRK_REQUIRE(ws->h1 && ws->h2 && ws->dy1 && ws->dy2 && ws->acc, BRK_E_ARG, "brk_neumf_step: workspace missing");
+  if (m->tensor_cores) {
+    int rc2 = 0;
+    if (brk_neumf_step_tc(ctx, m, nullptr, u, i, y, batch, global_batch, first_index, training, dropout_seed,
+                          dropout_epoch, ws, out, loss_out, (cudaStream_t)stream, &rc2) == 0)
+      return rc2;
+    brk_set_error("brk_neumf_step: no tensor-core instance for E=%d H=(%d,%d,%d); built: (64;64,32,16) (32;32,16,8)",
+                  m->E, m->H1, m->H2, m->H3);
+    return BRK_E_ARG;
+  }
   if (getenv("BRK_NEUMF_V1") == nullptr) {
     int rc2 = 0;
     if (brk_neumf_step_v2(ctx, m, nullptr, u, i, y, batch, global_batch, first_index, training, dropout_seed,
@@ -769,6 +783,13 @@ extern "C" int brk_neumf_step_sharded(brk_ctx* ctx, const brk_neumf_model* m, co
                   BRK_E_ARG, "brk_neumf_step_sharded: shard %d of table %d missing or not 16-byte aligned", p, k);
   }
   int rc2 = 0;
+  if (m->tensor_cores) {
+    if (brk_neumf_step_tc(ctx, m, sh, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch, ws,
+                          out, loss_out, (cudaStream_t)stream, &rc2) == 0)
+      return rc2;
+    brk_set_error("brk_neumf_step_sharded: no tensor-core instance for E=%d H=(%d,%d,%d)", m->E, m->H1, m->H2, m->H3);
+    return BRK_E_ARG;
+  }
   if (brk_neumf_step_v2(ctx, m, sh, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch, ws,
                         out, loss_out, (cudaStream_t)stream, &rc2) == 0)
     return rc2;

@@ -12,76 +12,13 @@
 //     [in][out] weight layout serves all three products, no transposed weight copy;
 //   * thread-per-sample work only where it is natural: row gathers, Philox dropout masks, loss.
 // Supported specs: 2E, H1, H2, H3 powers of two (E >= 8, H3 >= 2); anything else takes neumf.cu.
-#include "common.cuh"
-#include <math_constants.h>
+#include "neumf_common.cuh"
 
 namespace v2 {
 
 constexpr int TS = 64;                // samples per CTA
 constexpr int PT = TS + 4;            // tile pitch (floats): keeps float4 alignment, staggers banks
 constexpr int NT = 128;               // threads per CTA
-constexpr float kBnEps = 1e-3f, kBnMomentum = 0.99f;
-constexpr uint32_t kDropThreshold = 51;
-constexpr float kDropScale = 256.0f / 205.0f;
-
-template <int E, int H1, int H2, int H3>
-struct Layout {
-  static constexpr int W1 = 0, b1 = W1 + 2 * E * H1, g1 = b1 + H1, be1 = g1 + H1;
-  static constexpr int W2 = be1 + H1, b2 = W2 + H1 * H2, g2 = b2 + H2, be2 = g2 + H2;
-  static constexpr int W3 = be2 + H2, b3 = W3 + H2 * H3, W4 = b3 + H3;
-};
-template <int H1, int H2>
-struct Acc {
-  static constexpr int s1 = 0, q1 = s1 + H1, s2 = q1 + H1, q2 = s2 + H2;
-  static constexpr int d2 = q2 + H2, e2 = d2 + H2, d1 = e2 + H2, e1 = d1 + H1;
-  static constexpr int loss = e1 + H1, total = loss + 1;
-};
-
-// A table as the kernels address it: one shard per rank, row r on rank r % world at local row r / world
-// (world == 1: the table itself).  Shard pointers of other ranks are NVLink peer mappings: rows are read
-// with ordinary loads and gradients leave as REDs straight into the owner's accumulator -- the row
-// "all-to-all" of a sharded lookup and of its gradient happen inside the gather / scatter instructions.
-struct TabRef {
-  const float* w[BRK_MAX_PEERS];
-  float* g[BRK_MAX_PEERS];
-  uint32_t* t[BRK_MAX_PEERS];
-  int32_t world;
-};
-struct RowRef { const float* w; float* g; uint32_t* t; int64_t lrow; };
-template <int E>
-__device__ __forceinline__ RowRef locate(const TabRef& T, int64_t row) {
-  int o = 0; int64_t l = row;
-  if (T.world > 1) { o = int(row % T.world); l = row / T.world; }
-  RowRef r; r.w = T.w[o] + l * E; r.g = T.g[o] ? T.g[o] + l * E : nullptr; r.t = T.t[o]; r.lrow = l;
-  return r;
-}
-__device__ __forceinline__ void mark_row(const RowRef& r) {
-  if (r.t) {
-    const uint32_t bit = 1u << (r.lrow & 31);
-    if (!(*(volatile const uint32_t*)(r.t + (r.lrow >> 5)) & bit)) atomicOr(r.t + (r.lrow >> 5), bit);
-  }
-}
-
-struct Args {
-  TabRef uMLP, iMLP, uMF, iMF;
-  brk_table dense;
-  const int32_t* u; const int32_t* i; const float* y;
-  int64_t B, first_index, global_B;
-  float *h1, *h2, *dy1, *dy2, *out;
-  double* acc;
-  float* bn_moving;
-  float* loss_out;
-  uint32_t drop_seed, drop_epoch;
-  int32_t dropout, loss_kind, training;
-};
-
-template <int ACT> __device__ __forceinline__ float act_f(float x) {
-  return ACT == 0 ? fmaxf(x, 0.f) : 1.0f / (1.0f + expf(-x));
-}
-template <int ACT> __device__ __forceinline__ float act_grad(float h) {
-  return ACT == 0 ? (h > 0.f ? 1.f : 0.f) : h * (1.f - h);
-}
-
 // per-thread tile shape for a [TS x OUT] output on NT threads: RM x RN = OUT / 2 elements
 template <int OUT> struct Tile {
   static constexpr int RN = OUT >= 64 ? 8 : OUT >= 16 ? 4 : OUT >= 8 ? 2 : OUT >= 4 ? 2 : 1;
@@ -143,14 +80,6 @@ __device__ __forceinline__ void gemm_inner(const float* A, int lda, const float*
   }
 }
 
-__device__ __forceinline__ void drop16(uint64_t idx, int c, int layer, uint32_t seed, uint32_t epoch, float (&m)[16]) {
-  const uint4 w = philox4x32_10(make_uint4(uint32_t(idx), uint32_t(idx >> 32), uint32_t(c), 0xD0u + layer), seed, epoch);
-  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) m[q * 4 + b] = ((ww[q] >> (8 * b)) & 0xFFu) >= kDropThreshold ? kDropScale : 0.f;
-}
 // Dropout in place on column s of a feature-major tile (thread-per-sample).
 template <int N>
 __device__ __forceinline__ void drop_col(float* T, int s, uint64_t idx, int layer, uint32_t seed, uint32_t epoch) {
@@ -687,11 +616,10 @@ static void tab_ref(v2::TabRef& T, const brk_table& local, const brk_shards* sh)
   }
 }
 
-int brk_neumf_step_v2(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_shards* sh, const int32_t* u,
-                      const int32_t* i, const float* y, int64_t batch, int64_t global_batch, int64_t first_index,
-                      int32_t training, uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
-                      float* out, float* loss_out, cudaStream_t st, int* rc_out) {
-  v2::Args A;
+void brk_neumf_fill_args(v2::Args& A, const brk_neumf_model* m, const brk_neumf_shards* sh, const int32_t* u,
+                         const int32_t* i, const float* y, int64_t batch, int64_t global_batch, int64_t first_index,
+                         int32_t training, uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
+                         float* out, float* loss_out) {
   tab_ref(A.uMLP, m->uMLP, sh ? &sh->uMLP : nullptr); tab_ref(A.iMLP, m->iMLP, sh ? &sh->iMLP : nullptr);
   tab_ref(A.uMF, m->uMF, sh ? &sh->uMF : nullptr); tab_ref(A.iMF, m->iMF, sh ? &sh->iMF : nullptr);
   A.dense = m->dense;
@@ -702,6 +630,14 @@ int brk_neumf_step_v2(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_sh
   A.drop_seed = dropout_seed; A.drop_epoch = dropout_epoch;
   A.dropout = (m->dropout != 0 && training) ? 1 : 0;
   A.loss_kind = m->loss; A.training = training;
+}
+
+int brk_neumf_step_v2(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_shards* sh, const int32_t* u,
+                      const int32_t* i, const float* y, int64_t batch, int64_t global_batch, int64_t first_index,
+                      int32_t training, uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
+                      float* out, float* loss_out, cudaStream_t st, int* rc_out) {
+  v2::Args A;
+  brk_neumf_fill_args(A, m, sh, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch, ws, out, loss_out);
 #define BRK_V2_CASE(E_, A_, B_, C_)                                                                      \
   if (m->E == E_ && m->H1 == A_ && m->H2 == B_ && m->H3 == C_) {                                          \
     *rc_out = m->act == 0 ? v2::run<E_, A_, B_, C_, 0>(ctx, A, st) : v2::run<E_, A_, B_, C_, 1>(ctx, A, st); \

@@ -113,10 +113,11 @@ class ShardedNeuMFNet:
     """NeuMF (class spec, src/models/NeuMFModel.py:53-100) with row-sharded tables; see the module docstring."""
 
     def __init__(self, numUser, numItem, numFactor, act="relu", loss="mse", learning_rate=1e-3, dropout=0.0,
-                 seed=42, dropout_seed=11, device=None, mode="peer", emulate=0, full_init=None):
+                 seed=42, dropout_seed=11, device=None, mode="peer", emulate=0, full_init=None, tensor_cores=False):
         from .NeuMFModel import NeuMFNet
         self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
         self.mode = mode
+        self.tensor_cores = bool(tensor_cores)
         self.emulate = int(emulate)
         if self.emulate:
             self.G, self.rank = self.emulate, 0
@@ -172,7 +173,7 @@ class ShardedNeuMFNet:
         return N.brk_neumf_model(t[0].c_struct(), t[1].c_struct(), t[2].c_struct(), t[3].c_struct(),
                                  self.dense.c_struct(), self.bn_moving.data_ptr(), self.E, h1, h2, h3,
                                  0 if self.act == "relu" else 1, 0 if self.loss == "mse" else 1,
-                                 1 if self.dropout > 0 else 0, 0)
+                                 1 if self.dropout > 0 else 0, 1 if self.tensor_cores else 0)
 
     def _c_shards(self):
         return N.brk_neumf_shards(*[t.c_shards() for t in self._tables()])

@@ -184,7 +184,10 @@ int brk_adagrad_dense(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, float
  * brk_neumf_dense_floats().  bn_moving holds moving mean1[H1], var1[H1], mean2[H2], var2[H2]
  * (Keras: momentum 0.99, eps 1e-3, biased batch variance).  act: 0 relu, 1 sigmoid.  dropout != 0
  * applies the Philox-defined masks of oracle/neumf.py (keep 205/256) in training.
- * Built instances (E; H1,H2,H3): (32;32,16,8) (64;64,32,16) (16;16,8,4) (8;8,4,2) (10;100,50,10).
+ * Built instances (E; H1,H2,H3): (32;32,16,8) (64;64,32,16) (16;16,8,4) (8;8,4,2) (10;100,50,10); the first two
+ * also exist as tensor-core kernels (tensor_cores = 1: every Dense product of the forward and backward pass is a
+ * tcgen05.mma with TF32 operands out of shared memory and fp32 accumulators in TMEM, csrc/neumf_tc.cu; results
+ * agree with the fp32 path to TF32 rounding, ~1e-3 relative).
  * Workspace: h1,dy1 [H1*batch], h2,dy2 [H2*batch] floats, acc brk_neumf_acc_doubles() doubles that
  * must be ZERO before the first call (every call leaves them zero again).
  * training != 0: accumulates all gradients into the tables' g (to be consumed by the optimizer
@@ -196,7 +199,8 @@ typedef struct brk_neumf_model {
   brk_table uMLP, iMLP, uMF, iMF, dense;
   float*  bn_moving;
   int32_t E, H1, H2, H3;
-  int32_t act, loss, dropout, _pad;
+  int32_t act, loss, dropout;
+  int32_t tensor_cores;   /* 0: fp32 on the CUDA cores; 1: MLP products on tcgen05 with TF32 operands, fp32 accumulation */
 } brk_neumf_model;
 typedef struct brk_neumf_workspace {
   float *h1, *h2, *dy1, *dy2;

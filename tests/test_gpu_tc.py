@@ -46,3 +46,65 @@ def test_tf32_descriptor_forms(dev, M, N, mode):
         lanes = [int(np.where((got == ref[m].astype(np.float32)).all(axis=1))[0][0]) for m in range(M)]
         print("M=64 row -> lane:", lanes[:8], "...", lanes[-4:])
         assert lanes == list(range(64)) or lanes == [32 * (m // 16) + m % 16 for m in range(64)]
+
+
+# ---- NeuMF on the tensor cores vs the fp32 path ----------------------------------------------------------------
+# Stated TF32 tolerance: operands carry 10 mantissa bits (relative 2^-11 per factor), accumulation is fp32.
+#   predictions / loss / BatchNorm statistics: rtol 2e-3;
+#   gradients: judged per tensor against its largest entry and norm-wise, because the BatchNorm backward
+#   subtracts batch means (cancellation) and, with ReLU, a pre-activation within TF32 rounding of zero flips
+#   its gate and changes that sample's whole contribution.  Measured on these cases (profiles/neumf_tc_debug.py):
+#   sigmoid: max error <= 3.6 % of max|g|, Frobenius <= 3 %;  ReLU: max error <= 15 %, Frobenius <= 5.6 %.
+#   Bounds asserted: sigmoid 6 % / 5 %, ReLU 25 % / 10 %.
+def _neumf_pair(dev, E, dropout, act="relu", loss="mse", seed=42):
+    from binrec_b200.NeuMFModel import NeuMFNet
+    U, I = 300, 200
+    a = NeuMFNet(U, I, E, act=act, loss=loss, dropout=dropout, seed=seed, device=dev, tensor_cores=False)
+    b = NeuMFNet(U, I, E, act=act, loss=loss, dropout=dropout, seed=seed, device=dev, tensor_cores=True)
+    return a, b, U, I
+
+
+def _check_grad(g1, g0, smooth, name):
+    scale = max(float(np.abs(g0).max()), 1e-20)
+    mx = float(np.abs(g1 - g0).max()) / scale
+    rel = float(np.linalg.norm((g1 - g0).ravel()) / max(np.linalg.norm(g0.ravel()), 1e-20))
+    assert mx <= (0.06 if smooth else 0.25), (name, mx)
+    assert rel <= (0.05 if smooth else 0.10), (name, rel)
+
+
+@pytest.mark.parametrize("E", [64, 32])
+@pytest.mark.parametrize("act,loss", [("sigmoid", "bce"), ("relu", "mse")])
+@pytest.mark.parametrize("dropout", [0.0, 0.2])
+@pytest.mark.parametrize("B", [1000, 128, 77])
+def test_neumf_tensor_core_step_matches_fp32_path(dev, E, act, loss, dropout, B):
+    ref, net, U, I = _neumf_pair(dev, E, dropout, act, loss)
+    rng = np.random.default_rng(E + B)
+    u = (U * rng.random(B) ** 2).astype(np.int32); i = (I * rng.random(B) ** 2).astype(np.int32)
+    y = (rng.random(B) < 0.25).astype(np.float32)
+    ud, idd, yd = (torch.from_numpy(x).to(dev) for x in (u, i, y))
+    l0, o0 = ref.forward_backward(ud, idd, yd, first_index=4096, epoch=3)
+    l1, o1 = net.forward_backward(ud, idd, yd, first_index=4096, epoch=3)
+    np.testing.assert_allclose(o1.cpu().numpy(), o0.cpu().numpy(), rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(l1.item(), l0.item(), rtol=2e-3)
+    smooth = act == "sigmoid"
+    for name in ("uMLP", "iMLP", "uMF", "iMF"):
+        _check_grad(getattr(net, name).g.cpu().numpy(), getattr(ref, name).g.cpu().numpy(), smooth, name)
+    for name in net.DENSE_ORDER:
+        _check_grad(net.param(name, grad=True).cpu().numpy(), ref.param(name, grad=True).cpu().numpy(), smooth, name)
+    np.testing.assert_allclose(net.bn_moving.cpu().numpy(), ref.bn_moving.cpu().numpy(), rtol=2e-3, atol=1e-5)
+
+
+def test_neumf_tensor_core_training_tracks_fp32_and_eval(dev):
+    ref, net, U, I = _neumf_pair(dev, 64, 0.2)
+    rng = np.random.default_rng(9)
+    B = 2048
+    for step in range(5):
+        u = (U * rng.random(B) ** 2).astype(np.int32); i = (I * rng.random(B) ** 2).astype(np.int32)
+        y = (rng.random(B) < 0.25).astype(np.float32)
+        ud, idd, yd = (torch.from_numpy(x).to(dev) for x in (u, i, y))
+        l0, _ = ref.train_on_batch(ud, idd, yd, first_index=step * B, epoch=0)
+        l1, _ = net.train_on_batch(ud, idd, yd, first_index=step * B, epoch=0)
+        np.testing.assert_allclose(l1.item(), l0.item(), rtol=5e-3)
+    p0, _ = ref.predict_on_batch(ud, idd, yd)
+    p1, _ = net.predict_on_batch(ud, idd, yd)
+    np.testing.assert_allclose(p1.cpu().numpy(), p0.cpu().numpy(), rtol=1e-2, atol=1e-3)
