@@ -163,17 +163,29 @@ __device__ __forceinline__ void bn_prepare(float* mean, float* rstd, const doubl
     mean[f] = mu; rstd[f] = 1.0f / sqrtf(var + kBnEps);
   }
 }
-// per-feature sums over the tile's samples of a staged feature-major tile (double), one atomic pair per feature
+// per-feature sums over the tile's samples of a staged feature-major tile: all threads take a slice of the
+// samples (float partials over <= 32 samples), combined with double atomics
 template <int H>
 __device__ __forceinline__ void row_sums(const float* A, const float* Bm, double* sumA, double* sumAB) {
-  for (int f = threadIdx.x; f < H; f += NT) {
-    double s = 0.0, q = 0.0;
-    for (int r = 0; r < TS; ++r) {
-      const float a = A[f * SP + r], b = Bm ? Bm[f * SP + r] : a;
-      s += double(a); q += double(a) * double(b);
-    }
-    atomicAdd(sumA + f, s);
-    atomicAdd(sumAB + f, q);
+  constexpr int PARTS = NT / H, LEN = TS / PARTS;
+  static_assert(PARTS * H == NT && LEN * PARTS == TS, "row_sums split");
+  const int f = threadIdx.x % H, part = threadIdx.x / H;
+  float s = 0.f, q = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < LEN; ++i) {
+    const int r = part * LEN + ((i + f) & (LEN - 1));          // rotate: lanes of a warp hit distinct banks
+    const float a = A[f * SP + r], b = Bm ? Bm[f * SP + r] : a;
+    s += a; q = fmaf(a, b, q);
+  }
+  __shared__ float rs_part[2][NT];
+  rs_part[0][threadIdx.x] = s; rs_part[1][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.x < H) {                                       // one atomic pair per feature per CTA
+    double ds = 0.0, dq = 0.0;
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) { ds += double(rs_part[0][p * H + f]); dq += double(rs_part[1][p * H + f]); }
+    atomicAdd(sumA + f, ds);
+    atomicAdd(sumAB + f, dq);
   }
 }
 template <int H>
@@ -237,11 +249,50 @@ __device__ __forceinline__ void zero_pad_cols(uint8_t* T, bool mn) {
   }
 }
 
+// Tile ids into shared memory (one coalesced load per table), so that the row gathers do not chain on them.
+__device__ __forceinline__ void load_tile_ids(int32_t* ids_s, const Args& A, int64_t b0, int valid) {
+  const int t = threadIdx.x;
+  if (t < 2 * TS) {
+    const int r = t & (TS - 1);
+    ids_s[t] = r < valid ? __ldg((t < TS ? A.u : A.i) + b0 + r) : 0;
+  }
+}
+// Gather x0 = [uMLP[u], iMLP[i]] for a tile: E/4 lanes per row, 16 bytes each (coalesced rows); every load of the
+// thread is issued before the first use.  MN = 0: K-major swizzle, 1: MN-major swizzle.
+template <int E, int MN>
+__device__ __forceinline__ void gather_x0(uint8_t* Xs, const Args& A, const int32_t* ids_s, const uint32_t* masks, int valid) {
+  constexpr int LPR = E / 4, RPP = NT / LPR, NP = TS / RPP, MW = 2 * E / 32;
+  const int t = threadIdx.x, c4 = t % LPR, rr = t / LPR;
+  float4 v[2 * NP];
+#pragma unroll
+  for (int tab = 0; tab < 2; ++tab)
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const int r = p * RPP + rr;
+      v[tab * NP + p] = r < valid ? __ldg(reinterpret_cast<const float4*>(locate<E>(tab == 0 ? A.uMLP : A.iMLP, ids_s[tab * TS + r]).w) + c4)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+  for (int tab = 0; tab < 2; ++tab)
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const int r = p * RPP + rr;
+      float4 x = v[tab * NP + p];
+      if (A.dropout) {
+        const int f = tab * E + 4 * c4;
+        const uint32_t m = masks[r * MW + (f >> 5)] >> (f & 31);
+        x.x = (m & 1u) ? x.x * kDropScale : 0.f; x.y = (m & 2u) ? x.y * kDropScale : 0.f;
+        x.z = (m & 4u) ? x.z * kDropScale : 0.f; x.w = (m & 8u) ? x.w * kDropScale : 0.f;
+      }
+      *reinterpret_cast<float4*>(Xs + (MN ? mn_off16(TS, r, tab * LPR + c4) : km_off16(TS, r, tab * LPR + c4))) = x;
+    }
+}
+
 // ---- phase 1: x0 = dropout([uMLP[u], iMLP[i]]); h1 = act(x0 W1 + b1); batch sums of h1 -----------------
 template <int E, int H1, int H2, int H3, int ACT>
 __global__ void __launch_bounds__(NT) tc_fwd1(const Args A, const float* __restrict__ img) {
   using L = Layout<E, H1, H2, H3>; using AC = Acc<H1, H2>; using I = Img<E, H1, H2, H3>;
-  constexpr int K0 = 2 * E, LPR = E / 4, RPP = NT / LPR, MW = K0 / 32;
+  constexpr int K0 = 2 * E, MW = K0 / 32;
   uint8_t* sm = smem_base();
   uint8_t* As = sm;                                        // [K0/32][128 rows][128 B]   x0, K-major view
   uint8_t* Ws = As + TS * K0 * 4;                          // W1^T image
@@ -249,9 +300,11 @@ __global__ void __launch_bounds__(NT) tc_fwd1(const Args A, const float* __restr
   uint32_t* masks = reinterpret_cast<uint32_t*>(bs + H1);  // [128][MW] keep bits of layer 0
   float* Ys = reinterpret_cast<float*>(As);                // staging [H1][SP], aliases x0 once the MMA has read it
   __shared__ Ctl ctl;
+  __shared__ int32_t ids_s[2 * TS];
   const int64_t b0 = int64_t(blockIdx.x) * TS;
   const int valid = int((A.B - b0) < int64_t(TS) ? (A.B - b0) : int64_t(TS));
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  load_tile_ids(ids_s, A, b0, valid);
   const uint32_t tmem = tc_begin<64>(ctl);
   copy16(Ws, img + I::W1t, H1 * pad32(K0));
   copy_small<H1>(bs, A.dense.w + L::b1);
@@ -263,27 +316,7 @@ __global__ void __launch_bounds__(NT) tc_fwd1(const Args A, const float* __restr
     }
     __syncthreads();
   }
-  // gather: LPR lanes per row, 16 bytes each (coalesced rows); rows land sample-major in the K-major swizzle
-#pragma unroll
-  for (int tab = 0; tab < 2; ++tab) {
-    const TabRef& T = tab == 0 ? A.uMLP : A.iMLP;
-    const int32_t* ids = tab == 0 ? A.u : A.i;
-#pragma unroll 4
-    for (int r0 = 0; r0 < TS; r0 += RPP) {
-      const int r = r0 + t / LPR, c4 = t % LPR;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < valid) {
-        v = __ldg(reinterpret_cast<const float4*>(locate<E>(T, __ldg(ids + b0 + r)).w) + c4);
-        if (A.dropout) {
-          const int f = tab * E + 4 * c4;
-          const uint32_t m = masks[r * MW + (f >> 5)] >> (f & 31);
-          v.x = (m & 1u) ? v.x * kDropScale : 0.f; v.y = (m & 2u) ? v.y * kDropScale : 0.f;
-          v.z = (m & 4u) ? v.z * kDropScale : 0.f; v.w = (m & 8u) ? v.w * kDropScale : 0.f;
-        }
-      }
-      *reinterpret_cast<float4*>(As + km_off16(TS, r, tab * LPR + c4)) = v;
-    }
-  }
+  gather_x0<E, 0>(As, A, ids_s, masks, valid);
   NTC_OPERANDS_READY();
   if (t == 0) {
     issue_gemm<128, H1, 0, 0>(tmem, tc::smem_u32(As), TS, tc::smem_u32(Ws), H1, K0, false);
@@ -325,14 +358,16 @@ __device__ __forceinline__ void stage_bn_tile(uint8_t* At, const float* __restri
                                 : 0xFFFFu;
   // when HH is 8 the half's bits are the upper or lower byte of one 16-feature call
   const int bit0 = (hf * HH) & 15;
+  float hv[HH];
+#pragma unroll
+  for (int fl = 0; fl < HH; ++fl) hv[fl] = ok ? __ldg(h + int64_t(hf * HH + fl) * A.B + b0 + s) : 0.f;   // all loads in flight
 #pragma unroll
   for (int f4 = 0; f4 < HH / 4; ++f4) {
     float v[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int fl = f4 * 4 + q, f = hf * HH + fl;
-      const float hv = ok ? __ldg(h + int64_t(f) * A.B + b0 + s) : 0.f;
-      const float xh = (hv - mean[f]) * rstd[f];
+      const float xh = (hv[fl] - mean[f]) * rstd[f];
       if (Xh) Xh[f * SP + s] = ok ? xh : 0.f;
       float y = gam[f] * xh + bet[f];
       if (A.dropout) y = ((bits[(bit0 + fl) >> 4] >> ((bit0 + fl) & 15)) & 1u) ? y * kDropScale : 0.f;
@@ -407,9 +442,11 @@ __global__ void __launch_bounds__(NT) tc_head(const Args A, const float* __restr
   float* mean = mfs + TS; float* rstd = mean + H2; float* gam = rstd + H2; float* bet = gam + H2;
   __shared__ Ctl ctl;
   __shared__ double red[32];
+  __shared__ int32_t ids_s[2 * TS];
   const int64_t b0 = int64_t(blockIdx.x) * TS;
   const int valid = int((A.B - b0) < int64_t(TS) ? (A.B - b0) : int64_t(TS));
   const int t = threadIdx.x, warp = t >> 5;
+  load_tile_ids(ids_s, A, b0, valid);
   const uint32_t tmem = tc_begin<32>(ctl);
   copy16(Ws, img + I::W3t, N3 * pad32(H2));
   copy_small<H2 * H3>(W3s, A.dense.w + L::W3);
@@ -426,18 +463,25 @@ __global__ void __launch_bounds__(NT) tc_head(const Args A, const float* __restr
     issue_gemm<128, N3, 0, 0>(tmem, tc::smem_u32(As), TS, tc::smem_u32(Ws), N3, H2, false);
     tc::mma_commit(tc::smem_u32(&ctl.bar));
   }
-  // MF dot product while the tensor core works: LPR lanes per row pair
-#pragma unroll 2
-  for (int r0 = 0; r0 < TS; r0 += RPP) {
-    const int r = r0 + t / LPR, c4 = t % LPR;
-    float part = 0.f;
+  // MF dot product while the tensor core works: LPR lanes per row pair; the row chunks stay in registers for
+  // the gradient REDs further down
+  constexpr int NP = TS / RPP;
+  float4 mu[NP], mi[NP];
+  const int mc4 = t % LPR, mrr = t / LPR;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int r = p * RPP + mrr;
+    mu[p] = mi[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < valid) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(locate<E>(A.uMF, __ldg(A.u + b0 + r)).w) + c4);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(locate<E>(A.iMF, __ldg(A.i + b0 + r)).w) + c4);
-      part = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+      mu[p] = __ldg(reinterpret_cast<const float4*>(locate<E>(A.uMF, ids_s[r]).w) + mc4);
+      mi[p] = __ldg(reinterpret_cast<const float4*>(locate<E>(A.iMF, ids_s[TS + r]).w) + mc4);
     }
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    float part = fmaf(mu[p].x, mi[p].x, fmaf(mu[p].y, mi[p].y, fmaf(mu[p].z, mi[p].z, mu[p].w * mi[p].w)));
     part = group_sum<LPR>(part);
-    if (c4 == 0) mfs[r] = part;
+    if (mc4 == 0) mfs[p * RPP + mrr] = part;
   }
   tc::mbar_wait(tc::smem_u32(&ctl.bar), 0);
   tc::fence_after_sync();
@@ -475,24 +519,46 @@ __global__ void __launch_bounds__(NT) tc_head(const Args A, const float* __restr
   if (t == 0) atomicAdd(A.acc + AC::loss, lsum);
   if (A.training) {
     __syncthreads();
-    // head weights: dW4[j] = sum_s z[j][s] dl[s] (z = [h3, mf]), db4 = sum_s dl[s]
-    for (int j = t; j < H3 + 2; j += NT) {
+    // head weights: dW4[j] = sum_s z[j][s] dl[s] (z = [h3, mf]), db4 = sum_s dl[s]: one warp per output, lanes over samples
+    for (int j = warp; j < H3 + 2; j += NT / 32) {
       float sacc = 0.f;
-      for (int s = 0; s < TS; ++s) sacc = fmaf(j < H3 ? Ys[j * SP + s] : (j == H3 ? mfs[s] : 1.f), dl[s], sacc);
-      atomicAdd(A.dense.g + L::W4 + j, sacc);
+#pragma unroll
+      for (int q = 0; q < TS / 32; ++q) {
+        const int s = q * 32 + (t & 31);
+        sacc = fmaf(j < H3 ? Ys[j * SP + s] : (j == H3 ? mfs[s] : 1.f), dl[s], sacc);
+      }
+      sacc = warp_sum(sacc);
+      if ((t & 31) == 0) atomicAdd(A.dense.g + L::W4 + j, sacc);
     }
-    // layer-3 weights: dW3[k][j] = sum_s d2[s][k] dz3[s][j]; db3[j] = sum_s dz3[s][j]   (small: CUDA cores)
-    for (int o = t; o < H2 * H3 + H3; o += NT) {
-      float sacc = 0.f;
-      if (o < H2 * H3) {
-        const int k = o % H2, j = o / H2;
-        for (int s = 0; s < TS; ++s)
-          sacc = fmaf(*reinterpret_cast<const float*>(As + km_off16(TS, s, k >> 2) + (k & 3) * 4), Zt[s * ZP + j], sacc);
-        atomicAdd(A.dense.g + L::W3 + k * H3 + j, sacc);
-      } else {
-        const int j = o - H2 * H3;
-        for (int s = 0; s < TS; ++s) sacc += Zt[s * ZP + j];
-        atomicAdd(A.dense.g + L::b3 + j, sacc);
+    // layer-3 weights: dW3[k][j] = sum_s d2[s][k] dz3[s][j]; db3[j] = sum_s dz3[s][j]   (small: CUDA cores).
+    // thread = (k, group of JG outputs j); d2 is read from the swizzled K-major tile, 8 rows per address step
+    {
+      constexpr int JG = (H2 * H3) / NT > 0 ? (H2 * H3) / NT : 1;      // outputs j per thread
+      constexpr int NTH = (H2 * H3) / JG;                              // threads used
+      if (t < NTH) {
+        const int k = t % H2, j0 = (t / H2) * JG;
+        float acc[JG];
+#pragma unroll
+        for (int q = 0; q < JG; ++q) acc[q] = 0.f;
+        const uint8_t* base = As + (k & 3) * 4;
+        for (int s8 = 0; s8 < TS / 8; ++s8) {
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float a = *reinterpret_cast<const float*>(base + s8 * 1024 + r * 128 + (((k >> 2) ^ r) << 4));
+            const float* z = Zt + (s8 * 8 + r) * ZP + j0;
+#pragma unroll
+            for (int q = 0; q < JG; ++q) acc[q] = fmaf(a, z[q], acc[q]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < JG; ++q) atomicAdd(A.dense.g + L::W3 + k * H3 + j0 + q, acc[q]);
+      }
+      for (int j = warp; j < H3; j += NT / 32) {                       // db3: one warp per j
+        float sacc = 0.f;
+#pragma unroll
+        for (int q = 0; q < TS / 32; ++q) sacc += Zt[(q * 32 + (t & 31)) * ZP + j];
+        sacc = warp_sum(sacc);
+        if ((t & 31) == 0) atomicAdd(A.dense.g + L::b3 + j, sacc);
       }
     }
     // dd2[s][k] = dropout-mask * sum_j dz3[s][j] W3[k][j]: thread (sample, half of the k range)
@@ -520,17 +586,15 @@ __global__ void __launch_bounds__(NT) tc_head(const Args A, const float* __restr
       }
     }
     // MF embedding gradients: LPR lanes per row pair, 16-byte REDs into the owners' accumulators
-#pragma unroll 2
-    for (int r0 = 0; r0 < TS; r0 += RPP) {
-      const int r = r0 + t / LPR, c4 = t % LPR;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const int r = p * RPP + mrr;
       if (r < valid) {
-        const RowRef ru = locate<E>(A.uMF, __ldg(A.u + b0 + r)), ri = locate<E>(A.iMF, __ldg(A.i + b0 + r));
+        const RowRef ru = locate<E>(A.uMF, ids_s[r]), ri = locate<E>(A.iMF, ids_s[TS + r]);
         const float dmf = dl[r] * w4[H3];
-        const float4 a = __ldg(reinterpret_cast<const float4*>(ru.w) + c4);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(ri.w) + c4);
-        red_add_f4(ru.g + 4 * c4, make_float4(dmf * b.x, dmf * b.y, dmf * b.z, dmf * b.w));
-        red_add_f4(ri.g + 4 * c4, make_float4(dmf * a.x, dmf * a.y, dmf * a.z, dmf * a.w));
-        if (c4 == 0) { mark_row(ru); mark_row(ri); }
+        red_add_f4(ru.g + 4 * mc4, make_float4(dmf * mi[p].x, dmf * mi[p].y, dmf * mi[p].z, dmf * mi[p].w));
+        red_add_f4(ri.g + 4 * mc4, make_float4(dmf * mu[p].x, dmf * mu[p].y, dmf * mu[p].z, dmf * mu[p].w));
+        if (mc4 == 0) { mark_row(ru); mark_row(ri); }
       }
     }
     __syncthreads();
@@ -549,26 +613,28 @@ __device__ __forceinline__ void stage_dz_tiles(uint8_t* Zk, uint8_t* Zm, const f
   const int t = threadIdx.x, s = t & (TS - 1), hf = t >> 7;
   constexpr int HH = H / 2;
   const bool ok = s < valid;
+  float hv[HH], dv[HH];
+#pragma unroll
+  for (int fl = 0; fl < HH; ++fl) {                       // all loads in flight before the first use
+    hv[fl] = ok ? __ldg(h + int64_t(hf * HH + fl) * B + b0 + s) : 0.f;
+    dv[fl] = ok ? __ldg(dy + int64_t(hf * HH + fl) * B + b0 + s) : 0.f;
+  }
 #pragma unroll
   for (int f4 = 0; f4 < HH / 4; ++f4) {
     float v[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int j = hf * HH + f4 * 4 + q;
-      float dz = 0.f;
-      if (ok) {
-        const float hv = __ldg(h + int64_t(j) * B + b0 + s);
-        const float xh = (hv - mean[j]) * rstd[j];
-        const float dh = gam[j] * rstd[j] * (__ldg(dy + int64_t(j) * B + b0 + s) - sdy[j] - xh * sdyx[j]);
-        dz = dh * act_grad<ACT>(hv);
-      }
-      v[q] = dz;
+      const int fl = f4 * 4 + q, j = hf * HH + fl;
+      const float xh = (hv[fl] - mean[j]) * rstd[j];
+      const float dh = gam[j] * rstd[j] * (dv[fl] - sdy[j] - xh * sdyx[j]);
+      v[q] = ok ? dh * act_grad<ACT>(hv[fl]) : 0.f;
     }
     const float4 v4 = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(Zk + km_off16(TS, s, (hf * HH) / 4 + f4)) = v4;
     *reinterpret_cast<float4*>(Zm + mn_off16(TS, s, (hf * HH) / 4 + f4)) = v4;
   }
 }
+
 // ---- phase 4 (backward through layer 2 and BatchNorm 1), persistent over tiles ------------------------------
 //   dz2 = bn2-backward(dy2) * act'(h2);  dW2 += d1^T dz2 (accumulated in TMEM across this CTA's tiles);
 //   dd1 = dropout-mask * dz2 W2^T -> dy1 with its BatchNorm-backward sums
@@ -587,6 +653,7 @@ __global__ void __launch_bounds__(NT) tc_bwd2(const Args A, const float* __restr
   float* mean1 = Ds + H1 * SP; float* rstd1 = mean1 + H1; float* gam1 = rstd1 + H1; float* bet1 = gam1 + H1;
   float* mean2 = bet1 + H1; float* rstd2 = mean2 + H2; float* gam2 = rstd2 + H2; float* sdy = gam2 + H2; float* sdyx = sdy + H2;
   __shared__ Ctl ctl;
+  __shared__ float rs_part[NT];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const uint32_t tmem = tc_begin<TCOLS>(ctl);
   copy16(Ws, img + I::W2, H1 * pad32(H2));
@@ -621,13 +688,16 @@ __global__ void __launch_bounds__(NT) tc_bwd2(const Args A, const float* __restr
       for (int c = 0; c < (HH + 15) / 16; ++c)
         bits[c] = (A.dropout && ok) ? drop16_bits(uint64_t(A.first_index + b0 + s), (hf * HH) / 16 + c, 1, A.drop_seed, A.drop_epoch) : 0xFFFFu;
       const int bit0 = (hf * HH) & 15;
+      float hv1[HH];
+#pragma unroll
+      for (int fl = 0; fl < HH; ++fl) hv1[fl] = ok ? __ldg(A.h1 + int64_t(hf * HH + fl) * A.B + b0 + s) : 0.f;
 #pragma unroll
       for (int f4 = 0; f4 < HH / 4; ++f4) {
         float v[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int fl = f4 * 4 + q, f = hf * HH + fl;
-          const float hv = ok ? __ldg(A.h1 + int64_t(f) * A.B + b0 + s) : 0.f;
+          const float hv = hv1[fl];
           float y = gam1[f] * (hv - mean1[f]) * rstd1[f] + bet1[f];
           if (A.dropout) y = ((bits[(bit0 + fl) >> 4] >> ((bit0 + fl) & 15)) & 1u) ? y * kDropScale : 0.f;
           v[q] = ok ? y : 0.f;
@@ -683,10 +753,20 @@ __global__ void __launch_bounds__(NT) tc_bwd2(const Args A, const float* __restr
     __syncthreads();
     store_tile<H1>(Ds, A.dy1, A.B, b0, valid);
     double* sum_d = A.acc + AC::d1; double* sum_e = A.acc + AC::e1;
-    for (int f = t; f < H1; f += NT) {
-      double sd = 0.0;
-      for (int r = 0; r < TS; ++r) sd += double(Ds[f * SP + r]);
-      atomicAdd(sum_d + f, sd);
+    {
+      constexpr int PARTS = NT / H1, LEN = TS / PARTS;
+      const int f = t % H1, part = t / H1;
+      float sd = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < LEN; ++i) sd += Ds[f * SP + part * LEN + ((i + f) & (LEN - 1))];
+      rs_part[t] = sd;
+      __syncthreads();
+      if (t < H1) {
+        double d = 0.0;
+#pragma unroll
+        for (int p = 0; p < PARTS; ++p) d += double(rs_part[p * H1 + t]);
+        atomicAdd(sum_d + t, d);
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -696,10 +776,20 @@ __global__ void __launch_bounds__(NT) tc_bwd2(const Args A, const float* __restr
       Ds[f * SP + es] = dd[j] * (hv - mean1[f]) * rstd1[f];
     }
     __syncthreads();
-    for (int f = t; f < H1; f += NT) {
-      double se = 0.0;
-      for (int r = 0; r < TS; ++r) se += double(Ds[f * SP + r]);
-      atomicAdd(sum_e + f, se);
+    {
+      constexpr int PARTS = NT / H1, LEN = TS / PARTS;
+      const int f = t % H1, part = t / H1;
+      float se = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < LEN; ++i) se += Ds[f * SP + part * LEN + ((i + f) & (LEN - 1))];
+      rs_part[t] = se;
+      __syncthreads();
+      if (t < H1) {
+        double d = 0.0;
+#pragma unroll
+        for (int p = 0; p < PARTS; ++p) d += double(rs_part[p * H1 + t]);
+        atomicAdd(sum_e + t, d);
+      }
     }
     __syncthreads();
   }
@@ -723,7 +813,7 @@ __global__ void __launch_bounds__(NT) tc_bwd2(const Args A, const float* __restr
 template <int E, int H1, int H2, int H3, int ACT>
 __global__ void __launch_bounds__(NT) tc_bwd1(const Args A, const float* __restrict__ img, int n_tiles, unsigned int* ticket) {
   using L = Layout<E, H1, H2, H3>; using AC = Acc<H1, H2>; using I = Img<E, H1, H2, H3>;
-  constexpr int K0 = 2 * E, LPR = E / 4, RPP = NT / LPR, MWORDS = K0 / 32;
+  constexpr int K0 = 2 * E, MWORDS = K0 / 32;
   constexpr int WCOL = K0;                                 // TMEM: [0, K0) dx0, [WCOL, WCOL + H1) dW1
   constexpr int TCOLS = 256;
   uint8_t* sm = smem_base();
@@ -735,6 +825,7 @@ __global__ void __launch_bounds__(NT) tc_bwd1(const Args A, const float* __restr
   float* mean1 = reinterpret_cast<float*>(masks + TS * MWORDS); float* rstd1 = mean1 + H1; float* gam1 = rstd1 + H1;
   float* sdy = gam1 + H1; float* sdyx = sdy + H1;
   __shared__ Ctl ctl;
+  __shared__ int32_t ids_s[2 * TS];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const uint32_t tmem = tc_begin<TCOLS>(ctl);
   copy16(Ws, img + I::W1, K0 * pad32(H1));
@@ -754,34 +845,16 @@ __global__ void __launch_bounds__(NT) tc_bwd1(const Args A, const float* __restr
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int64_t b0 = int64_t(tile) * TS;
     const int valid = int((A.B - b0) < int64_t(TS) ? (A.B - b0) : int64_t(TS));
+    load_tile_ids(ids_s, A, b0, valid);
     if (A.dropout) {
       const int s = t & (TS - 1), hf = t >> 7;
       for (int c = hf * (K0 / 32); c < (hf + 1) * (K0 / 32); ++c) {
         const uint32_t bits = s < valid ? drop16_bits(uint64_t(A.first_index + b0 + s), c, 0, A.drop_seed, A.drop_epoch) : 0u;
         reinterpret_cast<uint16_t*>(masks + s * MWORDS)[c] = uint16_t(bits);
       }
-      __syncthreads();
     }
-#pragma unroll
-    for (int tab = 0; tab < 2; ++tab) {                     // re-gather x0 (rows are L2-hot from phase 1)
-      const TabRef& T = tab == 0 ? A.uMLP : A.iMLP;
-      const int32_t* ids = tab == 0 ? A.u : A.i;
-#pragma unroll 4
-      for (int r0 = 0; r0 < TS; r0 += RPP) {
-        const int r = r0 + t / LPR, c4 = t % LPR;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < valid) {
-          v = __ldg(reinterpret_cast<const float4*>(locate<E>(T, __ldg(ids + b0 + r)).w) + c4);
-          if (A.dropout) {
-            const int f = tab * E + 4 * c4;
-            const uint32_t m = masks[r * MWORDS + (f >> 5)] >> (f & 31);
-            v.x = (m & 1u) ? v.x * kDropScale : 0.f; v.y = (m & 2u) ? v.y * kDropScale : 0.f;
-            v.z = (m & 4u) ? v.z * kDropScale : 0.f; v.w = (m & 8u) ? v.w * kDropScale : 0.f;
-          }
-        }
-        *reinterpret_cast<float4*>(Xm + mn_off16(TS, r, tab * LPR + c4)) = v;
-      }
-    }
+    __syncthreads();
+    gather_x0<E, 1>(Xm, A, ids_s, masks, valid);           // re-gather x0 (rows are L2-hot from phase 1)
     stage_dz_tiles<H1, ACT>(Zk, Zm, A.h1, A.dy1, mean1, rstd1, gam1, sdy, sdyx, A.B, b0, valid);
     NTC_OPERANDS_READY();
     if (t == 0) {
@@ -807,7 +880,7 @@ __global__ void __launch_bounds__(NT) tc_bwd1(const Args A, const float* __restr
       const int s = (warp & 3) * 32 + lane, tab = warp >> 2;
       const bool ok = s < valid;
       RowRef rr; rr.w = nullptr; rr.g = nullptr; rr.t = nullptr; rr.lrow = 0;
-      if (ok) rr = locate<E>(tab == 0 ? A.uMLP : A.iMLP, __ldg((tab == 0 ? A.u : A.i) + b0 + s));
+      if (ok) rr = locate<E>(tab == 0 ? A.uMLP : A.iMLP, ids_s[tab * TS + s]);
       for (int cc = 0; cc < E; cc += 32) {
         float v[32];
         tmem_load32(tmem, warp, tab * E + cc, v);
@@ -902,11 +975,10 @@ int run(brk_ctx* ctx, const Args& A, cudaStream_t st) {
     BRK_CUDA(cudaFuncSetAttribute(tc_head<E, H1, H2, H3, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smC)));
     BRK_CUDA(cudaFuncSetAttribute(tc_bwd2<E, H1, H2, H3, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smD)));
     BRK_CUDA(cudaFuncSetAttribute(tc_bwd1<E, H1, H2, H3, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smE)));
-    BRK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_d, tc_bwd2<E, H1, H2, H3, ACT>, NT, smD));
-    BRK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, tc_bwd1<E, H1, H2, H3, ACT>, NT, smE));
-    // TMEM: 512 columns per SM -- bwd2 allocates 128, bwd1 256 per CTA
-    if (occ_d > 4) occ_d = 4;
-    if (occ_e > 2) occ_e = 2;
+    // persistent grids: CTAs per SM by shared memory (227 KB), registers (2 x 256 threads) and TMEM (512 columns:
+    // bwd2 allocates 128, bwd1 256 per CTA)
+    occ_d = int((227 * 1024) / (smD + 1024)); if (occ_d > 2) occ_d = 2;
+    occ_e = int((227 * 1024) / (smE + 1024)); if (occ_e > 2) occ_e = 2;
     BRK_REQUIRE(occ_d > 0 && occ_e > 0, BRK_E_STATE, "brk_neumf_step: tensor-core kernels do not fit");
     attr_done = true;
   }
