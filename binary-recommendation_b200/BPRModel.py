@@ -16,6 +16,7 @@ Differences from the reference, stated once:
   * ids are int32 (the reference casts them to float32, BPRModel.py:101-103).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -89,6 +90,14 @@ class BPRNet:
             losses = torch.empty(k, dtype=torch.float32, device=self.device)
         idx = (C.c_int64 * k)(*[int(b) for b in batch_indices])
         us, it = self.user.c_struct(), self.item.c_struct()
+        if self.peer is not None:
+            # mirrored data parallelism: one cooperative launch per rank runs all k steps, cross-GPU barriers and
+            # the reduce-scatter + Adam + all-gather over NVLink peer memory included (csrc/bpr.cu)
+            N.check(N.lib().brk_bpr_train_steps_dp(N.ctx(self.device), C.byref(us), C.byref(it), N.ptr(pr["u"]),
+                                                   N.ptr(pr["p"]), N.ptr(pr["n"]), pr["total"], batch_size, idx, k,
+                                                   self.optimizer.h, C.byref(self.peer.desc), N.ptr(self.optimizer.state),
+                                                   N.ptr(losses), N.stream_ptr()), "brk_bpr_train_steps_dp")
+            return losses
         N.check(N.lib().brk_bpr_train_steps(N.ctx(self.device), C.byref(us), C.byref(it), N.ptr(pr["u"]),
                                             N.ptr(pr["p"]), N.ptr(pr["n"]), pr["total"], batch_size, idx, k,
                                             self.optimizer.h, 1 if self.optimizer.sparse == "lazy" else 0,
@@ -168,6 +177,17 @@ class BPRNet:
         trains its own slice, gradients are scaled by 1/(world * batch) and summed by one all-reduce,
         every rank applies the same Adam step."""
         w = D.world_size()
+        if self.peer is not None and os.environ.get("BRK_DP_FUSED", "1") == "1":
+            # one cooperative launch: fused fwd/bwd + cross-GPU reduce-scatter / Adam / all-gather
+            if loss_out is None:
+                loss_out = torch.empty(1, dtype=torch.float32, device=self.device)
+            idx = (C.c_int64 * 1)(0)
+            us, it = self.user.c_struct(), self.item.c_struct()
+            N.check(N.lib().brk_bpr_train_steps_dp(N.ctx(self.device), C.byref(us), C.byref(it), N.ptr(H._i32(u, "u")),
+                                                   N.ptr(H._i32(p, "p")), N.ptr(H._i32(n, "n")), u.numel(), u.numel(), idx, 1,
+                                                   self.optimizer.h, C.byref(self.peer.desc), N.ptr(self.optimizer.state),
+                                                   N.ptr(loss_out), N.stream_ptr()), "brk_bpr_train_steps_dp")
+            return loss_out
         loss = H.bpr_fwd_bwd(self.user, self.item, u, p, n, loss_out=loss_out, global_batch=w * u.numel() if w > 1 else 0)
         self.apply_gradients()
         return loss

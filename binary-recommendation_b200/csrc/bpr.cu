@@ -184,7 +184,38 @@ struct BprCoopParams {
   int64_t stage_pitch;
   const int64_t* csr_indptr; const int32_t* csr_items;
   uint32_t seed, epoch, num_items;
+  // mirrored data parallelism (world > 1): both tables' w and g are views into per-rank arenas in NVLink
+  // peer-mapped memory; phase 2 becomes barrier -> reduce my slice over all ranks' g -> Adam -> write the new
+  // weights into every rank's arena -> barrier (csrc/dp_peer.cu, here inside the multi-step kernel)
+  float* const* peer_w; float* const* peer_g; uint32_t* const* peer_flags;
+  float* dp_m; float* dp_v; uint32_t* dp_sync;
+  int64_t arena_n4;
+  int32_t rank, world;
+  float inv_global;               // 1 / (world * batch): gradient scale of the global mean loss
+  unsigned long long* dbg;        // optional [n_steps][8] globaltimer stamps of block 0 (BRK_COOP_TRACE)
 };
+
+__device__ __forceinline__ void coop_st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool coop_spin_sys(const uint32_t* p, uint32_t epoch, uint32_t* err) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (int32_t(v - epoch) >= 0) return true;
+    if (clock64() - t0 > 6000000000LL) { atomicExch(err, 1u); return false; }      // ~3 s: a peer never arrived
+    __nanosleep(32);
+  }
+}
+
+__device__ __forceinline__ void coop_stamp(const BprCoopParams& P, int s, int k) {
+  if (P.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    P.dbg[s * 8 + k] = t;
+  }
+}
 
 __device__ __forceinline__ void adam4(float4& w, float4& m, float4& v, const float4 g, float alpha, float b1, float b2,
                                       float eps) {
@@ -236,7 +267,8 @@ __global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParam
   for (int s = 0; s < P.n_steps; ++s) {
     const BprStep sd = P.use_inline ? P.inline_steps[s] : P.steps[s];
     const int64_t batch = sd.count;
-    const float inv_batch = 1.0f / float(batch);
+    const float inv_batch = P.world > 1 ? P.inv_global : 1.0f / float(batch);
+    coop_stamp(P, s, 0);
     const int32_t *uid, *pid, *nid;
     if (sample) { uid = P.stage + int64_t(s & 1) * 3 * P.stage_pitch; pid = uid + P.stage_pitch; nid = pid + P.stage_pitch; }
     else { uid = P.u + sd.off; pid = P.p + sd.off; nid = P.n + sd.off; }
@@ -284,27 +316,87 @@ __global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParam
     const double part = block_sum_double(double(loss_local), red);
     if (threadIdx.x == 0) atomicAdd(P.loss_acc + (s & 1), part);
     grid.sync();
+    coop_stamp(P, s, 1);
     // ---- phase 2: exact Keras Adam over every element of both tables; zero the accumulators.  In sampling
     //      mode the first two warps of each CTA stage step s+1 instead (ids + negatives) ----
     p1 *= double(P.h.beta1); p2 *= double(P.h.beta2);
     const float alpha = float(double(P.h.lr) * sqrt(1.0 - p2) / (1.0 - p1));
     const bool staging = sample && s + 1 < P.n_steps;
-    if (staging && threadIdx.x < kStageThreads) {
+    const bool stager = staging && threadIdx.x < kStageThreads;
+    const int64_t atid = staging ? int64_t(blockIdx.x) * (kThreads - kStageThreads) + (threadIdx.x - kStageThreads) : tid;
+    const int64_t anthr = staging ? int64_t(gridDim.x) * (kThreads - kStageThreads) : nthr;
+    if (stager) {
       bpr_stage_step(P, P.use_inline ? P.inline_steps[s + 1] : P.steps[s + 1], (s + 1) & 1,
                      int64_t(blockIdx.x) * kStageThreads + threadIdx.x, int64_t(gridDim.x) * kStageThreads);
-    } else {
-      const int64_t atid = staging ? int64_t(blockIdx.x) * (kThreads - kStageThreads) + (threadIdx.x - kStageThreads) : tid;
-      const int64_t anthr = staging ? int64_t(gridDim.x) * (kThreads - kStageThreads) : nthr;
+    }
+    if (P.world == 1) {
+      if (!stager) {
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int64_t n4 = tabs[k].rows * tabs[k].d / 4;
-        float4* w4 = reinterpret_cast<float4*>(tabs[k].w); float4* g4 = reinterpret_cast<float4*>(tabs[k].g);
-        float4* m4 = reinterpret_cast<float4*>(tabs[k].m); float4* v4 = reinterpret_cast<float4*>(tabs[k].v);
-        for (int64_t i = atid; i < n4; i += anthr) {
-          float4 w = w4[i], m = m4[i], v = v4[i];
-          adam4(w, m, v, g4[i], alpha, P.h.beta1, P.h.beta2, P.h.eps);
-          w4[i] = w; m4[i] = m; v4[i] = v; g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 2; ++k) {
+          const int64_t n4 = tabs[k].rows * tabs[k].d / 4;
+          float4* w4 = reinterpret_cast<float4*>(tabs[k].w); float4* g4 = reinterpret_cast<float4*>(tabs[k].g);
+          float4* m4 = reinterpret_cast<float4*>(tabs[k].m); float4* v4 = reinterpret_cast<float4*>(tabs[k].v);
+          for (int64_t i = atid; i < n4; i += anthr) {
+            float4 w = w4[i], m = m4[i], v = v4[i];
+            adam4(w, m, v, g4[i], alpha, P.h.beta1, P.h.beta2, P.h.eps);
+            w4[i] = w; m4[i] = m; v4[i] = v; g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
+      }
+    } else {
+      // ---- data-parallel phase 2 over NVLink peer memory ----
+      const int G = P.world, me = P.rank;
+      const uint32_t ep = P.dp_sync[3] + uint32_t(s) + 1u;      // dp_sync[3]: epochs completed before this launch
+      uint32_t* my_flags = P.peer_flags[me];
+      if (blockIdx.x == 0 && threadIdx.x < G) {                 // barrier A: every rank's gradients are complete
+        __threadfence_system();
+        coop_st_release_sys(P.peer_flags[threadIdx.x] + me, ep);
+        coop_spin_sys(my_flags + threadIdx.x, ep, P.dp_sync + 4);
+      }
+      grid.sync();
+      coop_stamp(P, s, 2);
+      if (!stager) {
+        const int64_t lo = P.arena_n4 * me / G, hi = P.arena_n4 * (me + 1) / G;
+        float4* w_me = reinterpret_cast<float4*>(P.peer_w[me]);
+        float4* m4 = reinterpret_cast<float4*>(P.dp_m); float4* v4 = reinterpret_cast<float4*>(P.dp_v);
+        for (int64_t i = lo + atid; i < hi; i += anthr) {
+          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int p = 0; p < G; ++p) {                          // fixed order: every rank computes the same sum
+            const float4 x = __ldcg(reinterpret_cast<const float4*>(P.peer_g[p]) + i);
+            g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+          }
+          float4 w = __ldcg(w_me + i), m = m4[i - lo], v = v4[i - lo];
+          adam4(w, m, v, g, alpha, P.h.beta1, P.h.beta2, P.h.eps);
+          m4[i - lo] = m; v4[i - lo] = v;
+          w_me[i] = w;                                           // my slice, my arena only: the peers pull it below
+        }
+      }
+      coop_stamp(P, s, 3);
+      __threadfence();
+      grid.sync();
+      coop_stamp(P, s, 4);
+      if (blockIdx.x == 0 && threadIdx.x < G) {                 // barrier B: every rank's slice is final, reads of my g are done
+        __threadfence_system();
+        coop_st_release_sys(P.peer_flags[threadIdx.x] + G + me, ep);
+        coop_spin_sys(my_flags + G + threadIdx.x, ep, P.dp_sync + 4);
+      }
+      grid.sync();
+      coop_stamp(P, s, 5);
+      // all-gather by PULL: remote loads complete when their data arrives, so nothing has to wait for NVLink write
+      // acknowledgements (pushing the slices and fencing them system-wide cost ~8 us per step); zero my g meanwhile
+      {
+        float4* w_loc = reinterpret_cast<float4*>(P.peer_w[me]);
+        const int64_t lo = P.arena_n4 * me / G, hi = P.arena_n4 * (me + 1) / G;
+        const int64_t others = P.arena_n4 - (hi - lo);
+        for (int64_t j = tid; j < others; j += nthr) {
+          const int64_t i = j < lo ? j : j + (hi - lo);          // skip my own slice
+          int owner = int((i * G) / P.arena_n4);
+          while (P.arena_n4 * owner / G > i) --owner;
+          while (P.arena_n4 * (owner + 1) / G <= i) ++owner;
+          w_loc[i] = __ldcg(reinterpret_cast<const float4*>(P.peer_w[owner]) + i);
+        }
+        float4* g_me = reinterpret_cast<float4*>(P.peer_g[me]);
+        for (int64_t i = tid; i < P.arena_n4; i += nthr) g_me[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     if (tid == nthr - 1) {
@@ -312,10 +404,12 @@ __global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParam
       P.loss_acc[s & 1] = 0.0;
     }
     grid.sync();
+    coop_stamp(P, s, 6);
   }
   if (tid == 0) {
     double* pwo = reinterpret_cast<double*>(P.state);
     P.state[0] += P.n_steps; pwo[1] = p1; pwo[2] = p2;
+    if (P.world > 1) P.dp_sync[3] += uint32_t(P.n_steps);
   }
 }
 
@@ -391,6 +485,8 @@ static bool coop_eligible(const brk_table* user, const brk_table* item, int lazy
          ((user->rows * d) & 3) == 0 && ((item->rows * d) & 3) == 0 && getenv("BRK_NO_COOP") == nullptr;
 }
 
+static unsigned long long* g_coop_trace = nullptr;   // BRK_COOP_TRACE=1: per-step phase stamps of the last launch
+
 struct CoopSampler {                 // fused negative sampling for launch_coop_steps (n == nullptr)
   const int64_t* csr_indptr; const int32_t* csr_items;
   uint32_t seed, epoch, num_items;
@@ -410,7 +506,7 @@ static int ensure_scratch(brk_ctx* ctx, size_t need) {
 static int launch_coop_steps(brk_ctx* ctx, const brk_table* user, const brk_table* item, const int32_t* u,
                              const int32_t* p, const int32_t* n, const BprStep* steps_host, int32_t n_steps,
                              int64_t max_count, brk_adam_hyper h, int64_t* step_dev, float* losses, cudaStream_t st,
-                             const CoopSampler* smp = nullptr) {
+                             const CoopSampler* smp = nullptr, const brk_dp_peer* dp = nullptr) {
   const int d = user->d;
   BprCoopParams P;
   P.use_inline = n_steps <= kInlineSteps;
@@ -437,6 +533,19 @@ static int launch_coop_steps(brk_ctx* ctx, const brk_table* user, const brk_tabl
     P.stage = nullptr; P.stage_pitch = 0; P.csr_indptr = nullptr; P.csr_items = nullptr;
     P.seed = P.epoch = P.num_items = 0;
   }
+  if (dp && dp->world > 1) {
+    P.peer_w = dp->peer_w; P.peer_g = dp->peer_g; P.peer_flags = dp->peer_flags; P.dp_m = dp->m; P.dp_v = dp->v;
+    P.dp_sync = dp->local_sync; P.arena_n4 = dp->n / 4; P.rank = dp->rank; P.world = dp->world;
+    P.inv_global = 1.0f / float(int64_t(dp->world) * max_count);
+  } else {
+    P.peer_w = nullptr; P.peer_g = nullptr; P.peer_flags = nullptr; P.dp_m = nullptr; P.dp_v = nullptr; P.dp_sync = nullptr;
+    P.arena_n4 = 0; P.rank = 0; P.world = 1; P.inv_global = 0.f;
+  }
+  if (getenv("BRK_COOP_TRACE") && !g_coop_trace) {
+    BRK_CUDA(cudaMalloc(&g_coop_trace, 4096 * 8 * sizeof(unsigned long long)));
+    BRK_CUDA(cudaMemset(g_coop_trace, 0, 4096 * 8 * sizeof(unsigned long long)));
+  }
+  P.dbg = (g_coop_trace && n_steps <= 4096) ? g_coop_trace : nullptr;
   const int lpr = brk_lanes_per_row(d >> 2);
   void* fn = nullptr;
   int slot = 0;
@@ -556,6 +665,11 @@ extern "C" int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, con
       BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[q], cudaEventDisableTiming));
       BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[q], cudaEventDisableTiming));
     }
+    for (int a = 0; a < BRK_COPY_AUX; ++a) {
+      BRK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_aux[a], cudaStreamNonBlocking));
+      BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux[a], cudaEventDisableTiming));
+    }
+    BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_go, cudaEventDisableTiming));
     ctx->copy_ready = 1;
   }
   cudaStream_t cs = ctx->copy_stream;
@@ -572,14 +686,24 @@ extern "C" int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, con
         BRK_CUDA(cudaMemcpyAsync(losses_host + (j - 2) * kChunk, d_losses + (j - 2) * kChunk, kChunk * sizeof(float),
                                  cudaMemcpyDeviceToHost, cs));
     }
+    // the chunk's H2D copies are spread over kCopyLanes streams so that several DMAs are in flight at once (a
+    // single 128 KiB copy costs 10-35 us of latency on virtualised hosts); everything rejoins on `cs`
+    BRK_CUDA(cudaEventRecord(ctx->ev_go, cs));
+    for (int a = 0; a < BRK_COPY_AUX; ++a) BRK_CUDA(cudaStreamWaitEvent(ctx->copy_aux[a], ctx->ev_go, 0));
     for (int k = j * kChunk; k < (j + 1) * kChunk && k < n_steps; ++k) {
       const int64_t hoff = batch_index_host[k] * host_batch_stride, cnt = count_of(k);
+      const int lane = k % (BRK_COPY_AUX + 1);
+      cudaStream_t cl = lane == 0 ? cs : ctx->copy_aux[lane - 1];
       if (packed) {
-        BRK_CUDA(cudaMemcpyAsync(slot_of(k), u_host + hoff, 2 * batch * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+        BRK_CUDA(cudaMemcpyAsync(slot_of(k), u_host + hoff, 2 * batch * sizeof(int32_t), cudaMemcpyHostToDevice, cl));
       } else {
-        BRK_CUDA(cudaMemcpyAsync(slot_of(k), u_host + hoff, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
-        BRK_CUDA(cudaMemcpyAsync(slot_of(k) + batch, p_host + hoff, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+        BRK_CUDA(cudaMemcpyAsync(slot_of(k), u_host + hoff, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, cl));
+        BRK_CUDA(cudaMemcpyAsync(slot_of(k) + batch, p_host + hoff, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, cl));
       }
+    }
+    for (int a = 0; a < BRK_COPY_AUX; ++a) {
+      BRK_CUDA(cudaEventRecord(ctx->ev_aux[a], ctx->copy_aux[a]));
+      BRK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_aux[a], 0));
     }
     BRK_CUDA(cudaEventRecord(ctx->ev_ready[j & 1], cs));
     return 0;
@@ -677,4 +801,45 @@ extern "C" int brk_bpr_train_steps_mapped(brk_ctx* ctx, const brk_table* user, c
   return launch_coop_steps(ctx, user, item, reinterpret_cast<const int32_t*>(du), reinterpret_cast<const int32_t*>(dp),
                            nullptr, steps.data(), n_steps, batch < total ? batch : total, h, step_dev,
                            reinterpret_cast<float*>(const_cast<void*>(dl)), (cudaStream_t)stream, &smp);
+}
+
+// Mirrored data-parallel training steps (one process per GPU; the reference's MultiWorkerMirroredStrategy,
+// src/models/RModel.py:119-121) in ONE cooperative launch per rank: every step is this rank's fused fwd/bwd on
+// its slice of the global batch, a cross-GPU barrier, reduce-scatter + Adam + all-gather over NVLink peer memory
+// and a second barrier -- no NCCL call, no kernel launch and no host involvement between steps.  user / item
+// must be views into this rank's arenas of `dp` (user first, item right behind it, w and g alike); all ranks call
+// with the same n_steps and batch; gradients are scaled by 1 / (world * batch).
+extern "C" int brk_bpr_train_steps_dp(brk_ctx* ctx, const brk_table* user, const brk_table* item, const int32_t* u,
+                                      const int32_t* p, const int32_t* n, int64_t total, int64_t batch,
+                                      const int64_t* batch_index_host, int32_t n_steps, brk_adam_hyper h,
+                                      const brk_dp_peer* dp, int64_t* step_dev, float* losses, void* stream) {
+  BRK_REQUIRE(ctx && user && item && u && p && n && batch_index_host && step_dev && dp, BRK_E_ARG,
+              "brk_bpr_train_steps_dp: null argument");
+  BRK_REQUIRE(total > 0 && batch > 0 && n_steps >= 0, BRK_E_ARG, "brk_bpr_train_steps_dp: total=%lld batch=%lld",
+              (long long)total, (long long)batch);
+  BRK_REQUIRE(dp->world >= 1 && dp->world <= 64 && dp->rank >= 0 && dp->rank < dp->world && dp->n > 0 && (dp->n & 3) == 0 &&
+                  dp->peer_w && dp->peer_g && dp->peer_flags && dp->m && dp->v && dp->local_sync, BRK_E_ARG,
+              "brk_bpr_train_steps_dp: descriptor incomplete");
+  const int d = user->d;
+  BRK_REQUIRE(d == item->d && (d & 3) == 0 && d <= 128 && item->w == user->w + user->rows * d &&
+                  item->g == user->g + user->rows * d && (user->rows + item->rows) * d <= dp->n &&
+                  brk_aligned16(user->w) && brk_aligned16(user->g), BRK_E_ARG,
+              "brk_bpr_train_steps_dp: tables must be adjacent views into the peer arenas (d %% 4 == 0, d <= 128)");
+  const int64_t n_batches = (total + batch - 1) / batch;
+  for (int k = 0; k < n_steps; ++k)
+    BRK_REQUIRE(batch_index_host[k] >= 0 && batch_index_host[k] < n_batches && (batch_index_host[k] + 1) * batch <= total,
+                BRK_E_ARG, "brk_bpr_train_steps_dp: batch index %lld (full batches only: every rank must run the same count)",
+                (long long)batch_index_host[k]);
+  if (n_steps == 0) return 0;
+  std::vector<BprStep> steps(n_steps);
+  make_steps(steps.data(), batch_index_host, n_steps, total, batch);
+  return launch_coop_steps(ctx, user, item, u, p, n, steps.data(), n_steps, batch, h, step_dev, losses,
+                           (cudaStream_t)stream, nullptr, dp);
+}
+
+// Debug hook (profiles/dp_trace.py): copies the phase stamps of the last traced cooperative launch to the host.
+extern "C" int brk_coop_trace_read(unsigned long long* out_host, int32_t n_words) {
+  if (!g_coop_trace) return BRK_E_STATE;
+  BRK_CUDA(cudaMemcpy(out_host, g_coop_trace, size_t(n_words) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return 0;
 }

@@ -15,6 +15,8 @@ struct brk_ctx {
   // host-fed training: copy stream + events for H2D prefetch / loss D2H (created on first use)
   cudaStream_t  copy_stream;
   cudaEvent_t   ev_ready[4], ev_done[4];
+  cudaStream_t  copy_aux[3];  // extra DMA lanes: several H2D copies in flight
+  cudaEvent_t   ev_aux[3], ev_go;
   int           copy_ready;
   // NeuMF tensor-core path: swizzled weight images, rebuilt every step (csrc/neumf_tc.cu)
   float*        neumf_img;
@@ -22,6 +24,7 @@ struct brk_ctx {
 };
 
 #define BRK_STAGE_EVENTS 4
+#define BRK_COPY_AUX 3
 #define BRK_LOSS_SLOTS 16
 #define BRK_TICKETS 16
 

@@ -52,6 +52,8 @@ extern "C" int brk_destroy(brk_ctx* c) {
   if (c->copy_ready) {
     cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < BRK_STAGE_EVENTS; ++i) { cudaEventDestroy(c->ev_ready[i]); cudaEventDestroy(c->ev_done[i]); }
+    for (int i = 0; i < BRK_COPY_AUX; ++i) { cudaStreamDestroy(c->copy_aux[i]); cudaEventDestroy(c->ev_aux[i]); }
+    cudaEventDestroy(c->ev_go);
   }
   free(c);
   return 0;

@@ -274,6 +274,15 @@ typedef struct brk_dp_peer {
   int32_t rank, world;
 } brk_dp_peer;
 int brk_dp_adam_peer(brk_ctx* ctx, const brk_dp_peer* d, brk_adam_hyper h, int64_t* state, void* stream);
+/* The whole mirrored data-parallel BPR loop in ONE cooperative launch per rank: n_steps x (this rank's fused
+ * fwd/bwd on batch batch_index_host[k] of its own u/p/n arrays, cross-GPU barrier, reduce-scatter + Adam +
+ * all-gather over peer memory, cross-GPU barrier).  user / item must be adjacent views into this rank's arenas
+ * of `dp` (user first), all ranks call with the same n_steps and batch (full batches only); gradients are
+ * scaled by 1 / (world * batch); losses[k] = this rank's local-batch mean. */
+int brk_bpr_train_steps_dp(brk_ctx* ctx, const brk_table* user, const brk_table* item, const int32_t* u,
+                           const int32_t* p, const int32_t* n, int64_t total, int64_t batch,
+                           const int64_t* batch_index_host, int32_t n_steps, brk_adam_hyper h,
+                           const brk_dp_peer* dp, int64_t* step_dev, float* losses, void* stream);
 
 /* ---- two-tower: towers + in-batch softmax / rdZero loss + backward -------------------------------
  * Stands in for TwoTowerModel.computeEmb / computeLossTfrs / computeLossRdZero / train_step

@@ -21,7 +21,7 @@ def main():
         if mode == "nccl" and world == 1:
             continue
         for dist_name in ("uniform", "zipf"):
-            net = ShardedNeuMFNet(U, I, E, dropout=0.2, device=dev, mode=mode)
+            net = ShardedNeuMFNet(U, I, E, dropout=0.2, device=dev, mode=mode, tensor_cores=os.environ.get("SH_TC", "1") == "1")
             g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
             nb = 8
             if dist_name == "uniform":
