@@ -44,7 +44,7 @@ def load_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.2):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -90,6 +90,17 @@ class ClockSampler(threading.Thread):
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(self.samples)}
+
+
+def traffic_bytes(world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture (profiles/r01_traffic.json); N=1 only (ncu is never run on a multi-rank command)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if world != 1 or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    return t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"]
 
 
 def physical_gpu_index(local):
@@ -348,7 +359,7 @@ def product_arm(args):
                                     "bpr_steps_coop<16,1> (whole step incl. cross-GPU barriers and the peer-memory optimizer)"
                                     if net.peer is not None else "bpr_vec<16,1,true> (fused gather+loss+scatter-add)"),
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic_bytes(world), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": launch_bytes,
                          "avg_launch_ms": fb_mean_ms,
                          "note": "1536 B/triplet x 16384 (+ 32 B x 623744 table elements for the Adam phase at N=1); the "
@@ -420,7 +431,23 @@ def secondary_measurements(dev):
     o = torch.empty(B, device=dev); l = torch.empty(1, device=dev)
     s = timed(lambda: net.train_on_batch(u, i, y, out=o, loss_out=l), 50)
     out["neumf_train"] = {"value": B / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
-                          "config": "NeuMF F=32 (MLP 64-32-16-8, BN, dropout 0.2, MSE), ML-1M tables, batch 16384, Keras Adam"}
+                          "config": "NeuMF F=32 (MLP 64-32-16-8, BN, dropout 0.2, MSE), ML-1M tables, batch 16384, Keras Adam, "
+                                    "fp32 on the CUDA cores (csrc/neumf2.cu)"}
+    del net
+    for E, tag in ((32, "neumf_train_tc"), (64, "neumf64_train_tc")):
+        Bn = 65536
+        net = NeuMFNet(U, I, E, dropout=0.2, device=dev, tensor_cores=True)
+        u = torch.randint(0, U, (Bn,), generator=g, device=dev, dtype=torch.int32)
+        i = torch.randint(0, I, (Bn,), generator=g, device=dev, dtype=torch.int32)
+        y = (torch.rand(Bn, generator=g, device=dev) < 0.2).float()
+        o = torch.empty(Bn, device=dev); l = torch.empty(1, device=dev)
+        s = timed(lambda: net.train_on_batch(u, i, y, out=o, loss_out=l), 30)
+        flops = 3 * 2 * (2 * E * E + E * E // 2 + E * E // 8 + E // 4 + 1)      # fwd + two backward products per Dense layer
+        out[tag] = {"value": Bn / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
+                    "mlp_tflops": flops * Bn / s / 1e12,
+                    "config": f"NeuMF F={E} (MLP {2 * E}-{E}-{E // 2}-{E // 4}, BN, dropout 0.2, MSE), ML-1M tables, batch {Bn}, "
+                              f"Keras Adam, Dense products on tcgen05 (TF32 operands, fp32 accumulation; csrc/neumf_tc.cu)"}
+        del net
     users = list(range(U)); items = list(range(I))
     tt = TwoTowerModel(128, I, U, "u", "i", users, items, semb=128, device=dev)
     tt.compile("Adagrad", learningRate=0.1)
