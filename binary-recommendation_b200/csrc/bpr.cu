@@ -348,12 +348,14 @@ __global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParam
       const int G = P.world, me = P.rank;
       const uint32_t ep = P.dp_sync[3] + uint32_t(s) + 1u;      // dp_sync[3]: epochs completed before this launch
       uint32_t* my_flags = P.peer_flags[me];
-      if (blockIdx.x == 0 && threadIdx.x < G) {                 // barrier A: every rank's gradients are complete
+      // barrier A: every rank's gradients are complete.  Block 0 posts this rank's arrival on every peer; EVERY block
+      // then polls this rank's own flag block (local L2), which saves a second grid-wide barrier
+      if (blockIdx.x == 0 && threadIdx.x < G) {
         __threadfence_system();
         coop_st_release_sys(P.peer_flags[threadIdx.x] + me, ep);
-        coop_spin_sys(my_flags + threadIdx.x, ep, P.dp_sync + 4);
       }
-      grid.sync();
+      if (threadIdx.x < G) coop_spin_sys(my_flags + threadIdx.x, ep, P.dp_sync + 4);
+      __syncthreads();
       coop_stamp(P, s, 2);
       if (!stager) {
         const int64_t lo = P.arena_n4 * me / G, hi = P.arena_n4 * (me + 1) / G;
@@ -378,9 +380,9 @@ __global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParam
       if (blockIdx.x == 0 && threadIdx.x < G) {                 // barrier B: every rank's slice is final, reads of my g are done
         __threadfence_system();
         coop_st_release_sys(P.peer_flags[threadIdx.x] + G + me, ep);
-        coop_spin_sys(my_flags + G + threadIdx.x, ep, P.dp_sync + 4);
       }
-      grid.sync();
+      if (threadIdx.x < G) coop_spin_sys(my_flags + G + threadIdx.x, ep, P.dp_sync + 4);
+      __syncthreads();
       coop_stamp(P, s, 5);
       // all-gather by PULL: remote loads complete when their data arrives, so nothing has to wait for NVLink write
       // acknowledgements (pushing the slices and fencing them system-wide cost ~8 us per step); zero my g meanwhile
