@@ -461,7 +461,22 @@ def secondary_measurements(dev):
 
     s = timed(tt_step, 50)
     out["twotower_train"] = {"value": Bt / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
-                             "config": "two-tower E=S=128, in-batch softmax batch 1000 (twoTower.py:292), Adagrad 0.1, fp32"}
+                             "config": "two-tower E=S=128, in-batch softmax batch 1000 (twoTower.py:292), Adagrad 0.1, fp32 SGEMM"}
+    for Bt2, tag in ((1000, "twotower_train_tc"), (8192, "twotower_train_tc_b8192")):
+        tt2 = TwoTowerModel(128, I, U, "u", "i", users, items, semb=128, device=dev, tensor_cores=True)
+        tt2.compile("Adagrad", learningRate=0.1)
+        uid2 = torch.randint(2, U + 2, (Bt2,), generator=g, device=dev, dtype=torch.int32)
+        iid2 = torch.randint(2, I + 2, (Bt2,), generator=g, device=dev, dtype=torch.int32)
+
+        def tt2_step():
+            tt2._step(uid2, iid2, None, True)
+            tt2.optimizer.apply([tt2.userTower.emb, tt2.itemTower.emb], dense=[tt2.userTower.dense, tt2.itemTower.dense])
+
+        s = timed(tt2_step, 30)
+        out[tag] = {"value": Bt2 / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
+                    "config": f"two-tower E=S=128, in-batch softmax batch {Bt2}, Adagrad 0.1, every Dense / in-batch product on "
+                              f"tcgen05 (TF32 operands, fp32 accumulation; csrc/gemm_tc.cu)"}
+        del tt2
     Q = torch.randn(U, 128, generator=g, device=dev); Cm = torch.randn(I, 128, generator=g, device=dev)
     idx = H.BruteForceIndex(10).index(Cm)
     s = timed(lambda: idx(Q), 50)

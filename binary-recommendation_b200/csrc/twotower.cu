@@ -101,6 +101,32 @@ int sgemm(brk_ctx* ctx, cudaStream_t st, const float* A, const float* B, float* 
   return 0;
 }
 
+// out[n] += sum_m X[m][n]: bias gradients (ones^T dz) without a degenerate M = 1 product
+__global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ X, int M, int N, int ld, float* __restrict__ out) {
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  const int m0 = blockIdx.y * 64, m1 = min(M, m0 + 64);
+  if (n >= N) return;
+  float s = 0.f;
+  for (int m = m0; m < m1; ++m) s += __ldg(X + int64_t(m) * ld + n);
+  atomicAdd(out + n, s);
+}
+
+}  // namespace
+int brk_gemm_tf32_impl(brk_ctx* ctx, const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
+                       int ldb, int ldc, int trans_a, int trans_b, float alpha, int accumulate, bool allow_split,
+                       cudaStream_t st);
+namespace {
+
+// product dispatcher: tensor cores (TF32 operands) when asked for and the operands allow 16-byte loads, else fp32 SGEMM
+int gemm(brk_ctx* ctx, cudaStream_t st, int tcore, const float* A, const float* B, float* C, const float* bias, int M, int N,
+         int K, int lda, int ldb, int ldc, int ta, int tb, float alpha, int accumulate, bool allow_split) {
+  if (tcore) {
+    const int rc = brk_gemm_tf32_impl(ctx, A, B, C, bias, M, N, K, lda, ldb, ldc, ta, tb, alpha, accumulate, allow_split, st);
+    if (rc != BRK_E_ALIGN) return rc;
+  }
+  return sgemm(ctx, st, A, B, C, bias, M, N, K, lda, ldb, ldc, ta, tb, alpha, accumulate, allow_split);
+}
+
 // One CTA per row of the [B,B] score matrix: accidental-hit masking, log-sum-exp, loss, and in place
 // P = softmax - I (the gradient of the SUM-reduced cross-entropy w.r.t. the logits).
 constexpr float kMinFloatOver100 = -3.4028234663852886e36f;     // np.finfo(np.float32).min / 100
@@ -179,21 +205,29 @@ extern "C" int brk_sgemm(brk_ctx* ctx, const float* A, const float* B, float* C,
                true);
 }
 
+static int tower_forward(brk_ctx* ctx, const brk_tower* t, const int32_t* ids, int64_t n, float* emb_out, float* out,
+                         int tcore, void* stream) {
+  int rc = brk_gather_rows(ctx, t->emb.w, t->emb.rows, t->E, ids, n, emb_out, stream);
+  if (rc) return rc;
+  const float* W = t->dense.w;                       // [E, S] Keras kernel, then bias [S]
+  return gemm(ctx, (cudaStream_t)stream, tcore, emb_out, W, out, W + int64_t(t->E) * t->S, int(n), t->S, t->E, t->E, t->S,
+              t->S, 0, 0, 1.f, 0, false);
+}
+
 extern "C" int brk_tower_forward(brk_ctx* ctx, const brk_tower* t, const int32_t* ids, int64_t n, float* emb_out,
                                  float* out, void* stream) {
   BRK_REQUIRE(ctx && t && ids && emb_out && out, BRK_E_ARG, "brk_tower_forward: null argument");
   BRK_REQUIRE(t->emb.w && t->dense.w && t->E > 0 && t->S > 0 && n > 0, BRK_E_ARG, "brk_tower_forward: bad tower");
-  int rc = brk_gather_rows(ctx, t->emb.w, t->emb.rows, t->E, ids, n, emb_out, stream);
-  if (rc) return rc;
-  const float* W = t->dense.w;                       // [E, S] Keras kernel, then bias [S]
-  return sgemm(ctx, (cudaStream_t)stream, emb_out, W, out, W + int64_t(t->E) * t->S, int(n), t->S, t->E, t->E, t->S,
-               t->S, 0, 0, 1.f, 0, false);
+  return tower_forward(ctx, t, ids, n, emb_out, out, 0, stream);
 }
 
 extern "C" int brk_twotower_step(brk_ctx* ctx, const brk_tower* user, const brk_tower* item, const int32_t* u,
                                  const int32_t* i, const int32_t* cand_ids, const float* labels, int64_t batch,
                                  int32_t mode, int32_t training, const brk_twotower_workspace* ws, float* loss_out,
                                  void* stream) {
+  // mode bit 8 (0x100): Dense / in-batch products on the tensor cores (TF32 operands, gemm_tc.cu)
+  const int tcore = (mode & 0x100) ? 1 : 0;
+  mode &= 0xFF;
   BRK_REQUIRE(ctx && user && item && u && i && ws, BRK_E_ARG, "brk_twotower_step: null argument");
   BRK_REQUIRE(user->S == item->S && batch > 0 && batch < (1 << 30), BRK_E_ARG, "brk_twotower_step: S %d vs %d, batch %lld",
               user->S, item->S, (long long)batch);
@@ -206,17 +240,20 @@ extern "C" int brk_twotower_step(brk_ctx* ctx, const brk_tower* user, const brk_
   const int B = int(batch), S = user->S, Eu = user->E, Ei = item->E;
   int rc;
   // towers: q = Eu[u] Wu + bu, c = Ei[i] Wi + bi
-  if ((rc = brk_tower_forward(ctx, user, u, batch, ws->eu, ws->q, stream))) return rc;
-  if ((rc = brk_tower_forward(ctx, item, i, batch, ws->ei, ws->c, stream))) return rc;
+  if ((rc = tower_forward(ctx, user, u, batch, ws->eu, ws->q, tcore, stream))) return rc;
+  if ((rc = tower_forward(ctx, item, i, batch, ws->ei, ws->c, tcore, stream))) return rc;
   if (mode == 0) {
     // scores = q c^T; softmax CE (SUM) with accidental-hit removal; in place P = softmax - I
-    if ((rc = sgemm(ctx, st, ws->q, ws->c, ws->scores, nullptr, B, B, S, S, S, B, 0, 1, 1.f, 0, false))) return rc;
+    if ((rc = gemm(ctx, st, tcore, ws->q, ws->c, ws->scores, nullptr, B, B, S, S, S, B, 0, 1, 1.f, 0, false))) return rc;
     inbatch_softmax_kernel<<<B, 256, 0, st>>>(ws->scores, cand_ids, B, training, ws->acc);
     BRK_LAUNCH_CHECK();
     if (training) {
-      // dq = P c  [B,S];  dc = P^T q  [B,S]
-      if ((rc = sgemm(ctx, st, ws->scores, ws->c, ws->dq, nullptr, B, S, B, B, S, S, 0, 0, 1.f, 0, false))) return rc;
-      if ((rc = sgemm(ctx, st, ws->scores, ws->q, ws->dc, nullptr, B, S, B, B, S, S, 1, 0, 1.f, 0, false))) return rc;
+      // dq = P c  [B,S];  dc = P^T q  [B,S]: few output tiles (B/64 x S/64) and a long K = B, so the products are
+      // split along K across CTAs and accumulated with REDs into zeroed outputs
+      BRK_CUDA(cudaMemsetAsync(ws->dq, 0, size_t(B) * S * sizeof(float), st));
+      BRK_CUDA(cudaMemsetAsync(ws->dc, 0, size_t(B) * S * sizeof(float), st));
+      if ((rc = gemm(ctx, st, tcore, ws->scores, ws->c, ws->dq, nullptr, B, S, B, B, S, S, 0, 0, 1.f, 1, true))) return rc;
+      if ((rc = gemm(ctx, st, tcore, ws->scores, ws->q, ws->dc, nullptr, B, S, B, B, S, S, 1, 0, 1.f, 1, true))) return rc;
     }
   } else {
     rowdot_bce_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(ws->q, ws->c, labels, B, S, training, ws->dq, ws->dc, ws->acc);
@@ -235,12 +272,13 @@ extern "C" int brk_twotower_step(brk_ctx* ctx, const brk_tower* user, const brk_
   for (int k = 0; k < 2; ++k) {
     float* gW = tw[k]->dense.g;
     float* gb = gW + int64_t(E[k]) * S;
-    if ((rc = sgemm(ctx, st, e[k], dz[k], gW, nullptr, E[k], S, B, E[k], S, S, 1, 0, 1.f, 1, true))) return rc;
-    if ((rc = sgemm(ctx, st, ws->ones, dz[k], gb, nullptr, 1, S, B, 1, S, S, 1, 0, 1.f, 1, true))) return rc;
+    if ((rc = gemm(ctx, st, tcore, e[k], dz[k], gW, nullptr, E[k], S, B, E[k], S, S, 1, 0, 1.f, 1, true))) return rc;
+    colsum_kernel<<<dim3((S + 127) / 128, (B + 63) / 64), 128, 0, st>>>(dz[k], B, S, S, gb);
+    BRK_LAUNCH_CHECK();
     float* de = k == 0 ? ws->eu : ws->ei;                 // reuse the gathered-row buffer for de
     // de = dz W^T: W stored [E,S] = "B stored [N,K]" with N = E, K = S  (tb = 1)
     // (the dW product above has already consumed e)
-    if ((rc = sgemm(ctx, st, dz[k], tw[k]->dense.w, de, nullptr, B, E[k], S, S, S, E[k], 0, 1, 1.f, 0, false))) return rc;
+    if ((rc = gemm(ctx, st, tcore, dz[k], tw[k]->dense.w, de, nullptr, B, E[k], S, S, S, E[k], 0, 1, 1.f, 0, false))) return rc;
     if ((rc = brk_scatter_add_rows(ctx, tw[k]->emb.g, tw[k]->emb.rows, E[k], ids[k], batch, de, tw[k]->emb.touched, 0,
                                    stream)))
       return rc;

@@ -64,11 +64,13 @@ class Tower:
 
 class TwoTowerModel:
     def __init__(self, embedDim, nbrItem, nbrUser, userKey, itemKey, usersId, itemsId, eval_batch_size=8000,
-                 loss=None, rdZero=False, resKey=None, semb=100, seed=42, device=None):
+                 loss=None, rdZero=False, resKey=None, semb=100, seed=42, device=None, tensor_cores=False):
         self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
         self.embedDim, self.nbrItem, self.nbrUser = embedDim, nbrItem, nbrUser
         self.userKey, self.itemKey, self.resKey = userKey, itemKey, resKey
         self.eval_batch_size, self.rdZero, self.semb = eval_batch_size, rdZero, semb
+        # tensor_cores: Dense / in-batch products on tcgen05 with TF32 operands (csrc/gemm_tc.cu); fp32 FMA otherwise
+        self.tensor_cores = bool(tensor_cores)
         self.userTowerIn = StringLookup(usersId)
         self.itemTowerIn = StringLookup(itemsId)
         rng = np.random.Generator(np.random.Philox(key=seed))
@@ -120,7 +122,8 @@ class TwoTowerModel:
         ws = self._workspace(B)
         ut, it = self.userTower.c_struct(), self.itemTower.c_struct()
         N.check(N.lib().brk_twotower_step(N.ctx(self.device), C.byref(ut), C.byref(it), N.ptr(u), N.ptr(i), N.ptr(i),
-                                          N.ptr(labels) if labels is not None else None, B, 1 if self.rdZero else 0,
+                                          N.ptr(labels) if labels is not None else None, B,
+                                          (1 if self.rdZero else 0) | (0x100 if self.tensor_cores else 0),
                                           1 if training else 0, C.byref(ws), N.ptr(loss_out), N.stream_ptr()),
                 "brk_twotower_step")
         return loss_out

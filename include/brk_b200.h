@@ -297,7 +297,11 @@ int brk_bpr_train_steps_dp(brk_ctx* ctx, const brk_table* user, const brk_table*
  *     training != 0 additionally accumulates every gradient (emb.g rows, dense.g) for the optimizer.
  * Workspace (caller-owned, floats): eu [B,Eu], ei [B,Ei], q, c, dq, dc [B,S], scores [B,B] (mode 0),
  * ones [B] filled with 1.0, acc 1 double zero-initialised.
- *   brk_sgemm : C (+)= alpha opA(A) opB(B) (+ bias); trans_a: A stored [K,M]; trans_b: B stored [N,K]. */
+ *   brk_sgemm : C (+)= alpha opA(A) opB(B) (+ bias); trans_a: A stored [K,M]; trans_b: B stored [N,K]; fp32 FMA.
+ *   brk_gemm_tf32 : the same product on tcgen05 with TF32 operands and fp32 accumulation in TMEM (gemm_tc.cu);
+ *     needs 16-byte aligned operands with leading dimensions that are multiples of 4 (else BRK_E_ALIGN).
+ *   brk_twotower_step mode bit 0x100 routes every Dense / in-batch product through brk_gemm_tf32 (falling back to
+ *     the fp32 product where the alignment rule fails); results then agree with the fp32 path to TF32 rounding. */
 typedef struct brk_tower {
   brk_table emb, dense;
   int32_t E, S;
@@ -309,6 +313,9 @@ typedef struct brk_twotower_workspace {
 int brk_sgemm(brk_ctx* ctx, const float* A, const float* B, float* C, const float* bias, int32_t M,
               int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t trans_a, int32_t trans_b,
               float alpha, int32_t accumulate, void* stream);
+int brk_gemm_tf32(brk_ctx* ctx, const float* A, const float* B, float* C, const float* bias, int32_t M,
+                  int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t trans_a, int32_t trans_b,
+                  float alpha, int32_t accumulate, void* stream);
 int brk_tower_forward(brk_ctx* ctx, const brk_tower* t, const int32_t* ids, int64_t n, float* emb_out,
                       float* out, void* stream);
 int brk_twotower_step(brk_ctx* ctx, const brk_tower* user, const brk_tower* item, const int32_t* u,

@@ -108,3 +108,50 @@ def test_neumf_tensor_core_training_tracks_fp32_and_eval(dev):
     p0, _ = ref.predict_on_batch(ud, idd, yd)
     p1, _ = net.predict_on_batch(ud, idd, yd)
     np.testing.assert_allclose(p1.cpu().numpy(), p0.cpu().numpy(), rtol=1e-2, atol=1e-3)
+
+
+# ---- general TF32 product (csrc/gemm_tc.cu) and the two-tower step on it -------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (1000, 128, 128), (1000, 1000, 128), (1000, 128, 1000), (128, 128, 1000),
+                                   (300, 64, 96), (77, 200, 40)])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_tf32_all_layouts_exact_on_representable_inputs(dev, M, N, K, ta, tb):
+    from binrec_b200 import _native as Nn
+    rng = np.random.default_rng(M + N + K + 2 * ta + tb)
+    pad4 = lambda x: (x + 3) // 4 * 4
+    Al = (rng.integers(-8, 9, size=(M, K)) / 8.0).astype(np.float32)
+    Bl = (rng.integers(-8, 9, size=(K, N)) / 8.0).astype(np.float32)
+    bias = (rng.integers(-8, 9, size=N) / 4.0).astype(np.float32)
+    # storage with padded leading dimensions (multiples of 4 floats)
+    if ta: As = np.zeros((K, pad4(M)), np.float32); As[:, :M] = Al.T
+    else:  As = np.zeros((M, pad4(K)), np.float32); As[:, :K] = Al
+    if tb: Bs = np.zeros((N, pad4(K)), np.float32); Bs[:, :K] = Bl.T
+    else:  Bs = np.zeros((K, pad4(N)), np.float32); Bs[:, :N] = Bl
+    Ad, Bd, bd = (torch.from_numpy(x).to(dev) for x in (As, Bs, bias))
+    C0 = (rng.integers(-4, 5, size=(M, N)) / 2.0).astype(np.float32)
+    for accumulate in (0, 1):
+        Cd = torch.from_numpy(C0.copy()).to(dev)
+        Nn.check(Nn.lib().brk_gemm_tf32(Nn.ctx(dev), Nn.ptr(Ad), Nn.ptr(Bd), Nn.ptr(Cd), Nn.ptr(bd) if not accumulate else None,
+                                        M, N, K, As.shape[1], Bs.shape[1], N, ta, tb, 0.5, accumulate, Nn.stream_ptr()),
+                 "brk_gemm_tf32")
+        ref = 0.5 * (Al.astype(np.float64) @ Bl.astype(np.float64))
+        ref = ref + (C0 if accumulate else bias[None, :])
+        assert np.array_equal(Cd.cpu().numpy(), ref.astype(np.float32)), (accumulate,)
+
+
+def test_twotower_tensor_core_step_matches_fp32_path(dev):
+    """TF32 tolerance for the two-tower step: loss rtol 2e-3; gradients max error <= 2 % of max|g|, Frobenius <= 2 %."""
+    from binrec_b200.twoTower import TwoTowerModel
+    U, I, B = 500, 300, 1000
+    mk = lambda tcf: TwoTowerModel(128, I, U, "u", "i", list(range(U)), list(range(I)), semb=128, device=dev, tensor_cores=tcf)
+    a, b = mk(False), mk(True)
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    uid = torch.randint(2, U + 2, (B,), generator=g, device=dev, dtype=torch.int32)
+    iid = torch.randint(2, I + 2, (B,), generator=g, device=dev, dtype=torch.int32)
+    la = a._step(uid, iid, None, True); lb = b._step(uid, iid, None, True)
+    np.testing.assert_allclose(lb.item(), la.item(), rtol=2e-3)
+    for ta, tb, name in ((a.userTower.emb, b.userTower.emb, "Eu"), (a.itemTower.emb, b.itemTower.emb, "Ei"),
+                         (a.userTower.dense, b.userTower.dense, "Wu"), (a.itemTower.dense, b.itemTower.dense, "Wi")):
+        g0, g1 = ta.g.cpu().numpy(), tb.g.cpu().numpy()
+        scale = np.abs(g0).max()
+        assert np.abs(g1 - g0).max() <= 0.02 * scale, name
+        assert np.linalg.norm((g1 - g0).ravel()) <= 0.02 * np.linalg.norm(g0.ravel()), name
