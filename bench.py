@@ -44,7 +44,7 @@ def load_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.2):
+    def __init__(self, index, period=0.05):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -290,7 +290,7 @@ def product_arm(args):
         loss = net.train_on_batch(du, dp, dn)
         hloss[k:k + 1].copy_(loss, non_blocking=True)
 
-    if world == 1:
+    if world == 1 or net.peer is not None:
         # one C call enqueues K x (H2D ids, sampler, fused step, Adam, loss D2H): BPRNet.train_steps_from_host
         # host input in the loader's batch-major layout [n_batches, 2, BATCH] (pinned): one H2D per step
         packed = BPRNet.pack_host_batches(users[:n_batches * BATCH], items[:n_batches * BATCH], BATCH)
@@ -301,13 +301,15 @@ def product_arm(args):
         net.train_steps_from_host(packed, None, order, BATCH, 7, 1, hloss[W:W + K])
         e1.record()
         barrier()
+        e2e_wall = time.perf_counter() - t0
         e2e_launches = (K + 15) // 16                      # one cooperative launch per chunk of 16 steps
-        # zero-copy variant: ids stay in pinned host memory, ONE launch, the kernel pulls them over PCIe itself
-        net.train_steps_mapped(hu, hp, order[:W], BATCH, 7, 1, hloss[:W])
-        barrier()
-        e2.record(); net.train_steps_mapped(hu, hp, order, BATCH, 7, 1, hloss[W:W + K]); e3.record()
-        barrier()
-        mapped_ms = e2.elapsed_time(e3)
+        if world == 1:
+            # zero-copy variant: ids stay in pinned host memory, ONE launch, the kernel pulls them over PCIe itself
+            net.train_steps_mapped(hu, hp, order[:W], BATCH, 7, 1, hloss[:W])
+            barrier()
+            e2.record(); net.train_steps_mapped(hu, hp, order, BATCH, 7, 1, hloss[W:W + K]); e3.record()
+            barrier()
+            mapped_ms = e2.elapsed_time(e3)
     else:
         for k in range(W):
             e2e_step(k)
@@ -319,7 +321,7 @@ def product_arm(args):
         e1.record()
         barrier()
         e2e_launches = 3 * K
-    e2e_wall = time.perf_counter() - t0
+        e2e_wall = time.perf_counter() - t0
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * e2e_wall)
     clocks = sampler.stop()
     assert np.isfinite(hloss[W:W + K].numpy()).all()
@@ -373,8 +375,9 @@ def product_arm(args):
                              "ids (128 KiB block of the pinned batch-major host array; copy stream, ring of staging "
                              "slots); steps run in cooperative launches of 16 (Philox negatives drawn in-kernel, fused "
                              "step, Adam); the 16 step losses of a launch return in one cudaMemcpyAsync D2H; one host "
-                             "sync per K steps") if world == 1 else
-                            "per step: H2D ids, Philox negatives, fused fwd/bwd, fused peer optimizer, loss D2H"},
+                             "sync per K steps" + ("" if world == 1 else "; every rank feeds its own batches, the launches are the "
+                                                   "data-parallel cooperative kernel")) if (world == 1 or net.peer is not None) else
+                            "per step: H2D ids, Philox negatives, fused fwd/bwd, NCCL all-reduce, Adam, loss D2H"},
             "gpu_launches": (1 if (world == 1 or net.peer is not None) else 2) * K,   # one cooperative step kernel per step
             "clocks": clocks,
         }

@@ -150,6 +150,7 @@ class BPRNet:
             total, batch_size, stride, idx, k, sampler_seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, self.numItem,
             N.ptr(pr["indptr"]), N.ptr(pr["sitems"]), self.optimizer.h, 1 if self.optimizer.sparse == "lazy" else 0,
             N.ptr(self.optimizer.state), N.ptr(self._stage), N.ptr(d_losses), C.c_void_p(losses_host.data_ptr()),
+            C.cast(C.byref(self.peer.desc), C.c_void_p) if self.peer is not None else None,
             N.stream_ptr()), "brk_bpr_train_steps_host")
         self._d_losses = d_losses            # keep alive until the stream has consumed it
         return losses_host

@@ -84,7 +84,7 @@ SIGNATURES = {
                                       C.POINTER(C.c_int64), _I32, brk_adam_hyper, _I32, _P, _P, _P]),
     "brk_bpr_train_steps_host": (C.c_int, [_P, C.POINTER(brk_table), C.POINTER(brk_table), _P, _P, _I64, _I64, _I64,
                                            C.POINTER(C.c_int64), _I32, _U32, _U32, _I32, _P, _P, brk_adam_hyper, _I32,
-                                           _P, _P, _P, _P, _P]),
+                                           _P, _P, _P, _P, _P, _P]),
     "brk_bpr_host_stage_ints": (C.c_int64, [_I64]),
     "brk_bpr_train_steps_mapped": (C.c_int, [_P, C.POINTER(brk_table), C.POINTER(brk_table), _P, _P, _I64, _I64,
                                              C.POINTER(C.c_int64), _I32, _U32, _U32, _I32, _P, _P, brk_adam_hyper,

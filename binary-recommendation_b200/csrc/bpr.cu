@@ -644,7 +644,7 @@ extern "C" int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, con
                                         int64_t host_batch_stride, const int64_t* batch_index_host, int32_t n_steps, uint32_t seed, uint32_t epoch,
                                         int32_t num_items, const int64_t* csr_indptr, const int32_t* csr_items,
                                         brk_adam_hyper h, int32_t lazy_adam, int64_t* step_dev, int32_t* d_stage,
-                                        float* d_losses, float* losses_host, void* stream) {
+                                        float* d_losses, float* losses_host, const brk_dp_peer* dp, void* stream) {
   BRK_REQUIRE(ctx && user && item && u_host && p_host && batch_index_host && step_dev && d_stage && d_losses &&
                   csr_indptr && csr_items, BRK_E_ARG, "brk_bpr_train_steps_host: null argument");
   BRK_REQUIRE(total > 0 && batch > 0 && n_steps >= 0 && num_items > 0, BRK_E_ARG,
@@ -675,7 +675,11 @@ extern "C" int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, con
     ctx->copy_ready = 1;
   }
   cudaStream_t cs = ctx->copy_stream;
-  const bool coop_ok = coop_eligible(user, item, lazy_adam);
+  const bool use_dp = dp != nullptr && dp->world > 1;
+  // data-parallel mode: the tables are views into the peer arenas (their Adam moments live in `dp`, sharded)
+  const bool coop_ok = use_dp ? ((user->d & 3) == 0 && user->d <= 128 && !lazy_adam) : coop_eligible(user, item, lazy_adam);
+  BRK_REQUIRE(!use_dp || (coop_ok && item->w == user->w + user->rows * user->d && item->g == user->g + user->rows * user->d),
+              BRK_E_ARG, "brk_bpr_train_steps_host: data-parallel mode needs adjacent arena views, d %% 4 == 0, d <= 128");
   brk_table tabs[2] = {*user, *item};
   const int n_chunks = (n_steps + kChunk - 1) / kChunk;
   auto count_of = [&](int k) { const int64_t off = batch_index_host[k] * batch; return (off + batch <= total) ? batch : total - off; };
@@ -727,7 +731,7 @@ extern "C" int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, con
       }
       CoopSampler smp{csr_indptr, csr_items, seed, epoch, uint32_t(num_items)};
       int rc = launch_coop_steps(ctx, user, item, d_stage, d_stage + batch, nullptr, steps, k1 - k0, batch, h, step_dev,
-                                 d_losses + k0, st, &smp);
+                                 d_losses + k0, st, &smp, use_dp ? dp : nullptr);
       if (rc) return rc;
     } else {
       // generic widths / lazy Adam: separate sampler, fused fwd/bwd and optimizer launches (negatives in the

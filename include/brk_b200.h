@@ -50,6 +50,8 @@ typedef struct brk_table {
   int32_t   _pad;
 } brk_table;
 
+struct brk_dp_peer;   /* defined below: peer-memory descriptor of the data-parallel optimizer */
+
 typedef struct brk_adam_hyper {
   float lr, beta1, beta2, eps;   /* Keras defaults: 1e-3, 0.9, 0.999, 1e-7 */
 } brk_adam_hyper;
@@ -129,14 +131,16 @@ int brk_bpr_train_steps(brk_ctx* ctx, const brk_table* user, const brk_table* it
  * host_batch_stride: int32 elements between consecutive batches in u_host / p_host (0 = batch, i.e. two flat
  * arrays); with the batch-major layout [n_batches][2][batch] (p_host == u_host + batch, stride 2*batch;
  * the last block padded to full size) each step's ids move with ONE copy.
- * d_stage: device int32 scratch [brk_bpr_host_stage_ints(batch)]; d_losses: device [n_steps]. */
+ * d_stage: device int32 scratch [brk_bpr_host_stage_ints(batch)]; d_losses: device [n_steps].
+ * dp (may be NULL): mirrored data parallelism as in brk_bpr_train_steps_dp -- every rank feeds its own host
+ * batches, all ranks call with the same n_steps, full batches only. */
 int64_t brk_bpr_host_stage_ints(int64_t batch);
 int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, const brk_table* item,
                              const int32_t* u_host, const int32_t* p_host, int64_t total, int64_t batch,
                              int64_t host_batch_stride, const int64_t* batch_index_host, int32_t n_steps, uint32_t seed, uint32_t epoch,
                              int32_t num_items, const int64_t* csr_indptr, const int32_t* csr_items,
                              brk_adam_hyper h, int32_t lazy_adam, int64_t* step_dev, int32_t* d_stage,
-                             float* d_losses, float* losses_host, void* stream);
+                             float* d_losses, float* losses_host, const struct brk_dp_peer* dp, void* stream);
 /* Zero-copy variant: u_host / p_host / losses_host are MAPPED page-locked host memory; ONE cooperative
  * launch runs all n_steps, every step's kernel phase pulls that step's ids over PCIe (8*batch bytes),
  * draws the negatives, trains, and stores the loss straight into losses_host[k].  Exact Keras Adam

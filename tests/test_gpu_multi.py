@@ -48,7 +48,19 @@ def _worker(rank, world, port, ret):
         y = (rng2.random(world * B) < 0.3).astype(np.float32)
         lo, hi = D.local_slice(world * B)
         nm.train_on_batch(*(torch.from_numpy(x[lo:hi]).to(dev) for x in (u, it, y)))
+        # host-fed data-parallel steps: every rank feeds its own batches from pinned host memory, negatives drawn in-kernel
+        rngp = np.random.default_rng(8)
+        key = np.unique(rngp.integers(0, U * I, 3000))
+        pu, pi = (key // I).astype(np.int32), (key % I).astype(np.int32)
+        perm = rngp.permutation(len(pu)); pu, pi = pu[perm], pi[perm]
+        net2 = BPRNet(U, I, d, seed=43, device=dev)
+        net2.set_training_pairs(pu, pi)
+        packed = BPRNet.pack_host_batches(pu, pi, B)
+        order = [rank, 2 + rank, 4 + rank]
+        hl = net2.train_steps_from_host(packed, None, order, B, 7, 2)
+        torch.cuda.synchronize()
         ret[rank] = dict(user=net.user.w.cpu().numpy(), item=net.item.w.cpu().numpy(), losses=losses,
+                         hf_user=net2.user.w.cpu().numpy(), hf_item=net2.item.w.cpu().numpy(), hf_losses=hl.numpy().copy(),
                          tv=tv.cpu().numpy(), ti=ti.cpu().numpy(), neumf_W1=nm.param("W1").cpu().numpy(),
                          neumf_uMLP=nm.uMLP.w.cpu().numpy())
     finally:
@@ -80,6 +92,25 @@ def test_mirrored_bpr_neumf_and_sharded_topk_two_gpus():
     for r in range(world):
         np.testing.assert_allclose(ret[r]["user"], orc.user, rtol=1e-5, atol=2e-6)
         np.testing.assert_allclose(ret[r]["item"], orc.item, rtol=1e-5, atol=2e-6)
+    # host-fed DP path vs the oracle on the union of both ranks' batches, with the oracle's sampler
+    from oracle import philox as OP
+    rngp = np.random.default_rng(8)
+    key = np.unique(rngp.integers(0, U * I, 3000))
+    pu, pi = (key // I).astype(np.int32), (key % I).astype(np.int32)
+    perm = rngp.permutation(len(pu)); pu, pi = pu[perm], pi[perm]
+    indptr, sitems = OP.build_csr(pu, pi, U)
+    orc2 = OB.BPROracle(U, I, d, seed=43)
+    for step in range(3):
+        us, ps, ns = [], [], []
+        for r in range(world):
+            b = 2 * step + r
+            sl = slice(b * B, (b + 1) * B)
+            us.append(pu[sl]); ps.append(pi[sl]); ns.append(OP.bpr_negatives(pu[sl], 7, 2, I, indptr, sitems, first_index=b * B))
+        orc2.step(np.concatenate(us), np.concatenate(ps), np.concatenate(ns))
+    for r in range(world):
+        np.testing.assert_allclose(ret[r]["hf_user"], orc2.user, rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(ret[r]["hf_item"], orc2.item, rtol=1e-5, atol=2e-6)
+        assert np.isfinite(ret[r]["hf_losses"]).all()
     assert np.array_equal(ret[0]["user"], ret[1]["user"]) and np.array_equal(ret[0]["neumf_W1"], ret[1]["neumf_W1"])
     assert np.array_equal(ret[0]["neumf_uMLP"], ret[1]["neumf_uMLP"])
     Q = (np.random.default_rng(4).integers(-4, 5, size=(77, 64)) / 8.0).astype(np.float32)
