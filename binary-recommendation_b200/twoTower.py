@@ -164,15 +164,18 @@ class TwoTowerModel:
         """One fused forward/backward + Adagrad step; returns {"loss": device scalar} (twoTower.py:89-102).
         Under torch.distributed the replicas' SUM-reduced gradients are summed by one all-reduce per
         tower (MirroredStrategy sums per-replica gradients of a SUM-reduced loss)."""
+        u, i = self._ids(info)
+        return {"loss": self._train_ids(u, i, self._labels(info))}
+
+    def _train_ids(self, u, i, labels, loss_out=None):
         if self.optimizer is None:
             self.compile()
-        u, i = self._ids(info)
-        loss = self._step(u, i, self._labels(info), True)
+        loss = self._step(u, i, labels, True, loss_out)
         if D.world_size() > 1:
             for t in (self.userTower.emb, self.itemTower.emb, self.userTower.dense, self.itemTower.dense):
                 D.all_reduce_sum_(t.g)
         self.optimizer.apply([self.userTower.emb, self.itemTower.emb], dense=[self.userTower.dense, self.itemTower.dense])
-        return {"loss": loss}
+        return loss
 
     def test_step(self, info):
         u, i = self._ids(info)
@@ -181,11 +184,15 @@ class TwoTowerModel:
     def fit(self, dataset, epochs=1, verbose=0):
         """dataset: iterable of info dicts (batches), replayed every epoch like a cached tf.data set."""
         batches = list(dataset)
+        # string -> index lookups and H2D of the ids once per fit, not once per step and epoch (the reference caches
+        # its batched dataset too: trainSetCached, twoTower.py:197-198)
+        staged = [(self._ids(info), self._labels(info)) for info in batches]
         for e in range(epochs):
-            tot = 0.0
-            for info in batches:
-                tot += float(self.train_step(info)["loss"].item())
-            self.history["loss"].append(tot / max(len(batches), 1))
+            losses = torch.zeros(max(len(staged), 1), dtype=torch.float32, device=self.device)
+            for k, ((u, i), lab) in enumerate(staged):
+                self._train_ids(u, i, lab, losses[k:k + 1])
+            # one host sync per epoch: Keras reports the running mean of the per-batch losses
+            self.history["loss"].append(float(losses.double().sum().item()) / max(len(staged), 1))
             if verbose:
                 print(f"epoch {e + 1}: loss {self.history['loss'][-1]:.6f}")
         return self
