@@ -108,13 +108,19 @@ __device__ __forceinline__ void dense_pass(const TabList& tl, const Op& op) {
   }
 }
 
-// Row-sparse pass: warps scan the touched bitmask 32 words at a time, clear what they read and
-// update the flagged rows; a row is handled by `lpr` lanes as float4 chunks.
+// Row-sparse pass: warps scan the touched bitmask 32 words at a time, clear what they read, expand the set bits
+// into a per-warp row list in shared memory and update those rows; a row is handled by `lpr` lanes as float4
+// chunks and every lane group keeps kRowsInFlight rows' loads in flight (the pass is DRAM-latency bound: at
+// BASELINE.json configs[3] densities a warp finds 3-30 rows per 1024 scanned).
+constexpr int kRowsInFlight = 4;
+
 template <class Op, bool HAS_V>
 __device__ __forceinline__ void rows_pass(const TabList& tl, const Op& op) {
-  const int lane = threadIdx.x & 31;
+  __shared__ int32_t s_rows[kThreads / 32][1024];             // row offsets (relative to the chunk) per warp
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = (int64_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
   const int64_t n_warps = (int64_t(gridDim.x) * kThreads) >> 5;
+  int32_t* my_rows = s_rows[wib];
   for (int k = 0; k < tl.n; ++k) {
     const brk_table& t = tl.t[k];
     const bool vec = (t.d & 3) == 0 && brk_aligned16(t.w) && brk_aligned16(t.m) && brk_aligned16(t.g) &&
@@ -135,24 +141,65 @@ __device__ __forceinline__ void rows_pass(const TabList& tl, const Op& op) {
         word = t.touched[base + lane];
         if (word) t.touched[base + lane] = 0u;
       }
-      uint32_t active = __ballot_sync(0xffffffffu, word != 0u);
-      while (active) {
-        const int src = __ffs(active) - 1;
-        active &= active - 1;
-        const uint32_t w = __shfl_sync(0xffffffffu, word, src);
-        const int64_t row_base = (base + src) << 5;
-        const int cnt = __popc(w);
-        for (int j = 0; j < cnt; j += gpw) {
-          const int kth = j + grp;
-          if (kth < cnt) {
-            const int64_t row = row_base + __fns(w, 0, kth + 1);
-            for (int c = lane_in; c < chunks; c += lpr) {
-              if (vec) apply4<Op, HAS_V>(op, t.w, t.m, t.v, t.g, row * chunks + c);
-              else     apply1<Op, HAS_V>(op, t.w, t.m, t.v, t.g, row * chunks + c);
+      if (__ballot_sync(0xffffffffu, word != 0u) == 0u) continue;
+      // exclusive prefix sum of the per-lane popcounts -> each lane expands its word into the list
+      const int cnt = __popc(word);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int pos = incl - cnt;
+      uint32_t w = word;
+      while (w) {
+        const int bit = __ffs(w) - 1;
+        w &= w - 1;
+        my_rows[pos++] = lane * 32 + bit;
+      }
+      __syncwarp();
+      const int64_t row0 = base << 5;
+      if (vec && chunks <= lpr) {
+        // one float4 per lane and row: kRowsInFlight rows per group, loads first, then compute and store
+        for (int j0 = 0; j0 < total; j0 += gpw * kRowsInFlight) {
+          float4 w4[kRowsInFlight], m4[kRowsInFlight], v4[kRowsInFlight], g4[kRowsInFlight];
+          int64_t idx[kRowsInFlight];
+#pragma unroll
+          for (int q = 0; q < kRowsInFlight; ++q) {
+            const int j = j0 + q * gpw + grp;
+            idx[q] = -1;
+            if (j < total && lane_in < chunks) {
+              idx[q] = (row0 + my_rows[j]) * chunks + lane_in;
+              w4[q] = reinterpret_cast<const float4*>(t.w)[idx[q]];
+              m4[q] = reinterpret_cast<const float4*>(t.m)[idx[q]];
+              if (HAS_V) v4[q] = reinterpret_cast<const float4*>(t.v)[idx[q]];
+              g4[q] = reinterpret_cast<const float4*>(t.g)[idx[q]];
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < kRowsInFlight; ++q) {
+            if (idx[q] >= 0) {
+              float4 vv = HAS_V ? v4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+              op(w4[q].x, m4[q].x, vv.x, g4[q].x); op(w4[q].y, m4[q].y, vv.y, g4[q].y);
+              op(w4[q].z, m4[q].z, vv.z, g4[q].z); op(w4[q].w, m4[q].w, vv.w, g4[q].w);
+              reinterpret_cast<float4*>(t.w)[idx[q]] = w4[q];
+              reinterpret_cast<float4*>(t.m)[idx[q]] = m4[q];
+              if (HAS_V) reinterpret_cast<float4*>(t.v)[idx[q]] = vv;
+              reinterpret_cast<float4*>(t.g)[idx[q]] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
         }
+      } else {
+        for (int j = grp; j < total; j += gpw) {
+          const int64_t row = row0 + my_rows[j];
+          for (int c = lane_in; c < chunks; c += lpr) {
+            if (vec) apply4<Op, HAS_V>(op, t.w, t.m, t.v, t.g, row * chunks + c);
+            else     apply1<Op, HAS_V>(op, t.w, t.m, t.v, t.g, row * chunks + c);
+          }
+        }
       }
+      __syncwarp();
     }
   }
 }
