@@ -166,21 +166,31 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         if (x == 0x7fc12345u) thr = 0.f;
         return;
       }
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      // The scores are used straight out of the registers tcgen05.ld filled: copying them into a float array cost 32
+      // moves per 32 scores, more than the max-tree itself.  Only the last item tile can be ragged; it takes the
+      // generic path below.
+#define V(j) __uint_as_float(r[(j)])
       if (ragged) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (col0 + j >= P.I) v[j] = -CUDART_INF_F;
+        for (int j = 0; j < 32; ++j) scratch[j * kScratchStride] = V(j);
+#pragma unroll 1
+        for (int j = 0; j < 32; ++j) {
+          const float x = scratch[j * kScratchStride];
+          if (col0 + j < P.I && x > thr) {
+            topk_insert<K_CAP>(vals, ids, x, int32_t(col0 + j) + P.id_offset);
+            thr = vals[K_CAP - 1];
+          }
+        }
+        return;
       }
       // 4 independent FMNMX3 chains, one per group of 8 columns
       float gm[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        float m = fmaxf(fmaxf(v[8 * g], v[8 * g + 1]), v[8 * g + 2]);
-        m = fmaxf(fmaxf(m, v[8 * g + 3]), v[8 * g + 4]);
-        m = fmaxf(fmaxf(m, v[8 * g + 5]), v[8 * g + 6]);
-        gm[g] = fmaxf(m, v[8 * g + 7]);
+        float m = fmaxf(fmaxf(V(8 * g), V(8 * g + 1)), V(8 * g + 2));
+        m = fmaxf(fmaxf(m, V(8 * g + 3)), V(8 * g + 4));
+        m = fmaxf(fmaxf(m, V(8 * g + 5)), V(8 * g + 6));
+        gm[g] = fmaxf(m, V(8 * g + 7));
       }
       const float cmax = fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), gm[3]);
       if (cmax > thr) {
@@ -192,8 +202,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           if (gm[g] > thr) {
 #pragma unroll
             for (int j = 8 * g; j < 8 * g + 8; ++j) {
-              scratch[j * kScratchStride] = v[j];
-              mask |= (v[j] > thr) ? (1u << j) : 0u;
+              scratch[j * kScratchStride] = V(j);
+              mask |= (V(j) > thr) ? (1u << j) : 0u;
             }
           }
         }
@@ -208,6 +218,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           }
         }
       }
+#undef V
     };
 
     for (int t = 0; t < my_tiles; ++t) {
