@@ -100,6 +100,7 @@ SIGNATURES = {
                                  C.POINTER(brk_neumf_workspace), _P, _P, _P]),
     "brk_neumf_step_sharded": (C.c_int, [_P, C.POINTER(brk_neumf_model), C.POINTER(brk_neumf_shards), _P, _P, _P, _I64,
                                          _I64, _I64, _I32, _U32, _U32, C.POINTER(brk_neumf_workspace), _P, _P, _P]),
+    "brk_bpr_fwd_bwd_sharded": (C.c_int, [_P, C.POINTER(brk_shards), C.POINTER(brk_shards), _I32, _P, _P, _P, _I64, _I64, _P, _P]),
     "brk_peer_barrier": (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
     "brk_tc_selftest": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _I32, _I32, _P, _I32, _I32, _P, _P]),
     "brk_dp_adam_peer": (C.c_int, [_P, C.POINTER(brk_dp_peer), brk_adam_hyper, _P, _P]),

@@ -4,7 +4,7 @@
 // (3*4d B of RED traffic) => 1536 B of algorithmic traffic at d = 64.
 // Mapping: a group of LPR lanes owns a triplet, each lane holds NCH float4 chunks of u, p and n in
 // registers; the dot product is a group shuffle-reduction; gradients leave as 16-byte vector REDs.
-#include "common.cuh"
+#include "neumf_common.cuh"      // TabRef / locate / mark_row: row-sharded table addressing
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include <vector>
@@ -113,6 +113,71 @@ bpr_vec(const float* __restrict__ Wu, const float* __restrict__ Wi, float* __res
   }
   (void)GPW;
   if constexpr (TRAIN) finish_loss(double(loss_local), inv_local, loss_acc, ticket, out);
+}
+
+// Row-sharded tables (row r on rank r % world, local row r / world; peer shards are NVLink mappings): the same
+// fused triplet kernel with every row address resolved through the shard table -- peer rows are gathered with
+// ordinary loads, the three row gradients leave as 16-byte REDs into the owners' accumulators.
+template <int LPR, int NCH>
+__global__ void __launch_bounds__(kThreads)
+bpr_vec_sharded(const v2::TabRef TU, const v2::TabRef TI, int d4, const int32_t* __restrict__ uid,
+                const int32_t* __restrict__ pid, const int32_t* __restrict__ nid, int64_t batch, float inv_batch,
+                double inv_local, double* loss_acc, unsigned int* ticket, float* __restrict__ out) {
+  const int lane_in = threadIdx.x & (LPR - 1);
+  const int64_t group = (int64_t(blockIdx.x) * kThreads + threadIdx.x) / LPR;
+  const int64_t n_groups = int64_t(gridDim.x) * kThreads / LPR;
+  const int64_t warp_first = group - ((threadIdx.x & 31) / LPR);
+  float loss_local = 0.f;
+  auto locate = [&](const v2::TabRef& T, int64_t row) {
+    int o = 0; int64_t l = row;
+    if (T.world > 1) { o = int(row % T.world); l = row / T.world; }
+    v2::RowRef r; r.w = T.w[o] + l * d4 * 4; r.g = T.g[o] + l * d4 * 4; r.t = T.t[o]; r.lrow = l;
+    return r;
+  };
+  for (int64_t wb = warp_first; wb < batch; wb += n_groups) {
+    const int64_t b = wb + (threadIdx.x & 31) / LPR;
+    const bool valid = b < batch;
+    v2::RowRef ru, rp, rn;
+    ru = rp = rn = locate(TU, 0);
+    if (valid) { ru = locate(TU, __ldg(uid + b)); rp = locate(TI, __ldg(pid + b)); rn = locate(TI, __ldg(nid + b)); }
+    float4 u[NCH], p[NCH], n[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int c = lane_in + k * LPR;
+      if (valid && c < d4) {
+        u[k] = __ldg(reinterpret_cast<const float4*>(ru.w) + c);
+        p[k] = __ldg(reinterpret_cast<const float4*>(rp.w) + c);
+        n[k] = __ldg(reinterpret_cast<const float4*>(rn.w) + c);
+      } else {
+        u[k] = p[k] = n[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      dot = fmaf(u[k].x, p[k].x - n[k].x, dot); dot = fmaf(u[k].y, p[k].y - n[k].y, dot);
+      dot = fmaf(u[k].z, p[k].z - n[k].z, dot); dot = fmaf(u[k].w, p[k].w - n[k].w, dot);
+    }
+    const float x = group_sum<LPR>(dot);
+    const float s = sigmoidf_acc(x);
+    if (valid && lane_in == 0) loss_local += 1.0f - s;
+    const float g = -s * (1.0f - s) * inv_batch;
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const int c = lane_in + k * LPR;
+        if (c < d4) {
+          const float4 dp = make_float4(g * u[k].x, g * u[k].y, g * u[k].z, g * u[k].w);
+          red_add_f4(ru.g + c * 4, make_float4(g * (p[k].x - n[k].x), g * (p[k].y - n[k].y), g * (p[k].z - n[k].z),
+                                               g * (p[k].w - n[k].w)));
+          red_add_f4(rp.g + c * 4, dp);
+          red_add_f4(rn.g + c * 4, make_float4(-dp.x, -dp.y, -dp.z, -dp.w));
+        }
+      }
+      if (lane_in == 0) { v2::mark_row(ru); v2::mark_row(rp); v2::mark_row(rn); }
+    }
+  }
+  finish_loss(double(loss_local), inv_local, loss_acc, ticket, out);
 }
 
 // Generic width (d % 4 != 0 or unaligned): one warp per triplet, rows re-read for the backward.
@@ -847,5 +912,51 @@ extern "C" int brk_bpr_train_steps_dp(brk_ctx* ctx, const brk_table* user, const
 extern "C" int brk_coop_trace_read(unsigned long long* out_host, int32_t n_words) {
   if (!g_coop_trace) return BRK_E_STATE;
   BRK_CUDA(cudaMemcpy(out_host, g_coop_trace, size_t(n_words) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// Fused BPR forward/backward on row-sharded tables (see brk_neumf_step_sharded for the protocol around it: a
+// brk_peer_barrier, then every owner applies its optimizer to its shards, then another barrier).
+extern "C" int brk_bpr_fwd_bwd_sharded(brk_ctx* ctx, const brk_shards* user, const brk_shards* item, int32_t d,
+                                       const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch,
+                                       int64_t global_batch, float* loss_out, void* stream) {
+  BRK_REQUIRE(ctx && user && item && u && p && n, BRK_E_ARG, "brk_bpr_fwd_bwd_sharded: null argument");
+  BRK_REQUIRE(d > 0 && (d & 3) == 0 && d <= 512 && batch > 0, BRK_E_ARG, "brk_bpr_fwd_bwd_sharded: d=%d batch=%lld (d %% 4 == 0)",
+              d, (long long)batch);
+  BRK_REQUIRE(user->world >= 1 && user->world <= BRK_MAX_PEERS && item->world == user->world, BRK_E_ARG,
+              "brk_bpr_fwd_bwd_sharded: world=%d/%d", user->world, item->world);
+  v2::TabRef TU, TI;
+  const brk_shards* sh[2] = {user, item};
+  v2::TabRef* T[2] = {&TU, &TI};
+  for (int k = 0; k < 2; ++k) {
+    for (int q = 0; q < BRK_MAX_PEERS; ++q) { T[k]->w[q] = nullptr; T[k]->g[q] = nullptr; T[k]->t[q] = nullptr; }
+    T[k]->world = sh[k]->world;
+    for (int q = 0; q < sh[k]->world; ++q) {
+      BRK_REQUIRE(sh[k]->w[q] && sh[k]->g[q] && brk_aligned16(sh[k]->w[q]) && brk_aligned16(sh[k]->g[q]), BRK_E_ARG,
+                  "brk_bpr_fwd_bwd_sharded: shard %d of table %d missing or not 16-byte aligned", q, k);
+      T[k]->w[q] = sh[k]->w[q]; T[k]->g[q] = sh[k]->g[q]; T[k]->t[q] = sh[k]->touched[q];
+    }
+  }
+  const float inv_batch = 1.0f / float(global_batch > 0 ? global_batch : batch);
+  const double inv_local = 1.0 / double(batch);
+  const int d4 = d >> 2, lpr = brk_lanes_per_row(d4), nch = (d4 + lpr - 1) / lpr;
+  const int64_t cap = int64_t(ctx->sm_count) * (2048 / kThreads);
+  int64_t need = (batch * lpr + kThreads - 1) / kThreads;
+  const int grid = int(need < 1 ? 1 : (need < cap ? need : cap));
+  cudaStream_t st = (cudaStream_t)stream;
+#define BRK_BPRS_CASE(L, N)                                                                                         \
+  bpr_vec_sharded<L, N><<<grid, kThreads, 0, st>>>(TU, TI, d4, u, p, n, batch, inv_batch, inv_local, ctx->loss_acc + 0, \
+                                                   ctx->tickets + 0, loss_out)
+  if (lpr == 1) BRK_BPRS_CASE(1, 1);
+  else if (lpr == 2) BRK_BPRS_CASE(2, 1);
+  else if (lpr == 4) BRK_BPRS_CASE(4, 1);
+  else if (lpr == 8) BRK_BPRS_CASE(8, 1);
+  else if (lpr == 16) BRK_BPRS_CASE(16, 1);
+  else if (nch == 1) BRK_BPRS_CASE(32, 1);
+  else if (nch == 2) BRK_BPRS_CASE(32, 2);
+  else if (nch == 3) BRK_BPRS_CASE(32, 3);
+  else BRK_BPRS_CASE(32, 4);
+#undef BRK_BPRS_CASE
+  BRK_LAUNCH_CHECK();
   return 0;
 }

@@ -259,3 +259,67 @@ class ShardedNeuMFNet:
             self.peer.check()
             if int(self._bar_sync[1].item()) != 0:
                 raise RuntimeError("brk_peer_barrier timed out (a rank did not reach the step)")
+
+
+class PeerBarrier:
+    """brk_peer_barrier with its symmetric flag block (one instance per model)."""
+
+    def __init__(self, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.device = device
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)
+        self._h = symm_mem.rendezvous(self.flags, dist.group.WORLD.group_name)
+        self.flags.zero_()
+        self.ptrs = torch.tensor(list(self._h.buffer_ptrs), dtype=torch.int64, device=device)
+        self.sync = torch.zeros(4, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier()
+
+    def __call__(self):
+        N.check(N.lib().brk_peer_barrier(N.ctx(self.device), N.ptr(self.ptrs), N.ptr(self.sync), D.rank(), D.world_size(),
+                                         N.stream_ptr()), "brk_peer_barrier")
+
+    def check(self):
+        if int(self.sync[1].item()) != 0:
+            raise RuntimeError("brk_peer_barrier timed out (a rank did not reach the step)")
+
+
+class ShardedBPRNet:
+    """BPR matrix factorisation (src/models/BPRModel.py:49-74,124-144) with row-sharded user / item tables and
+    row-sparse (lazy) Adam: fused fwd/bwd over peer memory -> barrier -> every owner updates its shards -> barrier."""
+
+    def __init__(self, numUser, numItem, numFactor, learning_rate=1e-3, seed=42, device=None, emulate=0, full_init=None):
+        self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+        self.emulate = int(emulate)
+        self.G, self.rank = (self.emulate, 0) if self.emulate else (D.world_size(), D.rank())
+        self.d = int(numFactor)
+        symmetric = not self.emulate and self.G > 1
+        fi = full_init or {}
+        self.user = ShardedTable(numUser, self.d, self.G, self.rank, self.device, full_init=fi.get("user"), init_seed=seed * 16,
+                                 symmetric=symmetric, emulate=bool(self.emulate))
+        self.item = ShardedTable(numItem, self.d, self.G, self.rank, self.device, full_init=fi.get("item"), init_seed=seed * 16 + 1,
+                                 symmetric=symmetric, emulate=bool(self.emulate))
+        self.optimizer = H.Adam(learning_rate, sparse="lazy", device=self.device)
+        self.barrier = PeerBarrier(self.device) if symmetric else None
+
+    def train_on_batch(self, u, p, n, loss_out=None):
+        B = u.numel()
+        loss_out = loss_out if loss_out is not None else torch.empty(1, dtype=torch.float32, device=self.device)
+        us, it = self.user.c_shards(), self.item.c_shards()
+        gb = B * self.G if (self.G > 1 and not self.emulate) else 0
+        N.check(N.lib().brk_bpr_fwd_bwd_sharded(N.ctx(self.device), C.byref(us), C.byref(it), self.d, N.ptr(H._i32(u, "u")),
+                                                N.ptr(H._i32(p, "p")), N.ptr(H._i32(n, "n")), B, gb, N.ptr(loss_out),
+                                                N.stream_ptr()), "brk_bpr_fwd_bwd_sharded")
+        if self.emulate:
+            self.optimizer.apply([t.tables[r] for r in range(self.G) for t in (self.user, self.item)])
+            return loss_out
+        if self.barrier is not None:
+            self.barrier()                     # every rank's REDs have landed in my accumulators
+        self.optimizer.apply([self.user.local, self.item.local])
+        if self.barrier is not None:
+            self.barrier()                     # every owner has updated its shards before anybody's next gather
+        return loss_out
+
+    def check(self):
+        if self.barrier is not None:
+            self.barrier.check()

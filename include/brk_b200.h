@@ -248,6 +248,10 @@ int brk_neumf_step_sharded(brk_ctx* ctx, const brk_neumf_model* m, const brk_neu
                            int64_t global_batch, int64_t first_index, int32_t training, uint32_t dropout_seed,
                            uint32_t dropout_epoch, const brk_neumf_workspace* ws, float* out, float* loss_out,
                            void* stream);
+/* The fused BPR triplet forward/backward (brk_bpr_fwd_bwd) on row-sharded tables of width d. */
+int brk_bpr_fwd_bwd_sharded(brk_ctx* ctx, const brk_shards* user, const brk_shards* item, int32_t d,
+                            const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch,
+                            int64_t global_batch, float* loss_out, void* stream);
 /* Cross-GPU barrier on `stream`: returns (in stream order) once every rank's earlier work on its stream
  * has completed.  peer_flags: DEVICE array of `world` pointers to each rank's flag block (world uint32,
  * zero-initialised, peer-mapped); local_sync: 4 uint32 zero-initialised ([0] epoch, [1] error: a peer did

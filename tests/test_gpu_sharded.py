@@ -75,6 +75,25 @@ def test_sharded_addressing_equals_unsharded_one_gpu(dev, G, E):
                                atol=2e-6)
 
 
+@pytest.mark.parametrize("G", [2, 3])
+def test_sharded_bpr_equals_unsharded_one_gpu(dev, G):
+    from binrec_b200.BPRModel import BPRNet
+    from binrec_b200.sharded import ShardedBPRNet
+    U, I, d, B = 301, 203, 64, 400
+    ref = BPRNet(U, I, d, sparse_adam="lazy", device=dev)
+    sh = ShardedBPRNet(U, I, d, device=dev, emulate=G, full_init={"user": ref.user.w.cpu().numpy(), "item": ref.item.w.cpu().numpy()})
+    rng = np.random.default_rng(G)
+    for step in range(3):
+        u, p, n = ((U * rng.random(B) ** 2).astype(np.int32), (I * rng.random(B) ** 2).astype(np.int32),
+                   rng.integers(0, I, B).astype(np.int32))
+        ud, pd_, nd = (torch.from_numpy(x).to(dev) for x in (u, p, n))
+        l0 = ref.train_on_batch(ud, pd_, nd)
+        l1 = sh.train_on_batch(ud, pd_, nd)
+        np.testing.assert_allclose(l1.item(), l0.item(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sh.user.full_weights(), ref.user.w.cpu().numpy(), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(sh.item.full_weights(), ref.item.w.cpu().numpy(), rtol=1e-5, atol=2e-6)
+
+
 # ---- two GPUs ------------------------------------------------------------------------------------------
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
@@ -102,7 +121,19 @@ def _worker(rank, world, port, mode, init, ret):
             losses.append(float(l.item()))
         net.check()
         full = {n: getattr(net, n).full_weights() for n in ("uMLP", "iMLP", "uMF", "iMF")}
-        ret[(mode, rank)] = dict(losses=losses, dense=net.dense.w.cpu().numpy().reshape(-1), **full)
+        bpr = {}
+        if mode == "peer":                    # row-sharded BPR on the same two GPUs
+            from binrec_b200.sharded import ShardedBPRNet
+            b = ShardedBPRNet(U2, I2, 64, device=dev, full_init=init["bpr"])
+            rngb = np.random.default_rng(21)
+            for step in range(3):
+                u, p, n = (rngb.integers(0, U2, world * B2).astype(np.int32), rngb.integers(0, I2, world * B2).astype(np.int32),
+                           rngb.integers(0, I2, world * B2).astype(np.int32))
+                lo, hi = D.local_slice(world * B2)
+                b.train_on_batch(*(torch.from_numpy(x[lo:hi]).to(dev) for x in (u, p, n)))
+            b.check()
+            bpr = dict(bpr_user=b.user.full_weights(), bpr_item=b.item.full_weights())
+        ret[(mode, rank)] = dict(losses=losses, dense=net.dense.w.cpu().numpy().reshape(-1), **full, **bpr)
     finally:
         dist.destroy_process_group()
 
@@ -121,6 +152,14 @@ def test_sharded_neumf_two_gpus_matches_unsharded(mode):
     # optimizer step -- exactly what the two ranks do together
     ref = NeuMFNet(U2, I2, E2, dropout=0.0, sparse_adam="lazy", device=dev)
     init = _full_init(ref, E2, hidden)
+    from binrec_b200.BPRModel import BPRNet
+    bref = BPRNet(U2, I2, 64, sparse_adam="lazy", device=dev)
+    init["bpr"] = {"user": bref.user.w.cpu().numpy().copy(), "item": bref.item.w.cpu().numpy().copy()}
+    rngb = np.random.default_rng(21)
+    for step in range(3):                    # the global batch in one process (BPR has no per-replica statistics)
+        u, p, n = (rngb.integers(0, U2, world * B2).astype(np.int32), rngb.integers(0, I2, world * B2).astype(np.int32),
+                   rngb.integers(0, I2, world * B2).astype(np.int32))
+        bref.train_on_batch(*(torch.from_numpy(x).to(dev) for x in (u, p, n)))
     ref_losses = []
     for step, (u, i, y) in enumerate(_batches(U2, I2, world * B2, STEPS2, 5)):
         ls = []
@@ -150,3 +189,6 @@ def test_sharded_neumf_two_gpus_matches_unsharded(mode):
         n = len(got["dense"])
         np.testing.assert_allclose(got["dense"], ref.dense.w.cpu().numpy().reshape(-1)[:n], rtol=1e-4, atol=2e-6)
     assert np.array_equal(ret[(mode, 0)]["dense"], ret[(mode, 1)]["dense"])
+    if mode == "peer":
+        np.testing.assert_allclose(ret[(mode, 0)]["bpr_user"], bref.user.w.cpu().numpy(), rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(ret[(mode, 0)]["bpr_item"], bref.item.w.cpu().numpy(), rtol=1e-5, atol=2e-6)
