@@ -38,10 +38,22 @@ def gather_rows(table, ids, out=None):
     return out
 
 
+def index_skew(ids, sample=8192):
+    """Share of the most frequent id among the first `sample` ids (0..1)."""
+    smp = ids[:sample].long()
+    return float(torch.bincount(smp).max().item()) / float(smp.numel())
+
+
 def scatter_add_rows(acc, ids, vals, touched=None, mode=0):
-    """acc[ids[b],:] += vals[b,:]  -- IndexedSlices gradient accumulation."""
+    """acc[ids[b],:] += vals[b,:]  -- IndexedSlices gradient accumulation.
+    mode 0: vector atomics; 1: per-CTA sort + segment-reduce; "auto": picks by the measured index skew -- the
+    share of the most frequent id in a sample of the batch (one small device histogram + one host read): same-row
+    REDs serialise in L2, so mode 1 wins once a single row takes >= 1 % of the batch (measured: 6040-row table,
+    1 M ids, cubic head: 315 -> 166 us) and loses 25-60 % otherwise."""
     acc = _f32(acc, "acc"); ids = _i32(ids, "ids"); vals = _f32(vals, "vals")
     rows, d = acc.shape
+    if mode == "auto":
+        mode = 1 if (ids.numel() >= 4096 and index_skew(ids) >= 0.01) else 0
     N.check(N.lib().brk_scatter_add_rows(N.ctx(acc.device), N.ptr(acc), rows, d, N.ptr(ids), ids.numel(),
                                          N.ptr(vals), N.ptr(touched), mode, N.stream_ptr()),
             "brk_scatter_add_rows")

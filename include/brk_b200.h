@@ -74,7 +74,10 @@ int brk_gather_rows(brk_ctx* ctx, const float* table, int64_t rows, int32_t d,
  * Stands in for the IndexedSlices gradient of the gathers above and the optimizer's duplicate
  * summation (tf UnsortedSegmentSum; inside model.fit src/models/RModel.py:130 and
  * tape.gradient trainers/twoTower.py:97).  acc[ids[b],:] += vals[b,:].
- * mode 0: vector atomics (red.global.add.v4.f32); mode 1: sort-and-segment-reduce (deterministic).
+ * mode 0: vector atomics (red.global.add.v4.f32), one RED per occurrence and 16-byte chunk.
+ * mode 1: sort-and-segment-reduce -- each CTA sorts a tile of 1024 (id, position) pairs in shared memory and
+ *   sends one RED per run of up to 16 equal ids (d % 4 == 0, d <= 128, else mode 0 is taken); for small hot
+ *   tables where the same rows are hit over and over (pick it when n / rows, the mean duplicate factor, is large).
  * touched (may be NULL) gets bit ids[b] set. */
 int brk_scatter_add_rows(brk_ctx* ctx, float* acc, int64_t rows, int32_t d,
                          const int32_t* ids, int64_t n, const float* vals,

@@ -68,6 +68,8 @@ def sec_scatter():
             ids = ids_of(kind, rows, n, g)
             s = timeit(lambda: H.scatter_add_rows(acc, ids, vals))
             report(f"scatter_add_rows rows={rows} d={d} n={n} ids={kind}", s, n * (3 * 4 * d + 4))
+            s = timeit(lambda: H.scatter_add_rows(acc, ids, vals, mode=1))
+            report(f"scatter_add_rows mode=1 (sort+segment) rows={rows} d={d} n={n} ids={kind}", s, n * (3 * 4 * d + 4))
         del acc, vals
 
 

@@ -52,6 +52,36 @@ def test_scatter_add_rows_exact_on_integer_values(dev, d):
     assert np.array_equal(bits, expect)
 
 
+@pytest.mark.parametrize("d", [8, 64, 128])
+@pytest.mark.parametrize("n", [1, 1000, 20000, 70001])
+def test_scatter_add_sorted_mode_exact_on_integer_values(dev, d, n):
+    # mode 1 (per-CTA sort + segment-reduce) must give the same sums and touched bits as the definition
+    rng = np.random.default_rng(d + n)
+    rows = 211
+    ids = (rows * rng.random(n) ** 3).astype(np.int32)
+    vals = rng.integers(-8, 9, size=(n, d)).astype(np.float32)
+    acc = torch.zeros(rows, d, device=dev)
+    touched = torch.zeros((rows + 31) // 32, dtype=torch.int32, device=dev)
+    H().scatter_add_rows(acc, torch.from_numpy(ids).to(dev), torch.from_numpy(vals).to(dev), touched, mode=1)
+    assert np.array_equal(acc.cpu().numpy(), OE.scatter_add_rows(rows, ids, vals))
+    bits = np.unpackbits(touched.cpu().numpy().view(np.uint8), bitorder="little")[:rows]
+    expect = np.zeros(rows, dtype=np.uint8); expect[np.unique(ids)] = 1
+    assert np.array_equal(bits, expect)
+
+
+def test_scatter_add_auto_mode_picks_by_skew(dev):
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    n = 100000
+    uniform = torch.randint(0, 6040, (n,), generator=g, device=dev, dtype=torch.int32)
+    skewed = (6040 * torch.rand(n, generator=g, device=dev) ** 3).to(torch.int32)
+    assert H().index_skew(uniform) < 0.01 <= H().index_skew(skewed)
+    vals = torch.ones(n, 64, device=dev)
+    for ids in (uniform, skewed):
+        acc = torch.zeros(6040, 64, device=dev)
+        H().scatter_add_rows(acc, ids, vals, mode="auto")
+        assert torch.equal(acc[:, 0], torch.bincount(ids.long(), minlength=6040).float())
+
+
 def test_scatter_add_is_gather_transpose_property(dev):
     # <gather(T, ids), V> == <T, scatter_add(ids, V)>  (linearity / adjointness), exact in integers
     rng = np.random.default_rng(5)
