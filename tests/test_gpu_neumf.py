@@ -93,7 +93,9 @@ def test_neumf_five_steps_match_oracle_keras_adam(dev, E, hidden, act, loss):
     bn = net.bn_moving.cpu().numpy()
     for g, want in ((bn[:h1], orc.p.mm1), (bn[h1:2 * h1], orc.p.mv1), (bn[2 * h1:2 * h1 + h2], orc.p.mm2),
                     (bn[2 * h1 + h2:], orc.p.mv2)):
-        np.testing.assert_allclose(g, want.numpy(), rtol=1e-5, atol=1e-7)
+        # moving statistics follow weights that went through five noise-amplifying Adam steps (see the docstring):
+        # the multi-step fp32 tolerance of SURVEY.md section 8c (1e-4), not the one-step 1e-5
+        np.testing.assert_allclose(g, want.numpy(), rtol=1e-4, atol=1e-6)
     assert net.optimizer.step.item() == 5
     # inference path uses the moving statistics
     u, i, y = _batch(rng, U, I, 777)
