@@ -8,6 +8,9 @@ fused Keras-Adam launch over all parameters (csrc/optim.cu), all through the C A
 Differences from the reference, stated once:
   * negatives come from the counter-based sampler (same marginals as NeuMFModel.py:104-105: user and
     item both follow the positives' empirical popularity, no collision check), so runs are reproducible;
+    `rejectCollisions = True` on the model re-draws negatives that are known positives (SURVEY.md 8 f1);
+  * the merged frame of an epoch (sampling + labels + row shuffle) is written on the device by one kernel
+    (csrc/pipeline.cu) instead of pandas on the host;
   * dropout masks come from Philox with keep probability 205/256 (oracle/neumf.py); TensorFlow's
     dropout stream is not reproducible, so rate 0.2 is matched in distribution, not bit for bit;
   * `train` works without a distributedConfig (the reference raises NameError, RModel.py:139);
@@ -23,6 +26,7 @@ import torch
 from . import _native as N
 from . import distributed as D
 from . import hotpath as H
+from . import pipeline as PL
 from . import synth
 from .RModel import RModel
 
@@ -235,26 +239,45 @@ class NeuMFNet:
 class NeuMFDataset:
     """What bootstrapDataset returns: positives + Philox negatives, labels 1/0, one seeded row shuffle,
     cut into batches; resident on the device.  Iterating yields ({"user": ids, "item": ids}, label)
-    like the reference's tf.data pipeline (NeuMFModel.py:111-123)."""
+    like the reference's tf.data pipeline (NeuMFModel.py:111-123).  The whole frame is written by ONE
+    kernel (pipeline.neumf_epoch_build: keyed permutation + positive copy / negative draw + label);
+    resample(epoch) rebuilds it in place with fresh negatives and a fresh row order (the reference
+    samples once per bootstrapDataset call)."""
 
-    def __init__(self, users, items, negRatio, batchSize, shuffle, device, seed=7, epoch=0):
+    def __init__(self, users, items, negRatio, batchSize, shuffle, device, seed=7, epoch=0, reject=False,
+                 numUser=None):
         dev = device
-        pu = torch.from_numpy(np.ascontiguousarray(users, dtype=np.int32)).to(dev)
-        pi = torch.from_numpy(np.ascontiguousarray(items, dtype=np.int32)).to(dev)
-        P = pu.numel()
-        n_neg = int(round(P * negRatio))
-        if n_neg > 0:
-            nu, ni = H.philox_neumf_negatives(pu, pi, n_neg, seed, epoch)
-            u = torch.cat([pu, nu]); i = torch.cat([pi, ni])
-        else:
-            u, i = pu, pi
-        y = torch.cat([torch.ones(P, device=dev), torch.zeros(n_neg, device=dev)])
-        # mergeDf.sample(frac=1.): one row shuffle (seeded here; NeuMFModel.py:109)
-        perm = torch.from_numpy(np.random.Generator(np.random.Philox(key=seed + 77)).permutation(P + n_neg)).to(dev)
-        self.u, self.i, self.y = u[perm].contiguous(), i[perm].contiguous(), y[perm].contiguous()
+        users = np.ascontiguousarray(users, dtype=np.int32)
+        items = np.ascontiguousarray(items, dtype=np.int32)
+        self.pu = torch.from_numpy(users).to(dev)
+        self.pi = torch.from_numpy(items).to(dev)
+        P = self.pu.numel()
+        self.n_neg = int(round(P * negRatio))
+        self.n = P + self.n_neg
         self.batchSize, self.shuffle, self.seed = int(batchSize), shuffle, seed
-        self.n = P + n_neg
         self.device = dev
+        self.reject = bool(reject)
+        self.csr = None
+        if self.reject:
+            nu = int(numUser) if numUser is not None else int(users.max()) + 1
+            indptr, sitems = synth.build_csr(users, items, nu)
+            self.csr = (torch.from_numpy(indptr).to(dev), torch.from_numpy(sitems).to(dev))
+        self.u = torch.empty(self.n, dtype=torch.int32, device=dev)
+        self.i = torch.empty(self.n, dtype=torch.int32, device=dev)
+        self.y = torch.empty(self.n, dtype=torch.float32, device=dev)
+        self.resample(epoch)
+
+    def resample(self, epoch):
+        """mergeDf = concat(pos, neg).sample(frac=1.) (NeuMFModel.py:103-109), seeded by (seed, epoch)."""
+        PL.neumf_epoch_build(self.pu, self.pi, self.n_neg, self.seed, epoch, reject=self.reject,
+                             csr_indptr=self.csr[0] if self.csr else None,
+                             csr_items=self.csr[1] if self.csr else None, out=(self.u, self.i, self.y))
+        self.epoch = epoch
+
+    def batch_order(self, epoch):
+        """`.batch(batchSize).shuffle(...)` (NeuMFModel.py:117-121): whole batches are permuted per epoch."""
+        nb = len(self)
+        return PL.epoch_permutation_host(nb, self.seed, epoch, PL.SALT_BATCHES) if self.shuffle else np.arange(nb)
 
     def __len__(self):
         return (self.n + self.batchSize - 1) // self.batchSize
@@ -271,8 +294,7 @@ class NeuMFDataset:
 
     def run_epoch(self, net, epoch, steps=None):
         nb = len(self)
-        order = (np.random.Generator(np.random.Philox(key=self.seed + 1009 * (epoch + 1))).permutation(nb)
-                 if self.shuffle else np.arange(nb))
+        order = self.batch_order(epoch)
         if steps is not None:
             order = order[:int(steps)]
         losses = torch.empty(len(order), dtype=torch.float32, device=self.device)
@@ -290,6 +312,7 @@ class NeuMFModel(RModel):
         super().__init__('NeuMFModel', workDir)
         self.sparseAdam = "keras"
         self.dropout = 0.2
+        self.rejectCollisions = False      # reference semantics: no collision check (NeuMFModel.py:104-105)
         self._testProducts, self._testUsers = [], []
 
     def prepareToTrain(self, distributedConfig, path, rowLimit):
@@ -317,7 +340,8 @@ class NeuMFModel(RModel):
     def bootstrapDataset(self, df, negRatio=3., batchSize=128, shuffle=True):
         users, items = self._loadPairs(df, None)
         dev = torch.device(f"cuda:{torch.cuda.current_device()}")
-        return NeuMFDataset(users, items, negRatio, batchSize, shuffle, dev, seed=self.samplerSeed)
+        return NeuMFDataset(users, items, negRatio, batchSize, shuffle, dev, seed=self.samplerSeed,
+                            reject=self.rejectCollisions)
 
     def train(self, path, rowLimit, metricDict: dict = {}, distributedConfig=None):
         trainDataset, testDataset, trainSplit = self.prepareToTrain(distributedConfig, path, rowLimit)

@@ -374,6 +374,49 @@ int brk_topk_metrics(brk_ctx* ctx, const int32_t* ids, int64_t U, int32_t k, con
                      const int64_t* pos_indptr, const int32_t* pos_items, int64_t csr_users,
                      int64_t* counts_out, double* ndcg_sum_out, void* stream);
 
+/* ---- input pipeline (the caller's side of the training step) ------
+ * brk_epoch_permutation: out[j] = perm(first + j), j < count, where perm is the keyed bijection of [0, n)
+ *   "brk perm v1" (oracle/pipeline.py: six-round Feistel network over max(2, ceil(log2 n)) bits, round keys =
+ *   Philox4x32-10(counter (round, 0, salt, 0x5E), key (seed, epoch)) words 0/1, two-multiply 32-bit round mixer,
+ *   cycle walking).  Stands in for the unseeded shuffles of src/models/NeuMFModel.py:109 (rows, salt 0) and
+ *   :117-121 (`.batch().shuffle()`: batches, salt 1) and trainers/twoTower.py:197 -- no sort, no memory.
+ *   brk_epoch_permutation_host is the same function evaluated on the host (batch orders of host-driven
+ *   loops: batch_index_host of the brk_bpr_train_steps* calls); it needs no device and no context.
+ * brk_neumf_epoch_build: rows [first, first+count) of the shuffled training frame of one epoch in ONE launch --
+ *   what bootstrapDataset (src/models/NeuMFModel.py:102-109) builds with pandas: row j is source row
+ *   s = perm(j) of concat(positives, negatives); s < num_pos: the positive pair s, label 1; otherwise negative
+ *   number s - num_pos of the "brk sampler v2" NeuMF stream (brk_philox_neumf_negatives), label 0.
+ *   reject != 0 adds what the reference does not do (row f1): a draw that is a known positive (binary search in
+ *   the per-user sorted lists csr_indptr int64 [U+1] / csr_items) is re-drawn with Philox counter word 2 =
+ *   attempt 1..7; the eighth draw is kept whatever it is. */
+int brk_epoch_permutation(brk_ctx* ctx, int64_t n, int64_t first, int64_t count, uint32_t seed,
+                          uint32_t epoch, uint32_t salt, int64_t* out, void* stream);
+int brk_epoch_permutation_host(int64_t n, int64_t first, int64_t count, uint32_t seed, uint32_t epoch,
+                               uint32_t salt, int64_t* out_host);
+int brk_neumf_epoch_build(brk_ctx* ctx, const int32_t* pos_users, const int32_t* pos_items,
+                          int64_t num_pos, int64_t n_neg, int64_t first, int64_t count, uint32_t seed,
+                          uint32_t epoch, int32_t reject, const int64_t* csr_indptr,
+                          const int32_t* csr_items, int32_t* users, int32_t* items, float* labels,
+                          void* stream);
+/* Id factorisation: dense ids in order of first appearance -- `pd.unique` + positional lookup
+ * (trainers/loadBinaryMovieLens.py:16-19,58-61) and StringLookup(vocabulary=...) (trainers/twoTower.py:33-36;
+ * offset 2: index 0 = mask, 1 = OOV).  Keys are 64-bit (integer ids, or byte strings of <= 8 bytes packed
+ * exactly); the key 0xFFFFFFFFFFFFFFFF is reserved.  An open-addressing table (capacity = a power of two
+ * >= 2n, brk_vocab_capacity) records every distinct key with the smallest position it occurs at; a prefix sum
+ * over the first-occurrence flags turns positions into ranks.
+ *   ids[j] = offset + rank of keys[j];  vocab[r] = the r-th distinct key (may be NULL);  *n_unique (device)
+ *   = number of distinct keys.  Afterwards (table_keys, table_vals) map key -> id for brk_vocab_lookup_u64,
+ *   which writes `oov` for keys that are not in the table.
+ * workspace: brk_vocab_workspace_bytes(n) bytes of device scratch.  n < 2^31 - 2^24. */
+int64_t brk_vocab_capacity(int64_t n);
+int64_t brk_vocab_workspace_bytes(int64_t n);
+int brk_vocab_build_u64(brk_ctx* ctx, const uint64_t* keys, int64_t n, int32_t offset,
+                        uint64_t* table_keys, int32_t* table_vals, int64_t capacity, int32_t* ids,
+                        uint64_t* vocab, int64_t* n_unique, void* workspace, void* stream);
+int brk_vocab_lookup_u64(brk_ctx* ctx, const uint64_t* keys, int64_t n, const uint64_t* table_keys,
+                         const int32_t* table_vals, int64_t capacity, int32_t oov, int32_t* ids,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

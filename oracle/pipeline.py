@@ -16,11 +16,16 @@ the factorisation is pinned against `pandas.unique` / `pandas.factorize` execute
 (tests/test_oracle_pipeline.py), the permutation by its defining property (a bijection of [0, n)) and
 by the literal per-element definition below.
 
-"brk perm v1": a keyed bijection of [0, n) that needs no sort and no memory -- a balanced Feistel
-network over 2h bits (2h = the smallest even width with 2^(2h) >= max(n, 4)), six rounds, round
-function F(R, round) = word 0 of Philox4x32-10(counter = (R, round, salt, 0x5E), key = (seed, epoch))
-masked to h bits; values that land in [n, 2^(2h)) are walked through the network again (cycle
-walking), which keeps the map a bijection of [0, n).
+"brk perm v1": a keyed bijection of [0, n) that needs no sort and no memory -- a six-round Feistel
+network over `bits` = max(2, ceil(log2 n)) bits, split into a left part of bits // 2 and a right part of
+bits - bits // 2 bits (the widths swap every round, so odd widths work and the domain is < 2n), with
+cycle walking: values that land in [n, 2^bits) go through the network again, which keeps the map a
+bijection of [0, n).  Round r uses the key pair (k0_r, k1_r) = words 0, 1 of
+Philox4x32-10(counter = (r, 0, salt, 0x5E), key = (seed, epoch)) and the round function
+F(R) = mix32((R ^ k0_r), k1_r) truncated to the width of the left part, mix32 being the two-multiply
+integer finaliser  x ^= x >> 16; x *= 0x7feb352d; x ^= x >> 15; x += k1; x *= 0x846ca68b; x ^= x >> 16.
+(Philox supplies the keys, not the per-element rounds: 12 multiplies per evaluation instead of 120, so
+the shuffle runs at memory speed instead of being ALU-bound.)
 """
 import numpy as np
 
@@ -33,33 +38,54 @@ SALT_BATCHES = 1     # the per-epoch batch-order shuffle (NeuMFModel.py:120)
 MAX_ATTEMPTS = 8     # collision rejection: attempts 0..7, the last one is kept whatever it is
 
 
-def perm_half_bits(n):
+def perm_bits(n):
     bits = 2
     while (1 << bits) < n:
-        bits += 2
-    return bits // 2
+        bits += 1
+    return bits
 
 
-def _feistel_once(x, h, seed, epoch, salt):
-    mask = np.uint64((1 << h) - 1)
-    L = x >> np.uint64(h)
-    R = x & mask
+def perm_round_keys(seed, epoch, salt):
+    ctr = np.array([[r, 0, salt & 0xFFFFFFFF, TAG_PERM] for r in range(PERM_ROUNDS)], dtype=np.uint32)
+    w = PX.philox4x32_10(ctr, (seed, epoch))
+    return w[:, 0].astype(np.uint64), w[:, 1].astype(np.uint64)
+
+
+def _mix32(x, k0, k1):
+    m = np.uint64(0xFFFFFFFF)
+    x = (x ^ k0) & m
+    x ^= x >> np.uint64(16)
+    x = (x * np.uint64(0x7FEB352D)) & m
+    x ^= x >> np.uint64(15)
+    x = (x + k1) & m
+    x = (x * np.uint64(0x846CA68B)) & m
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def _feistel_once(x, bits, k0, k1):
+    hl = bits // 2
+    hr = bits - hl
+    L = x >> np.uint64(hr)
+    R = x & np.uint64((1 << hr) - 1)
+    wl, wr = hl, hr
     for r in range(PERM_ROUNDS):
-        ctr = np.stack([R, np.full_like(R, r), np.full_like(R, salt), np.full_like(R, TAG_PERM)], axis=1)
-        F = PX.philox4x32_10(ctr.astype(np.uint32), (seed, epoch))[:, 0].astype(np.uint64) & mask
+        F = _mix32(R & np.uint64(0xFFFFFFFF), k0[r], k1[r]) & np.uint64((1 << wl) - 1)
         L, R = R, L ^ F
-    return (L << np.uint64(h)) | R
+        wl, wr = wr, wl
+    return (L << np.uint64(hr)) | R
 
 
 def feistel_perm(n, seed, epoch, salt=SALT_ROWS, first=0, count=None):
     """perm[j] for j in [first, first+count): int64 array, a bijection of [0, n) over the full range."""
     count = n - first if count is None else count
-    h = perm_half_bits(n)
+    bits = perm_bits(n)
+    k0, k1 = perm_round_keys(seed, epoch, salt)
     x = np.arange(first, first + count, dtype=np.uint64)
     todo = np.arange(count)
     out = np.empty(count, dtype=np.int64)
     while len(todo):
-        x = _feistel_once(x, h, seed, epoch, salt)
+        x = _feistel_once(x, bits, k0, k1)
         done = x < np.uint64(n)
         out[todo[done]] = x[done].astype(np.int64)
         todo, x = todo[~done], x[~done]
@@ -67,16 +93,26 @@ def feistel_perm(n, seed, epoch, salt=SALT_ROWS, first=0, count=None):
 
 
 def feistel_perm_scalar(j, n, seed, epoch, salt=SALT_ROWS):
-    """The definition, one element at a time (small cases)."""
-    h = perm_half_bits(n)
-    mask = (1 << h) - 1
+    """The definition, one element at a time with Python integers (small cases)."""
+    bits = perm_bits(n)
+    hl = bits // 2
+    hr = bits - hl
+    k0, k1 = perm_round_keys(seed, epoch, salt)
     x = int(j)
     while True:
-        L, R = x >> h, x & mask
+        L, R = x >> hr, x & ((1 << hr) - 1)
+        wl, wr = hl, hr
         for r in range(PERM_ROUNDS):
-            F = int(PX.philox4x32_10(np.array([[R, r, salt, TAG_PERM]], dtype=np.uint32), (seed, epoch))[0, 0]) & mask
-            L, R = R, L ^ F
-        x = (L << h) | R
+            y = (R ^ int(k0[r])) & 0xFFFFFFFF
+            y ^= y >> 16
+            y = (y * 0x7FEB352D) & 0xFFFFFFFF
+            y ^= y >> 15
+            y = (y + int(k1[r])) & 0xFFFFFFFF
+            y = (y * 0x846CA68B) & 0xFFFFFFFF
+            y ^= y >> 16
+            L, R = R, L ^ (y & ((1 << wl) - 1))
+            wl, wr = wr, wl
+        x = (L << hr) | R
         if x < n:
             return x
 
