@@ -316,6 +316,28 @@ class BPRModel(RModel):
         self.model.fit(X, None, batch_size=self.batchSize, epochs=self.epochs, sampler_seed=self.samplerSeed)
         return {'result': 'completed', 'metrics': [self.model.history["loss"][-1]]}
 
+    def checkpointMeta(self) -> dict:
+        return {"model": self.modelName, "numUser": self.model.user.rows, "numItem": self.model.item.rows,
+                "numFactor": self.model.user.d, "productIds": [int(x) for x in self._productIds]}
+
+    def buildFromMeta(self, meta: dict):
+        self.compileModel(None, meta["numUser"], meta["numItem"], meta["numFactor"])
+        self.productIds = list(meta.get("productIds", []))
+
+    def predictForUsers(self, customerIds, numberOfItem=5):
+        """Top products for a batch of users (not in the reference, whose BPRModel stops after training; the scores
+        are bpr_predict's, src/models/bpr.py:122-133): one bf16 tcgen05 scoring GEMM with the fused top-K epilogue
+        over the whole catalog (hotpath.BruteForceIndex) -> [[(str(product), str(score)), ...] per user]."""
+        users = torch.as_tensor(np.asarray([int(c) for c in customerIds], dtype=np.int32)).to(self.model.device)
+        if users.numel() and (int(users.min()) < 0 or int(users.max()) >= self.model.user.rows):
+            raise ValueError("unknown customer id")
+        if users.numel() == 0:
+            return []
+        index = H.BruteForceIndex(k=numberOfItem).index(self.model.item.w)
+        v, ix = index(H.gather_rows(self.model.user.w, users))
+        v, ix = v.cpu().numpy(), ix.cpu().numpy()
+        return [[(str(int(j)), str(s)) for s, j in zip(v[r], ix[r])] for r in range(len(v))]
+
     def extractPositivesNegatives(self, customerId) -> list:
         """Exhaustive (positive, non-interacted) pairs of one customer -- BPRModel.py:111-119."""
         trU, trI = self._trainDf

@@ -231,9 +231,13 @@ class NeuMFNet:
         return sd
 
     def load_state_dict(self, sd):
+        """Also accepts the whole-table view of a checkpoint written by sharded.ShardedNeuMFNet (same names)."""
         self.bn_moving.copy_(sd["bn_moving"]); self.optimizer.state.copy_(sd["opt_state"])
         for name, t in zip(("uMLP", "iMLP", "uMF", "iMF", "dense"), self.tables() + [self.dense]):
-            t.w.copy_(sd[name]); t.m.copy_(sd[name + "_m"]); t.v.copy_(sd[name + "_v"])
+            for slot, key in ((t.w, name), (t.m, name + "_m"), (t.v, name + "_v")):
+                if tuple(sd[key].reshape(-1).shape) != tuple(slot.reshape(-1).shape):
+                    raise ValueError(f"checkpoint tensor {key!r} has {sd[key].numel()} elements, the model needs {slot.numel()}")
+                slot.copy_(sd[key].reshape(slot.shape))
 
 
 class NeuMFDataset:
@@ -357,6 +361,15 @@ class NeuMFModel(RModel):
         evaluatedMetric = self.model.evaluate(valDataset, steps=self.validationSteps)
         return {'result': 'completed', 'metrics': evaluatedMetric}
 
+    def checkpointMeta(self) -> dict:
+        return {"model": self.modelName, "numUser": self.model.numUser, "numItem": self.model.numItem,
+                "numFactor": self.model.E, "testProducts": [int(x) for x in self._testProducts],
+                "testUsers": [int(x) for x in self._testUsers]}
+
+    def buildFromMeta(self, meta: dict):
+        self.compileModel(None, meta["numUser"], meta["numItem"], meta["numFactor"])
+        self._testProducts, self._testUsers = list(meta.get("testProducts", [])), list(meta.get("testUsers", []))
+
     def getPredictableUsers(self) -> list:
         return list(self._testUsers)
 
@@ -365,11 +378,19 @@ class NeuMFModel(RModel):
 
     def predictForUser(self, customerId, numberOfItem=5):
         """[(str(item), str(score)), ...] best first, as NeuMFModel.py:133-150 returns."""
-        dev = self.model.device
-        items = torch.as_tensor(np.asarray(self._testProducts, dtype=np.int32)).to(dev)
-        users = torch.full_like(items, int(customerId))
-        out, _ = self.model.predict_on_batch(users, items)
-        k = min(numberOfItem, items.numel())
-        v, ix = H.topk_rows(out.view(1, -1), k)
-        v, ix = v.cpu().numpy()[0], ix.cpu().numpy()[0]
-        return [(str(self._testProducts[j]), str(s)) for s, j in zip(v, ix)]
+        return self.predictForUsers([customerId], numberOfItem)[0]
+
+    def predictForUsers(self, customerIds, numberOfItem=5):
+        """predictForUser for a batch of users in one pass (the serving handoff of SURVEY.md section 8 row f3): every
+        (user, product) pair goes through the fused forward in large batches and the per-user top lists come from
+        the device top-k kernel (NeuMFNet.score_all); one host read for the whole batch."""
+        customerIds = [int(c) for c in customerIds]
+        bad = [c for c in customerIds if not 0 <= c < self.model.numUser]
+        if bad:
+            raise ValueError(f"unknown customer ids {bad[:5]}")
+        if not self._testProducts or not customerIds:
+            return [[] for _ in customerIds]
+        k = min(int(numberOfItem), len(self._testProducts))
+        v, ix = self.model.score_all(customerIds, self._testProducts, k)
+        v, ix = v.cpu().numpy(), ix.cpu().numpy()
+        return [[(str(self._testProducts[j]), str(s)) for s, j in zip(v[r], ix[r])] for r in range(len(customerIds))]

@@ -6,8 +6,9 @@ C ABI.
 Deliberate differences from the reference (SURVEY.md section 0.5 lists its broken entry points):
   * `train` works without a distributedConfig (the reference raises NameError at RModel.py:139
     because `strategy` is unbound);
-  * data may be given as a CSV path with the reference's columns (NeuMFModel.py:21-27), or
-    directly as a (users, items) pair of int arrays / a dict with CUSTOMER_ID and PRODUCT_ID;
+  * data may be given as a CSV path with the reference's columns (NeuMFModel.py:21-27), as a ".brkc"
+    binary columnar cache of it (interactions.py), or directly as a (users, items) pair of int arrays /
+    a dict with CUSTOMER_ID and PRODUCT_ID;
   * splits, shuffles and samplers are seeded (the reference's are not reproducible);
   * plotting / model_to_dot / SMB access are out of scope (not compute).
 """
@@ -147,6 +148,11 @@ class RModel:
             users, items = path[self.CUSTOMER_ID], path[self.PRODUCT_ID]
         elif isinstance(path, (tuple, list)) and len(path) == 2:
             users, items = path
+        elif isinstance(path, str) and path.endswith(".brkc"):
+            # binary columnar cache written by interactions.csv_to_cache: memory-mapped columns
+            from .interactions import InteractionCache
+            cache = InteractionCache(path)
+            users, items = cache.columns["user"], cache.columns["item"]
         else:
             import pandas as pd
             with self.dataStore.openFile(path=path, mode='r') as f:
@@ -164,11 +170,26 @@ class RModel:
     def isMaster(self, taskType, taskId) -> bool:
         return taskType is None or taskType == 'chief' or (taskType == 'worker' and taskId == 0)
 
+    def checkpointMeta(self) -> dict:
+        """What restoreFromLatestCheckPoint needs to rebuild the model before loading tensors (the reference's
+        SavedModel carries its graph; its test users / products sit in the pickles of RModel.py:28-29)."""
+        return {"model": self.modelName}
+
+    def buildFromMeta(self, meta: dict):
+        raise NotImplementedError
+
     def saveCheckPoint(self):
-        import torch
-        os.makedirs(os.path.dirname(self.checkpointPath), exist_ok=True)
-        torch.save(self.model.state_dict(), self.checkpointPath)
+        """model.save(checkpointPath) (RModel.py:139): a checkpoint directory (checkpoint.py) holding the weights,
+        optimizer slots and step -- readable by a process with any number of GPUs."""
+        from . import checkpoint as CK
+        CK.save_state_dict(self.checkpointPath, self.model.state_dict(), meta=self.checkpointMeta())
 
     def restoreFromLatestCheckPoint(self):
-        import torch
-        self.model.load_state_dict(torch.load(self.checkpointPath, map_location="cpu"))
+        """tf.keras.models.load_model(checkpointPath) (RModel.py:172-173), as the REST endpoint calls it on a fresh
+        object (src/restful/RecommendationEndpoint.py:49): the model is rebuilt from the sizes recorded in the
+        checkpoint, then the tensors are loaded."""
+        from . import checkpoint as CK
+        meta = CK.read_manifest(self.checkpointPath).get("meta", {})
+        if self.model is None:
+            self.buildFromMeta(meta)
+        self.model.load_state_dict(CK.load_state_dict(self.checkpointPath))

@@ -40,6 +40,49 @@ def shard_rows(rows, G):
     return (rows + G - 1) // G
 
 
+def save_sharded_model(dirpath, tables, replicated, G, rank, emulate, meta=None):
+    """Checkpoint of a row-sharded model (checkpoint.py): every rank writes its shards of
+    the weights and optimizer slots, rank 0 the replicated tensors and -- after a barrier -- the manifest.
+    tables: {name: ShardedTable}."""
+    from . import checkpoint as CK
+    ranks = list(range(G - 1, -1, -1)) if emulate else [rank]          # emulation: rank 0 (the manifest) goes last
+    barrier = None
+    if not emulate and G > 1:
+        torch.cuda.synchronize()
+        barrier = dist.barrier
+    for r in ranks:
+        shd = {}
+        for name, t in tables.items():
+            tab = t.tables[r]
+            shd[name] = (tab.w, t.rows)
+            if tab.m is not None:
+                shd[name + "_m"] = (tab.m, t.rows)
+            if tab.v is not None:
+                shd[name + "_v"] = (tab.v, t.rows)
+        CK.save_checkpoint(dirpath, replicated=replicated if r == 0 else None, sharded=shd, rank=r, world=G,
+                           meta=meta, barrier=barrier)
+    return dirpath
+
+
+def load_sharded_model(dirpath, tables, G, rank, emulate):
+    """Restores the shards this process owns -- whatever world size wrote the checkpoint.  Returns (replicated, meta)."""
+    from . import checkpoint as CK
+    rep, meta = {}, {}
+    for r in (range(G) if emulate else [rank]):
+        rep, shd, meta = CK.load_checkpoint(dirpath, r, G)
+        for name, t in tables.items():
+            tab = t.tables[r]
+            tab.w.copy_(torch.from_numpy(shd[name]))
+            if tab.m is not None and name + "_m" in shd:
+                tab.m.copy_(torch.from_numpy(shd[name + "_m"]))
+            if tab.v is not None and name + "_v" in shd:
+                tab.v.copy_(torch.from_numpy(shd[name + "_v"]))
+    if not emulate and G > 1:
+        torch.cuda.synchronize()
+        dist.barrier()                                   # nobody gathers peer rows before every owner has loaded
+    return rep, meta
+
+
 class ShardedTable:
     """One row-sharded embedding table: local shard as an H.Table plus every rank's shard pointers."""
 
@@ -261,6 +304,49 @@ class ShardedNeuMFNet:
                 raise RuntimeError("brk_peer_barrier timed out (a rank did not reach the step)")
 
 
+    # ---- checkpoint -----------------------------------------------------------
+    def _dense_slots(self):
+        """(m, v) of the dense block as full-length host arrays: local slots, or -- in peer mode, where every rank
+        keeps the Adam moments of its own slice only (distributed.PeerArena) -- the slices summed over ranks."""
+        n = self.dense.w.numel()
+        if self.peer is None:
+            return self.dense.m.view(-1).cpu().numpy(), self.dense.v.view(-1).cpu().numpy()
+        out = []
+        for part in (self.peer.m, self.peer.v):
+            full = torch.zeros(n, dtype=torch.float32, device=self.device)
+            lo, hi = self.peer.slice_lo, self.peer.slice_hi
+            full[lo:hi] = part[:hi - lo]
+            dist.all_reduce(full)
+            out.append(full.cpu().numpy())
+        return tuple(out)
+
+    def save_checkpoint(self, dirpath):
+        m, v = self._dense_slots()
+        rep = {"dense": self.dense.w.view(-1), "dense_m": m, "dense_v": v, "bn_moving": self.bn_moving,
+               "opt_state": self.optimizer.state}
+        tabs = dict(zip(("uMLP", "iMLP", "uMF", "iMF"), self._tables()))
+        return save_sharded_model(dirpath, tabs, rep, self.G, self.rank, self.emulate,
+                                  meta={"model": "ShardedNeuMFNet", "E": self.E, "numUser": self.numUser,
+                                        "numItem": self.numItem, "act": self.act, "loss": self.loss})
+
+    def load_checkpoint(self, dirpath):
+        tabs = dict(zip(("uMLP", "iMLP", "uMF", "iMF"), self._tables()))
+        rep, meta = load_sharded_model(dirpath, tabs, self.G, self.rank, self.emulate)
+        n = self.dense.w.numel()
+        self.dense.w.view(-1).copy_(torch.from_numpy(rep["dense"][:n]))
+        m, v = torch.from_numpy(rep["dense_m"][:n]).to(self.device), torch.from_numpy(rep["dense_v"][:n]).to(self.device)
+        if self.peer is None:
+            self.dense.m.view(-1).copy_(m); self.dense.v.view(-1).copy_(v)
+        else:
+            lo, hi = self.peer.slice_lo, self.peer.slice_hi
+            self.peer.m[:hi - lo].copy_(m[lo:hi]); self.peer.v[:hi - lo].copy_(v[lo:hi])
+            torch.cuda.synchronize(self.device)
+            dist.barrier()
+        self.bn_moving.copy_(torch.from_numpy(rep["bn_moving"]))
+        self.optimizer.state.copy_(torch.from_numpy(rep["opt_state"]))
+        return meta
+
+
 class PeerBarrier:
     """brk_peer_barrier with its symmetric flag block (one instance per model)."""
 
@@ -323,3 +409,12 @@ class ShardedBPRNet:
     def check(self):
         if self.barrier is not None:
             self.barrier.check()
+
+    def save_checkpoint(self, dirpath):
+        return save_sharded_model(dirpath, {"user": self.user, "item": self.item}, {"opt_state": self.optimizer.state},
+                                  self.G, self.rank, self.emulate, meta={"model": "ShardedBPRNet", "d": self.d})
+
+    def load_checkpoint(self, dirpath):
+        rep, meta = load_sharded_model(dirpath, {"user": self.user, "item": self.item}, self.G, self.rank, self.emulate)
+        self.optimizer.state.copy_(torch.from_numpy(rep["opt_state"]))
+        return meta

@@ -11,7 +11,8 @@ Differences from the reference, stated once:
     compile() accepts hotpath.Adagrad / hotpath.Adam objects or the strings "Adagrad" / "Adam";
   * crossValidation takes in-memory folds (lists of dicts with the userKey / itemKey [/ resKey]
     columns) instead of prompting for SMB credentials (twoTower.py:130-134);
-  * StringLookup is a host dictionary: vocabulary entry j -> row j + 2 (0 mask, 1 OOV), as TF 2.3/2.4.
+  * StringLookup: vocabulary entry j -> row j + 2 (0 mask, 1 OOV), as TF 2.3/2.4; looked up by a device hash
+    table (csrc/pipeline.cu) for ids with an exact 64-bit key, by a host dictionary for longer strings.
 """
 import ctypes as C
 
@@ -30,9 +31,37 @@ class StringLookup:
     def __init__(self, vocabulary):
         self.vocabulary = list(vocabulary)
         self._map = {v: j + 2 for j, v in enumerate(self.vocabulary)}
+        self._dev = None          # pipeline.Vocabulary (device hash table), built on first device lookup
+        self._packable = True
 
     def __call__(self, values):
         return np.fromiter((self._map.get(v, 1) for v in values), dtype=np.int32, count=len(values))
+
+    def lookup_device(self, values, device):
+        """int32 device tensor of indices.  Ids that have an exact 64-bit key (integers, strings of <= 8 bytes --
+        the reference's CUSTOMER_ID / MATERIAL codes, loadBinaryMovieLens.py:49) are mapped by the device hash table
+        (csrc/pipeline.cu); longer strings keep the host dictionary (text handling, not the hot path)."""
+        from . import pipeline as PL
+        if self._packable:
+            try:
+                vals = np.asarray(list(values)) if not isinstance(values, np.ndarray) else values
+                voc = np.asarray(self.vocabulary)
+                kind = lambda a: "i" if a.dtype.kind in "iu" else "S"
+                if len(vals) and len(voc) and kind(vals) != kind(voc):
+                    raise TypeError("values and vocabulary are of different kinds")      # host dictionary decides
+                keys = PL.pack_keys(vals)
+                if self._dev is None:
+                    self._dev = PL.Vocabulary(device)
+                    self._dev.build(PL.pack_keys(voc), offset=2)
+                    if self._dev.size != len(self.vocabulary):
+                        raise ValueError("StringLookup vocabulary has duplicate entries")
+                return self._dev.lookup(torch.from_numpy(keys.view(np.int64)).to(device), oov=1)
+            except (ValueError, TypeError) as e:
+                if "duplicate" in str(e):
+                    raise
+                if "different kinds" not in str(e):
+                    self._packable = False
+        return torch.from_numpy(self(values)).to(device)
 
 
 class Tower:
@@ -112,9 +141,7 @@ class TwoTowerModel:
 
     def _ids(self, info):
         dev = self.device
-        u = torch.from_numpy(self.userTowerIn(info[self.userKey])).to(dev)
-        i = torch.from_numpy(self.itemTowerIn(info[self.itemKey])).to(dev)
-        return u, i
+        return self.userTowerIn.lookup_device(info[self.userKey], dev), self.itemTowerIn.lookup_device(info[self.itemKey], dev)
 
     def _step(self, u, i, labels, training, loss_out=None):
         B = u.numel()
