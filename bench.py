@@ -326,6 +326,8 @@ def product_arm(args):
     clocks = sampler.stop()
     assert np.isfinite(hloss[W:W + K].numpy()).all()
     extras = secondary_measurements(dev) if (world == 1 and not args.no_extras) else None
+    if extras is not None:
+        extras["svd_fit"] = svd_measurement(dev, cpu_baseline=not args.no_cpu_baseline)
 
     # ---- max over ranks ---------------------------------------------------------------------------
     t = torch.tensor([total_ms, hot_ms, e2e_ms, float(fb_ms.mean())], dtype=torch.float64, device=dev)
@@ -404,6 +406,46 @@ def product_arm(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def svd_measurement(dev, cpu_baseline=True):
+    """Biased-SVD epoch on the ML-1M-shaped file, the reference's d = 50, float64, exact
+    sequential semantics; the sequential C loop of the oracle timed beside it (1 core: the algorithm is sequential)."""
+    from binrec_b200 import SVD as S
+    from binrec_b200 import synth
+    u, i = synth.make_interactions()
+    r = np.random.default_rng(5).integers(1, 6, len(u)).astype(np.float64)
+    U, I, d = synth.ML1M_USERS, synth.ML1M_ITEMS, S.NUMBER_OF_EMBEDDINGS
+    frame = S.Ratings(u, i, r, num_users=U, num_items=I, device=dev)
+    P, Q, bu, bi = S.init_parameters(U, I, d, seed=0, device=dev)
+    mu = float(r.mean())
+    for _ in range(2):
+        S.fit_model(frame, P, Q, bu, bi, mu)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 5
+    e0.record()
+    for _ in range(iters):
+        S.fit_model(frame, P, Q, bu, bi, mu)
+    e1.record(); torch.cuda.synchronize()
+    S.check_fit(frame)
+    s = e0.elapsed_time(e1) * 1e-3 / iters
+    chain = frame.critical_path()
+    out = {"value": len(u) / s, "unit": "ratings/s", "ms_per_epoch": s * 1e3, "critical_path": chain,
+           "ns_per_chain_link": s * 1e9 / chain,
+           "config": f"biased SVD (SVD.py:187-221), {len(u)} ratings in file order, {U} x {I}, d={d}, float64, "
+                     f"sequential semantics kept exactly (ticketed rows, one cooperative launch per epoch)"}
+    if cpu_baseline:
+        from oracle import svd as OS                                    # cpu_baseline leg: the checker, timed
+        Pc, Qc = P.cpu().numpy().copy(), Q.cpu().numpy().copy()
+        buc, bic = bu.cpu().numpy().copy(), bi.cpu().numpy().copy()
+        OS.fit_epoch_c(u[:1000], i[:1000], r[:1000], Pc, Qc, buc, bic, mu, 0.01, 0.0, 0.01)
+        t0 = time.perf_counter()
+        OS.fit_epoch_c(u, i, r, Pc, Qc, buc, bic, mu, 0.01, 0.0, 0.01)
+        t = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": len(u) / t, "unit": "ratings/s", "cores": 1, "kind": "port",
+                               "sample": "one full epoch of the same file, sequential C loop (oracle/svd_c.c, gcc -O2)"}
+    return out
 
 
 def secondary_measurements(dev):

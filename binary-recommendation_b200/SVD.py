@@ -1,0 +1,322 @@
+"""Biased-SVD matrix factorisation -- drop-in mirror of the reference's src/origin_models/svd/SVD.py
+(SURVEY.md section 8 row f4).
+
+The reference is a module of constants and functions driven by pandas chunks: digest (:105-124) builds the id
+dictionaries and the global mean, fit_model (:187-221) walks the ratings one `iterrows()` row at a time,
+mean_square_error / mean_absolute_error (:223-253) walk them again, do_topk (:418-442) pushes the float32
+matrices through TFRS BruteForce and trainers/topKmetrics.  The names, argument order and return values are kept;
+what changes is underneath:
+
+  * the chunk iterator becomes a `Ratings` frame: dense int32 user / item ids, float64 ratings and the
+    dependency tickets of the file order, resident in HBM;
+  * fit_model is one cooperative kernel launch per epoch that applies the ratings with EXACTLY the sequential
+    semantics (csrc/svd.cu) -- not a Hogwild approximation;
+  * matrices and bias vectors are float64 device tensors, updated in place like the NumPy arrays.
+
+No CPU fallback: every function raises BrkError without the CUDA library / a device.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import hotpath as H
+from . import pipeline as PL
+from . import topKmetrics as topk
+
+# module constants of the reference (SVD.py:14-62)
+EPOCHS = 1
+LEARNING_RATE = 0.01
+EMBEDDING_REGULARIZATION = 0
+BIAS_REGULARIZATION = 0.01
+NUMBER_OF_EMBEDDINGS = 50
+TOPK_BATCH_SIZE = 5000
+EPOCH_ERROR_CALCULATION_FREQUENCY = 1
+EVALUATE = True
+TRANSACTION_COUNT_SCALE = 0.5
+QUANTITY_SUM_SCALE = 0.5
+TRANSACTION_COUNT_QUINTILES = (1, 2, 4)
+QUANTITY_SUM_QUINTILES = (1, 1, 2)
+
+
+def _dev(device=None):
+    if not torch.cuda.is_available():
+        raise N.BrkError("no CUDA device: the brk_b200 hot path is sm_100a CUDA only (no CPU fallback)")
+    return torch.device(device) if device is not None else torch.device(f"cuda:{torch.cuda.current_device()}")
+
+
+def _f64(t, name, dev=None):
+    if not isinstance(t, torch.Tensor):
+        t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.float64)).to(_dev(dev))
+    if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
+        raise TypeError(f"{name} must be a contiguous float64 CUDA tensor")
+    return t
+
+
+def _i32(t, name, dev=None):
+    if not isinstance(t, torch.Tensor):
+        t = torch.from_numpy(np.ascontiguousarray(t, dtype=np.int32)).to(_dev(dev))
+    if t.dtype != torch.int32 or not t.is_cuda or not t.is_contiguous():
+        raise TypeError(f"{name} must be a contiguous int32 CUDA tensor")
+    return t
+
+
+def _key_kind(column):
+    return "i" if isinstance(column, torch.Tensor) or np.asarray(column).dtype.kind in "iu" else "S"
+
+
+def _reduce_ws(dev):
+    return torch.empty(max(int(N.lib().brk_svd_reduce_workspace_bytes(N.ctx(dev))), 256), dtype=torch.uint8, device=dev)
+
+
+class Ratings:
+    """The reference's `dataset` (an iterable of DataFrame chunks) as device columns in file order:
+    users / items int32 dense ids, ratings float64, and `sched` int32 [n, 4] = (user, item, user ticket,
+    item ticket) -- how many earlier ratings touch the same user / item row (brk_svd_schedule)."""
+
+    def __init__(self, users, items, ratings, num_users=None, num_items=None, device=None):
+        dev = _dev(device)
+        self.users = _i32(users, "users", dev)
+        self.items = _i32(items, "items", dev)
+        self.ratings = _f64(ratings, "ratings", dev)
+        n = self.users.numel()
+        if self.items.numel() != n or self.ratings.numel() != n:
+            raise ValueError("users, items and ratings must have one entry per rating")
+        self.num_users = int(num_users) if num_users is not None else (int(self.users.max().item()) + 1 if n else 1)
+        self.num_items = int(num_items) if num_items is not None else (int(self.items.max().item()) + 1 if n else 1)
+        self.device = self.users.device
+        self.sched = torch.empty((max(n, 1), 4), dtype=torch.int32, device=self.device)
+        lib = N.lib()
+        ws_bytes = int(lib.brk_svd_schedule_workspace_bytes(n, self.num_users, self.num_items))
+        if ws_bytes < 0:
+            raise ValueError(f"unsupported sizes: n={n} users={self.num_users} items={self.num_items}")
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=self.device)
+        bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+        N.check(lib.brk_svd_schedule(N.ctx(self.device), N.ptr(self.users), N.ptr(self.items), n, self.num_users,
+                                     self.num_items, N.ptr(self.sched), N.ptr(bad), N.ptr(ws), ws.numel(),
+                                     N.stream_ptr()), "brk_svd_schedule")
+        if int(bad.item()):
+            raise IndexError(f"rating ids outside [0, {self.num_users}) x [0, {self.num_items})")
+        self._versions = torch.empty(self.num_users + self.num_items + 1, dtype=torch.int32, device=self.device)
+
+    def __len__(self):
+        return self.users.numel()
+
+    def critical_path(self):
+        """Length of the longest chain of ratings that must run one after the other (max dependency level) -- what
+        bounds an epoch on the device.  Host recurrence over the file; diagnostics only."""
+        u = self.users.cpu().numpy(); i = self.items.cpu().numpy()
+        lu = np.zeros(self.num_users, dtype=np.int64); li = np.zeros(self.num_items, dtype=np.int64)
+        for a, b in zip(u.tolist(), i.tolist()):
+            l = (lu[a] if lu[a] > li[b] else li[b]) + 1
+            lu[a] = l; li[b] = l
+        return int(max(lu.max(initial=0), li.max(initial=0)))
+
+
+def get_rating(transaction_count, quantity_sum, tc_scale=TRANSACTION_COUNT_SCALE, qs_scale=QUANTITY_SUM_SCALE,
+               tc_quintiles=TRANSACTION_COUNT_QUINTILES, qs_quintiles=QUANTITY_SUM_QUINTILES, device=None):
+    """get_rating with RATING_COLUMN = None (SVD.py:255-262) over whole columns: float64 ratings on the device."""
+    tc = _f64(transaction_count, "transaction_count", device)
+    qs = _f64(quantity_sum, "quantity_sum", device)
+    if tc.numel() != qs.numel():
+        raise ValueError("transaction_count and quantity_sum differ in length")
+    out = torch.empty_like(tc)
+    a = (C.c_double * 3)(*[float(x) for x in tc_quintiles]); b = (C.c_double * 3)(*[float(x) for x in qs_quintiles])
+    N.check(N.lib().brk_svd_quintile_ratings(N.ctx(tc.device), N.ptr(tc), N.ptr(qs), tc.numel(), float(tc_scale),
+                                             float(qs_scale), a, b, N.ptr(out), N.stream_ptr()),
+            "brk_svd_quintile_ratings")
+    return out
+
+
+def place_in_quintile(value, quintiles):
+    """SVD.py:264-270 for one value (host scalar helper, kept for callers of the reference's name)."""
+    q1, median, q3 = quintiles
+    return 4 if value > q3 else 3 if value > median else 2 if value > q1 else 1
+
+
+def digest(raw_users, raw_items, ratings, device=None):
+    """digest (SVD.py:105-124) over whole columns: returns (user_ids, item_ids, uid_max, iid_max, global_bias, frame)
+    where user_ids / item_ids are the reference's dicts raw id -> dense id (order of first appearance), global_bias
+    the mean rating, and frame the `Ratings` the other functions take in place of the chunk iterator."""
+    dev = _dev(device)
+    uv, iv = PL.Vocabulary(dev), PL.Vocabulary(dev)
+    u = uv.build(raw_users)
+    i = iv.build(raw_items)
+    r = _f64(ratings, "ratings", dev)
+    if r.numel() == 0:
+        raise ZeroDivisionError("digest of an empty rating file")          # the reference divides by the row count
+    out = torch.empty(2, dtype=torch.float64, device=dev)
+    N.check(N.lib().brk_svd_mean(N.ctx(dev), N.ptr(r), r.numel(), N.ptr(out), N.ptr(_reduce_ws(dev)), N.stream_ptr()),
+            "brk_svd_mean")
+    kind, kind_i = _key_kind(raw_users), _key_kind(raw_items)
+    uk, ik = uv.host_keys(kind), iv.host_keys(kind_i)
+    user_ids = {(int(k) if kind == "i" else k): j for j, k in enumerate(uk)}
+    item_ids = {(int(k) if kind_i == "i" else k): j for j, k in enumerate(ik)}
+    frame = Ratings(u, i, r, num_users=uv.size, num_items=iv.size, device=dev)
+    return user_ids, item_ids, uv.size - 1, iv.size - 1, float(out[0].item()), frame
+
+
+def init_parameters(number_of_users, number_of_items, number_of_embeddings=NUMBER_OF_EMBEDDINGS, seed=None, device=None):
+    """(user_matrix, item_matrix, user_bias_vector, item_bias_vector) as train_and_evaluate creates them
+    (SVD.py:446-449): U(0, 1) / d matrices, zero biases, float64."""
+    dev = _dev(device)
+    rng = np.random.default_rng(seed)
+    P = torch.from_numpy(rng.random((number_of_users, number_of_embeddings)) * (1 / number_of_embeddings)).to(dev)
+    Q = torch.from_numpy(rng.random((number_of_items, number_of_embeddings)) * (1 / number_of_embeddings)).to(dev)
+    return P, Q, torch.zeros(number_of_users, dtype=torch.float64, device=dev), \
+        torch.zeros(number_of_items, dtype=torch.float64, device=dev)
+
+
+def _check_params(frame, user_matrix, item_matrix, user_bias_vector, item_bias_vector):
+    P, Q = _f64(user_matrix, "user_matrix"), _f64(item_matrix, "item_matrix")
+    bu, bi = _f64(user_bias_vector, "user_bias_vector"), _f64(item_bias_vector, "item_bias_vector")
+    if P.dim() != 2 or Q.dim() != 2 or P.shape[1] != Q.shape[1]:
+        raise ValueError("user_matrix / item_matrix must be [rows, d] with one d")
+    if P.shape[0] < frame.num_users or Q.shape[0] < frame.num_items or bu.numel() < frame.num_users or \
+            bi.numel() < frame.num_items:
+        raise IndexError("parameter tables are smaller than the id range of the ratings")
+    return P, Q, bu, bi
+
+
+def fit_model(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias, user_ids=None,
+              item_ids=None, learning_rate=None, embedding_regularization=None, bias_regularization=None,
+              warps_per_sm=0):
+    """One pass over `dataset` (a Ratings frame) in file order, parameters updated in place (SVD.py:187-221).
+    Hyper-parameters default to the module constants, like the reference's globals."""
+    P, Q, bu, bi = _check_params(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector)
+    lr = LEARNING_RATE if learning_rate is None else learning_rate
+    ereg = EMBEDDING_REGULARIZATION if embedding_regularization is None else embedding_regularization
+    breg = BIAS_REGULARIZATION if bias_regularization is None else bias_regularization
+    N.check(N.lib().brk_svd_fit_epoch(N.ctx(dataset.device), N.ptr(dataset.sched), N.ptr(dataset.ratings), len(dataset),
+                                      N.ptr(P), N.ptr(Q), N.ptr(bu), N.ptr(bi), dataset.num_users, dataset.num_items,
+                                      P.shape[1], float(global_bias), float(lr), float(ereg), float(breg),
+                                      N.ptr(dataset._versions), int(warps_per_sm), N.stream_ptr()),
+            "brk_svd_fit_epoch")
+
+
+def check_fit(dataset):
+    """Raises if the last fit_model over `dataset` gave up on a wait (synchronises)."""
+    if int(dataset._versions[-1].item()) != 0:
+        raise N.BrkError("brk_svd_fit_epoch aborted: the schedule does not belong to these ratings")
+
+
+def predict(user, item, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias):
+    """predict (SVD.py:179-185) for one pair (Python ints -> float) or for id arrays (-> float64 device tensor)."""
+    P, Q = _f64(user_matrix, "user_matrix"), _f64(item_matrix, "item_matrix")
+    bu, bi = _f64(user_bias_vector, "user_bias_vector"), _f64(item_bias_vector, "item_bias_vector")
+    scalar = np.isscalar(user) and np.isscalar(item)
+    u = _i32(np.atleast_1d(user) if not isinstance(user, torch.Tensor) else user, "user", P.device)
+    i = _i32(np.atleast_1d(item) if not isinstance(item, torch.Tensor) else item, "item", P.device)
+    if u.numel() != i.numel():
+        raise ValueError("user and item differ in length")
+    if u.numel() and (int(u.min()) < 0 or int(u.max()) >= P.shape[0] or int(i.min()) < 0 or int(i.max()) >= Q.shape[0]):
+        raise IndexError("id outside the parameter tables")
+    out = torch.empty(u.numel(), dtype=torch.float64, device=P.device)
+    N.check(N.lib().brk_svd_predict(N.ctx(P.device), N.ptr(u), N.ptr(i), u.numel(), N.ptr(P), N.ptr(Q), N.ptr(bu),
+                                    N.ptr(bi), P.shape[1], float(global_bias), N.ptr(out), N.stream_ptr()),
+            "brk_svd_predict")
+    return float(out.item()) if scalar else out
+
+
+def _errors(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias):
+    P, Q, bu, bi = _check_params(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector)
+    if len(dataset) == 0:
+        raise ZeroDivisionError("mean error over an empty rating set")      # accumulator / count, SVD.py:247
+    out = torch.empty(2, dtype=torch.float64, device=dataset.device)
+    N.check(N.lib().brk_svd_errors(N.ctx(dataset.device), N.ptr(dataset.users), N.ptr(dataset.items),
+                                   N.ptr(dataset.ratings), len(dataset), N.ptr(P), N.ptr(Q), N.ptr(bu), N.ptr(bi),
+                                   P.shape[1], float(global_bias), N.ptr(out), N.ptr(_reduce_ws(dataset.device)),
+                                   N.stream_ptr()), "brk_svd_errors")
+    return out
+
+
+def mean_square_error(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias,
+                      user_ids=None, item_ids=None):
+    """SVD.py:252-253."""
+    return float(_errors(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias)[0].item())
+
+
+def mean_absolute_error(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias,
+                        user_ids=None, item_ids=None):
+    """SVD.py:249-250."""
+    return float(_errors(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias)[1].item())
+
+
+def recommend_users(users, user_matrix, item_matrix, k):
+    """(scores [n, k] float64, item rows [n, k] int32) for a list of dense user ids: plain dot products over the
+    whole item matrix, best first, ties -> lower item row (recommend, SVD.py:286-299, batched)."""
+    P, Q = _f64(user_matrix, "user_matrix"), _f64(item_matrix, "item_matrix")
+    u = _i32(np.atleast_1d(users) if not isinstance(users, torch.Tensor) else users, "users", P.device)
+    if u.numel() and (int(u.min()) < 0 or int(u.max()) >= P.shape[0]):
+        raise IndexError("user id outside user_matrix")
+    if int(k) < 1:
+        raise ValueError("k must be >= 1")
+    n, I = u.numel(), Q.shape[0]
+    vals = torch.empty((n, int(k)), dtype=torch.float64, device=P.device)
+    ids = torch.empty((n, int(k)), dtype=torch.int32, device=P.device)
+    chunk = max(1, min(n, (1 << 28) // max(I, 1)))                         # <= 2 GiB of float64 scores per launch
+    scores = torch.empty((min(chunk, max(n, 1)), I), dtype=torch.float64, device=P.device)
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        N.check(N.lib().brk_svd_recommend(N.ctx(P.device), N.ptr(P), N.ptr(u[a:b]), b - a, N.ptr(Q), I, P.shape[1],
+                                          int(k), N.ptr(scores), N.ptr(vals[a:b]), N.ptr(ids[a:b]), N.stream_ptr()),
+                "brk_svd_recommend")
+    return vals, ids
+
+
+def recommend(user_vector, item_matrix, k):
+    """recommend (SVD.py:286-299): the k best (index, prediction) of one user vector, best first.  The reference
+    returns its rating_prediction objects in replacement order; here they are (index, prediction) tuples sorted by
+    descending prediction (ties: lower index), the same set."""
+    Q = _f64(item_matrix, "item_matrix")
+    p = _f64(user_vector, "user_vector", Q.device).reshape(1, -1)
+    vals, ids = recommend_users(torch.zeros(1, dtype=torch.int32, device=Q.device), p, Q, k)
+    vals, ids = vals[0].cpu().numpy(), ids[0].cpu().numpy()
+    return [(int(i) if i >= 0 else None, float(v)) for v, i in zip(vals, ids)]
+
+
+def do_topk(user_matrix, item_matrix, test_idset, train_idset, user_ids, item_ids, k=10):
+    """do_topk (SVD.py:418-442): float32 BruteForce top-10 of every user over the item matrix (the fused scoring +
+    top-K kernel), then topKMetrics against the test pairs and against all pairs.  user_ids / item_ids: the
+    digest dicts raw id -> dense row."""
+    P, Q = _f64(user_matrix, "user_matrix"), _f64(item_matrix, "item_matrix")
+    index = H.BruteForceIndex(k).index(Q.to(torch.float32))                # tf.convert_to_tensor(..., float32), :422
+    q32 = P.to(torch.float32)
+    vals, ids = [], []
+    for a in range(0, P.shape[0], TOPK_BATCH_SIZE):
+        v, i = index(q32[a:a + TOPK_BATCH_SIZE])
+        vals.append(v); ids.append(i)
+    vals = torch.cat(vals).cpu().numpy(); ids = torch.cat(ids).cpu().numpy()
+    # the reference labels predictions with dense rows (user_id counter, item row) but probes sets of RAW ids
+    # (get_idset, :410-416) -- kept: predictions carry dense ids exactly as there
+    predictions = [(u, [(vals[u, j], int(ids[u, j])) for j in range(ids.shape[1])]) for u in range(ids.shape[0])]
+    actual_user_ids, actual_item_ids = list(user_ids.keys()), list(item_ids.keys())
+    return {"all_data": topk.topKMetrics(predictions, test_idset, actual_user_ids, actual_item_ids),
+            "train_set": topk.topKMetrics(predictions, train_idset, actual_user_ids, actual_item_ids)}
+
+
+def train_and_evaluate(dataset, test_set, user_ids, item_ids, uid_max, iid_max, global_bias, epochs=None, seed=None,
+                       evaluate=None, verbose=False):
+    """train_and_evaluate (SVD.py:437-497) on a training frame and a held-out frame (both `Ratings` over the same
+    dense id space).  Returns {'all_data', 'train_set', 'mse', 'epoch_mse'}; metrics only if evaluate."""
+    P, Q, bu, bi = init_parameters(uid_max + 1, iid_max + 1, NUMBER_OF_EMBEDDINGS, seed, dataset.device)
+    epoch_mse = []
+    for e in range(1, (EPOCHS if epochs is None else epochs) + 1):
+        fit_model(dataset, P, Q, bu, bi, global_bias, user_ids, item_ids)
+        if e % EPOCH_ERROR_CALCULATION_FREQUENCY == 0:
+            epoch_mse.append(mean_square_error(dataset, P, Q, bu, bi, global_bias))
+            if verbose:
+                print(f"::::EPOCH {e:=3}::::    MSE: {epoch_mse[-1]}", flush=True)
+    check_fit(dataset)
+    result = {"epoch_mse": epoch_mse, "parameters": (P, Q, bu, bi)}
+    if EVALUATE if evaluate is None else evaluate:
+        result["mse"] = mean_square_error(test_set, P, Q, bu, bi, global_bias)
+        inv_u = {v: k for k, v in user_ids.items()}; inv_i = {v: k for k, v in item_ids.items()}
+
+        def idset(frame):
+            u, i = frame.users.cpu().numpy(), frame.items.cpu().numpy()
+            return {(inv_u[int(a)], inv_i[int(b)]) for a, b in zip(u, i)}
+        test_idset = idset(test_set)
+        result.update(do_topk(P, Q, test_idset, test_idset | idset(dataset), user_ids, item_ids))
+    return result

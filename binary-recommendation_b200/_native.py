@@ -65,7 +65,7 @@ class brk_twotower_workspace(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("eu", "ei", "q", "c", "dq", "dc", "scores", "ones", "acc")]
 
 
-_P, _I32, _I64, _U32, _F32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float
+_P, _I32, _I64, _U32, _F32, _F64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float, C.c_double
 
 # name -> (restype, argtypes); mirrors include/brk_b200.h one to one.
 SIGNATURES = {
@@ -125,6 +125,17 @@ SIGNATURES = {
     "brk_vocab_workspace_bytes": (C.c_int64, [_I64]),
     "brk_vocab_build_u64": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _I64, _P, _P, _P, _P, _P]),
     "brk_vocab_lookup_u64": (C.c_int, [_P, _P, _I64, _P, _P, _I64, _I32, _P, _P]),
+    "brk_svd_schedule_workspace_bytes": (C.c_int64, [_I64, _I64, _I64]),
+    "brk_svd_schedule": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _I64, _P]),
+    "brk_svd_fit_epoch": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I32, _F64, _F64, _F64, _F64, _P,
+                                    _I32, _P]),
+    "brk_svd_predict": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _I32, _F64, _P, _P]),
+    "brk_svd_reduce_workspace_bytes": (C.c_int64, [_P]),
+    "brk_svd_errors": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _I32, _F64, _P, _P, _P]),
+    "brk_svd_mean": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
+    "brk_svd_quintile_ratings": (C.c_int, [_P, _P, _P, _I64, _F64, _F64, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                           _P, _P]),
+    "brk_svd_recommend": (C.c_int, [_P, _P, _P, _I32, _P, _I64, _I32, _I32, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -417,6 +417,56 @@ int brk_vocab_lookup_u64(brk_ctx* ctx, const uint64_t* keys, int64_t n, const ui
                          const int32_t* table_vals, int64_t capacity, int32_t oov, int32_t* ids,
                          void* stream);
 
+/* ---- biased-SVD SGD: src/origin_models/svd/SVD.py ---------------------------
+ * float64 throughout, like the NumPy original (np.random.random / np.zeros, SVD.py:446-449).
+ * brk_svd_schedule: the dependency tickets of a rating file.  sched is int32 [n, 4] = (user, item, tu, ti) with
+ *   tu[k] / ti[k] = number of earlier ratings (file order) of the same user / item; built by a stable radix sort
+ *   per key column.  *bad_id (device int32) becomes 1 if an id is outside [0, num_users) / [0, num_items): such a
+ *   schedule must not be used.  workspace: brk_svd_schedule_workspace_bytes(n, num_users, num_items) bytes.
+ * brk_svd_fit_epoch: ONE pass of fit_model (SVD.py:187-221) with the sequential semantics kept exactly: rating by
+ *   rating in file order,  e = r - (bu + bi + mu + <q, p>);  q' = q + lr (e p - emb_reg q);
+ *   p' = p + lr (e q' - emb_reg p)  (the UPDATED item vector);  b' = b + lr (e b - bias_reg b)  for both biases
+ *   (error times the bias itself, as the reference has it).  One warp per rating; a rating starts when the version
+ *   counters of its two rows equal its tickets and bumps them when done -- ratings that share no row run
+ *   concurrently, ratings that share one run in file order.  Result = the sequential pass up to the summation
+ *   order inside the dot product (element-wise operations are not contracted into FMAs).
+ *   versions: device uint32 [num_users + num_items + 1] scratch, zeroed by the call; the last word is an abort
+ *   flag that is non-zero afterwards only if a wait exceeded its bound (sched does not belong to these sizes).
+ *   warps_per_sm: resident warps per SM (0 = as many as fit).  d <= 512.  Cooperative launch.
+ * brk_svd_predict: out[k] = bu[u] + bi[i] + mu + <Q[i], P[u]>  (predict, SVD.py:179-185).
+ * brk_svd_errors: out[0] = mean squared error, out[1] = mean absolute error of rating - prediction over n >= 1
+ *   ratings (mean_generic_error, SVD.py:223-253); partial sums are combined in a fixed order.
+ *   workspace: brk_svd_reduce_workspace_bytes(ctx) bytes.
+ * brk_svd_mean: out[0] = mean of x (the global bias, calculate_average SVD.py:139-161), out[1] = 0.
+ * brk_svd_quintile_ratings: get_rating without a rating column (SVD.py:255-270):
+ *   out = tc_scale * quintile(transaction_count, tc_quintiles) + qs_scale * quintile(quantity_sum, qs_quintiles),
+ *   quintile(v, (q1, median, q3)) = 4 if v > q3, 3 if v > median, 2 if v > q1, else 1.  Quintiles: HOST double[3].
+ * brk_svd_recommend: recommend (SVD.py:286-299) for a list of users: scores [n_users, num_items] (device scratch)
+ *   = <P[users[j]], Q[i]>, then the k best per user, score descending, ties -> lower item index (the reference's
+ *   strict '>' replacement keeps the earlier item); ids -1 / -inf pad when k > num_items. */
+int64_t brk_svd_schedule_workspace_bytes(int64_t n, int64_t num_users, int64_t num_items);
+int brk_svd_schedule(brk_ctx* ctx, const int32_t* users, const int32_t* items, int64_t n, int64_t num_users,
+                     int64_t num_items, int32_t* sched, int32_t* bad_id, void* workspace,
+                     int64_t workspace_bytes, void* stream);
+int brk_svd_fit_epoch(brk_ctx* ctx, const int32_t* sched, const double* ratings, int64_t n, double* P,
+                      double* Q, double* bu, double* bi, int64_t num_users, int64_t num_items, int32_t d,
+                      double mu, double lr, double emb_reg, double bias_reg, uint32_t* versions,
+                      int32_t warps_per_sm, void* stream);
+int brk_svd_predict(brk_ctx* ctx, const int32_t* users, const int32_t* items, int64_t n, const double* P,
+                    const double* Q, const double* bu, const double* bi, int32_t d, double mu, double* out,
+                    void* stream);
+int64_t brk_svd_reduce_workspace_bytes(const brk_ctx* ctx);
+int brk_svd_errors(brk_ctx* ctx, const int32_t* users, const int32_t* items, const double* ratings, int64_t n,
+                   const double* P, const double* Q, const double* bu, const double* bi, int32_t d, double mu,
+                   double* out_mse_mae, void* workspace, void* stream);
+int brk_svd_mean(brk_ctx* ctx, const double* x, int64_t n, double* out2, void* workspace, void* stream);
+int brk_svd_quintile_ratings(brk_ctx* ctx, const double* transaction_count, const double* quantity_sum,
+                             int64_t n, double tc_scale, double qs_scale, const double* tc_quintiles_host,
+                             const double* qs_quintiles_host, double* out, void* stream);
+int brk_svd_recommend(brk_ctx* ctx, const double* P, const int32_t* users, int32_t n_users, const double* Q,
+                      int64_t num_items, int32_t d, int32_t k, double* scores, double* out_vals,
+                      int32_t* out_ids, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
