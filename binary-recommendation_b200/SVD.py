@@ -98,7 +98,9 @@ class Ratings:
                                      N.stream_ptr()), "brk_svd_schedule")
         if int(bad.item()):
             raise IndexError(f"rating ids outside [0, {self.num_users}) x [0, {self.num_items})")
-        self._versions = torch.empty(self.num_users + self.num_items + 1, dtype=torch.int32, device=self.device)
+        self._fit_ws = None           # device scratch of fit_model, sized on first use (depends on d)
+        # rating count of the busiest row = a lower bound of the critical path; n / that = the parallelism on offer
+        self.max_row_count = int(self.sched[:n, 2:4].max().item()) + 1 if n else 0
 
     def __len__(self):
         return self.users.numel()
@@ -181,23 +183,33 @@ def _check_params(frame, user_matrix, item_matrix, user_bias_vector, item_bias_v
 
 def fit_model(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias, user_ids=None,
               item_ids=None, learning_rate=None, embedding_regularization=None, bias_regularization=None,
-              warps_per_sm=0):
+              warps_per_sm=None):
     """One pass over `dataset` (a Ratings frame) in file order, parameters updated in place (SVD.py:187-221).
-    Hyper-parameters default to the module constants, like the reference's globals."""
+    Hyper-parameters default to the module constants, like the reference's globals.  warps_per_sm: resident warps
+    per SM (0 = as many as fit); by default 8 when the file offers little parallelism (fewer than 512 ratings per
+    link of its longest row chain: more waiting warps only add polling traffic -- measured 5.8 vs 6.4 ms on the
+    ML-1M-shaped file), otherwise 0.  The result does not depend on it."""
     P, Q, bu, bi = _check_params(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector)
     lr = LEARNING_RATE if learning_rate is None else learning_rate
     ereg = EMBEDDING_REGULARIZATION if embedding_regularization is None else embedding_regularization
     breg = BIAS_REGULARIZATION if bias_regularization is None else bias_regularization
+    if warps_per_sm is None:
+        warps_per_sm = 8 if len(dataset) < 512 * max(dataset.max_row_count, 1) else 0
+    need = int(N.lib().brk_svd_fit_workspace_bytes(dataset.num_users, dataset.num_items, P.shape[1]))
+    if need < 0:
+        raise ValueError(f"unsupported row width d={P.shape[1]} (1..512)")
+    if dataset._fit_ws is None or dataset._fit_ws.numel() < need:
+        dataset._fit_ws = torch.empty(need, dtype=torch.uint8, device=dataset.device)
     N.check(N.lib().brk_svd_fit_epoch(N.ctx(dataset.device), N.ptr(dataset.sched), N.ptr(dataset.ratings), len(dataset),
                                       N.ptr(P), N.ptr(Q), N.ptr(bu), N.ptr(bi), dataset.num_users, dataset.num_items,
                                       P.shape[1], float(global_bias), float(lr), float(ereg), float(breg),
-                                      N.ptr(dataset._versions), int(warps_per_sm), N.stream_ptr()),
-            "brk_svd_fit_epoch")
+                                      N.ptr(dataset._fit_ws), dataset._fit_ws.numel(), int(warps_per_sm),
+                                      N.stream_ptr()), "brk_svd_fit_epoch")
 
 
 def check_fit(dataset):
     """Raises if the last fit_model over `dataset` gave up on a wait (synchronises)."""
-    if int(dataset._versions[-1].item()) != 0:
+    if dataset._fit_ws is not None and int(dataset._fit_ws[:4].view(torch.int32).item()) != 0:
         raise N.BrkError("brk_svd_fit_epoch aborted: the schedule does not belong to these ratings")
 
 

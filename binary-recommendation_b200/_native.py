@@ -128,7 +128,8 @@ SIGNATURES = {
     "brk_svd_schedule_workspace_bytes": (C.c_int64, [_I64, _I64, _I64]),
     "brk_svd_schedule": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _I64, _P]),
     "brk_svd_fit_epoch": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _I64, _I64, _I32, _F64, _F64, _F64, _F64, _P,
-                                    _I32, _P]),
+                                    _I64, _I32, _P]),
+    "brk_svd_fit_workspace_bytes": (C.c_int64, [_I64, _I64, _I32]),
     "brk_svd_predict": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _I32, _F64, _P, _P]),
     "brk_svd_reduce_workspace_bytes": (C.c_int64, [_P]),
     "brk_svd_errors": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _I32, _F64, _P, _P, _P]),

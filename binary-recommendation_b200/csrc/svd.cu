@@ -144,6 +144,127 @@ __global__ void __launch_bounds__(kSvdThreads) svd_epoch_kernel(SvdFit a) {
   }
 }
 
+// ---- second form: self-validating rows ------------------------------------------------------------------------------
+// The flag form above pays, per hand-over of a row from one warp to the next: row stores -> fence -> flag store, then
+// on the other side flag poll -> row loads (about 3.5 L2 round trips).  Here every 8-byte word of a row carries its own
+// version: a float64 element is two words {low half | version << 32} {high half | version << 32} written by one
+// st.v2.b64 (two 8-byte accesses, each single-copy atomic).  The consumer polls the row itself and accepts a word
+// when its version equals the ticket; version t of a row is written once (by the rating with ticket t - 1), read by
+// exactly one warp (the rating with ticket t) and then overwritten by that same warp -- no fence, no separate flag,
+// no reader that could see a torn row.  Parameters are packed into this form at the start of the epoch and unpacked
+// at its end (two streaming passes over the tables).
+struct SvdLL {
+  const int4* sched;
+  const double* ratings;
+  int64_t n;
+  ulonglong2 *P, *Q, *bu, *bi;
+  uint32_t* abort;
+  double mu, lr, ereg, breg;
+  int32_t d;
+};
+__device__ __forceinline__ ulonglong2 ld_ll(const ulonglong2* p) {
+  ulonglong2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ ulonglong2 ll_pack(double x, uint32_t ver) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x), v = (unsigned long long)ver << 32;
+  return make_ulonglong2(v | (b & 0xffffffffull), v | (b >> 32));
+}
+__device__ __forceinline__ void st_ll(ulonglong2* p, double x, uint32_t ver) {
+  const ulonglong2 w = ll_pack(x, ver);
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1,%2};" :: "l"(p), "l"(w.x), "l"(w.y) : "memory");
+}
+__device__ __forceinline__ bool ll_valid(const ulonglong2& v, uint32_t ver) {
+  return uint32_t(v.x >> 32) == ver && uint32_t(v.y >> 32) == ver;
+}
+__device__ __forceinline__ double ll_value(const ulonglong2& v) {
+  return __longlong_as_double((long long)((v.y << 32) | (v.x & 0xffffffffull)));
+}
+
+template <int EPL>
+__global__ void __launch_bounds__(kSvdThreads) svd_epoch_ll_kernel(SvdLL a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t W = int64_t(gridDim.x) * kSvdWarps;
+  int64_t k = int64_t(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+  if (k >= a.n) return;
+  int4 s = __ldg(a.sched + k);
+  double r = __ldg(a.ratings + k);
+  uint32_t live = 0;                                   // bit e: element lane + 32 e exists
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) live |= (lane + 32 * e < a.d) ? (1u << e) : 0u;
+  while (true) {
+    const int64_t kn = k + W;
+    int4 sn = s;
+    double rn = r;
+    if (kn < a.n) { sn = __ldg(a.sched + kn); rn = __ldg(a.ratings + kn); }
+
+    const uint32_t tu = uint32_t(s.z), ti = uint32_t(s.w);
+    ulonglong2* prow = a.P + int64_t(s.x) * a.d + lane;
+    ulonglong2* qrow = a.Q + int64_t(s.y) * a.d + lane;
+    ulonglong2* brow = lane == 0 ? a.bu + s.x : a.bi + s.y;       // lane 0: user bias, lane 1: item bias
+    const uint32_t tb = lane == 0 ? tu : ti;
+    ulonglong2 pv[EPL], qv[EPL], bv = make_ulonglong2(0, 0);
+    uint32_t pend_p = live, pend_q = live;
+    bool pend_b = lane < 2;
+    uint32_t spins = 0;
+    while (true) {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        if (pend_p >> e & 1u) pv[e] = ld_ll(prow + 32 * e);
+        if (pend_q >> e & 1u) qv[e] = ld_ll(qrow + 32 * e);
+      }
+      if (pend_b) bv = ld_ll(brow);
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        if ((pend_p >> e & 1u) && ll_valid(pv[e], tu)) pend_p &= ~(1u << e);
+        if ((pend_q >> e & 1u) && ll_valid(qv[e], ti)) pend_q &= ~(1u << e);
+      }
+      if (pend_b && ll_valid(bv, tb)) pend_b = false;
+      if (__all_sync(0xffffffffu, (pend_p | pend_q) == 0u && !pend_b)) break;
+      if ((++spins & 1023u) == 0) {
+        if (spins >= kSvdSpinLimit) st_relaxed_u32(a.abort, 1u);
+        if (ld_relaxed_u32(a.abort) != 0u) return;
+      }
+    }
+    double p[EPL], q[EPL];
+    double dot = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      p[e] = (live >> e & 1u) ? ll_value(pv[e]) : 0.0;
+      q[e] = (live >> e & 1u) ? ll_value(qv[e]) : 0.0;
+      dot = __dadd_rn(dot, __dmul_rn(q[e], p[e]));
+    }
+    dot = warp_sum_f64(dot);
+    const double b_mine = ll_value(bv);
+    const double b_u = __shfl_sync(0xffffffffu, b_mine, 0), b_i = __shfl_sync(0xffffffffu, b_mine, 1);
+    const double err = __dsub_rn(r, __dadd_rn(__dadd_rn(__dadd_rn(b_u, b_i), a.mu), dot));
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      if (live >> e & 1u) {
+        const double qn = svd_rule(q[e], p[e], err, a.lr, a.ereg);
+        const double pn = svd_rule(p[e], qn, err, a.lr, a.ereg);
+        st_ll(qrow + 32 * e, qn, ti + 1u);
+        st_ll(prow + 32 * e, pn, tu + 1u);
+      }
+    }
+    if (lane < 2) st_ll(brow, svd_rule(b_mine, b_mine, err, a.lr, a.breg), tb + 1u);
+    if (kn >= a.n) break;
+    k = kn; s = sn; r = rn;
+  }
+}
+
+// plain float64 tables <-> self-validating form (version 0), all four tables in one launch each way
+struct SvdTables { double* plain[4]; ulonglong2* ll[4]; int64_t end[4]; };   // end: running element counts
+__global__ void svd_pack_kernel(SvdTables t, int unpack) {
+  for (int64_t x = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; x < t.end[3]; x += int64_t(gridDim.x) * blockDim.x) {
+    const int a = x < t.end[0] ? 0 : x < t.end[1] ? 1 : x < t.end[2] ? 2 : 3;
+    const int64_t j = x - (a ? t.end[a - 1] : 0);
+    if (unpack) t.plain[a][j] = ll_value(t.ll[a][j]);
+    else t.ll[a][j] = ll_pack(t.plain[a][j], 0u);
+  }
+}
+
 // ---- schedule ---------------------------------------------------------------------------------------------
 __global__ void svd_hist_kernel(const int32_t* __restrict__ keys, int64_t n, int32_t rows, uint32_t* cnt,
                                 int32_t* iota, int32_t* bad) {
@@ -372,14 +493,14 @@ extern "C" int brk_svd_schedule(brk_ctx* ctx, const int32_t* users, const int32_
 }
 
 template <int EPL>
-static int svd_launch_epoch(brk_ctx* ctx, SvdFit& a, int warps_per_sm, cudaStream_t st) {
-  // BRK_SVD_POLL=1 selects the relaxed-poll variant (a measurement knob, not part of the ABI)
-  const char* env = getenv("BRK_SVD_POLL");
-  const bool relaxed = env && env[0] == '1';
-  const void* fn = relaxed ? (const void*)svd_epoch_kernel<EPL, 1> : (const void*)svd_epoch_kernel<EPL, 0>;
+static int svd_launch_epoch(brk_ctx* ctx, SvdFit& a, SvdLL& b, int warps_per_sm, cudaStream_t st) {
+  // BRK_SVD_FORM=flags selects the first form (version counters + fences); a measurement knob, not part of the ABI
+  const char* env = getenv("BRK_SVD_FORM");
+  const bool flags = env && env[0] == 'f';
+  const void* fn = flags ? (const void*)svd_epoch_kernel<EPL, 0> : (const void*)svd_epoch_ll_kernel<EPL>;
   int occ = 0;
-  if (relaxed) BRK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, svd_epoch_kernel<EPL, 1>, kSvdThreads, 0));
-  else BRK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, svd_epoch_kernel<EPL, 0>, kSvdThreads, 0));
+  if (flags) BRK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, svd_epoch_kernel<EPL, 0>, kSvdThreads, 0));
+  else BRK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, svd_epoch_ll_kernel<EPL>, kSvdThreads, 0));
   BRK_REQUIRE(occ >= 1, BRK_E_STATE, "brk_svd_fit_epoch: kernel does not fit an SM");
   int per_sm = occ;
   if (warps_per_sm > 0) {
@@ -389,33 +510,67 @@ static int svd_launch_epoch(brk_ctx* ctx, SvdFit& a, int warps_per_sm, cudaStrea
   int64_t grid = int64_t(ctx->sm_count) * per_sm;
   const int64_t need = (a.n + kSvdWarps - 1) / kSvdWarps;
   if (grid > need) grid = need;
-  void* args[] = {&a};
+  void* args[] = {flags ? (void*)&a : (void*)&b};
   BRK_CUDA(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(kSvdThreads), args, 0, st));
   return 0;
 }
 
+// workspace: [abort flag, 256 B] [P, Q, bu, bi in self-validating form, 16 B per element] [version counters of the
+// flag form, 4 B per row]
+static int64_t svd_fit_ws_bytes(int64_t U, int64_t I, int64_t d) {
+  return 256 + int64_t(align256(size_t((U + I) * (d + 1)) * 16)) + int64_t(align256(size_t(U + I) * 4));
+}
+extern "C" int64_t brk_svd_fit_workspace_bytes(int64_t num_users, int64_t num_items, int32_t d) {
+  if (num_users < 1 || num_items < 1 || d < 1 || d > 512) return BRK_E_ARG;
+  return svd_fit_ws_bytes(num_users, num_items, d);
+}
+
 extern "C" int brk_svd_fit_epoch(brk_ctx* ctx, const int32_t* sched, const double* ratings, int64_t n, double* P,
                                  double* Q, double* bu, double* bi, int64_t num_users, int64_t num_items, int32_t d,
-                                 double mu, double lr, double emb_reg, double bias_reg, uint32_t* versions,
-                                 int32_t warps_per_sm, void* stream) {
-  BRK_REQUIRE(ctx && P && Q && bu && bi && versions, BRK_E_ARG, "brk_svd_fit_epoch: null argument");
+                                 double mu, double lr, double emb_reg, double bias_reg, void* workspace,
+                                 int64_t workspace_bytes, int32_t warps_per_sm, void* stream) {
+  BRK_REQUIRE(ctx && P && Q && bu && bi && workspace, BRK_E_ARG, "brk_svd_fit_epoch: null argument");
   BRK_REQUIRE(n >= 0 && num_users >= 1 && num_items >= 1 && d >= 1 && d <= 512, BRK_E_ARG,
               "brk_svd_fit_epoch: n=%lld d=%d (1..512)", (long long)n, d);
+  BRK_REQUIRE(brk_aligned16(workspace) && workspace_bytes >= svd_fit_ws_bytes(num_users, num_items, d), BRK_E_ARG,
+              "brk_svd_fit_epoch: workspace %lld < %lld bytes or not 16-byte aligned", (long long)workspace_bytes,
+              (long long)svd_fit_ws_bytes(num_users, num_items, d));
   cudaStream_t st = (cudaStream_t)stream;
+  char* ws = reinterpret_cast<char*>(workspace);
+  BRK_CUDA(cudaMemsetAsync(ws, 0, 256, st));
   if (n == 0) return 0;
   BRK_REQUIRE(sched && ratings, BRK_E_ARG, "brk_svd_fit_epoch: null schedule / ratings");
   BRK_REQUIRE(brk_aligned16(sched), BRK_E_ALIGN, "brk_svd_fit_epoch: sched not 16-byte aligned");
-  BRK_CUDA(cudaMemsetAsync(versions, 0, size_t(num_users + num_items + 1) * 4, st));
+  const char* env = getenv("BRK_SVD_FORM");
+  const bool flags = env && env[0] == 'f';
+  ulonglong2* ll = reinterpret_cast<ulonglong2*>(ws + 256);
+  uint32_t* versions = reinterpret_cast<uint32_t*>(ws + 256 + align256(size_t((num_users + num_items) * (int64_t(d) + 1)) * 16));
   SvdFit a;
   a.sched = reinterpret_cast<const int4*>(sched); a.ratings = ratings; a.n = n;
   a.P = P; a.Q = Q; a.bu = bu; a.bi = bi;
-  a.ver_u = versions; a.ver_i = versions + num_users; a.abort = versions + num_users + num_items;
+  a.ver_u = versions; a.ver_i = versions + num_users; a.abort = reinterpret_cast<uint32_t*>(ws);
   a.mu = mu; a.lr = lr; a.ereg = emb_reg; a.breg = bias_reg; a.d = d;
-  if (d <= 32) return svd_launch_epoch<1>(ctx, a, warps_per_sm, st);
-  if (d <= 64) return svd_launch_epoch<2>(ctx, a, warps_per_sm, st);
-  if (d <= 128) return svd_launch_epoch<4>(ctx, a, warps_per_sm, st);
-  if (d <= 256) return svd_launch_epoch<8>(ctx, a, warps_per_sm, st);
-  return svd_launch_epoch<16>(ctx, a, warps_per_sm, st);
+  SvdLL b;
+  b.sched = a.sched; b.ratings = ratings; b.n = n;
+  b.P = ll; b.Q = b.P + num_users * int64_t(d); b.bu = b.Q + num_items * int64_t(d); b.bi = b.bu + num_users;
+  b.abort = a.abort; b.mu = mu; b.lr = lr; b.ereg = emb_reg; b.breg = bias_reg; b.d = d;
+  SvdTables t;
+  t.plain[0] = P; t.plain[1] = Q; t.plain[2] = bu; t.plain[3] = bi;
+  t.ll[0] = b.P; t.ll[1] = b.Q; t.ll[2] = b.bu; t.ll[3] = b.bi;
+  t.end[0] = num_users * int64_t(d); t.end[1] = t.end[0] + num_items * int64_t(d);
+  t.end[2] = t.end[1] + num_users; t.end[3] = t.end[2] + num_items;
+  const int pack_grid = grid_for(t.end[3], ctx->sm_count, 256);
+  if (flags) BRK_CUDA(cudaMemsetAsync(versions, 0, size_t(num_users + num_items) * 4, st));
+  else { svd_pack_kernel<<<pack_grid, 256, 0, st>>>(t, 0); BRK_LAUNCH_CHECK(); }
+  int rc;
+  if (d <= 32) rc = svd_launch_epoch<1>(ctx, a, b, warps_per_sm, st);
+  else if (d <= 64) rc = svd_launch_epoch<2>(ctx, a, b, warps_per_sm, st);
+  else if (d <= 128) rc = svd_launch_epoch<4>(ctx, a, b, warps_per_sm, st);
+  else if (d <= 256) rc = svd_launch_epoch<8>(ctx, a, b, warps_per_sm, st);
+  else rc = svd_launch_epoch<16>(ctx, a, b, warps_per_sm, st);
+  if (rc) return rc;
+  if (!flags) { svd_pack_kernel<<<pack_grid, 256, 0, st>>>(t, 1); BRK_LAUNCH_CHECK(); }
+  return 0;
 }
 
 extern "C" int brk_svd_predict(brk_ctx* ctx, const int32_t* users, const int32_t* items, int64_t n, const double* P,
@@ -431,7 +586,7 @@ extern "C" int brk_svd_predict(brk_ctx* ctx, const int32_t* users, const int32_t
 }
 
 extern "C" int64_t brk_svd_reduce_workspace_bytes(const brk_ctx* ctx) {
-  return ctx ? int64_t(ctx->sm_count) * 8 * 2 * sizeof(double) : BRK_E_ARG;
+  return ctx ? int64_t(ctx->sm_count) * 8 * 2 * int64_t(sizeof(double)) : int64_t(BRK_E_ARG);
 }
 
 extern "C" int brk_svd_errors(brk_ctx* ctx, const int32_t* users, const int32_t* items, const double* ratings,

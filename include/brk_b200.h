@@ -426,13 +426,15 @@ int brk_vocab_lookup_u64(brk_ctx* ctx, const uint64_t* keys, int64_t n, const ui
  * brk_svd_fit_epoch: ONE pass of fit_model (SVD.py:187-221) with the sequential semantics kept exactly: rating by
  *   rating in file order,  e = r - (bu + bi + mu + <q, p>);  q' = q + lr (e p - emb_reg q);
  *   p' = p + lr (e q' - emb_reg p)  (the UPDATED item vector);  b' = b + lr (e b - bias_reg b)  for both biases
- *   (error times the bias itself, as the reference has it).  One warp per rating; a rating starts when the version
- *   counters of its two rows equal its tickets and bumps them when done -- ratings that share no row run
- *   concurrently, ratings that share one run in file order.  Result = the sequential pass up to the summation
- *   order inside the dot product (element-wise operations are not contracted into FMAs).
- *   versions: device uint32 [num_users + num_items + 1] scratch, zeroed by the call; the last word is an abort
- *   flag that is non-zero afterwards only if a wait exceeded its bound (sched does not belong to these sizes).
- *   warps_per_sm: resident warps per SM (0 = as many as fit).  d <= 512.  Cooperative launch.
+ *   (error times the bias itself, as the reference has it).  One warp per rating; a rating starts when both of
+ *   its rows carry the version its tickets name and leaves them one version higher -- ratings that share no row
+ *   run concurrently, ratings that share one run in file order.  Result = the sequential pass up to the summation
+ *   order inside the dot product (element-wise operations are not contracted into FMAs).  During the epoch the
+ *   tables live in a self-validating form inside the workspace (every 8-byte word carries its version); P, Q, bu,
+ *   bi are read at the start and written back at the end of the call.
+ *   workspace: brk_svd_fit_workspace_bytes(num_users, num_items, d) bytes of device scratch; its first uint32 is
+ *   an abort flag that is non-zero afterwards only if a wait exceeded its bound (sched does not belong to these
+ *   sizes).  warps_per_sm: resident warps per SM (0 = as many as fit).  d <= 512.  Cooperative launch.
  * brk_svd_predict: out[k] = bu[u] + bi[i] + mu + <Q[i], P[u]>  (predict, SVD.py:179-185).
  * brk_svd_errors: out[0] = mean squared error, out[1] = mean absolute error of rating - prediction over n >= 1
  *   ratings (mean_generic_error, SVD.py:223-253); partial sums are combined in a fixed order.
@@ -450,8 +452,9 @@ int brk_svd_schedule(brk_ctx* ctx, const int32_t* users, const int32_t* items, i
                      int64_t workspace_bytes, void* stream);
 int brk_svd_fit_epoch(brk_ctx* ctx, const int32_t* sched, const double* ratings, int64_t n, double* P,
                       double* Q, double* bu, double* bi, int64_t num_users, int64_t num_items, int32_t d,
-                      double mu, double lr, double emb_reg, double bias_reg, uint32_t* versions,
-                      int32_t warps_per_sm, void* stream);
+                      double mu, double lr, double emb_reg, double bias_reg, void* workspace,
+                      int64_t workspace_bytes, int32_t warps_per_sm, void* stream);
+int64_t brk_svd_fit_workspace_bytes(int64_t num_users, int64_t num_items, int32_t d);
 int brk_svd_predict(brk_ctx* ctx, const int32_t* users, const int32_t* items, int64_t n, const double* P,
                     const double* Q, const double* bu, const double* bi, int32_t d, double mu, double* out,
                     void* stream);

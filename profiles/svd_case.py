@@ -1,4 +1,4 @@
-"""Biased-SVD epoch kernel (csrc/svd.cu): epoch time against residency (warps per SM) and the poll variant, on the
+"""Biased-SVD epoch kernel (csrc/svd.cu): epoch time against residency (warps per SM) and the hand-over form (self-validating rows / flags + fences), on the
 ML-1M-shaped file (power-law head) and on a uniform file of the same size; prints the critical path so that the time
 per chain link can be read off.   python profiles/svd_case.py [once]      (once: a single epoch, for ncu)"""
 import os
@@ -43,13 +43,13 @@ def main():
         chain = frame.critical_path()
         print(f"skew={skew}: n={len(u)} critical path {chain} (max item count {np.bincount(i).max()}, max user count "
               f"{np.bincount(u).max()}), schedule build {t_sched * 1e3:.1f} ms (incl. H2D)", flush=True)
-        for poll in ("0", "1"):
-            os.environ["BRK_SVD_POLL"] = poll
-            for warps in (0, 16, 8, 4, 2):
+        for form in ("rows", "flags"):
+            os.environ["BRK_SVD_FORM"] = form
+            for warps in (0, 24, 16, 8):
                 ms = epoch_ms(frame, P, Q, bu, bi, mu, warps)
-                print(f"  poll={poll} warps_per_sm={warps:2d}: {ms:8.3f} ms/epoch  {len(u) / ms / 1e3:8.2f} M ratings/s  "
+                print(f"  form={form:5s} warps_per_sm={warps:2d}: {ms:8.3f} ms/epoch  {len(u) / ms / 1e3:8.2f} M ratings/s  "
                       f"{ms * 1e6 / chain:7.1f} ns per chain link", flush=True)
-        os.environ.pop("BRK_SVD_POLL", None)
+        os.environ.pop("BRK_SVD_FORM", None)
 
 
 if __name__ == "__main__":
