@@ -520,8 +520,20 @@ def secondary_measurements(dev):
         s = timed(tt2_step, 30)
         out[tag] = {"value": Bt2 / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
                     "config": f"two-tower E=S=128, in-batch softmax batch {Bt2}, Adagrad 0.1, every Dense / in-batch product on "
-                              f"tcgen05 (TF32 operands, fp32 accumulation; csrc/gemm_tc.cu)"}
-        del tt2
+                              f"tcgen05 (TF32 operands, fp32 accumulation; csrc/gemm_tc.cu); the two tower chains forked "
+                              f"onto two streams inside brk_twotower_step"}
+        # the same step as TwoTowerModel.fit runs it: one CUDA-graph replay per batch
+        side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            tt2_step()
+        torch.cuda.current_stream().wait_stream(side)
+        gph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gph):
+            tt2_step()
+        s = timed(gph.replay, 30)
+        out[tag + "_graph"] = {"value": Bt2 / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
+                               "config": out[tag]["config"] + "; replayed as one CUDA graph per step (what TwoTowerModel.fit does)"}
+        del tt2, gph
     Q = torch.randn(U, 128, generator=g, device=dev); Cm = torch.randn(I, 128, generator=g, device=dev)
     idx = H.BruteForceIndex(10).index(Cm)
     s = timed(lambda: idx(Q), 50)

@@ -21,7 +21,25 @@ struct brk_ctx {
   // NeuMF tensor-core path: swizzled weight images, rebuilt every step (csrc/neumf_tc.cu)
   float*        neumf_img;
   size_t        neumf_img_floats;
+  // fork/join inside one call: independent kernel chains of a step (the two towers of twotower.cu and, inside each,
+  // the Dense-gradient products beside the embedding-gradient chain) run side by side on these streams
+  cudaStream_t  fork_stream[3];
+  cudaEvent_t   ev_fork[3], ev_join[3];
 };
+#define BRK_FORK_STREAMS 3
+
+// Runs what follows on ctx->fork_stream[j] after everything queued on `from` so far ...
+#define BRK_FORK(ctx, from, j)                                                   \
+  do {                                                                           \
+    BRK_CUDA(cudaEventRecord((ctx)->ev_fork[j], (from)));                        \
+    BRK_CUDA(cudaStreamWaitEvent((ctx)->fork_stream[j], (ctx)->ev_fork[j], 0));  \
+  } while (0)
+// ... and makes `into` wait for that chain (both work under stream capture: the chain becomes a graph branch).
+#define BRK_JOIN(ctx, into, j)                                                   \
+  do {                                                                           \
+    BRK_CUDA(cudaEventRecord((ctx)->ev_join[j], (ctx)->fork_stream[j]));         \
+    BRK_CUDA(cudaStreamWaitEvent((into), (ctx)->ev_join[j], 0));                 \
+  } while (0)
 
 #define BRK_STAGE_EVENTS 4
 #define BRK_COPY_AUX 3

@@ -37,6 +37,11 @@ extern "C" int brk_create(brk_ctx** out, int device) {
   BRK_CUDA(cudaMemset(c->tickets, 0, BRK_TICKETS * sizeof(unsigned int)));
   c->scratch = nullptr;
   c->scratch_bytes = 0;
+  for (int j = 0; j < BRK_FORK_STREAMS; ++j) {
+    BRK_CUDA(cudaStreamCreateWithFlags(&c->fork_stream[j], cudaStreamNonBlocking));
+    BRK_CUDA(cudaEventCreateWithFlags(&c->ev_fork[j], cudaEventDisableTiming));
+    BRK_CUDA(cudaEventCreateWithFlags(&c->ev_join[j], cudaEventDisableTiming));
+  }
   BRK_CUDA(cudaDeviceSynchronize());
   *out = c;
   return 0;
@@ -49,6 +54,8 @@ extern "C" int brk_destroy(brk_ctx* c) {
   if (c->tickets) cudaFree(c->tickets);
   if (c->scratch) cudaFree(c->scratch);
   if (c->neumf_img) cudaFree(c->neumf_img);
+  for (int j = 0; j < BRK_FORK_STREAMS; ++j)
+    if (c->fork_stream[j]) { cudaStreamDestroy(c->fork_stream[j]); cudaEventDestroy(c->ev_fork[j]); cudaEventDestroy(c->ev_join[j]); }
   if (c->copy_ready) {
     cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < BRK_STAGE_EVENTS; ++i) { cudaEventDestroy(c->ev_ready[i]); cudaEventDestroy(c->ev_done[i]); }

@@ -234,54 +234,80 @@ extern "C" int brk_twotower_step(brk_ctx* ctx, const brk_tower* user, const brk_
   BRK_REQUIRE(mode == 0 || labels, BRK_E_ARG, "brk_twotower_step: rdZero mode needs labels");
   BRK_REQUIRE(ws->eu && ws->ei && ws->q && ws->c && ws->dq && ws->dc && ws->acc && (mode != 0 || ws->scores), BRK_E_ARG,
               "brk_twotower_step: workspace missing");
-  BRK_REQUIRE(!training || (user->emb.g && item->emb.g && user->dense.g && item->dense.g), BRK_E_ARG,
-              "brk_twotower_step: gradient accumulators missing");
+  BRK_REQUIRE(!training || (user->emb.g && item->emb.g && user->dense.g && item->dense.g && ws->deu && ws->dei), BRK_E_ARG,
+              "brk_twotower_step: gradient accumulators / deu, dei workspace missing");
   cudaStream_t st = (cudaStream_t)stream;
   const int B = int(batch), S = user->S, Eu = user->E, Ei = item->E;
   int rc;
+  // The user chain and the item chain are independent until the score product and again after the loss gradient, and
+  // inside each chain the Dense gradients (dW, db) are independent of the embedding gradient (de -> scatter): the item
+  // chain runs on fork stream 0, the Dense gradients on fork streams 1 / 2 (branches of the graph under stream
+  // capture), the user chain on `st`.  At the reference's batch of 1000 (twoTower.py:292) every kernel is a few
+  // microseconds, so the step is bound by the length of its dependency chain: 20 kernels in one line before, 8 now.
+  // Outside a capture every fork/join costs four driver calls on the launching thread, which is what bounds the eager
+  // step: there only the item chain is forked; the Dense-gradient side chains are used when the step is being captured.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  BRK_CUDA(cudaStreamIsCapturing(st, &cap));
+  const bool wide = cap == cudaStreamCaptureStatusActive;
+  cudaStream_t fk = ctx->fork_stream[0];
+  float* dz[2] = {ws->dq, ws->dc};
   // towers: q = Eu[u] Wu + bu, c = Ei[i] Wi + bi
+  BRK_FORK(ctx, st, 0);
+  if (training && mode == 0) BRK_CUDA(cudaMemsetAsync(dz[1], 0, size_t(B) * S * sizeof(float), fk));   // RED targets of
+  if ((rc = tower_forward(ctx, item, i, batch, ws->ei, ws->c, tcore, fk))) return rc;                    // the split-K
+  if (training && mode == 0) BRK_CUDA(cudaMemsetAsync(dz[0], 0, size_t(B) * S * sizeof(float), st));   // products below
   if ((rc = tower_forward(ctx, user, u, batch, ws->eu, ws->q, tcore, stream))) return rc;
-  if ((rc = tower_forward(ctx, item, i, batch, ws->ei, ws->c, tcore, stream))) return rc;
+  BRK_JOIN(ctx, st, 0);
   if (mode == 0) {
     // scores = q c^T; softmax CE (SUM) with accidental-hit removal; in place P = softmax - I
     if ((rc = gemm(ctx, st, tcore, ws->q, ws->c, ws->scores, nullptr, B, B, S, S, S, B, 0, 1, 1.f, 0, false))) return rc;
     inbatch_softmax_kernel<<<B, 256, 0, st>>>(ws->scores, cand_ids, B, training, ws->acc);
     BRK_LAUNCH_CHECK();
-    if (training) {
-      // dq = P c  [B,S];  dc = P^T q  [B,S]: few output tiles (B/64 x S/64) and a long K = B, so the products are
-      // split along K across CTAs and accumulated with REDs into zeroed outputs
-      BRK_CUDA(cudaMemsetAsync(ws->dq, 0, size_t(B) * S * sizeof(float), st));
-      BRK_CUDA(cudaMemsetAsync(ws->dc, 0, size_t(B) * S * sizeof(float), st));
-      if ((rc = gemm(ctx, st, tcore, ws->scores, ws->c, ws->dq, nullptr, B, S, B, B, S, S, 0, 0, 1.f, 1, true))) return rc;
-      if ((rc = gemm(ctx, st, tcore, ws->scores, ws->q, ws->dc, nullptr, B, S, B, B, S, S, 1, 0, 1.f, 1, true))) return rc;
-    }
   } else {
     rowdot_bce_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(ws->q, ws->c, labels, B, S, training, ws->dq, ws->dc, ws->acc);
     BRK_LAUNCH_CHECK();
   }
-  finish_loss_kernel<<<1, 1, 0, st>>>(ws->acc, loss_out);
-  BRK_LAUNCH_CHECK();
-  if (!training) return 0;
-  // Dense gradients: dW = e^T dz [E,S] (split-K over the batch), db = column sums of dz = ones^T dz;
-  // embedding-row gradients: de = dz W^T [B,E], scattered into the table accumulators.
+  if (!training) {
+    finish_loss_kernel<<<1, 1, 0, st>>>(ws->acc, loss_out);
+    BRK_LAUNCH_CHECK();
+    return 0;
+  }
+  BRK_FORK(ctx, st, 0);
+  // Per tower k (user on st, item on fork stream 0):
+  //   softmax mode: dz = P c [B,S] (user) / P^T q [B,S] (item): few output tiles (B/64 x S/64) and a long K = B, so
+  //   the products are split along K across CTAs and accumulated with REDs into the zeroed outputs;
+  //   embedding-row gradients: de = dz W^T [B,E], scattered into the table accumulators;
+  //   beside them (fork stream 1 + k): dW = e^T dz [E,S] (split-K over the batch), db = column sums of dz.
   const brk_tower* tw[2] = {user, item};
   const float* e[2] = {ws->eu, ws->ei};
-  const float* dz[2] = {ws->dq, ws->dc};
+  float* de[2] = {ws->deu, ws->dei};
+  const float* other[2] = {ws->c, ws->q};
   const int32_t* ids[2] = {u, i};
   const int E[2] = {Eu, Ei};
   for (int k = 0; k < 2; ++k) {
+    cudaStream_t sk = k == 0 ? st : fk;
+    cudaStream_t sd = wide ? ctx->fork_stream[1 + k] : sk;
+    if (mode == 0) {
+      if ((rc = gemm(ctx, sk, tcore, ws->scores, other[k], dz[k], nullptr, B, S, B, B, S, S, k, 0, 1.f, 1, true))) return rc;
+    }
+    if (wide) BRK_FORK(ctx, sk, 1 + k);
     float* gW = tw[k]->dense.g;
     float* gb = gW + int64_t(E[k]) * S;
-    if ((rc = gemm(ctx, st, tcore, e[k], dz[k], gW, nullptr, E[k], S, B, E[k], S, S, 1, 0, 1.f, 1, true))) return rc;
-    colsum_kernel<<<dim3((S + 127) / 128, (B + 63) / 64), 128, 0, st>>>(dz[k], B, S, S, gb);
+    if ((rc = gemm(ctx, sd, tcore, e[k], dz[k], gW, nullptr, E[k], S, B, E[k], S, S, 1, 0, 1.f, 1, true))) return rc;
+    colsum_kernel<<<dim3((S + 127) / 128, (B + 63) / 64), 128, 0, sd>>>(dz[k], B, S, S, gb);
     BRK_LAUNCH_CHECK();
-    float* de = k == 0 ? ws->eu : ws->ei;                 // reuse the gathered-row buffer for de
-    // de = dz W^T: W stored [E,S] = "B stored [N,K]" with N = E, K = S  (tb = 1)
-    // (the dW product above has already consumed e)
-    if ((rc = gemm(ctx, st, tcore, dz[k], tw[k]->dense.w, de, nullptr, B, E[k], S, S, S, E[k], 0, 1, 1.f, 0, false))) return rc;
-    if ((rc = brk_scatter_add_rows(ctx, tw[k]->emb.g, tw[k]->emb.rows, E[k], ids[k], batch, de, tw[k]->emb.touched, 0,
-                                   stream)))
+    if (k == 0) {                                  // the loss scalar rides on the user tower's side stream
+      finish_loss_kernel<<<1, 1, 0, sd>>>(ws->acc, loss_out);
+      BRK_LAUNCH_CHECK();
+    }
+    // de = dz W^T: W stored [E,S] = "B stored [N,K]" with N = E, K = S  (tb = 1); its own buffer: the dW product
+    // beside it is still reading the gathered rows e
+    if ((rc = gemm(ctx, sk, tcore, dz[k], tw[k]->dense.w, de[k], nullptr, B, E[k], S, S, S, E[k], 0, 1, 1.f, 0, false))) return rc;
+    if ((rc = brk_scatter_add_rows(ctx, tw[k]->emb.g, tw[k]->emb.rows, E[k], ids[k], batch, de[k], tw[k]->emb.touched, 0,
+                                   (void*)sk)))
       return rc;
+    if (wide) BRK_JOIN(ctx, sk, 1 + k);
   }
+  BRK_JOIN(ctx, st, 0);
   return 0;
 }

@@ -307,7 +307,9 @@ int brk_bpr_train_steps_dp(brk_ctx* ctx, const brk_table* user, const brk_table*
  *     sigmoid(<q_b, c_b>) against labels[b], mean binary cross-entropy.
  *     training != 0 additionally accumulates every gradient (emb.g rows, dense.g) for the optimizer.
  * Workspace (caller-owned, floats): eu [B,Eu], ei [B,Ei], q, c, dq, dc [B,S], scores [B,B] (mode 0),
- * ones [B] filled with 1.0, acc 1 double zero-initialised.
+ * ones [B] filled with 1.0, acc 1 double zero-initialised, deu [B,Eu] / dei [B,Ei] (training).
+ * Inside the call the item-tower chain and the two Dense-gradient chains run on streams owned by the context,
+ * forked from and joined back into `stream` (under stream capture they become branches of the graph).
  *   brk_sgemm : C (+)= alpha opA(A) opB(B) (+ bias); trans_a: A stored [K,M]; trans_b: B stored [N,K]; fp32 FMA.
  *   brk_gemm_tf32 : the same product on tcgen05 with TF32 operands and fp32 accumulation in TMEM (gemm_tc.cu);
  *     needs 16-byte aligned operands with leading dimensions that are multiples of 4 (else BRK_E_ALIGN).
@@ -320,6 +322,7 @@ typedef struct brk_tower {
 typedef struct brk_twotower_workspace {
   float *eu, *ei, *q, *c, *dq, *dc, *scores, *ones;
   double* acc;
+  float *deu, *dei;   /* [B,Eu], [B,Ei]: embedding-row gradients (training only) */
 } brk_twotower_workspace;
 int brk_sgemm(brk_ctx* ctx, const float* A, const float* B, float* C, const float* bias, int32_t M,
               int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t trans_a, int32_t trans_b,

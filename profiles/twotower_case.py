@@ -22,3 +22,18 @@ e0.record()
 for _ in range(50): step()
 e1.record(); torch.cuda.synchronize()
 print(f"tensor_cores={tc_flag} B={Bt}: {e0.elapsed_time(e1) * 1e3 / 50:.1f} us/step  {Bt / (e0.elapsed_time(e1) * 1e-3 / 50) / 1e6:.2f} M interactions/s")
+# the same step captured once into a CUDA graph (the fork/join inside brk_twotower_step becomes two graph branches)
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    step()
+torch.cuda.current_stream().wait_stream(side)
+graph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(graph):
+    step()
+for _ in range(5): graph.replay()
+torch.cuda.synchronize()
+e0.record()
+for _ in range(50): graph.replay()
+e1.record(); torch.cuda.synchronize()
+print(f"  as a CUDA graph: {e0.elapsed_time(e1) * 1e3 / 50:.1f} us/step  {Bt / (e0.elapsed_time(e1) * 1e-3 / 50) / 1e6:.2f} M interactions/s")
