@@ -145,10 +145,11 @@ __global__ void __launch_bounds__(NT) gemm_tf32_kernel(const Params P) {
   if (n_chunks > 0) {
     // epilogue: warp w reads lane quadrant (w & 3), column half (w >> 2); rows go through shared memory so that the
     // global stores are whole 16-byte chunks of consecutive columns (row-per-thread scalar stores cost 12 us per tile)
-    constexpr int HC = BN / 2, CP = BN + 4;
+    // (BN = 32: one 32-column read per lane quadrant, warps 4..7 have nothing to read)
+    constexpr int HC = BN >= 64 ? BN / 2 : BN, CP = BN + 4;
     float* Cs = reinterpret_cast<float*>(sm);
-    const int rl = (warp & 3) * 32 + lane, c0 = (warp >> 2) * HC;
-    for (int cc = 0; cc < HC; cc += 32) {
+    const int rl = (warp & 3) * 32 + lane, c0 = BN >= 64 ? (warp >> 2) * HC : 0;
+    for (int cc = 0; cc < HC && (BN >= 64 || warp < 4); cc += 32) {
       uint32_t r[32];
       tc::tmem_ld_32x32_issue(tmem + (uint32_t((warp & 3) * 32) << 16) + uint32_t(c0 + cc), r);
       tc::tmem_ld_wait(r);
@@ -219,8 +220,13 @@ int brk_gemm_tf32_impl(brk_ctx* ctx, const float* A, const float* B, float* C, c
   gtc::Params P;
   P.A = A; P.B = B; P.C = C; P.bias = bias; P.M = M; P.N = N; P.K = K; P.lda = lda; P.ldb = ldb; P.ldc = ldc;
   P.alpha = alpha; P.accumulate = accumulate;
-  const int BN = N > 64 ? 128 : 64;
-  const int tiles = ((N + BN - 1) / BN) * ((M + gtc::BM - 1) / gtc::BM);
+  // Tile width: the widest of 128 / 64 / 32 that still gives the grid a quarter of a wave of CTAs.  Small products
+  // (the two-tower Dense layers at batch 1000: 8 row tiles) are bound by the latency of ONE CTA -- staging, the
+  // tcgen05.ld epilogue and the stores of a 128-wide tile -- so narrower tiles on more SMs finish sooner.
+  const int row_tiles = (M + gtc::BM - 1) / gtc::BM;
+  int BN = 128;
+  while (BN > 32 && (BN / 2 >= N || row_tiles * ((N + BN - 1) / BN) < ctx->sm_count / 4)) BN /= 2;
+  const int tiles = ((N + BN - 1) / BN) * row_tiles;
   int splits = 1;
   if (allow_split && accumulate) {
     const int want = ctx->sm_count / tiles, max_by_k = (K + 4 * gtc::KC - 1) / (4 * gtc::KC);
@@ -236,6 +242,7 @@ int brk_gemm_tf32_impl(brk_ctx* ctx, const float* A, const float* B, float* C, c
 #define BRK_GTC(BN_, AM_, BM_) if (BN == BN_ && a_mn == AM_ && b_mn == BM_) return gtc::launch<BN_, AM_, BM_>(ctx, P, splits, st);
   BRK_GTC(128, 0, 0) BRK_GTC(128, 0, 1) BRK_GTC(128, 1, 0) BRK_GTC(128, 1, 1)
   BRK_GTC(64, 0, 0) BRK_GTC(64, 0, 1) BRK_GTC(64, 1, 0) BRK_GTC(64, 1, 1)
+  BRK_GTC(32, 0, 0) BRK_GTC(32, 0, 1) BRK_GTC(32, 1, 0) BRK_GTC(32, 1, 1)
 #undef BRK_GTC
   return BRK_E_ARG;
 }
