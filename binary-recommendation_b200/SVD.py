@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _native as N
+from . import distributed as D
 from . import hotpath as H
 from . import pipeline as PL
 from . import topKmetrics as topk
@@ -116,6 +117,103 @@ class Ratings:
         return int(max(lu.max(initial=0), li.max(initial=0)))
 
 
+class RatingChunks:
+    """The reference's chunked datasets -- movielens_cross_validation (SVD.py:301-347: one file, shuffled, split into
+    five) and grundfos_network_drive_files (:349-409: five files) -- over in-memory columns.  Same protocol:
+    iteration yields every chunk except the held-out one; use_no_test_set(), next_cross_validation_distribution(),
+    get_test_set().  A chunk is a (raw users, raw items, ratings) column triple; after digest() the chunks also hold
+    dense ids and `train_frame()` / `test_frame()` give the device frames fit_model and the error functions take."""
+
+    def __init__(self, chunks, test_positive_only=False):
+        self.chunks = [(np.asarray(u), np.asarray(i), np.asarray(r, dtype=np.float64)) for u, i, r in chunks]
+        if not self.chunks:
+            raise ValueError("no chunks")
+        self.number_of_chunks = len(self.chunks)
+        self.test_set_index = self.number_of_chunks - 1           # start with the last chunk as the test set
+        # grundfos_network_drive_files.get_test_set keeps only rows whose rating column is 1 (:389-392)
+        self.test_positive_only = bool(test_positive_only)
+        self.dense = None                                         # per chunk (users int32, items int32) after digest
+        self.num_users = self.num_items = None
+        self.device = None
+        self._frames = {}
+
+    @classmethod
+    def split(cls, raw_users, raw_items, ratings, number_of_chunks=5, shuffle_seed=None, **kw):
+        """movielens_cross_validation: (optionally shuffled, the reference's `.sample(frac=1)` is unseeded) rows cut
+        into number_of_chunks pieces with np.array_split (:308-310)."""
+        u, i, r = np.asarray(raw_users), np.asarray(raw_items), np.asarray(ratings, dtype=np.float64)
+        if shuffle_seed is not None:
+            perm = np.random.default_rng(shuffle_seed).permutation(len(u))
+            u, i, r = u[perm], i[perm], r[perm]
+        return cls(list(zip(np.array_split(u, number_of_chunks), np.array_split(i, number_of_chunks),
+                            np.array_split(r, number_of_chunks))), **kw)
+
+    def use_no_test_set(self):
+        self.test_set_index = self.number_of_chunks
+
+    def next_cross_validation_distribution(self):
+        self.test_set_index -= 1
+        return self.test_set_index >= 0
+
+    def _test_rows(self):
+        if self.test_set_index == self.number_of_chunks:
+            raise Exception("There is no test set because use_no_test_set was called. Call "
+                            "next_cross_validation_distribution to set the first chunk to be the test set again.")
+        u, i, r = self.chunks[self.test_set_index]
+        keep = (r == 1) if self.test_positive_only else np.ones(len(r), dtype=bool)
+        return keep
+
+    def get_test_set(self):
+        keep = self._test_rows()
+        u, i, r = self.chunks[self.test_set_index]
+        return u[keep], i[keep], r[keep]
+
+    def training_chunk_indices(self):
+        return [c for c in range(self.number_of_chunks) if c != self.test_set_index]
+
+    def __iter__(self):
+        return iter([self.chunks[c] for c in self.training_chunk_indices()])
+
+    # ---- device side (after digest) ------------------------------------------------------------------------
+    def _need_digest(self):
+        if self.dense is None:
+            raise N.BrkError("RatingChunks: call digest(dataset) first (dense ids are assigned there)")
+
+    def train_frame(self):
+        """Ratings frame of the training chunks in iteration order (cached per held-out chunk)."""
+        self._need_digest()
+        key = ("train", self.test_set_index)
+        if key not in self._frames:
+            idx = self.training_chunk_indices()
+            u = np.concatenate([self.dense[c][0] for c in idx]) if idx else np.zeros(0, np.int32)
+            i = np.concatenate([self.dense[c][1] for c in idx]) if idx else np.zeros(0, np.int32)
+            r = np.concatenate([self.chunks[c][2] for c in idx]) if idx else np.zeros(0)
+            self._frames[key] = Ratings(u, i, r, num_users=self.num_users, num_items=self.num_items, device=self.device)
+        return self._frames[key]
+
+    def test_frame(self):
+        self._need_digest()
+        key = ("test", self.test_set_index)
+        if key not in self._frames:
+            keep = self._test_rows()
+            du, di = self.dense[self.test_set_index]
+            self._frames[key] = Ratings(du[keep], di[keep], self.chunks[self.test_set_index][2][keep],
+                                        num_users=self.num_users, num_items=self.num_items, device=self.device)
+        return self._frames[key]
+
+
+def _frame_of(dataset):
+    """fit_model / the error functions take what the reference passes: the chunk iterator (its training chunks), a
+    list holding the test frame (`[test_dataframe]`, SVD.py:462) or a Ratings frame."""
+    if isinstance(dataset, Ratings):
+        return dataset
+    if isinstance(dataset, RatingChunks):
+        return dataset.train_frame()
+    if isinstance(dataset, (list, tuple)) and len(dataset) == 1 and isinstance(dataset[0], Ratings):
+        return dataset[0]
+    raise TypeError("expected a Ratings frame, a RatingChunks dataset or [Ratings]")
+
+
 def get_rating(transaction_count, quantity_sum, tc_scale=TRANSACTION_COUNT_SCALE, qs_scale=QUANTITY_SUM_SCALE,
                tc_quintiles=TRANSACTION_COUNT_QUINTILES, qs_quintiles=QUANTITY_SUM_QUINTILES, device=None):
     """get_rating with RATING_COLUMN = None (SVD.py:255-262) over whole columns: float64 ratings on the device."""
@@ -137,10 +235,34 @@ def place_in_quintile(value, quintiles):
     return 4 if value > q3 else 3 if value > median else 2 if value > q1 else 1
 
 
-def digest(raw_users, raw_items, ratings, device=None):
-    """digest (SVD.py:105-124) over whole columns: returns (user_ids, item_ids, uid_max, iid_max, global_bias, frame)
-    where user_ids / item_ids are the reference's dicts raw id -> dense id (order of first appearance), global_bias
-    the mean rating, and frame the `Ratings` the other functions take in place of the chunk iterator."""
+def digest(raw_users, raw_items=None, ratings=None, device=None):
+    """digest (SVD.py:105-124).  Two call forms:
+      digest(dataset)  with a RatingChunks -- the reference's call: ids and the global mean over the chunks the
+        iterator currently yields (all of them after use_no_test_set()); returns the reference's 5-tuple
+        (user_ids, item_ids, uid_max, iid_max, global_bias) and leaves the dense ids in the dataset;
+      digest(raw_users, raw_items, ratings)  over whole columns: returns the 5-tuple plus the Ratings frame.
+    user_ids / item_ids are the reference's dicts raw id -> dense id (order of first appearance)."""
+    if isinstance(raw_users, RatingChunks):
+        ds = raw_users
+        idx = ds.training_chunk_indices()
+        u = np.concatenate([ds.chunks[c][0] for c in idx]); i = np.concatenate([ds.chunks[c][1] for c in idx])
+        r = np.concatenate([ds.chunks[c][2] for c in idx])
+        user_ids, item_ids, uid_max, iid_max, mu, frame = digest(u, i, r, device=device)
+        ds.device, ds.num_users, ds.num_items = frame.device, uid_max + 1, iid_max + 1
+        du, di = frame.users.cpu().numpy(), frame.items.cpu().numpy()
+        cuts = np.cumsum([0] + [len(ds.chunks[c][0]) for c in idx])
+        ds.dense = [None] * ds.number_of_chunks
+        for n, c in enumerate(idx):
+            ds.dense[c] = (du[cuts[n]:cuts[n + 1]], di[cuts[n]:cuts[n + 1]])
+        for c in range(ds.number_of_chunks):                      # a chunk held out during digest: ids must be known
+            if ds.dense[c] is None:
+                try:
+                    ds.dense[c] = (np.array([user_ids[x] for x in ds.chunks[c][0].tolist()], np.int32),
+                                   np.array([item_ids[x] for x in ds.chunks[c][1].tolist()], np.int32))
+                except KeyError as e:                             # the reference fails the same way in fit_model
+                    raise KeyError(f"id {e} of the held-out chunk was not seen by digest") from None
+        ds._frames = {}
+        return user_ids, item_ids, uid_max, iid_max, mu
     dev = _dev(device)
     uv, iv = PL.Vocabulary(dev), PL.Vocabulary(dev)
     u = uv.build(raw_users)
@@ -189,6 +311,7 @@ def fit_model(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vec
     per SM (0 = as many as fit); by default 8 when the file offers little parallelism (fewer than 512 ratings per
     link of its longest row chain: more waiting warps only add polling traffic -- measured 5.8 vs 6.4 ms on the
     ML-1M-shaped file), otherwise 0.  The result does not depend on it."""
+    dataset = _frame_of(dataset)
     P, Q, bu, bi = _check_params(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector)
     lr = LEARNING_RATE if learning_rate is None else learning_rate
     ereg = EMBEDDING_REGULARIZATION if embedding_regularization is None else embedding_regularization
@@ -209,6 +332,7 @@ def fit_model(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vec
 
 def check_fit(dataset):
     """Raises if the last fit_model over `dataset` gave up on a wait (synchronises)."""
+    dataset = _frame_of(dataset)
     if dataset._fit_ws is not None and int(dataset._fit_ws[:4].view(torch.int32).item()) != 0:
         raise N.BrkError("brk_svd_fit_epoch aborted: the schedule does not belong to these ratings")
 
@@ -232,6 +356,7 @@ def predict(user, item, user_matrix, item_matrix, user_bias_vector, item_bias_ve
 
 
 def _errors(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias):
+    dataset = _frame_of(dataset)
     P, Q, bu, bi = _check_params(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector)
     if len(dataset) == 0:
         raise ZeroDivisionError("mean error over an empty rating set")      # accumulator / count, SVD.py:247
@@ -308,27 +433,81 @@ def do_topk(user_matrix, item_matrix, test_idset, train_idset, user_ids, item_id
             "train_set": topk.topKMetrics(predictions, train_idset, actual_user_ids, actual_item_ids)}
 
 
-def train_and_evaluate(dataset, test_set, user_ids, item_ids, uid_max, iid_max, global_bias, epochs=None, seed=None,
-                       evaluate=None, verbose=False):
-    """train_and_evaluate (SVD.py:437-497) on a training frame and a held-out frame (both `Ratings` over the same
-    dense id space).  Returns {'all_data', 'train_set', 'mse', 'epoch_mse'}; metrics only if evaluate."""
-    P, Q, bu, bi = init_parameters(uid_max + 1, iid_max + 1, NUMBER_OF_EMBEDDINGS, seed, dataset.device)
-    epoch_mse = []
+def train_and_evaluate(dataset, user_ids, item_ids, uid_max, iid_max, global_bias, bmThread=None, epochs=None,
+                       seed=None, evaluate=None, verbose=False):
+    """train_and_evaluate (SVD.py:437-497) for the current held-out chunk of a digested RatingChunks dataset: random
+    U(0,1)/d matrices, zero biases, EPOCHS passes of fit_model over the training chunks with the training / test MSE
+    after each, then the test MSE and do_topk.  Returns the reference's dict {'all_data', 'train_set', 'mse'} plus
+    'epoch_mse', 'epoch_test_mse' and 'parameters'.  bmThread (the reference's resource logger) is ignored."""
+    train, test = dataset.train_frame(), dataset.test_frame()
+    P, Q, bu, bi = init_parameters(uid_max + 1, iid_max + 1, NUMBER_OF_EMBEDDINGS, seed, train.device)
+    epoch_mse, epoch_test_mse = [], []
     for e in range(1, (EPOCHS if epochs is None else epochs) + 1):
         fit_model(dataset, P, Q, bu, bi, global_bias, user_ids, item_ids)
         if e % EPOCH_ERROR_CALCULATION_FREQUENCY == 0:
-            epoch_mse.append(mean_square_error(dataset, P, Q, bu, bi, global_bias))
+            epoch_mse.append(mean_square_error(dataset, P, Q, bu, bi, global_bias, user_ids, item_ids))
+            epoch_test_mse.append(mean_square_error([test], P, Q, bu, bi, global_bias, user_ids, item_ids))
             if verbose:
                 print(f"::::EPOCH {e:=3}::::    MSE: {epoch_mse[-1]}", flush=True)
-    check_fit(dataset)
-    result = {"epoch_mse": epoch_mse, "parameters": (P, Q, bu, bi)}
+                print(f"             And on the test set MSE: {epoch_test_mse[-1]}")
+    check_fit(train)
+    result = {"epoch_mse": epoch_mse, "epoch_test_mse": epoch_test_mse, "parameters": (P, Q, bu, bi)}
     if EVALUATE if evaluate is None else evaluate:
-        result["mse"] = mean_square_error(test_set, P, Q, bu, bi, global_bias)
-        inv_u = {v: k for k, v in user_ids.items()}; inv_i = {v: k for k, v in item_ids.items()}
+        result["mse"] = mean_square_error([test], P, Q, bu, bi, global_bias, user_ids, item_ids)
 
-        def idset(frame):
-            u, i = frame.users.cpu().numpy(), frame.items.cpu().numpy()
-            return {(inv_u[int(a)], inv_i[int(b)]) for a, b in zip(u, i)}
-        test_idset = idset(test_set)
-        result.update(do_topk(P, Q, test_idset, test_idset | idset(dataset), user_ids, item_ids))
+        def idset(columns):                                       # get_idset (:410-416): sets of RAW (user, item) pairs
+            return set(zip(np.asarray(columns[0]).tolist(), np.asarray(columns[1]).tolist()))
+        test_idset = idset(dataset.get_test_set())
+        train_idset = set(test_idset)
+        for chunk in dataset:
+            train_idset |= idset(chunk)
+        result.update(do_topk(P, Q, test_idset, train_idset, user_ids, item_ids))
     return result
+
+
+def cross_validate(dataset, epochs=None, seed=None, verbose=False):
+    """The reference's main program (SVD.py:519-566): digest every chunk, then hold each chunk out in turn (last one
+    first), train_and_evaluate, and average the metric dicts with getAverage.  Returns {'all_data', 'train_set',
+    'mse': [per fold], 'folds': [held-out chunk per fold]}.
+    The folds are independent, which is the only parallelism this model offers across GPUs ("replicas only"): under
+    torch.distributed fold f runs on rank f % world_size and the per-fold results are all-gathered."""
+    dataset.use_no_test_set()
+    user_ids, item_ids, uid_max, iid_max, global_bias = digest(dataset)
+    folds = []
+    while dataset.next_cross_validation_distribution():
+        folds.append(dataset.test_set_index)
+    mine = fold_assignment(len(folds), D.rank(), D.world_size())
+    local = {}
+    for f in mine:
+        dataset.test_set_index = folds[f]
+        if verbose:
+            print("=" * 16 + f"\nCross validation {f + 1} of {len(folds)}\n" + "=" * 16)
+        res = train_and_evaluate(dataset, user_ids, item_ids, uid_max, iid_max, global_bias, None, epochs=epochs,
+                                 seed=None if seed is None else seed + f, verbose=verbose)
+        local[f] = {"all_data": res["all_data"], "train_set": res["train_set"], "mse": res["mse"]}
+    merged = merge_fold_results(local, len(folds))
+    return {"all_data": topk.getAverage([merged[f]["all_data"] for f in range(len(folds))]),
+            "train_set": topk.getAverage([merged[f]["train_set"] for f in range(len(folds))]),
+            "mse": [merged[f]["mse"] for f in range(len(folds))], "folds": folds}
+
+
+def fold_assignment(n_folds, rank, world):
+    """Folds of this rank: f with f % world == rank (host logic, no device)."""
+    return [f for f in range(n_folds) if f % world == rank]
+
+
+def merge_fold_results(local, n_folds):
+    """All ranks' {fold: result} dicts -> one dict holding every fold (all_gather_object under torch.distributed)."""
+    if D.world_size() == 1:
+        merged = dict(local)
+    else:
+        import torch.distributed as dist
+        parts = [None] * D.world_size()
+        dist.all_gather_object(parts, local)
+        merged = {}
+        for part in parts:
+            merged.update(part)
+    missing = [f for f in range(n_folds) if f not in merged]
+    if missing:
+        raise N.BrkError(f"cross_validate: folds {missing} were not run by any rank")
+    return merged

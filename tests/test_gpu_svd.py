@@ -207,22 +207,52 @@ def test_result_does_not_depend_on_residency_or_run(S):
             assert torch.equal(a, b)
 
 
+def _planted(n=12000, U=200, I=120, seed=2):
+    rng = np.random.default_rng(seed)
+    u = rng.integers(0, U, n).astype(np.int64) + 1000; i = rng.integers(0, I, n).astype(np.int64) + 50000
+    return u, i, ((u + i) % 2).astype(np.float64)
+
+
 def test_zero_biases_stay_zero_and_train_and_evaluate_runs(S):
     """The reference starts from zero biases and multiplies the error by the bias itself (SVD.py:205-206): they never
-    move.  train_and_evaluate end to end on a planted low-rank preference matrix."""
-    rng = np.random.default_rng(2)
-    U, I, n = 200, 120, 12000
-    u = rng.integers(0, U, n).astype(np.int64) + 1000; i = rng.integers(0, I, n).astype(np.int64) + 50000
-    r = ((u + i) % 2).astype(np.float64)
-    user_ids, item_ids, uid_max, iid_max, mu, frame = S.digest(u[:10000], i[:10000], r[:10000])
-    # held-out frame over the same dense id space (pairs whose ids were seen in training)
-    keep = np.array([a in user_ids and b in item_ids for a, b in zip(u[10000:].tolist(), i[10000:].tolist())])
-    tu = np.array([user_ids[a] for a in u[10000:][keep].tolist()], np.int32)
-    ti = np.array([item_ids[b] for b in i[10000:][keep].tolist()], np.int32)
-    test = S.Ratings(tu, ti, r[10000:][keep], num_users=uid_max + 1, num_items=iid_max + 1)
-    res = S.train_and_evaluate(frame, test, user_ids, item_ids, uid_max, iid_max, mu, epochs=3, seed=0)
+    move.  train_and_evaluate end to end over a chunked dataset, with the reference's call sequence."""
+    from oracle import svd as OS
+    u, i, r = _planted()
+    ds = S.RatingChunks.split(u, i, r, 5)
+    ds.use_no_test_set()
+    user_ids, item_ids, uid_max, iid_max, mu = S.digest(ds)
+    uv, iv, du, di, mu_ref = OS.digest(u, i, r)
+    assert list(user_ids) == uv.tolist() and list(item_ids) == iv.tolist()
+    np.testing.assert_allclose(mu, mu_ref, rtol=1e-13)
+    assert ds.next_cross_validation_distribution() and ds.test_set_index == 4
+    res = S.train_and_evaluate(ds, user_ids, item_ids, uid_max, iid_max, mu, None, epochs=3, seed=0)
     P, Q, bu, bi = res["parameters"]
     assert not bu.any().item() and not bi.any().item()
-    assert res["epoch_mse"][0] > res["epoch_mse"][-1] > 0
+    assert res["epoch_mse"][0] > res["epoch_mse"][-1] > 0 and len(res["epoch_test_mse"]) == 3
     assert set(res["all_data"]) == {"tp", "tn", "fp", "fn", "precision", "recall", "hitRate"}
     assert res["all_data"]["tp"] + res["all_data"]["fp"] == 10 * (uid_max + 1)
+    # the same three epochs through the oracle, from the same start, over the same training chunks in order
+    P0, Q0, bu0, bi0 = S.init_parameters(uid_max + 1, iid_max + 1, S.NUMBER_OF_EMBEDDINGS, seed=0)
+    Pc, Qc, buc, bic = (t.cpu().numpy().copy() for t in (P0, Q0, bu0, bi0))
+    n_train = sum(len(c[0]) for c in ds)
+    for _ in range(3):
+        OS.fit_epoch_c(du[:n_train], di[:n_train], r[:n_train], Pc, Qc, buc, bic, mu, S.LEARNING_RATE,
+                       S.EMBEDDING_REGULARIZATION, S.BIAS_REGULARIZATION)
+    np.testing.assert_allclose(P.cpu().numpy(), Pc, rtol=RTOL, atol=1e-14)
+    np.testing.assert_allclose(Q.cpu().numpy(), Qc, rtol=RTOL, atol=1e-14)
+    mse_test, _ = OS.errors(du[n_train:], di[n_train:], r[n_train:], Pc, Qc, buc, bic, mu)
+    np.testing.assert_allclose(res["mse"], mse_test, rtol=RTOL)
+
+
+def test_cross_validate_is_the_reference_main_loop(S):
+    """Five folds, last chunk held out first, metric dicts averaged with getAverage (SVD.py:540-566); the grundfos
+    variant keeps only rating == 1 rows in the test set (:389-392)."""
+    u, i, r = _planted(n=6000, U=80, I=60, seed=4)
+    ds = S.RatingChunks.split(u, i, r, 5, test_positive_only=True)
+    out = S.cross_validate(ds, epochs=1, seed=1)
+    assert out["folds"] == [4, 3, 2, 1, 0] and len(out["mse"]) == 5
+    assert set(out["all_data"]) == {"tp", "tn", "fp", "fn", "precision", "recall", "hitRate"}
+    ds.test_set_index = 2
+    tu, ti, tr = ds.get_test_set()
+    assert (tr == 1).all() and len(ds.test_frame()) == len(tu) < len(ds.chunks[2][0])
+    assert len(ds.train_frame()) == sum(len(ds.chunks[c][0]) for c in (0, 1, 3, 4))

@@ -1,0 +1,65 @@
+"""Host-side logic of the biased-SVD mirror that needs no GPU: the chunked-dataset protocol of the reference
+(movielens_cross_validation / grundfos_network_drive_files, src/origin_models/svd/SVD.py:301-409) and the fold
+distribution of cross_validate over ranks (gloo, world size 2)."""
+import numpy as np
+import pytest
+
+from test_distributed_cpu import _spawn
+
+
+def _ds(n=23, chunks=5, **kw):
+    from binrec_b200 import SVD as S
+    return S, S.RatingChunks.split(np.arange(n) + 100, np.arange(n) + 500, (np.arange(n) % 3 == 0).astype(float), chunks, **kw)
+
+
+def test_chunk_protocol_follows_the_reference():
+    S, ds = _ds()
+    assert [len(c[0]) for c in ds.chunks] == [5, 5, 5, 4, 4]                 # np.array_split, SVD.py:310
+    assert ds.test_set_index == 4 and len(list(ds)) == 4                      # last chunk held out at first (:306)
+    ds.use_no_test_set()
+    assert len(list(ds)) == 5                                                 # iterator returns every chunk (:313-314)
+    with pytest.raises(Exception, match="There is no test set"):
+        ds.get_test_set()                                                     # (:328-330)
+    seen = []
+    while ds.next_cross_validation_distribution():                           # n-1, ..., 0 then False (:318-324)
+        seen.append(ds.test_set_index)
+        held = ds.get_test_set()
+        assert np.array_equal(held[0], ds.chunks[ds.test_set_index][0])
+        assert [c[0][0] for c in ds] == [ds.chunks[c][0][0] for c in range(5) if c != ds.test_set_index]
+    assert seen == [4, 3, 2, 1, 0] and ds.test_set_index == -1
+
+
+def test_grundfos_test_set_keeps_rating_one_rows_only():
+    S, ds = _ds(test_positive_only=True)
+    u, i, r = ds.get_test_set()                                               # query("RATING_TYPE==1"), SVD.py:389-392
+    assert (r == 1).all() and len(u) == int((ds.chunks[4][2] == 1).sum())
+
+
+def test_frames_need_digest_and_shuffle_is_seeded():
+    S, ds = _ds()
+    with pytest.raises(S.N.BrkError, match="digest"):
+        ds.train_frame()
+    a = S.RatingChunks.split(np.arange(50), np.arange(50), np.ones(50), 5, shuffle_seed=3)
+    b = S.RatingChunks.split(np.arange(50), np.arange(50), np.ones(50), 5, shuffle_seed=3)
+    assert all(np.array_equal(x[0], y[0]) for x, y in zip(a.chunks, b.chunks))
+    assert not np.array_equal(np.concatenate([c[0] for c in a.chunks]), np.arange(50))
+
+
+def test_fold_assignment_covers_every_fold_once():
+    from binrec_b200 import SVD as S
+    for world in (1, 2, 3, 8):
+        got = sorted(f for r in range(world) for f in S.fold_assignment(5, r, world))
+        assert got == [0, 1, 2, 3, 4]
+
+
+def _merge(rank, world):
+    from binrec_b200 import SVD as S
+    local = {f: {"mse": 10.0 * f + rank} for f in S.fold_assignment(5, rank, world)}
+    merged = S.merge_fold_results(local, 5)
+    return {f: merged[f]["mse"] for f in sorted(merged)}
+
+
+def test_fold_results_are_gathered_over_ranks_gloo():
+    out = _spawn(_merge, world=2)
+    want = {0: 0.0, 1: 11.0, 2: 20.0, 3: 31.0, 4: 40.0}                        # fold f ran on rank f % 2
+    assert out[0] == want and out[1] == want
