@@ -328,6 +328,9 @@ def product_arm(args):
     extras = secondary_measurements(dev) if (world == 1 and not args.no_extras) else None
     if extras is not None:
         extras["svd_fit"] = svd_measurement(dev, cpu_baseline=not args.no_cpu_baseline)
+        if rank == 0 and not args.no_cpu_baseline:
+            for key, cb in extras_cpu_baselines().items():       # cpu_baseline legs of the secondary measurements
+                extras.setdefault(key, {"config": "CPU leg only (the reference's own batch size)"})["cpu_baseline"] = cb
 
     # ---- max over ranks ---------------------------------------------------------------------------
     t = torch.tensor([total_ms, hot_ms, e2e_ms, float(fb_ms.mean())], dtype=torch.float64, device=dev)
@@ -406,6 +409,48 @@ def product_arm(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def extras_cpu_baselines(budget_s=2.5):
+    """The oracle (torch-CPU restatement of the reference, all host threads; NOT TensorFlow) timed on bounded samples
+    of the other BASELINE.json configs, keyed like `extras`: NeuMF at the bench batch and at the reference's own batch
+    of 128 (NeuMFModel.py:102), the two-tower step at its batch of 1000 (twoTower.py:292), full-catalog top-K as the
+    reference evaluates it (matmul + top_k in 5000-user batches, twoTower.py:293)."""
+    from oracle import neumf as ON, twotower as OTT
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    rng = np.random.default_rng(0)
+    U, I = 6040, 3706
+    out = {}
+
+    def timed(fn, units):
+        fn()                                                            # warm-up
+        t0 = time.perf_counter(); n = 0
+        while time.perf_counter() - t0 < budget_s:
+            fn(); n += 1
+        dt = time.perf_counter() - t0
+        return units * n / dt, n, dt
+
+    for B, key in ((BATCH, "neumf_train"), (128, "neumf_train_reference_batch")):
+        orc = ON.NeuMFOracle(U, I, emb=32, dropout=0.0)                 # no dropout: the oracle's NumPy Philox masks would dominate
+        u = rng.integers(0, U, B); i = rng.integers(0, I, B); y = (rng.random(B) < 0.2).astype(np.float32)
+        v, n, dt = timed(lambda: orc.step(u, i, y), B)
+        out[key] = {"value": v, "unit": "interactions/s", "cores": threads, "kind": "port",
+                    "sample": f"{n} steps of batch {B} in {dt:.1f} s, NeuMF F=32 oracle (autograd + exact Keras Adam, dropout off), fp32"}
+    tt = OTT.TwoTowerOracle(U, I, 128, 128)
+    u = rng.integers(2, U + 2, 1000); i = rng.integers(2, I + 2, 1000)
+    v, n, dt = timed(lambda: tt.step(u, i, cand_ids=i), 1000)
+    out["twotower_train"] = {"value": v, "unit": "interactions/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} steps of batch 1000 in {dt:.1f} s, two-tower E=S=128 oracle (in-batch softmax, Adagrad), fp32"}
+    Q = torch.randn(U, 128); Cm = torch.randn(I, 128)
+
+    def topk():
+        for a in range(0, U, 5000):
+            torch.topk(Q[a:a + 5000] @ Cm.T, 10)
+    v, n, dt = timed(topk, U)
+    out["topk_ml1m"] = {"value": v, "unit": "users/s", "cores": threads, "kind": "port",
+                        "sample": f"{n} passes of 6040 users x 3706 items, d=128, k=10 in {dt:.1f} s (fp32 matmul + top_k, 5000-user batches)"}
+    return out
 
 
 def svd_measurement(dev, cpu_baseline=True):
