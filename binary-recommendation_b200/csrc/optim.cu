@@ -116,7 +116,7 @@ constexpr int kRowsInFlight = 4;
 
 template <class Op, bool HAS_V>
 __device__ __forceinline__ void rows_pass(const TabList& tl, const Op& op) {
-  __shared__ int32_t s_rows[kThreads / 32][1024];             // row offsets (relative to the chunk) per warp
+  __shared__ int32_t s_rows[kThreads / 32][1024];             // touched rows of the warp's current pass
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = (int64_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
   const int64_t n_warps = (int64_t(gridDim.x) * kThreads) >> 5;
@@ -131,15 +131,21 @@ __device__ __forceinline__ void rows_pass(const TabList& tl, const Op& op) {
     const int gpw = 32 / lpr;
     const int grp = lane / lpr, lane_in = lane % lpr;
     const int64_t nwords = (t.rows + 31) >> 5;
-    // words per warp: 32 for big tables (coalesced scan), fewer when the table is too small to
-    // give every warp something to do
+    // words per warp and pass: 32 for big tables, fewer when the table is too small to give every warp something
+    // to do.  The wpw words of one pass are taken `stride` words apart (lane l reads word l * stride + slot), not
+    // next to each other: with skewed ids the touched rows crowd into a few neighbouring words (ids drawn as
+    // floor(rows * r^3) put ~700 of a 65 536 batch's rows into the first 1024), and a warp that owned that whole
+    // neighbourhood worked alone for 0.6 ms while the rest of the grid had finished (20 M-row tables: 601 -> the
+    // uniform-id time).  Spread out, no warp gets more than one word of any neighbourhood.
     int wpw = 32;
     while (wpw > 1 && nwords < n_warps * wpw) wpw >>= 1;
-    for (int64_t base = warp * wpw; base < nwords; base += n_warps * wpw) {
+    const int64_t stride = (nwords + wpw - 1) / wpw;            // slots: [0, stride)
+    for (int64_t slot = warp; slot < stride; slot += n_warps) {
       uint32_t word = 0u;
-      if (lane < wpw && base + lane < nwords) {
-        word = t.touched[base + lane];
-        if (word) t.touched[base + lane] = 0u;
+      const int64_t widx = int64_t(lane) * stride + slot;
+      if (lane < wpw && widx < nwords) {
+        word = t.touched[widx];
+        if (word) t.touched[widx] = 0u;
       }
       if (__ballot_sync(0xffffffffu, word != 0u) == 0u) continue;
       // exclusive prefix sum of the per-lane popcounts -> each lane expands its word into the list
@@ -156,10 +162,9 @@ __device__ __forceinline__ void rows_pass(const TabList& tl, const Op& op) {
       while (w) {
         const int bit = __ffs(w) - 1;
         w &= w - 1;
-        my_rows[pos++] = lane * 32 + bit;
+        my_rows[pos++] = int32_t(widx * 32 + bit);              // absolute row (rows < 2^31)
       }
       __syncwarp();
-      const int64_t row0 = base << 5;
       if (vec && chunks <= lpr) {
         // one float4 per lane and row: kRowsInFlight rows per group, loads first, then compute and store
         for (int j0 = 0; j0 < total; j0 += gpw * kRowsInFlight) {
@@ -170,7 +175,7 @@ __device__ __forceinline__ void rows_pass(const TabList& tl, const Op& op) {
             const int j = j0 + q * gpw + grp;
             idx[q] = -1;
             if (j < total && lane_in < chunks) {
-              idx[q] = (row0 + my_rows[j]) * chunks + lane_in;
+              idx[q] = int64_t(my_rows[j]) * chunks + lane_in;
               w4[q] = reinterpret_cast<const float4*>(t.w)[idx[q]];
               m4[q] = reinterpret_cast<const float4*>(t.m)[idx[q]];
               if (HAS_V) v4[q] = reinterpret_cast<const float4*>(t.v)[idx[q]];
@@ -192,7 +197,7 @@ __device__ __forceinline__ void rows_pass(const TabList& tl, const Op& op) {
         }
       } else {
         for (int j = grp; j < total; j += gpw) {
-          const int64_t row = row0 + my_rows[j];
+          const int64_t row = my_rows[j];
           for (int c = lane_in; c < chunks; c += lpr) {
             if (vec) apply4<Op, HAS_V>(op, t.w, t.m, t.v, t.g, row * chunks + c);
             else     apply1<Op, HAS_V>(op, t.w, t.m, t.v, t.g, row * chunks + c);
