@@ -164,6 +164,29 @@ class NeuMFNet:
         self.optimizer.apply(self.tables(), dense=[self.dense])
         return loss, out
 
+    def train_steps(self, u, i, y, batch, order, epoch=0, losses=None, out=None):
+        """The inner loop of fit over a resident frame u / i / y: batch b = rows [b * batch, (b + 1) * batch) for b
+        in `order`, fused step + optimizer each, enqueued by ONE C call (brk_neumf_train_steps) -- no Python between
+        steps.  Single process with the stock Adam only; otherwise the per-step path (train_on_batch) is used."""
+        order = np.ascontiguousarray(order, dtype=np.int64)
+        n = u.numel()
+        losses = losses if losses is not None else torch.empty(len(order), dtype=torch.float32, device=self.device)
+        out = out if out is not None else torch.empty(min(batch, n), dtype=torch.float32, device=self.device)
+        if D.world_size() > 1 or not isinstance(self.optimizer, H.Adam):
+            for k, b in enumerate(order):
+                s = slice(int(b) * batch, min(n, (int(b) + 1) * batch))
+                self.train_on_batch(u[s], i[s], y[s], first_index=int(b) * batch, epoch=epoch,
+                                    out=out[:s.stop - s.start], loss_out=losses[k:k + 1])
+            return losses
+        m, ws = self._c_model(), self._workspace(min(batch, n))
+        opt = self.optimizer
+        N.check(N.lib().brk_neumf_train_steps(
+            N.ctx(self.device), C.byref(m), N.ptr(H._i32(u, "u")), N.ptr(H._i32(i, "i")), N.ptr(H._f32(y, "y")), n,
+            int(batch), order.ctypes.data_as(C.POINTER(C.c_int64)), len(order), self.dropout_seed & 0xFFFFFFFF,
+            epoch & 0xFFFFFFFF, opt.h, N.ptr(opt.state), 1 if opt.sparse == "lazy" else 0, C.byref(ws), N.ptr(out),
+            N.ptr(losses), N.stream_ptr()), "brk_neumf_train_steps")
+        return losses
+
     def predict_on_batch(self, u, i, y=None):
         """Inference with the BN moving statistics; returns (predictions, loss or None)."""
         B = u.numel()
@@ -301,9 +324,11 @@ class NeuMFDataset:
         order = self.batch_order(epoch)
         if steps is not None:
             order = order[:int(steps)]
+        if hasattr(net, "train_steps"):                       # one C call for the whole list of batches
+            return net.train_steps(self.u, self.i, self.y, self.batchSize, order, epoch=epoch)
         losses = torch.empty(len(order), dtype=torch.float32, device=self.device)
         outs = torch.empty(self.batchSize, dtype=torch.float32, device=self.device)
-        for k, b in enumerate(order):
+        for k, b in enumerate(order):                         # nets with their own step (row-sharded tables)
             s = slice(b * self.batchSize, min(self.n, (b + 1) * self.batchSize))
             net.train_on_batch(self.u[s], self.i[s], self.y[s], first_index=int(b) * self.batchSize, epoch=epoch,
                                out=outs[:s.stop - s.start], loss_out=losses[k:k + 1])

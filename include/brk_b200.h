@@ -219,6 +219,18 @@ int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, con
                    const float* y, int64_t batch, int64_t global_batch, int64_t first_index, int32_t training,
                    uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
                    float* out, float* loss_out, void* stream);
+/* brk_neumf_train_steps: the inner loop of model.fit (src/models/RModel.py:130-137) over batches of a resident
+ * training frame u / i / y [n_rows] (what bootstrapDataset builds, NeuMFModel.py:102-123): for s < n_steps, batch
+ * b = batch_index_host[s] = rows [b * batch, min(n_rows, (b + 1) * batch)) goes through brk_neumf_step (training,
+ * first_index = b * batch: the dropout stream is a function of the row's position in the frame) and then the
+ * optimizer: lazy_adam == 0 exact Keras Adam over the four tables and the dense block (brk_adam_dense_keras),
+ * != 0 dense block + touched rows only (brk_adam_rows).  losses [n_steps] (device, may be NULL) receives the step
+ * losses, out [batch] the predictions of the last step.  Enqueues 6-7 kernels per step and returns; no sync. */
+int brk_neumf_train_steps(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, const int32_t* i,
+                          const float* y, int64_t n_rows, int64_t batch, const int64_t* batch_index_host,
+                          int32_t n_steps, uint32_t dropout_seed, uint32_t dropout_epoch, brk_adam_hyper h,
+                          int64_t* adam_state, int32_t lazy_adam, const brk_neumf_workspace* ws, float* out,
+                          float* losses, void* stream);
 
 /* Test hook for the tcgen05 building blocks of the NeuMF tensor-core path (csrc/neumf_tc.cu): stages A
  * [a_rows, a_cols] and B [b_rows, b_cols] (row-major fp32; cols multiples of 32, rows multiples of 8) as

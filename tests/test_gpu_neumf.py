@@ -135,3 +135,28 @@ def test_neumf_model_class_end_to_end(dev, tmp_path):
     m2 = NeuMFModel(workDir=str(tmp_path)); m2.compileModel(None, m.model.numUser, m.model.numItem, m.numFactor)
     m2.restoreFromLatestCheckPoint()
     assert torch.equal(m2.model.uMLP.w, m.model.uMLP.w)
+
+
+@pytest.mark.parametrize("sparse", ["keras", "lazy"])
+def test_train_steps_in_one_call_equal_the_per_step_loop(dev, sparse):
+    """brk_neumf_train_steps (fit's inner loop as one C call) against train_on_batch per batch: same batches, same
+    dropout stream positions, same optimizer calls -- equal up to the RED accumulation order."""
+    from binrec_b200.NeuMFModel import NeuMFNet
+    rng = np.random.default_rng(3)
+    U, I, n, B = 500, 300, 5000, 384                         # ragged last batch: 5000 = 13 * 384 + 8
+    u = torch.from_numpy(rng.integers(0, U, n).astype(np.int32)).to(dev)
+    i = torch.from_numpy(rng.integers(0, I, n).astype(np.int32)).to(dev)
+    y = torch.from_numpy((rng.random(n) < 0.25).astype(np.float32)).to(dev)
+    order = rng.permutation((n + B - 1) // B)
+    a = NeuMFNet(U, I, 32, dropout=0.2, device=dev, sparse_adam=sparse)
+    b = NeuMFNet(U, I, 32, dropout=0.2, device=dev, sparse_adam=sparse)
+    la = torch.empty(len(order), device=dev)
+    for k, bb in enumerate(order):
+        s = slice(int(bb) * B, min(n, (int(bb) + 1) * B))
+        a.train_on_batch(u[s], i[s], y[s], first_index=int(bb) * B, epoch=2, loss_out=la[k:k + 1])
+    lb = b.train_steps(u, i, y, B, order, epoch=2)
+    np.testing.assert_allclose(lb.cpu().numpy(), la.cpu().numpy(), rtol=1e-4, atol=1e-6)
+    for ta, tb in zip(a.tables() + [a.dense], b.tables() + [b.dense]):
+        np.testing.assert_allclose(tb.w.cpu().numpy(), ta.w.cpu().numpy(), rtol=1e-3, atol=2e-5)
+    assert int(a.optimizer.state[0].item()) == int(b.optimizer.state[0].item()) == len(order)
+    np.testing.assert_allclose(b.bn_moving.cpu().numpy(), a.bn_moving.cpu().numpy(), rtol=1e-4, atol=1e-6)
