@@ -6,6 +6,7 @@
 //   adagrad_rows     : Keras sparse Adagrad over touched rows: 4*4d + 4d + 4d B per touched row.
 // Reference call sites: Adam(1e-3) /root/reference/src/models/NeuMFModel.py:89, BPRModel.py:70,
 // bpr.py:201; Adam(lr=0.005) trainers/NFC_plain.py:153; "Adagrad" 0.1 trainers/twoTower.py:278-279.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -112,6 +113,8 @@ __device__ __forceinline__ void dense_pass(const TabList& tl, const Op& op) {
 // into a per-warp row list in shared memory and update those rows; a row is handled by `lpr` lanes as float4
 // chunks and every lane group keeps kRowsInFlight rows' loads in flight (the pass is DRAM-latency bound: at
 // BASELINE.json configs[3] densities a warp finds 3-30 rows per 1024 scanned).
+// Rows in flight per lane group.  4 costs 128 registers per thread (2 CTAs per SM); 2 would fit 3 CTAs per SM but
+// measured slower at every touched-row count (65 k of 20 M rows: 42 vs 37 us; 1 M: 397 vs 384 us).
 constexpr int kRowsInFlight = 4;
 
 template <class Op, bool HAS_V>
@@ -218,7 +221,7 @@ adam_dense_kernel(TabList tl, brk_adam_hyper h, int64_t* step_dev, unsigned int*
   advance_step_last_block(step_dev, h, ticket, advance);
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 adam_rows_kernel(TabList tl, brk_adam_hyper h, int64_t* step_dev, unsigned int* ticket, int advance) {
   AdamOp op;
   op.alpha = adam_alpha(h, step_dev);
@@ -227,7 +230,7 @@ adam_rows_kernel(TabList tl, brk_adam_hyper h, int64_t* step_dev, unsigned int* 
   advance_step_last_block(step_dev, h, ticket, advance);
 }
 
-__global__ void __launch_bounds__(kThreads) adagrad_rows_kernel(TabList tl, float lr, float eps) {
+__global__ void __launch_bounds__(kThreads, 2) adagrad_rows_kernel(TabList tl, float lr, float eps) {
   AdagradOp op{lr, eps};
   rows_pass<AdagradOp, false>(tl, op);
 }
@@ -254,6 +257,17 @@ int pack(const char* who, const brk_table* tabs, int32_t n_tabs, bool need_v, bo
   return 0;
 }
 
+// Row passes: a persistent grid of exactly the CTAs that are resident at once (the 8-per-SM cap of grid_for ran
+// the 2-per-SM row kernels in four waves, each with its own latency tail: 65 k touched rows of 20 M took 50 us,
+// 37 us now).
+template <class K>
+int rows_grid(const brk_ctx* ctx, K kernel, int64_t threads_wanted, int* grid) {
+  int occ = 0;
+  BRK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0));
+  const int64_t need = (threads_wanted + kThreads - 1) / kThreads, cap = int64_t(ctx->sm_count) * (occ < 1 ? 1 : occ);
+  *grid = int(need < 1 ? 1 : (need < cap ? need : cap));
+  return 0;
+}
 int grid_for(const brk_ctx* ctx, int64_t threads_wanted) {
   int64_t need = (threads_wanted + kThreads - 1) / kThreads;
   const int64_t cap = int64_t(ctx->sm_count) * (2048 / kThreads);
@@ -278,8 +292,9 @@ extern "C" int brk_adam_rows(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs
   BRK_REQUIRE(ctx && step_dev, BRK_E_ARG, "brk_adam_rows: null argument");
   TabList tl; int64_t work;
   if (int rc = pack("brk_adam_rows", tabs, n_tabs, true, true, &tl, &work)) return rc;
-  adam_rows_kernel<<<grid_for(ctx, work), kThreads, 0, (cudaStream_t)stream>>>(tl, h, step_dev, ctx->tickets + 2,
-                                                                              advance_step);
+  int grid = 1;
+  if (int rc = rows_grid(ctx, adam_rows_kernel, work, &grid)) return rc;
+  adam_rows_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(tl, h, step_dev, ctx->tickets + 2, advance_step);
   BRK_LAUNCH_CHECK();
   return 0;
 }
@@ -289,7 +304,9 @@ extern "C" int brk_adagrad_rows(brk_ctx* ctx, const brk_table* tabs, int32_t n_t
   BRK_REQUIRE(ctx, BRK_E_ARG, "brk_adagrad_rows: null context");
   TabList tl; int64_t work;
   if (int rc = pack("brk_adagrad_rows", tabs, n_tabs, false, true, &tl, &work)) return rc;
-  adagrad_rows_kernel<<<grid_for(ctx, work), kThreads, 0, (cudaStream_t)stream>>>(tl, lr, eps);
+  int grid = 1;
+  if (int rc = rows_grid(ctx, adagrad_rows_kernel, work, &grid)) return rc;
+  adagrad_rows_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(tl, lr, eps);
   BRK_LAUNCH_CHECK();
   return 0;
 }
