@@ -330,7 +330,7 @@ def product_arm(args):
         extras["svd_fit"] = svd_measurement(dev, cpu_baseline=not args.no_cpu_baseline)
         if rank == 0 and not args.no_cpu_baseline:
             for key, cb in extras_cpu_baselines().items():       # cpu_baseline legs of the secondary measurements
-                extras.setdefault(key, {"config": "CPU leg only (the reference's own batch size)"})["cpu_baseline"] = cb
+                extras.setdefault(key, {"config": "CPU leg only"})["cpu_baseline"] = cb
 
     # ---- max over ranks ---------------------------------------------------------------------------
     t = torch.tensor([total_ms, hot_ms, e2e_ms, float(fb_ms.mean())], dtype=torch.float64, device=dev)
@@ -523,6 +523,17 @@ def secondary_measurements(dev):
     out["neumf_train"] = {"value": B / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
                           "config": "NeuMF F=32 (MLP 64-32-16-8, BN, dropout 0.2, MSE), ML-1M tables, batch 16384, Keras Adam, "
                                     "fp32 on the CUDA cores (csrc/neumf2.cu)"}
+    # the reference's own batch size (bootstrapDataset default 128, NeuMFModel.py:102): fit's inner loop over a resident
+    # frame, one C call for all steps (brk_neumf_train_steps)
+    Br, steps_r = 128, 400
+    ur = torch.randint(0, U, (Br * steps_r,), generator=g, device=dev, dtype=torch.int32)
+    ir = torch.randint(0, I, (Br * steps_r,), generator=g, device=dev, dtype=torch.int32)
+    yr = (torch.rand(Br * steps_r, generator=g, device=dev) < 0.2).float()
+    order_r = np.arange(steps_r)
+    s = timed(lambda: net.train_steps(ur, ir, yr, Br, order_r), 3, warm=1) / steps_r
+    out["neumf_train_reference_batch"] = {"value": Br / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
+                                          "config": "NeuMF F=32 as above at the reference's batch of 128: latency-bound "
+                                                    "(six dependent kernels on one or two CTAs each)"}
     del net
     for E, tag in ((32, "neumf_train_tc"), (64, "neumf64_train_tc")):
         Bn = 65536
