@@ -112,7 +112,7 @@ def test_neumf_tensor_core_training_tracks_fp32_and_eval(dev):
 
 # ---- general TF32 product (csrc/gemm_tc.cu) and the two-tower step on it -------------------------------------------
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (1000, 128, 128), (1000, 1000, 128), (1000, 128, 1000), (128, 128, 1000),
-                                   (300, 64, 96), (77, 200, 40)])
+                                   (300, 64, 96), (77, 200, 40), (4100, 128, 64)])   # tile widths 32 / 64 / 128 all occur
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_gemm_tf32_all_layouts_exact_on_representable_inputs(dev, M, N, K, ta, tb):
     from binrec_b200 import _native as Nn
