@@ -110,6 +110,7 @@ SIGNATURES = {
                                          C.POINTER(C.c_int64), _I32, brk_adam_hyper, C.POINTER(brk_dp_peer), _P, _P, _P]),
     "brk_sgemm": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F32, _I32, _P]),
     "brk_gemm_tf32": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F32, _I32, _P]),
+    "brk_gemm_tf32_trace": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F32, _I32, _P, _P]),
     "brk_tower_forward": (C.c_int, [_P, C.POINTER(brk_tower), _P, _I64, _P, _P, _P]),
     "brk_twotower_step": (C.c_int, [_P, C.POINTER(brk_tower), C.POINTER(brk_tower), _P, _P, _P, _P, _I64, _I32, _I32,
                                     C.POINTER(brk_twotower_workspace), _P, _P]),

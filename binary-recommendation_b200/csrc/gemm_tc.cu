@@ -35,7 +35,15 @@ struct Params {
   float alpha;
   int accumulate;          // 0: C = ..., 1: C += ... (REDs when split-K)
   int k_per_split;         // multiple of KC
+  unsigned long long* trace;   // optional [8] globaltimer stamps of CTA 0 (brk_gemm_tf32_trace), else null
 };
+__device__ __forceinline__ void stamp(const Params& P, int k) {
+  if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    P.trace[k] = t;
+  }
+}
 
 // 16-byte asynchronous global -> shared copy; bytes beyond src_bytes are zero-filled (src_bytes in [0, 16])
 __device__ __forceinline__ void cp_async16(uint8_t* dst, const void* src, int src_bytes) {
@@ -85,6 +93,7 @@ __global__ void __launch_bounds__(NT) gemm_tf32_kernel(const Params P) {
   const int kbeg = blockIdx.z * P.k_per_split;
   const int kend = min(P.K, kbeg + P.k_per_split);
   const int m_end = P.M, n_end = P.N;
+  stamp(P, 0);
   if (t == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) tc::mbar_init(tc::smem_u32(&bar[s]), 1);
@@ -95,6 +104,7 @@ __global__ void __launch_bounds__(NT) gemm_tf32_kernel(const Params P) {
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
+  stamp(P, 1);                             // TMEM allocated
   constexpr uint32_t idesc = tc::idesc_tf32_f32(BM, BN, A_MN, B_MN);
   const int n_chunks = (kend - kbeg + KC - 1) / KC;
   auto issue = [&](int c) {               // copies of chunk c into stage c % STAGES (an empty group past the end)
@@ -114,6 +124,7 @@ __global__ void __launch_bounds__(NT) gemm_tf32_kernel(const Params P) {
     tc::fence_proxy_async_smem();
     __syncthreads();                      // ... and everybody's
     tc::fence_after_sync();
+    if (c == 0) stamp(P, 2);              // first chunk staged
     if (t == 0) {
       const uint32_t a = tc::smem_u32(sm + uint32_t(sidx) * STAGE_BYTES), bb = a + A_BYTES;
 #pragma unroll
@@ -142,6 +153,7 @@ __global__ void __launch_bounds__(NT) gemm_tf32_kernel(const Params P) {
   }
   tc::fence_after_sync();
   __syncthreads();                         // all MMAs done: the stage buffers become the epilogue's staging tile
+  stamp(P, 3);                             // products complete
   if (n_chunks > 0) {
     // epilogue: warp w reads lane quadrant (w & 3), column half (w >> 2); rows go through shared memory so that the
     // global stores are whole 16-byte chunks of consecutive columns (row-per-thread scalar stores cost 12 us per tile)
@@ -160,6 +172,7 @@ __global__ void __launch_bounds__(NT) gemm_tf32_kernel(const Params P) {
               make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
     }
     __syncthreads();
+    stamp(P, 4);                           // accumulators in shared memory
     const bool split = gridDim.z > 1;
     const bool vec = (P.ldc & 3) == 0 && brk_aligned16(P.C);
     for (int idx = t; idx < BM * (BN / 4); idx += NT) {
@@ -186,7 +199,9 @@ __global__ void __launch_bounds__(NT) gemm_tf32_kernel(const Params P) {
   }
   tc::fence_before_sync();
   __syncthreads();
+  stamp(P, 5);                             // stores issued
   if (t < 32) tc::tmem_dealloc<TCOLS>(tmem);
+  stamp(P, 6);
 }
 
 template <int BN, int A_MN, int B_MN>
@@ -210,16 +225,16 @@ int launch(brk_ctx* ctx, const Params& P, int splits, cudaStream_t st) {
 // Same contract as brk_sgemm (trans_a: A stored [K,M]; trans_b: B stored [N,K]); additionally lda / ldb / the
 // operand bases must allow 16-byte loads (multiples of 4 floats, 16-byte aligned) and M, N >= 1.  Returns
 // BRK_E_ALIGN when they do not -- the caller then takes brk_sgemm.
-int brk_gemm_tf32_impl(brk_ctx* ctx, const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
-                       int ldb, int ldc, int trans_a, int trans_b, float alpha, int accumulate, bool allow_split,
-                       cudaStream_t st) {
+static int gemm_tf32_run(brk_ctx* ctx, const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
+                         int ldb, int ldc, int trans_a, int trans_b, float alpha, int accumulate, bool allow_split,
+                         cudaStream_t st, unsigned long long* trace) {
   if ((lda & 3) || (ldb & 3) || !brk_aligned16(A) || !brk_aligned16(B)) {
     brk_set_error("brk_gemm_tf32: operands must be 16-byte aligned with leading dimensions that are multiples of 4");
     return BRK_E_ALIGN;
   }
   gtc::Params P;
   P.A = A; P.B = B; P.C = C; P.bias = bias; P.M = M; P.N = N; P.K = K; P.lda = lda; P.ldb = ldb; P.ldc = ldc;
-  P.alpha = alpha; P.accumulate = accumulate;
+  P.alpha = alpha; P.accumulate = accumulate; P.trace = trace;
   // Tile width: the widest of 128 / 64 / 32 that still gives the grid a quarter of a wave of CTAs.  Small products
   // (the two-tower Dense layers at batch 1000: 8 row tiles) are bound by the latency of ONE CTA -- staging, the
   // tcgen05.ld epilogue and the stores of a 128-wide tile -- so narrower tiles on more SMs finish sooner.
@@ -247,6 +262,12 @@ int brk_gemm_tf32_impl(brk_ctx* ctx, const float* A, const float* B, float* C, c
   return BRK_E_ARG;
 }
 
+int brk_gemm_tf32_impl(brk_ctx* ctx, const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
+                       int ldb, int ldc, int trans_a, int trans_b, float alpha, int accumulate, bool allow_split,
+                       cudaStream_t st) {
+  return gemm_tf32_run(ctx, A, B, C, bias, M, N, K, lda, ldb, ldc, trans_a, trans_b, alpha, accumulate, allow_split, st, nullptr);
+}
+
 extern "C" int brk_gemm_tf32(brk_ctx* ctx, const float* A, const float* B, float* C, const float* bias, int32_t M, int32_t N,
                              int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t trans_a, int32_t trans_b, float alpha,
                              int32_t accumulate, void* stream) {
@@ -254,4 +275,15 @@ extern "C" int brk_gemm_tf32(brk_ctx* ctx, const float* A, const float* B, float
   BRK_REQUIRE(M > 0 && N > 0 && K > 0, BRK_E_ARG, "brk_gemm_tf32: M=%d N=%d K=%d", M, N, K);
   return brk_gemm_tf32_impl(ctx, A, B, C, bias, M, N, K, lda, ldb, ldc, trans_a, trans_b, alpha, accumulate, true,
                             (cudaStream_t)stream);
+}
+
+// Diagnostics: the same product with CTA (0,0,0) writing %globaltimer (ns) into trace[0..6] at: kernel entry, TMEM
+// allocated, first K chunk staged, all MMAs complete, accumulators copied to shared memory, stores issued, TMEM freed.
+extern "C" int brk_gemm_tf32_trace(brk_ctx* ctx, const float* A, const float* B, float* C, const float* bias, int32_t M,
+                                   int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t trans_a,
+                                   int32_t trans_b, float alpha, int32_t accumulate, uint64_t* trace, void* stream) {
+  BRK_REQUIRE(ctx && A && B && C && trace, BRK_E_ARG, "brk_gemm_tf32_trace: null argument");
+  BRK_REQUIRE(M > 0 && N > 0 && K > 0, BRK_E_ARG, "brk_gemm_tf32_trace: M=%d N=%d K=%d", M, N, K);
+  return gemm_tf32_run(ctx, A, B, C, bias, M, N, K, lda, ldb, ldc, trans_a, trans_b, alpha, accumulate, true,
+                       (cudaStream_t)stream, reinterpret_cast<unsigned long long*>(trace));
 }

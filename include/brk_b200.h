@@ -342,6 +342,12 @@ int brk_sgemm(brk_ctx* ctx, const float* A, const float* B, float* C, const floa
 int brk_gemm_tf32(brk_ctx* ctx, const float* A, const float* B, float* C, const float* bias, int32_t M,
                   int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t trans_a, int32_t trans_b,
                   float alpha, int32_t accumulate, void* stream);
+/* Diagnostics: brk_gemm_tf32 with CTA (0,0,0) writing %globaltimer (ns) into trace[0..6] (device uint64 [8]) at kernel
+ * entry, TMEM allocated, first K chunk staged, all MMAs complete, accumulators in shared memory, stores issued, TMEM
+ * freed (profiles/gemm_trace.py). */
+int brk_gemm_tf32_trace(brk_ctx* ctx, const float* A, const float* B, float* C, const float* bias, int32_t M,
+                        int32_t N, int32_t K, int32_t lda, int32_t ldb, int32_t ldc, int32_t trans_a,
+                        int32_t trans_b, float alpha, int32_t accumulate, uint64_t* trace, void* stream);
 int brk_tower_forward(brk_ctx* ctx, const brk_tower* t, const int32_t* ids, int64_t n, float* emb_out,
                       float* out, void* stream);
 int brk_twotower_step(brk_ctx* ctx, const brk_tower* user, const brk_tower* item, const int32_t* u,
