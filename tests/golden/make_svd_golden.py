@@ -109,5 +109,51 @@ def main():
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", {k: float(out[k + "/mse"][-1]) for k in ("tiny", "defaults", "stars_reg", "quintiles")})
 
 
+def cv_protocol():
+    """tests/golden/svd_cv_protocol.json: the chunked-dataset protocol of movielens_cross_validation (SVD.py:301-347)
+    and of the main loop (:519-551) recorded from the executed class on a 23-row file: chunk sizes, which chunks the
+    iterator yields for every position of the test-set index, the order the folds are visited, the error text."""
+    import json
+    import tempfile
+    svd = load_svd()
+    n = 23
+    df = pd.DataFrame({"user_id": np.arange(n) + 100, "item_id": np.arange(n) + 500, "rating": (np.arange(n) % 3 == 0) * 1.0})
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "all.csv")
+        df.to_csv(path, index=False)
+        svd.FILE_PATH = path
+        np.random.seed(0)                                   # .sample(frac=1) draws from the global NumPy state
+        ds = svd.movielens_cross_validation(path, 5, ["user_id", "item_id", "rating"])
+    # np.array_split of a DataFrame gives DataFrames under the pandas the reference was written for and plain arrays
+    # under the pandas 3 of this container; the protocol (sizes, indices, iteration) is the same code either way
+    users_of = lambda ch: ch["user_id"].to_numpy() if hasattr(ch, "columns") else np.asarray(ch)[:, 0]
+    chunk_of = {}
+    for c, chunk in enumerate(ds.chunks):
+        for uid in users_of(chunk):
+            chunk_of[int(uid)] = c
+    yielded = lambda: [chunk_of[int(users_of(ch)[0])] for ch in ds]
+    out = {"sizes": [len(c) for c in ds.chunks], "initial_test_set_index": ds.test_set_index, "initial_yield": yielded()}
+    ds.use_no_test_set()
+    out["no_test_set_yield"] = yielded()
+    try:
+        ds.get_test_set()
+    except Exception as e:                                  # noqa: BLE001 -- the reference raises a bare Exception
+        out["no_test_set_error"] = str(e)
+    folds = []
+    while ds.next_cross_validation_distribution():
+        test = ds.get_test_set()
+        folds.append({"test_set_index": ds.test_set_index, "test_chunk": chunk_of[int(users_of(test)[0])],
+                      "test_rows": len(test), "yield": yielded()})
+    out["folds"] = folds
+    out["final_test_set_index"] = ds.test_set_index
+    dst = os.path.join(os.path.dirname(OUT), "svd_cv_protocol.json")
+    with open(dst, "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", dst, out["sizes"], [f["test_set_index"] for f in folds])
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "cv":
+        cv_protocol()
+    else:
+        main()

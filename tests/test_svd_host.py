@@ -29,6 +29,30 @@ def test_chunk_protocol_follows_the_reference():
     assert seen == [4, 3, 2, 1, 0] and ds.test_set_index == -1
 
 
+def test_chunk_protocol_matches_the_executed_reference_class():
+    """tests/golden/svd_cv_protocol.json was recorded by EXECUTING movielens_cross_validation (SVD.py:301-347) and the
+    main loop's fold walk (:540-551) on a 23-row file (tests/golden/make_svd_golden.py cv)."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "svd_cv_protocol.json")))
+    S, ds = _ds()
+    chunk_of = {int(u): c for c, ch in enumerate(ds.chunks) for u in ch[0]}
+    yielded = lambda: [chunk_of[int(ch[0][0])] for ch in ds]
+    assert [len(c[0]) for c in ds.chunks] == g["sizes"]
+    assert ds.test_set_index == g["initial_test_set_index"] and yielded() == g["initial_yield"]
+    ds.use_no_test_set()
+    assert yielded() == g["no_test_set_yield"]
+    with pytest.raises(Exception) as e:
+        ds.get_test_set()
+    assert str(e.value) == g["no_test_set_error"]
+    folds = []
+    while ds.next_cross_validation_distribution():
+        test = ds.get_test_set()
+        folds.append({"test_set_index": ds.test_set_index, "test_chunk": chunk_of[int(test[0][0])], "test_rows": len(test[0]),
+                      "yield": yielded()})
+    assert folds == g["folds"] and ds.test_set_index == g["final_test_set_index"]
+
+
 def test_grundfos_test_set_keeps_rating_one_rows_only():
     S, ds = _ds(test_positive_only=True)
     u, i, r = ds.get_test_set()                                               # query("RATING_TYPE==1"), SVD.py:389-392
