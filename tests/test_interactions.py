@@ -95,3 +95,32 @@ def test_csv_to_cache_with_raw_integer_ids(tmp_path):
     csv.write_text("CUSTOMER_ID,PRODUCT_ID,MATERIAL,QUANTITY\n-3,7,1,1\n")
     with pytest.raises(IX.InteractionError):
         IX.csv_to_cache(str(csv), str(tmp_path / "t2.brkc"), "neumf")
+
+
+def test_loaders_match_the_executed_reference():
+    """tests/golden/loader_golden.json holds what the reference's own loaders (trainers/loadBinaryMovieLens.py gfData
+    :41-62, movieLensData :8-39) returned for three small files (tests/golden/make_loader_golden.py): parsed id columns
+    (strings, leading zeros kept, first row dropped) and the pd.unique vocabularies in first-appearance order."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loader_golden.json")))
+
+    def first_appearance(col):
+        seen = {}
+        for x in col:
+            seen.setdefault(x, len(seen))
+        return list(seen)
+
+    for key, schema, vocab_u, vocab_i in (("gf", "twotower", "usersId", "materialsId"),
+                                          ("gf_rdzero", "twotower-rdzero", "usersId", "materialsId"),
+                                          ("ml100k", "ml-100k", "usersId", "moviesId")):
+        c = IX.read_csv_columns(io.StringIO(g["inputs"][key]), schema)
+        want = g[key]
+        assert [str(x) for x in c["user"]] == want["users"] and [str(x) for x in c["item"]] == want["items"], key
+        assert first_appearance([str(x) for x in c["user"]]) == want[vocab_u], key
+        assert first_appearance([str(x) for x in c["item"]]) == want[vocab_i], key
+        assert len(want[vocab_u]) == want["nbrUser"]
+        if "values" in want:
+            assert c["value"].tolist() == want["values"]
+    # ml-100k: the reference overwrites every rating with ratedVal (:15); the raw stars stay available here
+    assert IX.read_csv_columns(io.StringIO(g["inputs"]["ml100k"]), "ml-100k")["value"].tolist() == [3.0, 3.0, 1.0, 5.0, 2.0]
