@@ -76,3 +76,20 @@ def test_keras_adagrad_fp64():
     w2 = np.array([[1.0], [2.0]]); acc2 = np.full_like(w2, 0.1)
     E.adagrad_dense(w2, acc2, g, lr=0.1)
     assert np.array_equal(w, w2) and np.array_equal(acc, acc2)
+
+
+def test_bpr_exhaustive_triplets_match_the_executed_reference(tmp_path):
+    """BPRModel.extractPositivesNegatives against tests/golden/bpr_triplets_golden.json, recorded by EXECUTING the
+    reference's method (src/models/BPRModel.py:111-119; tests/golden/make_bpr_triplets_golden.py).  Host logic only."""
+    import json
+    import os
+    import numpy as np
+    from binrec_b200.BPRModel import BPRModel
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bpr_triplets_golden.json")))
+    for case in cases:
+        m = BPRModel(workDir=str(tmp_path))
+        m._trainDf = (np.asarray(case["users"]), np.asarray(case["items"]))
+        m._productIds = list(case["productIds"])
+        for customer, want in case["entries"].items():
+            got = [[e["CUSTOMER_ID"], int(e["pPRODUCT_ID"]), int(e["nPRODUCT_ID"])] for e in m.extractPositivesNegatives(int(customer))]
+            assert got == want, customer
