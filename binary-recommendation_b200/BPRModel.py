@@ -264,6 +264,75 @@ def bpr_predict(model, user_id, item_ids, user_layer='user_embedding', item_laye
     return (rows * uvec).sum(-1)
 
 
+def _rank_eval(model, ground_truth, items, k, user_layer='user_embedding', item_layer='item_embedding'):
+    """(auc [R], ap_at_k [R]) float64 NumPy arrays for the (user, true items) rows of ground_truth: fp32 scores of
+    every user against `items` (one SGEMM per chunk of users: bpr_predict for all of them), then ONE counting kernel
+    per chunk (brk_rank_eval_rows) instead of sklearn's roc_auc_score and a Python sort of the catalog per user."""
+    dev = model.device
+    rows = [(int(u), list(t)) for u, t in ground_truth]
+    items = list(items)
+    pos_of = {}
+    for j, it in enumerate(items):
+        pos_of.setdefault(it, j)                                   # list.index: the first occurrence
+    R, I = len(rows), len(items)
+    auc = np.full(R, np.nan); ap = np.full(R, np.nan)
+    if R == 0 or I == 0:
+        return auc, ap
+    indptr = np.zeros(R + 1, dtype=np.int64)
+    cols, alen = [], np.zeros(R, dtype=np.int32)
+    for r, (u, true_items) in enumerate(rows):
+        try:
+            c = sorted({pos_of[t] for t in true_items})
+        except KeyError as e:
+            raise ValueError(f"{e.args[0]} is not in list") from None     # items.index(p) in the reference
+        cols.extend(c); indptr[r + 1] = len(cols); alen[r] = len(true_items)
+    W_u, W_i = model.get_layer_weights(user_layer), model.get_layer_weights(item_layer)
+    d = W_u.shape[1]
+    item_rows = H.gather_rows(W_i, torch.as_tensor(np.asarray(items, dtype=np.int32)).to(dev))      # [I, d]
+    users = torch.as_tensor(np.asarray([u for u, _ in rows], dtype=np.int32)).to(dev)
+    cols_d = torch.as_tensor(np.asarray(cols if cols else [0], dtype=np.int32)).to(dev)
+    alen_d = torch.from_numpy(alen).to(dev)
+    rank_ws = torch.empty(max(len(cols), 1), dtype=torch.int32, device=dev)
+    part_ws = torch.empty(max(len(cols), 1), dtype=torch.float64, device=dev)
+    out = torch.empty((R, 2), dtype=torch.float64, device=dev)
+    chunk = max(1, min(R, (1 << 26) // I))                       # <= 256 MiB of fp32 scores per pass
+    scores = torch.empty((chunk, I), dtype=torch.float32, device=dev)
+    lib, ctx = N.lib(), N.ctx(dev)
+    for a in range(0, R, chunk):
+        b = min(R, a + chunk)
+        uv = H.gather_rows(W_u, users[a:b])                      # [b - a, d]
+        N.check(lib.brk_sgemm(ctx, N.ptr(uv), N.ptr(item_rows), N.ptr(scores), None, b - a, I, d, d, d, I, 0, 1, 1.0, 0,
+                              N.stream_ptr()), "brk_sgemm")
+        ip = torch.from_numpy(indptr[a:b + 1] - indptr[a]).to(dev)
+        off = int(indptr[a])
+        N.check(lib.brk_rank_eval_rows(ctx, N.ptr(scores), b - a, I, N.ptr(ip), N.ptr(cols_d[off:]), N.ptr(alen_d[a:b]), int(k),
+                                       N.ptr(rank_ws[off:]), N.ptr(part_ws[off:]), N.ptr(out[a:b]), N.stream_ptr()),
+                "brk_rank_eval_rows")
+    o = out.cpu().numpy()
+    return o[:, 0], o[:, 1]
+
+
+def full_auc(model, ground_truth, items) -> float:
+    """bpr.py:230-253: mean over the users with a non-empty true list of the AUC of that user's scores against the
+    whole item list (ties count half, as sklearn's roc_auc_score).  ground_truth: iterable of (user_id, true items)."""
+    rows = [(u, t) for u, t in ground_truth]
+    auc, _ = _rank_eval(model, rows, items, 1)
+    scores = [a for a, (_, t) in zip(auc, rows) if len(t)]
+    if any(np.isnan(a) for a in scores):
+        raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")   # sklearn's
+    return sum(scores) / len(scores)                              # ZeroDivisionError when nobody has a true item
+
+
+def mean_average_precision_k(model, ground_truth, items, k=100) -> float:
+    """bpr.py:256-289: mean over users of average precision at k over the catalog sorted by score (stable: the
+    earlier item first among equal scores), each divided by min(len(actual), k)."""
+    rows = [(u, t) for u, t in ground_truth]
+    if any(len(t) == 0 for _, t in rows):
+        raise ZeroDivisionError("float division by zero")         # score / min(len(actual), k)
+    _, ap = _rank_eval(model, rows, items, k)
+    return float(np.mean(ap))
+
+
 class BPRModel(RModel):
     def __init__(self, workDir=None):
         super().__init__('BPRModel', workDir)

@@ -395,6 +395,20 @@ int brk_topk_metrics(brk_ctx* ctx, const int32_t* ids, int64_t U, int32_t k, con
                      const int64_t* pos_indptr, const int32_t* pos_items, int64_t csr_users,
                      int64_t* counts_out, double* ndcg_sum_out, void* stream);
 
+/* brk_rank_eval_rows: per-user AUC and average precision at k of src/models/bpr.py:230-289 (full_auc ->
+ * sklearn roc_auc_score per user; mean_average_precision_k -> Python sort of the whole catalog per user) from ONE
+ * counting pass: for every positive p of row r of scores [R, I] (fp32, one row per user, one column per catalog
+ * item) its 0-based rank = #{j: s_j > s_p} + #{j < p: s_j == s_p} (stable descending order, the earlier item first
+ * among equals) and the number of negatives below / equal to it.
+ *   out[2r]   = AUC of row r, ties counted half (NaN when the row has no positive or no negative);
+ *   out[2r+1] = sum over positives with rank < k of (positives ranked at or above it) / (rank + 1), divided by
+ *               min(actual_len[r], k)  (actual_len NULL: the number of positives; NaN when that is 0).
+ * Positives: CSR over rows, pos_indptr int64 [R+1], pos_cols int32 column positions (distinct per row).
+ * rank_ws int32 / part_ws double: device scratch, one entry per positive (pos_indptr[R] entries). */
+int brk_rank_eval_rows(brk_ctx* ctx, const float* scores, int64_t R, int64_t I, const int64_t* pos_indptr,
+                       const int32_t* pos_cols, const int32_t* actual_len, int32_t k, int32_t* rank_ws,
+                       double* part_ws, double* out, void* stream);
+
 /* ---- input pipeline (the caller's side of the training step) ------
  * brk_epoch_permutation: out[j] = perm(first + j), j < count, where perm is the keyed bijection of [0, n)
  *   "brk perm v1" (oracle/pipeline.py: six-round Feistel network over max(2, ceil(log2 n)) bits, round keys =

@@ -71,3 +71,26 @@ class BPROracle:
 def bpr_predict(user_tab, item_tab, user_id, item_ids):
     """bpr.py:122-133: user vector times item matrix."""
     return item_tab[np.asarray(item_ids, dtype=np.int64)] @ user_tab[user_id]
+
+
+def auc_and_ap_at_k(scores, positives, actual_len, k):
+    """Per-user AUC and average precision at k as /root/reference/src/models/bpr.py:230-289 computes them, from one
+    row of scores over the catalog: AUC = sklearn's roc_auc_score (ties count half); AP@k over the catalog sorted by
+    score, descending, stable (earlier position first among equals), divided by min(actual_len, k).
+    positives: distinct column positions.  Returns (auc, ap); NaN where the reference would raise."""
+    s = np.asarray(scores)
+    pos = np.asarray(sorted(set(int(p) for p in positives)), dtype=np.int64)
+    is_pos = np.zeros(len(s), dtype=bool); is_pos[pos] = True
+    neg = s[~is_pos]
+    if len(pos) and len(neg):
+        auc = float(np.mean([(np.sum(neg < s[p]) + 0.5 * np.sum(neg == s[p])) / len(neg) for p in pos]))
+    else:
+        auc = float("nan")
+    order = np.argsort(-s.astype(np.float64), kind="stable")[:k]
+    hits, score = 0.0, 0.0
+    for rank, j in enumerate(order):
+        if is_pos[j]:
+            hits += 1.0
+            score += hits / (rank + 1.0)
+    den = min(int(actual_len), int(k))
+    return auc, (score / den if den > 0 else float("nan"))

@@ -68,3 +68,62 @@ def test_topkratings_format_and_scores(dev):
         ref = OT.topk_insert_reference(scores, 5)
         assert [i for _, i in lst] == [i for _, i in ref]
         assert [float(s) for s, _ in lst] == [s for s, _ in ref]
+
+
+class _FakeBPR:
+    """What full_auc / mean_average_precision_k need from a model: device, get_layer_weights(name)."""
+    def __init__(self, P, Q, dev):
+        self.device = dev
+        self.w = {"user_embedding": torch.from_numpy(np.ascontiguousarray(P, dtype=np.float32)).to(dev),
+                  "item_embedding": torch.from_numpy(np.ascontiguousarray(Q, dtype=np.float32)).to(dev)}
+
+    def get_layer_weights(self, name):
+        return self.w[name]
+
+
+def test_full_auc_and_map_match_the_executed_reference(dev):
+    """binrec_b200.BPRModel.full_auc / mean_average_precision_k (one SGEMM + one counting kernel per chunk of users)
+    against tests/golden/bpr_eval_golden.npz, recorded by EXECUTING the reference's functions (src/models/bpr.py:230-289):
+    exact on the exact-arithmetic case with heavy ties, 1e-6 where fp32 summation order may move a near-tie."""
+    import json
+    import os
+    from binrec_b200.BPRModel import full_auc, mean_average_precision_k, _rank_eval
+    from oracle import bpr as OB
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bpr_eval_golden.npz"))
+    for name in ("random", "ties", "small_k"):
+        g = lambda key: G[f"{name}/{key}"]
+        items, truth = g("items").tolist(), [(u, t) for u, t in json.loads(str(g("truth")))]
+        m = _FakeBPR(g("P"), g("Q"), dev)
+        tol = 1e-12 if name == "ties" else 1e-6
+        np.testing.assert_allclose(full_auc(m, truth, items), float(g("auc")), rtol=tol)
+        for k, want in zip(g("ks").tolist(), g("map")):
+            np.testing.assert_allclose(mean_average_precision_k(m, truth, items, k=k), want, rtol=tol)
+    # per-user values against the oracle restatement, exact-arithmetic inputs (bit-exact scores, heavy ties)
+    rng = np.random.default_rng(9)
+    P = (rng.integers(-2, 3, size=(50, 8)) / 2.0).astype(np.float32); Q = (rng.integers(-2, 3, size=(300, 8)) / 2.0).astype(np.float32)
+    items = rng.permutation(300)[:257].tolist()
+    truth = [(int(u), [int(x) for x in rng.choice(items, size=int(rng.integers(1, 40)), replace=False)]) for u in range(50)]
+    auc, ap = _rank_eval(_FakeBPR(P, Q, dev), truth, items, 10)
+    pos_of = {it: j for j, it in enumerate(items)}
+    for r, (u, t) in enumerate(truth):
+        a, p = OB.auc_and_ap_at_k(Q[items] @ P[u], [pos_of[x] for x in t], len(t), 10)
+        assert auc[r] == pytest.approx(a, rel=1e-13) and ap[r] == pytest.approx(p, rel=1e-13)
+
+
+def test_full_auc_and_map_edge_cases(dev):
+    from binrec_b200.BPRModel import full_auc, mean_average_precision_k
+    m = _FakeBPR(np.eye(3, 4), np.arange(20, dtype=np.float32).reshape(5, 4), dev)
+    items = [4, 2, 0, 1]
+    with pytest.raises(ValueError):                                         # items.index(p) of an unknown item
+        full_auc(m, [(0, [3])], items)
+    with pytest.raises(ZeroDivisionError):                                  # nobody has a true item: sum([]) / 0
+        full_auc(m, [(0, [])], items)
+    with pytest.raises(ZeroDivisionError):                                  # score / min(len(actual), k)
+        mean_average_precision_k(m, [(0, [])], items)
+    with pytest.raises(ValueError):                                         # every catalog item positive: one class only
+        full_auc(m, [(1, [4, 2, 0, 1])], items)
+    # user 0 scores items by their first coordinate: item 4 (16) > 2 (8) > 1 (4) > 0 (0); truth {2}: rank 1 of 4
+    assert full_auc(m, [(0, [2])], items) == pytest.approx(2.0 / 3.0)
+    assert mean_average_precision_k(m, [(0, [2])], items, k=1) == 0.0
+    assert mean_average_precision_k(m, [(0, [2])], items, k=2) == pytest.approx(0.5)
+    assert mean_average_precision_k(m, [(0, [2, 2, 2])], items, k=100) == pytest.approx(0.5 / 3.0)   # len(actual) counts repeats

@@ -93,3 +93,34 @@ def test_bpr_exhaustive_triplets_match_the_executed_reference(tmp_path):
         for customer, want in case["entries"].items():
             got = [[e["CUSTOMER_ID"], int(e["pPRODUCT_ID"]), int(e["nPRODUCT_ID"])] for e in m.extractPositivesNegatives(int(customer))]
             assert got == want, customer
+
+
+def _bpr_eval_cases():
+    import json
+    import os
+    import numpy as np
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bpr_eval_golden.npz"))
+    for name in ("random", "ties", "small_k"):
+        g = lambda key: G[f"{name}/{key}"]
+        yield name, g("P"), g("Q"), g("items").tolist(), json.loads(str(g("truth"))), float(g("auc")), g("ks").tolist(), g("map"), g("scores_u0")
+
+
+def test_auc_and_map_oracle_matches_the_executed_reference():
+    """oracle/bpr.py:auc_and_ap_at_k against tests/golden/bpr_eval_golden.npz, recorded by EXECUTING the reference's
+    full_auc / mean_average_precision_k / bpr_predict (src/models/bpr.py:122-289; make_bpr_eval_golden.py)."""
+    import numpy as np
+    from oracle import bpr as OB
+    for name, P, Q, items, truth, auc, ks, maps, scores_u0 in _bpr_eval_cases():
+        pos_of = {it: j for j, it in reversed(list(enumerate(items)))}
+        np.testing.assert_allclose(Q[items] @ P[truth[0][0]], scores_u0, rtol=1e-6, atol=1e-7)
+        aucs, aps = [], {k: [] for k in ks}
+        for u, true_items in truth:
+            s = (Q[items].astype(np.float32) @ P[u].astype(np.float32)).astype(np.float32)
+            for k in ks:
+                a, ap = OB.auc_and_ap_at_k(s, [pos_of[t] for t in true_items], len(true_items), k)
+                aps[k].append(ap)
+            aucs.append(a)
+        # the "ties" case is exact arithmetic, so equal scores are equal in every summation order: exact agreement
+        tol = 1e-12 if name == "ties" else 1e-6
+        np.testing.assert_allclose(np.mean(aucs), auc, rtol=tol)
+        np.testing.assert_allclose([np.mean(aps[k]) for k in ks], maps, rtol=tol)
