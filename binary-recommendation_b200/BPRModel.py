@@ -264,6 +264,33 @@ def bpr_predict(model, user_id, item_ids, user_layer='user_embedding', item_laye
     return (rows * uvec).sum(-1)
 
 
+def rating_triplets(user_ids, movie_ids, ratings, threshold=3):
+    """The explicit-rating triplet frame of the script version (bpr.py:96-110): for every user, in order of first
+    appearance, each positively rated item (rating > threshold) paired with each negatively rated one
+    (rating <= threshold), positives outer / negatives inner, both in file order; users lacking either kind are
+    skipped and reported.  Returns (user, positive, negative) int32 arrays -- the customerId_input / pProduct_input /
+    nProduct_input columns BPRNet.fit takes (bpr.py:215-217) -- and the list of skipped users.  Host NumPy: input preparation, not the hot path."""
+    u = np.asarray(user_ids); m = np.asarray(movie_ids); r = np.asarray(ratings)
+    if not (len(u) == len(m) == len(r)):
+        raise ValueError("user_ids, movie_ids and ratings differ in length")
+    order = np.argsort(u, kind="stable")                          # rows of one user stay in file order
+    su = u[order]
+    starts = np.flatnonzero(np.r_[True, su[1:] != su[:-1]]) if len(su) else np.zeros(0, np.int64)
+    ends = np.r_[starts[1:], len(su)]
+    first_row = order[starts] if len(su) else starts
+    uu, pp, nn, without = [], [], [], []
+    for g in np.argsort(first_row, kind="stable"):               # users in order of first appearance (.unique())
+        rows = order[starts[g]:ends[g]]
+        pos = m[rows][r[rows] > threshold]; neg = m[rows][r[rows] <= threshold]
+        if len(pos) == 0 or len(neg) == 0:
+            without.append(su[starts[g]].item())
+            continue
+        uu.append(np.full(len(pos) * len(neg), su[starts[g]]))
+        pp.append(np.repeat(pos, len(neg))); nn.append(np.tile(neg, len(pos)))
+    cat = lambda parts: np.concatenate(parts).astype(np.int32) if parts else np.zeros(0, np.int32)
+    return cat(uu), cat(pp), cat(nn), without
+
+
 def _rank_eval(model, ground_truth, items, k, user_layer='user_embedding', item_layer='item_embedding'):
     """(auc [R], ap_at_k [R]) float64 NumPy arrays for the (user, true items) rows of ground_truth: fp32 scores of
     every user against `items` (one SGEMM per chunk of users: bpr_predict for all of them), then ONE counting kernel

@@ -124,3 +124,26 @@ def test_auc_and_map_oracle_matches_the_executed_reference():
         tol = 1e-12 if name == "ties" else 1e-6
         np.testing.assert_allclose(np.mean(aucs), auc, rtol=tol)
         np.testing.assert_allclose([np.mean(aps[k]) for k in ks], maps, rtol=tol)
+
+
+def test_rating_triplets_follow_the_script_loop():
+    """binrec_b200.BPRModel.rating_triplets against the literal loop of src/models/bpr.py:96-107 (the script cannot be
+    executed: it downloads MovieLens and trains at import), on seeded ratings with users lacking positives / negatives."""
+    import numpy as np
+    from binrec_b200.BPRModel import rating_triplets
+    rng = np.random.default_rng(4)
+    u = rng.integers(0, 12, 300); m = rng.integers(0, 40, 300); r = rng.integers(1, 6, 300)
+    r[u == 3] = 5; r[u == 7] = 2                                   # user 3: no negatives, user 7: no positives
+    want, without = [], []
+    seen = list(dict.fromkeys(u.tolist()))                         # df_train.user_id.unique()
+    for user in seen:
+        pos = m[(u == user) & (r > 3)]; neg = m[(u == user) & (r <= 3)]
+        if len(neg) == 0 or len(pos) == 0:
+            without.append(user); continue
+        for p in pos:
+            for n in neg:
+                want.append((user, int(p), int(n)))
+    gu, gp, gn, gw = rating_triplets(u, m, r)
+    assert list(zip(gu.tolist(), gp.tolist(), gn.tolist())) == want and gw == without and set(without) == {3, 7}
+    e = rating_triplets([], [], [])
+    assert len(e[0]) == 0 and e[3] == []
