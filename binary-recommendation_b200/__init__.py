@@ -2,7 +2,8 @@
 full-catalog top-K scoring, as hand-written sm_100a CUDA behind a C ABI (include/brk_b200.h).
 
 Import as ``binrec_b200`` (this directory's name has a hyphen).  Modules mirror the reference:
-  RModel, NeuMFModel, BPRModel   <- src/models/*.py
+  RModel, NeuMFModel, BPRModel, NCFModel   <- src/models/*.py
+  SVD                            <- src/origin_models/svd/SVD.py
   twoTower                       <- trainers/twoTower.py
   topKmetrics                    <- trainers/topKmetrics.py
   hotpath / _native              <- the Keras/TF ops underneath (gather, scatter, optimizers, ...)

@@ -105,3 +105,46 @@ def test_sharded_neumf_checkpoint_serves_from_an_unsharded_model(dev, tmp_path):
     for t, t2 in zip(sh._tables(), sh2._tables()):
         assert np.array_equal(t.full_weights(), t2.full_weights())
     assert torch.equal(sh2.dense.m, sh.dense.m) and torch.equal(sh2.optimizer.state, sh.optimizer.state)
+
+
+def test_ncf_model_serves_like_the_reference(dev, tmp_path):
+    """NCFModel (src/models/NCFModel.py): serve-only class around the script-spec network -- product / customer ids
+    from the training file in first-appearance order (:60-64), checkpoint restore on a fresh object, predictForUser =
+    predictions over ALL product ids, those >= 1.0 dropped, best numberOfItem as {product: '%.9f'} (:42-51)."""
+    from binrec_b200.NCFModel import NCFModel
+    csv = tmp_path / "test.csv"
+    rng = np.random.default_rng(3)
+    rows = ["customer_id,normalized_customer_id,material,product_id,rating_type"]
+    cust = rng.integers(0, 40, 300); prod = rng.integers(0, 60, 300)
+    rows += [f"{900000 + c},{c},{55000 + p},{p},{int(rng.random() < 0.5)}" for c, p in zip(cust, prod)]
+    csv.write_text("\n".join(rows) + "\n")
+    m = NCFModel(workDir=str(tmp_path), trainData=str(csv))
+    assert m.productIds == list(dict.fromkeys(prod.tolist())) and m.customerIds == list(dict.fromkeys(cust.tolist()))
+    assert not m.readyToTrain() and m.getPredictableUsers() == m.customerIds
+    net = m.compileModel(None, 40, 60)
+    assert (net.E, net.hidden, net.act, net.loss) == (10, (100, 50, 10), "sigmoid", "bce")
+    u = torch.from_numpy(cust.astype(np.int32)).to(dev); i = torch.from_numpy(prod.astype(np.int32)).to(dev)
+    y = torch.from_numpy((rng.random(300) < 0.5).astype(np.float32)).to(dev)
+    for _ in range(5):
+        net.train_on_batch(u, i, y)
+    m.saveCheckPoint()
+    fresh = NCFModel(workDir=str(tmp_path))
+    fresh.restoreFromLatestCheckPoint()                                    # what the REST endpoint does
+    assert fresh.productIds == m.productIds and fresh.getPredictableUsers() == m.customerIds
+    customer = m.customerIds[3]
+    frame = fresh.getPredictDataFrame(customer)
+    assert frame["PRODUCT_ID"] == m.productIds and set(frame["CUSTOMER_ID"]) == {customer}
+    pred, _ = net.predict_on_batch(torch.full((len(m.productIds),), customer, dtype=torch.int32, device=dev),
+                                   torch.as_tensor(np.asarray(m.productIds, dtype=np.int32)).to(dev))
+    pred = pred.cpu().numpy()
+    want = dict(zip(m.productIds, pred))
+    want = dict(filter(lambda e: e[1] < 1.0, want.items()))
+    want = {k: '%.9f' % v for k, v in sorted(want.items(), key=lambda x: x[1], reverse=True)[:7]}
+    got = fresh.predictForUser(customer, 7)
+    assert list(got.items()) == list(want.items())
+    many = fresh.predictForUsers(m.customerIds[:5], 3)
+    assert [list(d) for d in many][3][:3] == list(want)[:3] and all(len(d) == 3 for d in many)
+    with pytest.raises(ValueError):
+        fresh.predictForUser(4000)
+    with pytest.raises(ValueError):
+        fresh.predictForUser(customer, 64)
