@@ -115,3 +115,50 @@ class NCFModel(RModel):
         first = lambda a: list(dict.fromkeys(np.asarray(a).tolist()))
         self.productIds = first(cols["item"])
         self.customerIds = first(cols["user"])
+
+
+def fit_nfc_plain(train, test, epochs=20, batch_size=50000, lr=0.005, dropout=0.2, seed=42, shuffle_seed=7, device=None,
+                  tensor_cores=False, verbose=0):
+    """The training script trainers/NFC_plain.py as a function: `train` / `test` are (customer, product, rating_type)
+    column triples (its two CSVs, columns normalized_customer_id / product_id / rating_type, :72-73).
+      tables   : num_customers + 1 rows with num_customers = #distinct customers over both files, num_materials + 1
+                 rows with num_materials = the largest product id (:79-82, :116-126);
+      model    : latent 10, Dense 100 / 50 / 10 sigmoid with BatchNorm after fc-1 / fc-2, dropout 0.2, head
+                 [pred_mf, pred_mlp], BCE, Adam(0.005) (:109-155);
+      fit      : explicit labels from the file (no negative sampling), batch 50 000, 20 epochs, rows reshuffled every
+                 epoch (`shuffle(train)` :85 and fit(shuffle=True) :165 -- seeded here);
+      after it : predictions on the test file rounded to 2 decimals -> mean absolute error (:178-180), evaluate (:183).
+    Returns {'model', 'history': [epoch losses], 'test_mae_rounded', 'evaluate': [loss, mse, mae, binary_accuracy]}."""
+    from . import pipeline as PL
+    dev = torch.device(device) if device is not None else torch.device(f"cuda:{torch.cuda.current_device()}")
+    tu, ti, ty = (np.asarray(c) for c in train)
+    su, si, sy = (np.asarray(c) for c in test)
+    num_customers = len(np.unique(np.concatenate([tu, su])))
+    num_materials = int(max(ti.max(initial=0), si.max(initial=0)))
+    if max(tu.max(initial=0), su.max(initial=0)) > num_customers:
+        raise ValueError("normalized customer ids must lie in [0, number of distinct customers] (Embedding(num_customers + 1))")
+    net = NeuMFNet(num_customers + 1, num_materials + 1, 10, hidden=(100, 50, 10), act="sigmoid", loss="bce", learning_rate=lr,
+                   dropout=dropout, seed=seed, head_order="mf_h3", device=dev, tensor_cores=tensor_cores)
+    u = torch.from_numpy(np.ascontiguousarray(tu, dtype=np.int32)).to(dev)
+    i = torch.from_numpy(np.ascontiguousarray(ti, dtype=np.int32)).to(dev)
+    y = torch.from_numpy(np.ascontiguousarray(ty, dtype=np.float32)).to(dev)
+    n = u.numel()
+    nb = (n + batch_size - 1) // batch_size
+    history = []
+    for e in range(epochs):
+        perm = PL.epoch_permutation(n, shuffle_seed, e, device=dev)          # rows reshuffled per epoch, on the device
+        ue, ie, ye = u[perm].contiguous(), i[perm].contiguous(), y[perm].contiguous()
+        losses = net.train_steps(ue, ie, ye, batch_size, np.arange(nb), epoch=e)
+        history.append(float(losses.double().mean().item()))
+        if verbose:
+            print(f"Epoch {e + 1}/{epochs} - loss: {history[-1]:.4f}")
+    tu_d = torch.from_numpy(np.ascontiguousarray(su, dtype=np.int32)).to(dev)
+    ti_d = torch.from_numpy(np.ascontiguousarray(si, dtype=np.int32)).to(dev)
+    ty_d = torch.from_numpy(np.ascontiguousarray(sy, dtype=np.float32)).to(dev)
+    pred, loss = net.predict_on_batch(tu_d, ti_d, ty_d)
+    y_hat = torch.round(pred * 100.0) / 100.0                               # np.round(..., decimals=2), :178
+    err = pred - ty_d
+    return {"model": net, "history": history,
+            "test_mae_rounded": float((y_hat - ty_d).abs().mean().item()),
+            "evaluate": [float(loss.item()), float((err * err).mean().item()), float(err.abs().mean().item()),
+                         float(((pred > 0.5).float() == ty_d).float().mean().item())]}

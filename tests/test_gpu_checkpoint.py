@@ -148,3 +148,19 @@ def test_ncf_model_serves_like_the_reference(dev, tmp_path):
         fresh.predictForUser(4000)
     with pytest.raises(ValueError):
         fresh.predictForUser(customer, 64)
+
+
+def test_fit_nfc_plain_learns_a_planted_rule(dev):
+    """fit_nfc_plain = the script trainers/NFC_plain.py as a function: explicit labels from the file, script-spec
+    network, rows reshuffled per epoch; a planted parity rule must be learnt and the table sizes follow :79-82."""
+    from binrec_b200.NCFModel import fit_nfc_plain
+    rng = np.random.default_rng(0)
+    C, P, n = 60, 90, 40000
+    c = rng.integers(0, C, n); p = rng.integers(1, P + 1, n)
+    y = ((c % 3 == 0) ^ (p % 2 == 0)).astype(np.float32)
+    res = fit_nfc_plain((c[:32000], p[:32000], y[:32000]), (c[32000:], p[32000:], y[32000:]), epochs=30, batch_size=4000)
+    net = res["model"]
+    assert net.numUser == C + 1 and net.numItem == P + 1 and net.head_order == "mf_h3"
+    assert res["history"][-1] < 0.5 * res["history"][0]
+    loss, mse, mae, acc = res["evaluate"]
+    assert acc > 0.9 and res["test_mae_rounded"] == pytest.approx(mae, abs=0.01)
