@@ -4,7 +4,7 @@ full-catalog top-K scoring, as hand-written sm_100a CUDA behind a C ABI (include
 Import as ``binrec_b200`` (this directory's name has a hyphen).  Modules mirror the reference:
   RModel, NeuMFModel, BPRModel, NCFModel   <- src/models/*.py
   SVD                            <- src/origin_models/svd/SVD.py
-  twoTower                       <- trainers/twoTower.py
+  twoTower, loadBinaryMovieLens  <- trainers/twoTower.py, trainers/loadBinaryMovieLens.py
   topKmetrics                    <- trainers/topKmetrics.py
   hotpath / _native              <- the Keras/TF ops underneath (gather, scatter, optimizers, ...)
 """

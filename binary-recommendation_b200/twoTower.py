@@ -334,10 +334,16 @@ def splitTrainTest(data, ratio, seed=0):
 def crossValidation(dataSets, k, learningRate, optimiser, loss, epoch, embNum, batchSize, randomZero=False,
                     rdZeroDataSets=None, testBatchSize=5000, semb=64, userKey="CUSTOMER_ID", itemKey="MATERIAL",
                     resKey="RATING_TYPE", seed=42, verbose=0):
-    """k-fold cross-validation of twoTower.py:125-272 on in-memory folds: train on all folds but one,
+    """k-fold cross-validation of twoTower.py:125-272 on in-memory folds (dicts of columns) or, like the reference,
+    on a list of file names read through loadBinaryMovieLens.gfData: train on all folds but one,
     index the whole catalog, top-k for every user, topKMetrics against the held-out fold and against
     the training folds ("full_" keys), averaged over folds."""
     folds = list(dataSets)
+    if folds and isinstance(folds[0], str):                    # the reference's call form: file names (twoTower.py:125-139)
+        from .loadBinaryMovieLens import gfData
+        folds = [gfData(f)["ratings"] for f in folds]
+        if randomZero:
+            rdZeroDataSets = [gfData(f, rdZero=True)["ratings"] if isinstance(f, str) else f for f in rdZeroDataSets]
     usersId = list(dict.fromkeys(u for f in folds for u in f[userKey]))
     matId = list(dict.fromkeys(m for f in folds for m in f[itemKey]))
     train_folds = list(rdZeroDataSets) if randomZero else folds

@@ -131,3 +131,19 @@ def test_fit_replayed_as_a_cuda_graph_equals_the_eager_loop(dev, rd):
         np.testing.assert_allclose(tb.w.cpu().numpy(), ta.w.cpu().numpy(), rtol=1e-4, atol=2e-5)
         np.testing.assert_allclose(tb.m.cpu().numpy(), ta.m.cpu().numpy(), rtol=1e-4, atol=1e-6)   # Adagrad accumulators
     assert ma.history["loss"][-1] < ma.history["loss"][0]
+
+
+def test_crossvalidation_from_files_like_the_reference(dev, tmp_path):
+    """crossValidation(filenames, ...) as trainers/twoTower.py:125-139 calls it: every fold is a CSV read through the
+    gfData mirror (string ids, first row dropped); same result keys as the in-memory form."""
+    from binrec_b200.twoTower import crossValidation
+    rng = np.random.default_rng(5)
+    files = []
+    for f in range(3):
+        u = rng.integers(0, 50, 600); m = (u * 7 + rng.integers(0, 3, 600)) % 40        # users prefer a few materials
+        p = tmp_path / f"fold{f}.csv"
+        p.write_text("CUSTOMER_ID,MATERIAL\n" + "".join(f"{a:04d},M{b:03d}\n" for a, b in zip(u, m)))
+        files.append(str(p))
+    res = crossValidation(files, 10, 0.1, "Adagrad", None, 2, 16, 200, semb=8)
+    assert {"tp", "fp", "fn", "tn", "precision", "recall", "hitRate"} <= set(res)
+    assert 0.0 < res["hitRate"] <= 1.0

@@ -124,3 +124,27 @@ def test_loaders_match_the_executed_reference():
             assert c["value"].tolist() == want["values"]
     # ml-100k: the reference overwrites every rating with ratedVal (:15); the raw stars stay available here
     assert IX.read_csv_columns(io.StringIO(g["inputs"]["ml100k"]), "ml-100k")["value"].tolist() == [3.0, 3.0, 1.0, 5.0, 2.0]
+
+
+def test_loader_mirror_returns_the_reference_dicts(tmp_path):
+    """binrec_b200.loadBinaryMovieLens.gfData / movieLensData against the executed reference loaders' results."""
+    import json
+    import os
+    from binrec_b200 import loadBinaryMovieLens as LB
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loader_golden.json")))
+    for key, rd in (("gf", False), ("gf_rdzero", True)):
+        f = tmp_path / (key + ".csv"); f.write_text(g["inputs"][key])
+        r = LB.gfData(str(f), "user", "password", rdZero=rd)
+        want = g[key]
+        assert r["ratings"]["CUSTOMER_ID"] == want["users"] and r["ratings"]["MATERIAL"] == want["items"]
+        assert r["usersId"].tolist() == want["usersId"] and r["materialsId"].tolist() == want["materialsId"]
+        assert (r["nbrUser"], r["nbrMaterial"]) == (want["nbrUser"], want["nbrMaterial"])
+        if rd:
+            assert r["ratings"]["RATING_TYPE"] == want["values"]
+    f = tmp_path / "u.data"; f.write_text(g["inputs"]["ml100k"])
+    r = LB.movieLensData(1, 0, 0.0, path=str(f))
+    want = g["ml100k"]
+    assert r["ratings"]["user_id"] == want["users"] and r["ratings"]["movie_id"] == want["items"]
+    assert r["ratings"]["rating"] == want["ratings"] and r["usersId"].tolist() == want["usersId"]
+    assert r["moviesId"].tolist() == want["moviesId"] and (r["nbrUser"], r["nbrMovie"]) == (want["nbrUser"], want["nbrMovie"])
+    assert r["realRat"] == set(zip(want["users"], want["items"]))
