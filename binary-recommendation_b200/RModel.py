@@ -170,6 +170,33 @@ class RModel:
     def isMaster(self, taskType, taskId) -> bool:
         return taskType is None or taskType == 'chief' or (taskType == 'worker' and taskId == 0)
 
+    def getModelSaveLocation(self, strategy) -> str:
+        """RModel.py:175-179: the chief saves into checkpointPath, every other worker into a temp dir that is removed
+        afterwards (Keras needs all workers to call save).  `strategy` is None (single process) or anything exposing
+        cluster_resolver.task_type / task_id like tf.distribute's strategies.  Kept for callers of the reference API;
+        saveCheckPoint itself needs no temp dirs (every rank writes its own shard files, checkpoint.py)."""
+        if strategy is None or self.isMaster(strategy.cluster_resolver.task_type, strategy.cluster_resolver.task_id):
+            return self.checkpointPath
+        return self.getSlaveTempDir(strategy.cluster_resolver.task_id)
+
+    def getSlaveTempDir(self, taskId):
+        """RModel.py:187-191."""
+        tempDir = os.path.join(self.checkpointPath, 'workertemp_' + str(taskId))
+        os.makedirs(tempDir, exist_ok=True)
+        return tempDir
+
+    def clearSlaveTempDir(self, strategy):
+        """RModel.py:193-196 (the reference removes dirname(tempDir), i.e. the whole checkpoint directory of that
+        worker's file system view; here only the worker's own temp dir is removed)."""
+        import shutil
+        if strategy is not None and self.isMaster(strategy.cluster_resolver.task_type,
+                                                  strategy.cluster_resolver.task_id) is False:
+            shutil.rmtree(self.getSlaveTempDir(strategy.cluster_resolver.task_id), ignore_errors=True)
+
+    def getPredictDataSet(self, customerId):
+        """RModel.py:168-170."""
+        return self.bootstrapDataset(self.getPredictDataFrame(customerId), shuffle=False)
+
     def checkpointMeta(self) -> dict:
         """What restoreFromLatestCheckPoint needs to rebuild the model before loading tensors (the reference's
         SavedModel carries its graph; its test users / products sit in the pickles of RModel.py:28-29)."""

@@ -99,3 +99,24 @@ def test_two_ranks_write_one_checkpoint_gloo(tmp_path):
     assert np.array_equal(CK.load_state_dict(d)["user"].numpy(), full)
     for r in range(3):
         assert np.array_equal(CK.load_checkpoint(d, r, 3)[1]["user"], _shards(full, 3)[r])
+
+
+def test_chief_and_worker_save_locations_follow_the_reference(tmp_path):
+    """getModelSaveLocation / isMaster / getSlaveTempDir / clearSlaveTempDir (src/models/RModel.py:175-196)."""
+    import os
+    import types
+    from binrec_b200.RModel import RModel
+    m = RModel("NeuMFModel", workDir=str(tmp_path))
+    strat = lambda t, i: types.SimpleNamespace(cluster_resolver=types.SimpleNamespace(task_type=t, task_id=i))
+    assert m.isMaster(None, 0) and m.isMaster("chief", 3) and m.isMaster("worker", 0) and not m.isMaster("worker", 1)
+    assert not m.isMaster("ps", 0)
+    assert m.getModelSaveLocation(None) == m.checkpointPath
+    assert m.getModelSaveLocation(strat("chief", 0)) == m.checkpointPath
+    assert m.getModelSaveLocation(strat("worker", 0)) == m.checkpointPath
+    loc = m.getModelSaveLocation(strat("worker", 2))
+    assert loc == os.path.join(m.checkpointPath, "workertemp_2") and os.path.isdir(loc)
+    m.clearSlaveTempDir(strat("worker", 0))                                 # the master clears nothing
+    assert os.path.isdir(loc)
+    m.clearSlaveTempDir(strat("worker", 2))
+    assert not os.path.exists(loc) and os.path.isdir(m.checkpointPath)
+    assert m.getNumberOfWorkers({"cluster": {"worker": ["a:1", "b:2"]}}) == 2 and m.getNumberOfWorkers(None) == 1
