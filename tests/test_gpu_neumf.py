@@ -128,6 +128,8 @@ def test_neumf_model_class_end_to_end(dev, tmp_path):
     feats, label = next(iter(ds))
     assert set(feats) == {"user", "item"} and label.shape == feats["user"].shape
     assert abs(float(ds.y.mean().item()) - 0.25) < 1e-6                     # negRatio 3 -> 1 positive in 4
+    pds = m.getPredictDataSet(m.getPredictableUsers()[0])               # RModel.py:168-170: the frame of predictForUser
+    assert pds.n == 4 * len(m._testProducts) and not pds.shuffle          # bootstrapDataset adds its 3x "negatives" here too
     recs = m.predictForUser(m.getPredictableUsers()[0], 5)
     assert len(recs) == 5 and all(isinstance(a, str) and isinstance(b, str) for a, b in recs)
     scores = [float(b) for _, b in recs]
