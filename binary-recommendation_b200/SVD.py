@@ -402,15 +402,52 @@ def recommend_users(users, user_matrix, item_matrix, k):
     return vals, ids
 
 
+class rating_prediction:
+    """SVD.py:272-283: what recommend returns -- .index, .prediction, printed as "(prediction @ index)".  Iterating
+    yields (index, prediction), so `for i, p in recommend(...)` works as well."""
+
+    def __init__(self, index, prediction):
+        self.index = index
+        self.prediction = prediction
+
+    def __iter__(self):
+        return iter((self.index, self.prediction))
+
+    def __str__(self):
+        return f"({self.prediction} @ {self.index})"
+
+    __repr__ = __str__
+
+
+class svd_prediction_doer:
+    """SVD.py:163-177: the adaptor that gives the factor matrices the `predict` interface of the NFC model, queried
+    with raw ids: predict([[raw user], [raw item]]) -> predict(user_ids[raw user], item_ids[raw item], ...)."""
+
+    def __init__(self, user_ids, item_ids, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias):
+        self.user_matrix = user_matrix
+        self.item_matrix = item_matrix
+        self.user_bias_vector = user_bias_vector
+        self.item_bias_vector = item_bias_vector
+        self.global_bias = global_bias
+        self.user_ids = user_ids
+        self.item_ids = item_ids
+
+    def predict(self, weird_array):
+        user = self.user_ids[weird_array[0][0]]
+        item = self.item_ids[weird_array[1][0]]
+        return predict(user, item, self.user_matrix, self.item_matrix, self.user_bias_vector, self.item_bias_vector,
+                       self.global_bias)
+
+
 def recommend(user_vector, item_matrix, k):
     """recommend (SVD.py:286-299): the k best (index, prediction) of one user vector, best first.  The reference
-    returns its rating_prediction objects in replacement order; here they are (index, prediction) tuples sorted by
-    descending prediction (ties: lower index), the same set."""
+    returns its rating_prediction objects in replacement order; here the same objects come sorted by descending
+    prediction (ties: lower index); unfilled slots (k > number of items) keep index None / prediction -inf as there."""
     Q = _f64(item_matrix, "item_matrix")
     p = _f64(user_vector, "user_vector", Q.device).reshape(1, -1)
     vals, ids = recommend_users(torch.zeros(1, dtype=torch.int32, device=Q.device), p, Q, k)
     vals, ids = vals[0].cpu().numpy(), ids[0].cpu().numpy()
-    return [(int(i) if i >= 0 else None, float(v)) for v, i in zip(vals, ids)]
+    return [rating_prediction(int(i) if i >= 0 else None, float(v)) for v, i in zip(vals, ids)]
 
 
 def do_topk(user_matrix, item_matrix, test_idset, train_idset, user_ids, item_ids, k=10):

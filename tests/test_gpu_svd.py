@@ -59,8 +59,13 @@ def test_fit_predict_errors_match_the_reference_golden(S, name):
     pred0 = S.predict(int(g("users")[0]), int(g("items")[0]), P, Q, bu, bi, mu)
     np.testing.assert_allclose(pred0, g("pred0"), rtol=RTOL)
     rec = S.recommend(P[0], Q, 3)
-    assert [i for i, _ in rec] == g("recommend_u0")[:, 1].astype(int).tolist()
+    assert [r.index for r in rec] == g("recommend_u0")[:, 1].astype(int).tolist()            # rating_prediction objects
     np.testing.assert_allclose([v for _, v in rec], g("recommend_u0")[:, 0], rtol=RTOL)
+    assert str(rec[0]) == f"({rec[0].prediction} @ {rec[0].index})"
+    # svd_prediction_doer (SVD.py:163-177): the same prediction, queried with raw ids
+    uv, iv = g("user_vocab"), g("item_vocab")
+    doer = S.svd_prediction_doer({int(x): j for j, x in enumerate(uv)}, {int(x): j for j, x in enumerate(iv)}, P, Q, bu, bi, mu)
+    np.testing.assert_allclose(doer.predict([[int(g("raw_users")[0])], [int(g("raw_items")[0])]]), g("pred0"), rtol=RTOL)
 
 
 @pytest.mark.parametrize("name", CASES)
