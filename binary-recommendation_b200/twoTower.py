@@ -333,11 +333,15 @@ def splitTrainTest(data, ratio, seed=0):
 
 def crossValidation(dataSets, k, learningRate, optimiser, loss, epoch, embNum, batchSize, randomZero=False,
                     rdZeroDataSets=None, testBatchSize=5000, semb=64, userKey="CUSTOMER_ID", itemKey="MATERIAL",
-                    resKey="RATING_TYPE", seed=42, verbose=0):
+                    resKey="RATING_TYPE", seed=42, verbose=0, rdZeroFilenames=None, bname=None):
     """k-fold cross-validation of twoTower.py:125-272 on in-memory folds (dicts of columns) or, like the reference,
     on a list of file names read through loadBinaryMovieLens.gfData: train on all folds but one,
     index the whole catalog, top-k for every user, topKMetrics against the held-out fold and against
     the training folds ("full_" keys), averaged over folds."""
+    # keyword names of the reference's signature (twoTower.py:125): rdZeroFilenames = the folds with randomly added
+    # zeros; bname = directory of its resource-usage logger (benchmarkLogger, out of scope here: accepted, unused)
+    if rdZeroDataSets is None and rdZeroFilenames is not None:
+        rdZeroDataSets = rdZeroFilenames
     folds = list(dataSets)
     if folds and isinstance(folds[0], str):                    # the reference's call form: file names (twoTower.py:125-139)
         from .loadBinaryMovieLens import gfData
