@@ -117,6 +117,56 @@ class RModel:
     def getPredictableUsers(self) -> list:
         return []
 
+    def getPredictDataFrame(self, customerId):
+        return None
+
+    def plot(self, history, metrics):
+        """RModel.py:100-113 draws loss / val_loss / the given metrics per epoch into trainResultPlotPath.  Plotting is
+        outside the hot path: the same series are written as JSON beside the checkpoint (and drawn when matplotlib is
+        importable).  history: object with .history (Keras) or a dict of lists; metrics: iterable of (key, label)."""
+        import json
+        series = getattr(history, "history", history) or {}
+        keep = {k: [float(x) for x in v] for k, v in series.items()
+                if k in ("loss", "val_loss") or k in {m for m, _ in (metrics.items() if isinstance(metrics, dict) else metrics)}}
+        path = os.path.join(os.path.dirname(self.checkpointPath), "trainResult.json")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "w") as f:
+            json.dump(keep, f)
+        try:
+            import matplotlib
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+        except Exception:
+            return path
+        fig, ax = plt.subplots(nrows=1, ncols=1)
+        for k, v in keep.items():
+            ax.plot(v, label=k)
+        plt.ylim([0, 1]); plt.xlabel('Epoch'); plt.ylabel('Error'); plt.legend()
+        fig.savefig(os.path.splitext(path)[0] + ".png")
+        plt.close(fig)
+        return path
+
+    def train(self, path, rowLimit, metricDict: dict = {}, distributedConfig=None):
+        """RModel.py:115-150, the generic flow a model class inherits: prepareToTrain -> fit (validation on the test
+        split; steps_per_epoch = len / epochs / workers when distributed) -> save -> plot -> evaluate on a 20 % split
+        of the training pairs -> {'result': 'completed', 'metrics': [...]}.  Under torchrun the data-parallel paths are
+        picked up by the model itself (no strategy scope is needed)."""
+        from . import synth
+        trainDataset, testDataset, trainSplit = self.prepareToTrain(distributedConfig, path, rowLimit)
+        if distributedConfig is None:
+            history = self.model.fit(trainDataset, validation_data=testDataset, epochs=self.epochs)
+        else:
+            steps = int(len(trainDataset) / self.epochs / self.getNumberOfWorkers(distributedConfig))
+            history = self.model.fit(trainDataset, validation_data=testDataset, epochs=self.epochs,
+                                     steps_per_epoch=max(steps, 1))
+        self.saveCheckPoint()
+        self.plot(history, metricDict)
+        print("Evaluating trained model...")
+        _, val = synth.train_test_split(trainSplit[0], trainSplit[1], 0.2, seed=self.splitSeed + 1)
+        valDataset = self.bootstrapDataset(val, shuffle=False)
+        evaluatedMetric = list(self.model.evaluate(valDataset, steps=self.validationSteps))
+        return {'result': 'completed', 'metrics': evaluatedMetric}
+
     def readyToTrain(self):
         return True
 

@@ -120,3 +120,14 @@ def test_chief_and_worker_save_locations_follow_the_reference(tmp_path):
     m.clearSlaveTempDir(strat("worker", 2))
     assert not os.path.exists(loc) and os.path.isdir(m.checkpointPath)
     assert m.getNumberOfWorkers({"cluster": {"worker": ["a:1", "b:2"]}}) == 2 and m.getNumberOfWorkers(None) == 1
+
+
+def test_rmodel_plot_writes_the_history_series(tmp_path):
+    """RModel.plot (RModel.py:100-113): loss / val_loss / the requested metrics per epoch, written beside the checkpoint."""
+    import json
+    from binrec_b200.RModel import RModel
+    m = RModel("NeuMFModel", workDir=str(tmp_path))
+    hist = {"loss": [0.5, 0.4], "val_loss": [0.6, 0.5], "mse": [0.3, 0.2], "unused": [1, 2]}
+    out = m.plot(hist, [("mse", "MSE")])
+    assert json.load(open(out)) == {"loss": [0.5, 0.4], "val_loss": [0.6, 0.5], "mse": [0.3, 0.2]}
+    assert m.getPredictDataFrame(3) is None and m.predictForUser(3) is None and m.getPredictableUsers() == []
