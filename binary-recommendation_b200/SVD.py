@@ -281,6 +281,40 @@ def digest(raw_users, raw_items=None, ratings=None, device=None):
     return user_ids, item_ids, uv.size - 1, iv.size - 1, float(out[0].item()), frame
 
 
+def convert_ids(chunk, chunk_number, user_ids, item_ids, next_user_id, next_item_id):
+    """SVD.py:126-137 for one chunk (a (raw users, raw items, ...) column tuple): raw ids not seen before get the next
+    dense id, in row order; the dicts are updated in place.  Host dict logic (digest does the same on the device for
+    whole files through pipeline.Vocabulary)."""
+    for raw in np.asarray(chunk[0]).tolist():
+        if raw not in user_ids:
+            user_ids[raw] = next_user_id
+            next_user_id += 1
+    for raw in np.asarray(chunk[1]).tolist():
+        if raw not in item_ids:
+            item_ids[raw] = next_item_id
+            next_item_id += 1
+    return next_user_id, next_item_id
+
+
+def calculate_average(chunk, chunk_number, total_so_far, average_so_far):
+    """SVD.py:139-161: the running mean rating after one more chunk (chunk[2] = its ratings)."""
+    r = np.asarray(chunk[2], dtype=np.float64)
+    chunk_total = len(r)
+    chunk_average = float(r.sum()) / chunk_total                  # ZeroDivisionError on an empty chunk, like the reference
+    total_so_far += chunk_total
+    average_so_far = ((chunk_total / total_so_far) * chunk_average) + \
+        (((total_so_far - chunk_total) / total_so_far) * average_so_far)
+    return total_so_far, average_so_far
+
+
+def get_idset(chunks):
+    """SVD.py:410-416: the set of (raw user, raw item) pairs of the given chunks."""
+    result = set()
+    for chunk in chunks:
+        result.update(zip(np.asarray(chunk[0]).tolist(), np.asarray(chunk[1]).tolist()))
+    return result
+
+
 def init_parameters(number_of_users, number_of_items, number_of_embeddings=NUMBER_OF_EMBEDDINGS, seed=None, device=None):
     """(user_matrix, item_matrix, user_bias_vector, item_bias_vector) as train_and_evaluate creates them
     (SVD.py:446-449): U(0, 1) / d matrices, zero biases, float64."""
@@ -492,12 +526,8 @@ def train_and_evaluate(dataset, user_ids, item_ids, uid_max, iid_max, global_bia
     if EVALUATE if evaluate is None else evaluate:
         result["mse"] = mean_square_error([test], P, Q, bu, bi, global_bias, user_ids, item_ids)
 
-        def idset(columns):                                       # get_idset (:410-416): sets of RAW (user, item) pairs
-            return set(zip(np.asarray(columns[0]).tolist(), np.asarray(columns[1]).tolist()))
-        test_idset = idset(dataset.get_test_set())
-        train_idset = set(test_idset)
-        for chunk in dataset:
-            train_idset |= idset(chunk)
+        test_idset = get_idset([dataset.get_test_set()])            # sets of RAW (user, item) pairs (:478-479)
+        train_idset = get_idset(list(dataset) + [dataset.get_test_set()])
         result.update(do_topk(P, Q, test_idset, train_idset, user_ids, item_ids))
     return result
 

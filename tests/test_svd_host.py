@@ -87,3 +87,24 @@ def test_fold_results_are_gathered_over_ranks_gloo():
     out = _spawn(_merge, world=2)
     want = {0: 0.0, 1: 11.0, 2: 20.0, 3: 31.0, 4: 40.0}                        # fold f ran on rank f % 2
     assert out[0] == want and out[1] == want
+
+
+def test_convert_ids_running_average_and_idset_follow_the_reference():
+    """convert_ids (:126-137), calculate_average (:139-161), get_idset (:410-416) against the golden digest of the
+    executed reference (tests/golden/svd_golden.npz): chunk by chunk they reproduce its vocabularies and global mean."""
+    import os
+    from binrec_b200 import SVD as S
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "svd_golden.npz"))
+    for name, n_chunks in (("tiny", 2), ("stars_reg", 3)):
+        g = lambda k: G[f"{name}/{k}"]
+        u, i, r = g("raw_users"), g("raw_items"), g("ratings")
+        cuts = np.linspace(0, len(u), n_chunks + 1).astype(int)
+        user_ids, item_ids, nu, ni, total, avg = {}, {}, 0, 0, 0, 0
+        chunks = [(u[a:b], i[a:b], r[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+        for c, chunk in enumerate(chunks):
+            nu, ni = S.convert_ids(chunk, c, user_ids, item_ids, nu, ni)
+            total, avg = S.calculate_average(chunk, c, total, avg)
+        assert list(user_ids) == g("user_vocab").tolist() and list(item_ids) == g("item_vocab").tolist()
+        assert (nu, ni) == (len(user_ids), len(item_ids)) and total == len(u)
+        np.testing.assert_allclose(avg, g("global_bias"), rtol=1e-13)
+        assert S.get_idset(chunks) == set(zip(u.tolist(), i.tolist()))
