@@ -211,6 +211,9 @@ class BPRNet:
         Batches are contiguous slices of the given row order; with shuffle=True the batch ORDER is
         permuted per epoch (seeded), which is what tf.data .batch().shuffle() does in the reference's
         other pipeline (NeuMFModel.py:117-121)."""
+        if 'user_input' in X:                                   # input names of the script version (bpr.py:215-217)
+            X = {'customerId_input': X['user_input'], 'pProduct_input': X['positive_item_input'],
+                 'nProduct_input': X.get('negative_item_input')}
         users = np.asarray(X['customerId_input']); pos = np.asarray(X['pProduct_input'])
         self.set_training_pairs(users, pos)
         fixed_neg = X.get('nProduct_input')
@@ -262,6 +265,32 @@ def bpr_predict(model, user_id, item_ids, user_layer='user_embedding', item_laye
     rows = H.gather_rows(model.get_layer_weights(item_layer), item_ids)
     uvec = model.get_layer_weights(user_layer)[int(user_id)]
     return (rows * uvec).sum(-1)
+
+
+def identity_loss(_, y_pred):
+    """bpr.py:136-138."""
+    return torch.mean(y_pred)
+
+
+def bpr_triplet_loss(X):
+    """bpr.py:141-157: 1 - sigmoid(<u, p> - <u, n>) per row; the script's argument order is [positive, negative, user]
+    (the class version BPRModel.bprTripletLoss takes [user, positive, negative])."""
+    positive_item_latent, negative_item_latent, user_latent = X
+    pos = (user_latent * positive_item_latent).sum(-1, keepdim=True)
+    neg = (user_latent * negative_item_latent).sum(-1, keepdim=True)
+    return 1.0 - torch.sigmoid(pos - neg)
+
+
+def out_shape(shapes):
+    """bpr.py:160-161."""
+    return shapes[0]
+
+
+def build_model(num_users: int, num_items: int, latent_dim: int, **kw):
+    """bpr.py:164-192: user table + ONE item table shared by the positive and the negative input, output = the
+    per-row triplet loss.  Returns the fused device model (BPRNet); its fit takes the script's input names
+    ('user_input', 'positive_item_input', 'negative_item_input', bpr.py:215-217) as well as the class version's."""
+    return BPRNet(num_users, num_items, latent_dim, **kw)
 
 
 def rating_triplets(user_ids, movie_ids, ratings, threshold=3):

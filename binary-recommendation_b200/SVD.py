@@ -16,6 +16,7 @@ what changes is underneath:
 No CPU fallback: every function raises BrkError without the CUDA library / a device.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -35,6 +36,15 @@ NUMBER_OF_EMBEDDINGS = 50
 TOPK_BATCH_SIZE = 5000
 EPOCH_ERROR_CALCULATION_FREQUENCY = 1
 EVALUATE = True
+VERBOSE = False
+NUMBER_OF_FILES = 5
+NUMBER_OF_CHUNKS_TO_EAT = 5
+USER_ID_COLUMN = "CUSTOMER_ID"
+ITEM_ID_COLUMN = "PRODUCT_ID"
+RATING_COLUMN = "RATING_TYPE"                 # None: ratings from the quintiles of the two columns below
+TRANSACTION_COUNT_COLUMN = "TRANSACTION_COUNT"
+QUANTITY_SUM_COLUMN = "QUANTITY_SUM"
+FILE_PATH = None
 TRANSACTION_COUNT_SCALE = 0.5
 QUANTITY_SUM_SCALE = 0.5
 TRANSACTION_COUNT_QUINTILES = (1, 2, 4)
@@ -172,7 +182,18 @@ class RatingChunks:
         return [c for c in range(self.number_of_chunks) if c != self.test_set_index]
 
     def __iter__(self):
-        return iter([self.chunks[c] for c in self.training_chunk_indices()])
+        """The dataset is its own iterator, as in the reference (:332-347): a new `for` restarts it."""
+        self.next_chunk = 0
+        return self
+
+    def __next__(self):
+        while self.next_chunk == self.test_set_index:
+            self.next_chunk += 1                                  # the held-out chunk is skipped
+        if self.next_chunk >= self.number_of_chunks:
+            raise StopIteration
+        chunk = self.chunks[self.next_chunk]
+        self.next_chunk += 1
+        return chunk
 
     # ---- device side (after digest) ------------------------------------------------------------------------
     def _need_digest(self):
@@ -200,6 +221,94 @@ class RatingChunks:
             self._frames[key] = Ratings(du[keep], di[keep], self.chunks[self.test_set_index][2][keep],
                                         num_users=self.num_users, num_items=self.num_items, device=self.device)
         return self._frames[key]
+
+
+def _read_chunk(path_or_file, columns):
+    """One rating file -> (raw users, raw items, ratings): `columns` is what the reference hands to read_csv as
+    usecols (SVD.py:503-506): [user, item, rating] or [user, item, transaction count, quantity sum]."""
+    import pandas as pd
+    df = pd.read_csv(path_or_file, usecols=list(columns))
+    u, i = df[columns[0]].to_numpy(), df[columns[1]].to_numpy()
+    if len(columns) == 3:
+        r = df[columns[2]].to_numpy(dtype=np.float64)
+    else:
+        r = get_rating(df[columns[2]].to_numpy(dtype=np.float64), df[columns[3]].to_numpy(dtype=np.float64)).cpu().numpy()
+    return u, i, r
+
+
+class movielens_cross_validation(RatingChunks):
+    """SVD.py:301-347 by name: one CSV, rows shuffled (`.sample(frac=1)` is unseeded there; shuffle_seed here, None =
+    file order), cut into five chunks; number_of_chunks_to_eat is the number of chunks the iterator walks."""
+
+    def __init__(self, file_path, number_of_chunks_to_eat, columns, shuffle_seed=0):
+        u, i, r = _read_chunk(file_path, columns)
+        split = RatingChunks.split(u, i, r, 5, shuffle_seed=shuffle_seed)
+        super().__init__(split.chunks)
+        self.file_path, self.number_of_chunks_to_eat, self.columns = file_path, number_of_chunks_to_eat, columns
+        self.test_set_index = self.number_of_chunks_to_eat - 1
+
+
+class grundfos_network_drive_files(RatingChunks):
+    """SVD.py:349-409 by name: number_of_files CSVs `file_path.format(1..n)` (read from the local file system; the
+    SMB credentials are accepted and ignored), one chunk per file; the test set keeps only rating == 1 rows when the
+    files carry a rating column (:389-392)."""
+
+    def __init__(self, file_path, number_of_files, credentials, columns):
+        chunks = [_read_chunk(file_path.format(n), columns) for n in range(1, number_of_files + 1)]
+        super().__init__(chunks, test_positive_only=(len(columns) == 3))
+        self.file_path, self.number_of_files, self.columns = file_path, number_of_files, columns
+        self.username, self.password = credentials if credentials else (None, None)
+        self.files = self.chunks
+
+
+def get_data(file_path=None, grundfos=True, credentials=(None, None)):
+    """SVD.py:499-514 without the prompts: the dataset object for FILE_PATH (or file_path) with the module's column
+    constants -- grundfos_network_drive_files over NUMBER_OF_FILES files, or movielens_cross_validation."""
+    path = file_path if file_path is not None else FILE_PATH
+    if path is None:
+        raise ValueError("get_data: set SVD.FILE_PATH or pass file_path (the reference hard-codes an SMB share)")
+    if RATING_COLUMN is not None:
+        columns = [USER_ID_COLUMN, ITEM_ID_COLUMN, RATING_COLUMN]
+    else:
+        columns = [USER_ID_COLUMN, ITEM_ID_COLUMN, TRANSACTION_COUNT_COLUMN, QUANTITY_SUM_COLUMN]
+    if grundfos:
+        return grundfos_network_drive_files(path, NUMBER_OF_FILES, credentials, columns)
+    return movielens_cross_validation(path, NUMBER_OF_CHUNKS_TO_EAT, columns)
+
+
+def get_config():
+    """SVD.py:79-103: the hyper-parameters of the run (the reference adds the git commit of its checkout)."""
+    import subprocess
+    try:
+        sha = subprocess.run(["git", "rev-parse", "HEAD"], capture_output=True, text=True, timeout=5,
+                             cwd=os.path.dirname(os.path.abspath(__file__))).stdout.strip() or None
+    except Exception:
+        sha = None
+    return {"epochs": EPOCHS, "learning_rate": LEARNING_RATE, "regularization": EMBEDDING_REGULARIZATION,
+            "number_of_embeddings": NUMBER_OF_EMBEDDINGS, "file_path": FILE_PATH, "git_commit_sha": sha,
+            "rating_column": RATING_COLUMN, "transaction_count_column": TRANSACTION_COUNT_COLUMN,
+            "transaction_count_scale": TRANSACTION_COUNT_SCALE, "transaction_count_quintiles": TRANSACTION_COUNT_QUINTILES,
+            "quantity_sum_column": QUANTITY_SUM_COLUMN, "quantity_sum_scale": QUANTITY_SUM_SCALE,
+            "quantity_sum_quintiles": QUANTITY_SUM_QUINTILES}
+
+
+_verbose_print_count = 0
+
+
+def print_verbose(message):
+    """SVD.py:64-71: progress line with a spinner, only when VERBOSE."""
+    global _verbose_print_count
+    if VERBOSE:
+        print("-\\|/-\\|/"[_verbose_print_count % 8] + "  " + message, end="\r")
+        _verbose_print_count += 1
+
+
+def clear_verbose_print():
+    """SVD.py:73-77."""
+    global _verbose_print_count
+    if VERBOSE:
+        _verbose_print_count = 0
+        print("\r" + " " * 80, end="\r")
 
 
 def _frame_of(dataset):
@@ -400,6 +509,23 @@ def _errors(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vecto
                                    P.shape[1], float(global_bias), N.ptr(out), N.ptr(_reduce_ws(dataset.device)),
                                    N.stream_ptr()), "brk_svd_errors")
     return out
+
+
+def mean_generic_error(generic, dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias,
+                       user_ids=None, item_ids=None):
+    """SVD.py:223-247: mean of generic(rating - prediction).  abs and squaring are recognised (by probing the callable)
+    and reduced on the device; any other callable is applied on the host to the device-computed errors."""
+    probe = (generic(-2.0), generic(0.5))
+    if probe == (2.0, 0.5):
+        return mean_absolute_error(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias)
+    if probe == (4.0, 0.25):
+        return mean_square_error(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias)
+    frame = _frame_of(dataset)
+    if len(frame) == 0:
+        raise ZeroDivisionError("mean error over an empty rating set")
+    pred = predict(frame.users, frame.items, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias)
+    err = (frame.ratings - pred).cpu().numpy()
+    return float(sum(generic(float(e)) for e in err) / len(err))
 
 
 def mean_square_error(dataset, user_matrix, item_matrix, user_bias_vector, item_bias_vector, global_bias,

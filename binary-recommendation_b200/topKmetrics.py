@@ -112,3 +112,29 @@ def getAverage(results):
             average[key] += result[key]
         average[key] /= len(results)
     return average
+
+
+# ---- the reference's module-private helpers (trainers/topKmetrics.py:45-72), kept for callers that reach for them ------
+var = {"__currentModel": None, "__currentUserId": None}
+
+
+def __predictForCurrentUser(i):
+    """(prediction, item) of the current model / user for one item (:45-49): one model.predict call per pair -- the
+    slow path the fused kernels replace; kept for models that only offer predict([users], [items])."""
+    return (var["__currentModel"].predict([np.array([var["__currentUserId"]]), np.array([i])]), i)
+
+
+def __topk(l, k):
+    """The k best (score, item) entries of l, best first; among equal scores the earlier entry wins -- what the
+    reference's insertion loop (:51-72) computes (held to its executed outputs: tests/golden/topk_golden.json).
+    Python's sort is stable, and stays so under reverse=True."""
+    return sorted(l, key=lambda x: x[0], reverse=True)[:k]
+
+
+def __insertSorted(l, val):
+    """Inserts val into the descending list l behind every entry that is not smaller (:63-72)."""
+    i = len(l)
+    while i > 0 and l[i - 1][0] < val[0]:
+        i -= 1
+    l.insert(i, val)
+

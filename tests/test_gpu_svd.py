@@ -54,6 +54,11 @@ def test_fit_predict_errors_match_the_reference_golden(S, name):
         np.testing.assert_allclose(S.mean_square_error(frame, P, Q, bu, bi, mu), g("mse")[e], rtol=RTOL)
         np.testing.assert_allclose(S.mean_absolute_error(frame, P, Q, bu, bi, mu), g("mae")[e], rtol=RTOL)
     S.check_fit(frame)
+    # mean_generic_error (SVD.py:223-247): abs / square are reduced on the device, any other callable on the host
+    np.testing.assert_allclose(S.mean_generic_error(abs, frame, P, Q, bu, bi, mu), g("mae")[-1], rtol=RTOL)
+    np.testing.assert_allclose(S.mean_generic_error(lambda x: x ** 2, frame, P, Q, bu, bi, mu), g("mse")[-1], rtol=RTOL)
+    cubes = (g("ratings") - S.predict(g("users"), g("items"), P, Q, bu, bi, mu).cpu().numpy())
+    np.testing.assert_allclose(S.mean_generic_error(lambda x: abs(x) ** 3, frame, P, Q, bu, bi, mu), np.mean(np.abs(cubes) ** 3), rtol=1e-12)
     for got, key in ((P, "P1"), (Q, "Q1"), (bu, "bu1"), (bi, "bi1")):
         np.testing.assert_allclose(got.cpu().numpy(), g(key), rtol=RTOL, atol=1e-14, err_msg=key)
     pred0 = S.predict(int(g("users")[0]), int(g("items")[0]), P, Q, bu, bi, mu)

@@ -70,3 +70,24 @@ def test_bf16_round_is_rne():
     x = np.array([1.0, 1.00390625, 1.01171875, -2.5, 3.1415927], dtype=np.float32)
     import torch
     assert np.array_equal(T.bf16_round(x), torch.from_numpy(x).bfloat16().float().numpy())
+
+
+def test_mirror_private_topk_helpers_match_the_executed_reference():
+    """binrec_b200.topKmetrics.__topk / __insertSorted (the reference's module-private helpers, kept by name) against
+    the golden outputs of the EXECUTED reference __topk (tests/golden/topk_golden.json) and its insertion rule."""
+    import json
+    import os
+    import random
+    from binrec_b200 import topKmetrics as T
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "topk_golden.json")))
+    topk, insert = getattr(T, "__topk"), getattr(T, "__insertSorted")
+    for c in g["topk"]:
+        got = topk([(s, i) for i, s in enumerate(c["scores"])], c["k"])
+        assert [list(x) for x in got] == c["out"]
+    random.seed(0)
+    for _ in range(500):                                            # insertion keeps the list descending and stable
+        l = sorted([(random.randint(0, 5), j) for j in range(random.randint(1, 8))], key=lambda x: x[0], reverse=True)
+        v = (random.randint(0, 6), "new")
+        a = list(l); insert(a, v)
+        assert [x[0] for x in a] == sorted([x[0] for x in a], reverse=True) and len(a) == len(l) + 1
+        assert all(x[0] >= v[0] for x in a[:a.index(v)]) and all(x[0] < v[0] for x in a[a.index(v) + 1:])

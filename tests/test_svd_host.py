@@ -108,3 +108,33 @@ def test_convert_ids_running_average_and_idset_follow_the_reference():
         assert (nu, ni) == (len(user_ids), len(item_ids)) and total == len(u)
         np.testing.assert_allclose(avg, g("global_bias"), rtol=1e-13)
         assert S.get_idset(chunks) == set(zip(u.tolist(), i.tolist()))
+
+
+def test_file_backed_dataset_classes_keep_the_reference_names(tmp_path):
+    """movielens_cross_validation / grundfos_network_drive_files / get_data / get_config (SVD.py:79-103, 301-409, 499-514)
+    over local CSV files: chunking, held-out chunk, rating == 1 filter of the grundfos test set."""
+    import pandas as pd
+    from binrec_b200 import SVD as S
+    n = 23
+    pd.DataFrame({"user_id": np.arange(n) + 100, "item_id": np.arange(n) + 500, "rating": (np.arange(n) % 3 == 0) * 1.0,
+                  "other": 0}).to_csv(tmp_path / "all.csv", index=False)
+    ml = S.movielens_cross_validation(str(tmp_path / "all.csv"), 5, ["user_id", "item_id", "rating"], shuffle_seed=None)
+    assert [len(c[0]) for c in ml.chunks] == [5, 5, 5, 4, 4] and ml.test_set_index == 4
+    assert np.array_equal(np.concatenate([c[0] for c in ml.chunks]), np.arange(n) + 100)      # file order without a seed
+    assert [len(c[0]) for c in ml] == [5, 5, 5, 4] and [len(c[0]) for c in ml] == [5, 5, 5, 4]  # a new `for` restarts it
+    for k in range(1, 4):
+        pd.DataFrame({"CUSTOMER_ID": np.arange(6) + 10 * k, "PRODUCT_ID": np.arange(6), "RATING_TYPE": [1, 0, 1, 0, 1, 1]}
+                     ).to_csv(tmp_path / f"part_{k}.csv", index=False)
+    old = S.NUMBER_OF_FILES
+    try:
+        S.NUMBER_OF_FILES = 3
+        gf = S.get_data(str(tmp_path / "part_{0}.csv"))
+    finally:
+        S.NUMBER_OF_FILES = old
+    assert isinstance(gf, S.grundfos_network_drive_files) and gf.number_of_chunks == 3 and gf.test_set_index == 2
+    u, i, r = gf.get_test_set()
+    assert (r == 1).all() and len(u) == 4                                                   # query("RATING_TYPE==1")
+    with pytest.raises(ValueError):
+        S.get_data()
+    cfg = S.get_config()
+    assert cfg["epochs"] == S.EPOCHS and cfg["learning_rate"] == S.LEARNING_RATE and "git_commit_sha" in cfg
