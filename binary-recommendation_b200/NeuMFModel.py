@@ -32,6 +32,8 @@ from .RModel import RModel
 
 TC_SPECS = {(64, 64, 32, 16), (32, 32, 16, 8)}
 BUILT_SPECS = {(32, 32, 16, 8), (64, 64, 32, 16), (16, 16, 8, 4), (8, 8, 4, 2), (10, 100, 50, 10)}
+# He et al. variant instances of the one-launch tensor-core kernel (csrc/neumf_fused.cu): (E, EMF, hidden)
+FUSED_VARIANTS = {(32, 8, (32, 16, 8))}
 
 
 class NeuMFNet:
@@ -41,15 +43,28 @@ class NeuMFNet:
 
     def __init__(self, numUser, numItem, numFactor, hidden=None, act="relu", loss="mse", learning_rate=1e-3,
                  dropout=0.2, seed=42, dropout_seed=11, sparse_adam="keras", device=None, head_order="h3_mf",
-                 tensor_cores=False):
+                 tensor_cores=False, mf_dim=None, mf_mode="dot", batch_norm=True):
+        """mf_dim / mf_mode / batch_norm select the He et al. variant BASELINE.json configs[0] names (not in the
+        reference tree): mf_mode="hadamard" feeds the element-wise product uMF[u] * iMF[i] (mf_dim wide) to the head
+        instead of the scalar Dot of NeuMFModel.py:79, batch_norm=False drops both BatchNormalization layers."""
         self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
         E = int(numFactor)
         h1, h2, h3 = hidden or (E, E // 2, E // 4)
-        if (E, h1, h2, h3) not in BUILT_SPECS:
+        EMF = E if mf_dim is None else int(mf_dim)
+        if mf_mode not in ("dot", "hadamard"):
+            raise ValueError(f"mf_mode {mf_mode!r}: 'dot' or 'hadamard'")
+        self.variant = EMF != E or mf_mode != "dot" or not batch_norm
+        if self.variant:
+            if (E, EMF, (h1, h2, h3)) not in FUSED_VARIANTS or mf_mode != "hadamard" or batch_norm or act != "relu":
+                raise ValueError(f"no kernel instance for the variant E={E}, mf_dim={EMF}, hidden={(h1, h2, h3)}, "
+                                 f"{mf_mode}, batch_norm={batch_norm}; built: {sorted(FUSED_VARIANTS)} hadamard / no BN / relu")
+            tensor_cores = True
+        elif (E, h1, h2, h3) not in BUILT_SPECS:
             raise ValueError(f"no kernel instance for E={E}, hidden={(h1, h2, h3)}; built: {sorted(BUILT_SPECS)}")
-        self.E, self.hidden = E, (h1, h2, h3)
+        self.E, self.hidden, self.EMF, self.mf_mode, self.batch_norm = E, (h1, h2, h3), EMF, mf_mode, bool(batch_norm)
+        head_mf = EMF if mf_mode == "hadamard" else 1
         # tensor_cores: the Dense products run on tcgen05 with TF32 operands (csrc/neumf_tc.cu); fp32 otherwise
-        if tensor_cores and (E, h1, h2, h3) not in TC_SPECS:
+        if tensor_cores and not self.variant and (E, h1, h2, h3) not in TC_SPECS:
             raise ValueError(f"no tensor-core instance for E={E}, hidden={(h1, h2, h3)}; built: {sorted(TC_SPECS)}")
         self.tensor_cores = bool(tensor_cores)
         self.numUser, self.numItem = int(numUser), int(numItem)
@@ -59,23 +74,24 @@ class NeuMFNet:
         lazy = sparse_adam == "lazy"
         dev = self.device
         rng = np.random.Generator(np.random.Philox(key=seed))
-        n_dense = int(N.lib().brk_neumf_dense_floats(E, h1, h2, h3))
+        n_dense = int(N.lib().brk_neumf_dense_floats_ex(E, h1, h2, h3, head_mf))
         npad = (n_dense + 3) // 4 * 4
         # one flat gradient arena (4 tables + dense block): data-parallel replicas all-reduce it once per step
-        sizes = [self.numUser * E, self.numItem * E, self.numUser * E, self.numItem * E, npad]
+        sizes = [self.numUser * E, self.numItem * E, self.numUser * EMF, self.numItem * EMF, npad]
         self.grad_arena = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
         views = list(torch.split(self.grad_arena, sizes))
 
-        def emb(rows):
-            return H.Table(torch.from_numpy(H.keras_embedding_init(rows, E, rng)).to(dev), touched=lazy, g=views.pop(0))
+        def emb(rows, width=E):
+            return H.Table(torch.from_numpy(H.keras_embedding_init(rows, width, rng)).to(dev), touched=lazy, g=views.pop(0))
 
         # draw order = oracle/neumf.py: uMLP, iMLP, uMF, iMF, then the Dense kernels (glorot-uniform)
-        self.uMLP, self.iMLP, self.uMF, self.iMF = emb(self.numUser), emb(self.numItem), emb(self.numUser), emb(self.numItem)
+        self.uMLP, self.iMLP = emb(self.numUser), emb(self.numItem)
+        self.uMF, self.iMF = emb(self.numUser, EMF), emb(self.numItem, EMF)
 
         if lazy and (E, h1, h2, h3) == (10, 100, 50, 10):
             raise ValueError("row-sparse Adam needs the touched-row marking of the tiled kernels (csrc/neumf2.cu); "
                              "the (10;100,50,10) script spec runs on the first-generation kernels")
-        parts = self.initial_dense_parts(E, (h1, h2, h3), rng)
+        parts = self.initial_dense_parts(E, (h1, h2, h3), rng, head_mf)
         flat = np.concatenate([parts[k].reshape(-1) for k in self.DENSE_ORDER])
         assert flat.size == n_dense
         self.dense = H.Table(torch.from_numpy(np.pad(flat, (0, npad - n_dense))).to(dev).view(1, -1), touched=False,
@@ -92,7 +108,7 @@ class NeuMFNet:
         self.history = {"loss": []}
 
     @staticmethod
-    def initial_dense_parts(E, hidden, rng):
+    def initial_dense_parts(E, hidden, rng, head_mf=1):
         """Keras defaults: Dense glorot-uniform kernels / zero biases, BN gamma 1 / beta 0 (draw order W1..W4)."""
         h1, h2, h3 = hidden
 
@@ -103,7 +119,7 @@ class NeuMFNet:
         return {"W1": glorot(2 * E, h1), "b1": np.zeros(h1, np.float32), "g1": np.ones(h1, np.float32),
                 "be1": np.zeros(h1, np.float32), "W2": glorot(h1, h2), "b2": np.zeros(h2, np.float32),
                 "g2": np.ones(h2, np.float32), "be2": np.zeros(h2, np.float32), "W3": glorot(h2, h3),
-                "b3": np.zeros(h3, np.float32), "W4": glorot(h3 + 1, 1), "b4": np.zeros(1, np.float32)}
+                "b3": np.zeros(h3, np.float32), "W4": glorot(h3 + head_mf, 1), "b4": np.zeros(1, np.float32)}
 
     @classmethod
     def initial_dense(cls, E, hidden, rng):
@@ -124,7 +140,8 @@ class NeuMFNet:
         return N.brk_neumf_model(self.uMLP.c_struct(), self.iMLP.c_struct(), self.uMF.c_struct(), self.iMF.c_struct(),
                                  self.dense.c_struct(), self.bn_moving.data_ptr(), self.E, h1, h2, h3,
                                  0 if self.act == "relu" else 1, 0 if self.loss == "mse" else 1,
-                                 1 if self.dropout > 0 else 0, 1 if self.tensor_cores else 0)
+                                 1 if self.dropout > 0 else 0, 1 if self.tensor_cores else 0,
+                                 self.EMF, 1 if self.mf_mode == "hadamard" else 0, 0 if self.batch_norm else 1, 0)
 
     def _workspace(self, batch):
         if batch > self._ws_batch:

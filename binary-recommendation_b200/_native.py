@@ -31,7 +31,9 @@ class brk_neumf_model(C.Structure):
     _fields_ = [("uMLP", brk_table), ("iMLP", brk_table), ("uMF", brk_table), ("iMF", brk_table),
                 ("dense", brk_table), ("bn_moving", C.c_void_p), ("E", C.c_int32), ("H1", C.c_int32),
                 ("H2", C.c_int32), ("H3", C.c_int32), ("act", C.c_int32), ("loss", C.c_int32),
-                ("dropout", C.c_int32), ("tensor_cores", C.c_int32)]
+                ("dropout", C.c_int32), ("tensor_cores", C.c_int32),
+                # ABI 2: He et al. variant (all zero = the reference class graph)
+                ("EMF", C.c_int32), ("mf_mode", C.c_int32), ("no_batch_norm", C.c_int32), ("_pad", C.c_int32)]
 
 
 class brk_neumf_workspace(C.Structure):
@@ -95,6 +97,7 @@ SIGNATURES = {
     "brk_adagrad_rows": (C.c_int, [_P, C.POINTER(brk_table), _I32, _F32, _F32, _P]),
     "brk_adagrad_dense": (C.c_int, [_P, C.POINTER(brk_table), _I32, _F32, _F32, _P]),
     "brk_neumf_dense_floats": (C.c_int64, [_I32, _I32, _I32, _I32]),
+    "brk_neumf_dense_floats_ex": (C.c_int64, [_I32, _I32, _I32, _I32, _I32]),
     "brk_neumf_acc_doubles": (C.c_int64, [_I32, _I32]),
     "brk_neumf_step": (C.c_int, [_P, C.POINTER(brk_neumf_model), _P, _P, _P, _I64, _I64, _I64, _I32, _U32, _U32,
                                  C.POINTER(brk_neumf_workspace), _P, _P, _P]),

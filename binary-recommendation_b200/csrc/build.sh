@@ -10,7 +10,10 @@ objs=""
 pids=""
 for f in *.cu; do
   o=build/${f%.cu}.o
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ common.cuh -nt "$o" ] || [ ../../include/brk_b200.h -nt "$o" ] || { [ -f tc.cuh ] && [ tc.cuh -nt "$o" ]; } || [ neumf_common.cuh -nt "$o" ]; then
+  stale=0
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ ../../include/brk_b200.h -nt "$o" ]; then stale=1; fi
+  for h in *.cuh; do [ "$h" -nt "$o" ] && stale=1; done
+  if [ $stale = 1 ]; then
     $NVCC $FLAGS ${BRK_PTXAS_V:+-Xptxas -v} -c "$f" -o "$o" &
     pids="$pids $!"
   fi

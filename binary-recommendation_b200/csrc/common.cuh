@@ -21,6 +21,9 @@ struct brk_ctx {
   // NeuMF tensor-core path: swizzled weight images, rebuilt every step (csrc/neumf_tc.cu)
   float*        neumf_img;
   size_t        neumf_img_floats;
+  // one-launch NeuMF step (csrc/neumf_fused.cu): per-tile slots of partial sums, summed after a grid barrier
+  float*        neumf_part;
+  size_t        neumf_part_floats;
   // fork/join inside one call: independent kernel chains of a step (the two towers of twotower.cu and, inside each,
   // the Dense-gradient products beside the embedding-gradient chain) run side by side on these streams
   cudaStream_t  fork_stream[3];

@@ -704,8 +704,20 @@ int brk_neumf_step_tc(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_sh
                       int32_t training, uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
                       float* out, float* loss_out, cudaStream_t st, int* rc_out);
 
+int brk_neumf_step_fused(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_shards* sh, const int32_t* u,
+                         const int32_t* i, const float* y, int64_t batch, int64_t global_batch, int64_t first_index,
+                         int32_t training, uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
+                         float* out, float* loss_out, cudaStream_t st, int* rc_out, int* handled);
+
+extern "C" int64_t brk_neumf_dense_floats_ex(int32_t E, int32_t H1, int32_t H2, int32_t H3, int32_t head_mf) {
+  return int64_t(2) * E * H1 + 3 * H1 + int64_t(H1) * H2 + 3 * H2 + int64_t(H2) * H3 + H3 + (H3 + head_mf) + 1;
+}
 extern "C" int64_t brk_neumf_dense_floats(int32_t E, int32_t H1, int32_t H2, int32_t H3) {
-  return int64_t(2) * E * H1 + 3 * H1 + int64_t(H1) * H2 + 3 * H2 + int64_t(H2) * H3 + H3 + (H3 + 1) + 1;
+  return brk_neumf_dense_floats_ex(E, H1, H2, H3, 1);
+}
+// the He et al. variant fields of brk_neumf_model (ABI 2): anything but the reference class graph
+static inline bool brk_neumf_is_variant(const brk_neumf_model* m) {
+  return (m->EMF > 0 && m->EMF != m->E) || m->mf_mode != 0 || m->no_batch_norm != 0;
 }
 extern "C" int64_t brk_neumf_acc_doubles(int32_t H1, int32_t H2) { return 4 * int64_t(H1) + 4 * int64_t(H2) + 1; }
 
@@ -721,8 +733,14 @@ extern "C" int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int3
   BRK_REQUIRE(!training || (m->uMLP.g && m->iMLP.g && m->uMF.g && m->iMF.g && m->dense.g), BRK_E_ARG,
               "brk_neumf_step: gradient accumulators missing");
   BRK_REQUIRE(ws->h1 && ws->h2 && ws->dy1 && ws->dy2 && ws->acc, BRK_E_ARG, "brk_neumf_step: workspace missing");
-  if (m->tensor_cores) {
-    int rc2 = 0;
+  if (m->tensor_cores || brk_neumf_is_variant(m)) {
+    int rc2 = 0, handled = 0;
+    brk_neumf_step_fused(ctx, m, nullptr, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch,
+                         ws, out, loss_out, (cudaStream_t)stream, &rc2, &handled);
+    if (handled) return rc2;
+    BRK_REQUIRE(!brk_neumf_is_variant(m), BRK_E_ARG,
+                "brk_neumf_step: no kernel for this variant (E=%d EMF=%d H=(%d,%d,%d) mf_mode=%d no_batch_norm=%d) at batch %lld",
+                m->E, m->EMF, m->H1, m->H2, m->H3, m->mf_mode, m->no_batch_norm, (long long)batch);
     if (brk_neumf_step_tc(ctx, m, nullptr, u, i, y, batch, global_batch, first_index, training, dropout_seed,
                           dropout_epoch, ws, out, loss_out, (cudaStream_t)stream, &rc2) == 0)
       return rc2;
@@ -783,7 +801,12 @@ extern "C" int brk_neumf_step_sharded(brk_ctx* ctx, const brk_neumf_model* m, co
                   BRK_E_ARG, "brk_neumf_step_sharded: shard %d of table %d missing or not 16-byte aligned", p, k);
   }
   int rc2 = 0;
+  BRK_REQUIRE(!brk_neumf_is_variant(m), BRK_E_ARG, "brk_neumf_step_sharded: the reference class graph only");
   if (m->tensor_cores) {
+    int handled = 0;
+    brk_neumf_step_fused(ctx, m, sh, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch, ws, out,
+                         loss_out, (cudaStream_t)stream, &rc2, &handled);
+    if (handled) return rc2;
     if (brk_neumf_step_tc(ctx, m, sh, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch, ws,
                           out, loss_out, (cudaStream_t)stream, &rc2) == 0)
       return rc2;

@@ -18,39 +18,9 @@
 // descriptor form against a host product; the NeuMF phases are built from the same helpers.
 #include "neumf_common.cuh"
 #include "tc.cuh"
+#include "tc_tiles.cuh"
 
 namespace ntc {
-
-constexpr int kThreads = 128;
-
-// byte offset of the 16-byte chunk c4 (= col / 4) of `row` in a tile of `rows` rows
-__device__ __forceinline__ uint32_t km_off16(int rows, int row, int c4) {     // K-major view, SWIZZLE_128B
-  const int kb = c4 >> 3, c = c4 & 7, r8 = row & 7;
-  return uint32_t(kb) * uint32_t(rows) * 128u + uint32_t(row >> 3) * 1024u + uint32_t(r8) * 128u + uint32_t((c ^ r8) << 4);
-}
-__device__ __forceinline__ uint32_t mn_off16(int rows, int row, int c4) {     // MN-major view, SWIZZLE_128B_BASE32B
-  const int kb = c4 >> 3, c32 = (c4 & 7) >> 1, half = c4 & 1, r4 = row & 3;
-  return uint32_t(kb) * uint32_t(rows) * 128u + uint32_t(row >> 2) * 512u + uint32_t(r4) * 128u + uint32_t((c32 ^ r4) << 5) +
-         uint32_t(half << 4);
-}
-
-// D[M x N] (+)= A * B over K, operands in the tile layout above.
-//   A_MN == 0: A tile has M rows, K columns.       A_MN == 1: A tile has K rows, M columns (read transposed).
-//   B_MN == 0: B tile has N rows, K columns.       B_MN == 1: B tile has K rows, N columns.
-// a_rows / b_rows: ROWS of the respective tiles.  Issued by ONE thread.
-template <int M, int N, int A_MN, int B_MN>
-__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_base, int a_rows, uint32_t b_base, int b_rows,
-                                           int K, bool accumulate_first) {
-  constexpr uint32_t idesc = tc::idesc_tf32_f32(M, N, A_MN, B_MN);
-  for (int ks = 0; ks < K / 8; ++ks) {
-    uint64_t ad, bd;
-    if (A_MN == 0) ad = tc::smem_desc_sw128_ex(a_base + uint32_t(ks >> 2) * uint32_t(a_rows) * 128u + uint32_t(ks & 3) * 32u, 16, 1024);
-    else           ad = tc::smem_desc_sw128_base32(a_base + uint32_t(ks) * 1024u, uint32_t(a_rows) * 128u, 512);
-    if (B_MN == 0) bd = tc::smem_desc_sw128_ex(b_base + uint32_t(ks >> 2) * uint32_t(b_rows) * 128u + uint32_t(ks & 3) * 32u, 16, 1024);
-    else           bd = tc::smem_desc_sw128_base32(b_base + uint32_t(ks) * 1024u, uint32_t(b_rows) * 128u, 512);
-    tc::mma_tf32_ss(d_tmem, ad, bd, idesc, (ks != 0 || accumulate_first) ? 1u : 0u);
-  }
-}
 
 // ---- self-test ---------------------------------------------------------------------------------------------
 // Stages Ag [a_rows x a_cols] and Bg [b_rows x b_cols] (row-major fp32, cols multiples of 32, rows multiples of
@@ -112,7 +82,6 @@ using v2::kBnEps; using v2::kBnMomentum; using v2::kDropScale;
 constexpr int TS = 128;          // samples per tile = TMEM lanes
 constexpr int NT = 256;          // threads per CTA: warp w reads TMEM lane quadrant (w & 3), column half (w >> 2)
 constexpr int SP = TS + 1;       // pitch of the feature-major fp32 staging tiles: odd -> conflict-free along s and along f
-__host__ __device__ constexpr int pad32(int x) { return (x + 31) & ~31; }
 
 // Weight images: the Dense kernels pre-arranged (once per step, prep_images) as the swizzled K-major B
 // operands the phases copy straight into shared memory.
@@ -229,12 +198,6 @@ __device__ __forceinline__ void tc_end(uint32_t tmem) {
 extern __shared__ __align__(1024) uint8_t ntc_smem_raw[];
 __device__ __forceinline__ uint8_t* smem_base() {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ntc_smem_raw) + 1023) & ~uintptr_t(1023));
-}
-
-// TMEM lane that holds row m of an M-row accumulator (M = 64 uses 16 lanes of each 32-lane quadrant)
-template <int M> __device__ __forceinline__ int row_of_lane(int lane128) {
-  if (M == 128) return lane128;
-  return (lane128 & 31) < 16 ? (lane128 >> 5) * 16 + (lane128 & 15) : -1;
 }
 
 // zero columns [H, pad32(H)) of a 128-row tile (both swizzles share the 16-byte granularity)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define BRK_ABI_VERSION 1
+#define BRK_ABI_VERSION 2
 
 #define BRK_E_ARG   (-1)   /* null pointer, negative size, unsupported dimension */
 #define BRK_E_ALIGN (-2)   /* pointer / row stride not aligned as required */
@@ -208,12 +208,21 @@ typedef struct brk_neumf_model {
   int32_t E, H1, H2, H3;
   int32_t act, loss, dropout;
   int32_t tensor_cores;   /* 0: fp32 on the CUDA cores; 1: MLP products on tcgen05 with TF32 operands, fp32 accumulation */
+  /* ABI 2 -- the He et al. NeuMF variant BASELINE.json configs[0] names ("GMF + MLP, 8-dim"): all zero = the
+   * reference class spec above.
+   *   EMF           width of the two MF tables (0 = E);
+   *   mf_mode       0: predMF = Dot(axes=1) scalar (NeuMFModel.py:79); 1: the Hadamard vector uMF[u]*iMF[i] [EMF] is
+   *                 concatenated to h3, so W4 has H3 + EMF rows (GMF of He et al.);
+   *   no_batch_norm 1: the two BatchNormalization layers are absent (gamma/beta slots stay in the block, unused). */
+  int32_t EMF, mf_mode, no_batch_norm, _pad;
 } brk_neumf_model;
 typedef struct brk_neumf_workspace {
   float *h1, *h2, *dy1, *dy2;
   double* acc;
 } brk_neumf_workspace;
 int64_t brk_neumf_dense_floats(int32_t E, int32_t H1, int32_t H2, int32_t H3);
+/* length of the dense block when the head takes head_mf MF inputs (1 for the scalar Dot, EMF for the Hadamard vector) */
+int64_t brk_neumf_dense_floats_ex(int32_t E, int32_t H1, int32_t H2, int32_t H3, int32_t head_mf);
 int64_t brk_neumf_acc_doubles(int32_t H1, int32_t H2);
 int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, const int32_t* i,
                    const float* y, int64_t batch, int64_t global_batch, int64_t first_index, int32_t training,

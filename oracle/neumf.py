@@ -1,7 +1,9 @@
 """ORACLE (test infrastructure, never the product path): NeuMF restated on the CPU with torch
 autograd (fp32 or fp64).  PARITY UNPINNED at the Keras boundary (the reference holds no golden
 vectors); the upstream Keras semantics restated here are listed in SURVEY.md
-section 8a row a1 and pinned by hand-computed cases in tests/test_oracle_neumf.py.
+section 8a row a1; the layer wiring is pinned by executing the reference's own compileModel against a
+torch-backed Keras shim (tests/golden/keras_shim.py -> tests/golden/wiring_golden.npz, tests/test_oracle_wiring.py)
+and the arithmetic is held to an independent NumPy restatement and fp64 finite differences (tests/test_oracle_nets.py).
 
 Follows /root/reference/src/models/NeuMFModel.py:53-100 (class spec) and
 /root/reference/trainers/NFC_plain.py:109-155 (script spec):
@@ -24,6 +26,13 @@ Dropout masks are not reproducible from TensorFlow; they are DEFINED here from P
 device can regenerate them (stream tags 0xD0 + layer): one Philox call yields 16 bytes, feature
 4*c16+.. keeps iff its byte >= 51, i.e. keep probability 205/256 (0.8008 instead of 0.8) with scale
 256/205.  rate == 0 disables dropout entirely.
+
+Variant (BASELINE.json configs[0], "NeuMF (GMF+MLP, 8-dim, layers 64-32-16-8)", He et al. 2017 -- NOT in the
+reference tree, defined here): mf_mode="hadamard" concatenates the element-wise product uMF[u]*iMF[i] [mf_dim]
+to h3 (W4 has H3 + mf_dim rows) instead of the scalar Dot; batch_norm=False drops both BatchNormalization layers.
+
+matmul: the Dense products go through `matmul(x, W)`; oracle/tf32.py supplies the TF32-operand form the tensor-core
+kernels compute (csrc/neumf_tc.cu, csrc/neumf_fused.cu).
 """
 import numpy as np
 import torch
@@ -54,22 +63,26 @@ def dropout_mask(n_features, sample_index, layer, seed, epoch):
 class NeuMFParams:
     """Plain container of torch tensors (requires_grad) in Keras layouts (Dense kernel [in, out])."""
 
-    def __init__(self, num_users, num_items, emb, hidden, seed=42, dtype=torch.float32):
+    def __init__(self, num_users, num_items, emb, hidden, seed=42, dtype=torch.float32, mf_dim=None, mf_mode="dot",
+                 batch_norm=True):
         rng = np.random.Generator(np.random.Philox(key=seed))
         h1, h2, h3 = hidden
         npdt = np.float64 if dtype == torch.float64 else np.float32
+        mf_dim = emb if mf_dim is None else int(mf_dim)
+        head_mf = mf_dim if mf_mode == "hadamard" else 1
+        self.mf_dim, self.mf_mode, self.batch_norm = mf_dim, mf_mode, bool(batch_norm)
 
-        def emb_init(rows):
-            return rng.uniform(-0.05, 0.05, size=(rows, emb)).astype(np.float32)
+        def emb_init(rows, width=emb):
+            return rng.uniform(-0.05, 0.05, size=(rows, width)).astype(np.float32)
 
         def glorot(i, o):
             lim = np.sqrt(6.0 / (i + o))
             return rng.uniform(-lim, lim, size=(i, o)).astype(np.float32)
 
-        arrs = dict(uMLP=emb_init(num_users), iMLP=emb_init(num_items), uMF=emb_init(num_users),
-                    iMF=emb_init(num_items), W1=glorot(2 * emb, h1), b1=np.zeros(h1, np.float32),
+        arrs = dict(uMLP=emb_init(num_users), iMLP=emb_init(num_items), uMF=emb_init(num_users, mf_dim),
+                    iMF=emb_init(num_items, mf_dim), W1=glorot(2 * emb, h1), b1=np.zeros(h1, np.float32),
                     W2=glorot(h1, h2), b2=np.zeros(h2, np.float32), W3=glorot(h2, h3), b3=np.zeros(h3, np.float32),
-                    W4=glorot(h3 + 1, 1), b4=np.zeros(1, np.float32),
+                    W4=glorot(h3 + head_mf, 1), b4=np.zeros(1, np.float32),
                     g1=np.ones(h1, np.float32), be1=np.zeros(h1, np.float32),
                     g2=np.ones(h2, np.float32), be2=np.zeros(h2, np.float32))
         self.t = {k: torch.tensor(v.astype(npdt), requires_grad=True) for k, v in arrs.items()}
@@ -96,23 +109,33 @@ def _bn(h, gamma, beta, training, mm, mv):
     return gamma * (h - mu) / torch.sqrt(var + BN_EPS) + beta, mu, var
 
 
-def forward(p, u, i, training=False, act="relu", masks=None):
+def forward(p, u, i, training=False, act="relu", masks=None, matmul=torch.matmul):
     """Returns (out [B], aux dict).  masks: None or (m0 [B,2E], m1 [B,H1], m2 [B,H2]) float masks."""
     t = p.t
     u = torch.as_tensor(np.asarray(u), dtype=torch.int64); i = torch.as_tensor(np.asarray(i), dtype=torch.int64)
+    bn_on = getattr(p, "batch_norm", True)
+
+    def bn(h, g, be, mm, mv):
+        if not bn_on:
+            return h, mm, mv
+        return _bn(h, g, be, training, mm, mv)
+
     x0 = torch.cat([t["uMLP"][u], t["iMLP"][i]], dim=1)
     if masks is not None:
         x0 = x0 * masks[0]
-    h1 = _act(x0 @ t["W1"] + t["b1"], act)
-    y1, mu1, var1 = _bn(h1, t["g1"], t["be1"], training, p.mm1, p.mv1)
+    h1 = _act(matmul(x0, t["W1"]) + t["b1"], act)
+    y1, mu1, var1 = bn(h1, t["g1"], t["be1"], p.mm1, p.mv1)
     if masks is not None:
         y1 = y1 * masks[1]
-    h2 = _act(y1 @ t["W2"] + t["b2"], act)
-    y2, mu2, var2 = _bn(h2, t["g2"], t["be2"], training, p.mm2, p.mv2)
+    h2 = _act(matmul(y1, t["W2"]) + t["b2"], act)
+    y2, mu2, var2 = bn(h2, t["g2"], t["be2"], p.mm2, p.mv2)
     if masks is not None:
         y2 = y2 * masks[2]
-    h3 = _act(y2 @ t["W3"] + t["b3"], act)
-    mf = (t["uMF"][u] * t["iMF"][i]).sum(1, keepdim=True)
+    h3 = _act(matmul(y2, t["W3"]) + t["b3"], act)
+    if getattr(p, "mf_mode", "dot") == "hadamard":
+        mf = t["uMF"][u] * t["iMF"][i]                       # GMF vector of He et al.
+    else:
+        mf = (t["uMF"][u] * t["iMF"][i]).sum(1, keepdim=True)
     logit = (torch.cat([h3, mf], dim=1) @ t["W4"] + t["b4"]).squeeze(1)
     return torch.sigmoid(logit), dict(logit=logit, mu1=mu1, var1=var1, mu2=mu2, var2=var2)
 
@@ -134,9 +157,11 @@ class NeuMFOracle:
     """Training-loop state with Keras Adam (dense-equivalent on the embedding tables)."""
 
     def __init__(self, num_users, num_items, emb=32, hidden=None, seed=42, act="relu", loss="mse", lr=1e-3,
-                 dropout=0.0, dropout_seed=11, dtype=torch.float32, lazy_adam=False):
+                 dropout=0.0, dropout_seed=11, dtype=torch.float32, lazy_adam=False, mf_dim=None, mf_mode="dot",
+                 batch_norm=True, matmul=torch.matmul):
         hidden = hidden or (emb, emb // 2, emb // 4)
-        self.p = NeuMFParams(num_users, num_items, emb, hidden, seed, dtype)
+        self.p = NeuMFParams(num_users, num_items, emb, hidden, seed, dtype, mf_dim, mf_mode, batch_norm)
+        self.matmul = matmul
         self.act, self.loss, self.lr, self.dropout, self.dropout_seed = act, loss, lr, dropout, dropout_seed
         self.dtype = dtype
         self.m = {k: torch.zeros_like(v) for k, v in self.p.t.items()}
@@ -156,7 +181,8 @@ class NeuMFOracle:
         for v in self.p.t.values():
             v.grad = None
         y = torch.as_tensor(np.asarray(y), dtype=self.dtype)
-        out, aux = forward(self.p, u, i, training=True, act=self.act, masks=self._masks(first_index, len(y), epoch))
+        out, aux = forward(self.p, u, i, training=True, act=self.act, masks=self._masks(first_index, len(y), epoch),
+                           matmul=self.matmul)
         loss = loss_fn(out, aux["logit"], y, self.loss)
         loss.backward()
         return loss.detach(), out.detach(), aux
@@ -166,10 +192,11 @@ class NeuMFOracle:
         B = len(np.asarray(y))
         with torch.no_grad():
             # Keras BN moving statistics: moving = moving*momentum + batch*(1-momentum)  (biased variance)
-            self.p.mm1.mul_(BN_MOMENTUM).add_(aux["mu1"].detach() * (1 - BN_MOMENTUM))
-            self.p.mv1.mul_(BN_MOMENTUM).add_(aux["var1"].detach() * (1 - BN_MOMENTUM))
-            self.p.mm2.mul_(BN_MOMENTUM).add_(aux["mu2"].detach() * (1 - BN_MOMENTUM))
-            self.p.mv2.mul_(BN_MOMENTUM).add_(aux["var2"].detach() * (1 - BN_MOMENTUM))
+            if self.p.batch_norm:
+                self.p.mm1.mul_(BN_MOMENTUM).add_(aux["mu1"].detach() * (1 - BN_MOMENTUM))
+                self.p.mv1.mul_(BN_MOMENTUM).add_(aux["var1"].detach() * (1 - BN_MOMENTUM))
+                self.p.mm2.mul_(BN_MOMENTUM).add_(aux["mu2"].detach() * (1 - BN_MOMENTUM))
+                self.p.mv2.mul_(BN_MOMENTUM).add_(aux["var2"].detach() * (1 - BN_MOMENTUM))
             self.t += 1
             b1, b2, eps = 0.9, 0.999, 1e-7
             alpha = self.lr * np.sqrt(1 - b2 ** self.t) / (1 - b1 ** self.t)
@@ -190,4 +217,4 @@ class NeuMFOracle:
 
     def predict(self, u, i):
         with torch.no_grad():
-            return forward(self.p, u, i, training=False, act=self.act)[0].numpy()
+            return forward(self.p, u, i, training=False, act=self.act, matmul=self.matmul)[0].numpy()

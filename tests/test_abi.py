@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_binding_covers_header():
     from binrec_b200 import _native
     assert sorted(_native.SIGNATURES) == _declared_symbols()
-    assert _native.lib().brk_abi_version() == 1
+    assert _native.lib().brk_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -48,66 +48,181 @@ def test_tf32_descriptor_forms(dev, M, N, mode):
         assert lanes == list(range(64)) or lanes == [32 * (m // 16) + m % 16 for m in range(64)]
 
 
-# ---- NeuMF on the tensor cores vs the fp32 path ----------------------------------------------------------------
-# Stated TF32 tolerance: operands carry 10 mantissa bits (relative 2^-11 per factor), accumulation is fp32.
-#   predictions / loss / BatchNorm statistics: rtol 2e-3;
-#   gradients: judged per tensor against its largest entry and norm-wise, because the BatchNorm backward
-#   subtracts batch means (cancellation) and, with ReLU, a pre-activation within TF32 rounding of zero flips
-#   its gate and changes that sample's whole contribution.  Measured on these cases (profiles/neumf_tc_debug.py):
-#   sigmoid: max error <= 3.6 % of max|g|, Frobenius <= 3 %;  ReLU: max error <= 15 %, Frobenius <= 5.6 %.
-#   Bounds asserted: sigmoid 6 % / 5 %, ReLU 25 % / 10 %.
-def _neumf_pair(dev, E, dropout, act="relu", loss="mse", seed=42):
-    from binrec_b200.NeuMFModel import NeuMFNet
-    U, I = 300, 200
-    a = NeuMFNet(U, I, E, act=act, loss=loss, dropout=dropout, seed=seed, device=dev, tensor_cores=False)
-    b = NeuMFNet(U, I, E, act=act, loss=loss, dropout=dropout, seed=seed, device=dev, tensor_cores=True)
-    return a, b, U, I
+# ---- which TF32 does the tensor core compute? ----------------------------------------------------------------------
+TF32_MODE = "trunc"      # oracle/tf32.py: the 13 dropped mantissa bits are truncated (determined by the test below)
 
 
-def _check_grad(g1, g0, smooth, name):
+def test_tf32_operand_rounding_is_truncation(dev):
+    """A has full fp32 mantissas, B is exactly representable: the product equals trunc(A) @ B and differs from
+    round-to-nearest(A) @ B -- this pins the operand rule oracle/tf32.py restates."""
+    from oracle import tf32
+    rng = np.random.default_rng(11)
+    M, N, K = 128, 64, 128
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = (rng.integers(-8, 9, size=(N, K)) / 8.0).astype(np.float32)
+    got = _run(dev, M, N, K, 0, A, B).astype(np.float64)
+    ref_t = tf32.trunc_np(A).astype(np.float64) @ B.astype(np.float64).T
+    ref_r = tf32.rn_np(A).astype(np.float64) @ B.astype(np.float64).T
+    err_t, err_r = np.abs(got - ref_t).max(), np.abs(got - ref_r).max()
+    print("TF32 operand rule: max |err| vs truncation", err_t, "vs round-to-nearest", err_r)
+    assert (err_t < 2e-5) != (err_r < 2e-5), (err_t, err_r)
+    assert (err_t < err_r) == (TF32_MODE == "trunc"), (err_t, err_r)
+
+
+# ---- NeuMF on the tensor cores vs the TF32-operand ORACLE ----------------------------------------------------------
+# oracle/neumf.py with matmul = oracle/tf32.py: every Dense product (forward, input gradient, weight gradient) reads
+# its operands with 10 mantissa bits and accumulates in fp32 -- the arithmetic of tcgen05.mma.kind::tf32.  Against
+# that oracle the device is held to (SURVEY.md section 8c / VERDICT r1 item 2a):
+#   predictions rtol 2e-3 / atol 1e-5, loss rtol 2e-3, BatchNorm moving statistics rtol 2e-3;
+#   gradients per tensor: Frobenius error <= 2e-2, and max |error| <= 1e-2 of the tensor's largest entry on all rows
+#   but a stated budget of max(1, 1 %) of them (hard cap 0.1 everywhere).  The budget exists because ReLU is
+#   discontinuous and TF32 truncation turns a 1-ulp difference of an activation (summation order) into a 2^-10
+#   step of the operand: a pre-activation that lands within that noise of zero flips its gate in one of the two
+#   implementations and changes that one sample's contribution to the rows it touches (measured: 0-2 rows).
+# The measured errors are printed; typical: predictions ~1e-6, gradients ~1e-4 of the largest entry.
+# path: "fused" = the one-launch cooperative kernel (csrc/neumf_fused.cu), "five" = the five-kernel path
+# (csrc/neumf_tc.cu, BRK_NEUMF_NO_FUSED), which is what runs when a batch does not fit on chip.
+def _tf32_matmul():
+    from oracle import tf32
+    return tf32.matmul if TF32_MODE == "trunc" else tf32.matmul_rn
+
+
+def _grad_err(g1, g0):
+    """(max |err| / max |g|, Frobenius error, rows whose max |err| exceeds 1e-2 max |g|, rows)"""
     scale = max(float(np.abs(g0).max()), 1e-20)
-    mx = float(np.abs(g1 - g0).max()) / scale
-    rel = float(np.linalg.norm((g1 - g0).ravel()) / max(np.linalg.norm(g0.ravel()), 1e-20))
-    assert mx <= (0.06 if smooth else 0.25), (name, mx)
-    assert rel <= (0.05 if smooth else 0.10), (name, rel)
+    e = np.abs(g1 - g0).reshape(g0.shape[0], -1) if g0.ndim > 1 else np.abs(g1 - g0).reshape(1, -1)
+    bad = int((e.max(axis=1) > 1e-2 * scale).sum())
+    return (float(e.max()) / scale, float(np.linalg.norm((g1 - g0).ravel()) / max(np.linalg.norm(g0.ravel()), 1e-20)),
+            bad, e.shape[0])
 
 
+def _path(monkeypatch, path):
+    if path == "five":
+        monkeypatch.setenv("BRK_NEUMF_NO_FUSED", "1")
+    else:
+        monkeypatch.delenv("BRK_NEUMF_NO_FUSED", raising=False)
+
+
+def _check_step_against_oracle(dev, net, orc, u, i, y, first, epoch, tag):
+    lref, oref, aux = orc.loss_and_grads(u, i, y, first_index=first, epoch=epoch)
+    ud, idd, yd = (torch.from_numpy(x).to(dev) for x in (u, i, y))
+    lgot, ogot = net.forward_backward(ud, idd, yd, first_index=first, epoch=epoch)
+    np.testing.assert_allclose(ogot.cpu().numpy(), oref.numpy(), rtol=2e-3, atol=1e-5)
+    np.testing.assert_allclose(lgot.item(), float(lref), rtol=2e-3)
+    worst = (0.0, 0.0, "", 0)
+    names = ["uMLP", "iMLP", "uMF", "iMF"] + list(net.DENSE_ORDER)
+    for name in names:
+        g0 = orc.p.t[name].grad
+        g0 = np.zeros(tuple(orc.p.t[name].shape), np.float32) if g0 is None else g0.numpy()
+        g1 = (getattr(net, name).g if name in ("uMLP", "iMLP", "uMF", "iMF") else net.param(name, grad=True)).cpu().numpy()
+        g1 = g1.reshape(g0.shape)
+        if not np.abs(g0).max() > 0:                      # unused BN slots of the variant: gradient exactly zero
+            assert not np.abs(g1).max() > 0, name
+            continue
+        mx, rel, bad, rows = _grad_err(g1, g0)
+        worst = max(worst, (mx, rel, name, bad))
+        assert rel <= 2e-2 and mx <= 0.1 and bad <= max(1, rows // 100), (tag, name, mx, rel, bad, rows)
+    print(f"{tag}: pred max|err| {np.abs(ogot.cpu().numpy() - oref.numpy()).max():.2e}, worst gradient {worst}")
+
+
+@pytest.mark.parametrize("path", ["fused", "five"])
 @pytest.mark.parametrize("E", [64, 32])
-@pytest.mark.parametrize("act,loss", [("sigmoid", "bce"), ("relu", "mse")])
 @pytest.mark.parametrize("dropout", [0.0, 0.2])
 @pytest.mark.parametrize("B", [1000, 128, 77])
-def test_neumf_tensor_core_step_matches_fp32_path(dev, E, act, loss, dropout, B):
-    ref, net, U, I = _neumf_pair(dev, E, dropout, act, loss)
+def test_neumf_tensor_core_step_matches_tf32_oracle(dev, monkeypatch, path, E, dropout, B):
+    from binrec_b200.NeuMFModel import NeuMFNet
+    from oracle import neumf as ON
+    _path(monkeypatch, path)
+    U, I = 300, 200
+    net = NeuMFNet(U, I, E, dropout=dropout, seed=42, dropout_seed=11, device=dev, tensor_cores=True)
+    orc = ON.NeuMFOracle(U, I, emb=E, seed=42, dropout=dropout, dropout_seed=11, matmul=_tf32_matmul())
     rng = np.random.default_rng(E + B)
     u = (U * rng.random(B) ** 2).astype(np.int32); i = (I * rng.random(B) ** 2).astype(np.int32)
     y = (rng.random(B) < 0.25).astype(np.float32)
-    ud, idd, yd = (torch.from_numpy(x).to(dev) for x in (u, i, y))
-    l0, o0 = ref.forward_backward(ud, idd, yd, first_index=4096, epoch=3)
-    l1, o1 = net.forward_backward(ud, idd, yd, first_index=4096, epoch=3)
-    np.testing.assert_allclose(o1.cpu().numpy(), o0.cpu().numpy(), rtol=2e-3, atol=2e-4)
-    np.testing.assert_allclose(l1.item(), l0.item(), rtol=2e-3)
-    smooth = act == "sigmoid"
-    for name in ("uMLP", "iMLP", "uMF", "iMF"):
-        _check_grad(getattr(net, name).g.cpu().numpy(), getattr(ref, name).g.cpu().numpy(), smooth, name)
-    for name in net.DENSE_ORDER:
-        _check_grad(net.param(name, grad=True).cpu().numpy(), ref.param(name, grad=True).cpu().numpy(), smooth, name)
-    np.testing.assert_allclose(net.bn_moving.cpu().numpy(), ref.bn_moving.cpu().numpy(), rtol=2e-3, atol=1e-5)
+    _check_step_against_oracle(dev, net, orc, u, i, y, 4096, 3, f"{path} E={E} B={B} dropout={dropout}")
+    assert not net._bufs["acc"].any().item()              # accumulators left zero for the next step
 
 
-def test_neumf_tensor_core_training_tracks_fp32_and_eval(dev):
-    ref, net, U, I = _neumf_pair(dev, 64, 0.2)
+@pytest.mark.parametrize("dropout", [0.0, 0.2])
+def test_neumf_five_kernel_sigmoid_bce_matches_tf32_oracle(dev, dropout):
+    """The sigmoid / BCE graph (trainers/NFC_plain.py activations) exists on the five-kernel tensor-core path only."""
+    from binrec_b200.NeuMFModel import NeuMFNet
+    from oracle import neumf as ON
+    U, I, B, E = 300, 200, 1000, 32
+    net = NeuMFNet(U, I, E, act="sigmoid", loss="bce", dropout=dropout, device=dev, tensor_cores=True)
+    orc = ON.NeuMFOracle(U, I, emb=E, act="sigmoid", loss="bce", dropout=dropout, matmul=_tf32_matmul())
+    rng = np.random.default_rng(1)
+    u = (U * rng.random(B) ** 2).astype(np.int32); i = (I * rng.random(B) ** 2).astype(np.int32)
+    y = (rng.random(B) < 0.25).astype(np.float32)
+    _check_step_against_oracle(dev, net, orc, u, i, y, 0, 1, f"five sigmoid/bce dropout={dropout}")
+
+
+@pytest.mark.parametrize("B", [1000, 128, 16384])
+def test_neumf_he_variant_matches_oracles(dev, B):
+    """BASELINE.json configs[0]: GMF (8-dim Hadamard vector) + MLP 64-32-16-8, no BatchNorm, no dropout."""
+    from binrec_b200.NeuMFModel import NeuMFNet
+    from oracle import neumf as ON
+    U, I = 6040, 3706
+    kw = dict(mf_dim=8, mf_mode="hadamard", batch_norm=False)
+    net = NeuMFNet(U, I, 32, dropout=0.0, device=dev, **kw)
+    orc = ON.NeuMFOracle(U, I, emb=32, dropout=0.0, matmul=_tf32_matmul(), **kw)
+    o32 = ON.NeuMFOracle(U, I, emb=32, dropout=0.0, **kw)
+    assert np.array_equal(net.param("W4").cpu().numpy().reshape(-1), orc.p.t["W4"].detach().numpy().reshape(-1))
+    assert net.param("W4").numel() == 8 + 8
+    rng = np.random.default_rng(B)
+    u = (U * rng.random(B) ** 2).astype(np.int32); i = (I * rng.random(B) ** 2).astype(np.int32)
+    y = (rng.random(B) < 0.2).astype(np.float32)
+    _check_step_against_oracle(dev, net, orc, u, i, y, 0, 0, f"He variant B={B}")
+    l32, o32p, _ = o32.loss_and_grads(u, i, y)                # and the plain fp32 oracle, TF32 tolerance
+    out, _ = net.predict_on_batch(torch.from_numpy(u).to(dev), torch.from_numpy(i).to(dev))
+    np.testing.assert_allclose(out.cpu().numpy(), o32p.numpy(), rtol=2e-3, atol=1e-4)
+
+
+def test_neumf_baseline_shape_three_steps_match_tf32_oracle(dev):
+    """BASELINE.json configs[0] shape: 6040 x 3706, numFactor 32, batch 16 384, three Keras-Adam steps with dropout."""
+    from binrec_b200.NeuMFModel import NeuMFNet
+    from oracle import neumf as ON
+    U, I, B, E = 6040, 3706, 16384, 32
+    net = NeuMFNet(U, I, E, dropout=0.2, device=dev, tensor_cores=True)
+    orc = ON.NeuMFOracle(U, I, emb=E, dropout=0.2, matmul=_tf32_matmul())
+    o64 = ON.NeuMFOracle(U, I, emb=E, dropout=0.2, dtype=torch.float64)
+    rng = np.random.default_rng(2)
+    for step in range(3):
+        u = (U * rng.random(B) ** 1.5).astype(np.int32); i = (I * rng.random(B) ** 2).astype(np.int32)
+        y = (rng.random(B) < 0.2).astype(np.float32)
+        lref, _ = orc.step(u, i, y, first_index=step * B, epoch=0)
+        l64, _ = o64.step(u, i, y, first_index=step * B, epoch=0)
+        lgot, _ = net.train_on_batch(*(torch.from_numpy(x).to(dev) for x in (u, i, y)), first_index=step * B, epoch=0)
+        np.testing.assert_allclose(lgot.item(), lref, rtol=2e-3)
+        np.testing.assert_allclose(lgot.item(), l64, rtol=2e-3)
+    ref, ref64 = orc.p.numpy(), o64.p.numpy()
+    for name, tab in zip(("uMLP", "iMLP", "uMF", "iMF"), net.tables()):
+        w = tab.w.cpu().numpy()
+        # three Adam steps move a weight by at most 3 lr = 3e-3; the device must stay as close to the fp64 run as
+        # the TF32 oracle does (x3 + 1e-4: Adam normalises the step, so gradient noise near |g| ~ eps is amplified)
+        err_dev, err_orc = np.abs(w - ref64[name]).max(), np.abs(ref[name] - ref64[name]).max()
+        print(name, "max |w - fp64|: device", err_dev, "tf32 oracle", err_orc)
+        assert err_dev <= 3 * err_orc + 1e-4, (name, err_dev, err_orc)
+    np.testing.assert_allclose(net.bn_moving.cpu().numpy(),
+                               np.concatenate([orc.p.mm1.numpy(), orc.p.mv1.numpy(), orc.p.mm2.numpy(), orc.p.mv2.numpy()]),
+                               rtol=2e-3, atol=1e-5)
+
+
+def test_neumf_tensor_core_eval_uses_moving_statistics(dev):
+    from binrec_b200.NeuMFModel import NeuMFNet
+    from oracle import neumf as ON
+    U, I, B = 300, 200, 2048
+    net = NeuMFNet(U, I, 64, dropout=0.2, device=dev, tensor_cores=True)
+    orc = ON.NeuMFOracle(U, I, emb=64, dropout=0.2, matmul=_tf32_matmul())
     rng = np.random.default_rng(9)
-    B = 2048
     for step in range(5):
         u = (U * rng.random(B) ** 2).astype(np.int32); i = (I * rng.random(B) ** 2).astype(np.int32)
         y = (rng.random(B) < 0.25).astype(np.float32)
-        ud, idd, yd = (torch.from_numpy(x).to(dev) for x in (u, i, y))
-        l0, _ = ref.train_on_batch(ud, idd, yd, first_index=step * B, epoch=0)
-        l1, _ = net.train_on_batch(ud, idd, yd, first_index=step * B, epoch=0)
-        np.testing.assert_allclose(l1.item(), l0.item(), rtol=5e-3)
-    p0, _ = ref.predict_on_batch(ud, idd, yd)
-    p1, _ = net.predict_on_batch(ud, idd, yd)
-    np.testing.assert_allclose(p1.cpu().numpy(), p0.cpu().numpy(), rtol=1e-2, atol=1e-3)
+        lref, _ = orc.step(u, i, y, first_index=step * B, epoch=0)
+        lgot, _ = net.train_on_batch(*(torch.from_numpy(x).to(dev) for x in (u, i, y)), first_index=step * B, epoch=0)
+        np.testing.assert_allclose(lgot.item(), lref, rtol=2e-3)
+    p1, _ = net.predict_on_batch(torch.from_numpy(u).to(dev), torch.from_numpy(i).to(dev), torch.from_numpy(y).to(dev))
+    np.testing.assert_allclose(p1.cpu().numpy(), orc.predict(u, i), rtol=5e-3, atol=1e-4)
 
 
 # ---- general TF32 product (csrc/gemm_tc.cu) and the two-tower step on it -------------------------------------------
