@@ -54,13 +54,11 @@ class NeuMFNet:
         if mf_mode not in ("dot", "hadamard"):
             raise ValueError(f"mf_mode {mf_mode!r}: 'dot' or 'hadamard'")
         self.variant = EMF != E or mf_mode != "dot" or not batch_norm
-        if self.variant:
-            if (E, EMF, (h1, h2, h3)) not in FUSED_VARIANTS or mf_mode != "hadamard" or batch_norm or act != "relu":
-                raise ValueError(f"no kernel instance for the variant E={E}, mf_dim={EMF}, hidden={(h1, h2, h3)}, "
-                                 f"{mf_mode}, batch_norm={batch_norm}; built: {sorted(FUSED_VARIANTS)} hadamard / no BN / relu")
-            tensor_cores = True
-        elif (E, h1, h2, h3) not in BUILT_SPECS:
-            raise ValueError(f"no kernel instance for E={E}, hidden={(h1, h2, h3)}; built: {sorted(BUILT_SPECS)}")
+        if min(E, EMF, h1, h2, h3) < 1:
+            raise ValueError(f"numFactor {numFactor}: every layer needs at least one unit (hidden={(h1, h2, h3)})")
+        if self.variant and (E, EMF, (h1, h2, h3)) in FUSED_VARIANTS and mf_mode == "hadamard" and not batch_norm and act == "relu":
+            tensor_cores = True                              # the built instance of the variant is the one-launch kernel
+        # every other width runs on the any-width kernels (csrc/neumf_generic.cu): numFactor is free (RModel.py:35)
         self.E, self.hidden, self.EMF, self.mf_mode, self.batch_norm = E, (h1, h2, h3), EMF, mf_mode, bool(batch_norm)
         head_mf = EMF if mf_mode == "hadamard" else 1
         # tensor_cores: the Dense products run on tcgen05 with TF32 operands (csrc/neumf_tc.cu); fp32 otherwise
@@ -88,7 +86,7 @@ class NeuMFNet:
         self.uMLP, self.iMLP = emb(self.numUser), emb(self.numItem)
         self.uMF, self.iMF = emb(self.numUser, EMF), emb(self.numItem, EMF)
 
-        if lazy and (E, h1, h2, h3) == (10, 100, 50, 10):
+        if lazy and (E, h1, h2, h3) == (10, 100, 50, 10) and not self.variant:
             raise ValueError("row-sparse Adam needs the touched-row marking of the tiled kernels (csrc/neumf2.cu); "
                              "the (10;100,50,10) script spec runs on the first-generation kernels")
         parts = self.initial_dense_parts(E, (h1, h2, h3), rng, head_mf)
@@ -174,6 +172,18 @@ class NeuMFNet:
         (RModel.py:119-121) -- gradients scaled by 1/(world * batch), ONE all-reduce of the flat arena,
         identical Adam step on every rank; BatchNorm statistics stay per replica."""
         w = D.world_size()
+        if w == 1 and isinstance(self.optimizer, H.Adam):
+            # one C call: fused step + optimizer (ONE kernel when the tensor-core instance covers the model)
+            B = u.numel()
+            out = out if out is not None else torch.empty(B, dtype=torch.float32, device=self.device)
+            loss_out = loss_out if loss_out is not None else torch.empty(1, dtype=torch.float32, device=self.device)
+            m, ws, opt = self._c_model(), self._workspace(B), self.optimizer
+            N.check(N.lib().brk_neumf_train_step(
+                N.ctx(self.device), C.byref(m), N.ptr(H._i32(u, "u")), N.ptr(H._i32(i, "i")), N.ptr(H._f32(y, "y")), B,
+                first_index, self.dropout_seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, opt.h, N.ptr(opt.state),
+                1 if opt.sparse == "lazy" else 0, C.byref(ws), N.ptr(out), N.ptr(loss_out), N.stream_ptr()),
+                "brk_neumf_train_step")
+            return loss_out, out
         loss, out = self.forward_backward(u, i, y, first_index, epoch, out, loss_out,
                                           global_batch=w * u.numel() if w > 1 else 0)
         if w > 1:

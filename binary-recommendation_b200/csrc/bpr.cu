@@ -258,18 +258,19 @@ struct BprCoopParams {
   int32_t rank, world;
   float inv_global;               // 1 / (world * batch): gradient scale of the global mean loss
   unsigned long long* dbg;        // optional [n_steps][8] globaltimer stamps of block 0 (BRK_COOP_TRACE)
+  long long spin_budget;          // clock64 budget of one cross-GPU wait (default ~30 s; BRK_PEER_SPIN_MS)
 };
 
 __device__ __forceinline__ void coop_st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ bool coop_spin_sys(const uint32_t* p, uint32_t epoch, uint32_t* err) {
+__device__ __forceinline__ bool coop_spin_sys(const uint32_t* p, uint32_t epoch, uint32_t* err, long long budget) {
   const long long t0 = clock64();
   while (true) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     if (int32_t(v - epoch) >= 0) return true;
-    if (clock64() - t0 > 6000000000LL) { atomicExch(err, 1u); return false; }      // ~3 s: a peer never arrived
+    if (clock64() - t0 > budget) { atomicExch(err, 1u); return false; }            // a peer never arrived
     __nanosleep(32);
   }
 }
@@ -419,10 +420,13 @@ __global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParam
         __threadfence_system();
         coop_st_release_sys(P.peer_flags[threadIdx.x] + me, ep);
       }
-      if (threadIdx.x < G) coop_spin_sys(my_flags + threadIdx.x, ep, P.dp_sync + 4);
-      __syncthreads();
+      // A peer that never arrives ABORTS the exchange on this rank: no reduce over incomplete gradients, no Adam, no
+      // pull; the sticky error word dp_sync[4] ends the launch at the next step boundary and PeerArena.check() raises.
+      bool okA = true;
+      if (threadIdx.x < G) okA = coop_spin_sys(my_flags + threadIdx.x, ep, P.dp_sync + 4, P.spin_budget);
+      const bool deadA = __syncthreads_or(okA ? 0 : 1) != 0 || *reinterpret_cast<volatile uint32_t*>(P.dp_sync + 4) != 0u;
       coop_stamp(P, s, 2);
-      if (!stager) {
+      if (!stager && !deadA) {
         const int64_t lo = P.arena_n4 * me / G, hi = P.arena_n4 * (me + 1) / G;
         float4* w_me = reinterpret_cast<float4*>(P.peer_w[me]);
         float4* m4 = reinterpret_cast<float4*>(P.dp_m); float4* v4 = reinterpret_cast<float4*>(P.dp_v);
@@ -442,16 +446,18 @@ __global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParam
       __threadfence();
       grid.sync();
       coop_stamp(P, s, 4);
-      if (blockIdx.x == 0 && threadIdx.x < G) {                 // barrier B: every rank's slice is final, reads of my g are done
+      const bool deadG = *reinterpret_cast<volatile uint32_t*>(P.dp_sync + 4) != 0u;   // uniform: read after the grid barrier
+      if (!deadG && blockIdx.x == 0 && threadIdx.x < G) {       // barrier B: every rank's slice is final, reads of my g are done
         __threadfence_system();
         coop_st_release_sys(P.peer_flags[threadIdx.x] + G + me, ep);
       }
-      if (threadIdx.x < G) coop_spin_sys(my_flags + G + threadIdx.x, ep, P.dp_sync + 4);
-      __syncthreads();
+      bool okB = true;
+      if (!deadG && threadIdx.x < G) okB = coop_spin_sys(my_flags + G + threadIdx.x, ep, P.dp_sync + 4, P.spin_budget);
+      const bool deadB = __syncthreads_or(okB ? 0 : 1) != 0 || deadG;
       coop_stamp(P, s, 5);
       // all-gather by PULL: remote loads complete when their data arrives, so nothing has to wait for NVLink write
       // acknowledgements (pushing the slices and fencing them system-wide cost ~8 us per step); zero my g meanwhile
-      {
+      if (!deadB) {
         float4* w_loc = reinterpret_cast<float4*>(P.peer_w[me]);
         const int64_t lo = P.arena_n4 * me / G, hi = P.arena_n4 * (me + 1) / G;
         const int64_t others = P.arena_n4 - (hi - lo);
@@ -472,8 +478,9 @@ __global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParam
     }
     grid.sync();
     coop_stamp(P, s, 6);
+    if (P.world > 1 && *reinterpret_cast<volatile uint32_t*>(P.dp_sync + 4) != 0u) break;   // aborted (uniform after the barrier)
   }
-  if (tid == 0) {
+  if (tid == 0 && !(P.world > 1 && *reinterpret_cast<volatile uint32_t*>(P.dp_sync + 4) != 0u)) {
     double* pwo = reinterpret_cast<double*>(P.state);
     P.state[0] += P.n_steps; pwo[1] = p1; pwo[2] = p2;
     if (P.world > 1) P.dp_sync[3] += uint32_t(P.n_steps);
@@ -613,6 +620,11 @@ static int launch_coop_steps(brk_ctx* ctx, const brk_table* user, const brk_tabl
     BRK_CUDA(cudaMemset(g_coop_trace, 0, 4096 * 8 * sizeof(unsigned long long)));
   }
   P.dbg = (g_coop_trace && n_steps <= 4096) ? g_coop_trace : nullptr;
+  {
+    const char* e = getenv("BRK_PEER_SPIN_MS");              // budget of one cross-GPU wait; default ~30 s at 2 GHz
+    const long long ms = e ? atoll(e) : 0;
+    P.spin_budget = ms > 0 ? ms * 2000000LL : 60000000000LL;
+  }
   const int lpr = brk_lanes_per_row(d >> 2);
   void* fn = nullptr;
   int slot = 0;

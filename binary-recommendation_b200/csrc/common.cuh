@@ -24,6 +24,9 @@ struct brk_ctx {
   // one-launch NeuMF step (csrc/neumf_fused.cu): per-tile slots of partial sums, summed after a grid barrier
   float*        neumf_part;
   size_t        neumf_part_floats;
+  // any-width NeuMF path (csrc/neumf_generic.cu): feature-major intermediates
+  float*        neumf_gen;
+  size_t        neumf_gen_floats;
   // fork/join inside one call: independent kernel chains of a step (the two towers of twotower.cu and, inside each,
   // the Dense-gradient products beside the embedding-gradient chain) run side by side on these streams
   cudaStream_t  fork_stream[3];

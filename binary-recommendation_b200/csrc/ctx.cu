@@ -55,6 +55,7 @@ extern "C" int brk_destroy(brk_ctx* c) {
   if (c->scratch) cudaFree(c->scratch);
   if (c->neumf_img) cudaFree(c->neumf_img);
   if (c->neumf_part) cudaFree(c->neumf_part);
+  if (c->neumf_gen) cudaFree(c->neumf_gen);
   for (int j = 0; j < BRK_FORK_STREAMS; ++j)
     if (c->fork_stream[j]) { cudaStreamDestroy(c->fork_stream[j]); cudaEventDestroy(c->ev_fork[j]); cudaEventDestroy(c->ev_join[j]); }
   if (c->copy_ready) {

@@ -15,13 +15,21 @@
 // NVLink bytes per rank per step: (G-1)/G * 4n read + (G-1)/G * 4n written (n floats in the arena).
 // Cross-rank flags are monotonic epochs (no reset), written with st.release.sys and polled with
 // ld.acquire.sys; every spin has a clock64() deadline that raises an error flag instead of hanging.
+#include <stdlib.h>
 #include "common.cuh"
 #include <cooperative_groups.h>
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr long long kSpinBudget = 6000000000LL;     // ~3 s at 2 GHz
+constexpr long long kSpinBudget = 60000000000LL;    // default ~30 s at 2 GHz (BRK_PEER_SPIN_MS overrides): a rank may be
+                                                    // seconds late into its first step (host-side data staging, checkpoint I/O)
+long long spin_budget_cycles() {
+  const char* e = getenv("BRK_PEER_SPIN_MS");
+  if (e == nullptr) return kSpinBudget;
+  const long long ms = atoll(e);
+  return ms > 0 ? ms * 2000000LL : kSpinBudget;
+}
 
 struct DpParams {
   float* const* peer_w;
@@ -33,6 +41,7 @@ struct DpParams {
   int32_t rank, world;
   brk_adam_hyper h;
   int64_t* state;
+  long long spin_budget;
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -51,12 +60,13 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ bool spin_until(const uint32_t* p, uint32_t epoch, bool sys, uint32_t* err) {
+__device__ __forceinline__ bool spin_until(const uint32_t* p, uint32_t epoch, bool sys, uint32_t* err,
+                                           long long budget = kSpinBudget) {
   const long long t0 = clock64();
   while (true) {
     const uint32_t v = sys ? ld_acquire_sys(p) : ld_acquire_gpu(p);
     if (int32_t(v - epoch) >= 0) return true;
-    if (clock64() - t0 > kSpinBudget) { atomicExch(err, 1u); return false; }
+    if (clock64() - t0 > budget) { atomicExch(err, 1u); return false; }
     __nanosleep(64);
   }
 }
@@ -71,14 +81,17 @@ __global__ void __launch_bounds__(kThreads) dp_adam_peer_kernel(const DpParams P
   if (blockIdx.x == 0) {
     if (t < G) {
       st_release_sys(P.peer_flags[t] + me, epoch);               // "rank `me` is ready", posted on peer t
-      spin_until(my_flags + t, epoch, true, sync + 4);           // wait for peer t's post on my pad
+      spin_until(my_flags + t, epoch, true, sync + 4, P.spin_budget);   // wait for peer t's post on my pad
     }
     __syncthreads();
     if (t == 0) st_release_gpu(sync + 0, epoch);
   } else {
-    if (t == 0) spin_until(sync + 0, epoch, false, sync + 4);
+    if (t == 0) spin_until(sync + 0, epoch, false, sync + 4, 2 * P.spin_budget);
     __syncthreads();
   }
+  // A peer that never arrived: this step is ABORTED on this rank -- no reduce over incomplete gradients, no Adam, no
+  // broadcast, the gradient arena stays as it is.  The error word is sticky; PeerArena.check() raises on it.
+  const bool dead = *reinterpret_cast<volatile uint32_t*>(sync + 4) != 0u;
 
   // Adam step size from the device-side optimizer state (running beta powers, see optim.cu)
   __shared__ float s_alpha;
@@ -96,7 +109,7 @@ __global__ void __launch_bounds__(kThreads) dp_adam_peer_kernel(const DpParams P
   float4* w_me = reinterpret_cast<float4*>(P.peer_w[me]);
   float4* m4 = reinterpret_cast<float4*>(P.m);
   float4* v4 = reinterpret_cast<float4*>(P.v);
-  for (int64_t i = lo + int64_t(blockIdx.x) * kThreads + t; i < hi; i += int64_t(gridDim.x) * kThreads) {
+  for (int64_t i = lo + int64_t(blockIdx.x) * kThreads + t; i < hi && !dead; i += int64_t(gridDim.x) * kThreads) {
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int p = 0; p < G; ++p) {                                // fixed order: deterministic sum
       const float4 x = *(reinterpret_cast<const float4*>(P.peer_g[p]) + i);
@@ -119,22 +132,23 @@ __global__ void __launch_bounds__(kThreads) dp_adam_peer_kernel(const DpParams P
   __syncthreads();
   if (s_last) {
     __threadfence_system();
-    if (t < G) {
+    if (t < G && !dead) {
       st_release_sys(P.peer_flags[t] + G + me, epoch);
-      spin_until(my_flags + G + t, epoch, true, sync + 4);
+      spin_until(my_flags + G + t, epoch, true, sync + 4, P.spin_budget);
     }
     __syncthreads();
     if (t == 0) {
       double* pw = reinterpret_cast<double*>(P.state);           // advance the optimizer state (once per rank)
-      P.state[0] += 1; pw[1] *= double(P.h.beta1); pw[2] *= double(P.h.beta2);
+      if (!dead) { P.state[0] += 1; pw[1] *= double(P.h.beta1); pw[2] *= double(P.h.beta2); }
       sync[2] = 0u;
       sync[3] = epoch;
       __threadfence();
       st_release_gpu(sync + 1, epoch);
     }
   }
-  if (t == 0) spin_until(sync + 1, epoch, false, sync + 4);
+  if (t == 0) spin_until(sync + 1, epoch, false, sync + 4, 2 * P.spin_budget);
   __syncthreads();
+  if (*reinterpret_cast<volatile uint32_t*>(sync + 4) != 0u) return;   // aborted: keep the gradients
 
   // ---- zero my gradient arena for the next step ----------------------------------------------------
   float4* g_me = reinterpret_cast<float4*>(P.peer_g[me]);
@@ -145,13 +159,13 @@ __global__ void __launch_bounds__(kThreads) dp_adam_peer_kernel(const DpParams P
 // Stand-alone cross-GPU barrier (one CTA): rank r posts epoch e on every peer's flag block and waits
 // until every peer has posted e on its own.  Used between the sharded fused step (whose REDs land in the
 // peers' accumulators) and the owners' optimizer pass.
-__global__ void peer_barrier_kernel(uint32_t* const* peer_flags, uint32_t* local_sync, int rank, int world) {
+__global__ void peer_barrier_kernel(uint32_t* const* peer_flags, uint32_t* local_sync, int rank, int world, long long budget) {
   const int t = threadIdx.x;
   const uint32_t epoch = local_sync[0] + 1u;
   __threadfence_system();
   if (t < world) {
     st_release_sys(peer_flags[t] + rank, epoch);
-    spin_until(peer_flags[rank] + t, epoch, true, local_sync + 1);
+    spin_until(peer_flags[rank] + t, epoch, true, local_sync + 1, budget);
   }
   __syncthreads();
   if (t == 0) local_sync[0] = epoch;
@@ -169,6 +183,7 @@ extern "C" int brk_dp_adam_peer(brk_ctx* ctx, const brk_dp_peer* d, brk_adam_hyp
   DpParams P;
   P.peer_w = d->peer_w; P.peer_g = d->peer_g; P.peer_flags = d->peer_flags; P.m = d->m; P.v = d->v;
   P.local_sync = d->local_sync; P.n4 = d->n / 4; P.rank = d->rank; P.world = d->world; P.h = h; P.state = state;
+  P.spin_budget = spin_budget_cycles();
   // all CTAs spin on flags set by other CTAs: they must be co-resident -> cooperative launch, one CTA per SM at most
   const int64_t slice4 = (P.n4 + d->world - 1) / d->world;
   int64_t need = (P.n4 + kThreads - 1) / kThreads;        // the zeroing pass covers the whole arena
@@ -186,7 +201,7 @@ extern "C" int brk_peer_barrier(brk_ctx* ctx, uint32_t* const* peer_flags, uint3
   BRK_REQUIRE(ctx && peer_flags && local_sync, BRK_E_ARG, "brk_peer_barrier: null argument");
   BRK_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, BRK_E_ARG, "brk_peer_barrier: rank=%d world=%d",
               rank, world);
-  peer_barrier_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(peer_flags, local_sync, rank, world);
+  peer_barrier_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(peer_flags, local_sync, rank, world, spin_budget_cycles());
   BRK_LAUNCH_CHECK();
   return 0;
 }

