@@ -81,10 +81,12 @@ class BPRNet:
         self._pairs["n"].copy_(torch.as_tensor(np.ascontiguousarray(negs, dtype=np.int32)))
 
     # ---- training -------------------------------------------------------------------------------
-    def train_steps(self, batch_indices, batch_size, losses=None):
+    def train_steps(self, batch_indices, batch_size, losses=None, arrays=None):
         """Enqueues len(batch_indices) training steps over the resident triplets; returns the device
-        tensor of per-step mean losses (no host sync)."""
-        pr = self._pairs
+        tensor of per-step mean losses (no host sync).  arrays: dict u / p / n / total to train on instead of the
+        resident frame (fit passes this rank's slice of every global batch under data parallelism).  In peer mode
+        every listed batch must be full (the cooperative launch runs the same number of samples on every rank)."""
+        pr = arrays if arrays is not None else self._pairs
         k = len(batch_indices)
         if losses is None:
             losses = torch.empty(k, dtype=torch.float32, device=self.device)
@@ -222,6 +224,9 @@ class BPRNet:
         total = self._pairs["total"]
         n_batches = (total + batch_size - 1) // batch_size
         rng = np.random.Generator(np.random.Philox(key=sampler_seed + 1000003))
+        W = D.world_size()
+        if W > 1:
+            return self._fit_data_parallel(batch_size, epochs, shuffle, sampler_seed, verbose, initial_epoch, fixed_neg, rng)
         for e in range(initial_epoch, initial_epoch + epochs):
             if fixed_neg is None:
                 self.sample_negatives(sampler_seed, e)
@@ -233,6 +238,75 @@ class BPRNet:
             if verbose:
                 print(f"epoch {e + 1}: loss {mean:.6f}")
         return self
+
+    def _fit_data_parallel(self, batch_size, epochs, shuffle, sampler_seed, verbose, initial_epoch, fixed_neg, rng):
+        """fit under torch.distributed -- what MultiWorkerMirroredStrategy does with an auto-sharded dataset
+        (RModel.py:119-121): `batch_size` stays the GLOBAL batch, rank r trains rows [r B/W, (r+1) B/W) of every global
+        batch, gradients are scaled by 1/B and summed, every rank applies the same Adam step.  Same frame, same
+        sampler stream and same batch order on every rank (all seeded), so W GPUs reproduce the single-GPU run up to
+        summation order.  The ragged last batch goes through the per-step path with unequal slices."""
+        W, r = D.world_size(), D.rank()
+        if batch_size % W:
+            raise ValueError(f"batch_size {batch_size} is the global batch: it must be a multiple of the {W} ranks")
+        pr = self._pairs
+        total, lb = pr["total"], batch_size // W
+        nfull, n_batches = total // batch_size, (total + batch_size - 1) // batch_size
+        dev = self.device
+        sel = (torch.arange(nfull, device=dev).view(-1, 1) * batch_size + r * lb + torch.arange(lb, device=dev).view(1, -1)).reshape(-1)
+        local = dict(u=pr["u"][sel].contiguous(), p=pr["p"][sel].contiguous(), n=None, total=nfull * lb)
+        D.barrier()                                             # nobody enters a cross-GPU wait while a rank is still staging
+        for e in range(initial_epoch, initial_epoch + epochs):
+            if fixed_neg is None:
+                self.sample_negatives(sampler_seed, e)           # counter = position in the GLOBAL frame: independent of W
+            local["n"] = pr["n"][sel].contiguous()
+            order = rng.permutation(n_batches) if shuffle else np.arange(n_batches)
+            parts = []
+            k = 0
+            while k < len(order):                                # runs of full batches -> one launch; the ragged one on its own
+                if order[k] == nfull:
+                    parts.append(self._ragged_global_batch(nfull * batch_size, total - nfull * batch_size).view(1))
+                    k += 1
+                    continue
+                j = k
+                while j < len(order) and order[j] != nfull:
+                    j += 1
+                parts.append(self._train_steps_local(order[k:j], lb, local, batch_size))
+                k = j
+            losses = torch.cat(parts).double()
+            if self.peer is not None:
+                self.peer.check()
+            mean = losses.mean().view(1)
+            D.all_reduce_sum_(mean)                              # equal local batches: global mean = mean of the local means
+            mean = float(mean.item()) / W
+            self.history["loss"].append(mean)
+            if verbose and r == 0:
+                print(f"epoch {e + 1}: loss {mean:.6f}")
+        return self
+
+    def _train_steps_local(self, batch_indices, lb, local, global_batch):
+        if self.peer is not None:
+            return self.train_steps(batch_indices, lb, arrays=local)
+        losses = torch.empty(len(batch_indices), dtype=torch.float32, device=self.device)
+        for k, b in enumerate(batch_indices):                   # NCCL fallback: one all-reduce of the flat arena per step
+            s = slice(int(b) * lb, (int(b) + 1) * lb)
+            H.bpr_fwd_bwd(self.user, self.item, local["u"][s], local["p"][s], local["n"][s], loss_out=losses[k:k + 1],
+                          global_batch=global_batch)
+            self.apply_gradients()
+        return losses
+
+    def _ragged_global_batch(self, first, count):
+        """The last, partial global batch: rank r takes its local_slice of the `count` rows (possibly none), the
+        gradient scale is 1/count; returns this rank's share of the batch loss scaled so that the ranks' values average
+        to the global mean."""
+        pr = self._pairs
+        lo, hi = D.local_slice(count)
+        loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        if hi > lo:
+            s = slice(first + lo, first + hi)
+            H.bpr_fwd_bwd(self.user, self.item, pr["u"][s], pr["p"][s], pr["n"][s], loss_out=loss, global_batch=count)
+            loss = loss * (float(hi - lo) * D.world_size() / float(count))
+        self.apply_gradients()
+        return loss.view(())
 
     # ---- inference ------------------------------------------------------------------------------
     def predict(self, X):
@@ -247,14 +321,32 @@ class BPRNet:
         return {"user_embedding": self.user.w, "item_embedding": self.item.w}[name]
 
     def state_dict(self):
+        """Collective under peer-mode data parallelism: the Adam moments are sharded over the ranks (every rank holds the
+        slice it applies) and are gathered here; every rank must call it."""
+        if self.peer is not None:
+            self.peer.check()
+            nu, ni = self.numUser * self.numFactor, self.numItem * self.numFactor
+            m, v = self.peer.full_moments()
+            shp_u, shp_i = (self.numUser, self.numFactor), (self.numItem, self.numFactor)
+            return {"user": self.user.w.cpu(), "item": self.item.w.cpu(), "user_m": m[:nu].view(shp_u).cpu(),
+                    "user_v": v[:nu].view(shp_u).cpu(), "item_m": m[nu:nu + ni].view(shp_i).cpu(),
+                    "item_v": v[nu:nu + ni].view(shp_i).cpu(), "opt_state": self.optimizer.state.cpu()}
         return {"user": self.user.w.cpu(), "item": self.item.w.cpu(), "user_m": self.user.m.cpu(),
                 "user_v": self.user.v.cpu(), "item_m": self.item.m.cpu(), "item_v": self.item.v.cpu(),
                 "opt_state": self.optimizer.state.cpu()}
 
     def load_state_dict(self, sd):
         self.user.w.copy_(sd["user"]); self.item.w.copy_(sd["item"])
-        self.user.m.copy_(sd["user_m"]); self.user.v.copy_(sd["user_v"])
-        self.item.m.copy_(sd["item_m"]); self.item.v.copy_(sd["item_v"])
+        if self.peer is not None:
+            dev = self.device
+            m = torch.zeros(self.peer.n, dtype=torch.float32, device=dev); v = torch.zeros_like(m)
+            nu, ni = self.numUser * self.numFactor, self.numItem * self.numFactor
+            m[:nu] = sd["user_m"].reshape(-1).to(dev); m[nu:nu + ni] = sd["item_m"].reshape(-1).to(dev)
+            v[:nu] = sd["user_v"].reshape(-1).to(dev); v[nu:nu + ni] = sd["item_v"].reshape(-1).to(dev)
+            self.peer.load_moments(m, v)
+        else:
+            self.user.m.copy_(sd["user_m"]); self.user.v.copy_(sd["user_v"])
+            self.item.m.copy_(sd["item_m"]); self.item.v.copy_(sd["item_v"])
         self.optimizer.state.copy_(sd["opt_state"])
 
 

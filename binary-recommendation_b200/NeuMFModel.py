@@ -167,10 +167,11 @@ class NeuMFNet:
                 "brk_neumf_step")
         return loss_out, out
 
-    def train_on_batch(self, u, i, y, first_index=0, epoch=0, out=None, loss_out=None):
+    def train_on_batch(self, u, i, y, first_index=0, epoch=0, out=None, loss_out=None, global_batch=None):
         """One training step.  Under torch.distributed: mirrored synchronous data parallelism
-        (RModel.py:119-121) -- gradients scaled by 1/(world * batch), ONE all-reduce of the flat arena,
-        identical Adam step on every rank; BatchNorm statistics stay per replica."""
+        (RModel.py:119-121) -- u / i / y are THIS rank's rows of the global batch (global_batch rows in all; default
+        world * len(u)), gradients are scaled by 1/global_batch, ONE all-reduce of the flat arena, identical Adam step
+        on every rank; BatchNorm statistics stay per replica (MirroredStrategy's default)."""
         w = D.world_size()
         if w == 1 and isinstance(self.optimizer, H.Adam):
             # one C call: fused step + optimizer (ONE kernel when the tensor-core instance covers the model)
@@ -184,8 +185,12 @@ class NeuMFNet:
                 1 if opt.sparse == "lazy" else 0, C.byref(ws), N.ptr(out), N.ptr(loss_out), N.stream_ptr()),
                 "brk_neumf_train_step")
             return loss_out, out
-        loss, out = self.forward_backward(u, i, y, first_index, epoch, out, loss_out,
-                                          global_batch=w * u.numel() if w > 1 else 0)
+        gb = (int(global_batch) if global_batch is not None else w * u.numel()) if w > 1 else 0
+        if u.numel() > 0:
+            loss, out = self.forward_backward(u, i, y, first_index, epoch, out, loss_out, global_batch=gb)
+        else:                                                # this rank's slice of a ragged last batch may be empty
+            loss = loss_out if loss_out is not None else torch.zeros(1, dtype=torch.float32, device=self.device)
+            loss.zero_()
         if w > 1:
             D.all_reduce_sum_(self.grad_arena)
         self.optimizer.apply(self.tables(), dense=[self.dense])
@@ -201,9 +206,14 @@ class NeuMFNet:
         out = out if out is not None else torch.empty(min(batch, n), dtype=torch.float32, device=self.device)
         if D.world_size() > 1 or not isinstance(self.optimizer, H.Adam):
             for k, b in enumerate(order):
-                s = slice(int(b) * batch, min(n, (int(b) + 1) * batch))
-                self.train_on_batch(u[s], i[s], y[s], first_index=int(b) * batch, epoch=epoch,
-                                    out=out[:s.stop - s.start], loss_out=losses[k:k + 1])
+                # data parallel: `batch` is the GLOBAL batch (MultiWorkerMirroredStrategy auto-shards the dataset,
+                # RModel.py:119-121); this rank trains its local_slice of it, the dropout stream follows the row's
+                # position in the frame, so W ranks reproduce the single-process step up to BatchNorm's per-replica statistics
+                lo_g, hi_g = int(b) * batch, min(n, (int(b) + 1) * batch)
+                lo, hi = D.local_slice(hi_g - lo_g)
+                s = slice(lo_g + lo, lo_g + hi)
+                self.train_on_batch(u[s], i[s], y[s], first_index=lo_g + lo, epoch=epoch, out=out[:hi - lo],
+                                    loss_out=losses[k:k + 1], global_batch=hi_g - lo_g)
             return losses
         m, ws = self._c_model(), self._workspace(min(batch, n))
         opt = self.optimizer
@@ -356,9 +366,11 @@ class NeuMFDataset:
         losses = torch.empty(len(order), dtype=torch.float32, device=self.device)
         outs = torch.empty(self.batchSize, dtype=torch.float32, device=self.device)
         for k, b in enumerate(order):                         # nets with their own step (row-sharded tables)
-            s = slice(b * self.batchSize, min(self.n, (b + 1) * self.batchSize))
-            net.train_on_batch(self.u[s], self.i[s], self.y[s], first_index=int(b) * self.batchSize, epoch=epoch,
-                               out=outs[:s.stop - s.start], loss_out=losses[k:k + 1])
+            lo_g, hi_g = int(b) * self.batchSize, min(self.n, (int(b) + 1) * self.batchSize)
+            lo, hi = D.local_slice(hi_g - lo_g)              # this rank's rows of the global batch (whole batch when single)
+            s = slice(lo_g + lo, lo_g + hi)
+            net.train_on_batch(self.u[s], self.i[s], self.y[s], first_index=lo_g + lo, epoch=epoch,
+                               out=outs[:hi - lo], loss_out=losses[k:k + 1])
         return losses
 
 

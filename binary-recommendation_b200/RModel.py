@@ -259,7 +259,11 @@ class RModel:
         """model.save(checkpointPath) (RModel.py:139): a checkpoint directory (checkpoint.py) holding the weights,
         optimizer slots and step -- readable by a process with any number of GPUs."""
         from . import checkpoint as CK
-        CK.save_state_dict(self.checkpointPath, self.model.state_dict(), meta=self.checkpointMeta())
+        from . import distributed as D
+        sd = self.model.state_dict()                 # collective under mirrored data parallelism (sharded Adam moments)
+        if D.rank() == 0:                            # replicas are identical: the chief saves (RModel.py:175-196)
+            CK.save_state_dict(self.checkpointPath, sd, meta=self.checkpointMeta())
+        D.barrier()
 
     def restoreFromLatestCheckPoint(self):
         """tf.keras.models.load_model(checkpointPath) (RModel.py:172-173), as the REST endpoint calls it on a fresh

@@ -7,7 +7,10 @@ the REST endpoint, src/restful/RecommendationEndpoint.py:19-23).  With mirrored 
 whole model, so "the chief saves" is enough there.  Here tables can be row-sharded over GPUs (sharded.py: row r
 lives on rank r % G at local row r // G), so a checkpoint is a directory:
 
-  manifest.json                      written last by rank 0 (atomic rename): format version, world size, entries
+  manifest.json                      written last by rank 0 (atomic rename): format version, world size, entries.
+                                     Re-saving into an existing directory first REMOVES the old manifest (and the shard
+                                     files of other world sizes), so a crash in the middle of a save leaves a directory
+                                     without manifest -- "incomplete", never a manifest naming a mix of old and new tensors
   <name>.bin                         replicated tensors (dense block, BatchNorm statistics, optimizer step), rank 0
   <name>.shard<r>-of-<G>.bin         row-sharded tensors (weights and Adam / Adagrad slots), one file per rank,
                                      raw little-endian arrays [local_rows, d]
@@ -55,7 +58,25 @@ def save_checkpoint(dirpath, replicated=None, sharded=None, rank=0, world=1, met
     barrier: callable run between the shard writes and the manifest (torch.distributed.barrier under N > 1), so the
     manifest only ever names complete shard sets."""
     replicated, sharded = replicated or {}, sharded or {}
+    for name in list(replicated) + list(sharded):
+        if not name or name != os.path.basename(name) or name in (".", "..") or "\\" in name or name.startswith("manifest"):
+            raise CheckpointError(f"tensor name {name!r} is not a plain file name")
+    for name, (t, rows) in sharded.items():                 # validate everything before touching what is on disk
+        shp = tuple(_np(t).shape) if not hasattr(t, "shape") else tuple(t.shape)
+        if len(shp) != 2 or shp[0] != shard_rows(int(rows), world):
+            raise CheckpointError(f"{name}: local shard has shape {shp}, expected [{shard_rows(int(rows), world)}, d]")
     os.makedirs(dirpath, exist_ok=True)
+    if rank == 0:
+        # invalidate what is there before the first byte of the new save is written
+        old = os.path.join(dirpath, "manifest.json")
+        if os.path.exists(old):
+            os.remove(old)
+        keep = {shard_file(n, q, world) for n in sharded for q in range(world)} | {n + ".bin" for n in replicated}
+        for f in os.listdir(dirpath):
+            if f.endswith(".bin") and f not in keep:
+                os.remove(os.path.join(dirpath, f))
+    if barrier is not None:
+        barrier()
     entries = {}
     for name, (t, rows) in sharded.items():
         a = _np(t)
@@ -122,6 +143,8 @@ def load_checkpoint(dirpath, rank=0, world=1, names=None):
     for name, e in m["entries"].items():
         if names is not None and name not in names:
             continue
+        if name != os.path.basename(name) or name in (".", ".."):
+            raise CheckpointError(f"{dirpath}: manifest entry {name!r} is not a plain file name")
         if e["sharding"] == "replicated":
             p = os.path.join(dirpath, name + ".bin")
             dt = np.dtype(e["dtype"])

@@ -47,6 +47,12 @@ def init_from_env(backend=None):
         dist.init_process_group(backend)
 
 
+def barrier():
+    """Host-side rendezvous of all ranks (no-op in a single process)."""
+    if is_dist() and world_size() > 1:
+        dist.barrier()
+
+
 def all_reduce_sum_(flat):
     """In-place sum over ranks of the flat gradient arena."""
     if is_dist() and world_size() > 1:
@@ -101,8 +107,25 @@ class PeerArena:
                 "brk_dp_adam_peer")
 
     def check(self):
+        """Raises when a cross-GPU wait of the fused exchange timed out (a rank never reached the step; the kernels
+        abort that step without touching the weights -- csrc/dp_peer.cu, csrc/bpr.cu).  One 4-byte device read: called
+        at epoch ends and before checkpoints, not per step."""
         if int(self.local_sync[4].item()) != 0:
-            raise RuntimeError("brk_dp_adam_peer: a cross-GPU barrier timed out (a rank did not reach the step)")
+            raise RuntimeError("mirrored data parallelism: a cross-GPU barrier timed out (a rank did not reach the step); "
+                               "the step was aborted on this rank and the replicas can no longer be trusted to be identical "
+                               "(BRK_PEER_SPIN_MS sets the wait budget, default 30 s)")
+
+    def full_moments(self):
+        """Adam moments of the whole arena on every rank (they are sharded: rank r holds float4 slice r): for checkpoints."""
+        m = torch.zeros(self.n, dtype=torch.float32, device=self.device); v = torch.zeros_like(m)
+        k = self.slice_hi - self.slice_lo
+        m[self.slice_lo:self.slice_hi] = self.m[:k]; v[self.slice_lo:self.slice_hi] = self.v[:k]
+        dist.all_reduce(m); dist.all_reduce(v)
+        return m, v
+
+    def load_moments(self, m, v):
+        k = self.slice_hi - self.slice_lo
+        self.m[:k].copy_(m.reshape(-1)[self.slice_lo:self.slice_hi]); self.v[:k].copy_(v.reshape(-1)[self.slice_lo:self.slice_hi])
 
 
 def peer_arena_or_none(n_floats, device):

@@ -237,6 +237,9 @@ def rows_to_bf16(x):
     return out
 
 
+MAX_FUSED_K = 32          # list length the selection kernels keep per row (csrc/topk.cu)
+
+
 class BruteForceIndex:
     """tfrs.layers.factorized_top_k.BruteForce as the reference uses it (trainers/twoTower.py:64-69,
     src/origin_models/svd/SVD.py:424-432): index(candidates, identifiers) once, then call(queries)
@@ -259,6 +262,10 @@ class BruteForceIndex:
         if self._c is None:
             raise RuntimeError("BruteForceIndex: call index(candidates) first")
         k = min(int(k or self.k), self.num_candidates)
+        if k > MAX_FUSED_K:
+            # the selection epilogue keeps at most 32 entries per row in registers; longer lists take the materialised
+            # route: fp32 scores of a chunk of users (brk_sgemm) + the multi-pass row top-k below
+            return self._call_materialised(queries, k)
         if queries.shape[1] != self.dim:
             raise ValueError(f"query dim {queries.shape[1]} != candidate dim {self.dim}")
         U = queries.shape[0]
@@ -279,6 +286,40 @@ class BruteForceIndex:
         return vals, ids
 
 
+def sgemm(a, b, trans_b=False):
+    """fp32 product a [M, K] @ b ([K, N], or [N, K] with trans_b) on the CUDA cores (csrc/twotower.cu brk_sgemm)."""
+    a = _f32(a, "a"); b = _f32(b, "b")
+    M, K = a.shape
+    Nn = b.shape[0] if trans_b else b.shape[1]
+    if (b.shape[1] if trans_b else b.shape[0]) != K:
+        raise ValueError("sgemm: inner dimensions differ")
+    out = torch.empty((M, Nn), dtype=torch.float32, device=a.device)
+    N.check(N.lib().brk_sgemm(N.ctx(a.device), N.ptr(a), N.ptr(b), N.ptr(out), None, M, Nn, K, a.shape[1], b.shape[1], Nn, 0,
+                              1 if trans_b else 0, 1.0, 0, N.stream_ptr()), "brk_sgemm")
+    return out
+
+
+def _bruteforce_materialised(self, queries, k):
+    """k > 32: bf16-rounded operands like the fused kernel (so shorter and longer lists agree on their common prefix up
+    to fp32 summation order), scores of <= 2^24 pairs at a time, multi-pass top-k."""
+    U, I = queries.shape[0], self.num_candidates
+    dev = queries.device
+    C = self._c[:, :self.dim].float().contiguous()
+    vals = torch.empty((U, k), dtype=torch.float32, device=dev)
+    ids = torch.empty((U, k), dtype=torch.int32, device=dev)
+    chunk = max(1, (1 << 24) // max(I, 1))
+    for s0 in range(0, U, chunk):
+        q = _f32(queries[s0:s0 + chunk], "queries").to(torch.bfloat16).float().contiguous()
+        v, ix = topk_rows(sgemm(q, C, trans_b=True), k)
+        vals[s0:s0 + chunk] = v; ids[s0:s0 + chunk] = ix + self.id_offset
+    if self._identifiers is not None:
+        return vals, self._identifiers[(ids - self.id_offset).long()]
+    return vals, ids
+
+
+BruteForceIndex._call_materialised = _bruteforce_materialised
+
+
 def topk_merge(part_vals, part_ids):
     """Merges [S, U, k] partial lists (global ids) into [U, k]: score desc, id asc."""
     part_vals = _f32(part_vals, "part_vals"); part_ids = _i32(part_ids, "part_ids")
@@ -295,6 +336,16 @@ def topk_rows(scores, k):
     scores = _f32(scores, "scores")
     R, I = scores.shape
     k = min(int(k), I)
+    if k > MAX_FUSED_K:
+        # the kernel selects at most 32 per pass: take 32, strike them out of a copy, repeat (the tie rule carries over:
+        # every pass prefers the lower column among equal scores)
+        work = scores.clone()
+        vs, js = [], []
+        for k0 in range(0, k, MAX_FUSED_K):
+            v, j = topk_rows(work, min(MAX_FUSED_K, k - k0))
+            vs.append(v); js.append(j)
+            work.scatter_(1, j.long(), float("-inf"))
+        return torch.cat(vs, 1), torch.cat(js, 1)
     vals = torch.empty((R, k), dtype=torch.float32, device=scores.device)
     ids = torch.empty((R, k), dtype=torch.int32, device=scores.device)
     N.check(N.lib().brk_topk_rows(N.ctx(scores.device), N.ptr(scores), R, I, k, N.ptr(vals), N.ptr(ids),

@@ -122,6 +122,8 @@ class Vocabulary:
         if isinstance(keys, torch.Tensor):
             if keys.dtype != torch.int64:
                 raise TypeError("device keys must be int64 (the 64-bit key pattern)")
+            if keys.numel() and bool((keys == -1).any().item()):      # the empty-slot marker of the hash table
+                raise ValueError("key 0xFFFFFFFFFFFFFFFF (int64 -1) is reserved")
             return keys.contiguous()
         return torch.from_numpy(pack_keys(keys).view(np.int64)).to(dev)
 

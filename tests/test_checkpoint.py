@@ -131,3 +131,36 @@ def test_rmodel_plot_writes_the_history_series(tmp_path):
     out = m.plot(hist, [("mse", "MSE")])
     assert json.load(open(out)) == {"loss": [0.5, 0.4], "val_loss": [0.6, 0.5], "mse": [0.3, 0.2]}
     assert m.getPredictDataFrame(3) is None and m.predictForUser(3) is None and m.getPredictableUsers() == []
+
+
+def test_resave_invalidates_the_old_checkpoint_first_and_rejects_path_names(tmp_path, monkeypatch):
+    """A crash in the middle of a re-save must leave an INCOMPLETE directory, never a manifest naming a mix of old and
+    new tensors; shards of an earlier world size are removed; tensor names are plain file names."""
+    d = str(tmp_path / "cp")
+    full = np.arange(18, dtype=np.float32).reshape(9, 2)
+    for r in (1, 0):
+        CK.save_checkpoint(d, replicated={"x": np.zeros(3)}, sharded={"user": (_shards(full, 2)[r], 9)}, rank=r, world=2)
+    CK.load_checkpoint(d)
+    calls = {"n": 0}
+    real = CK._write
+
+    def dying_write(path, a):
+        calls["n"] += 1
+        if calls["n"] == 2:
+            raise OSError("disk full")
+        real(path, a)
+
+    monkeypatch.setattr(CK, "_write", dying_write)
+    with pytest.raises(OSError):
+        CK.save_checkpoint(d, replicated={"x": np.ones(3), "y": np.ones(2)}, sharded={"user": (full + 1, 9)}, rank=0, world=1)
+    monkeypatch.setattr(CK, "_write", real)
+    with pytest.raises(CK.CheckpointError, match="manifest"):
+        CK.load_checkpoint(d)                                   # incomplete, not half old / half new
+    CK.save_checkpoint(d, replicated={"x": np.ones(3)}, sharded={"user": (full + 1, 9)}, rank=0, world=1)
+    rep, shd, _ = CK.load_checkpoint(d)
+    assert np.array_equal(shd["user"], full + 1) and np.array_equal(rep["x"], np.ones(3))
+    assert not any("-of-002" in f for f in os.listdir(d))       # the 2-rank shards are gone
+    for bad in ("../evil", "a/b", "", "..", "manifest.json"):
+        with pytest.raises(CK.CheckpointError, match="plain file name"):
+            CK.save_checkpoint(d, replicated={bad: np.zeros(1)})
+    CK.load_checkpoint(d)                                       # the rejected saves touched nothing

@@ -58,8 +58,29 @@ def _worker(rank, world, port, ret):
         packed = BPRNet.pack_host_batches(pu, pi, B)
         order = [rank, 2 + rank, 4 + rank]
         hl = net2.train_steps_from_host(packed, None, order, B, 7, 2)
+        # fit() under data parallelism: global batch 256 split over the ranks, ragged last batch, two epochs with fresh
+        # negatives and a shuffled batch order; then the checkpoint handoff (Adam moments are sharded over the ranks)
+        net3 = BPRNet(U, I, d, seed=44, device=dev)
+        net3.fit({'customerId_input': pu, 'pProduct_input': pi}, batch_size=256, epochs=2, shuffle=True, sampler_seed=9)
+        sd = net3.state_dict()
+        net4 = BPRNet(U, I, d, seed=45, device=dev)
+        net4.load_state_dict(sd)
+        sd4 = net4.state_dict()
+        assert all(torch.equal(sd[k], sd4[k]) for k in sd), "state_dict -> load_state_dict -> state_dict is not the identity"
+        # NeuMF data parallel through train_steps (the fit loop): He et al. variant has no BatchNorm, so W ranks on slices of
+        # the global batch must reproduce the single-process run on the whole batch
+        nm2 = NeuMFNet(U, I, 16, dropout=0.0, device=dev, mf_dim=4, mf_mode="hadamard", batch_norm=False)
+        rng3 = np.random.default_rng(12)
+        nrows = 1000                                           # global batch 192: five full batches + 40 rows (odd split)
+        fu = torch.from_numpy(rng3.integers(0, U, nrows).astype(np.int32)).to(dev)
+        fi = torch.from_numpy(rng3.integers(0, I, nrows).astype(np.int32)).to(dev)
+        fy = torch.from_numpy((rng3.random(nrows) < 0.3).astype(np.float32)).to(dev)
+        nm2.train_steps(fu, fi, fy, 192, np.arange(6), epoch=1)
         torch.cuda.synchronize()
         ret[rank] = dict(user=net.user.w.cpu().numpy(), item=net.item.w.cpu().numpy(), losses=losses,
+                         fit_user=net3.user.w.cpu().numpy(), fit_item=net3.item.w.cpu().numpy(), fit_hist=list(net3.history["loss"]),
+                         fit_user_m=sd["user_m"].numpy(), fit_item_v=sd["item_v"].numpy(), fit_t=int(sd["opt_state"][0]),
+                         he_W1=nm2.param("W1").cpu().numpy(), he_uMLP=nm2.uMLP.w.cpu().numpy(), he_iMF=nm2.iMF.w.cpu().numpy(),
                          hf_user=net2.user.w.cpu().numpy(), hf_item=net2.item.w.cpu().numpy(), hf_losses=hl.numpy().copy(),
                          tv=tv.cpu().numpy(), ti=ti.cpu().numpy(), neumf_W1=nm.param("W1").cpu().numpy(),
                          neumf_uMLP=nm.uMLP.w.cpu().numpy())
@@ -111,6 +132,39 @@ def test_mirrored_bpr_neumf_and_sharded_topk_two_gpus():
         np.testing.assert_allclose(ret[r]["hf_user"], orc2.user, rtol=1e-5, atol=2e-6)
         np.testing.assert_allclose(ret[r]["hf_item"], orc2.item, rtol=1e-5, atol=2e-6)
         assert np.isfinite(ret[r]["hf_losses"]).all()
+    # fit() through the data-parallel path against the oracle's single-process loop over the same global batches
+    orc3 = OB.BPROracle(U, I, d, seed=44)
+    n_batches = (len(pu) + 255) // 256
+    order_rng = np.random.Generator(np.random.Philox(key=9 + 1000003))
+    hist = []
+    for e in range(2):
+        neg = OP.bpr_negatives(pu, 9, e, I, indptr, sitems)
+        ls = []
+        for b in order_rng.permutation(n_batches):
+            sl = slice(b * 256, min(len(pu), (b + 1) * 256))
+            ls.append(orc3.step(pu[sl], pi[sl], neg[sl]))
+        hist.append(float(np.mean(ls)))
+    for r in range(world):
+        np.testing.assert_allclose(ret[r]["fit_user"], orc3.user, rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(ret[r]["fit_item"], orc3.item, rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(ret[r]["fit_hist"], hist, rtol=1e-5)
+        np.testing.assert_allclose(ret[r]["fit_user_m"], orc3.mu, rtol=1e-3, atol=1e-8)
+        np.testing.assert_allclose(ret[r]["fit_item_v"], orc3.vi, rtol=1e-3, atol=1e-12)
+        assert ret[r]["fit_t"] == 2 * n_batches
+    assert np.array_equal(ret[0]["fit_user"], ret[1]["fit_user"])
+    from oracle import neumf as ON
+    orc4 = ON.NeuMFOracle(U, I, emb=16, dropout=0.0, mf_dim=4, mf_mode="hadamard", batch_norm=False)
+    rng3 = np.random.default_rng(12)
+    fu = rng3.integers(0, U, 1000).astype(np.int32); fi = rng3.integers(0, I, 1000).astype(np.int32)
+    fy = (rng3.random(1000) < 0.3).astype(np.float32)
+    for b in range(6):
+        sl = slice(b * 192, min(1000, (b + 1) * 192))
+        orc4.step(fu[sl], fi[sl], fy[sl], first_index=b * 192, epoch=1)
+    ref4 = orc4.p.numpy()
+    for r in range(world):
+        np.testing.assert_allclose(ret[r]["he_W1"], ref4["W1"], rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(ret[r]["he_uMLP"], ref4["uMLP"], rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(ret[r]["he_iMF"], ref4["iMF"], rtol=1e-4, atol=2e-5)
     assert np.array_equal(ret[0]["user"], ret[1]["user"]) and np.array_equal(ret[0]["neumf_W1"], ret[1]["neumf_W1"])
     assert np.array_equal(ret[0]["neumf_uMLP"], ret[1]["neumf_uMLP"])
     Q = (np.random.default_rng(4).integers(-4, 5, size=(77, 64)) / 8.0).astype(np.float32)

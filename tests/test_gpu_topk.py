@@ -103,3 +103,22 @@ def test_topk_k_clamped_and_identifiers(dev):
     v, i = H().BruteForceIndex(10).index(torch.from_numpy(C).to(dev), identifiers=idents)(torch.from_numpy(Q).to(dev))
     rv, ri = OT.brute_force_topk(Q, C, 10)
     assert v.shape == (5, 7) and np.array_equal(i.cpu().numpy(), ri + 100)
+
+
+def test_lists_longer_than_the_fused_kernel_keeps(dev):
+    """BruteForce(k) takes any k in the reference (tfrs BruteForce, trainers/twoTower.py:64-69); the fused selection keeps
+    32 per row, longer lists take the materialised multi-pass route -- same order and tie rule."""
+    from binrec_b200 import hotpath as H
+    from oracle import topk as OT
+    rng = np.random.default_rng(1)
+    Q = (rng.integers(-4, 5, size=(37, 64)) / 8.0).astype(np.float32)
+    C = (rng.integers(-4, 5, size=(500, 64)) / 8.0).astype(np.float32)
+    for k in (33, 50, 100):
+        idx = H.BruteForceIndex(k).index(torch.from_numpy(C).to(dev))
+        v, ix = idx(torch.from_numpy(Q).to(dev))
+        rv, ri = OT.brute_force_topk(Q, C, k)
+        assert np.array_equal(ix.cpu().numpy(), ri) and np.array_equal(v.cpu().numpy(), rv)
+    S = (rng.integers(-20, 21, size=(9, 300)) / 8.0).astype(np.float32)
+    v, ix = H.topk_rows(torch.from_numpy(S).to(dev), 70)
+    rv, ri = OT.topk_from_scores(S, 70)
+    assert np.array_equal(ix.cpu().numpy(), ri) and np.array_equal(v.cpu().numpy(), rv)
