@@ -10,10 +10,25 @@ Metric: training interactions (triplets) per second.
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is produced.
+
+Beside the headline the line carries, each with its own `roofline` block:
+  neumf            BASELINE.json configs[0] (NeuMF, ML-1M shape, batch 16 384): the reference class graph (numFactor 32,
+                   BatchNorm, dropout) as ONE cooperative tcgen05 launch per step, device value / hot / host-fed e2e;
+  neumf_he         the He et al. variant configs[0] names (8-dim Hadamard GMF + MLP 64-32-16-8);
+  extras           (N = 1) two-tower, full-catalog top-K, NeuMF at configs[3] table sizes on one GPU, biased SVD;
+  c4_neumf_sharded (N > 1) BASELINE.json configs[3]: 20 M x 2 M x 64 tables row-sharded over the ranks, rows and row
+                   gradients exchanged inside the fused kernels over NVLink peer memory, local batch 65 536;
+  c5_topk_sharded  (N > 1) BASELINE.json configs[4]: 1 M users x 2 M items, items range-sharded, lists merged;
+  parity_multi     (N > 1) the data-parallel and row-sharded paths against a single-GPU run of the same global batches,
+                   computed inside this very run (the driver's GPU test lease has one GPU);
+  parity_check     (N = 1) per-step losses of the product against the CPU oracle's on the same seeds.
+The oracle never runs in this process: every CPU leg is a subprocess (`--impl cpu_legs`), so the product process maps
+nothing under oracle/.
 """
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -150,6 +165,52 @@ def cpu_loop(users, items, U, I, steps, warmup, time_budget_s=None):
             break
     dt = time.perf_counter() - t0
     return done * BATCH / dt, done, threads, dt
+
+
+PARITY_STEPS = 20
+
+
+def cpu_parity_losses(users, items, U, I):
+    """Per-step losses of the oracle port on batches 0..19 of the bench frame from the seeded initial weights: the
+    product arm runs the same 20 steps (same Philox negatives, seed 7 epoch 0) and reports the largest difference."""
+    from oracle import bpr as OB, bpr_torch as OT, philox as OP
+    orc = OB.BPROracle(U, I, DIM, seed=42)
+    model = OT.BPRTorchCPU(orc.user, orc.item)
+    indptr, sitems = OP.build_csr(users, items, U)
+    neg = OP.bpr_negatives(users[:PARITY_STEPS * BATCH], 7, 0, I, indptr, sitems)
+    out = []
+    for b in range(PARITY_STEPS):
+        sl = slice(b * BATCH, (b + 1) * BATCH)
+        out.append(float(model.step(users[sl], items[sl], neg[sl])))
+    return out
+
+
+def cpu_legs_main(args):
+    """`--impl cpu_legs` (a subprocess of the product arm, rank 0, N = 1): every oracle CPU leg of the line, as one JSON
+    object on stdout.  Bounded samples (about 25 s in all) of the same workloads, all host threads."""
+    users, items, U, I = make_workload()
+    out = {}
+    val, done, threads, dt = cpu_loop(users, items, U, I, steps=100000, warmup=3, time_budget_s=10.0)
+    out["bpr"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                  "sample": f"{done} full batches of {BATCH} triplets in {dt:.1f} s, torch-CPU oracle port of the reference "
+                            f"loop (not TensorFlow)"}
+    out["bpr_parity_losses"] = cpu_parity_losses(users, items, U, I)
+    out.update(extras_cpu_baselines())
+    out["svd_fit"] = svd_cpu_baseline()
+    print(json.dumps(out), flush=True)
+
+
+def run_cpu_legs():
+    """Runs the CPU legs in a child process and returns its JSON (None when it fails: the line then says so)."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu_legs"], capture_output=True, text=True,
+                           timeout=600, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    except Exception as e:  # pragma: no cover
+        return {"error": repr(e)}
 
 
 def reference_arm(args):
@@ -325,12 +386,28 @@ def product_arm(args):
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * e2e_wall)
     clocks = sampler.stop()
     assert np.isfinite(hloss[W:W + K].numpy()).all()
-    extras = secondary_measurements(dev) if (world == 1 and not args.no_extras) else None
-    if extras is not None:
-        extras["svd_fit"] = svd_measurement(dev, cpu_baseline=not args.no_cpu_baseline)
-        if rank == 0 and not args.no_cpu_baseline:
-            for key, cb in extras_cpu_baselines().items():       # cpu_baseline legs of the secondary measurements
-                extras.setdefault(key, {"config": "CPU leg only"})["cpu_baseline"] = cb
+    peaks, peak_src = load_peaks()
+    # ---- (4) parity: the first 20 steps of the workload from the seeded initial weights, product vs CPU oracle -----------
+    parity_losses = None
+    if world == 1:
+        pnet = BPRNet(U, I, DIM, seed=42, learning_rate=1e-3, sparse_adam="keras", device=dev)
+        pnet.set_training_pairs(users, items)
+        pnet.sample_negatives(7, 0)
+        parity_losses = pnet.train_steps(list(range(PARITY_STEPS)), BATCH).cpu().numpy().astype(np.float64)
+        del pnet
+    # ---- (5) the other BASELINE.json configs ------------------------------------------------------------------------
+    blocks = {}
+    if not args.no_extras:
+        if world == 1:
+            blocks["neumf"] = neumf_block(dev, peaks, "class")
+            blocks["neumf_he"] = neumf_block(dev, peaks, "he")
+            blocks["extras"] = secondary_measurements(dev, peaks)
+            blocks["extras"]["svd_fit"] = svd_measurement(dev)
+        else:
+            blocks["parity_multi"] = parity_multi_block(dev, world, rank)
+            blocks["c4_neumf_sharded"] = c4_sharded_block(dev, world, rank, peaks)
+            blocks["c5_topk_sharded"] = c5_topk_block(dev, world, rank, peaks)
+    cpu = run_cpu_legs() if (world == 1 and rank == 0 and not args.no_cpu_baseline) else None
 
     # ---- max over ranks ---------------------------------------------------------------------------
     t = torch.tensor([total_ms, hot_ms, e2e_ms, float(fb_ms.mean())], dtype=torch.float64, device=dev)
@@ -339,7 +416,6 @@ def product_arm(args):
     total_ms, hot_ms, e2e_ms, fb_mean_ms = (float(x) for x in t.tolist())
 
     if rank == 0:
-        peaks, peak_src = load_peaks()
         value = world * K * BATCH / (total_ms * 1e-3)
         adam_bytes = 32 * (U + I) * DIM                     # w,m,v read+write, g read, g zeroed: 32 B per element
         launch_bytes = BYTES_PER_TRIPLET * BATCH + (adam_bytes // world if (world == 1 or net.peer is not None) else 0)
@@ -399,13 +475,28 @@ def product_arm(args):
                 line["e2e_copy"], line["e2e"] = line["e2e"], zc
             else:
                 line["e2e_zero_copy"] = zc
-        if extras:
-            line["extras"] = extras
-        if world == 1 and not args.no_cpu_baseline:
-            val, done, threads, dt = cpu_loop(users, items, U, I, steps=100000, warmup=3, time_budget_s=12.0)
-            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{done} full batches of {BATCH} triplets in {dt:.1f} s, torch-CPU "
-                                              f"oracle port of the reference loop (not TensorFlow)"}
+        line.update(blocks)
+        if cpu is not None:
+            if "error" in cpu:
+                line["cpu_baseline"] = {"error": cpu["error"]}
+            else:
+                line["cpu_baseline"] = cpu["bpr"]
+                ref = np.asarray(cpu["bpr_parity_losses"], dtype=np.float64)
+                line["parity_check"] = {
+                    "what": f"per-step loss of the first {PARITY_STEPS} steps of this workload from the seeded initial weights "
+                            f"(same frame, same Philox negatives): product (bpr_steps_coop on the GPU) vs the CPU oracle "
+                            f"(subprocess)",
+                    "max_abs_loss_diff": float(np.abs(parity_losses - ref).max()),
+                    "max_rel_loss_diff": float((np.abs(parity_losses - ref) / np.abs(ref)).max()),
+                    "loss_first": float(parity_losses[0]), "loss_last": float(parity_losses[-1]),
+                    "tolerance": "fp32: 1e-5 relative per step (tests/test_gpu_fullsize.py holds the same run to it)"}
+                for key, blk in (("neumf", line.get("neumf")), ("neumf_he", line.get("neumf_he"))):
+                    if blk is not None and key + "_train" in cpu:
+                        blk["cpu_baseline"] = cpu[key + "_train"]
+                ex = line.get("extras") or {}
+                for key in ("neumf_train_reference_batch", "twotower_train", "topk_ml1m", "svd_fit"):
+                    if key in cpu:
+                        ex.setdefault(key, {"config": "CPU leg only"})["cpu_baseline"] = cpu[key]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -413,9 +504,9 @@ def product_arm(args):
 
 def extras_cpu_baselines(budget_s=2.5):
     """The oracle (torch-CPU restatement of the reference, all host threads; NOT TensorFlow) timed on bounded samples
-    of the other BASELINE.json configs, keyed like `extras`: NeuMF at the bench batch and at the reference's own batch
-    of 128 (NeuMFModel.py:102), the two-tower step at its batch of 1000 (twoTower.py:292), full-catalog top-K as the
-    reference evaluates it (matmul + top_k in 5000-user batches, twoTower.py:293)."""
+    of the other BASELINE.json configs: NeuMF (class graph and He et al. variant) at the bench batch and the class graph
+    at the reference's own batch of 128 (NeuMFModel.py:102), the two-tower step at its batch of 1000 (twoTower.py:292),
+    full-catalog top-K as the reference evaluates it (matmul + top_k in 5000-user batches, twoTower.py:293)."""
     from oracle import neumf as ON, twotower as OTT
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
@@ -431,12 +522,14 @@ def extras_cpu_baselines(budget_s=2.5):
         dt = time.perf_counter() - t0
         return units * n / dt, n, dt
 
-    for B, key in ((BATCH, "neumf_train"), (128, "neumf_train_reference_batch")):
-        orc = ON.NeuMFOracle(U, I, emb=32, dropout=0.0)                 # no dropout: the oracle's NumPy Philox masks would dominate
+    for B, key, kw, what in ((BATCH, "neumf_train", {}, "NeuMF F=32 class graph"),
+                             (BATCH, "neumf_he_train", dict(mf_dim=8, mf_mode="hadamard", batch_norm=False), "He et al. variant"),
+                             (128, "neumf_train_reference_batch", {}, "NeuMF F=32 class graph")):
+        orc = ON.NeuMFOracle(U, I, emb=32, dropout=0.0, **kw)            # no dropout: the oracle's NumPy Philox masks would dominate
         u = rng.integers(0, U, B); i = rng.integers(0, I, B); y = (rng.random(B) < 0.2).astype(np.float32)
         v, n, dt = timed(lambda: orc.step(u, i, y), B)
         out[key] = {"value": v, "unit": "interactions/s", "cores": threads, "kind": "port",
-                    "sample": f"{n} steps of batch {B} in {dt:.1f} s, NeuMF F=32 oracle (autograd + exact Keras Adam, dropout off), fp32"}
+                    "sample": f"{n} steps of batch {B} in {dt:.1f} s, {what} oracle (autograd + exact Keras Adam, dropout off), fp32"}
     tt = OTT.TwoTowerOracle(U, I, 128, 128)
     u = rng.integers(2, U + 2, 1000); i = rng.integers(2, I + 2, 1000)
     v, n, dt = timed(lambda: tt.step(u, i, cand_ids=i), 1000)
@@ -453,9 +546,29 @@ def extras_cpu_baselines(budget_s=2.5):
     return out
 
 
-def svd_measurement(dev, cpu_baseline=True):
+def svd_cpu_baseline():
+    """The sequential C loop of the oracle on the same rating file as svd_measurement (1 core: the algorithm is sequential)."""
+    from binrec_b200 import synth
+    from oracle import svd as OS
+    u, i = synth.make_interactions()
+    r = np.random.default_rng(5).integers(1, 6, len(u)).astype(np.float64)
+    U, I, d = synth.ML1M_USERS, synth.ML1M_ITEMS, 50
+    rng = np.random.default_rng(0)
+    Pc, Qc = rng.normal(0, 0.1, (U, d)), rng.normal(0, 0.1, (I, d))
+    buc, bic = np.zeros(U), np.zeros(I)
+    mu = float(r.mean())
+    OS.build_c()
+    OS.fit_epoch_c(u[:1000], i[:1000], r[:1000], Pc, Qc, buc, bic, mu, 0.01, 0.0, 0.01)
+    t0 = time.perf_counter()
+    OS.fit_epoch_c(u, i, r, Pc, Qc, buc, bic, mu, 0.01, 0.0, 0.01)
+    t = time.perf_counter() - t0
+    return {"value": len(u) / t, "unit": "ratings/s", "cores": 1, "kind": "port",
+            "sample": "one full epoch of the same file, sequential C loop (oracle/svd_c.c, gcc -O2)"}
+
+
+def svd_measurement(dev):
     """Biased-SVD epoch on the ML-1M-shaped file, the reference's d = 50, float64, exact
-    sequential semantics; the sequential C loop of the oracle timed beside it (1 core: the algorithm is sequential)."""
+    sequential semantics.  Bound: the longest dependency chain x one L2 hand-over."""
     from binrec_b200 import SVD as S
     from binrec_b200 import synth
     u, i = synth.make_interactions()
@@ -476,94 +589,179 @@ def svd_measurement(dev, cpu_baseline=True):
     S.check_fit(frame)
     s = e0.elapsed_time(e1) * 1e-3 / iters
     chain = frame.critical_path()
-    out = {"value": len(u) / s, "unit": "ratings/s", "ms_per_epoch": s * 1e3, "critical_path": chain,
-           "ns_per_chain_link": s * 1e9 / chain,
-           "config": f"biased SVD (SVD.py:187-221), {len(u)} ratings in file order, {U} x {I}, d={d}, float64, "
-                     f"sequential semantics kept exactly (ticketed rows, one cooperative launch per epoch)"}
-    if cpu_baseline:
-        from oracle import svd as OS                                    # cpu_baseline leg: the checker, timed
-        Pc, Qc = P.cpu().numpy().copy(), Q.cpu().numpy().copy()
-        buc, bic = bu.cpu().numpy().copy(), bi.cpu().numpy().copy()
-        OS.fit_epoch_c(u[:1000], i[:1000], r[:1000], Pc, Qc, buc, bic, mu, 0.01, 0.0, 0.01)
-        t0 = time.perf_counter()
-        OS.fit_epoch_c(u, i, r, Pc, Qc, buc, bic, mu, 0.01, 0.0, 0.01)
-        t = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": len(u) / t, "unit": "ratings/s", "cores": 1, "kind": "port",
-                               "sample": "one full epoch of the same file, sequential C loop (oracle/svd_c.c, gcc -O2)"}
+    return {"value": len(u) / s, "unit": "ratings/s", "ms_per_epoch": s * 1e3, "critical_path": chain,
+            "ns_per_chain_link": s * 1e9 / chain,
+            "roofline": {"bound": "latency", "kernel": "svd_epoch_kernel", "achieved": s * 1e9 / chain, "unit": "ns per chain link",
+                         "note": "neither HBM nor tensor: longest per-row dependency chain x one L2 hand-over (~1 us)"},
+            "config": f"biased SVD (SVD.py:187-221), {len(u)} ratings in file order, {U} x {I}, d={d}, float64, "
+                      f"sequential semantics kept exactly (ticketed rows, one cooperative launch per epoch)"}
+
+
+def _timed(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / iters
+
+
+def _hbm_roofline(kernel, bytes_per_launch, seconds, peaks, note):
+    a = bytes_per_launch / seconds / 1e9
+    return {"bound": "hbm", "kernel": kernel, "achieved": a, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": a / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": int(bytes_per_launch), "avg_launch_ms": seconds * 1e3,
+            "traffic": None, "note": note}
+
+
+def _tensor_roofline(kernel, flops, seconds, peaks, note):
+    a = flops / seconds / 1e12
+    pk = peaks.get("bf16_tflops", 1590.0)
+    return {"bound": "tensor", "kernel": kernel, "achieved": a, "peak": pk, "unit": "TFLOP/s", "frac": a / pk,
+            "flops_per_launch": float(flops), "avg_launch_ms": seconds * 1e3, "traffic": None, "note": note}
+
+
+def neumf_block(dev, peaks, which):
+    """BASELINE.json configs[0]: NeuMF on the ML-1M-shaped frame (1 000 209 positives + 4 Philox negatives each, labels
+    1 / 0, one seeded row shuffle: NeuMFModel.bootstrapDataset), batch 16 384, exact Keras Adam.  which = "class": the
+    reference's graph (numFactor 32: MLP 64-32-16-8, BatchNorm after the activations, dropout 0.2, scalar Dot, MSE;
+    NeuMFModel.py:53-100); "he": the He et al. variant the config line names (8-dim Hadamard GMF, no BatchNorm / dropout).
+    One cooperative tcgen05 launch per step (csrc/neumf_fused.cu): gather, three Dense layers forward and backward on the
+    tensor cores (TF32 operands), loss, row-gradient REDs, Adam over every parameter."""
+    from binrec_b200 import synth
+    from binrec_b200.NeuMFModel import NeuMFNet, NeuMFDataset
+    U, I, B = synth.ML1M_USERS, synth.ML1M_ITEMS, BATCH
+    users, items = synth.make_interactions()
+    ds = NeuMFDataset(users, items, 4.0, B, True, dev, seed=7)
+    nb = ds.n // B
+    if which == "class":
+        net = NeuMFNet(U, I, 32, dropout=0.2, device=dev, tensor_cores=True)
+        emf, per_fwd = 32, 528                                   # SURVEY 8d: 4 rows x 128 B + ids/label 12 B + prediction 4 B
+        kernel = "nfz::fused_step<Spec<32,32,32,16,8,relu,BN,dot>> (whole step incl. Adam)"
+    else:
+        net = NeuMFNet(U, I, 32, dropout=0.0, device=dev, mf_dim=8, mf_mode="hadamard", batch_norm=False)
+        emf, per_fwd = 8, 336
+        kernel = "nfz::fused_step<Spec<32,8,32,16,8,relu,noBN,hadamard>> (whole step incl. Adam)"
+    o = torch.empty(B, device=dev); l = torch.empty(1, device=dev)
+    K, W = 200, 5
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+    sink = torch.empty((), dtype=torch.float32, device=dev)
+
+    def step(k):
+        b = k % nb
+        sl = slice(b * B, (b + 1) * B)
+        net.train_on_batch(ds.u[sl], ds.i[sl], ds.y[sl], first_index=b * B, epoch=0, out=o, loss_out=l)
+
+    for k in range(W):
+        step(k)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+    torch.cuda.synchronize()
+    for k in range(K):                                          # L2 flushed between steps, events around the step's one kernel
+        flush.zero_(); torch.sum(flush, dim=0, out=sink)
+        evs[k][0].record(); step(W + k); evs[k][1].record()
+    torch.cuda.synchronize()
+    cold = float(np.mean([a.elapsed_time(b) for a, b in evs])) * 1e-3
+    hot = _timed(lambda: step(0), 200)
+    # end to end: the frame in pinned HOST memory, one H2D copy of 12 B x batch per step, losses back in one D2H copy
+    nh = min(nb, 64)
+    packed = NeuMFNet.pack_host_batches(ds.u[:nh * B].cpu().numpy(), ds.i[:nh * B].cpu().numpy(), ds.y[:nh * B].cpu().numpy(), B)
+    order = np.arange(K) % nh
+    net.train_steps_from_host(packed, order[:W])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(); hl = net.train_steps_from_host(packed, order); e1.record()
+    torch.cuda.synchronize()
+    e2e = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0) / K
+    assert np.isfinite(hl.numpy()).all()
+    n_tab = (U + I) * (32 + emf)
+    n_dense = net.dense.w.numel()
+    bytes_step = B * (per_fwd + 4 * 4 * (32 + emf) // 2 * 2) + 32 * (n_tab + n_dense)
+    # row gradients: the same sum 4 d_t bytes as the gather (SURVEY 8d), REDs resolved in L2
+    out = {"metric": "train interactions/sec (NeuMF, ML-1M shape, batch 16384)", "value": B / cold, "unit": "interactions/s",
+           "ms_per_step": cold * 1e3, "value_hot_l2": B / hot, "steps": K, "gpu_launches": K,
+           "e2e": {"value": B / e2e, "unit": "interactions/s", "h2d_bytes_per_step": 12 * B, "d2h_bytes_per_step": 4,
+                   "note": "NeuMFNet.train_steps_from_host (brk_neumf_train_steps_host): pinned batch-major host frame, one "
+                           "cudaMemcpyAsync per step on a copy stream (4 staging slots), the fused step, one D2H copy of the K losses"},
+           "roofline": _hbm_roofline(kernel, bytes_step, cold, peaks,
+                                     "per step: B x (gather + ids/label/prediction + row gradients) + 32 B x every parameter "
+                                     "for the exact Keras Adam pass; the 2.5 MB of tables (10 MB with m, v, g) are L2-resident, "
+                                     "the step is bound by its grid barriers and L2 round trips (profiles/r02_neumf_fused_trace.txt), "
+                                     "not by HBM; tensor pipe < 1 % busy by construction (16 kFLOP per interaction)"),
+           "config": {"workload": "BASELINE.json configs[0]: " + ("NeuMF class graph numFactor 32 (MLP 64-32-16-8, BN, dropout 0.2, "
+                                                                   "scalar Dot, MSE)" if which == "class" else
+                                                                   "He et al. NeuMF (MLP 64-32-16-8 on 32-dim tables + 8-dim Hadamard GMF, "
+                                                                   "head 16->1, MSE)") +
+                                  ", ML-1M shape, 4 negatives / positive, Keras Adam(1e-3)", "batch": B,
+                      "l2": "flushed between timed steps (value); back to back (value_hot_l2)",
+                      "dtype": "tf32 operands, fp32 accumulation / parameters"}}
+    del net, ds
+    torch.cuda.empty_cache()
     return out
 
 
-def secondary_measurements(dev):
-    """Other BASELINE.json configs on one GPU, short runs (CUDA events, back-to-back steps): NeuMF
-    (configs[0] shape), two-tower in-batch softmax + full-catalog top-K (configs[2])."""
+def secondary_measurements(dev, peaks):
+    """Other BASELINE.json configs on one GPU, short runs (CUDA events, back-to-back steps), each with its roofline."""
     from binrec_b200 import hotpath as H
     from binrec_b200.NeuMFModel import NeuMFNet
     from binrec_b200.twoTower import TwoTowerModel
     out = {}
-
-    def timed(fn, iters, warm=3):
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record(); torch.cuda.synchronize()
-        return e0.elapsed_time(e1) * 1e-3 / iters
-
     g = torch.Generator(device=dev); g.manual_seed(0)
     U, I, B = 6040, 3706, BATCH
-    net = NeuMFNet(U, I, 32, dropout=0.2, device=dev)
-    u = torch.randint(0, U, (B,), generator=g, device=dev, dtype=torch.int32)
-    i = torch.randint(0, I, (B,), generator=g, device=dev, dtype=torch.int32)
-    y = (torch.rand(B, generator=g, device=dev) < 0.2).float()
-    o = torch.empty(B, device=dev); l = torch.empty(1, device=dev)
-    s = timed(lambda: net.train_on_batch(u, i, y, out=o, loss_out=l), 50)
-    out["neumf_train"] = {"value": B / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
-                          "config": "NeuMF F=32 (MLP 64-32-16-8, BN, dropout 0.2, MSE), ML-1M tables, batch 16384, Keras Adam, "
-                                    "fp32 on the CUDA cores (csrc/neumf2.cu)"}
-    # the reference's own batch size (bootstrapDataset default 128, NeuMFModel.py:102): fit's inner loop over a resident
-    # frame, one C call for all steps (brk_neumf_train_steps)
+    # the reference's own batch size (bootstrapDataset default 128, NeuMFModel.py:102): fit's inner loop over a resident frame
+    net = NeuMFNet(U, I, 32, dropout=0.2, device=dev, tensor_cores=True)
     Br, steps_r = 128, 400
     ur = torch.randint(0, U, (Br * steps_r,), generator=g, device=dev, dtype=torch.int32)
     ir = torch.randint(0, I, (Br * steps_r,), generator=g, device=dev, dtype=torch.int32)
     yr = (torch.rand(Br * steps_r, generator=g, device=dev) < 0.2).float()
     order_r = np.arange(steps_r)
-    s = timed(lambda: net.train_steps(ur, ir, yr, Br, order_r), 3, warm=1) / steps_r
+    s = _timed(lambda: net.train_steps(ur, ir, yr, Br, order_r), 3, warm=1) / steps_r
     out["neumf_train_reference_batch"] = {"value": Br / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
-                                          "config": "NeuMF F=32 as above at the reference's batch of 128: latency-bound "
-                                                    "(six dependent kernels on one or two CTAs each)"}
+                                          "roofline": {"bound": "latency", "note": "one 128-sample tile: a single CTA's chain of "
+                                                       "phases plus the dense Adam pass; launch- and latency-bound"},
+                                          "config": "NeuMF F=32 class graph at the reference's batch of 128, one launch per step"}
     del net
-    for E, tag in ((32, "neumf_train_tc"), (64, "neumf64_train_tc")):
-        Bn = 65536
-        net = NeuMFNet(U, I, E, dropout=0.2, device=dev, tensor_cores=True)
-        u = torch.randint(0, U, (Bn,), generator=g, device=dev, dtype=torch.int32)
-        i = torch.randint(0, I, (Bn,), generator=g, device=dev, dtype=torch.int32)
-        y = (torch.rand(Bn, generator=g, device=dev) < 0.2).float()
-        o = torch.empty(Bn, device=dev); l = torch.empty(1, device=dev)
-        s = timed(lambda: net.train_on_batch(u, i, y, out=o, loss_out=l), 30)
-        flops = 3 * 2 * (2 * E * E + E * E // 2 + E * E // 8 + E // 4 + 1)      # fwd + two backward products per Dense layer
-        out[tag] = {"value": Bn / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
-                    "mlp_tflops": flops * Bn / s / 1e12,
-                    "config": f"NeuMF F={E} (MLP {2 * E}-{E}-{E // 2}-{E // 4}, BN, dropout 0.2, MSE), ML-1M tables, batch {Bn}, "
-                              f"Keras Adam, Dense products on tcgen05 (TF32 operands, fp32 accumulation; csrc/neumf_tc.cu)"}
-        del net
+    # fp32 CUDA-core path of the same step (neumf2.cu + Adam) for comparison
+    net = NeuMFNet(U, I, 32, dropout=0.2, device=dev)
+    u = torch.randint(0, U, (B,), generator=g, device=dev, dtype=torch.int32)
+    i = torch.randint(0, I, (B,), generator=g, device=dev, dtype=torch.int32)
+    y = (torch.rand(B, generator=g, device=dev) < 0.2).float()
+    o = torch.empty(B, device=dev); l = torch.empty(1, device=dev)
+    s = _timed(lambda: net.train_on_batch(u, i, y, out=o, loss_out=l), 50)
+    out["neumf_train_fp32"] = {"value": B / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
+                               "config": "NeuMF F=32 class graph, batch 16384, fp32 on the CUDA cores (csrc/neumf2.cu, five kernels + Adam)"}
+    del net
+    # NeuMF at BASELINE.json configs[3] table sizes on ONE GPU (20 M x 2 M x 64, lazy Adam, batch 65 536): the five-kernel
+    # tensor-core path (the batch does not fit on chip) -- the per-rank work of the row-sharded run
+    try:
+        from binrec_b200.sharded import ShardedNeuMFNet
+        Uc, Ic, Bc = 20_000_000, 2_000_000, 65536
+        netc = ShardedNeuMFNet(Uc, Ic, 64, dropout=0.2, device=dev, mode="peer", tensor_cores=True)
+        us = torch.randint(0, Uc, (4, Bc), generator=g, device=dev, dtype=torch.int32)
+        its = torch.randint(0, Ic, (4, Bc), generator=g, device=dev, dtype=torch.int32)
+        yc = (torch.rand((4, Bc), generator=g, device=dev) < 0.2).float()
+        oc = torch.empty(Bc, device=dev); lc = torch.empty(1, device=dev)
+        kk = [0]
+
+        def cstep():
+            k = kk[0]; kk[0] += 1
+            netc.train_on_batch(us[k % 4], its[k % 4], yc[k % 4], first_index=k * Bc, epoch=0, out=oc, loss_out=lc)
+
+        s = _timed(cstep, 20)
+        per = 1040 + 1024 + 1024 + 4 * 1792                       # fwd + re-gather + row gradients + lazy Adam on ~4 unique rows
+        out["neumf_c4_one_gpu"] = {"value": Bc / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
+                                   "roofline": _hbm_roofline("ntc::tc_fwd1/fwd2/head/bwd2/bwd1 + adam_rows_kernel (whole step)", Bc * per, s, peaks,
+                                                             "per interaction: 1040 B forward + 1024 B re-gather + 1024 B row gradients "
+                                                             "+ 4 x 1792 B lazy Adam (SURVEY 8d); tables 33.8 GB, HBM-resident"),
+                                   "config": "NeuMF E=64 (MLP 128-64-32-16), 20M x 2M tables on ONE GPU, batch 65536, lazy Adam, TF32 tensor cores"}
+        del netc, us, its, yc
+        torch.cuda.empty_cache()
+    except Exception as e:  # pragma: no cover - memory pressure on a shared box
+        out["neumf_c4_one_gpu"] = {"error": repr(e)[:200]}
     users = list(range(U)); items = list(range(I))
-    tt = TwoTowerModel(128, I, U, "u", "i", users, items, semb=128, device=dev)
-    tt.compile("Adagrad", learningRate=0.1)
-    Bt = 1000
-    uid = torch.randint(2, U + 2, (Bt,), generator=g, device=dev, dtype=torch.int32)
-    iid = torch.randint(2, I + 2, (Bt,), generator=g, device=dev, dtype=torch.int32)
-
-    def tt_step():
-        tt._step(uid, iid, None, True)
-        tt.optimizer.apply([tt.userTower.emb, tt.itemTower.emb], dense=[tt.userTower.dense, tt.itemTower.dense])
-
-    s = timed(tt_step, 50)
-    out["twotower_train"] = {"value": Bt / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
-                             "config": "two-tower E=S=128, in-batch softmax batch 1000 (twoTower.py:292), Adagrad 0.1, fp32 SGEMM"}
-    for Bt2, tag in ((1000, "twotower_train_tc"), (8192, "twotower_train_tc_b8192")):
+    for Bt2, tag in ((1000, "twotower_train"), (8192, "twotower_train_b8192")):
         tt2 = TwoTowerModel(128, I, U, "u", "i", users, items, semb=128, device=dev, tensor_cores=True)
         tt2.compile("Adagrad", learningRate=0.1)
         uid2 = torch.randint(2, U + 2, (Bt2,), generator=g, device=dev, dtype=torch.int32)
@@ -573,12 +771,8 @@ def secondary_measurements(dev):
             tt2._step(uid2, iid2, None, True)
             tt2.optimizer.apply([tt2.userTower.emb, tt2.itemTower.emb], dense=[tt2.userTower.dense, tt2.itemTower.dense])
 
-        s = timed(tt2_step, 30)
-        out[tag] = {"value": Bt2 / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
-                    "config": f"two-tower E=S=128, in-batch softmax batch {Bt2}, Adagrad 0.1, every Dense / in-batch product on "
-                              f"tcgen05 (TF32 operands, fp32 accumulation; csrc/gemm_tc.cu); the two tower chains forked "
-                              f"onto two streams inside brk_twotower_step"}
-        # the same step as TwoTowerModel.fit runs it: one CUDA-graph replay per batch
+        tt2_step()
+        # the step as TwoTowerModel.fit runs it: one CUDA-graph replay per batch
         side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             tt2_step()
@@ -586,24 +780,202 @@ def secondary_measurements(dev):
         gph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gph):
             tt2_step()
-        s = timed(gph.replay, 30)
-        out[tag + "_graph"] = {"value": Bt2 / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
-                               "config": out[tag]["config"] + "; replayed as one CUDA graph per step (what TwoTowerModel.fit does)"}
+        s = _timed(gph.replay, 30)
+        flops = 2.0 * Bt2 * 128 * 128 * 2 * 3 + 2.0 * Bt2 * Bt2 * 128 * 3   # two tower Dense layers and the B x B scores, fwd + 2 bwd products each
+        out[tag] = {"value": Bt2 / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
+                    "roofline": _tensor_roofline("gemm_tf32_kernel x 9 + inbatch_softmax_kernel (graph of one step)", flops, s, peaks,
+                                                 "TF32 products against the bf16 peak (TF32 dense peak is half of it); at batch 1000 the "
+                                                 "step is a chain of 8 dependent ~6 us kernels, at 8192 it is bound by the B x B score matrix"),
+                    "config": f"two-tower E=S=128 (twoTower.py:40-41 shape), in-batch softmax batch {Bt2}, Adagrad 0.1, all products on tcgen05 "
+                              f"(TF32), replayed as one CUDA graph per step (what TwoTowerModel.fit does)"}
         del tt2, gph
     Q = torch.randn(U, 128, generator=g, device=dev); Cm = torch.randn(I, 128, generator=g, device=dev)
     idx = H.BruteForceIndex(10).index(Cm)
-    s = timed(lambda: idx(Q), 50)
+    s = _timed(lambda: idx(Q), 50)
     out["topk_ml1m"] = {"value": U / s, "unit": "users/s", "ms": s * 1e3,
+                        "roofline": _tensor_roofline("score_topk_kernel", 2.0 * U * I * 128, s, peaks,
+                                                     "one wave of 48 CTAs: launch / latency bound at this size"),
                         "config": "6040 users x 3706 items, d=128, k=10, bf16 tcgen05 scoring + fused top-K (incl. query bf16 conversion)"}
     Ub, Ib = 65536, 250000
-    Q = torch.randn(Ub, 64, generator=g, device=dev); Cm = torch.randn(Ib, 64, generator=g, device=dev)
-    idx = H.BruteForceIndex(10).index(Cm)
-    s = timed(lambda: idx(Q), 5, warm=1)
-    peaks, _ = load_peaks()
-    out["topk_shard"] = {"value": Ub / s, "unit": "users/s", "ms": s * 1e3,
-                         "tensor_tflops": 2.0 * Ub * Ib * 64 / s / 1e12,
-                         "frac_of_measured_bf16_peak": 2.0 * Ub * Ib * 64 / s / 1e12 / peaks.get("bf16_tflops", 1590.0),
-                         "config": "65536 users x 250000 items (one 8-way item shard of BASELINE.json configs[4]), d=64, k=10"}
+    for d in (64, 128):
+        Q = torch.randn(Ub, d, generator=g, device=dev); Cm = torch.randn(Ib, d, generator=g, device=dev)
+        idx = H.BruteForceIndex(10).index(Cm)
+        s = _timed(lambda: idx(Q), 5, warm=1)
+        out[f"topk_shard_d{d}"] = {"value": Ub / s, "unit": "users/s", "ms": s * 1e3,
+                                   "roofline": _tensor_roofline("score_topk_kernel", 2.0 * Ub * Ib * d, s, peaks,
+                                                                "bound by the TMEM read rate of the selection epilogue (16 scores / clk / SM = "
+                                                                f"{2 * d * 4.5e12 / 1e12:.0f} TFLOP/s at d = {d}), DESIGN.md section 4.1"),
+                                   "config": f"65536 users x 250000 items (one 8-way item shard of BASELINE.json configs[4]), d={d}, k=10"}
+        del Q, Cm, idx
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# N > 1: the partitioning BASELINE.json north_star asks for, and parity inside the same run
+# ------------------------------------------------------------------------------------------------
+def c4_sharded_block(dev, world, rank, peaks):
+    """BASELINE.json configs[3]: NeuMF E=64 with 20 M x 2 M x 64 tables ROW-SHARDED over the ranks (row r on rank r % G);
+    local batch 65 536 per GPU (weak scaling).  The fused kernels gather peer rows with plain loads and send row
+    gradients as 16-byte REDs into the owner's accumulator over NVLink: the all-to-all of rows and of row gradients
+    happens inside the gather / scatter instructions; then a peer barrier, lazy Adam on the owned shards and the fused
+    reduce-scatter + Adam + all-gather of the mirrored dense block (csrc/dp_peer.cu)."""
+    import torch.distributed as dist
+    from binrec_b200.sharded import ShardedNeuMFNet
+    U, I, E, B, K = 20_000_000, 2_000_000, 64, 65536, 20
+    net = ShardedNeuMFNet(U, I, E, dropout=0.2, device=dev, mode="peer", tensor_cores=True)
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    nb = 8
+    us = torch.randint(0, U, (nb, B), generator=g, device=dev, dtype=torch.int32)
+    its = torch.randint(0, I, (nb, B), generator=g, device=dev, dtype=torch.int32)
+    y = (torch.rand((nb, B), generator=g, device=dev) < 0.2).float()
+    o = torch.empty(B, device=dev); l = torch.empty(1, device=dev)
+
+    def step(k):
+        net.train_on_batch(us[k % nb], its[k % nb], y[k % nb], first_index=k * B * world, epoch=0, out=o, loss_out=l)
+
+    for k in range(3):
+        step(k)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        step(3 + k)
+    e1.record(); torch.cuda.synchronize()
+    net.check()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    s = float(t.item()) * 1e-3 / K
+    loss = float(l.item())
+    del net, us, its, y
+    torch.cuda.empty_cache()
+    per_hbm = 1040 + 1024 + 1024 + 4 * 1792                        # as on one GPU (SURVEY 8d)
+    per_link = (world - 1) / world * (4 * 4 * E + 16) * 3          # rows out (fwd + re-gather) and row gradients back
+    t_hbm = B * per_hbm / (peaks["hbm_gbs"] * 1e9)
+    t_link = B * per_link / 770e9
+    return {"metric": "train interactions/sec (NeuMF E=64, 20M x 2M tables row-sharded)", "value": world * B / s,
+            "unit": "interactions/s", "n_gpus": world, "ms_per_step": s * 1e3, "steps": K, "scaling": "weak", "loss": loss,
+            "roofline": {"bound": "hbm+nvlink", "kernel": "ntc::tc_* on peer-mapped shards + adam_rows_kernel + dp_adam_peer_kernel (whole step, per rank)",
+                         "achieved": B * per_hbm / s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": B * per_hbm / s / 1e9 / peaks["hbm_gbs"],
+                         "nvlink_bytes_per_step_per_gpu": int(B * per_link), "nvlink_achieved_gbs": B * per_link / s / 1e9,
+                         "nvlink_peak_gbs": 770.0, "nvlink_frac": B * per_link / s / 1e9 / 770.0,
+                         "target_ms": max(t_hbm, t_link) * 1e3, "frac_of_target": max(t_hbm, t_link) / s, "traffic": None,
+                         "note": "per interaction: HBM 1040 + 1024 + 1024 + 4 x 1792 B at the owners; NVLink (G-1)/G x (sum 4 d_t + 16) B "
+                                 "each for the forward rows, the backward re-gather and the row gradients (SURVEY 8d); target = the "
+                                 "slower of HBM bytes / measured copy peak and NVLink bytes / 770 GB/s"},
+            "config": {"workload": "BASELINE.json configs[3]: NeuMF E=64 (MLP 128-64-32-16, BN, dropout 0.2), 20M users x 2M items, "
+                                   "uniform ids, lazy Adam", "local_batch": B,
+                       "parallelism": f"tables row-sharded x{world} (owner = id mod G) in NVLink peer-mapped memory; dense block mirrored"}}
+
+
+def c5_topk_block(dev, world, rank, peaks):
+    """BASELINE.json configs[4]: 1 M users x 2 M items, d = 64, k = 10; items RANGE-SHARDED over the ranks, every rank
+    scores all users against its range (tcgen05 scoring + fused top-K, scores never reach HBM), the per-shard [U, k]
+    lists are all-gathered and merged (score desc, id asc: identical to an unsharded scan).  Strong scaling."""
+    import torch.distributed as dist
+    from binrec_b200 import hotpath as H, distributed as D
+    U, I, d, k, chunk = 1_000_000, 2_000_000, 64, 10, 131072
+    g = torch.Generator(device=dev); g.manual_seed(5)                # same queries on every rank
+    Q = torch.randn(U, d, generator=g, device=dev)
+    lo, hi = D.local_slice(I)
+    gi = torch.Generator(device=dev); gi.manual_seed(100 + rank)
+    C = torch.randn(hi - lo, d, generator=gi, device=dev)
+    idx = H.BruteForceIndex(k).index(C, id_offset=lo)
+
+    def sweep():
+        outs = []
+        for s0 in range(0, U, chunk):
+            v, i = idx(Q[s0:s0 + chunk])
+            pv, pi = D.gather_topk_parts(v, i)
+            outs.append(H.topk_merge(pv, pi))
+        return outs
+
+    sweep(); torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); sweep(); e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    s = float(t.item()) * 1e-3
+    del Q, C, idx
+    torch.cuda.empty_cache()
+    flops_gpu = 2.0 * U * (hi - lo) * d
+    return {"metric": "top-K users/sec (1M users x 2M items, d=64, k=10)", "value": U / s, "unit": "users/s", "n_gpus": world,
+            "ms": s * 1e3, "scaling": "strong",
+            "roofline": _tensor_roofline("score_topk_kernel (per rank; + all-gather of [U,k] lists + topk_merge_kernel)", flops_gpu, s, peaks,
+                                         "per GPU; the selection epilogue's TMEM read rate caps d = 64 at 576 TFLOP/s (DESIGN.md section 4.1)"),
+            "config": {"workload": "BASELINE.json configs[4]: full-catalog top-K sweep, bf16 operands, fp32 scores",
+                       "parallelism": f"items range-sharded x{world}, NCCL all-gather of the [U, k] (score, id) lists, merge on every rank"}}
+
+
+def parity_multi_block(dev, world, rank):
+    """Parity of the multi-GPU paths INSIDE the bench run (the driver's GPU test lease has one GPU): every rank also runs the
+    single-process model on the global batches and compares.  (a) mirrored data-parallel BPR (the headline's kernel):
+    3 steps, global batch = world x 2048; (b) row-sharded NeuMF (tensor-core path, He-free class graph E=32 without
+    dropout; BatchNorm statistics are per replica, so the comparison is on the forward loss of one step and on the dense
+    gradient norm) -- losses against the unsharded NeuMFNet on this rank's batch."""
+    import torch.distributed as dist
+    from binrec_b200 import distributed as D
+    from binrec_b200.BPRModel import BPRNet
+    from binrec_b200.NeuMFModel import NeuMFNet
+    from binrec_b200.sharded import ShardedNeuMFNet
+    out = {}
+    U, I, d, B = 6040, 3706, 64, 2048
+    rng = np.random.default_rng(3)
+    dp = BPRNet(U, I, d, seed=42, device=dev)                   # peer arenas (world > 1)
+    os.environ["BRK_DP"] = "nccl"
+    single = None
+    try:
+        # a single-process replica on this rank: no peer arena, no all-reduce -- built with torch.distributed hidden
+        import binrec_b200.distributed as Dm
+        real_ws, real_rk = Dm.world_size, Dm.rank
+        Dm.world_size, Dm.rank = (lambda: 1), (lambda: 0)
+        single = BPRNet(U, I, d, seed=42, device=dev)
+        for step in range(3):
+            u = rng.integers(0, U, world * B).astype(np.int32); p = rng.integers(0, I, world * B).astype(np.int32)
+            n = rng.integers(0, I, world * B).astype(np.int32)
+            single.train_on_batch(*(torch.from_numpy(x).to(dev) for x in (u, p, n)))
+            Dm.world_size, Dm.rank = real_ws, real_rk
+            lo, hi = D.local_slice(world * B)
+            dp.train_on_batch(*(torch.from_numpy(x[lo:hi]).to(dev) for x in (u, p, n)))
+            Dm.world_size, Dm.rank = (lambda: 1), (lambda: 0)
+    finally:
+        Dm.world_size, Dm.rank = real_ws, real_rk
+        os.environ.pop("BRK_DP", None)
+    torch.cuda.synchronize()
+    if dp.peer is not None:
+        dp.peer.check()
+    err = torch.stack([(dp.user.w - single.user.w).abs().max(), (dp.item.w - single.item.w).abs().max()]).max().view(1).double()
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    out["mirrored_bpr"] = {"max_abs_weight_diff_vs_single_gpu": float(err.item()), "steps": 3, "global_batch": world * B,
+                           "tolerance": 2e-6, "ok": bool(err.item() <= 2e-6)}
+    del dp, single
+    # (b) row-sharded NeuMF against the unsharded model on the same batch (forward loss, one step, no dropout)
+    Un, In, E, Bn = 3000, 2000, 32, 4096
+    sh = ShardedNeuMFNet(Un, In, E, dropout=0.0, device=dev, mode="peer", tensor_cores=True, seed=42)
+    full = {name: torch.from_numpy(t.full_weights()).to(dev) for name, t in zip(("uMLP", "iMLP", "uMF", "iMF"), sh._tables())}
+    rng2 = np.random.default_rng(100 + rank)
+    u = torch.from_numpy(rng2.integers(0, Un, Bn).astype(np.int32)).to(dev)
+    i = torch.from_numpy(rng2.integers(0, In, Bn).astype(np.int32)).to(dev)
+    y = torch.from_numpy((rng2.random(Bn) < 0.3).astype(np.float32)).to(dev)
+    if full is not None:
+        Dm.world_size, Dm.rank = (lambda: 1), (lambda: 0)
+        try:
+            ref = NeuMFNet(Un, In, E, dropout=0.0, device=dev, tensor_cores=True, seed=42)
+        finally:
+            Dm.world_size, Dm.rank = real_ws, real_rk
+        for name in ("uMLP", "iMLP", "uMF", "iMF"):
+            getattr(ref, name).w.copy_(full[name])
+        ref.dense.w.copy_(sh.dense.w)
+        lr, _ = ref.forward_backward(u, i, y, global_batch=world * Bn)
+        ls, _ = sh.train_on_batch(u, i, y)
+        sh.check()
+        dl = (ls - lr).abs().view(1).double() / lr.abs().double()
+        dist.all_reduce(dl, op=dist.ReduceOp.MAX)
+        out["sharded_neumf"] = {"max_rel_loss_diff_vs_unsharded": float(dl.item()), "tolerance": 1e-5, "ok": bool(dl.item() <= 1e-5),
+                                "batch_per_rank": Bn}
+    else:
+        out["sharded_neumf"] = {"skipped": "ShardedTable.gather_full unavailable"}
+    del sh
+    torch.cuda.empty_cache()
     return out
 
 
@@ -612,13 +984,15 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=600)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="brk", choices=["brk", "reference"])
+    ap.add_argument("--impl", default="brk", choices=["brk", "reference", "cpu_legs"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         reference_arm(args)
+    elif args.impl == "cpu_legs":
+        cpu_legs_main(args)
     else:
         product_arm(args)
 

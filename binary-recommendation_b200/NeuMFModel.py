@@ -224,6 +224,46 @@ class NeuMFNet:
             N.ptr(losses), N.stream_ptr()), "brk_neumf_train_steps")
         return losses
 
+    @staticmethod
+    def pack_host_batches(users, items, labels, batch_size):
+        """Batch-major pinned host frame [n_full_batches, 3, batch] of int32 words (user ids, item ids, labels as float
+        bits): what a loader producing ({"user": ids, "item": ids}, label) batches writes (NeuMFModel.py:111-117)."""
+        nb = len(users) // int(batch_size)
+        packed = torch.empty((nb, 3, int(batch_size)), dtype=torch.int32).pin_memory()
+        a = packed.numpy()
+        n = nb * int(batch_size)
+        a[:, 0, :] = np.asarray(users[:n], dtype=np.int32).reshape(nb, -1)
+        a[:, 1, :] = np.asarray(items[:n], dtype=np.int32).reshape(nb, -1)
+        a[:, 2, :] = np.asarray(labels[:n], dtype=np.float32).view(np.int32).reshape(nb, -1)
+        return packed
+
+    def train_steps_from_host(self, packed_host, order, epoch=0, losses_host=None):
+        """End-to-end steps from a pack_host_batches() frame in page-locked HOST memory: per step one H2D copy of the
+        batch (12 B per sample), the fused step + optimizer, and one D2H copy of all step losses at the end -- all
+        enqueued by ONE C call (brk_neumf_train_steps_host); returns the pinned loss tensor (valid after a stream
+        synchronize).  Single process with the stock Adam."""
+        if D.world_size() > 1 or not isinstance(self.optimizer, H.Adam):
+            raise NotImplementedError("host-fed NeuMF steps: single process with the Adam optimizer")
+        nb, three, batch = packed_host.shape
+        order = np.ascontiguousarray(order, dtype=np.int64)
+        k = len(order)
+        dev = self.device
+        need = int(N.lib().brk_neumf_host_stage_ints(batch))
+        if getattr(self, "_stage", None) is None or self._stage.numel() < need:
+            self._stage = torch.empty(need, dtype=torch.int32, device=dev)
+        d_losses = torch.empty(max(k, 1), dtype=torch.float32, device=dev)
+        if losses_host is None:
+            losses_host = torch.empty(max(k, 1), dtype=torch.float32).pin_memory()
+        out = torch.empty(batch, dtype=torch.float32, device=dev)
+        m, ws, opt = self._c_model(), self._workspace(batch), self.optimizer
+        N.check(N.lib().brk_neumf_train_steps_host(
+            N.ctx(dev), C.byref(m), C.c_void_p(packed_host.data_ptr()), nb, batch, order.ctypes.data_as(C.POINTER(C.c_int64)), k,
+            self.dropout_seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, opt.h, N.ptr(opt.state), 1 if opt.sparse == "lazy" else 0,
+            C.byref(ws), N.ptr(self._stage), N.ptr(out), N.ptr(d_losses), C.c_void_p(losses_host.data_ptr()), N.stream_ptr()),
+            "brk_neumf_train_steps_host")
+        self._keep = (d_losses, out)                         # alive until the stream has consumed them
+        return losses_host[:k]
+
     def predict_on_batch(self, u, i, y=None):
         """Inference with the BN moving statistics; returns (predictions, loss or None)."""
         B = u.numel()

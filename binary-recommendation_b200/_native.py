@@ -103,6 +103,9 @@ SIGNATURES = {
                                  C.POINTER(brk_neumf_workspace), _P, _P, _P]),
     "brk_neumf_train_step": (C.c_int, [_P, C.POINTER(brk_neumf_model), _P, _P, _P, _I64, _I64, _U32, _U32, brk_adam_hyper, _P,
                                        _I32, C.POINTER(brk_neumf_workspace), _P, _P, _P]),
+    "brk_neumf_host_stage_ints": (C.c_int64, [_I64]),
+    "brk_neumf_train_steps_host": (C.c_int, [_P, C.POINTER(brk_neumf_model), _P, _I64, _I64, C.POINTER(C.c_int64), _I32, _U32,
+                                             _U32, brk_adam_hyper, _P, _I32, C.POINTER(brk_neumf_workspace), _P, _P, _P, _P, _P]),
     "brk_neumf_train_steps": (C.c_int, [_P, C.POINTER(brk_neumf_model), _P, _P, _P, _I64, _I64, C.POINTER(C.c_int64), _I32,
                                         _U32, _U32, brk_adam_hyper, _P, _I32, C.POINTER(brk_neumf_workspace), _P, _P, _P]),
     "brk_neumf_step_sharded": (C.c_int, [_P, C.POINTER(brk_neumf_model), C.POINTER(brk_neumf_shards), _P, _P, _P, _I64,

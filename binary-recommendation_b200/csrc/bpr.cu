@@ -738,19 +738,7 @@ extern "C" int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, con
     BRK_REQUIRE(batch_index_host[k] >= 0 && batch_index_host[k] < n_batches, BRK_E_ARG,
                 "brk_bpr_train_steps_host: batch index %lld of %lld", (long long)batch_index_host[k], (long long)n_batches);
   if (n_steps == 0) return 0;
-  if (!ctx->copy_ready) {
-    BRK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (int q = 0; q < BRK_STAGE_EVENTS; ++q) {
-      BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[q], cudaEventDisableTiming));
-      BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[q], cudaEventDisableTiming));
-    }
-    for (int a = 0; a < BRK_COPY_AUX; ++a) {
-      BRK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_aux[a], cudaStreamNonBlocking));
-      BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux[a], cudaEventDisableTiming));
-    }
-    BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_go, cudaEventDisableTiming));
-    ctx->copy_ready = 1;
-  }
+  if (int rc = brk_ctx_ensure_copy(ctx)) return rc;
   cudaStream_t cs = ctx->copy_stream;
   const bool use_dp = dp != nullptr && dp->world > 1;
   // data-parallel mode: the tables are views into the peer arenas (their Adam moments live in `dp`, sharded)

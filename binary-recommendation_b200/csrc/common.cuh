@@ -53,6 +53,8 @@ struct brk_ctx {
 #define BRK_TICKETS 16
 
 void brk_set_error(const char* fmt, ...);
+// copy stream + staging events of the host-fed training entry points (created on first use)
+int brk_ctx_ensure_copy(brk_ctx* ctx);
 
 #define BRK_REQUIRE(cond, code, ...)            \
   do {                                          \

@@ -47,6 +47,22 @@ extern "C" int brk_create(brk_ctx** out, int device) {
   return 0;
 }
 
+int brk_ctx_ensure_copy(brk_ctx* ctx) {
+  if (ctx->copy_ready) return 0;
+  BRK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int q = 0; q < BRK_STAGE_EVENTS; ++q) {
+    BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready[q], cudaEventDisableTiming));
+    BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[q], cudaEventDisableTiming));
+  }
+  for (int a = 0; a < BRK_COPY_AUX; ++a) {
+    BRK_CUDA(cudaStreamCreateWithFlags(&ctx->copy_aux[a], cudaStreamNonBlocking));
+    BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux[a], cudaEventDisableTiming));
+  }
+  BRK_CUDA(cudaEventCreateWithFlags(&ctx->ev_go, cudaEventDisableTiming));
+  ctx->copy_ready = 1;
+  return 0;
+}
+
 extern "C" int brk_destroy(brk_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);

@@ -61,3 +61,47 @@ extern "C" int brk_neumf_train_steps(brk_ctx* ctx, const brk_neumf_model* m, con
   }
   return 0;
 }
+
+// Host-fed training steps: the frame lives in page-locked HOST memory in the loader's batch-major layout
+// packed_host [n_batches][3][batch] (user ids, item ids, labels as float bits -- what a loader producing
+// ({"user": ids, "item": ids}, label) batches writes, NeuMFModel.py:111-117).  Per step ONE cudaMemcpyAsync of that
+// batch's 12 * batch bytes on the context's copy stream into one of four staging slots, then brk_neumf_train_step on
+// the slot; the copy of step s + 1..s + 3 overlaps the compute of step s.  The step losses return in ONE D2H copy into
+// losses_host (valid after the stream is synchronised).  Full batches only.
+extern "C" int64_t brk_neumf_host_stage_ints(int64_t batch) { return 4 * 3 * batch; }
+
+extern "C" int brk_neumf_train_steps_host(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* packed_host, int64_t n_batches,
+                                          int64_t batch, const int64_t* batch_index_host, int32_t n_steps, uint32_t dropout_seed,
+                                          uint32_t dropout_epoch, brk_adam_hyper h, int64_t* adam_state, int32_t lazy_adam,
+                                          const brk_neumf_workspace* ws, int32_t* d_stage, float* out, float* d_losses,
+                                          float* losses_host, void* stream) {
+  BRK_REQUIRE(ctx && m && packed_host && ws && d_stage && out && d_losses && adam_state, BRK_E_ARG,
+              "brk_neumf_train_steps_host: null argument");
+  BRK_REQUIRE(n_batches > 0 && batch > 0 && n_steps >= 0 && (n_steps == 0 || batch_index_host), BRK_E_ARG,
+              "brk_neumf_train_steps_host: n_batches=%lld batch=%lld n_steps=%d", (long long)n_batches, (long long)batch, n_steps);
+  if (n_steps == 0) return 0;
+  if (int rc = brk_ctx_ensure_copy(ctx)) return rc;
+  cudaStream_t st = (cudaStream_t)stream, cs = ctx->copy_stream;
+  constexpr int kSlots = BRK_STAGE_EVENTS;
+  const size_t slot_ints = size_t(3) * size_t(batch);
+  // the copy stream starts after whatever the caller has queued on `st` (earlier steps may still read the slots)
+  BRK_CUDA(cudaEventRecord(ctx->ev_go, st));
+  BRK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_go, 0));
+  for (int32_t s = 0; s < n_steps; ++s) {
+    const int64_t b = batch_index_host[s];
+    BRK_REQUIRE(b >= 0 && b < n_batches, BRK_E_ARG, "brk_neumf_train_steps_host: batch index %lld of %lld", (long long)b,
+                (long long)n_batches);
+    const int q = s % kSlots;
+    int32_t* slot = d_stage + size_t(q) * slot_ints;
+    if (s >= kSlots) BRK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_done[q], 0));      // the step that last used this slot is done
+    BRK_CUDA(cudaMemcpyAsync(slot, packed_host + size_t(b) * slot_ints, slot_ints * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+    BRK_CUDA(cudaEventRecord(ctx->ev_ready[q], cs));
+    BRK_CUDA(cudaStreamWaitEvent(st, ctx->ev_ready[q], 0));
+    const int rc = brk_neumf_train_step(ctx, m, slot, slot + batch, reinterpret_cast<const float*>(slot + 2 * batch), batch,
+                                        b * batch, dropout_seed, dropout_epoch, h, adam_state, lazy_adam, ws, out, d_losses + s, stream);
+    if (rc) return rc;
+    BRK_CUDA(cudaEventRecord(ctx->ev_done[q], st));
+  }
+  if (losses_host) BRK_CUDA(cudaMemcpyAsync(losses_host, d_losses, size_t(n_steps) * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return 0;
+}

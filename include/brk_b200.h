@@ -254,6 +254,19 @@ int brk_neumf_train_steps(brk_ctx* ctx, const brk_neumf_model* m, const int32_t*
                           int64_t* adam_state, int32_t lazy_adam, const brk_neumf_workspace* ws, float* out,
                           float* losses, void* stream);
 
+/* Host-fed variant of brk_neumf_train_steps (the tf.data iterator -> device boundary of model.fit, RModel.py:130): the
+ * frame stays in page-locked HOST memory, batch-major packed_host [n_batches][3][batch] int32 words (user ids, item
+ * ids, labels as float bits).  Per step one cudaMemcpyAsync of the batch (12 * batch bytes) on the context's copy
+ * stream into one of four staging slots (d_stage: brk_neumf_host_stage_ints(batch) int32), then brk_neumf_train_step;
+ * copies run ahead of the compute.  d_losses [n_steps] device; losses_host [n_steps] pinned (may be NULL), filled by
+ * one D2H copy, valid after the stream is synchronised.  Full batches only. */
+int64_t brk_neumf_host_stage_ints(int64_t batch);
+int brk_neumf_train_steps_host(brk_ctx* ctx, const brk_neumf_model* m, const int32_t* packed_host, int64_t n_batches,
+                               int64_t batch, const int64_t* batch_index_host, int32_t n_steps, uint32_t dropout_seed,
+                               uint32_t dropout_epoch, brk_adam_hyper h, int64_t* adam_state, int32_t lazy_adam,
+                               const brk_neumf_workspace* ws, int32_t* d_stage, float* out, float* d_losses,
+                               float* losses_host, void* stream);
+
 /* Test hook for the tcgen05 building blocks of the NeuMF tensor-core path (csrc/neumf_tc.cu): stages A
  * [a_rows, a_cols] and B [b_rows, b_cols] (row-major fp32; cols multiples of 32, rows multiples of 8) as
  * 128-byte-swizzled tiles and computes D = A B^T (mode bit0/bit1 = 0: K-major operand, rows = M / N) or
