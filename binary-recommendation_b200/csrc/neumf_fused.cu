@@ -253,6 +253,99 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ta
   __syncthreads();
 }
 
+// ---- after the tiles: the dense gradients -- the slots of all tiles, summed in tile order by the CTA that owns the
+//      parameter slice (float4 granularity) -- and, with do_adam, the exact Keras Adam of optim.cu over the dense block and
+//      the four tables in the same pass.  Run by EVERY CTA of a cooperative launch: the tile CTAs and the helper CTAs that
+//      only exist so that a small batch does not leave this phase (20 MB of optimizer traffic) to a handful of SMs.
+template <class S>
+__device__ __forceinline__ void dense_reduce_and_adam(const Args& A, const Extra& X, unsigned int& bar_target, float4* f4red, float alpha) {
+  const int t = threadIdx.x;
+  grid_barrier(X.bar, bar_target);
+  const float b1c = X.hyp.beta1, b2c = X.hyp.beta2, ob1c = 1.0f - X.hyp.beta1, ob2c = 1.0f - X.hyp.beta2, epsc = X.hyp.eps;
+  auto adam1 = [&](float& w, float& m, float& v, float g) {
+    m = b1c * m + ob1c * g;
+    v = b2c * v + ob2c * g * g;
+    w -= alpha * m / (sqrtf(v) + epsc);
+  };
+  auto adam4 = [&](float4* w, float4* m, float4* v, float4 g4) {
+    float4 w4 = *w, m4 = *m, v4 = *v;
+    adam1(w4.x, m4.x, v4.x, g4.x); adam1(w4.y, m4.y, v4.y, g4.y); adam1(w4.z, m4.z, v4.z, g4.z); adam1(w4.w, m4.w, v4.w, g4.w);
+    *w = w4; *m = m4; *v = v4;
+  };
+  constexpr int n4 = S::NDP / 4;
+  const int per4 = (n4 + int(gridDim.x) - 1) / int(gridDim.x);
+  const int lo4 = int(blockIdx.x) * per4, hi4 = lo4 + per4 < n4 ? lo4 + per4 : n4;
+  int PP = 1;
+  while (PP < per4 && PP < NT) PP <<= 1;
+  const int groups = NT / PP, grp = t / PP, pl = t % PP;
+  float4* G4 = reinterpret_cast<float4*>(A.dense.g);
+  for (int p0 = lo4; p0 < hi4; p0 += PP) {
+    const int pp = p0 + pl;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pp < hi4)
+#pragma unroll 8
+      for (int j = grp; j < X.n_tiles; j += groups) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(X.part + size_t(j) * S::PT + S::pDense) + pp);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    f4red[t] = acc;
+    __syncthreads();
+    if (grp == 0 && pp < hi4) {
+      // with Adam in this launch the block's accumulator is not read: it is zero between steps (include/brk_b200.h)
+      float4 g4 = X.do_adam ? make_float4(0.f, 0.f, 0.f, 0.f) : G4[pp];
+      for (int gg = 0; gg < groups; ++gg) {
+        const float4 v = f4red[gg * PP + pl];
+        g4.x += v.x; g4.y += v.y; g4.z += v.z; g4.w += v.w;
+      }
+      if (X.do_adam) {
+        adam4(reinterpret_cast<float4*>(X.dw) + pp, reinterpret_cast<float4*>(X.dm) + pp, reinterpret_cast<float4*>(X.dv) + pp, g4);
+      } else {
+        G4[pp] = g4;
+      }
+    }
+    __syncthreads();
+  }
+  stamp(X, 10);
+  if (X.do_adam) {                                      // the four tables: every element moves (Keras' sparse Adam is dense-equivalent)
+    const int64_t gtid = int64_t(blockIdx.x) * NT + t, nthr = int64_t(gridDim.x) * NT;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      const int64_t e4 = X.tn[k] >> 2;
+      float4* w = reinterpret_cast<float4*>(X.tw[k]); float4* m = reinterpret_cast<float4*>(X.tm[k]);
+      float4* v = reinterpret_cast<float4*>(X.tv[k]); float4* g = reinterpret_cast<float4*>(X.tg[k]);
+      // four elements per thread and pass: all sixteen loads are issued before the first store (the compiler
+      // cannot hoist them itself past stores through pointers it must assume to alias)
+      for (int64_t i0 = gtid; i0 < e4; i0 += 4 * nthr) {
+        float4 gq[4], wq[4], mq[4], vq[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int64_t i = i0 + q4 * nthr;
+          if (i < e4) { gq[q4] = g[i]; wq[q4] = w[i]; mq[q4] = m[i]; vq[q4] = v[i]; }
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int64_t i = i0 + q4 * nthr;
+          if (i < e4) {
+            adam1(wq[q4].x, mq[q4].x, vq[q4].x, gq[q4].x); adam1(wq[q4].y, mq[q4].y, vq[q4].y, gq[q4].y);
+            adam1(wq[q4].z, mq[q4].z, vq[q4].z, gq[q4].z); adam1(wq[q4].w, mq[q4].w, vq[q4].w, gq[q4].w);
+            w[i] = wq[q4]; m[i] = mq[q4]; v[i] = vq[q4]; g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      if (X.tt[k] != nullptr) {
+        const int64_t nwords = (X.trows[k] + 31) >> 5;
+        for (int64_t i = gtid; i < nwords; i += nthr) X.tt[k][i] = 0u;
+      }
+    }
+    if (blockIdx.x == 0 && t == 0) {                    // every CTA read the state during set-up, before the barriers
+      double* pw = reinterpret_cast<double*>(X.adam_state);
+      X.adam_state[0] += 1;
+      pw[1] *= double(X.hyp.beta1);
+      pw[2] *= double(X.hyp.beta2);
+    }
+  }
+}
+
 #define NFZ_OPERANDS_READY() do { tc::fence_proxy_async_smem(); tc::fence_before_sync(); __syncthreads(); tc::fence_after_sync(); } while (0)
 
 template <class S>
@@ -309,6 +402,21 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
   uint32_t phase = 0;
   const int c1 = hf * HC1, c2 = hf * HC2;            // first column of this thread's half in layers 1 / 2
   stamp(X, 0);
+
+  if (int(blockIdx.x) >= X.n_tiles) {
+    // helper CTA of a cooperative training launch (grid = max(tiles, SMs)): no tile, only the barriers and its share of
+    // the dense-gradient reduction and of the Adam pass
+    if (t == 64 && X.do_adam) {
+      const double* pw = reinterpret_cast<const double*>(X.adam_state);
+      const double p1 = pw[1] * double(X.hyp.beta1), p2 = pw[2] * double(X.hyp.beta2);
+      alpha_s = float(double(X.hyp.lr) * sqrt(1.0 - p2) / (1.0 - p1));
+    }
+    __syncthreads();
+    if (BN)
+      for (int k = 0; k < 4; ++k) grid_barrier(X.bar, bar_target);
+    dense_reduce_and_adam<S>(A, X, bar_target, reinterpret_cast<float4*>(Q), alpha_s);
+    return;
+  }
 
   // ---- set-up: ids and the dense parameter block (one coalesced copy into the R / S tile space, free until phase C;
   //      the operand images and small vectors are then built from shared memory) -----------------------------------
@@ -812,94 +920,7 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
     }
     if (coop) {
       for (int f = S::ND + t; f < S::NDP; f += NT) dp[f] = 0.f;           // pad words of the block
-      // ---- dense gradients: the slots of all tiles, summed in tile order by the CTA that owns the parameter slice
-      //      (float4 granularity); with do_adam the exact Keras Adam of optim.cu follows in the same pass ------------
-      grid_barrier(X.bar, bar_target);
-      const float b1c = X.hyp.beta1, b2c = X.hyp.beta2, ob1c = 1.0f - X.hyp.beta1, ob2c = 1.0f - X.hyp.beta2, epsc = X.hyp.eps;
-      const float alpha = alpha_s;
-      auto adam1 = [&](float& w, float& m, float& v, float g) {
-        m = b1c * m + ob1c * g;
-        v = b2c * v + ob2c * g * g;
-        w -= alpha * m / (sqrtf(v) + epsc);
-      };
-      auto adam4 = [&](float4* w, float4* m, float4* v, float4 g4) {
-        float4 w4 = *w, m4 = *m, v4 = *v;
-        adam1(w4.x, m4.x, v4.x, g4.x); adam1(w4.y, m4.y, v4.y, g4.y); adam1(w4.z, m4.z, v4.z, g4.z); adam1(w4.w, m4.w, v4.w, g4.w);
-        *w = w4; *m = m4; *v = v4;
-      };
-      constexpr int n4 = S::NDP / 4;
-      const int per4 = (n4 + int(gridDim.x) - 1) / int(gridDim.x);
-      const int lo4 = int(blockIdx.x) * per4, hi4 = lo4 + per4 < n4 ? lo4 + per4 : n4;
-      int PP = 1;
-      while (PP < per4 && PP < NT) PP <<= 1;
-      const int groups = NT / PP, grp = t / PP, pl = t % PP;
-      float4* f4red = reinterpret_cast<float4*>(Q);                         // NT float4; every tile buffer is dead by now
-      float4* G4 = reinterpret_cast<float4*>(G);
-      for (int p0 = lo4; p0 < hi4; p0 += PP) {
-        const int pp = p0 + pl;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pp < hi4)
-#pragma unroll 8
-          for (int j = grp; j < X.n_tiles; j += groups) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(X.part + size_t(j) * S::PT + S::pDense) + pp);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-          }
-        f4red[t] = acc;
-        __syncthreads();
-        if (grp == 0 && pp < hi4) {
-          // with Adam in this launch the block's accumulator is not read: it is zero between steps (include/brk_b200.h)
-          float4 g4 = X.do_adam ? make_float4(0.f, 0.f, 0.f, 0.f) : G4[pp];
-          for (int gg = 0; gg < groups; ++gg) {
-            const float4 v = f4red[gg * PP + pl];
-            g4.x += v.x; g4.y += v.y; g4.z += v.z; g4.w += v.w;
-          }
-          if (X.do_adam) {
-            adam4(reinterpret_cast<float4*>(X.dw) + pp, reinterpret_cast<float4*>(X.dm) + pp, reinterpret_cast<float4*>(X.dv) + pp, g4);
-          } else {
-            G4[pp] = g4;
-          }
-        }
-        __syncthreads();
-      }
-      stamp(X, 10);
-      if (X.do_adam) {                                      // the four tables: every element moves (Keras' sparse Adam is dense-equivalent)
-        const int64_t gtid = int64_t(blockIdx.x) * NT + t, nthr = int64_t(gridDim.x) * NT;
-#pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-          const int64_t e4 = X.tn[k] >> 2;
-          float4* w = reinterpret_cast<float4*>(X.tw[k]); float4* m = reinterpret_cast<float4*>(X.tm[k]);
-          float4* v = reinterpret_cast<float4*>(X.tv[k]); float4* g = reinterpret_cast<float4*>(X.tg[k]);
-          // four elements per thread and pass: all sixteen loads are issued before the first store (the compiler
-          // cannot hoist them itself past stores through pointers it must assume to alias)
-          for (int64_t i0 = gtid; i0 < e4; i0 += 4 * nthr) {
-            float4 gq[4], wq[4], mq[4], vq[4];
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const int64_t i = i0 + q4 * nthr;
-              if (i < e4) { gq[q4] = g[i]; wq[q4] = w[i]; mq[q4] = m[i]; vq[q4] = v[i]; }
-            }
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const int64_t i = i0 + q4 * nthr;
-              if (i < e4) {
-                adam1(wq[q4].x, mq[q4].x, vq[q4].x, gq[q4].x); adam1(wq[q4].y, mq[q4].y, vq[q4].y, gq[q4].y);
-                adam1(wq[q4].z, mq[q4].z, vq[q4].z, gq[q4].z); adam1(wq[q4].w, mq[q4].w, vq[q4].w, gq[q4].w);
-                w[i] = wq[q4]; m[i] = mq[q4]; v[i] = vq[q4]; g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-            }
-          }
-          if (X.tt[k] != nullptr) {
-            const int64_t nwords = (X.trows[k] + 31) >> 5;
-            for (int64_t i = gtid; i < nwords; i += nthr) X.tt[k][i] = 0u;
-          }
-        }
-        if (blockIdx.x == 0 && t == 0) {                    // every CTA read the state during set-up, before the barriers
-          double* pw = reinterpret_cast<double*>(X.adam_state);
-          X.adam_state[0] += 1;
-          pw[1] *= double(X.hyp.beta1);
-          pw[2] *= double(X.hyp.beta2);
-        }
-      }
+      dense_reduce_and_adam<S>(A, X, bar_target, reinterpret_cast<float4*>(Q), alpha_s);   // every tile buffer is dead by now
       if (blockIdx.x == 0) {                                // BN moving statistics, loss
         if (BN) {
           for (int f = t; f < H1; f += NT) {
@@ -989,8 +1010,10 @@ int run(brk_ctx* ctx, const Args& A, const AdamReq* adam, cudaStream_t st, int* 
     ctx->neumf_part_floats = need;
   }
   X.part = ctx->neumf_part; X.coop = 1;
+  // helper CTAs up to one per SM: the final reduction / Adam phase is spread over the whole GPU even for a small batch
+  const unsigned grid = unsigned(n_tiles > ctx->sm_count ? n_tiles : (ctx->sm_count < max_blocks ? ctx->sm_count : max_blocks));
   X.bar = bar; X.bar_base = bar_count;
-  bar_count += unsigned(n_tiles) * (S::BN ? 5u : 1u);       // barriers of one training launch
+  bar_count += grid * (S::BN ? 5u : 1u);                     // barriers of one training launch
   if (adam != nullptr) {
     const brk_table* tb[4] = {&adam->m->uMLP, &adam->m->iMLP, &adam->m->uMF, &adam->m->iMF};
     for (int k = 0; k < 4; ++k) {
@@ -1007,7 +1030,7 @@ int run(brk_ctx* ctx, const Args& A, const AdamReq* adam, cudaStream_t st, int* 
     X.do_adam = 1; X.hyp = adam->h; X.adam_state = adam->state;
   }
   void* args[] = {(void*)&Ac, (void*)&X};
-  BRK_CUDA(cudaLaunchCooperativeKernel((const void*)fn, dim3(unsigned(n_tiles)), dim3(NT), args, S::smem, st));
+  BRK_CUDA(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid), dim3(NT), args, S::smem, st));
   return 0;
 }
 

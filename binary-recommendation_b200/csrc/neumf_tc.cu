@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(NT) tc_fwd2(const Args A, const float* __restr
 // ---- phase 3: d2 = dropout(bn2(h2)); h3 = act(d2 W3 + b3); MF dot; logit, prediction, loss; then (training)
 //      head / layer-3 gradients and dd2 = d loss / d d2 with its BatchNorm-backward sums -----------------------
 template <int E, int H1, int H2, int H3, int ACT>
-__global__ void __launch_bounds__(NT) tc_head(const Args A, const float* __restrict__ img) {
+__global__ void __launch_bounds__(NT) tc_head(const Args A, const float* __restrict__ img, int n_tiles) {
   using L = Layout<E, H1, H2, H3>; using AC = Acc<H1, H2>; using I = Img<E, H1, H2, H3>;
   constexpr int N3 = I::N3, LPR = E / 4, RPP = NT / LPR, ZP = H3 + 1;
   uint8_t* sm = smem_base();
@@ -406,10 +406,14 @@ __global__ void __launch_bounds__(NT) tc_head(const Args A, const float* __restr
   __shared__ Ctl ctl;
   __shared__ double red[32];
   __shared__ int32_t ids_s[2 * TS];
-  const int64_t b0 = int64_t(blockIdx.x) * TS;
-  const int valid = int((A.B - b0) < int64_t(TS) ? (A.B - b0) : int64_t(TS));
+  // Persistent over tiles: the head / layer-3 weight gradients of all of this CTA's tiles are summed here and leave
+  // with ONE atomic per entry per CTA.  (One CTA per tile with its own atomics put 512 tiles' worth of adds on the same
+  // ~550 words at configs[3] sizes: 85 us for this kernel, most of it the serialised atomics.)
+  __shared__ float aW3[H2 * H3], ab3[H3], aW4[H3 + 2];
   const int t = threadIdx.x, warp = t >> 5;
-  load_tile_ids(ids_s, A, b0, valid);
+  for (int j = t; j < H2 * H3; j += NT) aW3[j] = 0.f;
+  if (t < H3) ab3[t] = 0.f;
+  if (t < H3 + 2) aW4[t] = 0.f;
   const uint32_t tmem = tc_begin<32>(ctl);
   copy16(Ws, img + I::W3t, N3 * pad32(H2));
   copy_small<H2 * H3>(W3s, A.dense.w + L::W3);
@@ -419,6 +423,11 @@ __global__ void __launch_bounds__(NT) tc_head(const Args A, const float* __restr
   copy_small<H2>(bet, A.dense.w + L::be2);
   bn_prepare<H2>(mean, rstd, A.acc + AC::s2, A.acc + AC::q2, A.bn_moving + 2 * H1, A.bn_moving + 2 * H1 + H2, A.B, A.training);
   zero_pad_cols<H2>(As, false);                            // unused K columns of the tile
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int64_t b0 = int64_t(tile) * TS;
+  const int valid = int((A.B - b0) < int64_t(TS) ? (A.B - b0) : int64_t(TS));
+  load_tile_ids(ids_s, A, b0, valid);
   __syncthreads();
   stage_bn_tile<H2, 2>(As, A.h2, A, b0, valid, mean, rstd, gam, bet, Xh);
   NTC_OPERANDS_READY();
@@ -446,7 +455,8 @@ __global__ void __launch_bounds__(NT) tc_head(const Args A, const float* __restr
     part = group_sum<LPR>(part);
     if (mc4 == 0) mfs[p * RPP + mrr] = part;
   }
-  tc::mbar_wait(tc::smem_u32(&ctl.bar), 0);
+  tc::mbar_wait(tc::smem_u32(&ctl.bar), phase);
+  phase ^= 1u;
   tc::fence_after_sync();
   __syncthreads();                                         // mfs visible
   float loss_local = 0.f;
@@ -491,7 +501,7 @@ __global__ void __launch_bounds__(NT) tc_head(const Args A, const float* __restr
         sacc = fmaf(j < H3 ? Ys[j * SP + s] : (j == H3 ? mfs[s] : 1.f), dl[s], sacc);
       }
       sacc = warp_sum(sacc);
-      if ((t & 31) == 0) atomicAdd(A.dense.g + L::W4 + j, sacc);
+      if ((t & 31) == 0) aW4[j] += sacc;
     }
     // layer-3 weights: dW3[k][j] = sum_s d2[s][k] dz3[s][j]; db3[j] = sum_s dz3[s][j]   (small: CUDA cores).
     // thread = (k, group of JG outputs j); d2 is read from the swizzled K-major tile, 8 rows per address step
@@ -514,14 +524,14 @@ __global__ void __launch_bounds__(NT) tc_head(const Args A, const float* __restr
           }
         }
 #pragma unroll
-        for (int q = 0; q < JG; ++q) atomicAdd(A.dense.g + L::W3 + k * H3 + j0 + q, acc[q]);
+        for (int q = 0; q < JG; ++q) aW3[k * H3 + j0 + q] += acc[q];
       }
       for (int j = warp; j < H3; j += NT / 32) {                       // db3: one warp per j
         float sacc = 0.f;
 #pragma unroll
         for (int q = 0; q < TS / 32; ++q) sacc += Zt[(q * 32 + (t & 31)) * ZP + j];
         sacc = warp_sum(sacc);
-        if ((t & 31) == 0) atomicAdd(A.dense.g + L::b3 + j, sacc);
+        if ((t & 31) == 0) ab3[j] += sacc;
       }
     }
     // dd2[s][k] = dropout-mask * sum_j dz3[s][j] W3[k][j]: thread (sample, half of the k range)
@@ -563,6 +573,14 @@ __global__ void __launch_bounds__(NT) tc_head(const Args A, const float* __restr
     __syncthreads();
     store_tile<H2>(Ds, A.dy2, A.B, b0, valid);
     row_sums<H2>(Ds, Xh, A.acc + AC::d2, A.acc + AC::e2);
+  }
+  tc::fence_before_sync();
+  __syncthreads();                                         // tiles, ids and TMEM may be overwritten by the next iteration
+  }
+  if (A.training) {                                        // one atomic per entry per CTA
+    for (int j = t; j < H2 * H3; j += NT) atomicAdd(A.dense.g + L::W3 + j, aW3[j]);
+    if (t < H3) atomicAdd(A.dense.g + L::b3 + t, ab3[t]);
+    if (t < H3 + 2) atomicAdd(A.dense.g + L::W4 + t, aW4[t]);
   }
   tc_end<32>(tmem);
 }
@@ -931,7 +949,7 @@ int run(brk_ctx* ctx, const Args& A, cudaStream_t st) {
   const size_t smD = by(size_t(TS) * pad32(H1) + 2 * size_t(TS) * pad32(H2) + H1 * pad32(H2) + size_t(H1) * SP + 4 * H1 + 5 * H2);
   const size_t smE = by(size_t(TS) * K0 + 2 * size_t(TS) * pad32(H1) + K0 * pad32(H1) + TS * (K0 / 32) + 5 * H1);
   static bool attr_done = false;
-  static int occ_d = 0, occ_e = 0;
+  static int occ_d = 0, occ_e = 0, occ_c = 0;
   if (!attr_done) {
     BRK_CUDA(cudaFuncSetAttribute(tc_fwd1<E, H1, H2, H3, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smA)));
     BRK_CUDA(cudaFuncSetAttribute(tc_fwd2<E, H1, H2, H3, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smB)));
@@ -942,13 +960,18 @@ int run(brk_ctx* ctx, const Args& A, cudaStream_t st) {
     // bwd2 allocates 128, bwd1 256 per CTA)
     occ_d = int((227 * 1024) / (smD + 1024)); if (occ_d > 2) occ_d = 2;
     occ_e = int((227 * 1024) / (smE + 1024)); if (occ_e > 2) occ_e = 2;
-    BRK_REQUIRE(occ_d > 0 && occ_e > 0, BRK_E_STATE, "brk_neumf_step: tensor-core kernels do not fit");
+    BRK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, tc_head<E, H1, H2, H3, ACT>, NT, smC));
+    if (occ_c > 4) occ_c = 4;
+    BRK_REQUIRE(occ_d > 0 && occ_e > 0 && occ_c > 0, BRK_E_STATE, "brk_neumf_step: tensor-core kernels do not fit");
     attr_done = true;
   }
   prep_images<E, H1, H2, H3><<<(I::total + 255) / 256, 256, 0, st>>>(A.dense.w, img);
   tc_fwd1<E, H1, H2, H3, ACT><<<n_tiles, NT, smA, st>>>(A, img);
   tc_fwd2<E, H1, H2, H3, ACT><<<n_tiles, NT, smB, st>>>(A, img);
-  tc_head<E, H1, H2, H3, ACT><<<n_tiles, NT, smC, st>>>(A, img);
+  {
+    const int gc = n_tiles < occ_c * ctx->sm_count ? n_tiles : occ_c * ctx->sm_count;
+    tc_head<E, H1, H2, H3, ACT><<<gc, NT, smC, st>>>(A, img, n_tiles);
+  }
   if (A.training) {
     const int gd = n_tiles < occ_d * ctx->sm_count ? n_tiles : occ_d * ctx->sm_count;
     const int ge = n_tiles < occ_e * ctx->sm_count ? n_tiles : occ_e * ctx->sm_count;
