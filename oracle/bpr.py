@@ -1,6 +1,13 @@
 """ORACLE (test infrastructure, never the product path): BPR matrix factorisation restated on
-the CPU.  PARITY UNPINNED at the Keras boundary (no golden vectors in the reference; SURVEY.md
-section 0.3); pinned by hand-computed fp64 cases in tests/test_oracle_models.py.
+the CPU.
+
+Pinning.  WIRING PINNED: the reference's BPRModel.compileModel, bprTripletLoss and identityLoss are EXECUTED over a
+torch-backed Keras stand-in (tests/golden/keras_shim.py, tests/golden/make_wiring_golden.py -> wiring_golden.npz) and
+this oracle reproduces the per-triplet output, the loss, both table gradients (one item table shared by the positive
+and the negative lookup) and the tables after the compiled Adam(1e-3) step to 1e-9 (tests/test_oracle_wiring.py).
+UPSTREAM NUMERICS UNPINNED: Embedding / Adam arithmetic is restated from the upstream documentation (no TensorFlow
+here, no golden vectors in the reference), held to hand-computed fp64 cases
+(tests/test_oracle_models.py).
 
 Follows /root/reference/src/models/BPRModel.py:49-74 (graph: one user table, one item table
 shared by the positive and negative lookup), :124-144 (bprTripletLoss, identityLoss) and the

@@ -1,11 +1,12 @@
 """ORACLE (test infrastructure, never the product path): embedding gather, sparse-gradient
 scatter-add and the Keras optimizers, restated on the CPU in NumPy.
 
-PARITY UNPINNED at the Keras boundary: the reference's tests hold no numbers for these ops
- and TensorFlow cannot be installed here, so these functions restate the
-upstream Keras/TensorFlow (>=2.3.1, /root/reference/requirements.txt:1) semantics that the
-reference's call sites rely on.  tests/test_oracle_models.py pins them against hand-computed
-fp64 cases instead.
+UPSTREAM NUMERICS UNPINNED: the reference's tests hold no numbers for these ops (SURVEY.md section
+0.3) and TensorFlow cannot be installed here, so these functions restate the upstream Keras/TensorFlow
+(>=2.3.1, /root/reference/requirements.txt:1) semantics that the reference's call sites rely on.
+tests/test_oracle_models.py pins them against hand-computed fp64 cases; how the reference WIRES them
+(which table feeds which lookup, which optimizer with which learning rate) is pinned by executed
+reference code (tests/test_oracle_wiring.py).
 
 Call sites restated:
   Embedding(...)(ids)           NeuMFModel.py:58-63, BPRModel.py:55-61, bpr.py:178-184, twoTower.py:34,36

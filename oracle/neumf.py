@@ -1,9 +1,14 @@
 """ORACLE (test infrastructure, never the product path): NeuMF restated on the CPU with torch
-autograd (fp32 or fp64).  PARITY UNPINNED at the Keras boundary (the reference holds no golden
-vectors); the upstream Keras semantics restated here are listed in SURVEY.md
-section 8a row a1; the layer wiring is pinned by executing the reference's own compileModel against a
-torch-backed Keras shim (tests/golden/keras_shim.py -> tests/golden/wiring_golden.npz, tests/test_oracle_wiring.py)
-and the arithmetic is held to an independent NumPy restatement and fp64 finite differences (tests/test_oracle_nets.py).
+autograd (fp32 or fp64).
+
+Pinning.  WIRING PINNED: the reference's own NeuMFModel.compileModel is EXECUTED over a torch-backed Keras stand-in
+(tests/golden/keras_shim.py, tests/golden/make_wiring_golden.py -> tests/golden/wiring_golden.npz) and this oracle
+reproduces its predictions, loss, every gradient, the weights after the compiled Adam(1e-3) step, the BatchNorm moving
+statistics and the inference output to 1e-9 in float64 (tests/test_oracle_wiring.py; numFactor 32, 8 and 20).
+UPSTREAM NUMERICS UNPINNED: the arithmetic INSIDE each Keras layer (Dense, BatchNormalization, Dropout, Adam ...) is
+restated from the upstream documentation in both the shim and here -- TensorFlow cannot be installed and the reference
+holds no golden vectors -- and is held to an independent NumPy restatement and fp64 finite
+differences (tests/test_oracle_nets.py).  The He et al. variant below is not in the reference tree at all.
 
 Follows /root/reference/src/models/NeuMFModel.py:53-100 (class spec) and
 /root/reference/trainers/NFC_plain.py:109-155 (script spec):

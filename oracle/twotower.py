@@ -1,6 +1,14 @@
 """ORACLE (test infrastructure, never the product path): the two-tower model restated on the CPU with
-torch autograd.  PARITY UNPINNED at the Keras/TFRS boundary (no golden vectors in the reference;
-tensorflow_recommenders is not even listed in requirements.txt).
+torch autograd.
+
+Pinning.  WIRING PINNED: the reference's TwoTowerModel (constructor, computeEmb, computeLossTfrs / computeLossRdZero,
+train_step with its GradientTape / apply_gradients sequence, setCandidates + call) is EXECUTED over a torch-backed
+Keras / TFRS stand-in (tests/golden/keras_shim.py, tests/golden/make_wiring_golden.py -> wiring_golden.npz) and this
+oracle reproduces the loss, every gradient, the weights after the Adagrad(0.1) step and the BruteForce top-k lists to
+1e-9 (tests/test_oracle_wiring.py; both loss modes; StringLookup offset 2; candidate_ids = the MATERIAL column).
+UPSTREAM NUMERICS UNPINNED: what tfrs.tasks.Retrieval, BruteForce, Adagrad and the Keras layers compute inside is
+restated from the upstream documentation (tensorflow_recommenders is not even listed in requirements.txt, SURVEY.md
+section 8c).
 
 Follows /root/reference/trainers/twoTower.py:19-111:
   towers : StringLookup -> Embedding(n + 2, E) -> Dense(S), linear (:33-41).  StringLookup (TF 2.3/2.4)
@@ -18,7 +26,10 @@ MIN_FLOAT = float(np.finfo(np.float32).min) / 100.0
 
 
 class TwoTowerOracle:
-    def __init__(self, n_users, n_items, E, S, seed=42, lr=0.1, dtype=torch.float32, rdZero=False):
+    def __init__(self, n_users, n_items, E, S, seed=42, lr=0.1, dtype=torch.float32, rdZero=False, matmul=torch.matmul):
+        # matmul: oracle/tf32.matmul gives the TF32-operand form of every product the tensor-core step computes
+        # (tower Dense layers and the in-batch score matrix, forward and both gradient products each)
+        self.mm = matmul
         rng = np.random.Generator(np.random.Philox(key=seed))
         npdt = np.float64 if dtype == torch.float64 else np.float32
 
@@ -37,8 +48,8 @@ class TwoTowerOracle:
 
     def towers(self, u_idx, i_idx):
         t = self.t
-        q = t["Eu"][torch.as_tensor(u_idx, dtype=torch.int64)] @ t["Wu"] + t["bu"]
-        c = t["Ei"][torch.as_tensor(i_idx, dtype=torch.int64)] @ t["Wi"] + t["bi"]
+        q = self.mm(t["Eu"][torch.as_tensor(u_idx, dtype=torch.int64)], t["Wu"]) + t["bu"]
+        c = self.mm(t["Ei"][torch.as_tensor(i_idx, dtype=torch.int64)], t["Wi"]) + t["bi"]
         return q, c
 
     def loss(self, u_idx, i_idx, cand_ids=None, labels=None):
@@ -47,7 +58,7 @@ class TwoTowerOracle:
             logit = (q * c).sum(1)
             y = torch.as_tensor(np.asarray(labels), dtype=self.dtype)
             return torch.nn.functional.binary_cross_entropy_with_logits(logit, y)
-        scores = q @ c.T
+        scores = self.mm(q, c.T)
         B = scores.shape[0]
         if cand_ids is not None:
             ids = torch.as_tensor(np.asarray(cand_ids))

@@ -125,3 +125,50 @@ def test_lazy_adam_moves_exactly_the_batch_rows_on_a_large_table(dev):
     # first Adam step with g > 0: every coordinate of a hit row moves by -lr (up to rounding)
     step = (tab.w - w0)[hit]
     torch.testing.assert_close(step, torch.full_like(step, -1e-3), rtol=1e-3, atol=1e-7)
+
+
+def test_bpr_twenty_bench_identical_steps_match_the_oracle(dev):
+    """BASELINE.json configs[1] exactly as bench.py runs it: 6040 x 3706, d = 64, batch 16 384, the bench frame, Philox
+    negatives (seed 7, epoch 0), twenty Keras-Adam steps from the seeded initial tables -- per-step loss and final tables
+    against oracle/bpr.py (fp32: loss rtol 1e-5; tables rtol 1e-4 / atol 2e-5 after 20 Adam steps)."""
+    from binrec_b200 import synth
+    from binrec_b200.BPRModel import BPRNet
+    from oracle import bpr as OB, philox as OP
+    users, items = synth.make_interactions()
+    U, I, d, B, K = synth.ML1M_USERS, synth.ML1M_ITEMS, 64, 16384, 20
+    net = BPRNet(U, I, d, seed=42, learning_rate=1e-3, sparse_adam="keras", device=dev)
+    net.set_training_pairs(users, items)
+    net.sample_negatives(7, 0)
+    losses = net.train_steps(list(range(K)), B).cpu().numpy()
+    orc = OB.BPROracle(U, I, d, seed=42)
+    indptr, sitems = OP.build_csr(users, items, U)
+    neg = OP.bpr_negatives(users[:K * B], 7, 0, I, indptr, sitems)
+    assert np.array_equal(net._pairs["n"][:K * B].cpu().numpy(), neg)            # sampled indices: bit-exact
+    ref = [orc.step(users[b * B:(b + 1) * B], items[b * B:(b + 1) * B], neg[b * B:(b + 1) * B]) for b in range(K)]
+    np.testing.assert_allclose(losses, np.asarray(ref, dtype=np.float32), rtol=1e-5)
+    np.testing.assert_allclose(net.user.w.cpu().numpy(), orc.user, rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(net.item.w.cpu().numpy(), orc.item, rtol=1e-4, atol=2e-5)
+
+
+def test_twotower_three_steps_at_baseline_shape_match_the_oracle(dev):
+    """BASELINE.json configs[2] shape: 6040 x 3706, E = S = 128, in-batch softmax batch 1000, Adagrad 0.1 -- three fp32 steps."""
+    from binrec_b200.twoTower import TwoTowerModel
+    from oracle import twotower as OT
+    U, I, E, S, B = 6040, 3706, 128, 128, 1000
+    m = TwoTowerModel(E, I, U, "u", "i", list(range(U)), list(range(I)), semb=S, device=dev)
+    m.compile("Adagrad", learningRate=0.1)
+    o = OT.TwoTowerOracle(U, I, E, S, seed=42)
+    with torch.no_grad():
+        o.t["Eu"].copy_(m.userTower.emb.w.cpu()); o.t["Ei"].copy_(m.itemTower.emb.w.cpu())
+        for tw, wn, bn in ((m.userTower, "Wu", "bu"), (m.itemTower, "Wi", "bi")):
+            flat = tw.dense.w.view(-1).cpu()
+            o.t[wn].copy_(flat[:E * S].view(E, S)); o.t[bn].copy_(flat[E * S:E * S + S])
+    rng = np.random.default_rng(0)
+    for step in range(3):
+        u = rng.integers(2, U + 2, B).astype(np.int32); i = rng.integers(2, I + 2, B).astype(np.int32)
+        lref = o.step(u, i, cand_ids=i)
+        lgot = m._step(torch.from_numpy(u).to(dev), torch.from_numpy(i).to(dev), None, True)
+        m.optimizer.apply([m.userTower.emb, m.itemTower.emb], dense=[m.userTower.dense, m.itemTower.dense])
+        np.testing.assert_allclose(lgot.item(), lref, rtol=1e-5)
+    np.testing.assert_allclose(m.userTower.emb.w.cpu().numpy(), o.t["Eu"].detach().numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(m.itemTower.emb.w.cpu().numpy(), o.t["Ei"].detach().numpy(), rtol=1e-4, atol=1e-5)

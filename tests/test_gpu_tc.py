@@ -278,20 +278,41 @@ def test_gemm_tf32_all_layouts_exact_on_representable_inputs(dev, M, N, K, ta, t
         assert np.array_equal(Cd.cpu().numpy(), ref.astype(np.float32)), (accumulate,)
 
 
-def test_twotower_tensor_core_step_matches_fp32_path(dev):
-    """TF32 tolerance for the two-tower step: loss rtol 2e-3; gradients max error <= 2 % of max|g|, Frobenius <= 2 %."""
+@pytest.mark.parametrize("U,I,E,S,B", [(500, 300, 128, 128, 1000), (6040, 3706, 128, 128, 1000), (300, 200, 64, 64, 2048)])
+def test_twotower_tensor_core_step_matches_tf32_oracle(dev, U, I, E, S, B):
+    """The two-tower step with every product on tcgen05 (TF32 operands; csrc/gemm_tc.cu) against oracle/twotower.py with
+    oracle/tf32.py's matmul: loss rtol 2e-3; gradients max |error| <= 1e-2 of the largest entry and Frobenius <= 1e-2
+    (no ReLU here: the graph is smooth, measured ~1e-4).  (6040, 3706, 128, 128, 1000) is BASELINE.json configs[2]."""
     from binrec_b200.twoTower import TwoTowerModel
-    U, I, B = 500, 300, 1000
-    mk = lambda tcf: TwoTowerModel(128, I, U, "u", "i", list(range(U)), list(range(I)), semb=128, device=dev, tensor_cores=tcf)
-    a, b = mk(False), mk(True)
+    from oracle import twotower as OT
+    m = TwoTowerModel(E, I, U, "u", "i", list(range(U)), list(range(I)), semb=S, device=dev, tensor_cores=True)
+    o = OT.TwoTowerOracle(U, I, E, S, seed=42, matmul=_tf32_matmul())
+    with torch.no_grad():                                          # identical weights: copy the device model's into the oracle
+        o.t["Eu"].copy_(m.userTower.emb.w.cpu()); o.t["Ei"].copy_(m.itemTower.emb.w.cpu())
+        for tw, wn, bn in ((m.userTower, "Wu", "bu"), (m.itemTower, "Wi", "bi")):
+            flat = tw.dense.w.view(-1).cpu()
+            o.t[wn].copy_(flat[:E * S].view(E, S)); o.t[bn].copy_(flat[E * S:E * S + S])
     g = torch.Generator(device=dev); g.manual_seed(3)
     uid = torch.randint(2, U + 2, (B,), generator=g, device=dev, dtype=torch.int32)
-    iid = torch.randint(2, I + 2, (B,), generator=g, device=dev, dtype=torch.int32)
-    la = a._step(uid, iid, None, True); lb = b._step(uid, iid, None, True)
-    np.testing.assert_allclose(lb.item(), la.item(), rtol=2e-3)
-    for ta, tb, name in ((a.userTower.emb, b.userTower.emb, "Eu"), (a.itemTower.emb, b.itemTower.emb, "Ei"),
-                         (a.userTower.dense, b.userTower.dense, "Wu"), (a.itemTower.dense, b.itemTower.dense, "Wi")):
-        g0, g1 = ta.g.cpu().numpy(), tb.g.cpu().numpy()
-        scale = np.abs(g0).max()
-        assert np.abs(g1 - g0).max() <= 0.02 * scale, name
-        assert np.linalg.norm((g1 - g0).ravel()) <= 0.02 * np.linalg.norm(g0.ravel()), name
+    iid = torch.randint(2, min(I, 400) + 2, (B,), generator=g, device=dev, dtype=torch.int32)   # repeated items: accidental hits
+    lref = o.loss_and_grads(uid.cpu().numpy(), iid.cpu().numpy(), cand_ids=iid.cpu().numpy())
+    lgot = m._step(uid, iid, None, True)
+    np.testing.assert_allclose(lgot.item(), float(lref), rtol=2e-3)
+    worst = (0.0, 0.0, "")
+    for got, name in ((m.userTower.emb.g, "Eu"), (m.itemTower.emb.g, "Ei"),
+                      (m.userTower.dense.g.view(-1)[:E * S].view(E, S), "Wu"), (m.itemTower.dense.g.view(-1)[:E * S].view(E, S), "Wi"),
+                      (m.userTower.dense.g.view(-1)[E * S:E * S + S], "bu")):
+        mx, rel, _, _ = _grad_err(got.cpu().numpy(), o.t[name].grad.numpy())
+        worst = max(worst, (mx, rel, name))
+        assert mx <= 1e-2 and rel <= 1e-2, (name, mx, rel)
+    print(f"two-tower TC U={U} B={B}: loss rel err {abs(lgot.item() - float(lref)) / abs(float(lref)):.2e}, worst gradient {worst}")
+    # three Adagrad steps at the same shape: the losses keep tracking the oracle
+    m.compile("Adagrad", learningRate=0.1)
+    m.userTower.emb.g.zero_(); m.itemTower.emb.g.zero_(); m.userTower.dense.g.zero_(); m.itemTower.dense.g.zero_()
+    for step in range(3):
+        uid = torch.randint(2, U + 2, (B,), generator=g, device=dev, dtype=torch.int32)
+        iid = torch.randint(2, I + 2, (B,), generator=g, device=dev, dtype=torch.int32)
+        lr_ = o.step(uid.cpu().numpy(), iid.cpu().numpy(), cand_ids=iid.cpu().numpy())
+        lg_ = m._step(uid, iid, None, True)
+        m.optimizer.apply([m.userTower.emb, m.itemTower.emb], dense=[m.userTower.dense, m.itemTower.dense])
+        np.testing.assert_allclose(lg_.item(), lr_, rtol=2e-3)
