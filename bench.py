@@ -109,8 +109,8 @@ class ClockSampler(threading.Thread):
 
 def traffic_bytes(world):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture (profiles/r01_traffic.json); N=1 only (ncu is never run on a multi-rank command)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    `ncu --set full` capture (profiles/r02_traffic.json); N=1 only (ncu is never run on a multi-rank command)."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if world != 1 or not os.path.exists(p):
         return None
     with open(p) as f:
@@ -697,6 +697,12 @@ def neumf_block(dev, peaks, which):
                                   ", ML-1M shape, 4 negatives / positive, Keras Adam(1e-3)", "batch": B,
                       "l2": "flushed between timed steps (value); back to back (value_hot_l2)",
                       "dtype": "tf32 operands, fp32 accumulation / parameters"}}
+    if which == "class":
+        tp = os.path.join(ROOT, "profiles", "r02_neumf_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            out["roofline"]["traffic"] = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
     del net, ds
     torch.cuda.empty_cache()
     return out

@@ -76,8 +76,10 @@ class NeuMFNet:
         npad = (n_dense + 3) // 4 * 4
         # one flat gradient arena (4 tables + dense block): data-parallel replicas all-reduce it once per step
         sizes = [self.numUser * E, self.numItem * E, self.numUser * EMF, self.numItem * EMF, npad]
-        self.grad_arena = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
-        views = list(torch.split(self.grad_arena, sizes))
+        # under torch.distributed the arena is NVLink peer-mapped memory and the per-step gradient sum is
+        # brk_allreduce_dense_peer (fixed-order sum, bit-identical replicas, no NCCL call on the step's path)
+        self.grad_arena, self._reducer = D.gradient_arena(sum(sizes), dev)
+        views = list(torch.split(self.grad_arena[:sum(sizes)], sizes))
 
         def emb(rows, width=E):
             return H.Table(torch.from_numpy(H.keras_embedding_init(rows, width, rng)).to(dev), touched=lazy, g=views.pop(0))
@@ -192,7 +194,7 @@ class NeuMFNet:
             loss = loss_out if loss_out is not None else torch.zeros(1, dtype=torch.float32, device=self.device)
             loss.zero_()
         if w > 1:
-            D.all_reduce_sum_(self.grad_arena)
+            D.all_reduce_sum_(self.grad_arena, self._reducer)
         self.optimizer.apply(self.tables(), dense=[self.dense])
         return loss, out
 

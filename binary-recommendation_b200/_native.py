@@ -112,6 +112,9 @@ SIGNATURES = {
                                          _I64, _I64, _I32, _U32, _U32, C.POINTER(brk_neumf_workspace), _P, _P, _P]),
     "brk_bpr_fwd_bwd_sharded": (C.c_int, [_P, C.POINTER(brk_shards), C.POINTER(brk_shards), _I32, _P, _P, _P, _I64, _I64, _P, _P]),
     "brk_peer_barrier": (C.c_int, [_P, _P, _P, _I32, _I32, _P]),
+    "brk_allreduce_dense_peer": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _P]),
+    "brk_gather_rows_sharded": (C.c_int, [_P, C.POINTER(brk_shards), _I32, _P, _I64, _P, _P]),
+    "brk_scatter_add_rows_sharded": (C.c_int, [_P, C.POINTER(brk_shards), _I32, _P, _I64, _P, _P]),
     "brk_tc_selftest": (C.c_int, [_P, _I32, _I32, _I32, _I32, _P, _I32, _I32, _P, _I32, _I32, _P, _P]),
     "brk_dp_adam_peer": (C.c_int, [_P, C.POINTER(brk_dp_peer), brk_adam_hyper, _P, _P]),
     "brk_bpr_train_steps_dp": (C.c_int, [_P, C.POINTER(brk_table), C.POINTER(brk_table), _P, _P, _P, _I64, _I64,

@@ -156,6 +156,56 @@ __global__ void __launch_bounds__(kThreads) dp_adam_peer_kernel(const DpParams P
     g_me[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// All-reduce (sum) of a flat fp32 arena over NVLink peer memory, in place on every rank: barrier in, every rank sums ITS
+// float4 slice over all peers' arenas (fixed order: identical bits everywhere) and stores the sum into that slice of
+// every peer's arena, barrier out.  The collective of a mirrored data-parallel step whose optimizer is not the fused
+// Adam above (Keras Adagrad of the two-tower model, lazy Adam): stands in for the gradient all-reduce of
+// MultiWorkerMirroredStrategy (src/models/RModel.py:119-121) without an NCCL call on the step's path.
+__global__ void __launch_bounds__(kThreads) allreduce_peer_kernel(float* const* peer_buf, uint32_t* const* peer_flags,
+                                                                  uint32_t* sync, int64_t n4, int me, int G, long long budget) {
+  const int t = threadIdx.x;
+  const uint32_t epoch = sync[3] + 1u;
+  uint32_t* my_flags = peer_flags[me];
+  if (blockIdx.x == 0) {
+    if (t < G) {
+      __threadfence_system();
+      st_release_sys(peer_flags[t] + me, epoch);
+      spin_until(my_flags + t, epoch, true, sync + 4, budget);
+    }
+    __syncthreads();
+    if (t == 0) st_release_gpu(sync + 0, epoch);
+  } else {
+    if (t == 0) spin_until(sync + 0, epoch, false, sync + 4, 2 * budget);
+    __syncthreads();
+  }
+  const bool dead = *reinterpret_cast<volatile uint32_t*>(sync + 4) != 0u;
+  const int64_t lo = n4 * me / G, hi = n4 * (me + 1) / G;
+  for (int64_t i = lo + int64_t(blockIdx.x) * kThreads + t; i < hi && !dead; i += int64_t(gridDim.x) * kThreads) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < G; ++p) {
+      const float4 x = *(reinterpret_cast<const float4*>(peer_buf[p]) + i);
+      g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+    }
+    for (int p = 0; p < G; ++p) *(reinterpret_cast<float4*>(peer_buf[p]) + i) = g;
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool s_last;
+  if (t == 0) s_last = atomicAdd(sync + 2, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    if (t < G && !dead) {
+      st_release_sys(peer_flags[t] + G + me, epoch);
+      spin_until(my_flags + G + t, epoch, true, sync + 4, budget);
+    }
+    __syncthreads();
+    if (t == 0) { sync[2] = 0u; sync[3] = epoch; __threadfence(); st_release_gpu(sync + 1, epoch); }
+  }
+  if (t == 0) spin_until(sync + 1, epoch, false, sync + 4, 2 * budget);
+  __syncthreads();
+}
+
 // Stand-alone cross-GPU barrier (one CTA): rank r posts epoch e on every peer's flag block and waits
 // until every peer has posted e on its own.  Used between the sharded fused step (whose REDs land in the
 // peers' accumulators) and the owners' optimizer pass.
@@ -193,6 +243,22 @@ extern "C" int brk_dp_adam_peer(brk_ctx* ctx, const brk_dp_peer* d, brk_adam_hyp
   void* args[] = {(void*)&P};
   BRK_CUDA(cudaLaunchCooperativeKernel((void*)dp_adam_peer_kernel, dim3(grid), dim3(kThreads), args, 0,
                                        (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int brk_allreduce_dense_peer(brk_ctx* ctx, float* const* peer_buf, uint32_t* const* peer_flags, uint32_t* local_sync,
+                                        int64_t n, int32_t rank, int32_t world, void* stream) {
+  BRK_REQUIRE(ctx && peer_buf && peer_flags && local_sync, BRK_E_ARG, "brk_allreduce_dense_peer: null argument");
+  BRK_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world && n > 0 && (n & 3) == 0, BRK_E_ARG,
+              "brk_allreduce_dense_peer: world=%d rank=%d n=%lld (n must be a multiple of 4)", world, rank, (long long)n);
+  const int64_t n4 = n / 4;
+  const int64_t need = (n4 / world + kThreads) / kThreads;
+  int grid = int(need < ctx->sm_count ? need : ctx->sm_count);
+  if (grid < 1) grid = 1;
+  long long budget = spin_budget_cycles();
+  void* args[] = {(void*)&peer_buf, (void*)&peer_flags, (void*)&local_sync, (void*)&n4, (void*)&rank, (void*)&world, (void*)&budget};
+  // every CTA spins on a flag another CTA sets: they must be co-resident -> cooperative launch
+  BRK_CUDA(cudaLaunchCooperativeKernel((void*)allreduce_peer_kernel, dim3(grid), dim3(kThreads), args, 0, (cudaStream_t)stream));
   return 0;
 }
 

@@ -254,3 +254,66 @@ extern "C" int brk_scatter_add_rows(brk_ctx* ctx, float* acc, int64_t rows, int3
   BRK_LAUNCH_CHECK();
   return 0;
 }
+
+
+// ---- row-sharded tables over NVLink peer memory: the "all-to-all of looked-up rows" and "of row gradients" as ops -------
+// Row r of the table lives on rank r % world at local row r / world (include/brk_b200.h, brk_shards).  The gather reads
+// peer rows with ordinary 16-byte loads, the scatter-add sends 16-byte REDs into the owner's accumulator and marks the
+// owner's touched bit: the exchange IS the memory instruction, there is no staging buffer and no separate collective.
+// (The fused NeuMF / BPR kernels do the same inline; these are the stand-alone forms.)
+namespace {
+__global__ void __launch_bounds__(256) gather_rows_sharded_kernel(brk_shards sh, int d4, const int32_t* __restrict__ ids, int64_t n,
+                                                                 float4* __restrict__ out, int lpr) {
+  const int64_t gt = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t row = gt / lpr; const int c = int(gt % lpr);
+  if (row >= n) return;
+  const int64_t id = __ldg(ids + row);
+  const int o = int(id % sh.world); const int64_t l = id / sh.world;
+  const float4* src = reinterpret_cast<const float4*>(sh.w[o]) + l * d4;
+  for (int k = c; k < d4; k += lpr) out[row * d4 + k] = ldg_nc_f4(src + k);
+}
+__global__ void __launch_bounds__(256) scatter_add_rows_sharded_kernel(brk_shards sh, int d4, const int32_t* __restrict__ ids, int64_t n,
+                                                                      const float4* __restrict__ vals, int lpr) {
+  const int64_t gt = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t row = gt / lpr; const int c = int(gt % lpr);
+  if (row >= n) return;
+  const int64_t id = __ldg(ids + row);
+  const int o = int(id % sh.world); const int64_t l = id / sh.world;
+  float* dst = sh.g[o] + l * d4 * 4;
+  for (int k = c; k < d4; k += lpr) red_add_f4(dst + 4 * k, __ldg(vals + row * d4 + k));
+  if (c == 0 && sh.touched[o] != nullptr) atomicOr(sh.touched[o] + (l >> 5), 1u << (l & 31));
+}
+}  // namespace
+
+extern "C" int brk_gather_rows_sharded(brk_ctx* ctx, const brk_shards* sh, int32_t d, const int32_t* ids, int64_t n, float* out,
+                                       void* stream) {
+  BRK_REQUIRE(ctx && sh && ids && out, BRK_E_ARG, "brk_gather_rows_sharded: null argument");
+  BRK_REQUIRE(sh->world >= 1 && sh->world <= BRK_MAX_PEERS && d > 0 && (d & 3) == 0 && n >= 0, BRK_E_ARG,
+              "brk_gather_rows_sharded: world=%d d=%d (d must be a multiple of 4)", sh->world, d);
+  for (int p = 0; p < sh->world; ++p)
+    BRK_REQUIRE(sh->w[p] && brk_aligned16(sh->w[p]), BRK_E_ALIGN, "brk_gather_rows_sharded: shard %d missing or not 16-byte aligned", p);
+  BRK_REQUIRE(brk_aligned16(out), BRK_E_ALIGN, "brk_gather_rows_sharded: out is not 16-byte aligned");
+  if (n == 0) return 0;
+  const int d4 = d / 4, lpr = brk_lanes_per_row(d4);
+  const int64_t threads = n * lpr;
+  gather_rows_sharded_kernel<<<unsigned((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*sh, d4, ids, n, reinterpret_cast<float4*>(out), lpr);
+  BRK_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int brk_scatter_add_rows_sharded(brk_ctx* ctx, const brk_shards* sh, int32_t d, const int32_t* ids, int64_t n,
+                                            const float* values, void* stream) {
+  BRK_REQUIRE(ctx && sh && ids && values, BRK_E_ARG, "brk_scatter_add_rows_sharded: null argument");
+  BRK_REQUIRE(sh->world >= 1 && sh->world <= BRK_MAX_PEERS && d > 0 && (d & 3) == 0 && n >= 0, BRK_E_ARG,
+              "brk_scatter_add_rows_sharded: world=%d d=%d (d must be a multiple of 4)", sh->world, d);
+  for (int p = 0; p < sh->world; ++p)
+    BRK_REQUIRE(sh->g[p] && brk_aligned16(sh->g[p]), BRK_E_ALIGN, "brk_scatter_add_rows_sharded: accumulator %d missing or not 16-byte aligned", p);
+  BRK_REQUIRE(brk_aligned16(values), BRK_E_ALIGN, "brk_scatter_add_rows_sharded: values are not 16-byte aligned");
+  if (n == 0) return 0;
+  const int d4 = d / 4, lpr = brk_lanes_per_row(d4);
+  const int64_t threads = n * lpr;
+  scatter_add_rows_sharded_kernel<<<unsigned((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(*sh, d4, ids, n,
+                                                                                                       reinterpret_cast<const float4*>(values), lpr);
+  BRK_LAUNCH_CHECK();
+  return 0;
+}

@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(NT) tc_fwd2(const Args A, const float* __restr
 // ---- phase 3: d2 = dropout(bn2(h2)); h3 = act(d2 W3 + b3); MF dot; logit, prediction, loss; then (training)
 //      head / layer-3 gradients and dd2 = d loss / d d2 with its BatchNorm-backward sums -----------------------
 template <int E, int H1, int H2, int H3, int ACT>
-__global__ void __launch_bounds__(NT) tc_head(const Args A, const float* __restrict__ img, int n_tiles) {
+__global__ void __launch_bounds__(NT, 2) tc_head(const Args A, const float* __restrict__ img, int n_tiles) {
   using L = Layout<E, H1, H2, H3>; using AC = Acc<H1, H2>; using I = Img<E, H1, H2, H3>;
   constexpr int N3 = I::N3, LPR = E / 4, RPP = NT / LPR, ZP = H3 + 1;
   uint8_t* sm = smem_base();

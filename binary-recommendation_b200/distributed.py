@@ -53,11 +53,60 @@ def barrier():
         dist.barrier()
 
 
-def all_reduce_sum_(flat):
-    """In-place sum over ranks of the flat gradient arena."""
-    if is_dist() and world_size() > 1:
+def all_reduce_sum_(flat, reducer=None):
+    """In-place sum over ranks of the flat gradient arena: over NVLink peer memory when the arena came from
+    gradient_arena() (brk_allreduce_dense_peer: no NCCL call on the step's path), else one NCCL all-reduce."""
+    if reducer is not None:
+        reducer.all_reduce_()
+    elif is_dist() and world_size() > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     return flat
+
+
+class PeerBuffer:
+    """A flat fp32 arena in NVLink peer-mapped (symmetric) memory with the flag block of brk_allreduce_dense_peer."""
+
+    def __init__(self, n_floats, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _native as N
+        self.n = (int(n_floats) + 3) // 4 * 4
+        self.device = device
+        group = dist.group.WORLD.group_name
+        self.buf = symm_mem.empty(self.n, dtype=torch.float32, device=device)
+        self.flags = symm_mem.empty(2 * 64, dtype=torch.int32, device=device)
+        hb = symm_mem.rendezvous(self.buf, group)
+        hf = symm_mem.rendezvous(self.flags, group)
+        self.buf.zero_(); self.flags.zero_()
+        self._ptrs = [torch.tensor(list(h.buffer_ptrs), dtype=torch.int64, device=device) for h in (hb, hf)]
+        self.local_sync = torch.zeros(8, dtype=torch.int32, device=device)
+        self._handles = (hb, hf)
+        torch.cuda.synchronize(device)
+        dist.barrier()                       # nobody posts a flag before everyone has zeroed its block
+
+    def all_reduce_(self):
+        from . import _native as N
+        N.check(N.lib().brk_allreduce_dense_peer(N.ctx(self.device), self._ptrs[0].data_ptr(), self._ptrs[1].data_ptr(),
+                                                 N.ptr(self.local_sync), self.n, rank(), world_size(), N.stream_ptr()),
+                "brk_allreduce_dense_peer")
+
+    def check(self):
+        if int(self.local_sync[4].item()) != 0:
+            raise RuntimeError("peer all-reduce: a cross-GPU barrier timed out (a rank did not reach the step); the step was "
+                               "aborted on this rank (BRK_PEER_SPIN_MS sets the wait budget, default 30 s)")
+
+
+def gradient_arena(n_floats, device):
+    """(flat fp32 tensor of >= n_floats zeros, reducer or None): under torch.distributed with peer access the arena is
+    symmetric memory and `reducer` sums it over the ranks through NVLink peer memory; otherwise a plain tensor (and
+    all_reduce_sum_ falls back to NCCL when there is more than one rank)."""
+    if is_dist() and world_size() > 1 and os.environ.get("BRK_DP", "peer") != "nccl":
+        try:
+            pb = PeerBuffer(n_floats, device)
+            return pb.buf, pb
+        except Exception as e:                # pragma: no cover - depends on the box
+            if rank() == 0:
+                print(f"[binrec_b200] symmetric memory unavailable ({e!r}); using NCCL all-reduce", flush=True)
+    return torch.zeros((int(n_floats) + 3) // 4 * 4, dtype=torch.float32, device=device), None
 
 
 def broadcast_(t, src=0):

@@ -178,10 +178,10 @@ class Adagrad:
         self.lr, self.eps = learning_rate, epsilon
         self.rows_threshold_bytes = rows_threshold_bytes
 
-    def apply(self, tables, dense=()):
+    def apply(self, tables, dense=(), force_dense=False):
         lib, st = N.lib(), N.stream_ptr()
         tables, dense = list(tables), list(dense)
-        big = [t for t in tables if t.bytes > self.rows_threshold_bytes and t.touched is not None]
+        big = [] if force_dense else [t for t in tables if t.bytes > self.rows_threshold_bytes and t.touched is not None]
         small = [t for t in tables if t not in big] + dense
         dev = (tables + dense)[0].w.device
         if small:
@@ -190,6 +190,23 @@ class Adagrad:
         if big:
             N.check(lib.brk_adagrad_rows(N.ctx(dev), _pack(big), len(big), self.lr, self.eps, st),
                     "brk_adagrad_rows")
+
+
+def gather_rows_sharded(shards, d, ids):
+    """Rows `ids` of a row-sharded table (row r on rank r % G at local row r // G; `shards`: _native.brk_shards with every
+    rank's peer-mapped shard pointers): the all-to-all of looked-up rows as plain peer loads (brk_gather_rows_sharded)."""
+    ids = _i32(ids, "ids")
+    out = torch.empty((ids.numel(), d), dtype=torch.float32, device=ids.device)
+    N.check(N.lib().brk_gather_rows_sharded(N.ctx(ids.device), C.byref(shards), d, N.ptr(ids), ids.numel(), N.ptr(out),
+                                            N.stream_ptr()), "brk_gather_rows_sharded")
+    return out
+
+
+def scatter_add_rows_sharded(shards, d, ids, values):
+    """values[b, :] added to the OWNER's accumulator row of ids[b] (16-byte REDs over NVLink, owner's touched bit set)."""
+    ids = _i32(ids, "ids"); values = _f32(values, "values")
+    N.check(N.lib().brk_scatter_add_rows_sharded(N.ctx(ids.device), C.byref(shards), d, N.ptr(ids), ids.numel(), N.ptr(values),
+                                                 N.stream_ptr()), "brk_scatter_add_rows_sharded")
 
 
 # ----------------------------------------------------------------------------------------------

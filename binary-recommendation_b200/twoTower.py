@@ -108,6 +108,15 @@ class TwoTowerModel:
         self.itemTower = Tower(nbrItem + 2, embedDim, semb, rng, self.device)
         self.userTower.init_dense(rng, self.device)
         self.itemTower.init_dense(rng, self.device)
+        # mirrored data parallelism: the four gradient accumulators become views of ONE flat arena in NVLink peer-mapped
+        # memory, summed over the ranks once per step by brk_allreduce_dense_peer (no NCCL call on the step's path)
+        self.grad_arena = self._reducer = None
+        if D.world_size() > 1:
+            tabs = [self.userTower.emb, self.itemTower.emb, self.userTower.dense, self.itemTower.dense]
+            sizes = [t.w.numel() for t in tabs]
+            self.grad_arena, self._reducer = D.gradient_arena(sum(sizes), self.device)
+            for t, v in zip(tabs, torch.split(self.grad_arena[:sum(sizes)], sizes)):
+                t.g = v.view(t.rows, t.d)
         self.bruteForceLayer = None
         self._candidates = None
         self.optimizer = None
@@ -200,8 +209,12 @@ class TwoTowerModel:
             self.compile()
         loss = self._step(u, i, labels, True, loss_out)
         if D.world_size() > 1:
-            for t in (self.userTower.emb, self.itemTower.emb, self.userTower.dense, self.itemTower.dense):
-                D.all_reduce_sum_(t.g)
+            D.all_reduce_sum_(self.grad_arena, self._reducer)
+            # the touched-row bitmasks are per rank: after the sum every rank applies the dense pass (rows nobody touched
+            # have g == 0 and do not move under Adagrad)
+            self.optimizer.apply([self.userTower.emb, self.itemTower.emb], dense=[self.userTower.dense, self.itemTower.dense],
+                                 force_dense=True)
+            return loss
         self.optimizer.apply([self.userTower.emb, self.itemTower.emb], dense=[self.userTower.dense, self.itemTower.dense])
         return loss
 

@@ -298,6 +298,14 @@ int brk_neumf_step_sharded(brk_ctx* ctx, const brk_neumf_model* m, const brk_neu
                            int64_t global_batch, int64_t first_index, int32_t training, uint32_t dropout_seed,
                            uint32_t dropout_epoch, const brk_neumf_workspace* ws, float* out, float* loss_out,
                            void* stream);
+/* The all-to-all of looked-up rows and of row gradients as stand-alone ops (SURVEY.md section 8b "a2a_rows"): gather
+ * out[b,:] = row ids[b] of the sharded table (peer loads), scatter-add values[b,:] into the OWNER's accumulator
+ * (16-byte REDs over NVLink, owner's touched bit set).  d % 4 == 0.  The same barriers as after brk_neumf_step_sharded
+ * apply before an owner consumes its accumulator. */
+int brk_gather_rows_sharded(brk_ctx* ctx, const brk_shards* sh, int32_t d, const int32_t* ids, int64_t n, float* out,
+                            void* stream);
+int brk_scatter_add_rows_sharded(brk_ctx* ctx, const brk_shards* sh, int32_t d, const int32_t* ids, int64_t n,
+                                 const float* values, void* stream);
 /* The fused BPR triplet forward/backward (brk_bpr_fwd_bwd) on row-sharded tables of width d. */
 int brk_bpr_fwd_bwd_sharded(brk_ctx* ctx, const brk_shards* user, const brk_shards* item, int32_t d,
                             const int32_t* u, const int32_t* p, const int32_t* n, int64_t batch,
@@ -332,6 +340,15 @@ typedef struct brk_dp_peer {
   int32_t rank, world;
 } brk_dp_peer;
 int brk_dp_adam_peer(brk_ctx* ctx, const brk_dp_peer* d, brk_adam_hyper h, int64_t* state, void* stream);
+/* In-place all-reduce (sum) of a flat fp32 arena over NVLink peer memory (SURVEY.md section 8b "allreduce_dense"): the
+ * gradient all-reduce of MultiWorkerMirroredStrategy (src/models/RModel.py:119-121) for steps whose optimizer is not
+ * the fused Adam above (Keras Adagrad of trainers/twoTower.py:278-279, lazy Adam).  peer_buf / peer_flags: DEVICE
+ * arrays of `world` pointers to each rank's symmetric arena (n floats, n % 4 == 0) and flag block (2*world uint32,
+ * zero before the first call); local_sync: 8 uint32, zero-initialised ([4] != 0 afterwards: a peer never arrived, the
+ * call was aborted and the arena left as it was).  Every rank sums its float4 slice over all peers in a fixed order
+ * and stores it to every peer: the result is bit-identical on all ranks.  No NCCL. */
+int brk_allreduce_dense_peer(brk_ctx* ctx, float* const* peer_buf, uint32_t* const* peer_flags, uint32_t* local_sync,
+                             int64_t n, int32_t rank, int32_t world, void* stream);
 /* The whole mirrored data-parallel BPR loop in ONE cooperative launch per rank: n_steps x (this rank's fused
  * fwd/bwd on batch batch_index_host[k] of its own u/p/n arrays, cross-GPU barrier, reduce-scatter + Adam +
  * all-gather over peer memory, cross-GPU barrier).  user / item must be adjacent views into this rank's arenas

@@ -76,8 +76,21 @@ def _worker(rank, world, port, ret):
         fi = torch.from_numpy(rng3.integers(0, I, nrows).astype(np.int32)).to(dev)
         fy = torch.from_numpy((rng3.random(nrows) < 0.3).astype(np.float32)).to(dev)
         nm2.train_steps(fu, fi, fy, 192, np.arange(6), epoch=1)
+        # two-tower mirrored step: per-replica in-batch softmax (each rank's negatives are its own batch, MirroredStrategy's
+        # per-replica loss), SUM-reduced gradients summed over the ranks through the NVLink peer all-reduce, Adagrad
+        from binrec_b200.twoTower import TwoTowerModel
+        tt = TwoTowerModel(32, I, U, "u", "i", list(range(U)), list(range(I)), semb=16, device=dev)
+        tt.compile("Adagrad", learningRate=0.1)
+        rng4 = np.random.default_rng(21)
+        for step in range(3):
+            tu = rng4.integers(2, U + 2, world * 128).astype(np.int32); ti_ = rng4.integers(2, I + 2, world * 128).astype(np.int32)
+            lo, hi = D.local_slice(world * 128)
+            tt._train_ids(torch.from_numpy(tu[lo:hi]).to(dev), torch.from_numpy(ti_[lo:hi]).to(dev), None)
+        if tt._reducer is not None:
+            tt._reducer.check()
         torch.cuda.synchronize()
         ret[rank] = dict(user=net.user.w.cpu().numpy(), item=net.item.w.cpu().numpy(), losses=losses,
+                         tt_Eu=tt.userTower.emb.w.cpu().numpy(), tt_Wi=tt.itemTower.W.cpu().numpy(), tt_peer=tt._reducer is not None,
                          fit_user=net3.user.w.cpu().numpy(), fit_item=net3.item.w.cpu().numpy(), fit_hist=list(net3.history["loss"]),
                          fit_user_m=sd["user_m"].numpy(), fit_item_v=sd["item_v"].numpy(), fit_t=int(sd["opt_state"][0]),
                          he_W1=nm2.param("W1").cpu().numpy(), he_uMLP=nm2.uMLP.w.cpu().numpy(), he_iMF=nm2.iMF.w.cpu().numpy(),
@@ -165,6 +178,26 @@ def test_mirrored_bpr_neumf_and_sharded_topk_two_gpus():
         np.testing.assert_allclose(ret[r]["he_W1"], ref4["W1"], rtol=1e-4, atol=2e-5)
         np.testing.assert_allclose(ret[r]["he_uMLP"], ref4["uMLP"], rtol=1e-4, atol=2e-5)
         np.testing.assert_allclose(ret[r]["he_iMF"], ref4["iMF"], rtol=1e-4, atol=2e-5)
+    # two-tower: the oracle with the two replicas' losses summed
+    from oracle import twotower as OTT
+    o5 = OTT.TwoTowerOracle(U, I, 32, 16, seed=42)
+    rng4 = np.random.default_rng(21)
+    for step in range(3):
+        tu = rng4.integers(2, U + 2, world * 128).astype(np.int32); ti_ = rng4.integers(2, I + 2, world * 128).astype(np.int32)
+        for v in o5.t.values():
+            v.grad = None
+        tot = sum(o5.loss(tu[r * 128:(r + 1) * 128], ti_[r * 128:(r + 1) * 128], cand_ids=ti_[r * 128:(r + 1) * 128]) for r in range(world))
+        tot.backward()
+        with torch.no_grad():
+            for k, w in o5.t.items():
+                g = w.grad if w.grad is not None else torch.zeros_like(w)
+                o5.acc[k] += g * g
+                w -= o5.lr * g / (o5.acc[k].sqrt() + 1e-7)
+    for r in range(world):
+        assert ret[r]["tt_peer"], "the two-tower gradient sum should run over NVLink peer memory on this box"
+        np.testing.assert_allclose(ret[r]["tt_Eu"], o5.t["Eu"].detach().numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(ret[r]["tt_Wi"], o5.t["Wi"].detach().numpy(), rtol=1e-4, atol=1e-5)
+    assert np.array_equal(ret[0]["tt_Eu"], ret[1]["tt_Eu"])
     assert np.array_equal(ret[0]["user"], ret[1]["user"]) and np.array_equal(ret[0]["neumf_W1"], ret[1]["neumf_W1"])
     assert np.array_equal(ret[0]["neumf_uMLP"], ret[1]["neumf_uMLP"])
     Q = (np.random.default_rng(4).integers(-4, 5, size=(77, 64)) / 8.0).astype(np.float32)

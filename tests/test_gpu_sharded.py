@@ -192,3 +192,29 @@ def test_sharded_neumf_two_gpus_matches_unsharded(mode):
     if mode == "peer":
         np.testing.assert_allclose(ret[(mode, 0)]["bpr_user"], bref.user.w.cpu().numpy(), rtol=1e-5, atol=2e-6)
         np.testing.assert_allclose(ret[(mode, 0)]["bpr_item"], bref.item.w.cpu().numpy(), rtol=1e-5, atol=2e-6)
+
+
+def test_standalone_sharded_gather_and_scatter_add(dev):
+    """brk_gather_rows_sharded / brk_scatter_add_rows_sharded (the all-to-all of rows and of row gradients as ops) with
+    the G shards of one table held by one process: bit-exact gather, exact integer scatter-add into the owners'
+    accumulators, owners' touched bits == the distinct ids."""
+    from binrec_b200 import hotpath as H
+    from binrec_b200.sharded import ShardedTable
+    rng = np.random.default_rng(0)
+    for G, rows, d in ((3, 1000, 64), (8, 4097, 32), (2, 77, 8)):
+        full = rng.integers(-8, 9, size=(rows, d)).astype(np.float32)
+        tab = ShardedTable(rows, d, G, 0, dev, full_init=full, symmetric=False, emulate=True)
+        ids = torch.from_numpy((rows * rng.random(5000) ** 2).astype(np.int32)).to(dev)
+        out = H.gather_rows_sharded(tab.c_shards(), d, ids)
+        assert np.array_equal(out.cpu().numpy(), full[ids.cpu().numpy()])
+        vals = torch.from_numpy(rng.integers(-4, 5, size=(5000, d)).astype(np.float32)).to(dev)
+        H.scatter_add_rows_sharded(tab.c_shards(), d, ids, vals)
+        ref = np.zeros((rows, d), np.float32)
+        np.add.at(ref, ids.cpu().numpy(), vals.cpu().numpy())
+        for r in range(G):
+            mine = ref[r::G]
+            assert np.array_equal(tab.tables[r].g.cpu().numpy()[:len(mine)], mine)
+            bits = np.zeros(tab.local_rows, bool); loc = np.unique(ids.cpu().numpy()[ids.cpu().numpy() % G == r] // G); bits[loc] = True
+            words = tab.tables[r].touched.cpu().numpy().view(np.uint32)
+            got = ((words[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(bool).reshape(-1)[:tab.local_rows]
+            assert np.array_equal(got, bits)
