@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import _native as N
+from . import _torchext as T
 from . import distributed as D
 from . import hotpath as H
 from . import pipeline as PL
@@ -181,6 +182,20 @@ class NeuMFNet:
             out = out if out is not None else torch.empty(B, dtype=torch.float32, device=self.device)
             loss_out = loss_out if loss_out is not None else torch.empty(1, dtype=torch.float32, device=self.device)
             m, ws, opt = self._c_model(), self._workspace(B), self.optimizer
+            if T.ops() is not None and opt.sparse == "keras":
+                # the PyTorch-extension route: one custom op, tensors in (torch.ops.brk.neumf_train_step)
+                tabs = self.tables() + [self.dense]
+                h1, h2, h3 = self.hidden
+                b = self._bufs
+                T.ops().neumf_train_step([t.w for t in tabs], [t.g for t in tabs], [t.m for t in tabs], [t.v for t in tabs],
+                                         self.bn_moving, [self.E, h1, h2, h3, 0 if self.act == "relu" else 1,
+                                                          0 if self.loss == "mse" else 1, 1 if self.dropout > 0 else 0,
+                                                          1 if self.tensor_cores else 0, self.EMF,
+                                                          1 if self.mf_mode == "hadamard" else 0, 0 if self.batch_norm else 1],
+                                         H._i32(u, "u"), H._i32(i, "i"), H._f32(y, "y"), int(first_index),
+                                         self.dropout_seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, opt.h.lr, opt.h.beta1, opt.h.beta2,
+                                         opt.h.eps, opt.state, b["h1"], b["h2"], b["dy1"], b["dy2"], b["acc"], out, loss_out)
+                return loss_out, out
             N.check(N.lib().brk_neumf_train_step(
                 N.ctx(self.device), C.byref(m), N.ptr(H._i32(u, "u")), N.ptr(H._i32(i, "i")), N.ptr(H._f32(y, "y")), B,
                 first_index, self.dropout_seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, opt.h, N.ptr(opt.state),

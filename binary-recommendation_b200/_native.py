@@ -201,6 +201,8 @@ def ctx(device=None):
                 check(lib().brk_create(C.byref(out), dev), "brk_create")
                 h = out
                 _ctx[dev] = h
+                from . import _torchext
+                _torchext.share_ctx(dev, h.value)            # the torch-extension ops use the same context
     return h
 
 

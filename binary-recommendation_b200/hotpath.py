@@ -8,6 +8,7 @@ import numpy as np
 import torch
 
 from . import _native as N
+from . import _torchext as T
 
 
 def _i32(t, name):
@@ -31,6 +32,9 @@ def gather_rows(table, ids, out=None):
     table = _f32(table, "table"); ids = _i32(ids, "ids")
     rows, d = table.shape
     n = ids.numel()
+    if out is None and T.ops() is not None:
+        N.ctx(table.device)
+        return T.ops().gather_rows(table, ids)
     if out is None:
         out = torch.empty((n, d), dtype=torch.float32, device=table.device)
     N.check(N.lib().brk_gather_rows(N.ctx(table.device), N.ptr(table), rows, d, N.ptr(ids), n, N.ptr(out),
@@ -54,6 +58,10 @@ def scatter_add_rows(acc, ids, vals, touched=None, mode=0):
     rows, d = acc.shape
     if mode == "auto":
         mode = 1 if (ids.numel() >= 4096 and index_skew(ids) >= 0.01) else 0
+    if T.ops() is not None:
+        N.ctx(acc.device)
+        T.ops().scatter_add_rows(acc, ids, vals, touched, int(mode))
+        return acc
     N.check(N.lib().brk_scatter_add_rows(N.ctx(acc.device), N.ptr(acc), rows, d, N.ptr(ids), ids.numel(),
                                          N.ptr(vals), N.ptr(touched), mode, N.stream_ptr()),
             "brk_scatter_add_rows")
@@ -75,6 +83,10 @@ def philox_bpr_negatives(users, seed, epoch, num_items, csr_indptr, csr_items, f
     users = _i32(users, "users")
     if csr_indptr.dtype != torch.int64 or csr_items.dtype != torch.int32:
         raise TypeError("csr_indptr must be int64 and csr_items int32")
+    if out is None and T.ops() is not None:
+        N.ctx(users.device)
+        return T.ops().philox_bpr_negatives(users, seed & 0xFFFFFFFF, epoch & 0xFFFFFFFF, int(num_items), csr_indptr, csr_items,
+                                            int(first_index))
     if out is None:
         out = torch.empty_like(users)
     N.check(N.lib().brk_philox_bpr_negatives(N.ctx(users.device), N.ptr(users), users.numel(), first_index,
@@ -247,6 +259,9 @@ def rows_to_bf16(x):
     """fp32 [rows, d] -> bf16 [rows, dpad] (zero padded to a multiple of 64 columns)."""
     x = _f32(x, "x")
     rows, d = x.shape
+    if T.ops() is not None:
+        N.ctx(x.device)
+        return T.ops().rows_to_bf16(x)
     dpad = N.lib().brk_bf16_padded_dim(d)
     out = torch.empty((rows, dpad), dtype=torch.bfloat16, device=x.device)
     N.check(N.lib().brk_rows_to_bf16(N.ctx(x.device), N.ptr(x), rows, d, N.ptr(out), dpad, N.stream_ptr()),
@@ -292,6 +307,11 @@ class BruteForceIndex:
         if U == 0:
             return vals, ids
         q = rows_to_bf16(queries)
+        if T.ops() is not None:
+            vals, ids = T.ops().score_topk(q, self._c, k, self.id_offset)
+            if self._identifiers is not None:
+                return vals, self._identifiers[(ids - self.id_offset).long()]
+            return vals, ids
         lib, ctx = N.lib(), N.ctx(dev)
         ws_bytes = lib.brk_score_topk_workspace_bytes(ctx, U, self.num_candidates, k)
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
@@ -341,6 +361,9 @@ def topk_merge(part_vals, part_ids):
     """Merges [S, U, k] partial lists (global ids) into [U, k]: score desc, id asc."""
     part_vals = _f32(part_vals, "part_vals"); part_ids = _i32(part_ids, "part_ids")
     S, U, k = part_vals.shape
+    if T.ops() is not None:
+        N.ctx(part_vals.device)
+        return T.ops().topk_merge(part_vals, part_ids)
     vals = torch.empty((U, k), dtype=torch.float32, device=part_vals.device)
     ids = torch.empty((U, k), dtype=torch.int32, device=part_vals.device)
     N.check(N.lib().brk_topk_merge(N.ctx(part_vals.device), N.ptr(part_vals), N.ptr(part_ids), S, U, k,

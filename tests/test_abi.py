@@ -50,3 +50,19 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_torch_extension_loads_and_registers_the_ops():
+    """The PyTorch-extension face of the boundary (csrc_torch/brk_torch.cpp -> libbrk_torch.so): loads without a GPU and
+    registers every op under torch.ops.brk; compute calls need a GPU (tests/test_gpu_torchext.py)."""
+    import torch
+    from binrec_b200 import _torchext as T
+    assert os.path.exists(T.LIB_PATH), "build it with __graft_entry__.build()"
+    o = T.ops()
+    assert o is not None and int(o.abi_version()) == 2
+    for name in ("gather_rows", "scatter_add_rows", "philox_bpr_negatives", "bpr_fwd_bwd", "adam_dense_keras", "rows_to_bf16",
+                 "score_topk", "topk_merge", "neumf_train_step", "use_ctx"):
+        assert hasattr(o, name), name
+    import pytest
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        o.gather_rows(torch.zeros(4, 4), torch.zeros(2, dtype=torch.int32))
