@@ -41,10 +41,13 @@ __device__ __forceinline__ RowRef locate(const TabRef& T, int64_t row) {
   RowRef r; r.w = T.w[o] + l * E; r.g = T.g[o] ? T.g[o] + l * E : nullptr; r.t = T.t[o]; r.lrow = l;
   return r;
 }
+// Touched bit of a row: one fire-and-forget RED.OR.  (Round 1 peeked at the word first with a volatile load to skip
+// redundant REDs; at configs[3] table sizes every peek is a dependent HBM round trip, volatile loads do not overlap, and
+// tc_head issued 16 of them in a row per tile: ncu put most of that kernel's samples on the instruction consuming them.)
 __device__ __forceinline__ void mark_row(const RowRef& r) {
   if (r.t) {
     const uint32_t bit = 1u << (r.lrow & 31);
-    if (!(*(volatile const uint32_t*)(r.t + (r.lrow >> 5)) & bit)) atomicOr(r.t + (r.lrow >> 5), bit);
+    asm volatile("red.global.or.b32 [%0], %1;" ::"l"(r.t + (r.lrow >> 5)), "r"(bit) : "memory");
   }
 }
 

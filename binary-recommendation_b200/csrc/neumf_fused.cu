@@ -63,7 +63,9 @@ struct Spec {
   static constexpr int ND = ob4 + 1, NDP = (ND + 3) & ~3;                // dense block length
   // per-tile slot of partial sums (floats): BN forward sums of layers 1, 2; BN backward sums of layers 2, 1; the
   // tile's dense gradients; the tile's loss (a double)
-  static constexpr int pS1 = 0, pS2 = pS1 + 2 * H1, pD2 = pS2 + 2 * H2, pD1 = pD2 + 2 * H2, pDense = pD1 + 2 * H1;
+  // the four BatchNorm exchanges use TAGGED 64-bit words {value | launch tag << 32} (2 H words each: sum A, sum B):
+  // readers poll the data itself, there is no separate barrier for them
+  static constexpr int pS1 = 0, pS2 = pS1 + 4 * H1, pD2 = pS2 + 4 * H2, pD1 = pD2 + 4 * H2, pDense = pD1 + 4 * H1;
   static constexpr int pLoss = pDense + NDP, PT = pLoss + 4;             // all multiples of 4 floats
   // shared memory (bytes); every tile is a multiple of 1024 B
   static constexpr int szP = TS * K0 * 4, szT = TS * PH * 4;
@@ -89,6 +91,7 @@ struct Extra {
   int32_t coop;                // 1: cooperative launch (slots + grid barriers); 0: independent tiles (atomics + last-CTA ticket)
   unsigned int* bar;           // [0] arrival counter of the grid barrier (never reset), [1] time-out flag
   unsigned int bar_base;       // value of the counter when this launch starts (the host keeps the running total)
+  unsigned int tag;            // launch tag of the self-validating slot words (unique per launch on this context, never 0)
   // exact Keras Adam inside the same launch (after the last barrier): do_adam != 0
   int32_t do_adam;
   brk_adam_hyper hyp;
@@ -166,6 +169,74 @@ __device__ __forceinline__ void cta_feature_sums(float (&a)[HC], float (&b)[HC],
     for (int qq = 0; qq < 4; ++qq) { sa += part[(0 * 8 + hh * 4 + qq) * 32 + j]; sb += part[(1 * 8 + hh * 4 + qq) * 32 + j]; }
     slotA[t] = sa;
     slotB[t] = sb;
+  }
+  __syncthreads();
+}
+// The same two sums as SELF-VALIDATING words: word f (f < 2 HC) = {sum A of feature f | tag << 32}, word 2 HC + f = sum B.
+// A 64-bit store is single-copy atomic, so a reader that sees the tag sees the value: no fence, no flag, no barrier.
+// plainA / plainB (optional): the same sums as plain floats (the tile's BatchNorm parameter gradients in its dense slot).
+template <int HC>
+__device__ __forceinline__ void cta_feature_sums_tagged(float (&a)[HC], float (&b)[HC], float* part, unsigned long long* words,
+                                                        uint32_t tag, float* plainA, float* plainB) {
+  constexpr int SH = 5 - ilog2(HC);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  warp_feat_reduce<HC>(a);
+  warp_feat_reduce<HC>(b);
+  if ((lane & ((1 << SH) - 1)) == 0) {
+    part[(0 * 8 + warp) * 32 + (lane >> SH)] = a[0];
+    part[(1 * 8 + warp) * 32 + (lane >> SH)] = b[0];
+  }
+  __syncthreads();
+  if (t < 2 * HC) {
+    const int hh = t / HC, j = t % HC;
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) { sa += part[(0 * 8 + hh * 4 + qq) * 32 + j]; sb += part[(1 * 8 + hh * 4 + qq) * 32 + j]; }
+    const unsigned long long hi = static_cast<unsigned long long>(tag) << 32;
+    asm volatile("st.global.cg.u64 [%0], %1;" ::"l"(words + t), "l"(hi | __float_as_uint(sa)) : "memory");
+    asm volatile("st.global.cg.u64 [%0], %1;" ::"l"(words + 2 * HC + t), "l"(hi | __float_as_uint(sb)) : "memory");
+    if (plainA != nullptr) { plainA[t] = sa; plainB[t] = sb; }
+  }
+  __syncthreads();
+}
+// Totals over all tiles of W tagged words (W = 2 H): every thread takes one 16-byte pair of words and every
+// (NT / (W / 2))-th tile, eight loads in flight, and re-reads a word until it carries this launch's tag -- the wait for
+// the slowest tile and the data transfer are the same round trip.  Summed per thread in tile order, in double.
+// scratch: (NT / (W / 2)) * W doubles of shared memory; tot: W doubles.  Bounded: a tile that never arrives raises err.
+template <int W>
+__device__ __forceinline__ void gather_tagged(const unsigned long long* base, int stride64, int n_tiles, uint32_t tag, double* scratch,
+                                              double* tot, unsigned int* err) {
+  constexpr int C2 = W / 2, G = NT / C2;
+  static_assert(W % 2 == 0 && NT % C2 == 0, "slot width");
+  const int t = threadIdx.x, f2 = t % C2, g = t / C2;
+  double a0 = 0.0, a1 = 0.0;
+  const long long t0 = clock64();
+  for (int j0 = g; j0 < n_tiles; j0 += 8 * G) {
+    ulonglong2 v[8];
+#pragma unroll
+    for (int q8 = 0; q8 < 8; ++q8) {
+      const int j = j0 + q8 * G;
+      if (j < n_tiles) v[q8] = __ldcg(reinterpret_cast<const ulonglong2*>(base + size_t(j) * stride64) + f2);
+    }
+#pragma unroll
+    for (int q8 = 0; q8 < 8; ++q8) {
+      const int j = j0 + q8 * G;
+      if (j < n_tiles) {
+        while (uint32_t(v[q8].x >> 32) != tag || uint32_t(v[q8].y >> 32) != tag) {
+          if (clock64() - t0 > 4000000000LL) { atomicExch(err, 1u); break; }
+          v[q8] = __ldcg(reinterpret_cast<const ulonglong2*>(base + size_t(j) * stride64) + f2);
+        }
+        a0 += double(__uint_as_float(uint32_t(v[q8].x))); a1 += double(__uint_as_float(uint32_t(v[q8].y)));
+      }
+    }
+  }
+  scratch[g * W + 2 * f2] = a0; scratch[g * W + 2 * f2 + 1] = a1;
+  __syncthreads();
+  if (t < W) {
+    double tt = 0.0;
+#pragma unroll
+    for (int gg = 0; gg < G; ++gg) tt += scratch[gg * W + t];
+    tot[t] = tt;
   }
   __syncthreads();
 }
@@ -412,8 +483,6 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
       alpha_s = float(double(X.hyp.lr) * sqrt(1.0 - p2) / (1.0 - p1));
     }
     __syncthreads();
-    if (BN)
-      for (int k = 0; k < 4; ++k) grid_barrier(X.bar, bar_target);
     dense_reduce_and_adam<S>(A, X, bar_target, reinterpret_cast<float4*>(Q), alpha_s);
     return;
   }
@@ -531,9 +600,8 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
     float a[HC1], b[HC1];
 #pragma unroll
     for (int j = 0; j < HC1; ++j) { a[j] = h1[j]; b[j] = h1[j] * h1[j]; }
-    cta_feature_sums<HC1>(a, b, part, slot + S::pS1, slot + S::pS1 + H1);
-    grid_barrier(X.bar, bar_target);
-    reduce_slots<2 * H1>(X.part + S::pS1, S::PT, X.n_tiles, dred, tot);
+    cta_feature_sums_tagged<HC1>(a, b, part, reinterpret_cast<unsigned long long*>(slot + S::pS1), X.tag, nullptr, nullptr);
+    gather_tagged<2 * H1>(reinterpret_cast<const unsigned long long*>(X.part + S::pS1), S::PT / 2, X.n_tiles, X.tag, dred, tot, X.bar + 1);
     for (int f = t; f < H1; f += NT) {
       const double m = tot[f] / double(A.B);
       const double var = fmax(tot[H1 + f] / double(A.B) - m * m, 0.0);
@@ -587,11 +655,10 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
 #pragma unroll
     for (int j = 0; j < HC2; ++j) { a[j] = h2[j]; b[j] = h2[j] * h2[j]; }
     stamp(X, 12);
-    cta_feature_sums<HC2>(a, b, part, slot + S::pS2, slot + S::pS2 + H2);
+    cta_feature_sums_tagged<HC2>(a, b, part, reinterpret_cast<unsigned long long*>(slot + S::pS2), X.tag, nullptr, nullptr);
     stamp(X, 13);
-    grid_barrier(X.bar, bar_target);
     stamp(X, 14);
-    reduce_slots<2 * H2>(X.part + S::pS2, S::PT, X.n_tiles, dred, tot);
+    gather_tagged<2 * H2>(reinterpret_cast<const unsigned long long*>(X.part + S::pS2), S::PT / 2, X.n_tiles, X.tag, dred, tot, X.bar + 1);
     stamp(X, 15);
     for (int f = t; f < H2; f += NT) {
       const double m = tot[f] / double(A.B);
@@ -748,10 +815,9 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
 #pragma unroll
       for (int j = 0; j < HC2; ++j) { a[j] = dy2[j]; b[j] = dy2[j] * ((h2[j] - mean2[c2 + j]) * rstd2[c2 + j]); }
       // the tile's sums are also its share of the BatchNorm parameter gradients: d beta = sum dy, d gamma = sum dy xhat
-      cta_feature_sums<HC2>(a, b, part, dp + S::obe2, dp + S::og2);
-      grid_barrier(X.bar, bar_target);
-      reduce_slots<2 * H2>(X.part + S::pDense + S::og2, S::PT, X.n_tiles, dred, tot);   // [gamma | beta] slots are adjacent
-      for (int f = t; f < H2; f += NT) { sdyx2[f] = float(tot[f] / double(A.B)); sdy2[f] = float(tot[H2 + f] / double(A.B)); }
+      cta_feature_sums_tagged<HC2>(a, b, part, reinterpret_cast<unsigned long long*>(slot + S::pD2), X.tag, dp + S::obe2, dp + S::og2);
+      gather_tagged<2 * H2>(reinterpret_cast<const unsigned long long*>(X.part + S::pD2), S::PT / 2, X.n_tiles, X.tag, dred, tot, X.bar + 1);
+      for (int f = t; f < H2; f += NT) { sdy2[f] = float(tot[f] / double(A.B)); sdyx2[f] = float(tot[H2 + f] / double(A.B)); }
       __syncthreads();
     }
 
@@ -806,10 +872,9 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
       float a[HC1], b[HC1];
 #pragma unroll
       for (int j = 0; j < HC1; ++j) { a[j] = dy1[j]; b[j] = dy1[j] * ((h1[j] - mean1[c1 + j]) * rstd1[c1 + j]); }
-      cta_feature_sums<HC1>(a, b, part, dp + S::obe1, dp + S::og1);
-      grid_barrier(X.bar, bar_target);
-      reduce_slots<2 * H1>(X.part + S::pDense + S::og1, S::PT, X.n_tiles, dred, tot);
-      for (int f = t; f < H1; f += NT) { sdyx1[f] = float(tot[f] / double(A.B)); sdy1[f] = float(tot[H1 + f] / double(A.B)); }
+      cta_feature_sums_tagged<HC1>(a, b, part, reinterpret_cast<unsigned long long*>(slot + S::pD1), X.tag, dp + S::obe1, dp + S::og1);
+      gather_tagged<2 * H1>(reinterpret_cast<const unsigned long long*>(X.part + S::pD1), S::PT / 2, X.n_tiles, X.tag, dred, tot, X.bar + 1);
+      for (int f = t; f < H1; f += NT) { sdy1[f] = float(tot[f] / double(A.B)); sdyx1[f] = float(tot[H1 + f] / double(A.B)); }
       __syncthreads();
     }
 
@@ -962,6 +1027,8 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
   stamp(X, 11);
 }
 
+unsigned int g_launch_tag = 0;   // launch tags of the self-validating slot words: one sequence for every instance and context
+
 struct AdamReq {                 // optional: exact Keras Adam in the same launch (single process, mirrored tables)
   const brk_neumf_model* m;
   brk_adam_hyper h;
@@ -1007,13 +1074,16 @@ int run(brk_ctx* ctx, const Args& A, const AdamReq* adam, cudaStream_t st, int* 
     if (ctx->neumf_part) BRK_CUDA(cudaFree(ctx->neumf_part));
     ctx->neumf_part = nullptr; ctx->neumf_part_floats = 0;
     BRK_CUDA(cudaMalloc(&ctx->neumf_part, need * sizeof(float)));
+    BRK_CUDA(cudaMemsetAsync(ctx->neumf_part, 0, need * sizeof(float), st));   // no stale word may carry a future tag
     ctx->neumf_part_floats = need;
   }
   X.part = ctx->neumf_part; X.coop = 1;
   // helper CTAs up to one per SM: the final reduction / Adam phase is spread over the whole GPU even for a small batch
   const unsigned grid = unsigned(n_tiles > ctx->sm_count ? n_tiles : (ctx->sm_count < max_blocks ? ctx->sm_count : max_blocks));
   X.bar = bar; X.bar_base = bar_count;
-  bar_count += grid * (S::BN ? 5u : 1u);                     // barriers of one training launch
+  bar_count += grid;                                         // ONE counter barrier per training launch (before the reduction / Adam)
+  X.tag = ++g_launch_tag;
+  if (X.tag == 0u) X.tag = ++g_launch_tag;
   if (adam != nullptr) {
     const brk_table* tb[4] = {&adam->m->uMLP, &adam->m->iMLP, &adam->m->uMF, &adam->m->iMF};
     for (int k = 0; k < 4; ++k) {
