@@ -473,6 +473,11 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
   uint32_t phase = 0;
   const int c1 = hf * HC1, c2 = hf * HC2;            // first column of this thread's half in layers 1 / 2
   stamp(X, 0);
+  if (X.trace != nullptr && t == 0 && blockIdx.x < 480) {   // which SM runs this CTA (trace words 32 ..)
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    X.trace[32 + blockIdx.x] = smid;
+  }
 
   if (int(blockIdx.x) >= X.n_tiles) {
     // helper CTA of a cooperative training launch (grid = max(tiles, SMs)): no tile, only the barriers and its share of
@@ -1042,7 +1047,7 @@ int run(brk_ctx* ctx, const Args& A, const AdamReq* adam, cudaStream_t st, int* 
   static unsigned int bar_count = 0;                        // host mirror of the counter (launches are stream-ordered)
   auto fn = fused_step<S>;
   if (max_blocks < 0) {
-    BRK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(S::smem)));
+    BRK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(S::smem > 120 * 1024 ? S::smem : 120 * 1024)));
     int per_sm = 0;
     BRK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NT, S::smem));
     const int by_tmem = 512 / S::TCOLS;                     // TMEM columns per SM
@@ -1100,7 +1105,12 @@ int run(brk_ctx* ctx, const Args& A, const AdamReq* adam, cudaStream_t st, int* 
     X.do_adam = 1; X.hyp = adam->h; X.adam_state = adam->state;
   }
   void* args[] = {(void*)&Ac, (void*)&X};
-  BRK_CUDA(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid), dim3(NT), args, S::smem, st));
+  // A grid of at most one CTA per SM must also RUN one per SM: with room for two CTAs the block scheduler may pack pairs
+  // onto one SM and leave others idle, and every barrier then waits for the slow pairs.  Asking for more than half of the
+  // SM's shared memory forces the spread.
+  size_t smem = S::smem;
+  if (int(grid) <= ctx->sm_count && smem < size_t(120) * 1024 && getenv("BRK_NEUMF_PACK") == nullptr) smem = size_t(120) * 1024;
+  BRK_CUDA(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid), dim3(NT), args, smem, st));
   return 0;
 }
 

@@ -14,7 +14,7 @@ for tag, kw in (("class spec", dict(dropout=0.2, tensor_cores=True)),
                 ("He variant", dict(dropout=0.0, mf_dim=8, mf_mode="hadamard", batch_norm=False))):
     if E != 32 and tag == "He variant":
         continue
-    trace = torch.zeros(16, dtype=torch.int64, device=dev)
+    trace = torch.zeros(32 + 480, dtype=torch.int64, device=dev)
     os.environ["BRK_NEUMF_TRACE"] = hex(trace.data_ptr())
     net = NeuMFNet(U, I, E, device=dev, **kw)
     g = torch.Generator(device=dev); g.manual_seed(0)
@@ -28,6 +28,8 @@ for tag, kw in (("class spec", dict(dropout=0.2, tensor_cores=True)),
     print(f"{tag} E={E} B={B}: block 0 phases (us since entry; delta)")
     for k in range(1, 12):
         print(f"  {NAMES[k]:44s} {(t[k] - t[0]) / 1e3:8.2f}  (+{(t[k] - t[k - 1]) / 1e3:6.2f})")
+    sm = t[32:32 + 148]
+    print(f"  CTAs 0..147 run on {len(set(sm.tolist()))} distinct SMs")
     if t[12]:
         print(f"  inside the BN2 barrier phase: h2 read {(t[12] - t[4]) / 1e3:.2f}, tile sums {(t[13] - t[12]) / 1e3:.2f}, "
               f"grid barrier {(t[14] - t[13]) / 1e3:.2f}, slot reduction {(t[15] - t[14]) / 1e3:.2f}, stats {(t[5] - t[15]) / 1e3:.2f}")
