@@ -809,8 +809,8 @@ def secondary_measurements(dev, peaks):
         s = _timed(lambda: idx(Q), 5, warm=1)
         out[f"topk_shard_d{d}"] = {"value": Ub / s, "unit": "users/s", "ms": s * 1e3,
                                    "roofline": _tensor_roofline("score_topk_kernel", 2.0 * Ub * Ib * d, s, peaks,
-                                                                "bound by the TMEM read rate of the selection epilogue (16 scores / clk / SM = "
-                                                                f"{2 * d * 4.5e12 / 1e12:.0f} TFLOP/s at d = {d}), DESIGN.md section 4.1"),
+                                                                "limited by the selection epilogue (tcgen05.ld + compare tree per 32 scores) and the warm-up of "
+                                                                "the running k-th-best threshold on a short shard, DESIGN.md section 4"),
                                    "config": f"65536 users x 250000 items (one 8-way item shard of BASELINE.json configs[4]), d={d}, k=10"}
         del Q, Cm, idx
     return out
@@ -907,7 +907,7 @@ def c5_topk_block(dev, world, rank, peaks):
     return {"metric": "top-K users/sec (1M users x 2M items, d=64, k=10)", "value": U / s, "unit": "users/s", "n_gpus": world,
             "ms": s * 1e3, "scaling": "strong",
             "roofline": _tensor_roofline("score_topk_kernel (per rank; + all-gather of [U,k] lists + topk_merge_kernel)", flops_gpu, s, peaks,
-                                         "per GPU; the selection epilogue's TMEM read rate caps d = 64 at 576 TFLOP/s (DESIGN.md section 4.1)"),
+                                         "per GPU, all-gather of the lists and merge included; the selection epilogue is the limiter (DESIGN.md section 4)"),
             "config": {"workload": "BASELINE.json configs[4]: full-catalog top-K sweep, bf16 operands, fp32 scores",
                        "parallelism": f"items range-sharded x{world}, NCCL all-gather of the [U, k] (score, id) lists, merge on every rank"}}
 
