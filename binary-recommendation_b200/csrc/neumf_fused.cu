@@ -81,7 +81,7 @@ struct Spec {
                                  size_t(nFloats + nInts) * 4 + 1024;
   static_assert(K0 % 32 == 0 && H1 % 32 == 0 && H2 % 16 == 0 && H3 % 8 == 0, "widths");
   static_assert(HC1 <= 32 && HC2 <= 32 && (HC1 & (HC1 - 1)) == 0 && (HC2 & (HC2 - 1)) == 0 && (H3 & (H3 - 1)) == 0, "halves");
-  static_assert(EMF % 4 == 0 && EMF <= 128 && E % 32 == 0, "embedding widths");
+  static_assert(EMF % 4 == 0 && EMF <= 128 && E % 32 == 0 && (!HAD_ || EMF <= 32), "embedding widths");
   static_assert(CEND <= 256, "TMEM columns");
 };
 
@@ -745,10 +745,11 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
       constexpr int SH3 = 5 - ilog2(H3);
       warp_feat_reduce<H3>(pw);
       warp_feat_reduce<H3>(dz3);
-      if ((lane & ((1 << SH3) - 1)) == 0) { atomicAdd(gw4 + (lane >> SH3), pw[0]); atomicAdd(gb3 + (lane >> SH3), dz3[0]); }
+      // per-warp partials into `part` (combined in warp order after the barrier below: no atomics, reproducible bits)
+      if ((lane & ((1 << SH3) - 1)) == 0) { part[(0 * 8 + warp) * 32 + (lane >> SH3)] = pw[0]; part[(1 * 8 + warp) * 32 + (lane >> SH3)] = dz3[0]; }
       const float sdl = warp_sum(dlogit);
       const float smf = HAD ? 0.f : warp_sum(ok ? mfs[s] * dlogit : 0.f);
-      if (lane == 0) { atomicAdd(gw4 + H3 + HM, sdl); if (!HAD) atomicAdd(gw4 + H3, smf); }
+      if (lane == 0) { part[(0 * 8 + warp) * 32 + 30] = sdl; part[(0 * 8 + warp) * 32 + 31] = smf; }
     }
   }
   {
@@ -761,7 +762,20 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
 
   stamp(X, 6);
   if (training) {
-    __syncthreads();                                        // dl visible
+    __syncthreads();                                        // dl and the warps' head partials visible
+    if (t < H3) {
+      float sw = 0.f, sb = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) { sw += part[(0 * 8 + w) * 32 + t]; sb += part[(1 * 8 + w) * 32 + t]; }
+      gw4[t] += sw; gb3[t] += sb;
+    }
+    if (t == 32) {
+      float sl = 0.f, sm_ = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) { sl += part[(0 * 8 + w) * 32 + 30]; sm_ += part[(0 * 8 + w) * 32 + 31]; }
+      gw4[H3 + HM] += sl;
+      if (!HAD) gw4[H3] += sm_;
+    }
     // MF embedding gradients: 16-byte REDs into the owners' accumulators; Hadamard head weights
     float4 hw = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -785,9 +799,17 @@ __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_ste
         hw.x += __shfl_xor_sync(0xffffffffu, hw.x, o); hw.y += __shfl_xor_sync(0xffffffffu, hw.y, o);
         hw.z += __shfl_xor_sync(0xffffffffu, hw.z, o); hw.w += __shfl_xor_sync(0xffffffffu, hw.w, o);
       }
+      __syncthreads();                                      // the head partials above have been consumed
       if (lane < MLPR) {
-        atomicAdd(gw4 + H3 + 4 * mc4, hw.x); atomicAdd(gw4 + H3 + 4 * mc4 + 1, hw.y);
-        atomicAdd(gw4 + H3 + 4 * mc4 + 2, hw.z); atomicAdd(gw4 + H3 + 4 * mc4 + 3, hw.w);
+        float* pr = part + (1 * 8 + warp) * 32 + 4 * mc4;
+        pr[0] = hw.x; pr[1] = hw.y; pr[2] = hw.z; pr[3] = hw.w;
+      }
+      __syncthreads();
+      if (t < EMF) {
+        float sw = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sw += part[(1 * 8 + w) * 32 + t];
+        gw4[H3 + t] += sw;
       }
     }
     // da2 = dz3 W3^T;  dW3 = a2^T dz3 (M = 64: rows >= H2 alias / are ignored)
