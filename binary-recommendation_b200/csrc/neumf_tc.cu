@@ -656,6 +656,7 @@ __global__ void __launch_bounds__(NT) tc_bwd2(const Args A, const float* __restr
   __syncthreads();
   uint32_t phase = 0;
   int it = 0;
+  float db_acc = 0.f;                                      // this thread's bias-gradient feature, summed over the CTA's tiles
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int64_t b0 = int64_t(tile) * TS;
     const int valid = int((A.B - b0) < int64_t(TS) ? (A.B - b0) : int64_t(TS));
@@ -703,7 +704,7 @@ __global__ void __launch_bounds__(NT) tc_bwd2(const Args A, const float* __restr
     if (t < H2) {
       float sacc = 0.f;
       for (int r = 0; r < TS; ++r) sacc += *reinterpret_cast<const float*>(Zk + km_off16(TS, r, t >> 2) + (t & 3) * 4);
-      atomicAdd(A.dense.g + L::b2 + t, sacc);
+      db_acc += sacc;                                       // one atomic per feature per CTA, after the last tile
     }
     tc::mbar_wait(tc::smem_u32(&ctl.bar), phase);
     phase ^= 1u;
@@ -780,11 +781,12 @@ __global__ void __launch_bounds__(NT) tc_bwd2(const Args A, const float* __restr
     float v[32];
     tmem_load32(tmem, warp, WCOL, v);
     const int k = row_of_lane<MW>(warp * 32 + lane);
-    if (k >= 0 && k < H1)
+    if (k >= 0 && k < H1)                                  // 16-byte REDs: a quarter of the L2 atomic operations
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < H2) atomicAdd(A.dense.g + L::W2 + k * H2 + j, v[j]);
+      for (int j = 0; j < 32; j += 4)
+        if (j < H2) red_add_f4(A.dense.g + L::W2 + k * H2 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
   }
+  if (it > 0 && t < H2) atomicAdd(A.dense.g + L::b2 + t, db_acc);
   tc_end<TCOLS>(tmem);
 }
 
@@ -823,6 +825,7 @@ __global__ void __launch_bounds__(NT) tc_bwd1(const Args A, const float* __restr
   __syncthreads();
   uint32_t phase = 0;
   int it = 0;
+  float db_acc = 0.f;                                      // this thread's bias-gradient feature, summed over the CTA's tiles
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int64_t b0 = int64_t(tile) * TS;
     const int valid = int((A.B - b0) < int64_t(TS) ? (A.B - b0) : int64_t(TS));
@@ -851,7 +854,7 @@ __global__ void __launch_bounds__(NT) tc_bwd1(const Args A, const float* __restr
     if (t < H1) {                                           // db1 on the CUDA cores meanwhile
       float sacc = 0.f;
       for (int r = 0; r < TS; ++r) sacc += *reinterpret_cast<const float*>(Zk + km_off16(TS, r, t >> 2) + (t & 3) * 4);
-      atomicAdd(A.dense.g + L::b1 + t, sacc);
+      db_acc += sacc;                                       // one atomic per feature per CTA, after the last tile
     }
     tc::mbar_wait(tc::smem_u32(&ctl.bar), phase);
     phase ^= 1u;
@@ -889,10 +892,11 @@ __global__ void __launch_bounds__(NT) tc_bwd1(const Args A, const float* __restr
     const int k = row_of_lane<K0>(( warp & 3) * 32 + lane), c0 = (warp >> 2) * HC;
     float v[32];
     tmem_load32(tmem, warp, WCOL + c0, v);
-    if (k >= 0)
+    if (k >= 0)                                             // 16-byte REDs: a quarter of the L2 atomic operations
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < HC) atomicAdd(A.dense.g + L::W1 + k * H1 + c0 + j, v[j]);
+      for (int j = 0; j < 32; j += 4)
+        if (j < HC) red_add_f4(A.dense.g + L::W1 + k * H1 + c0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+    if (t < H1) atomicAdd(A.dense.g + L::b1 + t, db_acc);
   }
   // last CTA: BN moving statistics, loss output, accumulator reset
   __syncthreads();
