@@ -298,8 +298,12 @@ class NeuMFNet:
         """dataset: a NeuMFDataset (bootstrapDataset).  One pass per epoch; batch ORDER reshuffled per
         epoch as tf.data's .batch().shuffle() does (NeuMFModel.py:117-121)."""
         for e in range(epochs):
+            if e == 0:
+                D.barrier()                                  # nobody enters a cross-GPU wait while a rank is still staging
             losses = dataset.run_epoch(self, e, steps_per_epoch)
             mean = float(losses.double().mean().item())
+            if getattr(self, "_reducer", None) is not None:
+                self._reducer.check()                        # a peer all-reduce that timed out aborted its step: raise here
             self.history["loss"].append(mean)
             if validation_data is not None:
                 self.history.setdefault("val_loss", []).append(self.evaluate(validation_data)[0])

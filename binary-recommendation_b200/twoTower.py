@@ -207,7 +207,11 @@ class TwoTowerModel:
     def _train_ids(self, u, i, labels, loss_out=None):
         if self.optimizer is None:
             self.compile()
-        loss = self._step(u, i, labels, True, loss_out)
+        if u.numel() > 0:
+            loss = self._step(u, i, labels, True, loss_out)
+        else:                                                # this rank's slice of a small global batch is empty
+            loss = loss_out if loss_out is not None else torch.zeros(1, dtype=torch.float32, device=self.device)
+            loss.zero_()
         if D.world_size() > 1:
             D.all_reduce_sum_(self.grad_arena, self._reducer)
             # the touched-row bitmasks are per rank: after the sum every rank applies the dense pass (rows nobody touched
@@ -231,6 +235,17 @@ class TwoTowerModel:
         # string -> index lookups and H2D of the ids once per fit, not once per step and epoch (the reference caches
         # its batched dataset too: trainSetCached, twoTower.py:197-198)
         staged = [(self._ids(info), self._labels(info)) for info in batches]
+        if D.world_size() > 1:
+            # mirrored data parallelism: a batch of the dataset is the GLOBAL batch (MultiWorkerMirroredStrategy auto-shards
+            # it); this rank trains its slice, with its slice's items as in-batch negatives (the per-replica loss), and the
+            # SUM-reduced gradients are summed over the ranks (peer all-reduce in _train_ids)
+            def mine(t):
+                if t is None:
+                    return None
+                lo, hi = D.local_slice(t.numel())
+                return t[lo:hi].contiguous()
+            staged = [((mine(u), mine(i)), mine(lab)) for (u, i), lab in staged]
+            D.barrier()
         sizes = [u.numel() for (u, _), _ in staged]
         n_full = 0
         while n_full < len(sizes) and sizes[n_full] == sizes[0]:
@@ -255,6 +270,8 @@ class TwoTowerModel:
                 self._train_ids(u, i, lab, losses[k:k + 1])
             # one host sync per epoch: Keras reports the running mean of the per-batch losses
             self.history["loss"].append(float(losses.double().sum().item()) / max(len(staged), 1))
+            if self._reducer is not None:
+                self._reducer.check()                        # a peer all-reduce that timed out aborted its step: raise here
             if verbose:
                 print(f"epoch {e + 1}: loss {self.history['loss'][-1]:.6f}")
         return self
