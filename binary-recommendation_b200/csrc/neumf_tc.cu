@@ -195,6 +195,25 @@ __device__ __forceinline__ void tc_end(uint32_t tmem) {
 // operands written with st.shared -> visible to the tensor core; then one thread issues
 #define NTC_OPERANDS_READY() do { tc::fence_proxy_async_smem(); __syncthreads(); tc::fence_after_sync(); } while (0)
 
+// BRK_NTC_TRACE (hex address of a device buffer of >= 320 uint64): %globaltimer stamps of block 0 / thread 0 of
+// tc_head (words 0..63), tc_bwd2 (64..127), tc_bwd1 (128..191), tc_fwd1 (192..223), tc_fwd2 (224..255) --
+// profiles/neumf_tc_trace.py.  A null pointer (the default) costs one predicated-off branch per stamp.
+__device__ unsigned long long* g_trace = nullptr;
+struct Stamper {
+  unsigned long long* p; unsigned long long* end;
+  __device__ __forceinline__ Stamper(int base, int n) {
+    unsigned long long* g = (blockIdx.x == 0 && threadIdx.x == 0) ? g_trace : nullptr;
+    p = g ? g + base : nullptr; end = g ? g + base + n : nullptr;
+  }
+  __device__ __forceinline__ void operator()() {
+    if (p != nullptr && p < end) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      *p++ = t;
+    }
+  }
+};
+
 extern __shared__ __align__(1024) uint8_t ntc_smem_raw[];
 __device__ __forceinline__ uint8_t* smem_base() {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ntc_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -222,11 +241,11 @@ __device__ __forceinline__ void load_tile_ids(int32_t* ids_s, const Args& A, int
 }
 // Gather x0 = [uMLP[u], iMLP[i]] for a tile: E/4 lanes per row, 16 bytes each (coalesced rows); every load of the
 // thread is issued before the first use.  MN = 0: K-major swizzle, 1: MN-major swizzle.
-template <int E, int MN>
-__device__ __forceinline__ void gather_x0(uint8_t* Xs, const Args& A, const int32_t* ids_s, const uint32_t* masks, int valid) {
-  constexpr int LPR = E / 4, RPP = NT / LPR, NP = TS / RPP, MW = 2 * E / 32;
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int E>
+__device__ __forceinline__ void gather_x0_issue(float4 (&v)[2 * (TS / (NT / (E / 4)))], const Args& A, const int32_t* ids_s, int valid) {
+  constexpr int LPR = E / 4, RPP = NT / LPR, NP = TS / RPP;
   const int t = threadIdx.x, c4 = t % LPR, rr = t / LPR;
-  float4 v[2 * NP];
 #pragma unroll
   for (int tab = 0; tab < 2; ++tab)
 #pragma unroll
@@ -235,6 +254,12 @@ __device__ __forceinline__ void gather_x0(uint8_t* Xs, const Args& A, const int3
       v[tab * NP + p] = r < valid ? __ldg(reinterpret_cast<const float4*>(locate<E>(tab == 0 ? A.uMLP : A.iMLP, ids_s[tab * TS + r]).w) + c4)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+}
+template <int E, int MN>
+__device__ __forceinline__ void gather_x0_store(uint8_t* Xs, const float4 (&v)[2 * (TS / (NT / (E / 4)))], const Args& A,
+                                                const uint32_t* masks) {
+  constexpr int LPR = E / 4, RPP = NT / LPR, NP = TS / RPP, MW = 2 * E / 32;
+  const int t = threadIdx.x, c4 = t % LPR, rr = t / LPR;
 #pragma unroll
   for (int tab = 0; tab < 2; ++tab)
 #pragma unroll
@@ -249,6 +274,12 @@ __device__ __forceinline__ void gather_x0(uint8_t* Xs, const Args& A, const int3
       }
       *reinterpret_cast<float4*>(Xs + (MN ? mn_off16(TS, r, tab * LPR + c4) : km_off16(TS, r, tab * LPR + c4))) = x;
     }
+}
+template <int E, int MN>
+__device__ __forceinline__ void gather_x0(uint8_t* Xs, const Args& A, const int32_t* ids_s, const uint32_t* masks, int valid) {
+  float4 v[2 * (TS / (NT / (E / 4)))];
+  gather_x0_issue<E>(v, A, ids_s, valid);
+  gather_x0_store<E, MN>(Xs, v, A, masks);
 }
 
 // ---- phase 1: x0 = dropout([uMLP[u], iMLP[i]]); h1 = act(x0 W1 + b1); batch sums of h1 -----------------
@@ -411,6 +442,8 @@ __global__ void __launch_bounds__(NT, 2) tc_head(const Args A, const float* __re
   // ~550 words at configs[3] sizes: 85 us for this kernel, most of it the serialised atomics.)
   __shared__ float aW3[H2 * H3], ab3[H3], aW4[H3 + 2];
   const int t = threadIdx.x, warp = t >> 5;
+  Stamper stamp(0, 64);
+  stamp();
   for (int j = t; j < H2 * H3; j += NT) aW3[j] = 0.f;
   if (t < H3) ab3[t] = 0.f;
   if (t < H3 + 2) aW4[t] = 0.f;
@@ -427,10 +460,13 @@ __global__ void __launch_bounds__(NT, 2) tc_head(const Args A, const float* __re
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
   const int64_t b0 = int64_t(tile) * TS;
   const int valid = int((A.B - b0) < int64_t(TS) ? (A.B - b0) : int64_t(TS));
+  stamp();
   load_tile_ids(ids_s, A, b0, valid);
   __syncthreads();
+  stamp();
   stage_bn_tile<H2, 2>(As, A.h2, A, b0, valid, mean, rstd, gam, bet, Xh);
   NTC_OPERANDS_READY();
+  stamp();
   if (t == 0) {
     issue_gemm<128, N3, 0, 0>(tmem, tc::smem_u32(As), TS, tc::smem_u32(Ws), N3, H2, false);
     tc::mma_commit(tc::smem_u32(&ctl.bar));
@@ -455,10 +491,26 @@ __global__ void __launch_bounds__(NT, 2) tc_head(const Args A, const float* __re
     part = group_sum<LPR>(part);
     if (mc4 == 0) mfs[p * RPP + mrr] = part;
   }
+  if (tile + int(gridDim.x) < n_tiles) {                   // ask the next tile's h2 columns and MF rows into L2
+    const int64_t nb0 = int64_t(tile + gridDim.x) * TS;
+    for (int l = t; l < H2 * (TS / 32); l += NT) {
+      const int64_t col = nb0 + (l % (TS / 32)) * 32;
+      if (col < A.B) prefetch_l2(A.h2 + int64_t(l / (TS / 32)) * A.B + col);
+    }
+    for (int l = t; l < 2 * TS; l += NT) {
+      const int s = l & (TS - 1), tab = l / TS;
+      if (nb0 + s < A.B) {
+        const float* w = locate<E>(tab == 0 ? A.uMF : A.iMF, __ldg((tab == 0 ? A.u : A.i) + nb0 + s)).w;
+#pragma unroll
+        for (int c = 0; c < E; c += 32) prefetch_l2(w + c);
+      }
+    }
+  }
   tc::mbar_wait(tc::smem_u32(&ctl.bar), phase);
   phase ^= 1u;
   tc::fence_after_sync();
   __syncthreads();                                         // mfs visible
+  stamp();
   float loss_local = 0.f;
   if (t < TS) {                                            // one thread per sample: warps 0..3 = the four lane quadrants
     const int s = t;
@@ -490,6 +542,7 @@ __global__ void __launch_bounds__(NT, 2) tc_head(const Args A, const float* __re
   }
   const double lsum = block_sum_double(double(loss_local), red);
   if (t == 0) atomicAdd(A.acc + AC::loss, lsum);
+  stamp();
   if (A.training) {
     __syncthreads();
     // head weights: dW4[j] = sum_s z[j][s] dl[s] (z = [h3, mf]), db4 = sum_s dl[s]: one warp per output, lanes over samples
@@ -558,6 +611,7 @@ __global__ void __launch_bounds__(NT, 2) tc_head(const Args A, const float* __re
         Ds[k * SP + s] = s < valid ? d : 0.f;
       }
     }
+    stamp();
     // MF embedding gradients: LPR lanes per row pair, 16-byte REDs into the owners' accumulators
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
@@ -571,12 +625,14 @@ __global__ void __launch_bounds__(NT, 2) tc_head(const Args A, const float* __re
       }
     }
     __syncthreads();
+    stamp();
     store_tile<H2>(Ds, A.dy2, A.B, b0, valid);
     row_sums<H2>(Ds, Xh, A.acc + AC::d2, A.acc + AC::e2);
   }
   tc::fence_before_sync();
   __syncthreads();                                         // tiles, ids and TMEM may be overwritten by the next iteration
   }
+  stamp();
   if (A.training) {                                        // one atomic per entry per CTA
     for (int j = t; j < H2 * H3; j += NT) atomicAdd(A.dense.g + L::W3 + j, aW3[j]);
     if (t < H3) atomicAdd(A.dense.g + L::b3 + t, ab3[t]);
@@ -587,19 +643,24 @@ __global__ void __launch_bounds__(NT, 2) tc_head(const Args A, const float* __re
 
 // dz of a BatchNorm-followed layer for this thread's (sample, feature half): written in both operand
 // swizzles (K-major for the input-gradient product, MN-major for the weight-gradient product)
-template <int H, int ACT>
-__device__ __forceinline__ void stage_dz_tiles(uint8_t* Zk, uint8_t* Zm, const float* __restrict__ h, const float* __restrict__ dy,
-                                               const float* mean, const float* rstd, const float* gam, const float* sdy,
-                                               const float* sdyx, int64_t B, int64_t b0, int valid) {
+template <int H>
+__device__ __forceinline__ void dz_issue(float (&hv)[H / 2], float (&dv)[H / 2], const float* __restrict__ h, const float* __restrict__ dy,
+                                         int64_t B, int64_t b0, int valid) {
   const int t = threadIdx.x, s = t & (TS - 1), hf = t >> 7;
   constexpr int HH = H / 2;
   const bool ok = s < valid;
-  float hv[HH], dv[HH];
 #pragma unroll
   for (int fl = 0; fl < HH; ++fl) {                       // all loads in flight before the first use
     hv[fl] = ok ? __ldg(h + int64_t(hf * HH + fl) * B + b0 + s) : 0.f;
     dv[fl] = ok ? __ldg(dy + int64_t(hf * HH + fl) * B + b0 + s) : 0.f;
   }
+}
+template <int H, int ACT>
+__device__ __forceinline__ void dz_store(uint8_t* Zk, uint8_t* Zm, const float (&hv)[H / 2], const float (&dv)[H / 2], const float* mean,
+                                         const float* rstd, const float* gam, const float* sdy, const float* sdyx, int valid) {
+  const int t = threadIdx.x, s = t & (TS - 1), hf = t >> 7;
+  constexpr int HH = H / 2;
+  const bool ok = s < valid;
 #pragma unroll
   for (int f4 = 0; f4 < HH / 4; ++f4) {
     float v[4];
@@ -614,6 +675,14 @@ __device__ __forceinline__ void stage_dz_tiles(uint8_t* Zk, uint8_t* Zm, const f
     *reinterpret_cast<float4*>(Zk + km_off16(TS, s, (hf * HH) / 4 + f4)) = v4;
     *reinterpret_cast<float4*>(Zm + mn_off16(TS, s, (hf * HH) / 4 + f4)) = v4;
   }
+}
+template <int H, int ACT>
+__device__ __forceinline__ void stage_dz_tiles(uint8_t* Zk, uint8_t* Zm, const float* __restrict__ h, const float* __restrict__ dy,
+                                               const float* mean, const float* rstd, const float* gam, const float* sdy,
+                                               const float* sdyx, int64_t B, int64_t b0, int valid) {
+  float hv[H / 2], dv[H / 2];
+  dz_issue<H>(hv, dv, h, dy, B, b0, valid);
+  dz_store<H, ACT>(Zk, Zm, hv, dv, mean, rstd, gam, sdy, sdyx, valid);
 }
 
 // ---- phase 4 (backward through layer 2 and BatchNorm 1), persistent over tiles ------------------------------
@@ -808,8 +877,10 @@ __global__ void __launch_bounds__(NT) tc_bwd1(const Args A, const float* __restr
   float* mean1 = reinterpret_cast<float*>(masks + TS * MWORDS); float* rstd1 = mean1 + H1; float* gam1 = rstd1 + H1;
   float* sdy = gam1 + H1; float* sdyx = sdy + H1;
   __shared__ Ctl ctl;
-  __shared__ int32_t ids_s[2 * TS];
+  __shared__ int32_t ids_s[2][2 * TS];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  Stamper stamp(128, 64);
+  stamp();
   const uint32_t tmem = tc_begin<TCOLS>(ctl);
   copy16(Ws, img + I::W1, K0 * pad32(H1));
   copy_small<H1>(gam1, A.dense.w + L::g1);
@@ -829,7 +900,14 @@ __global__ void __launch_bounds__(NT) tc_bwd1(const Args A, const float* __restr
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
     const int64_t b0 = int64_t(tile) * TS;
     const int valid = int((A.B - b0) < int64_t(TS) ? (A.B - b0) : int64_t(TS));
-    load_tile_ids(ids_s, A, b0, valid);
+    stamp();
+    // three independent memory phases, issued back to back so their DRAM latencies overlap: the h1 / dy1 columns of
+    // the tile (no dependence on the ids), the ids (prefetched into the other half of ids_s during the previous tile),
+    // the embedding rows; the dropout bits are drawn while the first loads fly
+    float hv[H1 / 2], dv[H1 / 2];
+    dz_issue<H1>(hv, dv, A.h1, A.dy1, A.B, b0, valid);
+    const int32_t* ids_c = ids_s[it & 1];
+    if (it == 0) load_tile_ids(ids_s[0], A, b0, valid);
     if (A.dropout) {
       const int s = t & (TS - 1), hf = t >> 7;
       for (int c = hf * (K0 / 32); c < (hf + 1) * (K0 / 32); ++c) {
@@ -838,9 +916,21 @@ __global__ void __launch_bounds__(NT) tc_bwd1(const Args A, const float* __restr
       }
     }
     __syncthreads();
-    gather_x0<E, 1>(Xm, A, ids_s, masks, valid);           // re-gather x0 (rows are L2-hot from phase 1)
-    stage_dz_tiles<H1, ACT>(Zk, Zm, A.h1, A.dy1, mean1, rstd1, gam1, sdy, sdyx, A.B, b0, valid);
+    stamp();
+    float4 xv[2 * (TS / (NT / (E / 4)))];
+    gather_x0_issue<E>(xv, A, ids_c, valid);
+    {                                                       // next tile's ids
+      const int64_t nb0 = int64_t(tile + gridDim.x) * TS;
+      if (tile + int(gridDim.x) < n_tiles) {
+        const int nvalid = int((A.B - nb0) < int64_t(TS) ? (A.B - nb0) : int64_t(TS));
+        load_tile_ids(ids_s[(it + 1) & 1], A, nb0, nvalid);
+      }
+    }
+    dz_store<H1, ACT>(Zk, Zm, hv, dv, mean1, rstd1, gam1, sdy, sdyx, valid);
+    stamp();
+    gather_x0_store<E, 1>(Xm, xv, A, masks);
     NTC_OPERANDS_READY();
+    stamp();
     if (t == 0) {
       issue_gemm<128, K0, 0, 0>(tmem, tc::smem_u32(Zk), TS, tc::smem_u32(Ws), K0, H1, false);             // dx0
       constexpr uint32_t idesc = tc::idesc_tf32_f32(K0, H1, 1, 1);
@@ -851,6 +941,22 @@ __global__ void __launch_bounds__(NT) tc_bwd1(const Args A, const float* __restr
       }
       tc::mma_commit(tc::smem_u32(&ctl.bar));
     }
+    if (tile + int(gridDim.x) < n_tiles) {                  // ask the next tile's operands into L2 while this one computes
+      const int64_t nb0 = int64_t(tile + gridDim.x) * TS;
+      const int32_t* ids_n = ids_s[(it + 1) & 1];
+      for (int l = t; l < H1 * (TS / 32); l += NT) {
+        const int64_t off = int64_t(l / (TS / 32)) * A.B + nb0 + (l % (TS / 32)) * 32;
+        if (nb0 + (l % (TS / 32)) * 32 < A.B) { prefetch_l2(A.h1 + off); prefetch_l2(A.dy1 + off); }
+      }
+      for (int l = t; l < 2 * TS; l += NT) {
+        const int s = l & (TS - 1), tab = l / TS;
+        if (nb0 + s < A.B) {
+          const float* w = locate<E>(tab == 0 ? A.uMLP : A.iMLP, ids_n[tab * TS + s]).w;
+#pragma unroll
+          for (int c = 0; c < E; c += 32) prefetch_l2(w + c);
+        }
+      }
+    }
     if (t < H1) {                                           // db1 on the CUDA cores meanwhile
       float sacc = 0.f;
       for (int r = 0; r < TS; ++r) sacc += *reinterpret_cast<const float*>(Zk + km_off16(TS, r, t >> 2) + (t & 3) * 4);
@@ -859,33 +965,49 @@ __global__ void __launch_bounds__(NT) tc_bwd1(const Args A, const float* __restr
     tc::mbar_wait(tc::smem_u32(&ctl.bar), phase);
     phase ^= 1u;
     tc::fence_after_sync();
-    // epilogue: warps 0..3 carry the user half of dx0, warps 4..7 the item half; 16-byte REDs per row
+    stamp();
+    // epilogue: warps 0..3 read the user half of dx0 out of TMEM, warps 4..7 the item half (lane = sample) and park it,
+    // masked, in the x0 tile (free once the products have completed; 16-byte chunk ^ (sample & 7): conflict-free both
+    // ways).  The REDs then go out ROW-contiguous, 16 lanes per 256-byte row: with lane = sample every RED instruction
+    // touched 32 different lines and the epilogue was half of the tile's time (profiles/r02_neumf_tc_trace.txt).
     {
       const int s = (warp & 3) * 32 + lane, tab = warp >> 2;
       const bool ok = s < valid;
-      RowRef rr; rr.w = nullptr; rr.g = nullptr; rr.t = nullptr; rr.lrow = 0;
-      if (ok) rr = locate<E>(tab == 0 ? A.uMLP : A.iMLP, ids_s[tab * TS + s]);
       for (int cc = 0; cc < E; cc += 32) {
         float v[32];
         tmem_load32(tmem, warp, tab * E + cc, v);
-        if (ok) {
-          const int f0 = tab * E + cc;
-          const uint32_t m = A.dropout ? masks[s * MWORDS + (f0 >> 5)] : 0xFFFFFFFFu;
+        const int f0 = tab * E + cc;
+        const uint32_t m = !ok ? 0u : (A.dropout ? masks[s * MWORDS + (f0 >> 5)] : 0xFFFFFFFFu);
+        const float sc = A.dropout ? kDropScale : 1.f;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 g4;
-            g4.x = ((m >> (j + 0)) & 1u) ? v[j + 0] : 0.f; g4.y = ((m >> (j + 1)) & 1u) ? v[j + 1] : 0.f;
-            g4.z = ((m >> (j + 2)) & 1u) ? v[j + 2] : 0.f; g4.w = ((m >> (j + 3)) & 1u) ? v[j + 3] : 0.f;
-            if (A.dropout) { g4.x *= kDropScale; g4.y *= kDropScale; g4.z *= kDropScale; g4.w *= kDropScale; }
-            if (cc + j < E) red_add_f4(rr.g + cc + j, g4);
-          }
+        for (int j = 0; j < 32; j += 4) {
+          float4 g4;
+          g4.x = ((m >> (j + 0)) & 1u) ? v[j + 0] * sc : 0.f; g4.y = ((m >> (j + 1)) & 1u) ? v[j + 1] * sc : 0.f;
+          g4.z = ((m >> (j + 2)) & 1u) ? v[j + 2] * sc : 0.f; g4.w = ((m >> (j + 3)) & 1u) ? v[j + 3] * sc : 0.f;
+          if (cc + j < E) *reinterpret_cast<float4*>(Xm + s * (K0 * 4) + ((((f0 + j) >> 2) ^ (s & 7)) << 4)) = g4;
         }
       }
-      if (ok) mark_row(rr);
     }
+    __syncthreads();
+    {
+      constexpr int LPR = E / 4, RPP = NT / LPR, NPASS = 2 * TS / RPP;
+      const int c4 = t % LPR, q = t / LPR;
+#pragma unroll 4
+      for (int p = 0; p < NPASS; ++p) {
+        const int pr = p * RPP + q, s = pr & (TS - 1), tab = pr / TS;
+        if (s < valid) {
+          const RowRef rr = locate<E>(tab == 0 ? A.uMLP : A.iMLP, ids_c[tab * TS + s]);
+          const float4 g4 = *reinterpret_cast<const float4*>(Xm + s * (K0 * 4) + (((tab * LPR + c4) ^ (s & 7)) << 4));
+          red_add_f4(rr.g + 4 * c4, g4);
+          if (c4 == 0) mark_row(rr);
+        }
+      }
+    }
+    stamp();
     tc::fence_before_sync();
     __syncthreads();                                        // tiles and masks may be overwritten by the next iteration
   }
+  stamp();
   if (it > 0) {                                             // flush dW1: lane = row k, this warp's column half
     tc::fence_after_sync();
     constexpr int HC = H1 / 2;
@@ -903,6 +1025,7 @@ __global__ void __launch_bounds__(NT) tc_bwd1(const Args A, const float* __restr
   __shared__ bool last;
   if (t == 0) { __threadfence(); last = atomicAdd(ticket, 1u) == gridDim.x - 1; }
   __syncthreads();
+  stamp();
   if (last) {
     __threadfence();
     for (int f = t; f < H1; f += NT) {
@@ -968,6 +1091,12 @@ int run(brk_ctx* ctx, const Args& A, cudaStream_t st) {
     if (occ_c > 4) occ_c = 4;
     BRK_REQUIRE(occ_d > 0 && occ_e > 0 && occ_c > 0, BRK_E_STATE, "brk_neumf_step: tensor-core kernels do not fit");
     attr_done = true;
+  }
+  {
+    static unsigned long long* trace_set = nullptr;
+    const char* tr = getenv("BRK_NTC_TRACE");
+    unsigned long long* want = tr ? reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 16)) : nullptr;
+    if (want != trace_set) { BRK_CUDA(cudaMemcpyToSymbolAsync(g_trace, &want, sizeof(want), 0, cudaMemcpyHostToDevice, st)); trace_set = want; }
   }
   prep_images<E, H1, H2, H3><<<(I::total + 255) / 256, 256, 0, st>>>(A.dense.w, img);
   tc_fwd1<E, H1, H2, H3, ACT><<<n_tiles, NT, smA, st>>>(A, img);
