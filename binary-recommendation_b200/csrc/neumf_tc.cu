@@ -1087,8 +1087,24 @@ int run(brk_ctx* ctx, const Args& A, cudaStream_t st) {
     // bwd2 allocates 128, bwd1 256 per CTA)
     occ_d = int((227 * 1024) / (smD + 1024)); if (occ_d > 2) occ_d = 2;
     occ_e = int((227 * 1024) / (smE + 1024)); if (occ_e > 2) occ_e = 2;
-    BRK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, tc_head<E, H1, H2, H3, ACT>, NT, smC));
-    if (occ_c > 4) occ_c = 4;
+    {
+      // tc_head: CTAs per SM from its own resource use.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for
+      // this kernel at 128 registers x 256 threads + 80 KB although two CTAs do run side by side -- in-kernel stamps,
+      // profiles/r02_neumf_tc_trace.txt -- and the persistent tile loop is correct for any grid.)
+      cudaFuncAttributes fa;
+      BRK_CUDA(cudaFuncGetAttributes(&fa, tc_head<E, H1, H2, H3, ACT>));
+      const int by_smem = int((227 * 1024) / (smC + fa.sharedSizeBytes + 1024));
+      const int by_regs = 65536 / (((fa.numRegs + 7) & ~7) * NT);
+      occ_c = by_smem < by_regs ? by_smem : by_regs;
+      if (occ_c > 4) occ_c = 4;
+      if (occ_c < 1) occ_c = 1;
+    }
+    if (getenv("BRK_NTC_DEBUG")) {
+      cudaFuncAttributes fa;
+      BRK_CUDA(cudaFuncGetAttributes(&fa, tc_head<E, H1, H2, H3, ACT>));
+      fprintf(stderr, "[brk] tc_head: regs %d static smem %zu dynamic %zu -> %d CTAs/SM; bwd2 %d, bwd1 %d (smem %zu / %zu)\n",
+              fa.numRegs, fa.sharedSizeBytes, smC, occ_c, occ_d, occ_e, smD, smE);
+    }
     BRK_REQUIRE(occ_d > 0 && occ_e > 0 && occ_c > 0, BRK_E_STATE, "brk_neumf_step: tensor-core kernels do not fit");
     attr_done = true;
   }

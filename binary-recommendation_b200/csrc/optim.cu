@@ -119,7 +119,7 @@ constexpr int kRowsInFlight = 4;
 
 template <class Op, bool HAS_V>
 __device__ __forceinline__ void rows_pass(const TabList& tl, const Op& op) {
-  __shared__ int32_t s_rows[kThreads / 32][1024];             // touched rows of the warp's current pass
+  __shared__ int32_t s_rows[kThreads / 32][1024 + 32 * kRowsInFlight];   // touched rows waiting for the warp's row loop
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = (int64_t(blockIdx.x) * kThreads + threadIdx.x) >> 5;
   const int64_t n_warps = (int64_t(gridDim.x) * kThreads) >> 5;
@@ -143,14 +143,22 @@ __device__ __forceinline__ void rows_pass(const TabList& tl, const Op& op) {
     int wpw = 32;
     while (wpw > 1 && nwords < n_warps * wpw) wpw >>= 1;
     const int64_t stride = (nwords + wpw - 1) / wpw;            // slots: [0, stride)
+    // The bitmask words of slot s+1 are loaded before the rows of slot s are touched (one DRAM round trip per slot
+    // instead of two), and sparse slots are merged: rows pile up in the list until one full round of the row loop
+    // (gpw * kRowsInFlight rows) is there, so a warp that finds 3 rows per slot pays one row round trip per 3 slots.
+    auto load_word = [&](int64_t slot_) -> uint32_t {
+      const int64_t widx_ = int64_t(lane) * stride + slot_;
+      return (slot_ < stride && lane < wpw && widx_ < nwords) ? t.touched[widx_] : 0u;
+    };
+    int have = 0;                                               // rows waiting in the list
+    uint32_t word_next = load_word(warp);
     for (int64_t slot = warp; slot < stride; slot += n_warps) {
-      uint32_t word = 0u;
+      const uint32_t word = word_next;
       const int64_t widx = int64_t(lane) * stride + slot;
-      if (lane < wpw && widx < nwords) {
-        word = t.touched[widx];
-        if (word) t.touched[widx] = 0u;
-      }
-      if (__ballot_sync(0xffffffffu, word != 0u) == 0u) continue;
+      word_next = load_word(slot + n_warps);
+      if (word) t.touched[widx] = 0u;
+      const bool last_slot = slot + n_warps >= stride;
+      if (__ballot_sync(0xffffffffu, word != 0u) == 0u && !(last_slot && have > 0)) continue;
       // exclusive prefix sum of the per-lane popcounts -> each lane expands its word into the list
       const int cnt = __popc(word);
       int incl = cnt;
@@ -159,14 +167,17 @@ __device__ __forceinline__ void rows_pass(const TabList& tl, const Op& op) {
         const int v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
       }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      int pos = incl - cnt;
+      int pos = have + incl - cnt;
+      have += __shfl_sync(0xffffffffu, incl, 31);
       uint32_t w = word;
       while (w) {
         const int bit = __ffs(w) - 1;
         w &= w - 1;
         my_rows[pos++] = int32_t(widx * 32 + bit);              // absolute row (rows < 2^31)
       }
+      if (have < gpw * kRowsInFlight && !last_slot) continue;   // not a full round yet: take the next slot too
+      const int total = have;
+      have = 0;
       __syncwarp();
       if (vec && chunks <= lpr) {
         // one float4 per lane and row: kRowsInFlight rows per group, loads first, then compute and store
