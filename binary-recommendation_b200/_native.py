@@ -125,6 +125,8 @@ SIGNATURES = {
     "brk_tower_forward": (C.c_int, [_P, C.POINTER(brk_tower), _P, _I64, _P, _P, _P]),
     "brk_twotower_step": (C.c_int, [_P, C.POINTER(brk_tower), C.POINTER(brk_tower), _P, _P, _P, _P, _I64, _I32, _I32,
                                     C.POINTER(brk_twotower_workspace), _P, _P]),
+    "brk_twotower_train_step": (C.c_int, [_P, C.POINTER(brk_tower), C.POINTER(brk_tower), _P, _P, _P, _P, _I64, _I32,
+                                          C.POINTER(brk_twotower_workspace), _F32, _F32, _I64, _P, _P]),
     "brk_bf16_padded_dim": (C.c_int32, [_I32]),
     "brk_rows_to_bf16": (C.c_int, [_P, _P, _I64, _I32, _P, _I32, _P]),
     "brk_score_topk_workspace_bytes": (C.c_int64, [_P, _I64, _I64, _I32]),

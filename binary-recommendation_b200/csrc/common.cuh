@@ -24,6 +24,10 @@ struct brk_ctx {
   // one-launch NeuMF step (csrc/neumf_fused.cu): per-tile slots of partial sums, summed after a grid barrier
   float*        neumf_part;
   size_t        neumf_part_floats;
+  // one-launch two-tower step (csrc/twotower_fused.cu): per-tile softmax partials, grid-barrier words {count, error, base}
+  float*        tt_part;
+  size_t        tt_part_floats;
+  unsigned int* tt_bar;
   // any-width NeuMF path (csrc/neumf_generic.cu): feature-major intermediates
   float*        neumf_gen;
   size_t        neumf_gen_floats;

@@ -112,6 +112,9 @@ __global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ X
 }
 
 }  // namespace
+int brk_twotower_step_fused(brk_ctx* ctx, const brk_tower* user, const brk_tower* item, const int32_t* u, const int32_t* i,
+                            const int32_t* cand_ids, int64_t batch, int32_t training, const brk_twotower_workspace* ws,
+                            float* loss_out, cudaStream_t st, int* handled, int do_opt, float lr, float eps);   // twotower_fused.cu
 int brk_gemm_tf32_impl(brk_ctx* ctx, const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
                        int ldb, int ldc, int trans_a, int trans_b, float alpha, int accumulate, bool allow_split,
                        cudaStream_t st);
@@ -239,6 +242,11 @@ extern "C" int brk_twotower_step(brk_ctx* ctx, const brk_tower* user, const brk_
   cudaStream_t st = (cudaStream_t)stream;
   const int B = int(batch), S = user->S, Eu = user->E, Ei = item->E;
   int rc;
+  if (mode == 0 && tcore) {                         // the whole step as one cooperative launch when the batch fits on chip
+    int handled = 0;
+    if ((rc = brk_twotower_step_fused(ctx, user, item, u, i, cand_ids, batch, training, ws, loss_out, st, &handled, 0, 0.f, 0.f))) return rc;
+    if (handled) return 0;
+  }
   // The user chain and the item chain are independent until the score product and again after the loss gradient, and
   // inside each chain the Dense gradients (dW, db) are independent of the embedding gradient (de -> scatter): the item
   // chain runs on fork stream 0, the Dense gradients on fork streams 1 / 2 (branches of the graph under stream
@@ -309,5 +317,37 @@ extern "C" int brk_twotower_step(brk_ctx* ctx, const brk_tower* user, const brk_
     if (wide) BRK_JOIN(ctx, sk, 1 + k);
   }
   BRK_JOIN(ctx, st, 0);
+  return 0;
+}
+
+// Training step + Keras Adagrad (twoTower.py:89-102 with the optimizer of :278-279) in one call.  In-batch-softmax steps
+// on the tensor cores whose batch fits on chip run as ONE launch (twotower_fused.cu: the optimizer is the last phase of the
+// same cooperative kernel and only visits the rows the batch touched); everything else is brk_twotower_step followed by
+// the dense or row-sparse Adagrad pass of optim.cu (row-sparse for tables above rows_threshold_bytes that carry a bitmask).
+extern "C" int brk_twotower_train_step(brk_ctx* ctx, const brk_tower* user, const brk_tower* item, const int32_t* u,
+                                       const int32_t* i, const int32_t* cand_ids, const float* labels, int64_t batch,
+                                       int32_t mode, const brk_twotower_workspace* ws, float lr, float eps,
+                                       int64_t rows_threshold_bytes, float* loss_out, void* stream) {
+  BRK_REQUIRE(ctx && user && item && u && i && ws, BRK_E_ARG, "brk_twotower_train_step: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((mode & 0xFF) == 0 && (mode & 0x100) && user->S == item->S && batch > 0 && batch < (1 << 30) && ws->q && ws->c && ws->dq &&
+      ws->dc && ws->acc && user->emb.g && item->emb.g && user->dense.g && item->dense.g) {
+    int handled = 0;
+    if ((rc = brk_twotower_step_fused(ctx, user, item, u, i, cand_ids, batch, 1, ws, loss_out, st, &handled, 1, lr, eps))) return rc;
+    if (handled) return 0;
+  }
+  if ((rc = brk_twotower_step(ctx, user, item, u, i, cand_ids, labels, batch, mode, 1, ws, loss_out, stream))) return rc;
+  brk_table dense_pass[4], rows_pass[2];
+  int nd = 0, nr = 0;
+  const brk_tower* tw[2] = {user, item};
+  for (int k = 0; k < 2; ++k) {
+    const brk_table& e = tw[k]->emb;
+    if (e.touched && int64_t(e.rows) * e.d * 4 > rows_threshold_bytes) rows_pass[nr++] = e;
+    else dense_pass[nd++] = e;
+  }
+  dense_pass[nd++] = user->dense; dense_pass[nd++] = item->dense;
+  if ((rc = brk_adagrad_dense(ctx, dense_pass, nd, lr, eps, stream))) return rc;
+  if (nr && (rc = brk_adagrad_rows(ctx, rows_pass, nr, lr, eps, stream))) return rc;
   return 0;
 }

@@ -204,9 +204,26 @@ class TwoTowerModel:
         u, i = self._ids(info)
         return {"loss": self._train_ids(u, i, self._labels(info))}
 
+    def _train_step_native(self, u, i, labels, loss_out=None):
+        """Step + Keras Adagrad in one library call (brk_twotower_train_step): ONE cooperative launch when the in-batch
+        softmax step runs on the tensor cores and the batch fits on chip, the step + optimizer kernels otherwise."""
+        B = u.numel()
+        loss_out = loss_out if loss_out is not None else torch.empty(1, dtype=torch.float32, device=self.device)
+        ws = self._workspace(B)
+        ut, it = self.userTower.c_struct(), self.itemTower.c_struct()
+        opt = self.optimizer
+        N.check(N.lib().brk_twotower_train_step(N.ctx(self.device), C.byref(ut), C.byref(it), N.ptr(u), N.ptr(i), N.ptr(i),
+                                                N.ptr(labels) if labels is not None else None, B,
+                                                (1 if self.rdZero else 0) | (0x100 if self.tensor_cores else 0), C.byref(ws),
+                                                float(opt.lr), float(opt.eps), int(opt.rows_threshold_bytes), N.ptr(loss_out),
+                                                N.stream_ptr()), "brk_twotower_train_step")
+        return loss_out
+
     def _train_ids(self, u, i, labels, loss_out=None):
         if self.optimizer is None:
             self.compile()
+        if D.world_size() == 1 and u.numel() > 0 and isinstance(self.optimizer, H.Adagrad):
+            return self._train_step_native(u, i, labels, loss_out)
         if u.numel() > 0:
             loss = self._step(u, i, labels, True, loss_out)
         else:                                                # this rank's slice of a small global batch is empty

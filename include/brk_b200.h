@@ -406,6 +406,17 @@ int brk_twotower_step(brk_ctx* ctx, const brk_tower* user, const brk_tower* item
                       const int32_t* i, const int32_t* cand_ids, const float* labels, int64_t batch,
                       int32_t mode, int32_t training, const brk_twotower_workspace* ws, float* loss_out,
                       void* stream);
+/* One training step INCLUDING the optimizer: TwoTowerModel.train_step (trainers/twoTower.py:89-102) with
+ * tf.keras.optimizers.Adagrad(lr) (trainers/twoTower.py:278-279; accumulators in the tables' `m`).  mode as above.
+ * In-batch-softmax steps with mode bit 0x100 whose batch fits on chip (ceil(batch/128)^2 <= SM count, widths <= 128)
+ * run as ONE cooperative launch (csrc/twotower_fused.cu): towers, score tiles that never leave the SM, loss, all
+ * gradients and Adagrad on the touched rows + Dense blocks.  Everything else = brk_twotower_step + brk_adagrad_dense /
+ * brk_adagrad_rows (row-sparse for tables above rows_threshold_bytes that carry a touched bitmask).  Same results
+ * either way up to the summation order of the REDs. */
+int brk_twotower_train_step(brk_ctx* ctx, const brk_tower* user, const brk_tower* item, const int32_t* u,
+                            const int32_t* i, const int32_t* cand_ids, const float* labels, int64_t batch,
+                            int32_t mode, const brk_twotower_workspace* ws, float lr, float eps,
+                            int64_t rows_threshold_bytes, float* loss_out, void* stream);
 
 /* ---- K7/K8: full-catalog scoring + top-K ------------------------------------------------------
  * Stands in for tfrs.layers.factorized_top_k.BruteForce(k).index(candidates) + call(queries)

@@ -278,11 +278,15 @@ def test_gemm_tf32_all_layouts_exact_on_representable_inputs(dev, M, N, K, ta, t
         assert np.array_equal(Cd.cpu().numpy(), ref.astype(np.float32)), (accumulate,)
 
 
-@pytest.mark.parametrize("U,I,E,S,B", [(500, 300, 128, 128, 1000), (6040, 3706, 128, 128, 1000), (300, 200, 64, 64, 2048)])
+@pytest.mark.parametrize("U,I,E,S,B", [(500, 300, 128, 128, 1000), (6040, 3706, 128, 128, 1000), (300, 200, 64, 64, 2048),
+                                       (300, 200, 100, 60, 333), (300, 200, 32, 128, 100), (300, 200, 128, 128, 1536),
+                                       (300, 200, 64, 64, 129)])
 def test_twotower_tensor_core_step_matches_tf32_oracle(dev, U, I, E, S, B):
-    """The two-tower step with every product on tcgen05 (TF32 operands; csrc/gemm_tc.cu) against oracle/twotower.py with
-    oracle/tf32.py's matmul: loss rtol 2e-3; gradients max |error| <= 1e-2 of the largest entry and Frobenius <= 1e-2
-    (no ReLU here: the graph is smooth, measured ~1e-4).  (6040, 3706, 128, 128, 1000) is BASELINE.json configs[2]."""
+    """The two-tower step with every product on tcgen05 (TF32 operands) against oracle/twotower.py with oracle/tf32.py's
+    matmul: loss rtol 2e-3; gradients max |error| <= 1e-2 of the largest entry and Frobenius <= 1e-2 (no ReLU here: the graph
+    is smooth, measured ~1e-4).  (6040, 3706, 128, 128, 1000) is BASELINE.json configs[2].  Batches up to 1536 run as the ONE
+    cooperative launch of csrc/twotower_fused.cu (ragged last tiles, widths that are not multiples of 32, T = 1 / 2 / 3 / 8 /
+    12 row blocks); batch 2048 takes the multi-kernel step of csrc/twotower.cu + gemm_tc.cu."""
     from binrec_b200.twoTower import TwoTowerModel
     from oracle import twotower as OT
     m = TwoTowerModel(E, I, U, "u", "i", list(range(U)), list(range(I)), semb=S, device=dev, tensor_cores=True)
@@ -316,3 +320,58 @@ def test_twotower_tensor_core_step_matches_tf32_oracle(dev, U, I, E, S, B):
         lg_ = m._step(uid, iid, None, True)
         m.optimizer.apply([m.userTower.emb, m.itemTower.emb], dense=[m.userTower.dense, m.itemTower.dense])
         np.testing.assert_allclose(lg_.item(), lr_, rtol=2e-3)
+
+
+@pytest.mark.parametrize("E,S,B,gtol", [(128, 128, 1000, 5e-4), (100, 60, 332, 5e-4), (64, 64, 76, 5e-4), (100, 60, 333, 1e-2)])
+def test_twotower_one_launch_step_equals_the_multi_kernel_step(dev, monkeypatch, E, S, B, gtol):
+    """csrc/twotower_fused.cu (one cooperative launch, scores on chip) against the multi-kernel step it replaces
+    (BRK_TT_NO_FUSED=1: gemm_tf32 products + inbatch_softmax_kernel) on the same inputs: same TF32 operand rule, so they
+    differ by summation order and by ex2.approx in the softmax only -- loss rtol 1e-5; gradients 5e-4 of the largest entry
+    (measured 1e-4: a last-bit difference in P now and then moves an operand across a TF32 truncation boundary).  Batch 333:
+    the multi-kernel step takes the fp32 product wherever a leading dimension is not a multiple of 4 (the B x B matrix), the
+    one-launch step stays on the tensor cores, so there the two differ by TF32 rounding itself (measured 8e-4..4e-3; bound 1e-2
+    as against the oracle).
+    Then brk_twotower_train_step: five steps with Adagrad in the same launch against five steps + brk_adagrad_dense."""
+    from binrec_b200.twoTower import TwoTowerModel
+    U, I = 400, 150                                                     # 150 items: accidental hits in every batch
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    uid = torch.randint(2, U + 2, (B,), generator=g, device=dev, dtype=torch.int32)
+    iid = torch.randint(2, I + 2, (B,), generator=g, device=dev, dtype=torch.int32)
+    res = {}
+    for path in ("fused", "multi"):
+        if path == "multi":
+            monkeypatch.setenv("BRK_TT_NO_FUSED", "1")
+        else:
+            monkeypatch.delenv("BRK_TT_NO_FUSED", raising=False)
+        m = TwoTowerModel(E, I, U, "u", "i", list(range(U)), list(range(I)), semb=S, device=dev, tensor_cores=True)
+        loss = m._step(uid, iid, None, True).item()
+        le = m._step(uid, iid, None, False).item()                      # forward only: same loss, accumulators untouched
+        grads = [t.g.clone() for t in (m.userTower.emb, m.itemTower.emb, m.userTower.dense, m.itemTower.dense)]
+        touched = [t.touched.clone() for t in (m.userTower.emb, m.itemTower.emb)]
+        for t in (m.userTower.emb, m.itemTower.emb, m.userTower.dense, m.itemTower.dense):
+            t.g.zero_()
+        for t in (m.userTower.emb, m.itemTower.emb):
+            t.touched.zero_()
+        m.compile("Adagrad", learningRate=0.1)
+        losses = []
+        for k in range(5):
+            uk = torch.roll(uid, k); ik = torch.roll(iid, 2 * k)
+            losses.append(m._train_ids(uk, ik, None).item())
+        res[path] = (loss, le, grads, touched, losses, [t.w.clone() for t in (m.userTower.emb, m.itemTower.emb, m.userTower.dense,
+                                                                              m.itemTower.dense)],
+                     [t.g.abs().max().item() for t in (m.userTower.emb, m.itemTower.emb, m.userTower.dense, m.itemTower.dense)],
+                     [int(t.touched.count_nonzero().item()) for t in (m.userTower.emb, m.itemTower.emb)])
+    f, mk = res["fused"], res["multi"]
+    np.testing.assert_allclose(f[0], mk[0], rtol=1e-5)
+    np.testing.assert_allclose(f[1], f[0], rtol=1e-6)
+    for a, b_ in zip(f[2], mk[2]):
+        scale = b_.abs().max().item()
+        assert (a - b_).abs().max().item() <= gtol * scale, ((a - b_).abs().max().item(), scale)
+    for a, b_ in zip(f[3], mk[3]):
+        assert torch.equal(a, b_)                                       # same rows marked
+    np.testing.assert_allclose(f[4], mk[4], rtol=2e-5 if gtol < 1e-3 else 1e-4)
+    # weights after five steps: Adagrad moves an entry by lr * g / sqrt(0.1 + sum g^2), i.e. an entry whose g is small against
+    # the largest one sees the <= 2e-3 * max|g| gradient difference as lr * dg / 0.32 per step: bound 5 steps * 0.1 * 1e-2
+    for a, b_ in zip(f[5], mk[5]):
+        assert (a - b_).abs().max().item() <= (5e-3 if gtol < 1e-3 else 5e-2)
+    assert f[6] == [0.0] * 4 and f[7] == [0, 0] and mk[6] == [0.0] * 4 and mk[7] == [0, 0]   # accumulators and bitmasks left clean
