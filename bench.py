@@ -774,8 +774,7 @@ def secondary_measurements(dev, peaks):
         iid2 = torch.randint(2, I + 2, (Bt2,), generator=g, device=dev, dtype=torch.int32)
 
         def tt2_step():
-            tt2._step(uid2, iid2, None, True)
-            tt2.optimizer.apply([tt2.userTower.emb, tt2.itemTower.emb], dense=[tt2.userTower.dense, tt2.itemTower.dense])
+            tt2._train_ids(uid2, iid2, None)               # step + Adagrad: brk_twotower_train_step
 
         tt2_step()
         # the step as TwoTowerModel.fit runs it: one CUDA-graph replay per batch
@@ -789,9 +788,13 @@ def secondary_measurements(dev, peaks):
         s = _timed(gph.replay, 30)
         flops = 2.0 * Bt2 * 128 * 128 * 2 * 3 + 2.0 * Bt2 * Bt2 * 128 * 3   # two tower Dense layers and the B x B scores, fwd + 2 bwd products each
         out[tag] = {"value": Bt2 / s, "unit": "interactions/s", "ms_per_step": s * 1e3,
-                    "roofline": _tensor_roofline("gemm_tf32_kernel x 9 + inbatch_softmax_kernel (graph of one step)", flops, s, peaks,
+                    "roofline": _tensor_roofline("ttf::fused_step (one cooperative launch: towers, on-chip score tiles, gradients, Adagrad)"
+                                                 if Bt2 <= 1536 else "gemm_tf32_kernel x 9 + inbatch_softmax_kernel + adagrad (graph of one step)",
+                                                 flops, s, peaks,
                                                  "TF32 products against the bf16 peak (TF32 dense peak is half of it); at batch 1000 the "
-                                                 "step is a chain of 8 dependent ~6 us kernels, at 8192 it is bound by the B x B score matrix"),
+                                                 "step is latency: five phases of ~5 us separated by four grid barriers of ~1.4 us "
+                                                 "(profiles/r02_twotower_fused_trace.txt); at 8192 the batch does not fit on chip and the "
+                                                 "multi-kernel step is bound by the B x B score matrix"),
                     "config": f"two-tower E=S=128 (twoTower.py:40-41 shape), in-batch softmax batch {Bt2}, Adagrad 0.1, all products on tcgen05 "
                               f"(TF32), replayed as one CUDA graph per step (what TwoTowerModel.fit does)"}
         del tt2, gph

@@ -330,7 +330,6 @@ __global__ void __launch_bounds__(NT, 1) fused_step(const Params P) {
 #pragma unroll
       for (int k = 0; k < 64; k += 4)
         *reinterpret_cast<float4*>(buf2 + mn_off16(TS, r, h * 16 + (k >> 2))) = make_float4(pv[k], pv[k + 1], pv[k + 2], pv[k + 3]);
-      tmem_to_staging(tmem, 128, buf0);                                  // dq partial out of TMEM meanwhile (c_j is consumed)
       tc::fence_proxy_async_smem();
       __syncthreads();
       tc::fence_after_sync();
@@ -338,6 +337,8 @@ __global__ void __launch_bounds__(NT, 1) fused_step(const Params P) {
         issue_gemm<128, 128, 1, 1>(tmem, tc::smem_u32(buf2), TS, tc::smem_u32(buf1), TS, TS, false);
         tc::mma_commit(tc::smem_u32(&mbar));
       }
+      tmem_to_staging(tmem, 128, buf0);                                  // the dq partial leaves TMEM while that product runs (c_j is consumed)
+      __syncthreads();
       for (int idx = t; idx < TS * 32; idx += NT) {                      // row-contiguous REDs of the dq partial
         const int rr = idx >> 5, c4 = idx & 31;
         if (ti * TS + rr < B && c4 * 4 < S) red_add_f4(P.dz[0] + int64_t(ti * TS + rr) * S + c4 * 4, staging_ld(buf0, rr, c4));
