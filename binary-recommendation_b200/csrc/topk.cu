@@ -4,17 +4,22 @@
 // bpr_predict (src/models/bpr.py:122-133) and the streaming __topk of trainers/topKmetrics.py:51-72.
 //
 // scores = Q C^T is a tcgen05 GEMM (bf16 operands staged by TMA with the 128-byte swizzle, fp32
-// accumulators in TMEM, M = 128 users x N = 256 items per MMA tile) whose epilogue never writes a
+// accumulators in TMEM, M = 128 users x N = 128 items per MMA tile) whose epilogue never writes a
 // score to HBM: each epilogue thread owns one user row (= one TMEM lane), pulls 32 scores at a time
-// with tcgen05.ld, rejects the chunk with a FMNMX3 max-tree against the row's running k-th best and
-// only on a hit runs the exact sorted insertion.  Tie rule: strict '>' while items stream in
-// ascending id, i.e. equal scores keep the lower item id (tf.math.top_k / the reference's __topk).
+// with tcgen05.ld, reduces them with a FMNMX3 max-tree and compares the chunk maximum with the row's
+// running k-th best -- branch-free: the four chunk flags of a tile are voted on once per warp -- and
+// only flagged chunks are read again for the exact sorted insertion.  Tie rule: strict '>' while items
+// stream in ascending id, i.e. equal scores keep the lower item id (tf.math.top_k / the reference's __topk).
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected
-// lane), warps 2-9 = epilogue: warp w reads TMEM lanes 32*(w%4)..., and the two warps that share a
-// lane quadrant each take one 128-column half of every tile (two partial lists per row, merged by
-// topk_merge_kernel).  tcgen05.ld is double-buffered against the compare work.  Two 256-column
-// accumulators double-buffer MMA against epilogue.  Algorithmic traffic: 2*dpad B per user + 2*dpad B per item
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected
+// lane), warps 2-5 = epilogue: warp w reads TMEM lanes 32*(w%4)... of the whole 128-column tile.
+// tcgen05.ld is double-buffered against the compare work, two 128-column accumulators double-buffer
+// MMA against epilogue, and TWO CTAs share an SM (256 TMEM columns, <= 113 KB of shared memory each):
+// the four epilogue warps of a CTA advance in lockstep with their MMA issuer -- the accumulator of
+// tile t+2 is only free when the slowest warp has finished tile t -- and with one CTA per SM (round 1:
+// 8 epilogue warps on 256-column tiles) they spent 24 % of their time waiting for it (ncu, r02); a
+// second CTA fills those gaps: 4.04 -> 3.20 ms on the 65 536 x 250 k x 64 shard, 4.47 -> 3.77 ms at
+// d = 128 (profiles/r02_topk_probe.txt).  Algorithmic traffic: 2*dpad B per user + 2*dpad B per item
 // per m-tile pass (L2-resident item index) + 8k B of results per user.
 #include "common.cuh"
 #include "tc.cuh"
@@ -25,11 +30,11 @@
 namespace {
 
 constexpr int kBM = 128;          // users per CTA (TMEM lanes)
-constexpr int kBN = 256;          // items per MMA tile (TMEM columns per accumulator)
+constexpr int kBN = 128;          // items per MMA tile (TMEM columns per accumulator)
 constexpr int kKBlock = 64;       // bf16 elements per 128-byte swizzle row
-constexpr int kThreadsTopk = 320;
-constexpr int kEpiWarps = 8;
-constexpr int kHalves = 2;        // column halves per tile (epilogue warps per TMEM lane quadrant)
+constexpr int kThreadsTopk = 192;
+constexpr int kEpiWarps = 4;
+constexpr int kHalves = 1;        // column parts per tile (epilogue warps per TMEM lane quadrant)
 constexpr int kMaxKB = 4;         // dpad <= 256
 constexpr uint32_t kABytesPerKB = kBM * 128;   // 16 KB
 constexpr uint32_t kBBytes = kBN * 128;        // 32 KB per stage (one k-block of one item tile)
@@ -61,10 +66,13 @@ __device__ __forceinline__ void topk_insert(float (&vals)[K], int32_t (&ids)[K],
 }
 
 template <int K_CAP>
-__global__ void __launch_bounds__(kThreadsTopk, 1)
+__global__ void __launch_bounds__(kThreadsTopk, 2)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                   const TopkParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // slow-path scratch of the epilogue threads: STATIC shared memory, so that the compiler emits STS / LDS for it (carved
+  // out of the dynamic block through a generic pointer it was 32 generic ST.E per spilled chunk)
+  __shared__ float scratch_s[kEpiWarps * 32 * 32];
   // 1024-byte alignment for the 128-byte swizzle
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t smem_a = tc::smem_u32(smem);
@@ -93,7 +101,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     for (int b = 0; b < 2; ++b) { tc::mbar_init(tmem_full(b), 1); tc::mbar_init(tmem_empty(b), kEpiWarps); }
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc<512>(tc::smem_u32(tmem_slot));
+  if (warp == 1) tc::tmem_alloc<2 * kBN>(tc::smem_u32(tmem_slot));
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -154,12 +162,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     // Slow-path scratch: 32 floats per epilogue thread, column-major so that lane i of a warp hits
     // bank i (conflict-free).  Keeps ONE compact copy of the insertion code (a dynamic loop) instead
     // of 32 unrolled copies per call site -- the unrolled form overflowed the instruction cache.
-    float* scratch = reinterpret_cast<float*>(smem + P.KB * kABytesPerKB + P.stages * kBBytes + 256) +
-                     (threadIdx.x - 64);
+    float* scratch = scratch_s + (threadIdx.x - 64);
     constexpr int kScratchStride = kEpiWarps * 32;
 
     auto process = [&](uint32_t (&r)[32], int64_t col0, bool ragged) {
-      if (P.probe) {                                    // keep the loads alive, do nothing else
+      if (P.probe == 1) {                               // keep the loads alive, do nothing else
         uint32_t x = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) x ^= r[j];
@@ -221,6 +228,21 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 #undef V
     };
 
+    // max of a 32-score chunk: 4 independent FMNMX3 chains (one per group of 8 columns), no branch
+    auto chunk_max = [&](const uint32_t (&r)[32]) -> float {
+#define V(j) __uint_as_float(r[(j)])
+      float gm[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float m = fmaxf(fmaxf(V(8 * g), V(8 * g + 1)), V(8 * g + 2));
+        m = fmaxf(fmaxf(m, V(8 * g + 3)), V(8 * g + 4));
+        m = fmaxf(fmaxf(m, V(8 * g + 5)), V(8 * g + 6));
+        gm[g] = fmaxf(m, V(8 * g + 7));
+      }
+#undef V
+      return fmaxf(fmaxf(fmaxf(gm[0], gm[1]), gm[2]), gm[3]);
+    };
+
     for (int t = 0; t < my_tiles; ++t) {
       const int buf = t & 1;
       tc::mbar_wait(tmem_full(buf), (t >> 1) & 1);
@@ -229,16 +251,59 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       const bool ragged = col_half + kBN / kHalves > P.I;   // only in the last item tile
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + buf * kBN + half * (kBN / kHalves);
       uint32_t ra[32], rb[32];
-      tc::tmem_ld_32x32_issue(taddr, ra);
-      tc::tmem_ld_wait(ra);
-#pragma unroll 1
-      for (int c = 0; c < kChunks; c += 2) {
-        tc::tmem_ld_32x32_issue(taddr + (c + 1) * 32, rb);     // in flight while chunk c is processed
-        process(ra, col_half + c * 32, ragged);
+      if (P.probe == 2) {                                 // diagnostics: the half-tile as 2 x 64 packed 16-bit columns
+        tc::tmem_ld_32x32_pack16_issue(taddr, ra);
+        tc::tmem_ld_32x32_pack16_issue(taddr + 64, rb);
+        tc::tmem_ld_wait(ra);
         tc::tmem_ld_wait(rb);
-        if (c + 2 < kChunks) tc::tmem_ld_32x32_issue(taddr + (c + 2) * 32, ra);
-        process(rb, col_half + (c + 1) * 32, ragged);
-        if (c + 2 < kChunks) tc::tmem_ld_wait(ra);
+        uint32_t x = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x ^= ra[j] ^ rb[j];
+        if (x == 0x7fc12345u) thr = 0.f;
+      } else if (ragged || P.probe != 0) {                // last item tile / diagnostics: chunk by chunk
+        tc::tmem_ld_32x32_issue(taddr, ra);
+        tc::tmem_ld_wait(ra);
+#pragma unroll 1
+        for (int c = 0; c < kChunks; c += 2) {
+          tc::tmem_ld_32x32_issue(taddr + (c + 1) * 32, rb);     // in flight while chunk c is processed
+          process(ra, col_half + c * 32, ragged);
+          tc::tmem_ld_wait(rb);
+          if (c + 2 < kChunks) tc::tmem_ld_32x32_issue(taddr + (c + 2) * 32, ra);
+          process(rb, col_half + (c + 1) * 32, ragged);
+          if (c + 2 < kChunks) tc::tmem_ld_wait(ra);
+        }
+      } else {
+        // The common case has NO branch per chunk: the four chunk maxima are compared with the row's k-th best (as it
+        // stood at the start of the tile: it only rises, so this flags a superset) into a 4-bit mask, and ONE warp-wide
+        // vote per tile decides whether anything has to be looked at again.  (With a compare-and-branch, a probe check
+        // and a ragged check per chunk the epilogue ran at 15-17 scores/clk/SM against 29 for the bare TMEM drain: the
+        // ~5 branches per chunk, not the max-tree, were the cost -- profiles/r02_topk_probe.txt.)
+        static_assert(kChunks == 4, "the tile epilogue is written out for four 32-column chunks per warp");
+        uint32_t flagged = 0u;
+        tc::tmem_ld_32x32_issue(taddr, ra);
+        tc::tmem_ld_wait(ra);
+        tc::tmem_ld_32x32_issue(taddr + 32, rb);
+        flagged |= chunk_max(ra) > thr ? 1u : 0u;
+        tc::tmem_ld_wait(rb);
+        tc::tmem_ld_32x32_issue(taddr + 64, ra);
+        flagged |= chunk_max(rb) > thr ? 2u : 0u;
+        tc::tmem_ld_wait(ra);
+        tc::tmem_ld_32x32_issue(taddr + 96, rb);
+        flagged |= chunk_max(ra) > thr ? 4u : 0u;
+        tc::tmem_ld_wait(rb);
+        flagged |= chunk_max(rb) > thr ? 8u : 0u;
+        // chunks some lane of the warp has to look at again.  They are read out of TMEM a second time (the accumulator is
+        // still ours): keeping all four chunks in registers and inlining the candidate path four times measured slower
+        // (instruction cache: 4.34 vs 4.04 ms on the 65 536 x 250 k shard)
+        uint32_t todo = __reduce_or_sync(0xffffffffu, flagged);
+#pragma unroll 1
+        while (todo) {                                    // ascending chunk = ascending item id
+          const int c = __ffs(todo) - 1;
+          todo &= todo - 1;
+          tc::tmem_ld_32x32_issue(taddr + c * 32, ra);
+          tc::tmem_ld_wait(ra);
+          process(ra, col_half + c * 32, false);
+        }
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -256,7 +321,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc<512>(tmem_base);
+  if (warp == 1) tc::tmem_dealloc<2 * kBN>(tmem_base);
 }
 
 // Merge S sorted partial lists per user into one: score descending, id ascending on ties --
@@ -338,11 +403,12 @@ int launch_topk(const CUtensorMap& tq, const CUtensorMap& tcm, const TopkParams&
   return 0;
 }
 
-int plan_splits(const brk_ctx* ctx, int64_t U, int64_t I, int* n_splits, int* tiles_per_split) {
+// Item splits for small user counts: enough CTAs for every slot (`slots` = SMs x CTAs per SM at this row width)
+int plan_splits(int slots, int64_t U, int64_t I, int* n_splits, int* tiles_per_split) {
   const int64_t m_tiles = (U + kBM - 1) / kBM;
   const int n_tiles = int((I + kBN - 1) / kBN);
   int S = 1;
-  if (m_tiles < ctx->sm_count) S = int((ctx->sm_count + m_tiles - 1) / m_tiles);
+  if (m_tiles < slots) S = int((slots + m_tiles - 1) / m_tiles);
   if (S > n_tiles) S = n_tiles;
   if (S > 32) S = 32;
   if (S < 1) S = 1;
@@ -374,7 +440,7 @@ extern "C" int brk_rows_to_bf16(brk_ctx* ctx, const float* src, int64_t rows, in
 extern "C" int64_t brk_score_topk_workspace_bytes(brk_ctx* ctx, int64_t U, int64_t I, int32_t k) {
   if (!ctx || U <= 0 || I <= 0 || k <= 0) return 0;
   int S, tps;
-  plan_splits(ctx, U, I, &S, &tps);
+  plan_splits(2 * ctx->sm_count, U, I, &S, &tps);      // the most any row width asks for
   return int64_t(S) * kHalves * U * k * 8;
 }
 
@@ -392,17 +458,20 @@ extern "C" int brk_score_topk_bf16(brk_ctx* ctx, const uint16_t* q_bf16, int64_t
 
   TopkParams P;
   P.U = U; P.I = I; P.KB = dpad / kKBlock; P.k = k; P.id_offset = id_offset;
-  P.probe = getenv("BRK_TOPK_PROBE") != nullptr;
+  P.probe = getenv("BRK_TOPK_PROBE") ? atoi(getenv("BRK_TOPK_PROBE")) : 0;
   int S, tps;
-  P.n_tiles = plan_splits(ctx, U, I, &S, &tps);
+  P.n_tiles = plan_splits(ctx->sm_count * (dpad <= 128 ? 2 : 1), U, I, &S, &tps);
   P.tiles_per_split = tps;
   const size_t a_bytes = size_t(P.KB) * kABytesPerKB;
   constexpr size_t kScratchBytes = size_t(kEpiWarps) * 32 * 32 * sizeof(float);   // 32 KB
-  int stages = int((227 * 1024 - 1024 - 256 - kScratchBytes - a_bytes) / kBBytes);
+  // two CTAs per SM (each with its own pair of TMEM accumulators) when the query tile leaves room: while one CTA's epilogue
+  // warps wait for their next accumulator the other's keep the SM busy
+  const size_t budget = a_bytes <= 32 * 1024 ? size_t(113) * 1024 : size_t(227) * 1024;
+  int stages = int((budget - 1024 - 256 - kScratchBytes - a_bytes) / kBBytes);
   if (stages > 6) stages = 6;
   BRK_REQUIRE(stages >= 2, BRK_E_ARG, "brk_score_topk_bf16: no room for a 2-stage pipeline at dpad=%d", dpad);
   P.stages = stages;
-  const size_t smem = 1024 + a_bytes + size_t(stages) * kBBytes + 256 + kScratchBytes;
+  const size_t smem = 1024 + a_bytes + size_t(stages) * kBBytes + 256;   // + kScratchBytes of static shared memory
 
   const int parts = S * kHalves;                       // partial lists per user row
   const int64_t need = int64_t(parts) * U * k * 8;
