@@ -803,7 +803,7 @@ def secondary_measurements(dev, peaks):
     s = _timed(lambda: idx(Q), 50)
     out["topk_ml1m"] = {"value": U / s, "unit": "users/s", "ms": s * 1e3,
                         "roofline": _tensor_roofline("score_topk_kernel", 2.0 * U * I * 128, s, peaks,
-                                                     "one wave of 48 CTAs: launch / latency bound at this size"),
+                                                     "48 user tiles x 7 item splits on 296 CTA slots: launch / latency bound at this size"),
                         "config": "6040 users x 3706 items, d=128, k=10, bf16 tcgen05 scoring + fused top-K (incl. query bf16 conversion)"}
     Ub, Ib = 65536, 250000
     for d in (64, 128):
@@ -812,8 +812,9 @@ def secondary_measurements(dev, peaks):
         s = _timed(lambda: idx(Q), 5, warm=1)
         out[f"topk_shard_d{d}"] = {"value": Ub / s, "unit": "users/s", "ms": s * 1e3,
                                    "roofline": _tensor_roofline("score_topk_kernel", 2.0 * Ub * Ib * d, s, peaks,
-                                                                "limited by the selection epilogue (tcgen05.ld + compare tree per 32 scores) and the warm-up of "
-                                                                "the running k-th-best threshold on a short shard, DESIGN.md section 4"),
+                                                                "two CTAs per SM, branch-free chunk flags; with warm thresholds the epilogue runs at the TMEM drain rate "
+                                                                "(31 scores/clk/SM), what is left on random data is the second look at flagged chunks while the "
+                                                                "k-th-best thresholds warm up on a short shard (DESIGN.md section 4.1, profiles/r02_topk_probe.txt)"),
                                    "config": f"65536 users x 250000 items (one 8-way item shard of BASELINE.json configs[4]), d={d}, k=10"}
         del Q, Cm, idx
     return out
@@ -910,7 +911,7 @@ def c5_topk_block(dev, world, rank, peaks):
     return {"metric": "top-K users/sec (1M users x 2M items, d=64, k=10)", "value": U / s, "unit": "users/s", "n_gpus": world,
             "ms": s * 1e3, "scaling": "strong",
             "roofline": _tensor_roofline("score_topk_kernel (per rank; + all-gather of [U,k] lists + topk_merge_kernel)", flops_gpu, s, peaks,
-                                         "per GPU, all-gather of the lists and merge included; the selection epilogue is the limiter (DESIGN.md section 4)"),
+                                         "per GPU, all-gather of the lists and merge included; the selection epilogue is the limiter (DESIGN.md section 4.1)"),
             "config": {"workload": "BASELINE.json configs[4]: full-catalog top-K sweep, bf16 operands, fp32 scores",
                        "parallelism": f"items range-sharded x{world}, NCCL all-gather of the [U, k] (score, id) lists, merge on every rank"}}
 
