@@ -241,7 +241,6 @@ __device__ __forceinline__ void load_tile_ids(int32_t* ids_s, const Args& A, int
 }
 // Gather x0 = [uMLP[u], iMLP[i]] for a tile: E/4 lanes per row, 16 bytes each (coalesced rows); every load of the
 // thread is issued before the first use.  MN = 0: K-major swizzle, 1: MN-major swizzle.
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 template <int E>
 __device__ __forceinline__ void gather_x0_issue(float4 (&v)[2 * (TS / (NT / (E / 4)))], const Args& A, const int32_t* ids_s, int valid) {
   constexpr int LPR = E / 4, RPP = NT / LPR, NP = TS / RPP;
@@ -490,21 +489,6 @@ __global__ void __launch_bounds__(NT, 2) tc_head(const Args A, const float* __re
     float part = fmaf(mu[p].x, mi[p].x, fmaf(mu[p].y, mi[p].y, fmaf(mu[p].z, mi[p].z, mu[p].w * mi[p].w)));
     part = group_sum<LPR>(part);
     if (mc4 == 0) mfs[p * RPP + mrr] = part;
-  }
-  if (tile + int(gridDim.x) < n_tiles) {                   // ask the next tile's h2 columns and MF rows into L2
-    const int64_t nb0 = int64_t(tile + gridDim.x) * TS;
-    for (int l = t; l < H2 * (TS / 32); l += NT) {
-      const int64_t col = nb0 + (l % (TS / 32)) * 32;
-      if (col < A.B) prefetch_l2(A.h2 + int64_t(l / (TS / 32)) * A.B + col);
-    }
-    for (int l = t; l < 2 * TS; l += NT) {
-      const int s = l & (TS - 1), tab = l / TS;
-      if (nb0 + s < A.B) {
-        const float* w = locate<E>(tab == 0 ? A.uMF : A.iMF, __ldg((tab == 0 ? A.u : A.i) + nb0 + s)).w;
-#pragma unroll
-        for (int c = 0; c < E; c += 32) prefetch_l2(w + c);
-      }
-    }
   }
   tc::mbar_wait(tc::smem_u32(&ctl.bar), phase);
   phase ^= 1u;
@@ -940,22 +924,6 @@ __global__ void __launch_bounds__(NT) tc_bwd1(const Args A, const float* __restr
         tc::mma_tf32_ss(tmem + WCOL, ad, bd, idesc, (ks != 0 || it != 0) ? 1u : 0u);
       }
       tc::mma_commit(tc::smem_u32(&ctl.bar));
-    }
-    if (tile + int(gridDim.x) < n_tiles) {                  // ask the next tile's operands into L2 while this one computes
-      const int64_t nb0 = int64_t(tile + gridDim.x) * TS;
-      const int32_t* ids_n = ids_s[(it + 1) & 1];
-      for (int l = t; l < H1 * (TS / 32); l += NT) {
-        const int64_t off = int64_t(l / (TS / 32)) * A.B + nb0 + (l % (TS / 32)) * 32;
-        if (nb0 + (l % (TS / 32)) * 32 < A.B) { prefetch_l2(A.h1 + off); prefetch_l2(A.dy1 + off); }
-      }
-      for (int l = t; l < 2 * TS; l += NT) {
-        const int s = l & (TS - 1), tab = l / TS;
-        if (nb0 + s < A.B) {
-          const float* w = locate<E>(tab == 0 ? A.uMLP : A.iMLP, ids_n[tab * TS + s]).w;
-#pragma unroll
-          for (int c = 0; c < E; c += 32) prefetch_l2(w + c);
-        }
-      }
     }
     if (t < H1) {                                           // db1 on the CUDA cores meanwhile
       float sacc = 0.f;
