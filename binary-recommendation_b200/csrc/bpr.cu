@@ -259,6 +259,7 @@ struct BprCoopParams {
   float inv_global;               // 1 / (world * batch): gradient scale of the global mean loss
   unsigned long long* dbg;        // optional [n_steps][8] globaltimer stamps of block 0 (BRK_COOP_TRACE)
   long long spin_budget;          // clock64 budget of one cross-GPU wait (default ~30 s; BRK_PEER_SPIN_MS)
+  int32_t prefetch;               // bulk L2 prefetch of the table state at kernel entry (BRK_BPR_NO_PREFETCH=1 turns it off)
 };
 
 __device__ __forceinline__ void coop_st_release_sys(uint32_t* p, uint32_t v) {
@@ -326,6 +327,28 @@ __global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParam
   double p1 = pw[1], p2 = pw[2];                       // running beta powers, advanced per step in registers
   const brk_table tabs[2] = {P.user, P.item};
 
+  // The whole optimizer state is asked into L2 up front with BULK prefetches (one instruction per CTA and array slice,
+  // streamed by the copy engine of the SM): when other work has evicted the 10 MB since the last launch -- bench.py's
+  // flushed-L2 measurement is exactly that -- phase 2 of the first step otherwise starts on cold m / v / g lines.
+  // (Per-line prefetch.global.L2, 80 k requests, cost more than it hid: section 4.3 of DESIGN.md.)
+  if (P.prefetch && threadIdx.x == 0) {
+    for (int k = 0; k < 2; ++k) {
+      const int64_t bytes = tabs[k].rows * tabs[k].d * 4;
+      int64_t per = (bytes + gridDim.x - 1) / gridDim.x;
+      per = (per + 15) & ~int64_t(15);
+      const int64_t off = int64_t(blockIdx.x) * per;
+      if (off < bytes) {
+        const uint32_t n = uint32_t(((off + per <= bytes ? per : bytes - off)) & ~int64_t(15));
+        if (n) {
+          const float* arrs[4] = {tabs[k].w, tabs[k].g, P.world > 1 ? nullptr : tabs[k].m, P.world > 1 ? nullptr : tabs[k].v};
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+            if (arrs[a] != nullptr && brk_aligned16(arrs[a]))
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(arrs[a]) + off), "r"(n) : "memory");
+        }
+      }
+    }
+  }
   if (sample) {                                         // step 0 is staged by everybody, up front
     bpr_stage_step(P, P.use_inline ? P.inline_steps[0] : P.steps[0], 0, tid, nthr);
     grid.sync();
@@ -620,6 +643,7 @@ static int launch_coop_steps(brk_ctx* ctx, const brk_table* user, const brk_tabl
     BRK_CUDA(cudaMemset(g_coop_trace, 0, 4096 * 8 * sizeof(unsigned long long)));
   }
   P.dbg = (g_coop_trace && n_steps <= 4096) ? g_coop_trace : nullptr;
+  P.prefetch = getenv("BRK_BPR_NO_PREFETCH") ? 0 : 1;
   {
     const char* e = getenv("BRK_PEER_SPIN_MS");              // budget of one cross-GPU wait; default ~30 s at 2 GHz
     const long long ms = e ? atoll(e) : 0;
