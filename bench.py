@@ -363,7 +363,9 @@ def product_arm(args):
         e1.record()
         barrier()
         e2e_wall = time.perf_counter() - t0
-        e2e_launches = (K + 15) // 16                      # one cooperative launch per chunk of 16 steps
+        e2e_launches, _k, _c = 0, 0, 2                     # one cooperative launch per chunk: 2, 4, 8, then 16 steps each
+        while _k < K:
+            e2e_launches += 1; _k += _c; _c = min(2 * _c, 16)
         if world == 1:
             # zero-copy variant: ids stay in pinned host memory, ONE launch, the kernel pulls them over PCIe itself
             net.train_steps_mapped(hu, hp, order[:W], BATCH, 7, 1, hloss[:W])

@@ -770,22 +770,31 @@ extern "C" int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, con
   BRK_REQUIRE(!use_dp || (coop_ok && item->w == user->w + user->rows * user->d && item->g == user->g + user->rows * user->d),
               BRK_E_ARG, "brk_bpr_train_steps_host: data-parallel mode needs adjacent arena views, d %% 4 == 0, d <= 128");
   brk_table tabs[2] = {*user, *item};
-  const int n_chunks = (n_steps + kChunk - 1) / kChunk;
+  // Chunk plan: 2, 4, 8 steps, then kChunk each.  The first launch waits for its whole chunk's ids, so a call of a few
+  // steps (the bench's default --steps 20) used to spend ~150 us on 16 steps' worth of DMA before the first kernel; with a
+  // short first chunk the kernels start after two steps' ids (256 KB) and every later copy hides behind compute.
+  std::vector<int> starts;                          // chunk j = steps [starts[j], starts[j + 1])
+  for (int k = 0, c = 2; k < n_steps; k += c, c = (c * 2 < kChunk ? c * 2 : kChunk)) starts.push_back(k);
+  const int n_chunks = int(starts.size());
+  starts.push_back(n_steps);
+  std::vector<int> chunk_of(n_steps);
+  for (int j = 0; j < n_chunks; ++j)
+    for (int k = starts[j]; k < starts[j + 1]; ++k) chunk_of[k] = j;
   auto count_of = [&](int k) { const int64_t off = batch_index_host[k] * batch; return (off + batch <= total) ? batch : total - off; };
   // slot of step k: two chunk halves of kChunk slots, each slot = [u: batch][p: batch]
-  auto slot_of = [&](int k) { return d_stage + (int64_t((k / kChunk) & 1) * kChunk + (k % kChunk)) * 2 * batch; };
+  auto slot_of = [&](int k) { const int j = chunk_of[k]; return d_stage + (int64_t(j & 1) * kChunk + (k - starts[j])) * 2 * batch; };
   auto copy_chunk = [&](int j) -> int {            // on the copy stream: results of chunk j-2 back, ids of chunk j in
     if (j >= 2) {
       BRK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_done[j & 1], 0));
-      if (losses_host)                               // the kChunk step losses of chunk j-2, one DMA
-        BRK_CUDA(cudaMemcpyAsync(losses_host + (j - 2) * kChunk, d_losses + (j - 2) * kChunk, kChunk * sizeof(float),
+      if (losses_host)                               // the step losses of chunk j-2, one DMA
+        BRK_CUDA(cudaMemcpyAsync(losses_host + starts[j - 2], d_losses + starts[j - 2], (starts[j - 1] - starts[j - 2]) * sizeof(float),
                                  cudaMemcpyDeviceToHost, cs));
     }
     // the chunk's H2D copies are spread over kCopyLanes streams so that several DMAs are in flight at once (a
     // single 128 KiB copy costs 10-35 us of latency on virtualised hosts); everything rejoins on `cs`
     BRK_CUDA(cudaEventRecord(ctx->ev_go, cs));
     for (int a = 0; a < BRK_COPY_AUX; ++a) BRK_CUDA(cudaStreamWaitEvent(ctx->copy_aux[a], ctx->ev_go, 0));
-    for (int k = j * kChunk; k < (j + 1) * kChunk && k < n_steps; ++k) {
+    for (int k = starts[j]; k < starts[j + 1]; ++k) {
       const int64_t hoff = batch_index_host[k] * host_batch_stride, cnt = count_of(k);
       const int lane = k % (BRK_COPY_AUX + 1);
       cudaStream_t cl = lane == 0 ? cs : ctx->copy_aux[lane - 1];
@@ -809,7 +818,7 @@ extern "C" int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, con
   if (int rc = copy_chunk(0)) return rc;
   for (int j = 0; j < n_chunks; ++j) {
     if (j + 1 < n_chunks) { if (int rc = copy_chunk(j + 1)) return rc; }
-    const int k0 = j * kChunk, k1 = (k0 + kChunk < n_steps) ? k0 + kChunk : n_steps;
+    const int k0 = starts[j], k1 = starts[j + 1];
     BRK_CUDA(cudaStreamWaitEvent(st, ctx->ev_ready[j & 1], 0));
     if (coop_ok) {
       BprStep steps[kChunk];
@@ -844,7 +853,7 @@ extern "C" int brk_bpr_train_steps_host(brk_ctx* ctx, const brk_table* user, con
   // results of the last two chunks, then rejoin: everything the copy stream did is ordered before
   // whatever follows on `st`
   if (losses_host) {
-    const int first = (n_chunks >= 2 ? n_chunks - 2 : 0) * kChunk;
+    const int first = starts[n_chunks >= 2 ? n_chunks - 2 : 0];
     BRK_CUDA(cudaStreamWaitEvent(cs, ctx->ev_done[(n_chunks - 1) & 1], 0));
     BRK_CUDA(cudaMemcpyAsync(losses_host + first, d_losses + first, (n_steps - first) * sizeof(float),
                              cudaMemcpyDeviceToHost, cs));
