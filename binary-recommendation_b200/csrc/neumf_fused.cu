@@ -223,7 +223,7 @@ __device__ __forceinline__ void gather_tagged(const unsigned long long* base, in
       const int j = j0 + q8 * G;
       if (j < n_tiles) {
         while (uint32_t(v[q8].x >> 32) != tag || uint32_t(v[q8].y >> 32) != tag) {
-          if (clock64() - t0 > 4000000000LL) { atomicExch(err, 1u); break; }
+          if (clock64() - t0 > 4000000000LL) { atomicExch(err, 1u); __trap(); }
           v[q8] = __ldcg(reinterpret_cast<const ulonglong2*>(base + size_t(j) * stride64) + f2);
         }
         a0 += double(__uint_as_float(uint32_t(v[q8].x))); a1 += double(__uint_as_float(uint32_t(v[q8].y)));
@@ -307,8 +307,8 @@ __device__ __forceinline__ void build_image(uint8_t* dst, F value) {
 
 // Grid-wide barrier of a cooperative launch: one release-RED on a monotonically increasing counter and an acquire
 // spin by thread 0 (cg::grid.sync() costs two fences and an atomic with return; measured ~1 us more per barrier).
-// `target` is the counter value at which every CTA has arrived.  A bounded spin: a lost CTA raises bar[1] instead of
-// hanging the GPU.
+// `target` is the counter value at which every CTA has arrived.  A bounded spin: a lost CTA raises bar[1] and TRAPS (the
+// launch fails with a CUDA error at the next synchronisation) instead of hanging the GPU or returning a half-reduced step.
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& target) {
   __syncthreads();
   target += gridDim.x;
@@ -318,7 +318,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ta
     unsigned int v;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-      if (clock64() - t0 > 4000000000LL) { atomicExch(bar + 1, 1u); break; }
+      if (clock64() - t0 > 4000000000LL) { atomicExch(bar + 1, 1u); __trap(); }
     } while (int(v - target) < 0);
   }
   __syncthreads();

@@ -119,7 +119,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ta
     unsigned int v;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-      if (clock64() - t0 > 4000000000LL) { atomicExch(bar + 1, 1u); break; }      // a lost CTA: flag it instead of hanging
+      if (clock64() - t0 > 4000000000LL) { atomicExch(bar + 1, 1u); __trap(); }      // a lost CTA: flag it and fail the launch instead of hanging
     } while (int(v - target) < 0);
   }
   __syncthreads();
