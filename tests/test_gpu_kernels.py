@@ -266,7 +266,8 @@ def test_bpr_host_fed_steps_match_oracle(dev, path):
     net.set_training_pairs(u, p)
     orc = OB.BPROracle(U, I, d, seed=42)
     indptr, sitems = OP.build_csr(u, p, U)
-    order = [2, 0, 7, 3, 3, 1, len(u) // B, 5, 4, 6, 0, 1, 2, len(u) // B, 9, 8, 3, 7, 10]   # ragged tail batches; three chunks of the host-fed ring
+    # ragged tail batches; 37 steps = chunks of 2, 4, 8, 16 and 7 steps of the host-fed ring (ramped plan of brk_bpr_train_steps_host)
+    order = [2, 0, 7, 3, 3, 1, len(u) // B, 5, 4, 6, 0, 1, 2, len(u) // B, 9, 8, 3, 7, 10] + [(3 * k + 1) % (len(u) // B + 1) for k in range(18)]
     hu, hp = torch.from_numpy(u).pin_memory(), torch.from_numpy(p).pin_memory()
     if path == "copy":
         losses = net.train_steps_from_host(hu, hp, order, B, 7, 5)
