@@ -240,11 +240,6 @@ __global__ void __launch_bounds__(NT, 1) fused_step(const Params P) {
     wait_mma();
     __syncthreads();                                                    // every thread knows the operand tiles are free
     stamp(P, 9);
-    if (P.training) {                                                   // the gradient products' B operands, in flight from here
-      load_tile<1>(buf0, P.z[1], S, tj * TS, B, S);                     // c_j [K = j][N = S]
-      load_tile<1>(buf1, P.z[0], S, ti * TS, B, S);                     // q_i [K = i][N = S]
-      cp_async_commit();
-    }
     // Read-out in the log2 domain (one FFMA + one MUFU.EX2 per score).  pv[k] ends up holding e_k = 2^(s_k - m) with m the
     // maximum of this thread's 64 columns, so that the gradient phase needs ONE scale per thread, not a second exponential
     // per score: P_k = e_k * 2^(m - lse).
@@ -279,6 +274,11 @@ __global__ void __launch_bounds__(NT, 1) fused_step(const Params P) {
       const float m0 = pm[0][r], m1 = pm[1][r], M = fmaxf(m0, m1);
       const float Ms = M == -CUDART_INF_F ? 0.f : M;
       P.part[int64_t(ig) * T + tj] = make_float2(M, ps[0][r] * ex2(m0 - Ms) + ps[1][r] * ex2(m1 - Ms));
+    }
+    if (P.training) {                                                   // the gradient products' B operands travel while the grid
+      load_tile<1>(buf0, P.z[1], S, tj * TS, B, S);                     // waits at the barrier: c_j [K = j][N = S]
+      load_tile<1>(buf1, P.z[0], S, ti * TS, B, S);                     // q_i [K = i][N = S]
+      cp_async_commit();
     }
   }
   stamp(P, 3);
@@ -355,6 +355,21 @@ __global__ void __launch_bounds__(NT, 1) fused_step(const Params P) {
       tc::fence_before_sync();
     }
   }
+  // phase G's operands that do not depend on the barrier travel across it: the Dense kernel (rows job) or the embedding rows,
+  // gathered again straight into the MN-major view (weights job)
+  const bool g_cta = P.training && b < 4 * T;
+  const int gk = b / (2 * T), g_r0 = ((b % (2 * T)) >> 1) * TS, g_valid = min(TS, B - g_r0), g_job = b & 1;
+  if (g_cta) {
+    __syncthreads();                                                    // staging and operand tiles of the phase above are done with
+    if (t < TS) ids_s[t] = t < g_valid ? __ldg(P.ids[gk] + g_r0 + t) : 0;
+    if (g_job == 0) {
+      load_tile<0>(buf1, P.W[gk], S, 0, P.E[gk], S);
+    } else {
+      __syncthreads();
+      gather_tile<1>(buf0, (gk == 0 ? P.eu : P.ei).w, P.E[gk], ids_s, g_valid);
+    }
+    cp_async_commit();
+  }
   stamp(P, 5);
   grid_barrier(P.bar, bar_target);
   stamp(P, 6);
@@ -365,16 +380,12 @@ __global__ void __launch_bounds__(NT, 1) fused_step(const Params P) {
   }
 
   // ---------------- phase G: gradients of the tower parameters ----------------
-  if (P.training && b < 4 * T) {
-    const int k = b / (2 * T), rb = (b % (2 * T)) >> 1, job = b & 1;
-    const int r0 = rb * TS, valid = min(TS, B - r0), E = P.E[k];
+  if (g_cta) {
+    const int k = gk, job = g_job, r0 = g_r0, valid = g_valid, E = P.E[k];
     const brk_table& tab = k == 0 ? P.eu : P.ei;
-    __syncthreads();                                                    // ids_s / staging of the earlier phases are done with
-    if (t < TS) ids_s[t] = t < valid ? __ldg(P.ids[k] + r0 + t) : 0;
     if (job == 0) {
       // de = dz W^T : A = dz [M = samples][K = S] K-major, B = W [N = E][K = S] K-major -> REDs into the rows' accumulators
       load_tile<0>(buf0, P.dz[k], S, r0, B, S);
-      load_tile<0>(buf1, P.W[k], S, 0, E, S);
       cp_async_commit();
       TTF_OPERANDS_READY();
       if (t == 0) {
@@ -395,8 +406,6 @@ __global__ void __launch_bounds__(NT, 1) fused_step(const Params P) {
     } else {
       // dW += e^T dz : A = e [K = samples][M = E] MN-major (gathered again, straight into that view), B = dz [K][N = S] MN-major
       load_tile<1>(buf1, P.dz[k], S, r0, B, S);
-      __syncthreads();
-      gather_tile<1>(buf0, tab.w, E, ids_s, valid);
       cp_async_commit();
       TTF_OPERANDS_READY();
       if (t == 0) {
