@@ -680,7 +680,7 @@ __device__ __forceinline__ void stage_dz_tiles(uint8_t* Zk, uint8_t* Zm, const f
 //   dz2 = bn2-backward(dy2) * act'(h2);  dW2 += d1^T dz2 (accumulated in TMEM across this CTA's tiles);
 //   dd1 = dropout-mask * dz2 W2^T -> dy1 with its BatchNorm-backward sums
 template <int E, int H1, int H2, int H3, int ACT>
-__global__ void __launch_bounds__(NT) tc_bwd2(const Args A, const float* __restrict__ img, int n_tiles) {
+__global__ void __launch_bounds__(NT, 2) tc_bwd2(const Args A, const float* __restrict__ img, int n_tiles) {
   using L = Layout<E, H1, H2, H3>; using AC = Acc<H1, H2>; using I = Img<E, H1, H2, H3>;
   constexpr int MW = H1 >= 64 ? H1 : 64;                   // weight-gradient rows per MMA (M); H1 = 32 reads its column block twice
   constexpr int WCOL = H1;                                 // TMEM: [0, H1) dd1, [WCOL, WCOL + H2) dW2
@@ -722,15 +722,18 @@ __global__ void __launch_bounds__(NT) tc_bwd2(const Args A, const float* __restr
     const int valid = int((A.B - b0) < int64_t(TS) ? (A.B - b0) : int64_t(TS));
     const int s = t & (TS - 1), hf = t >> 7;
     const bool ok = s < valid;
+    // both memory phases of the tile are issued back to back (h2 / dy2 columns, then h1 columns): one DRAM round trip, not two
+    float hv2[H2 / 2], dv2[H2 / 2];
+    dz_issue<H2>(hv2, dv2, A.h2, A.dy2, A.B, b0, valid);
+    constexpr int HH = H1 / 2;
+    float hv1[HH];                                          // kept for the epilogue's dd1 * xhat1 (same thread = same sample, same half)
     // d1 = dropout(bn1(h1)) in the MN swizzle (weight-gradient A operand)
     {
-      constexpr int HH = H1 / 2;
       uint32_t bits[(HH + 15) / 16];
 #pragma unroll
       for (int c = 0; c < (HH + 15) / 16; ++c)
         bits[c] = (A.dropout && ok) ? drop16_bits(uint64_t(A.first_index + b0 + s), (hf * HH) / 16 + c, 1, A.drop_seed, A.drop_epoch) : 0xFFFFu;
       const int bit0 = (hf * HH) & 15;
-      float hv1[HH];
 #pragma unroll
       for (int fl = 0; fl < HH; ++fl) hv1[fl] = ok ? __ldg(A.h1 + int64_t(hf * HH + fl) * A.B + b0 + s) : 0.f;
 #pragma unroll
@@ -747,7 +750,7 @@ __global__ void __launch_bounds__(NT) tc_bwd2(const Args A, const float* __restr
         *reinterpret_cast<float4*>(Xm + mn_off16(TS, s, (hf * HH) / 4 + f4)) = make_float4(v[0], v[1], v[2], v[3]);
       }
     }
-    stage_dz_tiles<H2, ACT>(Zk, Zm, A.h2, A.dy2, mean2, rstd2, gam2, sdy, sdyx, A.B, b0, valid);
+    dz_store<H2, ACT>(Zk, Zm, hv2, dv2, mean2, rstd2, gam2, sdy, sdyx, valid);
     NTC_OPERANDS_READY();
     if (t == 0) {
       issue_gemm<128, H1, 0, 0>(tmem, tc::smem_u32(Zk), TS, tc::smem_u32(Ws), H1, H2, false);              // dd1
@@ -814,8 +817,7 @@ __global__ void __launch_bounds__(NT) tc_bwd2(const Args A, const float* __restr
 #pragma unroll
     for (int j = 0; j < HC; ++j) {                          // second pass through the same staging tile: dd1 * xhat1
       const int f = c0 + j;
-      const float hv = es < valid ? __ldg(A.h1 + int64_t(f) * A.B + b0 + es) : 0.f;
-      Ds[f * SP + es] = dd[j] * (hv - mean1[f]) * rstd1[f];
+      Ds[f * SP + es] = dd[j] * (hv1[j] - mean1[f]) * rstd1[f];      // es == s, c0 == hf * HH: the h1 values loaded for d1
     }
     __syncthreads();
     {
