@@ -456,8 +456,8 @@ def product_arm(args):
                     "gpu_launches": e2e_launches,
                     "note": ("BPRNet.train_steps_from_host: per step one cudaMemcpyAsync H2D of the step's user + positive "
                              "ids (128 KiB block of the pinned batch-major host array; copy stream, ring of staging "
-                             "slots); steps run in cooperative launches of 16 (Philox negatives drawn in-kernel, fused "
-                             "step, Adam); the 16 step losses of a launch return in one cudaMemcpyAsync D2H; one host "
+                             "slots); steps run in cooperative launches of 2, 4, 8, then 16 steps (Philox negatives drawn "
+                             "in-kernel, fused step, Adam); the step losses of a launch return in one cudaMemcpyAsync D2H; one host "
                              "sync per K steps" + ("" if world == 1 else "; every rank feeds its own batches, the launches are the "
                                                    "data-parallel cooperative kernel")) if (world == 1 or net.peer is not None) else
                             "per step: H2D ids, Philox negatives, fused fwd/bwd, NCCL all-reduce, Adam, loss D2H"},
