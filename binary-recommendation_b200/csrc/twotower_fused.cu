@@ -13,6 +13,11 @@
 //   ---- grid barrier ----
 //   phase G  (4T CTAs: tower x row block x {rows, weights})   de = dz W^T -> row-contiguous REDs into the table
 //                                           accumulators;  dW += e^T dz, db += column sums of dz
+//   ---- grid barrier ----                  (brk_twotower_train_step only)
+//   phase O  (all CTAs)                     Keras Adagrad on the Dense blocks and on the rows this batch touched
+//
+// Operand loads that do not depend on a barrier (the MN-major re-staging of q_i / c_j, phase G's Dense kernel and
+// re-gathered embedding rows) are issued in front of it and land while the grid waits.
 //
 // All six products are tcgen05.mma kind::tf32 (operands = fp32 bits truncated by the tensor core, fp32 accumulation in
 // TMEM) on 128 x 128 tiles staged by cp.async in the swizzle of the view that reads them (tc_tiles.cuh); no operand is
