@@ -355,24 +355,40 @@ def product_arm(args):
         # one C call enqueues K x (H2D ids, sampler, fused step, Adam, loss D2H): BPRNet.train_steps_from_host
         # host input in the loader's batch-major layout [n_batches, 2, BATCH] (pinned): one H2D per step
         packed = BPRNet.pack_host_batches(users[:n_batches * BATCH], items[:n_batches * BATCH], BATCH)
-        net.train_steps_from_host(packed, None, order[:W], BATCH, 7, 1, hloss[:W])
+        # warm-up = one untimed pass over the SAME K host batches (what every epoch after the first sees): the first DMA out of a
+        # page-locked host page pays its address translation (a first 20-step call measured 513 us, every later one 380-396:
+        # profiles/e2e_k20.py), and all launch shapes of the chunk plan have run once
+        # -- two passes when the call is short: the second 20-step call still measured 440 us against 380-395 from the third on
+        hwarm = torch.empty(K, dtype=torch.float32).pin_memory()
+        for _ in range(2 if K <= 64 else 1):
+            net.train_steps_from_host(packed, None, order, BATCH, 7, 1, hwarm)
         barrier()
+        # host clock from before the call to after the synchronize that follows it (no CUDA events inside: two event records are
+        # 25 us of a 400 us region, and the host clock is the more inclusive measure anyway)
         t0 = time.perf_counter()
-        e0.record()
         net.train_steps_from_host(packed, None, order, BATCH, 7, 1, hloss[W:W + K])
-        e1.record()
         barrier()
         e2e_wall = time.perf_counter() - t0
+        e2e_events_ms = 0.0
+        if os.environ.get("BRK_BENCH_E2E_DEBUG"):
+            ws = []
+            for _ in range(6):
+                barrier(); _t = time.perf_counter()
+                net.train_steps_from_host(packed, None, order, BATCH, 7, 1, hloss[W:W + K])
+                barrier(); ws.append(round(1e6 * (time.perf_counter() - _t)))
+            print(f"[e2e debug] timed shot {1e6 * e2e_wall:.0f} us; repeats {ws}", file=sys.stderr)
         e2e_launches, _k, _c = 0, 0, 2                     # one cooperative launch per chunk: 2, 4, 8, then 16 steps each
         while _k < K:
             e2e_launches += 1; _k += _c; _c = min(2 * _c, 16)
         if world == 1:
             # zero-copy variant: ids stay in pinned host memory, ONE launch, the kernel pulls them over PCIe itself
-            net.train_steps_mapped(hu, hp, order[:W], BATCH, 7, 1, hloss[:W])
+            for _ in range(2 if K <= 64 else 1):
+                net.train_steps_mapped(hu, hp, order, BATCH, 7, 1, hwarm)
             barrier()
-            e2.record(); net.train_steps_mapped(hu, hp, order, BATCH, 7, 1, hloss[W:W + K]); e3.record()
+            _t = time.perf_counter()
+            net.train_steps_mapped(hu, hp, order, BATCH, 7, 1, hloss[W:W + K])
             barrier()
-            mapped_ms = e2.elapsed_time(e3)
+            mapped_ms = 1e3 * (time.perf_counter() - _t)          # host clock, as for the copy leg
     else:
         for k in range(W):
             e2e_step(k)
@@ -385,7 +401,8 @@ def product_arm(args):
         barrier()
         e2e_launches = 3 * K
         e2e_wall = time.perf_counter() - t0
-    e2e_ms = max(e0.elapsed_time(e1), 1e3 * e2e_wall)
+        e2e_events_ms = e0.elapsed_time(e1)
+    e2e_ms = max(e2e_events_ms, 1e3 * e2e_wall)
     clocks = sampler.stop()
     assert np.isfinite(hloss[W:W + K].numpy()).all()
     peaks, peak_src = load_peaks()
@@ -670,13 +687,14 @@ def neumf_block(dev, peaks, which):
     nh = min(nb, 64)
     packed = NeuMFNet.pack_host_batches(ds.u[:nh * B].cpu().numpy(), ds.i[:nh * B].cpu().numpy(), ds.y[:nh * B].cpu().numpy(), B)
     order = np.arange(K) % nh
-    net.train_steps_from_host(packed, order[:W])
+    for _ in range(2 if K <= 64 else 1):                        # warm-up: untimed passes over the same host batches (see the BPR e2e leg)
+        net.train_steps_from_host(packed, order)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    e0.record(); hl = net.train_steps_from_host(packed, order); e1.record()
+    hl = net.train_steps_from_host(packed, order)
     torch.cuda.synchronize()
-    e2e = max(e0.elapsed_time(e1) * 1e-3, time.perf_counter() - t0) / K
+    e2e = (time.perf_counter() - t0) / K                        # host clock around the call and the synchronize after it
     assert np.isfinite(hl.numpy()).all()
     n_tab = (U + I) * (32 + emf)
     n_dense = net.dense.w.numel()

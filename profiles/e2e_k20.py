@@ -24,7 +24,23 @@ for K in (20, 600):
             t0 = time.perf_counter(); e0.record(); fn(order, hl[W:W + K]); e1.record()
             t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
             rows.append((1e6 * (t1 - t0), 1e3 * e0.elapsed_time(e1), 1e6 * (t2 - t0)))
+        print(f"   walls in call order (us): {[round(r[2]) for r in rows]}")
         rows.sort(key=lambda r: r[2])
         enq, devt, wall = rows[len(rows) // 2]
         print(f"K={K:3d} {tag}: enqueue {enq:7.1f} us  device {devt:7.1f} us  wall {wall:7.1f} us  -> {K * B / wall:.0f} M interactions/s "
               f"({wall / K:.2f} us/step)", flush=True)
+# the same 20-step copy call as isolated single shots (13 ms of idle in front of each, as in bench.py where one shot is timed),
+# without and with bench.py's NVML clock sampler thread (a sample every 50 ms)
+import bench
+K = 20; order = [k % nb for k in range(K)]; hl = torch.empty(K + W, dtype=torch.float32).pin_memory()
+for tag in ("no sampler", "NVML sampler"):
+    smp = None
+    if tag != "no sampler":
+        smp = bench.ClockSampler(0); smp.start(); time.sleep(0.2)
+    rows = []
+    for rep in range(60):
+        torch.cuda.synchronize(); time.sleep(0.013)
+        t0 = time.perf_counter(); net.train_steps_from_host(packed, None, order, B, 7, 1, hl[W:W + K]); torch.cuda.synchronize(); t2 = time.perf_counter()
+        rows.append(round(1e6 * (t2 - t0)))
+    srt = sorted(rows)
+    print(f"isolated shots, {tag}: median {srt[30]} us, p10 {srt[6]}, p90 {srt[54]}, first five {rows[:5]}", smp.stop() if smp else "")
