@@ -28,6 +28,7 @@ struct brk_ctx {
   float*        tt_part;
   size_t        tt_part_floats;
   unsigned int* tt_bar;
+  unsigned int* bpr_bar;      // bpr_steps_coop: grid-barrier words {count, error, base}
   // any-width NeuMF path (csrc/neumf_generic.cu): feature-major intermediates
   float*        neumf_gen;
   size_t        neumf_gen_floats;

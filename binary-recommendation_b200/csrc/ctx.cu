@@ -37,6 +37,8 @@ extern "C" int brk_create(brk_ctx** out, int device) {
   BRK_CUDA(cudaMemset(c->tickets, 0, BRK_TICKETS * sizeof(unsigned int)));
   BRK_CUDA(cudaMalloc(&c->tt_bar, 4 * sizeof(unsigned int)));
   BRK_CUDA(cudaMemset(c->tt_bar, 0, 4 * sizeof(unsigned int)));
+  BRK_CUDA(cudaMalloc(&c->bpr_bar, 4 * sizeof(unsigned int)));
+  BRK_CUDA(cudaMemset(c->bpr_bar, 0, 4 * sizeof(unsigned int)));
   c->scratch = nullptr;
   c->scratch_bytes = 0;
   for (int j = 0; j < BRK_FORK_STREAMS; ++j) {
@@ -76,6 +78,7 @@ extern "C" int brk_destroy(brk_ctx* c) {
   if (c->neumf_gen) cudaFree(c->neumf_gen);
   if (c->tt_part) cudaFree(c->tt_part);
   if (c->tt_bar) cudaFree(c->tt_bar);
+  if (c->bpr_bar) cudaFree(c->bpr_bar);
   for (int j = 0; j < BRK_FORK_STREAMS; ++j)
     if (c->fork_stream[j]) { cudaStreamDestroy(c->fork_stream[j]); cudaEventDestroy(c->ev_fork[j]); cudaEventDestroy(c->ev_join[j]); }
   if (c->copy_ready) {
