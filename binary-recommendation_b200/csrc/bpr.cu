@@ -329,6 +329,27 @@ __global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParam
     }
     __syncthreads();
   };
+  // Data parallel: in front of a cross-GPU flag exchange only block 0 has to know that every local block has arrived (it is
+  // the one that tells the peers); the other blocks go straight on to poll the flags -- their own rank's flag among them,
+  // which block 0 posts after this collection -- so the second half of a full barrier (everybody spinning on the counter)
+  // is not paid twice per step.
+  auto gcollect = [&]() {
+    if (P.bar == nullptr) { grid.sync(); return; }
+    __syncthreads();
+    bar_target += gridDim.x;
+    if (threadIdx.x == 0) {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.bar) : "memory");
+      if (blockIdx.x == 0) {
+        const long long t0 = clock64();
+        unsigned int v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.bar) : "memory");
+          if (clock64() - t0 > 8000000000LL) { atomicExch(P.bar + 1, 1u); __trap(); }
+        } while (int(v - bar_target) < 0);
+      }
+    }
+    if (blockIdx.x == 0) __syncthreads();
+  };
   __shared__ double red[32];
   const bool sample = P.n == nullptr;
   const int d4 = P.user.d >> 2;
@@ -423,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParam
     }
     const double part = block_sum_double(double(loss_local), red);
     if (threadIdx.x == 0) atomicAdd(P.loss_acc + (s & 1), part);
-    gsync();
+    if (P.world > 1) gcollect(); else gsync();
     coop_stamp(P, s, 1);
     // ---- phase 2: exact Keras Adam over every element of both tables; zero the accumulators.  In sampling
     //      mode the first two warps of each CTA stage step s+1 instead (ids + negatives) ----
@@ -486,9 +507,9 @@ __global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParam
       }
       coop_stamp(P, s, 3);
       __threadfence();
-      gsync();
+      gcollect();
       coop_stamp(P, s, 4);
-      const bool deadG = *reinterpret_cast<volatile uint32_t*>(P.dp_sync + 4) != 0u;   // uniform: read after the grid barrier
+      const bool deadG = *reinterpret_cast<volatile uint32_t*>(P.dp_sync + 4) != 0u;   // sticky error word of an earlier time-out
       if (!deadG && blockIdx.x == 0 && threadIdx.x < G) {       // barrier B: every rank's slice is final, reads of my g are done
         __threadfence_system();
         coop_st_release_sys(P.peer_flags[threadIdx.x] + G + me, ep);
@@ -503,6 +524,8 @@ __global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParam
         float4* w_loc = reinterpret_cast<float4*>(P.peer_w[me]);
         const int64_t lo = P.arena_n4 * me / G, hi = P.arena_n4 * (me + 1) / G;
         const int64_t others = P.arena_n4 - (hi - lo);
+        float4* g_me = reinterpret_cast<float4*>(P.peer_g[me]);             // the zeroing stores go first: they do not wait for
+        for (int64_t i = tid; i < P.arena_n4; i += nthr) g_me[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // the NVLink round trip below
         for (int64_t j = tid; j < others; j += nthr) {
           const int64_t i = j < lo ? j : j + (hi - lo);          // skip my own slice
           int owner = int((i * G) / P.arena_n4);
@@ -510,8 +533,6 @@ __global__ void __launch_bounds__(kThreads, 4) bpr_steps_coop(const BprCoopParam
           while (P.arena_n4 * (owner + 1) / G <= i) ++owner;
           w_loc[i] = __ldcg(reinterpret_cast<const float4*>(P.peer_w[owner]) + i);
         }
-        float4* g_me = reinterpret_cast<float4*>(P.peer_g[me]);
-        for (int64_t i = tid; i < P.arena_n4; i += nthr) g_me[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     if (tid == nthr - 1) {
