@@ -22,7 +22,7 @@ buf = (ctypes.c_uint64 * (K * 8))()
 lib = N.lib(); lib.brk_coop_trace_read.argtypes = [ctypes.c_void_p, ctypes.c_int32]
 assert lib.brk_coop_trace_read(buf, K * 8) == 0
 a = np.frombuffer(buf, dtype=np.uint64).reshape(K, 8).astype(np.int64)[20:]
-names = ["phase1 (fwd/bwd + grid.sync)", "barrier A (+sync)", "reduce+Adam+broadcast", "fence.sys + grid.sync", "barrier B (+sync)", "zero g + loss + grid.sync"]
+names = ["phase1 (fwd/bwd + block 0 collects the local arrivals)", "barrier A (flags over NVLink)", "reduce + Adam of my slice", "block 0 collects the local arrivals", "barrier B (flags over NVLink)", "zero g + pull + loss + grid barrier"]
 d = np.diff(a[:, :7], axis=1)
 for r in range(world):
     if r == rank:
