@@ -423,7 +423,7 @@ template <class S>
 __global__ void __launch_bounds__(NT, (S::smem <= 110 * 1024) ? 2 : 1) fused_step(const Args A, const Extra X) {
   using AC = Acc<S::H1, S::H2>;
   constexpr int E = S::E, EMF = S::EMF, H1 = S::H1, H2 = S::H2, H3 = S::H3, ACT = S::ACT, N3 = S::N3, HM = S::HM;
-  constexpr int K0 = S::K0, HC1 = S::HC1, HC2 = S::HC2, PH = S::PH;
+  constexpr int K0 = S::K0, HC1 = S::HC1, HC2 = S::HC2;
   constexpr bool BN = S::BN != 0, HAD = S::HAD != 0;
   
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(nfz_smem_raw) + 1023) & ~uintptr_t(1023));
